@@ -1,0 +1,101 @@
+/* rxb200.h — C ABI of the B200-native ReaxFF force-and-charge path (librxb200.so).
+ *
+ * Drop-in boundary for the LAMMPS add-on styles of run-towards-the-future/SW_REAXFF.  In the reference every
+ * accelerator call is an extern "C" void function taking one plain-C "param pack" (SURVEY.md §8b); the host owns all
+ * buffers and the CPEs DMA them per call.  Here the device owns the state (atoms, lists, bonds, charges stay in HBM
+ * across timesteps), so the entry points are coarser, one per LAMMPS style hook, and they return a status instead of
+ * calling MPI_Abort:
+ *      0  success        < 0  fatal, text via rxb_last_error()
+ * All pointers are HOST pointers unless stated otherwise; arrays are C-contiguous, x/f are [nall][3] doubles as
+ * LAMMPS' atom->x / atom->f, types are LAMMPS types (1-based), tags are 32-bit (LAMMPS_SMALLBIG).
+ * One host thread per handle; a handle is bound to one CUDA device.  Not re-entrant per handle.
+ */
+#ifndef RXB200_H
+#define RXB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rxb_handle rxb_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------- */
+int rxb_create(int cuda_device, rxb_handle** out);
+void rxb_destroy(rxb_handle* h);
+const char* rxb_last_error(void);
+
+/* ---- pair_style reax/c <control|NULL> [lgvdw yes/no] [enobonds yes/no]
+ *      replaces PairReaxCSunway::settings, pair_reaxc_sunway.cpp:202-290 (Read_Control_File, reaxc_control_sunway.cpp:34) */
+int rxb_pair_settings(rxb_handle* h, const char* control_file, int lgvdw, int enobonds);
+
+/* ---- pair_coeff * * <ffield> <element per LAMMPS type | NULL>
+ *      replaces PairReaxCSunway::coeff, pair_reaxc_sunway.cpp:294-362 (Read_Force_Field, reaxc_ffield_sunway.cpp:35) */
+int rxb_pair_coeff(rxb_handle* h, const char* ffield_file, int ntypes, const char* const* elements);
+
+/* ---- Pair::extract("chi"|"eta"|"gamma") : per LAMMPS type, out[0..ntypes] (index 0 unused)
+ *      replaces PairReaxCSunway::extract, pair_reaxc_sunway.cpp:1106-1128 */
+int rxb_pair_extract(rxb_handle* h, const char* name, double* out, int ntypes);
+
+/* ---- fix qeq/reax <nevery> <swa> <swb> <tol> reax/c   (fix_qeq_reax_sunway.cpp:76-99); neighbor <skin> bin */
+int rxb_fix_qeq(rxb_handle* h, double swa, double swb, double tolerance, int max_iter);
+int rxb_neighbor_skin(rxb_handle* h, double skin);
+
+/* canonical flat dump of every parsed parameter (parity tests); returns the count, writes min(count, cap) values */
+long rxb_params_dump(rxb_handle* h, double* out, long cap);
+
+/* ---- atoms: local [0,nlocal) then ghost [nlocal,nlocal+nghost)
+ *      replaces write_reax_atoms_and_pack, pair_reaxc_sw64.c:114-190.
+ *      ghost_owner[g] = local index whose image ghost g is (single-rank periodic images), or NULL to derive it from
+ *      tags (atom->map); -1 = owned by another rank (the caller's comm layer must then refresh ghost values). */
+int rxb_set_atoms(rxb_handle* h, int nlocal, int nghost, const double* x, const int* type, const int* tag,
+                  const double* q, const int* ghost_owner);
+int rxb_set_positions(rxb_handle* h, const double* x);  /* every step, after forward_comm */
+int rxb_set_charges(rxb_handle* h, const double* q);
+
+/* ---- neighbour build (every reneighbouring step)
+ *      replaces NPairFullBin{Atomonly,Ghost}Sunway::build, npair_full_bin_atomonly_sunway.cpp:39-198,
+ *      npair_full_bin_ghost_sw5.c:80-228: full list r <= cutmax+skin for local rows, plus the (bond_cut+skin) rows
+ *      the bond-order kernels need for ghost atoms. */
+int rxb_neigh_build(rxb_handle* h);
+
+/* ---- FixQEqReaxSunway::pre_force (fix_qeq_reax_sunway.cpp:539-600): H build + dual-RHS pipelined CG + q.
+ *      matvecs2[0..1] = iterations of the s and t solves (the reference's matvecs_s, matvecs_t). */
+int rxb_qeq_pre_force(rxb_handle* h, int* matvecs2);
+int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist); /* [nlocal][5] */
+int rxb_qeq_get_history(rxb_handle* h, double* s_hist, double* t_hist);
+int rxb_get_charges(rxb_handle* h, double* q); /* nall */
+
+/* ---- PairReaxCSunway::compute (pair_reaxc_sunway.cpp:541-793)
+ *      f_out   : [nall][3] forces to ADD INTO atom->f by the caller (ghost rows included: caller reverse_comm's), or NULL
+ *      pvector : 14 per-term energies in the reference's order (pair_reaxc_sunway.cpp:657-670), or NULL
+ *      eng2    : eng_vdwl, eng_coul, or NULL ; virial6 : xx,yy,zz,xy,xz,yz, or NULL */
+int rxb_pair_compute(rxb_handle* h, int eflag, int vflag, double* f_out, double* pvector, double* eng2, double* virial6);
+
+/* ---- device-resident run: fix nve (fix_nve_sw64.c:25-170) + periodic ghosts + the calls above, nothing leaves HBM.
+ *      box6 = xprd,yprd,zprd,xy,xz,yz ; mass[0..ntypes] indexed by LAMMPS type */
+int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x, const double* v, const int* type,
+                 const int* tag, const double* mass, int ntypes, double dt, int reneigh_every, int thermo_every,
+                 int qeq_on);
+int rxb_md_run(rxb_handle* h, int nsteps);
+int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q); /* local atoms, any may be NULL */
+int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke);
+
+/* ---- introspection (tests, fix reax/c/bonds, fix reax/c/species) ---- */
+/* counts[0..7] = nlocal, nall, verlet nnz, bond-candidate nnz, directed bonds, far nnz(sum), kernel launches, qeq iterations */
+int rxb_get_counts(rxb_handle* h, long long* counts8);
+int rxb_get_neighbors(rxb_handle* h, int which /*0 verlet, 1 bond candidates*/, long long* off, int* idx);
+/* bonds, CSR by atom (row = b_start[i] .. +b_cnt[i], ascending neighbour index), 31 doubles per directed bond:
+ * d,dvec3,BO,BO_s,BO_pi,BO_pi2,dBOp3,dln_BOp_pi3,dln_BOp_pi2_3,C1..3dbo,C1..4dbopi,C1..4dbopi2,Cdbo,Cdbopi,Cdbopi2 */
+int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, double* fields31);
+/* per atom 16 doubles: total_bo,Delta_boc,Deltap,Deltap_boc,Delta,Delta_e,Delta_val,vlpex,nlp,Delta_lp,Clp,dDelta_lp,
+ * nlp_temp,Delta_lp_temp,dDelta_lp_temp,CdDelta */
+int rxb_get_workspace(rxb_handle* h, double* w16);
+/* far list == H pattern: num[nlocal], and for row i the entries off_verlet[i] .. +num[i] of idx/val */
+int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val);
+/* profile[0..8] = ms per phase (neigh, qeq H, qeq CG, bond list, BO, bonded, nonbonded, dBond, other) when enabled */
+int rxb_profile(rxb_handle* h, int enable, double* ms9);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,216 @@
+"""ctypes binding of include/rxb200.h (one method per C entry point, same names minus the rxb_ prefix)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librxb200.so")
+DATA_DIR = os.path.join(HERE, "data")
+
+SYMBOLS = [
+    "rxb_create", "rxb_destroy", "rxb_last_error", "rxb_pair_settings", "rxb_pair_coeff", "rxb_pair_extract",
+    "rxb_fix_qeq", "rxb_neighbor_skin", "rxb_params_dump", "rxb_set_atoms", "rxb_set_positions", "rxb_set_charges",
+    "rxb_neigh_build", "rxb_qeq_pre_force", "rxb_qeq_set_history", "rxb_qeq_get_history", "rxb_get_charges",
+    "rxb_pair_compute", "rxb_md_setup", "rxb_md_run", "rxb_md_get", "rxb_md_thermo", "rxb_get_counts",
+    "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile",
+]
+
+E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
+
+
+class RxbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """Load librxb200.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RxbError(f"{path} is missing: build it first (__graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(path)
+    lib.rxb_last_error.restype = C.c_char_p
+    lib.rxb_params_dump.restype = C.c_long
+    _lib = lib
+    return lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Rxb:
+    """One handle == one GPU-resident ReaxFF system."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._chk(self.lib.rxb_create(int(device), C.byref(h)))
+        self.h = h
+        self.nlocal = self.nall = 0
+        self.ntypes = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RxbError(self.lib.rxb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rxb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----
+    def pair_settings(self, control_file, lgvdw=False, enobonds=True):
+        self._chk(self.lib.rxb_pair_settings(self.h, control_file.encode() if control_file else None, int(lgvdw), int(enobonds)))
+
+    def pair_coeff(self, ffield, elements):
+        arr = (C.c_char_p * len(elements))(*[e.encode() for e in elements])
+        self.ntypes = len(elements)
+        self._chk(self.lib.rxb_pair_coeff(self.h, ffield.encode(), len(elements), arr))
+
+    def pair_extract(self, name):
+        out = np.zeros(self.ntypes + 1)
+        self._chk(self.lib.rxb_pair_extract(self.h, name.encode(), _p(out), self.ntypes))
+        return out
+
+    def fix_qeq(self, swa=0.0, swb=10.0, tol=1e-6, max_iter=200):
+        self._chk(self.lib.rxb_fix_qeq(self.h, C.c_double(swa), C.c_double(swb), C.c_double(tol), int(max_iter)))
+
+    def neighbor_skin(self, skin):
+        self._chk(self.lib.rxb_neighbor_skin(self.h, C.c_double(skin)))
+
+    def params_dump(self):
+        n = self.lib.rxb_params_dump(self.h, None, C.c_long(0))
+        out = np.zeros(n)
+        self.lib.rxb_params_dump(self.h, _p(out), C.c_long(n))
+        return out
+
+    # ---- atoms / lists ----
+    def set_atoms(self, nlocal, x, types, tags, q=None, ghost_owner=None):
+        x = _f(x); types = _i(types); tags = _i(tags)
+        nall = len(types)
+        q = _f(q) if q is not None else np.zeros(nall)
+        go = _i(ghost_owner) if ghost_owner is not None else None
+        self.nlocal, self.nall = int(nlocal), int(nall)
+        self._chk(self.lib.rxb_set_atoms(self.h, int(nlocal), int(nall - nlocal), _p(x), _p(types), _p(tags), _p(q), _p(go)))
+
+    def set_positions(self, x):
+        x = _f(x)
+        self._chk(self.lib.rxb_set_positions(self.h, _p(x)))
+
+    def set_charges(self, q):
+        q = _f(q)
+        self._chk(self.lib.rxb_set_charges(self.h, _p(q)))
+
+    def neigh_build(self):
+        self._chk(self.lib.rxb_neigh_build(self.h))
+
+    # ---- QEq ----
+    def qeq_pre_force(self):
+        mv = np.zeros(2, dtype=np.int32)
+        self._chk(self.lib.rxb_qeq_pre_force(self.h, _p(mv)))
+        return int(mv[0]), int(mv[1])
+
+    def qeq_set_history(self, s_hist, t_hist):
+        s = _f(s_hist); t = _f(t_hist)
+        self._chk(self.lib.rxb_qeq_set_history(self.h, _p(s), _p(t)))
+
+    def qeq_get_history(self):
+        s = np.zeros((self.nlocal, 5)); t = np.zeros((self.nlocal, 5))
+        self._chk(self.lib.rxb_qeq_get_history(self.h, _p(s), _p(t)))
+        return s, t
+
+    def get_charges(self):
+        q = np.zeros(self.nall)
+        self._chk(self.lib.rxb_get_charges(self.h, _p(q)))
+        return q
+
+    # ---- pair compute ----
+    def pair_compute(self, eflag=True, vflag=True, want_forces=True, f_out=None):
+        f = f_out if f_out is not None else (np.zeros((self.nall, 3)) if want_forces else None)
+        pv = np.zeros(14); eng = np.zeros(2); vir = np.zeros(6)
+        self._chk(self.lib.rxb_pair_compute(self.h, int(eflag), int(vflag), _p(f), _p(pv), _p(eng), _p(vir)))
+        return dict(f=f, pvector=pv, eng=eng, virial=vir)
+
+    # ---- resident MD ----
+    def md_setup(self, box6, x, v, types, tags, mass, dt=0.0625, every=5, thermo=5, qeq=True):
+        x = _f(x); v = _f(v); types = _i(types); tags = _i(tags); mass = _f(mass); box6 = _f(box6)
+        self.nlocal = len(types)
+        self._chk(self.lib.rxb_md_setup(self.h, _p(box6), len(types), _p(x), _p(v), _p(types), _p(tags), _p(mass),
+                                        len(mass) - 1, C.c_double(dt), int(every), int(thermo), int(qeq)))
+        self.nall = int(self.counts()[1])
+
+    def md_run(self, nsteps):
+        self._chk(self.lib.rxb_md_run(self.h, int(nsteps)))
+        self.nall = int(self.counts()[1])
+
+    def md_get(self):
+        n = self.nlocal
+        x = np.zeros((n, 3)); v = np.zeros((n, 3)); f = np.zeros((n, 3)); q = np.zeros(n)
+        self._chk(self.lib.rxb_md_get(self.h, _p(x), _p(v), _p(f), _p(q)))
+        return dict(x=x, v=v, f=f, q=q)
+
+    def md_thermo(self):
+        pv = np.zeros(14); pe = C.c_double(); ke = C.c_double()
+        self._chk(self.lib.rxb_md_thermo(self.h, _p(pv), C.byref(pe), C.byref(ke)))
+        return dict(pvector=pv, pe=pe.value, ke=ke.value)
+
+    # ---- introspection ----
+    def counts(self):
+        c = np.zeros(8, dtype=np.int64)
+        self._chk(self.lib.rxb_get_counts(self.h, _p(c)))
+        return c
+
+    def neighbors(self, which=0):
+        c = self.counts()
+        nrows = int(c[0]) if which == 0 else int(c[1])
+        nnz = int(c[2]) if which == 0 else int(c[3])
+        off = np.zeros(nrows + 1, dtype=np.int64); idx = np.zeros(max(nnz, 1), dtype=np.int32)
+        self._chk(self.lib.rxb_get_neighbors(self.h, which, _p(off), _p(idx)))
+        return off, idx[:nnz]
+
+    def bonds(self):
+        c = self.counts()
+        N, nb = int(c[1]), int(c[4])
+        bs = np.zeros(N, dtype=np.int32); bc = np.zeros(N, dtype=np.int32)
+        nbr = np.zeros(max(nb, 1), dtype=np.int32); sym = np.zeros(max(nb, 1), dtype=np.int32)
+        fld = np.zeros((max(nb, 1), 31))
+        self._chk(self.lib.rxb_get_bonds(self.h, _p(bs), _p(bc), _p(nbr), _p(sym), _p(fld)))
+        return bs, bc, nbr[:nb], sym[:nb], fld[:nb]
+
+    def workspace(self):
+        N = int(self.counts()[1])
+        w = np.zeros((N, 16))
+        self._chk(self.lib.rxb_get_workspace(self.h, _p(w)))
+        return w
+
+    def far(self):
+        c = self.counts()
+        n, nnz = int(c[0]), int(c[2])
+        num = np.zeros(n, dtype=np.int32); idx = np.zeros(max(nnz, 1), dtype=np.int32); val = np.zeros(max(nnz, 1))
+        self._chk(self.lib.rxb_get_far(self.h, _p(num), _p(idx), _p(val)))
+        return num, idx, val
+
+    def profile(self, enable=None):
+        ms = np.zeros(9)
+        self._chk(self.lib.rxb_profile(self.h, -1 if enable is None else int(enable), _p(ms)))
+        return ms

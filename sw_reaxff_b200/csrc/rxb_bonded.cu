@@ -1,0 +1,714 @@
+// Bonded energy terms and the dE/dBO chain rule: all enumerated from the device bond CSR, one warp per centre atom,
+// grid-stride persistent blocks, fp64 atomics for the scatters.
+//
+//   K-multi : lone pair / over- / under-coordination + bond energy + e_pol
+//             /root/reference/reaxc_multi_body_sw64.c:21-333 (runs SERIALLY on the MPE in the reference)
+//   K-hb    : hydrogen bonds            /root/reference/reaxc_hydrogen_bonds_sunway.cpp:310-436 (== reaxc_hydrogen_bonds_cpe.h)
+//   K-vt    : valence angle + torsion + conjugation, no stored three-body list
+//             /root/reference/reaxc_torsion_angles_sunway.cpp:652-1312 (== reaxc_torsion_angles_cpe.h:1-768)
+//             Calculate_Theta / dCos_Theta  reaxc_valence_angles_sunway.cpp:50-84, Calculate_Omega reaxc_torsion_angles_sunway.cpp:44-125
+//   K-dbond : Add_All_dBond_to_Forces_C, no-branch directed form /root/reference/reaxc_forces_sw64.c:500-587
+// The reference serialises scatter conflicts with locked software write caches (SWCACHE_UPDATE); here the per-bond
+// coefficient sums that every angle of a centre adds to ALL of its bonds are reduced in the warp first, and only
+// what genuinely leaves the warp's rows goes through atomicAdd(double).
+// Roofline: fp64-compute bound (acos/atan2/exp/pow per angle and per torsion), SURVEY.md §8d.
+#include "rxb_system.h"
+
+namespace rxb {
+namespace {
+
+constexpr double kConstPI = 3.14159265;  // reaxc_defs_sunway.h:55 (8 digits on purpose)
+constexpr double kKcalToEv = 23.02;      // KCALpMOL_to_EV
+constexpr double kHbThreshold = 1e-2;    // HB_THRESHOLD
+constexpr double kMinSine = 1e-10;       // MIN_SINE
+constexpr int kWarps = 8;
+constexpr int kBlocks = 148 * 4;
+
+__device__ __forceinline__ double sqr(double a) { return a * a; }
+__device__ __forceinline__ double deg2rad(double a) { return a * kConstPI / 180.0; }
+
+__device__ __forceinline__ void fadd3(double* f, int i, double c, double x, double y, double z) {
+  atomicAdd(&f[3 * i], c * x);
+  atomicAdd(&f[3 * i + 1], c * y);
+  atomicAdd(&f[3 * i + 2], c * z);
+}
+
+// tag-ordered half selection with z,y,x tie-break (reaxc_multi_body_sw64.c:256-268)
+__device__ __forceinline__ bool half_select(int tag_i, int tag_j, const double4& xi, const double4& xj) {
+  if (tag_i > tag_j) return false;
+  if (tag_i == tag_j) {
+    if (xj.z < xi.z) return false;
+    if (xj.z == xi.z && xj.y < xi.y) return false;
+    if (xj.z == xi.z && xj.y == xi.y && xj.x < xi.x) return false;
+  }
+  return true;
+}
+
+// commit per-thread partial energies: warp shuffle, then one atomic per block per slot
+template <int K>
+__device__ __forceinline__ void block_commit(double* en, const int (&slots)[K], double (&vals)[K]) {
+  __shared__ double sh[K][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double s = warp_sum(vals[k]);
+    if (lane == 0) sh[k][w] = s;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double s = lane < nw ? sh[k][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0 && s != 0.0) atomicAdd(&en[slots[k]], s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+k_multi(DevView v, DevParams P) {
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double p_lp3 = P.gp[5], p_ovun3 = P.gp[32], p_ovun4 = P.gp[31], p_ovun6 = P.gp[6], p_ovun7 = P.gp[8], p_ovun8 = P.gp[9];
+  const double gp3 = P.gp[3], gp4 = P.gp[4], gp7 = P.gp[7], gp10 = P.gp[10];
+  const int gp37 = (int)P.gp[37];
+  double e_lp = 0, e_ov = 0, e_un = 0, e_bond = 0, e_pol = 0;
+  for (int i = wg; i < v.n; i += nwg) {
+    const int ti = v.type[i];
+    if (ti < 0) continue;
+    const AtomPar& ai = P.atom[ti];
+    const double4 xi = v.xq[i];
+    const int tag_i = v.tag[i];
+    const int start = v.b_start[i], cnt = v.b_cnt[i];
+    const double dfvl = (ai.mass > 21.0) ? 0.0 : 1.0;
+    if (lane == 0) e_pol += kKcalToEv * (ai.chi * xi.w + (ai.eta / 2.) * sqr(xi.w));
+    const double Delta_i = v.Delta[i], Delta_lp_i = v.Delta_lp[i], dDelta_lp_i = v.dDelta_lp[i], Delta_lp_temp_i = v.Delta_lp_temp[i];
+    const double total_bo_i = v.total_bo[i];
+
+    double sum_ovun1 = 0, sum_ovun2 = 0, cdd_i = 0;
+    for (int e = lane; e < cnt; e += 32) {
+      const int p = start + e;
+      const int j = v.b_nbr[p], tj = v.type[j];
+      if (tj < 0) continue;
+      const PairPar& tw = P.pair[ti * P.nt + tj];
+      const double4 bo = v.b_bo[p];
+      sum_ovun1 += tw.p_ovun1 * tw.De_s * bo.x;
+      sum_ovun2 += (v.Delta[j] - dfvl * v.Delta_lp_temp[j]) * (bo.z + bo.w);
+    }
+    sum_ovun1 = warp_sum(sum_ovun1);
+    sum_ovun2 = warp_sum(sum_ovun2);
+
+    const double p_lp2 = ai.p_lp2, p_ovun2 = ai.p_ovun2, p_ovun5 = ai.p_ovun5;
+    const double expvd2 = exp(-75 * Delta_lp_i);
+    const double inv_expvd2 = 1. / (1. + expvd2);
+    const double dElp = p_lp2 * inv_expvd2 + 75 * p_lp2 * Delta_lp_i * expvd2 * sqr(inv_expvd2);
+    const double CElp = dElp * dDelta_lp_i;
+
+    const double exp_ovun1 = p_ovun3 * exp(p_ovun4 * sum_ovun2);
+    const double inv_exp_ovun1 = 1.0 / (1 + exp_ovun1);
+    const double Delta_lpcorr = Delta_i - (dfvl * Delta_lp_temp_i) * inv_exp_ovun1;
+    const double exp_ovun2 = exp(p_ovun2 * Delta_lpcorr);
+    const double inv_exp_ovun2 = 1.0 / (1.0 + exp_ovun2);
+    const double DlpVi = 1.0 / (Delta_lpcorr + ai.valency + 1e-8);
+    const double CEover1 = Delta_lpcorr * DlpVi * inv_exp_ovun2;
+    const double CEover2 = sum_ovun1 * DlpVi * inv_exp_ovun2 * (1.0 - Delta_lpcorr * (DlpVi + p_ovun2 * exp_ovun2 * inv_exp_ovun2));
+    const double CEover3 = CEover2 * (1.0 - dfvl * dDelta_lp_i * inv_exp_ovun1);
+    const double CEover4 = CEover2 * (dfvl * Delta_lp_temp_i) * p_ovun4 * exp_ovun1 * sqr(inv_exp_ovun1);
+    const double exp_ovun2n = 1.0 / exp_ovun2;
+    const double exp_ovun6 = exp(p_ovun6 * Delta_lpcorr);
+    const double exp_ovun8 = p_ovun7 * exp(p_ovun8 * sum_ovun2);
+    const double inv_exp_ovun2n = 1.0 / (1.0 + exp_ovun2n);
+    const double inv_exp_ovun8 = 1.0 / (1.0 + exp_ovun8);
+    double eun = 0.0;
+    const bool active = (cnt > 0) || P.ctl.enobondsflag;
+    if (active) eun = -p_ovun5 * (1.0 - exp_ovun6) * inv_exp_ovun2n * inv_exp_ovun8;
+    const double CEunder1 = inv_exp_ovun2n * (p_ovun5 * p_ovun6 * exp_ovun6 * inv_exp_ovun8 + p_ovun2 * eun * exp_ovun2n);
+    const double CEunder2 = -eun * p_ovun8 * exp_ovun8 * inv_exp_ovun8;
+    const double CEunder3 = CEunder1 * (1.0 - dfvl * dDelta_lp_i * inv_exp_ovun1);
+    const double CEunder4 = CEunder1 * (dfvl * Delta_lp_temp_i) * p_ovun4 * exp_ovun1 * sqr(inv_exp_ovun1) + CEunder2;
+    if (lane == 0) {
+      e_ov += sum_ovun1 * CEover1;
+      cdd_i += CEover3;
+      if (active) {
+        e_un += eun;
+        cdd_i += CEunder3;
+        cdd_i += CElp;
+        e_lp += p_lp2 * Delta_lp_i * inv_expvd2;
+      }
+    }
+
+    const bool c2corr = p_lp3 > 0.001 && ai.is_carbon;
+    for (int e = lane; e < cnt; e += 32) {
+      const int p = start + e;
+      const int j = v.b_nbr[p], tj = v.type[j];
+      if (tj < 0) continue;
+      const AtomPar& aj = P.atom[tj];
+      const PairPar& tw = P.pair[ti * P.nt + tj];
+      const double4 bo = v.b_bo[p];
+      double cdbo = 0, cdbopi = 0, cdbopi2 = 0;
+      if (c2corr && aj.is_carbon) {
+        const double vov3 = bo.x - Delta_i - 0.040 * pow(Delta_i, 4.);
+        if (vov3 > 3.) {
+          e_lp += p_lp3 * sqr(vov3 - 3.0);
+          cdbo += 2. * p_lp3 * (vov3 - 3.);
+          cdd_i += 2. * p_lp3 * (vov3 - 3.) * (-1. - 0.16 * pow(Delta_i, 3.));
+        }
+      }
+      const double Delta_j = v.Delta[j], Dlt_j = v.Delta_lp_temp[j];
+      cdbo += CEover1 * tw.p_ovun1 * tw.De_s;
+      const double ftmp2 = (1.0 - dfvl * v.dDelta_lp[j]) * (bo.z + bo.w);
+      const double dj = Delta_j - dfvl * Dlt_j;
+      double cdd_j = CEover4 * ftmp2;
+      cdbopi += CEover4 * dj; cdbopi2 += CEover4 * dj;
+      cdd_j += CEunder4 * ftmp2;
+      cdbopi += CEunder4 * dj; cdbopi2 += CEunder4 * dj;
+      if (half_select(tag_i, v.tag[j], xi, v.xq[j])) {
+        const double pow_BOs_be2 = (bo.y == 0.0) ? 0.0 : pow(bo.y, tw.p_be2);
+        const double exp_be12 = exp(tw.p_be1 * (1.0 - pow_BOs_be2));
+        const double CEbo = -tw.De_s * exp_be12 * (1.0 - tw.p_be1 * tw.p_be2 * pow_BOs_be2);
+        e_bond += -tw.De_s * bo.y * exp_be12 - tw.De_p * bo.z - tw.De_pp * bo.w;
+        cdbo += CEbo;
+        cdbopi -= (CEbo + tw.De_p);
+        cdbopi2 -= (CEbo + tw.De_pp);
+        if (bo.x >= 1.00) {
+          if (gp37 == 2 || (ai.mass == 12.0000 && aj.mass == 15.9990) || (aj.mass == 12.0000 && ai.mass == 15.9990)) {
+            const double exphu = exp(-gp7 * sqr(bo.x - 2.50));
+            const double exphua1 = exp(-gp3 * (total_bo_i - bo.x));
+            const double exphub1 = exp(-gp3 * (v.total_bo[j] - bo.x));
+            const double exphuov = exp(gp4 * (Delta_i + Delta_j));
+            const double hulpov = 1.0 / (1.0 + 25.0 * exphuov);
+            e_bond += gp10 * exphu * hulpov * (exphua1 + exphub1);
+            cdbo += gp10 * exphu * hulpov * (exphua1 + exphub1) * (gp3 - 2.0 * gp7 * (bo.x - 2.50));
+            cdd_i += -gp10 * exphu * hulpov * (gp3 * exphua1 + 25.0 * gp4 * exphuov * hulpov * (exphua1 + exphub1));
+            cdd_j += -gp10 * exphu * hulpov * (gp3 * exphub1 + 25.0 * gp4 * exphuov * hulpov * (exphua1 + exphub1));
+          }
+        }
+      }
+      // own row: this lane is the only writer of slot p in this kernel
+      v.b_Cdbo[p] += cdbo;
+      v.b_Cdbopi[p] += cdbopi;
+      v.b_Cdbopi2[p] += cdbopi2;
+      if (cdd_j != 0.0) atomicAdd(&v.CdDelta[j], cdd_j);
+    }
+    cdd_i = warp_sum(cdd_i);
+    if (lane == 0 && cdd_i != 0.0) atomicAdd(&v.CdDelta[i], cdd_i);
+  }
+  const int slots[5] = {E_LP, E_OV, E_UN, E_BOND, E_POL};
+  double vals[5] = {e_lp, e_ov, e_un, e_bond, e_pol};
+  block_commit<5>(v.en, slots, vals);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void calc_theta(const double4& a, const double4& b, double& theta, double& cos_theta) {
+  cos_theta = (a.y * b.y + a.z * b.z + a.w * b.w) / (a.x * b.x);
+  if (cos_theta > 1.) cos_theta = 1.0;
+  if (cos_theta < -1.) cos_theta = -1.0;
+  theta = acos(cos_theta);
+}
+// geo = (d, dx, dy, dz); outputs derivative wrt end atom of a ("di"), centre ("dj"), end atom of b ("dk")
+__device__ __forceinline__ void calc_dcos(const double4& a, const double4& b, double* di, double* dj, double* dk) {
+  const double sqr_d_ji = a.x * a.x, sqr_d_jk = b.x * b.x;
+  const double inv_dists = 1.0 / (a.x * b.x);
+  const double inv_dists3 = inv_dists * inv_dists * inv_dists;
+  const double dot = a.y * b.y + a.z * b.z + a.w * b.w;
+  const double Cdot_inv3 = dot * inv_dists3;
+  const double av[3] = {a.y, a.z, a.w}, bv[3] = {b.y, b.z, b.w};
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    di[t] = bv[t] * inv_dists - Cdot_inv3 * sqr_d_jk * av[t];
+    dj[t] = -(bv[t] + av[t]) * inv_dists + Cdot_inv3 * (sqr_d_jk * av[t] + sqr_d_ji * bv[t]);
+    dk[t] = av[t] * inv_dists - Cdot_inv3 * sqr_d_ji * bv[t];
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_hbond(DevView v, DevParams P) {
+  __shared__ int s_hb[kWarps][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double hbond_cut = P.ctl.hbond_cut;
+  double e_hb = 0;
+  if (hbond_cut > 0)
+  for (int j = wg; j < v.n; j += nwg) {
+    const int tj = v.type[j];
+    if (tj < 0 || P.atom[tj].p_hbond != 1) continue;
+    const int start = v.b_start[j], cnt = v.b_cnt[j];
+    // acceptor bonds of this hydrogen
+    int top = 0;
+    for (int e0 = 0; e0 < cnt; e0 += 32) {
+      const int e = e0 + lane;
+      bool ok = false;
+      if (e < cnt) {
+        const int p = start + e;
+        const int ti = v.type[v.b_nbr[p]];
+        ok = ti >= 0 && P.atom[ti].p_hbond == 2 && v.b_bo[p].x >= kHbThreshold;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) { const int slot = top + __popc(m & ((1u << lane) - 1)); if (slot < 32) s_hb[wib][slot] = start + e; }
+      top += __popc(m);
+    }
+    __syncwarp();
+    if (top > 32) { if (lane == 0) atomicOr(v.overflow, 4); top = 32; }
+    if (top == 0) continue;
+    const double4 xj = v.xq[j];
+    const long long fbeg = v.vl_off[j];
+    const int fnum = v.far_num[j];
+    double fjx = 0, fjy = 0, fjz = 0;
+    for (int itr = 0; itr < top; itr++) {
+      const int pi = s_hb[wib][itr];
+      const int i = v.b_nbr[pi];
+      const int ti = v.type[i], tag_i = v.tag[i];
+      const double4 gij = v.b_geo[pi];
+      const double BOij = v.b_bo[pi].x;
+      double fix = 0, fiy = 0, fiz = 0, cd = 0;
+      for (int k0 = 0; k0 < fnum; k0 += 32) {
+        const int kk = k0 + lane;
+        if (kk >= fnum) continue;
+        const int k = v.far_idx[fbeg + kk];
+        const int tk = v.type[k];
+        if (tk < 0 || P.atom[tk].p_hbond != 2) continue;
+        const double4 xk = v.xq[k];
+        const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
+        const double r_jk = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        if (!(r_jk <= hbond_cut)) continue;
+        if (tag_i == v.tag[k]) continue;
+        const HbPar hp = P.hb[(ti * P.nt + tj) * P.nt + tk];
+        if (hp.r0_hb <= 0.0) continue;
+        const double4 gjk = make_double4(r_jk, dx, dy, dz);
+        double theta, cos_theta, di[3], dj[3], dk[3];
+        calc_theta(gij, gjk, theta, cos_theta);
+        calc_dcos(gij, gjk, di, dj, dk);
+        const double sin_theta2 = sin(theta / 2.0);
+        double sin_xhz4 = sqr(sin_theta2);
+        sin_xhz4 *= sin_xhz4;
+        const double cos_xhz1 = (1.0 - cos_theta);
+        const double exp_hb2 = exp(-hp.p_hb2 * BOij);
+        const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
+        const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
+        e_hb += ehb;
+        const double CEhb1 = hp.p_hb1 * hp.p_hb2 * exp_hb2 * exp_hb3 * sin_xhz4;
+        const double CEhb2 = -hp.p_hb1 / 2.0 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
+        const double CEhb3 = -hp.p_hb3 * (-hp.r0_hb / sqr(r_jk) + 1.0 / hp.r0_hb) * ehb;
+        cd += CEhb1;
+        // reference accumulates -force in fCdDelta; f is the true force here
+        fix -= CEhb2 * di[0]; fiy -= CEhb2 * di[1]; fiz -= CEhb2 * di[2];
+        const double c3 = CEhb3 / r_jk;
+        fjx -= CEhb2 * dj[0] - c3 * dx; fjy -= CEhb2 * dj[1] - c3 * dy; fjz -= CEhb2 * dj[2] - c3 * dz;
+        atomicAdd(&v.f[3 * k], -(CEhb2 * dk[0] + c3 * dx));
+        atomicAdd(&v.f[3 * k + 1], -(CEhb2 * dk[1] + c3 * dy));
+        atomicAdd(&v.f[3 * k + 2], -(CEhb2 * dk[2] + c3 * dz));
+      }
+      fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz); cd = warp_sum(cd);
+      if (lane == 0) {
+        if (cd != 0.0) atomicAdd(&v.b_Cdbo[pi], cd);
+        atomicAdd(&v.f[3 * i], fix); atomicAdd(&v.f[3 * i + 1], fiy); atomicAdd(&v.f[3 * i + 2], fiz);
+      }
+    }
+    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
+    if (lane == 0) { atomicAdd(&v.f[3 * j], fjx); atomicAdd(&v.f[3 * j + 1], fjy); atomicAdd(&v.f[3 * j + 2], fjz); }
+    __syncwarp();
+  }
+  const int slots[1] = {E_HB};
+  double vals[1] = {e_hb};
+  block_commit<1>(v.en, slots, vals);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct Omega { double omega; double di[3], dj[3], dk[3], dl[3]; };
+
+__device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, const double4& gkl, const double* dvec_li,
+                                        double r_li, double theta_ijk, const double* ijk_di, const double* ijk_dj,
+                                        const double* ijk_dk, double theta_jkl, const double* jkl_di, const double* jkl_dj,
+                                        const double* jkl_dk, Omega& o) {
+  const double r_ij = gij.x, r_jk = gjk.x, r_kl = gkl.x;
+  const double vij[3] = {gij.y, gij.z, gij.w}, vjk[3] = {gjk.y, gjk.z, gjk.w}, vkl[3] = {gkl.y, gkl.z, gkl.w};
+  double sin_ijk = sin(theta_ijk), cos_ijk = cos(theta_ijk);
+  double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
+  auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  const double unnorm_cos_omega = -dot(vij, vjk) * dot(vjk, vkl) + sqr(r_jk) * dot(vij, vkl);
+  const double cr[3] = {vjk[1] * vkl[2] - vjk[2] * vkl[1], vjk[2] * vkl[0] - vjk[0] * vkl[2], vjk[0] * vkl[1] - vjk[1] * vkl[0]};
+  const double unnorm_sin_omega = -r_jk * dot(vij, cr);
+  o.omega = atan2(unnorm_sin_omega, unnorm_cos_omega);
+  const double htra = r_ij + cos_ijk * (r_kl * cos_jkl - r_jk);
+  const double htrb = r_jk - r_ij * cos_ijk - r_kl * cos_jkl;
+  const double htrc = r_kl + cos_jkl * (r_ij * cos_ijk - r_jk);
+  const double hthd = r_ij * sin_ijk * (r_jk - r_kl * cos_jkl);
+  const double hthe = r_kl * sin_jkl * (r_jk - r_ij * cos_ijk);
+  const double hnra = r_kl * sin_ijk * sin_jkl;
+  const double hnrc = r_ij * sin_ijk * sin_jkl;
+  const double hnhd = r_ij * r_kl * cos_ijk * sin_jkl;
+  const double hnhe = r_ij * r_kl * sin_ijk * cos_jkl;
+  double poem = 2.0 * r_ij * r_kl * sin_ijk * sin_jkl;
+  if (poem < 1e-20) poem = 1e-20;
+  const double tel = sqr(r_ij) + sqr(r_jk) + sqr(r_kl) - sqr(r_li) -
+                     2.0 * (r_ij * r_jk * cos_ijk - r_ij * r_kl * cos_ijk * cos_jkl + r_jk * r_kl * cos_jkl);
+  double arg = tel / poem;
+  if (arg > 1.0) arg = 1.0;
+  if (arg < -1.0) arg = -1.0;
+  if (sin_ijk >= 0 && sin_ijk <= kMinSine) sin_ijk = kMinSine;
+  else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) sin_ijk = -kMinSine;
+  if (sin_jkl >= 0 && sin_jkl <= kMinSine) sin_jkl = kMinSine;
+  else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) sin_jkl = -kMinSine;
+  const double a1 = (htra - arg * hnra) / r_ij, a2 = (hthd - arg * hnhd) / sin_ijk, a3 = (hthe - arg * hnhe) / sin_jkl;
+  const double a4 = (htrc - arg * hnrc) / r_kl, a5 = htrb / r_jk, sc = 2.0 / poem;
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    o.di[t] = sc * ((a1 * vij[t] + -1. * dvec_li[t]) + -a2 * ijk_dk[t]);
+    o.dj[t] = sc * (((-a1 * vij[t] + -a5 * vjk[t]) + -a2 * ijk_dj[t]) + -a3 * jkl_di[t]);
+    o.dk[t] = sc * (((-a4 * vkl[t] + a5 * vjk[t]) + -a2 * ijk_di[t]) + -a3 * jkl_dj[t]);
+    o.dl[t] = sc * ((a4 * vkl[t] + 1. * dvec_li[t]) + -a3 * jkl_dk[t]);
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_valtor(DevView v, DevParams P) {
+  __shared__ int s_strong[kWarps][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double p_tor2 = P.gp[23], p_tor3 = P.gp[24], p_tor4 = P.gp[25], p_cot2 = P.gp[27];
+  const double p_val6 = P.gp[14], p_val8 = P.gp[33], p_val9 = P.gp[16], p_val10 = P.gp[17];
+  const double p_pen2 = P.gp[19], p_pen3 = P.gp[20], p_pen4 = P.gp[21];
+  const double p_coa2 = P.gp[2], p_coa3 = P.gp[38], p_coa4 = P.gp[30];
+  const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq;
+  const int nt = P.nt;
+  double e_ang = 0, e_pen = 0, e_coa = 0, e_tor = 0, e_con = 0;
+
+  for (int j = wg; j < v.n; j += nwg) {
+    const int type_j = v.type[j];
+    const int start_j = v.b_start[j], cnt_j = v.b_cnt[j];
+    if (type_j < 0 || cnt_j <= 0) continue;
+    const double Delta_boc_j = v.Delta_boc[j];
+    const double p_val3 = P.atom[type_j].p_val3, p_val5 = P.atom[type_j].p_val5;
+    // SBOp / prod_SBO over all bonds of j + list of "strong" bonds (BO > thb_cut): only those can enter an
+    // angle or a torsion (every filter in the reference requires BO_jk > thb_cut and BO_hj > thb_cut)
+    double SBOp = 0, prod_SBO = 1;
+    int ns = 0;
+    for (int e0 = 0; e0 < cnt_j; e0 += 32) {
+      const int e = e0 + lane;
+      bool strong = false;
+      if (e < cnt_j) {
+        const double4 bo = v.b_bo[start_j + e];
+        SBOp += bo.z + bo.w;
+        double t8 = bo.x * bo.x; t8 *= t8; t8 *= t8;
+        prod_SBO *= exp(-t8);
+        strong = bo.x > thb_cut;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, strong);
+      if (strong) { const int slot = ns + __popc(m & ((1u << lane) - 1)); if (slot < 32) s_strong[wib][slot] = start_j + e; }
+      ns += __popc(m);
+    }
+    __syncwarp();
+    if (ns > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = 32; }
+    SBOp = warp_sum(SBOp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) prod_SBO *= __shfl_xor_sync(0xffffffffu, prod_SBO, o);
+    if (ns < 2) { __syncwarp(); continue; }
+
+    const double vlpex_j = v.vlpex[j], nlp_j = v.nlp[j], dDelta_lp_j = v.dDelta_lp[j];
+    double vlpadj, dSBO2;
+    if (vlpex_j >= 0) { vlpadj = 0; dSBO2 = prod_SBO - 1; }
+    else { vlpadj = nlp_j; dSBO2 = (prod_SBO - 1) * (1 - p_val8 * dDelta_lp_j); }
+    const double SBO = SBOp + (1 - prod_SBO) * (-Delta_boc_j - p_val8 * vlpadj);
+    const double dSBO1 = -8 * prod_SBO * (Delta_boc_j + p_val8 * vlpadj);
+    double SBO2, CSBO2;
+    if (SBO <= 0) { SBO2 = 0; CSBO2 = 0; }
+    else if (SBO > 0 && SBO <= 1) { SBO2 = pow(SBO, p_val9); CSBO2 = p_val9 * pow(SBO, p_val9 - 1); }
+    else if (SBO > 1 && SBO < 2) { SBO2 = 2 - pow(2 - SBO, p_val9); CSBO2 = p_val9 * pow(2 - SBO, p_val9 - 1); }
+    else { SBO2 = 2; CSBO2 = 0; }
+    const double expval6 = exp(p_val6 * Delta_boc_j);
+    const double Delta_j = v.Delta[j], Delta_val_j = v.Delta_val[j];
+    const double4 xj = v.xq[j];
+    const int tag_j = v.tag[j];
+
+    double fjx = 0, fjy = 0, fjz = 0, cdd_j = 0, sum5 = 0, sum6 = 0;
+    const int npair = ns * ns;
+    for (int q = lane; q < npair; q += 32) {
+      const int a = q / ns, b = q - a * ns;
+      if (a == b) continue;
+      const int pk = s_strong[wib][a], ph = s_strong[wib][b];
+      const int k = v.b_nbr[pk], h = v.b_nbr[ph];
+      const int type_k = v.type[k], type_h = v.type[h];
+      if (type_k < 0 || type_h < 0) continue;
+      const double4 gjk = v.b_geo[pk], ghj = v.b_geo[ph];
+      const double4 bo_jk = v.b_bo[pk], bo_hj = v.b_bo[ph];
+      const double BOA_jk = bo_jk.x - thb_cut, BOA_hj = bo_hj.x - thb_cut;
+      const int start_k = v.b_start[k], cnt_k = v.b_cnt[k];
+      if (cnt_k <= 0) continue;
+      double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
+      calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
+      calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> h
+
+      // ---------------- valence angle k-j-h (each unordered pair once: ph > pk) ----------------
+      if (ph > pk && bo_jk.x * bo_hj.x > thb_cutsq) {
+        double sin_theta_hjk = sin(theta_hjk);
+        if (sin_theta_hjk < 1.0e-5) sin_theta_hjk = 1.0e-5;
+        const AngleSet& as = P.angle[(type_k * nt + type_j) * nt + type_h];
+        const double tbo_k = v.total_bo[k], tbo_h = v.total_bo[h];
+        for (int c = 0; c < as.cnt && c < kMaxAngleSets; c++) {
+          const AnglePar tp = as.prm[c];
+          if (!(fabs(tp.p_val1) > 0.001)) continue;
+          const double p_val1 = tp.p_val1, p_val2 = tp.p_val2, p_val4 = tp.p_val4, p_val7 = tp.p_val7, theta_00 = tp.theta_00;
+          const double exp3jk = exp(-p_val3 * pow(BOA_jk, p_val4));
+          const double f7_jk = 1.0 - exp3jk;
+          const double Cf7jk = p_val3 * p_val4 * pow(BOA_jk, p_val4 - 1.0) * exp3jk;
+          const double exp3hj = exp(-p_val3 * pow(BOA_hj, p_val4));
+          const double f7_hj = 1.0 - exp3hj;
+          const double Cf7hj = p_val3 * p_val4 * pow(BOA_hj, p_val4 - 1.0) * exp3hj;
+          const double expval7 = exp(-p_val7 * Delta_boc_j);
+          const double trm8 = 1.0 + expval6 + expval7;
+          const double f8_Dj = p_val5 - ((p_val5 - 1.0) * (2.0 + expval6) / trm8);
+          const double Cf8j = ((1.0 - p_val5) / sqr(trm8)) *
+                              (p_val6 * expval6 * trm8 - (2.0 + expval6) * (p_val6 * expval6 - p_val7 * expval7));
+          const double ex10 = exp(-p_val10 * (2.0 - SBO2));
+          double theta_0 = 180.0 - theta_00 * (1.0 - ex10);
+          theta_0 = deg2rad(theta_0);
+          const double expval2theta = exp(-p_val2 * sqr(theta_0 - theta_hjk));
+          const double expval12theta = (p_val1 >= 0) ? p_val1 * (1.0 - expval2theta) : p_val1 * -expval2theta;
+          const double CEval1 = Cf7jk * f7_hj * f8_Dj * expval12theta;
+          const double CEval2 = Cf7hj * f7_jk * f8_Dj * expval12theta;
+          const double CEval3 = Cf8j * f7_hj * f7_jk * expval12theta;
+          const double CEval4 = -2.0 * p_val1 * p_val2 * f7_jk * f7_hj * f8_Dj * expval2theta * (theta_0 - theta_hjk);
+          const double Ctheta_0 = p_val10 * deg2rad(theta_00) * ex10;
+          const double CEval5 = -CEval4 * Ctheta_0 * CSBO2;
+          const double CEval6 = CEval5 * dSBO1;
+          const double CEval7 = CEval5 * dSBO2;
+          const double CEval8 = -CEval4 / sin_theta_hjk;
+          e_ang += f7_jk * f7_hj * f8_Dj * expval12theta;
+
+          const double exp_pen2jk = exp(-p_pen2 * sqr(BOA_jk - 2.0));
+          const double exp_pen2hj = exp(-p_pen2 * sqr(BOA_hj - 2.0));
+          const double exp_pen3 = exp(-p_pen3 * Delta_j);
+          const double exp_pen4 = exp(p_pen4 * Delta_j);
+          const double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
+          const double f9_Dj = (2.0 + exp_pen3) / trm_pen34;
+          const double Cf9j = (-p_pen3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-p_pen3 * exp_pen3 + p_pen4 * exp_pen4)) / sqr(trm_pen34);
+          const double epen = tp.p_pen1 * f9_Dj * exp_pen2jk * exp_pen2hj;
+          e_pen += epen;
+          const double CEpen1 = epen * Cf9j / f9_Dj;
+          const double tpen = -2.0 * p_pen2 * epen;
+          const double CEpen2 = tpen * (BOA_jk - 2.0);
+          const double CEpen3 = tpen * (BOA_hj - 2.0);
+
+          const double exp_coa2 = exp(p_coa2 * Delta_val_j);
+          const double ecoa = tp.p_coa1 / (1. + exp_coa2) * exp(-p_coa3 * sqr(tbo_k - BOA_jk)) * exp(-p_coa3 * sqr(tbo_h - BOA_hj)) *
+                              exp(-p_coa4 * sqr(BOA_jk - 1.5)) * exp(-p_coa4 * sqr(BOA_hj - 1.5));
+          e_coa += ecoa;
+          const double CEcoa1 = -2 * p_coa4 * (BOA_jk - 1.5) * ecoa;
+          const double CEcoa2 = -2 * p_coa4 * (BOA_hj - 1.5) * ecoa;
+          const double CEcoa3 = -p_coa2 * exp_coa2 * ecoa / (1 + exp_coa2);
+          const double CEcoa4 = -2 * p_coa3 * (tbo_k - BOA_jk) * ecoa;
+          const double CEcoa5 = -2 * p_coa3 * (tbo_h - BOA_hj) * ecoa;
+
+          atomicAdd(&v.b_Cdbo[pk], (CEval1 + CEpen2 + (CEcoa1 - CEcoa4)));
+          atomicAdd(&v.b_Cdbo[ph], (CEval2 + CEpen3 + (CEcoa2 - CEcoa5)));
+          cdd_j += ((CEval3 + CEval7) + CEpen1 + CEcoa3);
+          atomicAdd(&v.CdDelta[k], CEcoa4);
+          atomicAdd(&v.CdDelta[h], CEcoa5);
+          sum6 += CEval6;  // applied to every bond t of j after the pair loop: Cdbo[t] += CEval6 * BO_t^7
+          sum5 += CEval5;  //                                                  Cdbopi[t], Cdbopi2[t] += CEval5
+          fadd3(v.f, k, -CEval8, hjk_di[0], hjk_di[1], hjk_di[2]);
+          fjx -= CEval8 * hjk_dj[0]; fjy -= CEval8 * hjk_dj[1]; fjz -= CEval8 * hjk_dj[2];
+          fadd3(v.f, h, -CEval8, hjk_dk[0], hjk_dk[1], hjk_dk[2]);
+        }
+      }
+
+      // ---------------- torsion h-j-k-w, bond j-k taken once by tag order ----------------
+      const double4 xk = v.xq[k];
+      if (!half_select(tag_j, v.tag[k], xj, xk)) continue;
+      const int pj = v.b_sym[pk];  // j on k's row
+      if (pj < 0) continue;
+      const double4 gkj = v.b_geo[pj];
+      const int i = h, type_i = type_h;
+      const double r_ij = ghj.x;
+      const double BOA_ij = BOA_hj;
+      const double sin_ijk = sin(theta_hjk), cos_ijk = cos(theta_hjk);
+      double tan_ijk_i;
+      if (sin_ijk >= 0 && sin_ijk <= kMinSine) tan_ijk_i = cos_ijk / kMinSine;
+      else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) tan_ijk_i = cos_ijk / -kMinSine;
+      else tan_ijk_i = cos_ijk / sin_ijk;
+      const double exp_tor2_ij = exp(-p_tor2 * BOA_ij);
+      const double exp_cot2_ij = exp(-p_cot2 * sqr(BOA_ij - 1.5));
+      const double exp_tor2_jk = exp(-p_tor2 * BOA_jk);
+      const double exp_cot2_jk = exp(-p_cot2 * sqr(BOA_jk - 1.5));
+      const double Delta_k = v.Delta_boc[k];
+      const double exp_tor3_DjDk = exp(-p_tor3 * (Delta_boc_j + Delta_k));
+      const double exp_tor4_DjDk = exp(p_tor4 * (Delta_boc_j + Delta_k));
+      const double exp_tor34_inv = 1.0 / (1.0 + exp_tor3_DjDk + exp_tor4_DjDk);
+      const double f11_DjDk = (2.0 + exp_tor3_DjDk) * exp_tor34_inv;
+      const double4 xi = v.xq[i];
+      double fix = 0, fiy = 0, fiz = 0, fkx = 0, fky = 0, fkz = 0, cdbo_ij = 0, cdbo_jk = 0, cdbopi_jk = 0, cdd_k = 0;
+
+      for (int pw = start_k; pw < start_k + cnt_k; pw++) {
+        if (pw == pj) continue;
+        const double4 bo_kl = v.b_bo[pw];
+        if (!(bo_kl.x > thb_cut)) continue;
+        const int l = v.b_nbr[pw];
+        if (i == l) continue;
+        const int type_l = v.type[l];
+        if (type_l < 0) continue;
+        const TorsPar fp = P.tors[((type_i * nt + type_j) * nt + type_k) * nt + type_l];
+        if (!fp.cnt) continue;
+        if (!(bo_hj.x * bo_jk.x * bo_kl.x > thb_cut)) continue;
+        const double4 gkl = v.b_geo[pw];
+        double theta_jkl, cos_theta_jkl, jkl_di[3], jkl_dj[3], jkl_dk[3];
+        calc_theta(gkj, gkl, theta_jkl, cos_theta_jkl);
+        calc_dcos(gkj, gkl, jkl_di, jkl_dj, jkl_dk);  // di <-> j, dj <-> k, dk <-> l
+        const double r_kl = gkl.x;
+        const double BOA_kl = bo_kl.x - thb_cut;
+        const double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
+        double tan_jkl_i;
+        if (sin_jkl >= 0 && sin_jkl <= kMinSine) tan_jkl_i = cos_jkl / kMinSine;
+        else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) tan_jkl_i = cos_jkl / -kMinSine;
+        else tan_jkl_i = cos_jkl / sin_jkl;
+        const double4 xl = v.xq[l];
+        const double dvec_li[3] = {xi.x - xl.x, xi.y - xl.y, xi.z - xl.z};
+        const double r_li = sqrt(dvec_li[0] * dvec_li[0] + dvec_li[1] * dvec_li[1] + dvec_li[2] * dvec_li[2]);
+        Omega om;
+        calc_omega(ghj, gjk, gkl, dvec_li, r_li, theta_hjk, hjk_di, hjk_dj, hjk_dk, theta_jkl, jkl_di, jkl_dj, jkl_dk, om);
+        const double cos_omega = cos(om.omega), cos2omega = cos(2. * om.omega), cos3omega = cos(3. * om.omega);
+        const double exp_tor1 = exp(fp.p_tor1 * sqr(2.0 - bo_jk.z - f11_DjDk));
+        const double exp_tor2_kl = exp(-p_tor2 * BOA_kl);
+        const double exp_cot2_kl = exp(-p_cot2 * sqr(BOA_kl - 1.5));
+        const double fn10 = (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
+        const double CV = 0.5 * (fp.V1 * (1.0 + cos_omega) + fp.V2 * exp_tor1 * (1.0 - cos2omega) + fp.V3 * (1.0 + cos3omega));
+        e_tor += fn10 * sin_ijk * sin_jkl * CV;
+        const double dfn11 = (-p_tor3 * exp_tor3_DjDk + (p_tor3 * exp_tor3_DjDk - p_tor4 * exp_tor4_DjDk) * (2.0 + exp_tor3_DjDk) * exp_tor34_inv) * exp_tor34_inv;
+        const double CEtors1 = sin_ijk * sin_jkl * CV;
+        const double CEtors2 = -fn10 * 2.0 * fp.p_tor1 * fp.V2 * exp_tor1 * (2.0 - bo_jk.z - f11_DjDk) * (1.0 - sqr(cos_omega)) * sin_ijk * sin_jkl;
+        const double CEtors3 = CEtors2 * dfn11;
+        const double CEtors4 = CEtors1 * p_tor2 * exp_tor2_ij * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
+        const double CEtors5 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * exp_tor2_jk * (1.0 - exp_tor2_kl);
+        const double CEtors6 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * exp_tor2_kl;
+        const double cmn = -fn10 * CV;
+        const double CEtors7 = cmn * sin_jkl * tan_ijk_i;
+        const double CEtors8 = cmn * sin_ijk * tan_jkl_i;
+        const double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * fp.V1 - 2.0 * fp.V2 * exp_tor1 * cos_omega + 1.5 * fp.V3 * (cos2omega + 2.0 * sqr(cos_omega)));
+        const double fn12 = exp_cot2_ij * exp_cot2_jk * exp_cot2_kl;
+        const double cterm = (1.0 + (sqr(cos_omega) - 1.0) * sin_ijk * sin_jkl);
+        e_con += fp.p_cot1 * fn12 * cterm;
+        const double Cconj = -2.0 * fn12 * fp.p_cot1 * p_cot2 * cterm;
+        const double CEconj1 = Cconj * (BOA_ij - 1.5e0);
+        const double CEconj2 = Cconj * (BOA_jk - 1.5e0);
+        const double CEconj3 = Cconj * (BOA_kl - 1.5e0);
+        const double CEconj4 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_jkl * tan_ijk_i;
+        const double CEconj5 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_ijk * tan_jkl_i;
+        const double CEconj6 = 2.0 * fp.p_cot1 * fn12 * cos_omega * sin_ijk * sin_jkl;
+
+        cdbopi_jk += CEtors2;
+        cdd_j += CEtors3;
+        cdd_k += CEtors3;
+        cdbo_ij += (CEtors4 + CEconj1);
+        cdbo_jk += (CEtors5 + CEconj2);
+        atomicAdd(&v.b_Cdbo[pw], (CEtors6 + CEconj3));
+        const double c74 = CEtors7 + CEconj4, c85 = CEtors8 + CEconj5, c96 = CEtors9 + CEconj6;
+        fix -= c74 * hjk_dk[0] + c96 * om.di[0]; fiy -= c74 * hjk_dk[1] + c96 * om.di[1]; fiz -= c74 * hjk_dk[2] + c96 * om.di[2];
+        fjx -= c74 * hjk_dj[0] + c85 * jkl_di[0] + c96 * om.dj[0];
+        fjy -= c74 * hjk_dj[1] + c85 * jkl_di[1] + c96 * om.dj[1];
+        fjz -= c74 * hjk_dj[2] + c85 * jkl_di[2] + c96 * om.dj[2];
+        fkx -= c74 * hjk_di[0] + c85 * jkl_dj[0] + c96 * om.dk[0];
+        fky -= c74 * hjk_di[1] + c85 * jkl_dj[1] + c96 * om.dk[1];
+        fkz -= c74 * hjk_di[2] + c85 * jkl_dj[2] + c96 * om.dk[2];
+        atomicAdd(&v.f[3 * l], -(c85 * jkl_dk[0] + c96 * om.dl[0]));
+        atomicAdd(&v.f[3 * l + 1], -(c85 * jkl_dk[1] + c96 * om.dl[1]));
+        atomicAdd(&v.f[3 * l + 2], -(c85 * jkl_dk[2] + c96 * om.dl[2]));
+      }
+      if (cdbo_ij != 0.0) atomicAdd(&v.b_Cdbo[ph], cdbo_ij);
+      if (cdbo_jk != 0.0) atomicAdd(&v.b_Cdbo[pk], cdbo_jk);
+      if (cdbopi_jk != 0.0) atomicAdd(&v.b_Cdbopi[pk], cdbopi_jk);
+      if (cdd_k != 0.0) atomicAdd(&v.CdDelta[k], cdd_k);
+      if (fix != 0.0 || fiy != 0.0 || fiz != 0.0) { atomicAdd(&v.f[3 * i], fix); atomicAdd(&v.f[3 * i + 1], fiy); atomicAdd(&v.f[3 * i + 2], fiz); }
+      if (fkx != 0.0 || fky != 0.0 || fkz != 0.0) { atomicAdd(&v.f[3 * k], fkx); atomicAdd(&v.f[3 * k + 1], fky); atomicAdd(&v.f[3 * k + 2], fkz); }
+    }
+    // warp-level epilogue for the centre atom
+    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
+    cdd_j = warp_sum(cdd_j); sum5 = warp_sum(sum5); sum6 = warp_sum(sum6);
+    if (lane == 0) {
+      atomicAdd(&v.f[3 * j], fjx); atomicAdd(&v.f[3 * j + 1], fjy); atomicAdd(&v.f[3 * j + 2], fjz);
+      if (cdd_j != 0.0) atomicAdd(&v.CdDelta[j], cdd_j);
+    }
+    if (sum5 != 0.0 || sum6 != 0.0)
+      for (int e = lane; e < cnt_j; e += 32) {
+        const int t = start_j + e;
+        const double bo = v.b_bo[t].x;
+        const double b3 = bo * bo * bo;
+        atomicAdd(&v.b_Cdbo[t], sum6 * (b3 * b3 * bo));
+        atomicAdd(&v.b_Cdbopi[t], sum5);
+        atomicAdd(&v.b_Cdbopi2[t], sum5);
+      }
+    __syncwarp();
+  }
+  const int slots[5] = {E_ANG, E_PEN, E_COA, E_TOR, E_CON};
+  double vals[5] = {e_ang, e_pen, e_coa, e_tor, e_con};
+  block_commit<5>(v.en, slots, vals);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+k_dbond(DevView v) {
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  for (int i = wg; i < v.N; i += nwg) {
+    const int start = v.b_start[i], cnt = v.b_cnt[i];
+    if (cnt <= 0) continue;
+    const double dsx = v.dDeltap_self[3 * i], dsy = v.dDeltap_self[3 * i + 1], dsz = v.dDeltap_self[3 * i + 2];
+    const double cdd_i = v.CdDelta[i];
+    double fx = 0, fy = 0, fz = 0, buf_c = 0;
+    for (int e = lane; e < cnt; e += 32) {
+      const int p = start + e;
+      const int j = v.b_nbr[p];
+      const int sym = v.b_sym[p];
+      if (sym < 0) continue;
+      const double Cdbo = v.b_Cdbo[p] + v.b_Cdbo[sym];
+      const double Cdbopi = v.b_Cdbopi[p] + v.b_Cdbopi[sym];
+      const double Cdbopi2 = v.b_Cdbopi2[p] + v.b_Cdbopi2[sym];
+      const double cdd = cdd_i + v.CdDelta[j];
+      if (Cdbo == 0.0 && Cdbopi == 0.0 && Cdbopi2 == 0.0 && cdd == 0.0) continue;
+      const double4 c1 = v.b_c1[p], c2 = v.b_c2[p], c3 = v.b_c3[p], der = v.b_der[p], geo = v.b_geo[p];
+      const double C1dbo = c1.x * Cdbo, C2dbo = c1.y * Cdbo;
+      const double C1dbopi = c1.w * Cdbopi, C2dbopi = c2.x * Cdbopi, C3dbopi = c2.y * Cdbopi;
+      const double C1dbopi2 = c2.w * Cdbopi2, C2dbopi2 = c3.x * Cdbopi2, C3dbopi2 = c3.y * Cdbopi2;
+      const double C1dDelta = c1.x * cdd, C2dDelta = c1.y * cdd;
+      // temp = sum coef * vector; dBOp = der.x*dvec, dln_BOp_pi = der.y*dvec, dln_BOp_pi2 = der.z*dvec
+      const double a_dbop = C1dbo + C1dDelta + C2dbopi + C2dbopi2;
+      const double a_self = C2dbo + C2dDelta + C3dbopi + C3dbopi2;
+      const double along = a_dbop * der.x + C1dbopi * der.y + C1dbopi2 * der.z;
+      // reference adds temp to fCdDelta (= -force)
+      fx -= along * geo.y + a_self * dsx;
+      fy -= along * geo.z + a_self * dsy;
+      fz -= along * geo.w + a_self * dsz;
+      buf_c += -a_self;
+    }
+    buf_c = warp_sum(buf_c);
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0 && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
+      atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
+    }
+    if (buf_c != 0.0)
+      for (int e = lane; e < cnt; e += 32) {
+        const int p = start + e;
+        const double4 geo = v.b_geo[p];
+        const double c = -buf_c * v.b_der[p].x;
+        fadd3(v.f, v.b_nbr[p], c, geo.y, geo.z, geo.w);
+      }
+  }
+}
+
+}  // namespace
+
+void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
+  if (v.n == 0) return;
+  k_multi<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  k_hbond<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  k_valtor<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  s.kernel_launches += 3;
+}
+
+void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
+  (void)P;
+  if (v.N == 0) return;
+  k_dbond<<<kBlocks, kWarps * 32, 0, st>>>(v);
+  s.kernel_launches++;
+}
+
+}  // namespace rxb

@@ -1,0 +1,265 @@
+// extern "C" layer of librxb200.so: thin, exception -> status translation only (see include/rxb200.h).
+#include <cstring>
+#include <string>
+
+#include "../../include/rxb200.h"
+#include "rxb_system.h"
+
+using rxb::System;
+
+struct rxb_handle {
+  System* sys = nullptr;
+  int lgvdw = 0, enobonds = 1;
+  std::string control;
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <class F>
+int guard(F&& fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  } catch (...) {
+    g_err = "unknown error";
+    return -1;
+  }
+}
+
+template <class T>
+void d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
+  if (n == 0) return;
+  RXB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+  RXB_CUDA(cudaStreamSynchronize(st));
+}
+}  // namespace
+
+extern "C" {
+
+const char* rxb_last_error(void) { return g_err.c_str(); }
+
+int rxb_create(int cuda_device, rxb_handle** out) {
+  return guard([&] {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw std::runtime_error("rxb_create: no CUDA device available (this path has no CPU fallback)");
+    rxb_handle* h = new rxb_handle();
+    h->sys = new System(cuda_device);
+    *out = h;
+  });
+}
+
+void rxb_destroy(rxb_handle* h) {
+  if (!h) return;
+  delete h->sys;
+  delete h;
+}
+
+int rxb_pair_settings(rxb_handle* h, const char* control_file, int lgvdw, int enobonds) {
+  return guard([&] {
+    auto& ff = h->sys->ff;
+    ff.ctl.lgflag = lgvdw;       // defaults: pair_reaxc_sunway.cpp:235-241
+    ff.ctl.enobondsflag = enobonds;
+    std::string e = ff.load_control(control_file);
+    if (!e.empty()) throw std::runtime_error(e);
+  });
+}
+
+int rxb_pair_coeff(rxb_handle* h, const char* ffield_file, int ntypes, const char* const* elements) {
+  return guard([&] {
+    auto& ff = h->sys->ff;
+    std::string e = ff.load_ffield(ffield_file);
+    if (e.empty()) e = ff.set_elements(ntypes, elements);
+    if (!e.empty()) throw std::runtime_error(e);
+    h->sys->upload_params();
+  });
+}
+
+int rxb_pair_extract(rxb_handle* h, const char* name, double* out, int ntypes) {
+  return guard([&] {
+    const auto& ff = h->sys->ff;
+    for (int t = 0; t <= ntypes; t++) {
+      out[t] = 0.0;
+      if (t >= 1 && t < (int)ff.map.size() && ff.map[t] >= 0) {
+        const rxb::AtomPar& a = ff.atom[ff.map[t]];
+        if (!strcmp(name, "chi")) out[t] = a.chi;
+        else if (!strcmp(name, "eta")) out[t] = a.eta;
+        else if (!strcmp(name, "gamma")) out[t] = a.gamma;
+        else throw std::runtime_error(std::string("rxb_pair_extract: unknown quantity ") + name);
+      }
+    }
+  });
+}
+
+int rxb_fix_qeq(rxb_handle* h, double swa, double swb, double tolerance, int max_iter) {
+  return guard([&] {
+    if (swb < 0) throw std::runtime_error("Fix qeq/reax has negative upper Taper radius cutoff");
+    h->sys->qeq_swa = swa; h->sys->qeq_swb = swb; h->sys->qeq_tol = tolerance;
+    if (max_iter > 0) h->sys->qeq_imax = max_iter;
+  });
+}
+
+int rxb_neighbor_skin(rxb_handle* h, double skin) { return guard([&] { h->sys->skin = skin; }); }
+
+long rxb_params_dump(rxb_handle* h, double* out, long cap) {
+  std::vector<double> v = h->sys->params_dump();
+  if (out) for (long i = 0; i < (long)v.size() && i < cap; i++) out[i] = v[i];
+  return (long)v.size();
+}
+
+int rxb_set_atoms(rxb_handle* h, int nlocal, int nghost, const double* x, const int* type, const int* tag, const double* q,
+                  const int* ghost_owner) {
+  return guard([&] { h->sys->set_atoms(nlocal, nghost, x, type, tag, q, ghost_owner); });
+}
+int rxb_set_positions(rxb_handle* h, const double* x) { return guard([&] { h->sys->set_positions(x); }); }
+int rxb_set_charges(rxb_handle* h, const double* q) { return guard([&] { h->sys->set_charges(q); }); }
+int rxb_neigh_build(rxb_handle* h) { return guard([&] { h->sys->build_neighbors(); }); }
+
+int rxb_qeq_pre_force(rxb_handle* h, int* matvecs2) {
+  return guard([&] {
+    h->sys->qeq_pre_force();
+    if (matvecs2) { matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t; }
+  });
+}
+int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist) {
+  return guard([&] { h->sys->qeq_set_history(s_hist, t_hist); });
+}
+int rxb_qeq_get_history(rxb_handle* h, double* s_hist, double* t_hist) {
+  return guard([&] { h->sys->qeq_get_history(s_hist, t_hist); });
+}
+int rxb_get_charges(rxb_handle* h, double* q) { return guard([&] { h->sys->get_charges(q); }); }
+
+static void fill_pvector(const double* e, double* pvector, double* eng2) {
+  using namespace rxb;
+  if (pvector) {  // pair_reaxc_sunway.cpp:657-670
+    pvector[0] = e[E_BOND]; pvector[1] = e[E_OV] + e[E_UN]; pvector[2] = e[E_LP]; pvector[3] = 0.0;
+    pvector[4] = e[E_ANG]; pvector[5] = e[E_PEN]; pvector[6] = e[E_COA]; pvector[7] = e[E_HB];
+    pvector[8] = e[E_TOR]; pvector[9] = e[E_CON]; pvector[10] = e[E_VDW]; pvector[11] = e[E_ELE];
+    pvector[12] = 0.0; pvector[13] = e[E_POL];
+  }
+  if (eng2) {  // evdwl / ecoul split, pair_reaxc_sunway.cpp:636-650
+    eng2[0] = e[E_BOND] + e[E_OV] + e[E_UN] + e[E_LP] + e[E_ANG] + e[E_PEN] + e[E_COA] + e[E_HB] + e[E_TOR] + e[E_CON] + e[E_VDW];
+    eng2[1] = e[E_ELE] + e[E_POL];
+  }
+}
+
+int rxb_pair_compute(rxb_handle* h, int eflag, int vflag, double* f_out, double* pvector, double* eng2, double* virial6) {
+  return guard([&] {
+    System& s = *h->sys;
+    s.compute(eflag != 0, vflag != 0);
+    if (f_out) s.get_forces(f_out);
+    fill_pvector(s.energies, pvector, eng2);
+    if (virial6) memcpy(virial6, s.virial, 6 * sizeof(double));
+  });
+}
+
+int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x, const double* v, const int* type,
+                 const int* tag, const double* mass, int ntypes, double dt, int reneigh_every, int thermo_every, int qeq_on) {
+  return guard([&] {
+    h->sys->qeq_on = qeq_on != 0;
+    h->sys->md_thermo = thermo_every;
+    h->sys->md_setup(box6, nlocal, x, v, type, tag, mass, ntypes, dt, reneigh_every);
+  });
+}
+int rxb_md_run(rxb_handle* h, int nsteps) { return guard([&] { h->sys->md_run(nsteps); }); }
+int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q) { return guard([&] { h->sys->md_get(x, v, f, q); }); }
+int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke) {
+  return guard([&] {
+    System& s = *h->sys;
+    double eng2[2];
+    fill_pvector(s.energies, pvector, eng2);
+    if (pe) *pe = eng2[0] + eng2[1];
+    if (ke) *ke = s.md_kinetic();
+  });
+}
+
+int rxb_get_counts(rxb_handle* h, long long* c) {
+  return guard([&] {
+    System& s = *h->sys;
+    c[0] = s.n; c[1] = s.N; c[2] = s.vl.nnz; c[3] = s.bc.nnz; c[4] = s.num_bonds;
+    long long far = 0;
+    if (s.n > 0 && s.far_num.n >= (size_t)s.n) {
+      std::vector<int> num(s.n);
+      d2h(num.data(), s.far_num.p, s.n, s.stream());
+      for (int v : num) far += v;
+    }
+    c[5] = far; c[6] = s.kernel_launches; c[7] = s.qeq_iters_total;
+  });
+}
+
+int rxb_get_neighbors(rxb_handle* h, int which, long long* off, int* idx) {
+  return guard([&] {
+    System& s = *h->sys;
+    rxb::Csr& c = which == 0 ? s.vl : s.bc;
+    d2h(off, c.off.p, (size_t)c.nrows + 1, s.stream());
+    d2h(idx, c.idx.p, (size_t)c.nnz, s.stream());
+  });
+}
+
+int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, double* fld) {
+  return guard([&] {
+    System& s = *h->sys;
+    const size_t N = s.N, nb = s.num_bonds;
+    d2h(b_start, s.b_start.p, N, s.stream());
+    d2h(b_cnt, s.b_cnt.p, N, s.stream());
+    d2h(nbr, s.b_nbr.p, nb, s.stream());
+    d2h(sym, s.b_sym.p, nb, s.stream());
+    std::vector<double4> geo(nb), bo(nb), der(nb), c1(nb), c2(nb), c3(nb);
+    std::vector<double> cd(nb), cdpi(nb), cdpi2(nb);
+    d2h(geo.data(), s.b_geo.p, nb, s.stream()); d2h(bo.data(), s.b_bo.p, nb, s.stream());
+    d2h(der.data(), s.b_der.p, nb, s.stream()); d2h(c1.data(), s.b_c1.p, nb, s.stream());
+    d2h(c2.data(), s.b_c2.p, nb, s.stream()); d2h(c3.data(), s.b_c3.p, nb, s.stream());
+    d2h(cd.data(), s.b_Cdbo.p, nb, s.stream()); d2h(cdpi.data(), s.b_Cdbopi.p, nb, s.stream());
+    d2h(cdpi2.data(), s.b_Cdbopi2.p, nb, s.stream());
+    for (size_t p = 0; p < nb; p++) {
+      double* o = fld + 31 * p;
+      const double dv[3] = {geo[p].y, geo[p].z, geo[p].w};
+      o[0] = geo[p].x; o[1] = dv[0]; o[2] = dv[1]; o[3] = dv[2];
+      o[4] = bo[p].x; o[5] = bo[p].y; o[6] = bo[p].z; o[7] = bo[p].w;
+      for (int t = 0; t < 3; t++) { o[8 + t] = der[p].x * dv[t]; o[11 + t] = der[p].y * dv[t]; o[14 + t] = der[p].z * dv[t]; }
+      o[17] = c1[p].x; o[18] = c1[p].y; o[19] = c1[p].z;
+      o[20] = c1[p].w; o[21] = c2[p].x; o[22] = c2[p].y; o[23] = c2[p].z;
+      o[24] = c2[p].w; o[25] = c3[p].x; o[26] = c3[p].y; o[27] = c3[p].z;
+      o[28] = cd[p]; o[29] = cdpi[p]; o[30] = cdpi2[p];
+    }
+  });
+}
+
+int rxb_get_workspace(rxb_handle* h, double* w16) {
+  return guard([&] {
+    System& s = *h->sys;
+    const size_t N = s.N;
+    std::vector<double> a(N);
+    std::vector<double2> dp(N);
+    auto col = [&](const double* src, int c) { d2h(a.data(), src, N, s.stream()); for (size_t i = 0; i < N; i++) w16[16 * i + c] = a[i]; };
+    memset(w16, 0, N * 16 * sizeof(double));
+    col(s.total_bo.p, 0); col(s.Delta_boc.p, 1);
+    d2h(dp.data(), s.Deltap.p, N, s.stream());
+    for (size_t i = 0; i < N; i++) { w16[16 * i + 2] = dp[i].x; w16[16 * i + 3] = dp[i].y; }
+    col(s.Delta.p, 4); col(s.Delta_val.p, 6); col(s.vlpex.p, 7); col(s.nlp.p, 8); col(s.Delta_lp.p, 9);
+    col(s.dDelta_lp.p, 10); col(s.dDelta_lp.p, 11); col(s.Delta_lp_temp.p, 13); col(s.CdDelta.p, 15);
+  });
+}
+
+int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val) {
+  return guard([&] {
+    System& s = *h->sys;
+    d2h(num, s.far_num.p, (size_t)s.n, s.stream());
+    d2h(idx, s.far_idx.p, (size_t)s.vl.nnz, s.stream());
+    d2h(val, s.H_val.p, (size_t)s.vl.nnz, s.stream());
+  });
+}
+
+int rxb_profile(rxb_handle* h, int enable, double* ms9) {
+  return guard([&] {
+    System& s = *h->sys;
+    if (ms9) for (int k = 0; k < rxb::StepTimers::NUM; k++) ms9[k] = s.timers.ms[k];
+    if (enable >= 0) { s.profile = enable != 0; if (enable) s.timers = rxb::StepTimers(); }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// Cell-sorted full neighbour-list build on the GPU -> device CSR.
+//
+// Replaces NPairFullBin{Atomonly,Ghost}Sunway::build and its slave kernels
+// (/root/reference/npair_full_bin_atomonly_sunway.cpp:39-198, npair_full_bin_ghost_sw5.c:80-228):
+// same list semantics (full list, j != i, r^2 <= cut^2 in fp64, rows for ghost atoms when asked),
+// different machinery: atoms are radix-sorted by cell (x fastest) so that every (y,z) stencil row is ONE
+// contiguous run of the sorted position array; a warp owns a row atom, sweeps the runs with coalesced
+// 32-byte loads and ballot-compacts the hits.  No per-atom pages, no fixed row stride.
+//
+// HBM-bound by design (28(N+G) read + 4 nnz written); the stencil re-reads hit L1/L2.
+#include <cub/cub.cuh>
+
+#include "rxb_system.h"
+
+namespace rxb {
+
+namespace {
+
+constexpr double kSlack = 1e-6;  // Angstrom
+
+struct Grid {
+  double lo[3], inv[3], size[3];
+  int nb[3];
+};
+
+__global__ void k_bounds(const double4* __restrict__ xq, int N, double* __restrict__ out6) {
+  // out6 = min xyz, max xyz; atomics on order-preserving integer images of the doubles
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    double4 p = xq[i];
+    mn[0] = fmin(mn[0], p.x); mn[1] = fmin(mn[1], p.y); mn[2] = fmin(mn[2], p.z);
+    mx[0] = fmax(mx[0], p.x); mx[1] = fmax(mx[1], p.y); mx[2] = fmax(mx[2], p.z);
+  }
+  for (int t = 0; t < 3; t++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[t] = fmin(mn[t], __shfl_xor_sync(0xffffffffu, mn[t], o));
+      mx[t] = fmax(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    auto enc = [](double d) { long long b = __double_as_longlong(d); return b >= 0 ? b : b ^ 0x7fffffffffffffffLL; };
+    for (int t = 0; t < 3; t++) {
+      atomicMin((long long*)out6 + t, enc(mn[t]));
+      atomicMax((long long*)out6 + 3 + t, enc(mx[t]));
+    }
+  }
+}
+
+__device__ __forceinline__ int bin_coord(double x, double lo, double inv, int nb) {
+  int b = (int)((x - lo) * inv);
+  return min(max(b, 0), nb - 1);
+}
+
+__global__ void k_bin_ids(const double4* __restrict__ xq, int N, Grid g, int* __restrict__ key, int* __restrict__ val,
+                          int* __restrict__ bin_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double4 p = xq[i];
+  int bx = bin_coord(p.x, g.lo[0], g.inv[0], g.nb[0]);
+  int by = bin_coord(p.y, g.lo[1], g.inv[1], g.nb[1]);
+  int bz = bin_coord(p.z, g.lo[2], g.inv[2], g.nb[2]);
+  int id = (bz * g.nb[1] + by) * g.nb[0] + bx;
+  key[i] = id;
+  val[i] = i;
+  atomicAdd(&bin_count[id], 1);
+}
+
+__global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __restrict__ sorted_idx, int N,
+                                double4* __restrict__ spos) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  int i = sorted_idx[k];
+  double4 p = xq[i];
+  p.w = __longlong_as_double((long long)i);
+  spos[k] = p;
+}
+
+// One warp per row atom.  FILL=false: count hits -> cnt[i];  FILL=true: write columns at off[i].
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const int* __restrict__ bin_start, Grid g,
+        int nrows, double cut, int reach, int* __restrict__ cnt, const long long* __restrict__ off, int* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= nrows) return;
+  const double4 pi = xq[i];
+  const double c2 = cut * cut;
+  const int bx = bin_coord(pi.x, g.lo[0], g.inv[0], g.nb[0]);
+  const int by = bin_coord(pi.y, g.lo[1], g.inv[1], g.nb[1]);
+  const int bz = bin_coord(pi.z, g.lo[2], g.inv[2], g.nb[2]);
+  long long w = FILL ? off[i] : 0;
+  int total = 0;
+  for (int cz = max(bz - reach, 0); cz <= min(bz + reach, g.nb[2] - 1); cz++) {
+    double dz = 0.0;
+    if (cz > bz) dz = (g.lo[2] + cz * g.size[2]) - pi.z;
+    else if (cz < bz) dz = pi.z - (g.lo[2] + (cz + 1) * g.size[2]);
+    dz = fmax(dz - kSlack, 0.0);  // bin edges are rounded; never prune a run that could hold a boundary pair
+    if (dz * dz > c2) continue;
+    for (int cy = max(by - reach, 0); cy <= min(by + reach, g.nb[1] - 1); cy++) {
+      double dy = 0.0;
+      if (cy > by) dy = (g.lo[1] + cy * g.size[1]) - pi.y;
+      else if (cy < by) dy = pi.y - (g.lo[1] + (cy + 1) * g.size[1]);
+      dy = fmax(dy - kSlack, 0.0);
+      const double rem = c2 - dz * dz - dy * dy;
+      if (rem < 0.0) continue;
+      // trim the x run to the chord of the cutoff sphere (one bin of slack for rounding)
+      const double half = sqrt(rem) + kSlack;
+      int x0 = (int)floor((pi.x - half - g.lo[0]) * g.inv[0]) - 1;
+      int x1 = (int)floor((pi.x + half - g.lo[0]) * g.inv[0]) + 1;
+      x0 = max(max(x0, bx - reach), 0);
+      x1 = min(min(x1, bx + reach), g.nb[0] - 1);
+      const int rowbase = (cz * g.nb[1] + cy) * g.nb[0];
+      const int kbeg = bin_start[rowbase + x0], kend = bin_start[rowbase + x1 + 1];
+      for (int k0 = kbeg; k0 < kend; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        int j = -1;
+        if (k < kend) {
+          const double4 pj = spos[k];
+          j = (int)__double_as_longlong(pj.w);
+          // explicit rn ops: no FMA contraction, so the r^2 <= cut^2 test is the oracle's arithmetic bit for bit
+          const double ddx = __dsub_rn(pi.x, pj.x), ddy = __dsub_rn(pi.y, pj.y), ddz = __dsub_rn(pi.z, pj.z);
+          const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+          hit = (j != i) && (r2 <= c2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL) {
+          if (hit) idx[w + __popc(m & ((1u << lane) - 1))] = j;
+          w += __popc(m);
+        } else {
+          total += __popc(m);
+        }
+      }
+    }
+  }
+  if (!FILL && lane == 0) cnt[i] = total;
+}
+
+__global__ void k_cnt_to_ll(const int* __restrict__ cnt, int n, long long* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cnt[i];
+  if (i == n) out[n] = 0;
+}
+
+}  // namespace
+
+void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaStream_t st) {
+  reach = reach_;
+  // bounding box (one small D2H per rebuild)
+  bounds.resize(6);
+  double init[6];
+  {
+    auto enc = [](double d) { long long b; memcpy(&b, &d, 8); b = b >= 0 ? b : b ^ 0x7fffffffffffffffLL; double o; memcpy(&o, &b, 8); return o; };
+    for (int t = 0; t < 3; t++) { init[t] = enc(1e300); init[3 + t] = enc(-1e300); }
+  }
+  RXB_CUDA(cudaMemcpyAsync(bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  k_bounds<<<296, 256, 0, st>>>(xq, N, bounds.p);
+  double got[6];
+  RXB_CUDA(cudaMemcpyAsync(got, bounds.p, sizeof(got), cudaMemcpyDeviceToHost, st));
+  RXB_CUDA(cudaStreamSynchronize(st));
+  for (int t = 0; t < 6; t++) { long long b; memcpy(&b, &got[t], 8); b = b >= 0 ? b : b ^ 0x7fffffffffffffffLL; memcpy(&got[t], &b, 8); }
+  Grid g;
+  long long nbins = 1;
+  for (int t = 0; t < 3; t++) {
+    double ext = got[3 + t] - got[t];
+    if (!(ext > 1e-9)) ext = 1e-9;
+    int nb = (int)(ext / bin_size);
+    if (nb < 1) nb = 1;
+    g.nb[t] = nb; g.lo[t] = got[t]; g.size[t] = ext / nb; g.inv[t] = nb / ext;
+    nbins *= nb;
+  }
+  memcpy(grid_blob, &g, sizeof(g));
+  static_assert(sizeof(Grid) <= sizeof(grid_blob), "grid blob too small");
+  num_bins = (int)nbins;
+  key.resize(N); val.resize(N); key2.resize(N); sorted_idx.resize(N); spos.resize(N);
+  bin_count.resize(num_bins + 1); bin_start.resize(num_bins + 1);
+  RXB_CUDA(cudaMemsetAsync(bin_count.p, 0, (num_bins + 1) * sizeof(int), st));
+  k_bin_ids<<<(N + 255) / 256, 256, 0, st>>>(xq, N, g, key.p, val.p, bin_count.p);
+  size_t need = 0, need2 = 0;
+  int bits = 1;
+  while ((1LL << bits) < nbins) bits++;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, key.p, key2.p, val.p, sorted_idx.p, N, 0, bits, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, need2, bin_count.p, bin_start.p, num_bins + 1, st);
+  if (need2 > need) need = need2;
+  temp.resize(need + 16);
+  cub::DeviceRadixSort::SortPairs(temp.p, need, key.p, key2.p, val.p, sorted_idx.p, N, 0, bits, st);
+  cub::DeviceScan::ExclusiveSum(temp.p, need, bin_count.p, bin_start.p, num_bins + 1, st);
+  k_gather_sorted<<<(N + 255) / 256, 256, 0, st>>>(xq, sorted_idx.p, N, spos.p);
+  RXB_CUDA(cudaGetLastError());
+}
+
+void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st) {
+  Grid g;
+  memcpy(&g, grid_blob, sizeof(g));
+  cnt.resize(nrows + 1);
+  out.off.resize(nrows + 1);
+  const int warps_per_block = 8;
+  const int blocks = (nrows + warps_per_block - 1) / warps_per_block;
+  if (nrows > 0)
+    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, bin_start.p, g, nrows, cut, reach, cnt.p, nullptr, nullptr);
+  cntll.resize(nrows + 1);
+  k_cnt_to_ll<<<(nrows + 256) / 256, 256, 0, st>>>(cnt.p, nrows, cntll.p);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, cntll.p, out.off.p, nrows + 1, st);
+  temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(temp.p, need, cntll.p, out.off.p, nrows + 1, st);
+  long long total = 0;
+  RXB_CUDA(cudaMemcpyAsync(&total, out.off.p + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  RXB_CUDA(cudaStreamSynchronize(st));
+  out.nnz = total;
+  out.nrows = nrows;
+  out.idx.resize((size_t)(total > 0 ? total : 1));
+  if (nrows > 0)
+    k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, bin_start.p, g, nrows, cut, reach, nullptr, out.off.p, out.idx.p);
+  RXB_CUDA(cudaGetLastError());
+}
+
+}  // namespace rxb

@@ -1,0 +1,205 @@
+// Per-step far-neighbour filter fused with the QEq H-matrix build, and the tapered vdW/Coulomb kernel.
+//
+//   K-farH : write_reax_lists_c (r <= nonb_cut filter)   /root/reference/pair_reaxc_sw64.c:49-95,193-341
+//            + compute_H_Full_C / calculate_H            /root/reference/fix_qeq_reax_sw64.c:147-189, fix_qeq_reax_sunway.cpp:965-981
+//            The reference materialises 64-byte far_neighbor_data_full records (29 KB/atom/step) AND a separate
+//            600-wide H row; here both are ONE compacted int32 column list (+ one fp64 value) in the slots of the
+//            Verlet row, because "r <= nonb_cut" and "r <= swb" select the same pairs (both 10 A in every shipped
+//            input; if they differ the list takes the larger cut-off and each consumer re-tests its own).
+//   K-nb   : vdW_Coulomb_Energy_Full_C                   /root/reference/reaxc_nonbonded_sw64.c:40-258 (serial twin)
+//            full list, local i only, force on i only (no scatter), 1/2 energy per directed pair,
+//            pair virial + (-x_i (x) f_i) correction as reaxc_nonbonded_cpe.h:531-536 / reaxc_nonbonded_sw64.c:247-252.
+// Roofline: K-farH is HBM-bound (4 B/Verlet entry read, 12 B/far entry written); K-nb is fp64-compute bound
+// (2 pow + 2 exp + 1 cube-root-like pow per pair).
+#include "rxb_system.h"
+
+namespace rxb {
+namespace {
+
+constexpr double kCele = 332.06371;  // C_ele
+constexpr double kEvToKcal = 14.4;   // EV_TO_KCAL_PER_MOL
+constexpr int kWarps = 8;
+constexpr int kBlocks = 148 * 8;
+
+__device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+struct QeqConst { double Tap[8]; double swb2; double far2; };
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  for (int i = wg; i < v.n; i += nwg) {
+    const double4 pi = v.xq[i];
+    const int ti = v.type[i];
+    const long long beg = v.vl_off[i], end = v.vl_off[i + 1];
+    long long w = beg;
+    for (long long k0 = beg; k0 < end; k0 += 32) {
+      const long long k = k0 + lane;
+      bool hit = false;
+      int j = 0;
+      double val = 0.0;
+      if (k < end) {
+        j = v.vl_idx[k];
+        const double4 pj = v.xq[j];
+        const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
+        hit = r2 <= qc.far2;
+        if (hit && r2 <= qc.swb2) {
+          const int tj = v.type[j];
+          if (ti >= 0 && tj >= 0) {
+            const double r = sqrt(r2);
+            double T = qc.Tap[7] * r + qc.Tap[6];
+            T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
+            T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
+            const double denom = pow(r * r * r + shld[ti * nt + tj], 0.3333333333333);
+            val = T * kEvToKcal / denom;
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const long long o = w + __popc(m & ((1u << lane) - 1));
+        v.far_idx[o] = j;
+        v.H_val[o] = val;
+      }
+      w += __popc(m);
+    }
+    if (lane == 0) v.far_num[i] = (int)(w - beg);
+  }
+}
+
+template <bool EV>
+__global__ void __launch_bounds__(kWarps * 32)
+k_nonbonded(DevView v, DevParams P) {
+  __shared__ double sh[8][kWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double p_vdW1 = P.gp[28], p_vdW1i = 1.0 / p_vdW1;
+  const double nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
+  const int vdw_type = P.ctl.vdw_type, lgflag = P.ctl.lgflag, nt = P.nt;
+  double Tap[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) Tap[t] = P.ctl.Tap[t];
+  double e_vdw = 0, e_ele = 0, vir[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = wg; i < v.n; i += nwg) {
+    const int ti = v.type[i];
+    if (ti < 0) continue;
+    const double4 pi = v.xq[i];
+    const long long beg = v.vl_off[i];
+    const int num = v.far_num[i];
+    double fx = 0, fy = 0, fz = 0;
+    for (int k0 = 0; k0 < num; k0 += 32) {
+      const int k = k0 + lane;
+      if (k >= num) continue;
+      const int j = v.far_idx[beg + k];
+      const int tj = v.type[j];
+      if (tj < 0) continue;
+      const double4 pj = v.xq[j];
+      const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      const double r2 = dist2_rn(dx, dy, dz);
+      if (!(r2 <= nonb_cut2)) continue;
+      const double r_ij = sqrt(r2);
+      const PairPar& tw = P.pair[ti * nt + tj];
+      double T = Tap[7] * r_ij + Tap[6];
+      T = T * r_ij + Tap[5]; T = T * r_ij + Tap[4]; T = T * r_ij + Tap[3];
+      T = T * r_ij + Tap[2]; T = T * r_ij + Tap[1]; T = T * r_ij + Tap[0];
+      double dT = 7 * Tap[7] * r_ij + 6 * Tap[6];
+      dT = dT * r_ij + 5 * Tap[5]; dT = dT * r_ij + 4 * Tap[4]; dT = dT * r_ij + 3 * Tap[3];
+      dT = dT * r_ij + 2 * Tap[2];
+      dT += Tap[1] / r_ij;
+      double e_vdW, CEvd, e_core = 0, e_lg = 0;
+      if (vdw_type == 1 || vdw_type == 3) {
+        const double powr = pow(r_ij, p_vdW1);
+        const double powgi = tw.powgi_vdW1;
+        const double fn13 = pow(powr + powgi, p_vdW1i);
+        const double exp1 = exp(tw.alpha * (1.0 - fn13 / tw.r_vdW));
+        const double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 / tw.r_vdW));
+        e_vdW = tw.D * (exp1 - 2.0 * exp2);
+        const double dfn13 = pow(powr + powgi, p_vdW1i - 1.0) * pow(r_ij, p_vdW1 - 2.0);
+        CEvd = dT * e_vdW - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) * dfn13;
+      } else {
+        const double exp1 = exp(tw.alpha * (1.0 - r_ij / tw.r_vdW));
+        const double exp2 = exp(0.5 * tw.alpha * (1.0 - r_ij / tw.r_vdW));
+        e_vdW = tw.D * (exp1 - 2.0 * exp2);
+        CEvd = dT * e_vdW - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) / r_ij;
+      }
+      if (vdw_type == 2 || vdw_type == 3) {
+        e_core = tw.ecore * exp(tw.acore * (1.0 - (r_ij / tw.rcore)));
+        const double de_core = -(tw.acore / tw.rcore) * e_core;
+        CEvd += dT * e_core + T * de_core / r_ij;
+        if (lgflag) {
+          const double r5 = pow(r_ij, 5.0), r6 = pow(r_ij, 6.0), re6 = pow(tw.lgre, 6.0);
+          e_lg = -(tw.lgcij / (r6 + re6));
+          const double de_lg = -6.0 * e_lg * r5 / (r6 + re6);
+          CEvd += dT * e_lg + T * de_lg / r_ij;
+        }
+      }
+      const double dr3gamij_1 = r_ij * r_ij * r_ij + tw.gamma;
+      const double dr3gamij_3 = pow(dr3gamij_1, 0.33333333333333);
+      const double qq = kCele * pi.w * pj.w;
+      const double CEclmb = qq * (dT - T * r_ij / dr3gamij_1) / dr3gamij_3;
+      const double ftot = CEvd + CEclmb;  // f_i = +ftot * dvec  (reference: fCdDelta[i] += -ftot*dvec, f = -fCdDelta)
+      fx += ftot * dx; fy += ftot * dy; fz += ftot * dz;
+      if (EV) {
+        e_vdw += 0.5 * T * (e_vdW + e_core + e_lg);
+        e_ele += 0.5 * qq * (T / dr3gamij_3);
+        const double fpair = -ftot;
+        vir[0] += 0.5 * dx * dx * fpair; vir[1] += 0.5 * dy * dy * fpair; vir[2] += 0.5 * dz * dz * fpair;
+        vir[3] += 0.5 * dx * dy * fpair; vir[4] += 0.5 * dx * dz * fpair; vir[5] += 0.5 * dy * dz * fpair;
+      }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+      // only writer of f[i] so far in the step for local i would be a plain store, but bonded kernels may run
+      // concurrently on another stream: keep it an atomic
+      atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
+      if (EV) {  // -x_i (x) f_i^nb : cancels this kernel's share of the later f.x sum over all atoms
+        vir[0] -= pi.x * fx; vir[1] -= pi.y * fy; vir[2] -= pi.z * fz;
+        vir[3] -= pi.x * fy; vir[4] -= pi.x * fz; vir[5] -= pi.y * fz;
+      }
+    }
+  }
+  if (EV) {
+    double vals[8] = {e_vdw, e_ele, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5]};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double s = warp_sum(vals[k]);
+      if (lane == 0) sh[k][wib] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double s = 0;
+      for (int w = 0; w < kWarps; w++) s += sh[threadIdx.x][w];
+      if (s != 0.0) {
+        if (threadIdx.x == 0) atomicAdd(&v.en[E_VDW], s);
+        else if (threadIdx.x == 1) atomicAdd(&v.en[E_ELE], s);
+        else atomicAdd(&v.virial[threadIdx.x - 2], s);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* qeq_tap, const double* shld, double swb,
+                      cudaStream_t st) {
+  if (v.n == 0) return;
+  QeqConst qc;
+  for (int t = 0; t < 8; t++) qc.Tap[t] = qeq_tap[t];
+  qc.swb2 = swb * swb;
+  const double far = swb > P.ctl.nonb_cut ? swb : P.ctl.nonb_cut;
+  qc.far2 = far * far;
+  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld);
+  s.kernel_launches++;
+}
+
+void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st) {
+  if (v.n == 0) return;
+  if (evflag) k_nonbonded<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  else k_nonbonded<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  s.kernel_launches++;
+}
+
+}  // namespace rxb

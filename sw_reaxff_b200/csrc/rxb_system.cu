@@ -1,0 +1,564 @@
+// System: device-resident state + launch sequence of one timestep (see rxb_system.h).
+//
+// Step order follows the reference's Verlet/Compute_Forces order:
+//   fix nve initial -> [reneighbour | ghost forward] -> qeq pre_force -> pair compute
+//   (Reset -> bond list -> nonbonded -> BO -> multi-body -> hbonds -> valence/torsion -> dBond) -> reverse -> nve final
+// /root/reference/pair_reaxc_sunway.cpp:541-793, reaxc_forces_sunway.cpp:1297-1365, fix_nve_sw64.c:43-170.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <unordered_map>
+
+#include "rxb_system.h"
+
+namespace rxb {
+
+namespace {
+
+constexpr double kFtm2v = 1.0 / 48.88821291 / 48.88821291;  // LAMMPS units real
+constexpr double kMvv2e = 48.88821291 * 48.88821291;
+
+__global__ void k_set_xyz(int N, const double* __restrict__ x, double4* __restrict__ xq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double4 p = xq[i];
+  p.x = x[3 * i]; p.y = x[3 * i + 1]; p.z = x[3 * i + 2];
+  xq[i] = p;
+}
+__global__ void k_set_q(int N, const double* __restrict__ q, double4* __restrict__ xq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) xq[i].w = q[i];
+}
+__global__ void k_get_q(int N, const double4* __restrict__ xq, double* __restrict__ q) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) q[i] = xq[i].w;
+}
+__global__ void k_get_xyz(int N, const double4* __restrict__ xq, double* __restrict__ x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double4 p = xq[i];
+  x[3 * i] = p.x; x[3 * i + 1] = p.y; x[3 * i + 2] = p.z;
+}
+
+// virial_fdotr over all atoms, pair_reaxc_sunway.cpp:674-702
+__global__ void k_fdotr(int N, const double4* __restrict__ xq, const double* __restrict__ f, double* __restrict__ virial) {
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const double4 p = xq[i];
+    const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
+    v[0] += fx * p.x; v[1] += fy * p.y; v[2] += fz * p.z;
+    v[3] += fy * p.x; v[4] += fz * p.x; v[5] += fz * p.y;
+  }
+  for (int k = 0; k < 6; k++) {
+    const double s = warp_sum(v[k]);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(&virial[k], s);
+  }
+}
+
+// ---- mini LAMMPS core on the device ----
+struct BoxD { double h[6], h_inv[6]; };
+
+__device__ __forceinline__ void x2lamda(const BoxD& b, double x, double y, double z, double* l) {
+  l[0] = b.h_inv[0] * x + b.h_inv[5] * y + b.h_inv[4] * z;
+  l[1] = b.h_inv[1] * y + b.h_inv[3] * z;
+  l[2] = b.h_inv[2] * z;
+}
+__device__ __forceinline__ void shift_vec(const BoxD& b, int sx, int sy, int sz, double* d) {
+  d[0] = sx * b.h[0] + sy * b.h[5] + sz * b.h[4];
+  d[1] = sy * b.h[1] + sz * b.h[3];
+  d[2] = sz * b.h[2];
+}
+
+__global__ void k_remap(int n, BoxD b, double4* __restrict__ xq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = xq[i];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  const int s0 = (int)floor(l[0]), s1 = (int)floor(l[1]), s2 = (int)floor(l[2]);
+  if (s0 | s1 | s2) {
+    double d[3];
+    shift_vec(b, s0, s1, s2, d);
+    p.x -= d[0]; p.y -= d[1]; p.z -= d[2];
+    xq[i] = p;
+  }
+}
+
+// periodic-image ghosts out to cutghost (LAMMPS Comm::borders semantics, single rank)
+template <bool FILL>
+__global__ void k_ghosts(int n, BoxD b, double cg0, double cg1, double cg2, int m0, int m1, int m2,
+                         double4* __restrict__ xq, int* __restrict__ type, int* __restrict__ tag, int* __restrict__ ltype,
+                         long long* __restrict__ count, const long long* __restrict__ off, int* __restrict__ owner,
+                         int* __restrict__ shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  int c = 0;
+  long long w = FILL ? off[i] : 0;
+  for (int sz = -m2; sz <= m2; sz++) {
+    const double l2 = l[2] + sz;
+    if (!(l2 >= -cg2 && l2 < 1.0 + cg2)) continue;
+    for (int sy = -m1; sy <= m1; sy++) {
+      const double l1 = l[1] + sy;
+      if (!(l1 >= -cg1 && l1 < 1.0 + cg1)) continue;
+      for (int sx = -m0; sx <= m0; sx++) {
+        if (!sx && !sy && !sz) continue;
+        const double l0 = l[0] + sx;
+        if (!(l0 >= -cg0 && l0 < 1.0 + cg0)) continue;
+        if (FILL) {
+          double d[3];
+          shift_vec(b, sx, sy, sz, d);
+          const long long g = n + w;
+          xq[g] = make_double4(p.x + d[0], p.y + d[1], p.z + d[2], p.w);
+          type[g] = type[i]; tag[g] = tag[i]; ltype[g] = ltype[i];
+          owner[w] = i;
+          shift[3 * w] = sx; shift[3 * w + 1] = sy; shift[3 * w + 2] = sz;
+          w++;
+        } else {
+          c++;
+        }
+      }
+    }
+  }
+  if (!FILL) count[i] = c;
+}
+
+__global__ void k_forward_x(int n, int nghost, BoxD b, const int* __restrict__ owner, const int* __restrict__ shift,
+                            double4* __restrict__ xq) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int o = owner[g];
+  if (o < 0) return;
+  double d[3];
+  shift_vec(b, shift[3 * g], shift[3 * g + 1], shift[3 * g + 2], d);
+  const double4 p = xq[o];
+  xq[n + g] = make_double4(p.x + d[0], p.y + d[1], p.z + d[2], p.w);
+}
+
+__global__ void k_reverse_f(int n, int nghost, const int* __restrict__ owner, double* __restrict__ f) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int o = owner[g];
+  if (o < 0) return;
+  const double fx = f[3 * (n + g)], fy = f[3 * (n + g) + 1], fz = f[3 * (n + g) + 2];
+  if (fx != 0.0) atomicAdd(&f[3 * o], fx);
+  if (fy != 0.0) atomicAdd(&f[3 * o + 1], fy);
+  if (fz != 0.0) atomicAdd(&f[3 * o + 2], fz);
+}
+
+// fix nve, fix_nve_sw64.c:43-99 (per-type mass branch)
+__global__ void k_nve_initial(int n, double dtf, double dtv, const int* __restrict__ ltype, const double* __restrict__ mass,
+                              const double* __restrict__ f, double* __restrict__ vel, double4* __restrict__ xq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dtfm = dtf / mass[ltype[i]];
+  double4 p = xq[i];
+  double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+  vx += dtfm * f[3 * i]; vy += dtfm * f[3 * i + 1]; vz += dtfm * f[3 * i + 2];
+  p.x += dtv * vx; p.y += dtv * vy; p.z += dtv * vz;
+  vel[3 * i] = vx; vel[3 * i + 1] = vy; vel[3 * i + 2] = vz;
+  xq[i] = p;
+}
+__global__ void k_nve_final(int n, double dtf, const int* __restrict__ ltype, const double* __restrict__ mass,
+                            const double* __restrict__ f, double* __restrict__ vel) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double dtfm = dtf / mass[ltype[i]];
+  vel[3 * i] += dtfm * f[3 * i]; vel[3 * i + 1] += dtfm * f[3 * i + 1]; vel[3 * i + 2] += dtfm * f[3 * i + 2];
+}
+__global__ void k_kinetic(int n, const int* __restrict__ ltype, const double* __restrict__ mass, const double* __restrict__ vel,
+                          double* __restrict__ out) {
+  double ke = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    ke += mass[ltype[i]] * (vel[3 * i] * vel[3 * i] + vel[3 * i + 1] * vel[3 * i + 1] + vel[3 * i + 2] * vel[3 * i + 2]);
+  ke = warp_sum(ke);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, ke);
+}
+
+inline int nblk(long n, int t = 256) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+void Box::set(double xprd, double yprd, double zprd, double xy, double xz, double yz) {
+  h[0] = xprd; h[1] = yprd; h[2] = zprd; h[3] = yz; h[4] = xz; h[5] = xy;
+  h_inv[0] = 1.0 / h[0]; h_inv[1] = 1.0 / h[1]; h_inv[2] = 1.0 / h[2];
+  h_inv[3] = -h[3] / (h[1] * h[2]);
+  h_inv[4] = (h[3] * h[5] - h[1] * h[4]) / (h[0] * h[1] * h[2]);
+  h_inv[5] = -h[5] / (h[0] * h[1]);
+}
+
+System::System(int device) : device_(device) {
+  RXB_CUDA(cudaSetDevice(device));
+  RXB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+  RXB_CUDA(cudaEventCreate(&ev_[0]));
+  RXB_CUDA(cudaEventCreate(&ev_[1]));
+  b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6);
+  RXB_CUDA(cudaMemset(overflow.p, 0, sizeof(int)));
+}
+
+System::~System() {
+  cudaSetDevice(device_);
+  if (h_pin_) cudaFreeHost(h_pin_);
+  cudaEventDestroy(ev_[0]);
+  cudaEventDestroy(ev_[1]);
+  if (st_) cudaStreamDestroy(st_);
+}
+
+double* System::pin(size_t doubles) {
+  if (doubles > h_pin_cap_) {
+    if (h_pin_) cudaFreeHost(h_pin_);
+    h_pin_cap_ = doubles + doubles / 4 + 1024;
+    RXB_CUDA(cudaMallocHost(&h_pin_, h_pin_cap_ * sizeof(double)));
+  }
+  return h_pin_;
+}
+
+void System::tick(int) {
+  if (profile) RXB_CUDA(cudaEventRecord(ev_[0], st_));
+}
+void System::tock(int which) {
+  if (!profile) return;
+  RXB_CUDA(cudaEventRecord(ev_[1], st_));
+  RXB_CUDA(cudaEventSynchronize(ev_[1]));
+  float ms = 0;
+  RXB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+  timers.ms[which] += ms;
+  timers.calls[which]++;
+}
+
+void System::upload_params() {
+  RXB_CUDA(cudaSetDevice(device_));
+  ff.derive();
+  const int nt = ff.nt;
+  size_t o_gp = 0;
+  size_t o_atom = o_gp + ((ff.gp.size() * sizeof(double) + 31) / 32) * 32;
+  size_t o_pair = o_atom + ((ff.atom.size() * sizeof(AtomPar) + 31) / 32) * 32;
+  size_t o_angle = o_pair + ((ff.pair.size() * sizeof(PairPar) + 31) / 32) * 32;
+  size_t o_tors = o_angle + ((ff.angle.size() * sizeof(AngleSet) + 31) / 32) * 32;
+  size_t o_hb = o_tors + ((ff.tors.size() * sizeof(TorsPar) + 31) / 32) * 32;
+  size_t total = o_hb + ff.hb.size() * sizeof(HbPar) + 64;
+  std::vector<char> blob(total, 0);
+  memcpy(blob.data() + o_gp, ff.gp.data(), ff.gp.size() * sizeof(double));
+  memcpy(blob.data() + o_atom, ff.atom.data(), ff.atom.size() * sizeof(AtomPar));
+  memcpy(blob.data() + o_pair, ff.pair.data(), ff.pair.size() * sizeof(PairPar));
+  memcpy(blob.data() + o_angle, ff.angle.data(), ff.angle.size() * sizeof(AngleSet));
+  memcpy(blob.data() + o_tors, ff.tors.data(), ff.tors.size() * sizeof(TorsPar));
+  memcpy(blob.data() + o_hb, ff.hb.data(), ff.hb.size() * sizeof(HbPar));
+  param_blob_.resize(total);
+  RXB_CUDA(cudaMemcpy(param_blob_.p, blob.data(), total, cudaMemcpyHostToDevice));
+  dp_.nt = nt;
+  dp_.ctl = ff.ctl;
+  dp_.gp = reinterpret_cast<const double*>(param_blob_.p + o_gp);
+  dp_.atom = reinterpret_cast<const AtomPar*>(param_blob_.p + o_atom);
+  dp_.pair = reinterpret_cast<const PairPar*>(param_blob_.p + o_pair);
+  dp_.angle = reinterpret_cast<const AngleSet*>(param_blob_.p + o_angle);
+  dp_.tors = reinterpret_cast<const TorsPar*>(param_blob_.p + o_tors);
+  dp_.hb = reinterpret_cast<const HbPar*>(param_blob_.p + o_hb);
+  // fix qeq/reax shielding: shld = (gamma_i gamma_j)^-1.5 from Pair::extract("gamma"), fix_qeq_reax_sunway.cpp:440-454
+  std::vector<double> sh((size_t)nt * nt);
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j < nt; j++) sh[(size_t)i * nt + j] = pow(ff.atom[i].gamma * ff.atom[j].gamma, -1.5);
+  shld_d.resize(sh.size());
+  RXB_CUDA(cudaMemcpy(shld_d.p, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+double System::cutneigh() const {
+  const Control& c = ff.ctl;
+  const double cutmax = std::max(c.nonb_cut, std::max(c.hbond_cut, 2 * c.bond_cut));  // pair_reaxc_sunway.cpp:410
+  return std::max(cutmax, qeq_swb) + skin;
+}
+
+void System::ensure_atom_capacity() {
+  const size_t NN = N;
+  xq.resize_keep(NN); type.resize_keep(NN); tag.resize_keep(NN); ltype_d.resize_keep(NN);
+  f.resize(3 * NN); CdDelta.resize(NN);
+  b_start.resize(NN); b_cnt.resize(NN);
+  total_bop.resize(NN); Deltap.resize(NN); dDeltap_self.resize(3 * NN); total_bo.resize(NN); Delta_boc.resize(NN);
+  Delta.resize(NN); Delta_val.resize(NN); vlpex.resize(NN); nlp.resize(NN); Delta_lp.resize(NN); dDelta_lp.resize(NN);
+  Delta_lp_temp.resize(NN);
+  far_num.resize(n > 0 ? n : 1);
+  if (cap_bonds < (int)std::min<size_t>(NN * 14 + 1024, 2000000000)) ensure_bond_capacity((int)std::min<size_t>(NN * 14 + 1024, 2000000000));
+}
+
+void System::ensure_bond_capacity(int cap) {
+  if (cap <= cap_bonds) return;
+  const size_t c = cap;
+  b_nbr.resize(c); b_sym.resize(c); b_geo.resize(c); b_bo.resize(c); b_der.resize(c); b_c1.resize(c); b_c2.resize(c);
+  b_c3.resize(c); b_Cdbo.resize(c); b_Cdbopi.resize(c); b_Cdbopi2.resize(c);
+  cap_bonds = cap;
+}
+
+void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype, const int* tg, const double* q,
+                       const int* owner_in) {
+  RXB_CUDA(cudaSetDevice(device_));
+  n = nlocal; N = nlocal + nghost;
+  ensure_atom_capacity();
+  std::vector<double4> hx(N);
+  std::vector<int> ht(N), hown(std::max(nghost, 1), -1);
+  for (int i = 0; i < N; i++) {
+    hx[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], q ? q[i] : 0.0);
+    const int lt = ltype[i];
+    ht[i] = (lt >= 1 && lt < (int)ff.map.size()) ? ff.map[lt] : -1;
+  }
+  if (owner_in) {
+    for (int g = 0; g < nghost; g++) hown[g] = owner_in[g];
+  } else {  // single-rank LAMMPS: the ghost's owner is the local atom with the same tag (atom->map)
+    std::unordered_map<int, int> by_tag;
+    by_tag.reserve(nlocal * 2);
+    for (int i = 0; i < nlocal; i++) by_tag.emplace(tg[i], i);
+    for (int g = 0; g < nghost; g++) {
+      auto it = by_tag.find(tg[nlocal + g]);
+      hown[g] = it == by_tag.end() ? -1 : it->second;
+    }
+  }
+  ghost_owner.resize(std::max(nghost, 1));
+  RXB_CUDA(cudaMemcpyAsync(xq.p, hx.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(type.p, ht.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(tag.p, tg, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(ltype_d.p, ltype, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(ghost_owner.p, hown.data(), hown.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void System::set_positions(const double* x_host) {
+  RXB_CUDA(cudaSetDevice(device_));
+  double* pp = pin((size_t)3 * N);
+  memcpy(pp, x_host, (size_t)3 * N * sizeof(double));
+  x_stage.resize((size_t)3 * N);
+  RXB_CUDA(cudaMemcpyAsync(x_stage.p, pp, (size_t)3 * N * sizeof(double), cudaMemcpyHostToDevice, st_));
+  k_set_xyz<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, xq.p);
+  kernel_launches++;
+}
+
+void System::set_charges(const double* q_host) {
+  RXB_CUDA(cudaSetDevice(device_));
+  double* pp = pin((size_t)N);
+  memcpy(pp, q_host, (size_t)N * sizeof(double));
+  x_stage.resize((size_t)3 * N);
+  RXB_CUDA(cudaMemcpyAsync(x_stage.p, pp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st_));
+  k_set_q<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, xq.p);
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  kernel_launches++;
+}
+
+void System::get_forces(double* f_host) {
+  RXB_CUDA(cudaSetDevice(device_));
+  double* pp = pin((size_t)3 * N);
+  RXB_CUDA(cudaMemcpyAsync(pp, f.p, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  memcpy(f_host, pp, (size_t)3 * N * sizeof(double));
+}
+
+void System::get_charges(double* q_host) {
+  RXB_CUDA(cudaSetDevice(device_));
+  x_stage.resize((size_t)3 * N);
+  k_get_q<<<nblk(N), 256, 0, st_>>>(N, xq.p, x_stage.p);
+  double* pp = pin((size_t)N);
+  RXB_CUDA(cudaMemcpyAsync(pp, x_stage.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  memcpy(q_host, pp, (size_t)N * sizeof(double));
+  kernel_launches++;
+}
+
+DevView System::view() {
+  DevView v{};
+  v.n = n; v.N = N; v.cap_bonds = cap_bonds;
+  v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
+  v.vl_off = vl.off.p; v.vl_idx = vl.idx.p;
+  v.bc_off = bc.off.p; v.bc_idx = bc.idx.p;
+  v.hc_off = nullptr; v.hc_idx = nullptr;
+  v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
+  v.b_start = b_start.p; v.b_cnt = b_cnt.p; v.b_cursor = b_cursor.p; v.overflow = overflow.p;
+  v.b_nbr = b_nbr.p; v.b_sym = b_sym.p; v.b_geo = b_geo.p; v.b_bo = b_bo.p; v.b_der = b_der.p;
+  v.b_c1 = b_c1.p; v.b_c2 = b_c2.p; v.b_c3 = b_c3.p;
+  v.b_Cdbo = b_Cdbo.p; v.b_Cdbopi = b_Cdbopi.p; v.b_Cdbopi2 = b_Cdbopi2.p;
+  v.total_bop = total_bop.p; v.Deltap = Deltap.p; v.dDeltap_self = dDeltap_self.p; v.total_bo = total_bo.p;
+  v.Delta_boc = Delta_boc.p; v.Delta = Delta.p; v.Delta_val = Delta_val.p; v.vlpex = vlpex.p; v.nlp = nlp.p;
+  v.Delta_lp = Delta_lp.p; v.dDelta_lp = dDelta_lp.p; v.Delta_lp_temp = Delta_lp_temp.p;
+  v.en = en_d.p; v.virial = virial_d.p;
+  return v;
+}
+
+void System::build_neighbors() {
+  RXB_CUDA(cudaSetDevice(device_));
+  tick(StepTimers::NEIGH);
+  const double cn = cutneigh();
+  // Verlet list for local rows: bins of cn/2, +-2 cells
+  cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
+  cells_a_.build(xq.p, n, cn, vl, st_);
+  // bond candidates for all rows (ghosts too): bond_cut + skin
+  const double cb = ff.ctl.bond_cut + skin;
+  cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
+  cells_b_.build(xq.p, N, cb, bc, st_);
+  far_idx.resize((size_t)std::max<long long>(vl.nnz, 1));
+  H_val.resize((size_t)std::max<long long>(vl.nnz, 1));
+  kernel_launches += 12;
+  tock(StepTimers::NEIGH);
+}
+
+void System::step_forces(bool eflag, bool vflag) {
+  DevView v = view();
+  RXB_CUDA(cudaMemsetAsync(f.p, 0, (size_t)3 * N * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(en_d.p, 0, E_NUM * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, 6 * sizeof(double), st_));
+  tick(StepTimers::BONDS);
+  launch_bond_list(*this, v, dp_, st_);
+  tock(StepTimers::BONDS);
+  tick(StepTimers::NONB);
+  launch_nonbonded(*this, v, dp_, eflag || vflag, st_);
+  tock(StepTimers::NONB);
+  tick(StepTimers::BO);
+  launch_bond_orders(*this, v, dp_, st_);
+  tock(StepTimers::BO);
+  tick(StepTimers::BONDED);
+  launch_bonded(*this, v, dp_, st_);
+  tock(StepTimers::BONDED);
+  tick(StepTimers::DBOND);
+  launch_dbond(*this, v, dp_, st_);
+  tock(StepTimers::DBOND);
+  if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
+}
+
+void System::compute(bool eflag, bool vflag) {
+  RXB_CUDA(cudaSetDevice(device_));
+  if (!qeq_ran_this_step_) {
+    // pair style without fix qeq/reax this step (checkqeq no): the far list is still needed
+    DevView v = view();
+    double Tap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    launch_far_and_H(*this, v, dp_, Tap, shld_d.p, 0.0, st_);
+  }
+  qeq_ran_this_step_ = false;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    step_forces(eflag, vflag);
+    int h[2];
+    RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    if (eflag || vflag) {
+      RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
+      RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    }
+    RXB_CUDA(cudaStreamSynchronize(st_));
+    num_bonds = h[0];
+    overflow_flag = h[1];
+    if (!(overflow_flag & 2)) break;
+    // bond rows did not fit: grow and replay the force computation of this step (positions are unchanged)
+    RXB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st_));
+    ensure_bond_capacity((int)std::min<long long>((long long)h[0] + h[0] / 4 + 1024, 2000000000LL));
+  }
+  if (overflow_flag & ~2)
+    throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void System::md_setup(const double* box6, int nlocal, const double* x, const double* v, const int* ltype, const int* tg,
+                      const double* mass_by_type, int ntypes, double dt, int every) {
+  RXB_CUDA(cudaSetDevice(device_));
+  box.set(box6[0], box6[1], box6[2], box6[3], box6[4], box6[5]);
+  md_dt = dt; md_every = every; md_ago = 0; ntimestep = 0;
+  std::vector<double> q0(nlocal, 0.0);
+  set_atoms(nlocal, 0, x, ltype, tg, q0.data(), nullptr);
+  v_d.resize((size_t)3 * nlocal);
+  RXB_CUDA(cudaMemcpy(v_d.p, v, (size_t)3 * nlocal * sizeof(double), cudaMemcpyHostToDevice));
+  mass_d.resize(ntypes + 1);
+  RXB_CUDA(cudaMemcpy(mass_d.p, mass_by_type, (size_t)(ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  qeq_reset_history();
+  md_make_ghosts();
+  build_neighbors();
+  md_force();
+}
+
+void System::md_make_ghosts() {
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  const double cut = cutneigh();
+  const double cg0 = cut * sqrt(b.h_inv[0] * b.h_inv[0] + b.h_inv[5] * b.h_inv[5] + b.h_inv[4] * b.h_inv[4]);
+  const double cg1 = cut * sqrt(b.h_inv[1] * b.h_inv[1] + b.h_inv[3] * b.h_inv[3]);
+  const double cg2 = cut * b.h_inv[2];
+  const int m0 = (int)ceil(cg0), m1 = (int)ceil(cg1), m2 = (int)ceil(cg2);
+  k_remap<<<nblk(n), 256, 0, st_>>>(n, b, xq.p);
+  gcount.resize(n + 1); goff.resize(n + 1);
+  k_ghosts<false><<<nblk(n), 256, 0, st_>>>(n, b, cg0, cg1, cg2, m0, m1, m2, xq.p, type.p, tag.p, ltype_d.p, gcount.p, nullptr,
+                                           nullptr, nullptr);
+  RXB_CUDA(cudaMemsetAsync(gcount.p + n, 0, sizeof(long long), st_));
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, gcount.p, goff.p, n + 1, st_);
+  scan_temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(scan_temp.p, need, gcount.p, goff.p, n + 1, st_);
+  long long nghost = 0;
+  RXB_CUDA(cudaMemcpyAsync(&nghost, goff.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  N = n + (int)nghost;
+  ensure_atom_capacity();
+  ghost_owner.resize(std::max<size_t>(nghost, 1));
+  ghost_shift.resize(std::max<size_t>(3 * nghost, 3));
+  k_ghosts<true><<<nblk(n), 256, 0, st_>>>(n, b, cg0, cg1, cg2, m0, m1, m2, xq.p, type.p, tag.p, ltype_d.p, nullptr, goff.p,
+                                          ghost_owner.p, ghost_shift.p);
+  kernel_launches += 5;
+  RXB_CUDA(cudaGetLastError());
+}
+
+void System::md_force() {
+  if (qeq_on) qeq_pre_force();
+  const bool ev = md_thermo > 0 && (ntimestep % md_thermo == 0);
+  compute(ev, ev);
+  const int nghost = N - n;
+  if (nghost > 0) { k_reverse_f<<<nblk(nghost), 256, 0, st_>>>(n, nghost, ghost_owner.p, f.p); kernel_launches++; }
+}
+
+void System::md_run(int nsteps) {
+  RXB_CUDA(cudaSetDevice(device_));
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  const double dtv = md_dt, dtf = 0.5 * md_dt * kFtm2v;
+  for (int s = 0; s < nsteps; s++) {
+    ntimestep++;
+    k_nve_initial<<<nblk(n), 256, 0, st_>>>(n, dtf, dtv, ltype_d.p, mass_d.p, f.p, v_d.p, xq.p);
+    md_ago++;
+    if (md_ago % md_every == 0) {
+      md_make_ghosts();
+      build_neighbors();
+      md_ago = 0;
+    } else if (N > n) {
+      k_forward_x<<<nblk(N - n), 256, 0, st_>>>(n, N - n, b, ghost_owner.p, ghost_shift.p, xq.p);
+    }
+    md_force();
+    k_nve_final<<<nblk(n), 256, 0, st_>>>(n, dtf, ltype_d.p, mass_d.p, f.p, v_d.p);
+    kernel_launches += 3;
+  }
+  RXB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void System::md_get(double* x, double* v, double* fo, double* q) {
+  RXB_CUDA(cudaSetDevice(device_));
+  x_stage.resize((size_t)3 * N);
+  if (x) {
+    k_get_xyz<<<nblk(n), 256, 0, st_>>>(n, xq.p, x_stage.p);
+    RXB_CUDA(cudaMemcpyAsync(x, x_stage.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaStreamSynchronize(st_));
+  }
+  if (v) RXB_CUDA(cudaMemcpy(v, v_d.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (fo) RXB_CUDA(cudaMemcpy(fo, f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (q) {
+    k_get_q<<<nblk(n), 256, 0, st_>>>(n, xq.p, x_stage.p);
+    RXB_CUDA(cudaMemcpyAsync(q, x_stage.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaStreamSynchronize(st_));
+  }
+}
+
+double System::md_kinetic() {
+  RXB_CUDA(cudaSetDevice(device_));
+  RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, sizeof(double), st_));
+  k_kinetic<<<148 * 2, 256, 0, st_>>>(n, ltype_d.p, mass_d.p, v_d.p, virial_d.p);
+  double ke = 0;
+  RXB_CUDA(cudaMemcpyAsync(&ke, virial_d.p, sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  return 0.5 * kMvv2e * ke;
+}
+
+}  // namespace rxb

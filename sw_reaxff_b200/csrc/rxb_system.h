@@ -1,0 +1,209 @@
+// Host-side owner of all device-resident state of the B200 ReaxFF path and the launch sequence of one timestep.
+// Plays the role of the reference's reax_system + storage + reax_list[] + the *_sunway.cpp drivers
+// (pair_reaxc_sunway.cpp:434-793, reaxc_forces_sunway.cpp:1297-1365, fix_qeq_reax_sunway.cpp:539-600),
+// re-designed for residency: buffers are grown, never re-allocated per step, and nothing returns to the host
+// inside a step except a few scalars.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rxb_dev.cuh"
+#include "rxb_params.h"
+
+#define RXB_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + \
+                               std::to_string(__LINE__));                                                \
+  } while (0)
+
+namespace rxb {
+
+template <class T>
+struct DBuf {  // grow-only device buffer (contents are NOT preserved across growth unless resize_keep is used)
+  T* p = nullptr;
+  size_t cap = 0, n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { if (p) cudaFree(p); }
+  void resize(size_t m) {
+    if (m > cap) {
+      if (p) cudaFree(p);
+      size_t want = m + m / 8 + 64;
+      RXB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+      cap = want;
+    }
+    n = m;
+  }
+  void resize_keep(size_t m) {
+    if (m > cap) {
+      size_t want = m + m / 8 + 64;
+      T* q = nullptr;
+      RXB_CUDA(cudaMalloc(&q, want * sizeof(T)));
+      if (p) { RXB_CUDA(cudaMemcpy(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice)); cudaFree(p); }
+      p = q;
+      cap = want;
+    }
+    n = m;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+struct Csr {
+  DBuf<long long> off;
+  DBuf<int> idx;
+  long long nnz = 0;
+  int nrows = 0;
+};
+
+struct CellList {
+  DBuf<double> bounds;
+  DBuf<int> key, key2, val, sorted_idx, bin_count, bin_start, cnt;
+  DBuf<long long> cntll;
+  DBuf<double4> spos;
+  DBuf<char> temp;
+  char grid_blob[96];
+  int num_bins = 0, reach = 2;
+  void bin(const double4* xq, int N, double bin_size, int reach, cudaStream_t st);
+  void build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st);
+};
+
+struct Box {  // LAMMPS triclinic box, lo = 0
+  double h[6] = {1, 1, 1, 0, 0, 0};  // xprd, yprd, zprd, yz, xz, xy
+  double h_inv[6];
+  void set(double xprd, double yprd, double zprd, double xy, double xz, double yz);
+};
+
+struct QeqScalars;  // device-side CG scalars, rxb_qeq.cu
+
+struct StepTimers {
+  enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, OTHER, NUM };
+  double ms[NUM] = {0};
+  long calls[NUM] = {0};
+};
+
+class System {
+ public:
+  explicit System(int device);
+  ~System();
+
+  // ---- configuration (pair_style / pair_coeff / fix qeq/reax arguments) ----
+  ForceField ff;
+  void upload_params();
+  double qeq_swa = 0.0, qeq_swb = 10.0, qeq_tol = 1e-6;
+  int qeq_imax = 200;       // fix_qeq_reax_sunway.cpp:998
+  int qeq_check_every = 4;  // host polls the device convergence flags every this many iterations
+  double skin = 2.5;
+
+  // ---- atoms ----
+  int n = 0, N = 0;
+  void set_atoms(int nlocal, int nghost, const double* x, const int* ltype, const int* tag, const double* q,
+                 const int* ghost_owner);
+  void set_positions(const double* x_host);  // all N, host pointer (H2D)
+  void set_charges(const double* q_host);    // all N
+  void get_forces(double* f_host);           // all N (caller does reverse_comm, as LAMMPS does)
+  void get_charges(double* q_host);          // all N
+
+  // ---- lists ----
+  void build_neighbors();   // a1: Verlet (local rows) + bond-candidate (all rows) lists
+  double cutneigh() const;
+
+  // ---- QEq (fix qeq/reax pre_force) ----
+  void qeq_reset_history();
+  void qeq_set_history(const double* s_hist, const double* t_hist);  // [n][5] host
+  void qeq_get_history(double* s_hist, double* t_hist);
+  void qeq_pre_force();
+  int matvecs_s = 0, matvecs_t = 0;
+  long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
+
+  // ---- pair compute ----
+  void compute(bool eflag, bool vflag);
+  double energies[E_NUM] = {0};
+  double virial[6] = {0};
+  int overflow_flag = 0;
+  int num_bonds = 0;         // directed bonds this step
+
+  // ---- device-resident MD (mini LAMMPS core: fix nve + periodic ghosts) ----
+  Box box;
+  void md_setup(const double* box6, int nlocal, const double* x, const double* v, const int* ltype, const int* tag,
+                const double* mass_by_type, int ntypes, double dt, int every);
+  void md_run(int nsteps);
+  void md_get(double* x, double* v, double* f, double* q);  // local atoms
+  double md_kinetic();
+  long ntimestep = 0;
+  int md_every = 5, md_ago = 0;
+  double md_dt = 0.0625;
+  bool qeq_on = true;
+  int md_thermo = 5;         // energies are reduced every md_thermo steps (thermo 5, in.reaxc.lattice:832)
+
+  // introspection for parity tests
+  DevView view();
+  std::vector<double> params_dump() const { return ff.dump(); }
+  cudaStream_t stream() const { return st_; }
+  StepTimers timers;
+  bool profile = false;
+  long kernel_launches = 0;
+
+  // raw buffers (public: the C ABI copies them out for tests / fix reax/c/bonds)
+  DBuf<double4> xq;
+  DBuf<int> type, tag, ltype_d, ghost_owner;
+  DBuf<double> f, CdDelta;
+  Csr vl, bc;
+  DBuf<int> far_num, far_idx;
+  DBuf<double> H_val;
+  DBuf<int> b_start, b_cnt, b_cursor, overflow, b_nbr, b_sym;
+  DBuf<double4> b_geo, b_bo, b_der, b_c1, b_c2, b_c3;
+  DBuf<double> b_Cdbo, b_Cdbopi, b_Cdbopi2;
+  DBuf<double> total_bop, dDeltap_self, total_bo, Delta_boc, Delta, Delta_val, vlpex, nlp, Delta_lp, dDelta_lp, Delta_lp_temp;
+  DBuf<double2> Deltap;
+  DBuf<double> en_d, virial_d;
+  // qeq
+  DBuf<double> q_s_hist, q_t_hist;   // [n][5]
+  DBuf<double2> q_x, q_r, q_u, q_w, q_p, q_ss, q_v, q_z, q_d, q_q, q_b, q_m;  // (s,t) interleaved; q_x,q_d length N
+  DBuf<double> q_Hdia_inv;
+  DBuf<double> q_scal;               // device scalars
+  DBuf<double> shld_d;               // nt*nt shielding (gamma_i gamma_j)^-1.5
+  // md
+  DBuf<double> v_d, mass_d, x_stage;
+  DBuf<int> ghost_shift;             // per ghost 3 ints
+  DBuf<long long> gcount, goff;
+  DBuf<char> scan_temp;
+  int cap_bonds = 0;
+
+ private:
+  int device_;
+  cudaStream_t st_ = nullptr;
+  cudaEvent_t ev_[2];
+  DBuf<char> param_blob_;
+  DevParams dp_{};
+  CellList cells_a_, cells_b_;
+  bool qeq_ran_this_step_ = false;
+  double* h_pin_ = nullptr;  // pinned staging
+  size_t h_pin_cap_ = 0;
+  double* pin(size_t doubles);
+  void step_forces(bool eflag, bool vflag);
+  void ensure_atom_capacity();
+  void ensure_bond_capacity(int cap);
+  void tick(int which);
+  void tock(int which);
+  void md_make_ghosts();
+  void md_force();
+  friend struct Launch;
+};
+
+// kernel launchers (one per translation unit)
+void launch_bond_list(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_bond_orders(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* qeq_tap, const double* shld, double swb,
+                      cudaStream_t st);
+void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st);
+
+}  // namespace rxb
