@@ -42,6 +42,9 @@ int rxb_neighbor_skin(rxb_handle* h, double skin);
 
 /* canonical flat dump of every parsed parameter (parity tests); returns the count, writes min(count, cap) values */
 long rxb_params_dump(rxb_handle* h, double* out, long cap);
+/* host-only: parse control + ffield + element map without touching a GPU and dump as above; -1 on error */
+long rxb_parse_dump(const char* control_file, const char* ffield_file, int ntypes, const char* const* elements,
+                    int lgvdw, int enobonds, double* out, long cap);
 
 /* ---- atoms: local [0,nlocal) then ghost [nlocal,nlocal+nghost)
  *      replaces write_reax_atoms_and_pack, pair_reaxc_sw64.c:114-190.
@@ -77,6 +80,7 @@ int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x,
                  const int* tag, const double* mass, int ntypes, double dt, int reneigh_every, int thermo_every,
                  int qeq_on);
 int rxb_md_run(rxb_handle* h, int nsteps);
+double rxb_md_last_run_ms(rxb_handle* h); /* device time of the last rxb_md_run: CUDA events on the launch stream */
 int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q); /* local atoms, any may be NULL */
 int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke);
 
@@ -92,8 +96,12 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
 int rxb_get_workspace(rxb_handle* h, double* w16);
 /* far list == H pattern: num[nlocal], and for row i the entries off_verlet[i] .. +num[i] of idx/val */
 int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val);
-/* profile[0..8] = ms per phase (neigh, qeq H, qeq CG, bond list, BO, bonded, nonbonded, dBond, other) when enabled */
-int rxb_profile(rxb_handle* h, int enable, double* ms9);
+/* CUDA-event timers on the launch stream (no sync inside a step).  out26 = 13 accumulated ms then 13 call counts for:
+ * neigh, qeq far+H, qeq CG (whole solve), bond list, BO, bonded (all), nonbonded, dBond, SpMV (per launch), hbond items,
+ * angle+torsion items, multi-body, enumeration.  enable: 1 reset+start, 0 stop, -1 read only. */
+int rxb_profile(rxb_handle* h, int enable, double* out26);
+/* cudaProfilerStart/Stop, so that `ncu --profile-from-start off` captures only the steady-state steps */
+int rxb_profiler_range(int start);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ SYMBOLS = [
     "rxb_fix_qeq", "rxb_neighbor_skin", "rxb_params_dump", "rxb_set_atoms", "rxb_set_positions", "rxb_set_charges",
     "rxb_neigh_build", "rxb_qeq_pre_force", "rxb_qeq_set_history", "rxb_qeq_get_history", "rxb_get_charges",
     "rxb_pair_compute", "rxb_md_setup", "rxb_md_run", "rxb_md_get", "rxb_md_thermo", "rxb_get_counts",
-    "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile",
+    "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -36,6 +36,8 @@ def load_library(path=LIB_PATH):
     lib = C.CDLL(path)
     lib.rxb_last_error.restype = C.c_char_p
     lib.rxb_params_dump.restype = C.c_long
+    lib.rxb_md_last_run_ms.restype = C.c_double
+    lib.rxb_parse_dump.restype = C.c_long
     _lib = lib
     return lib
 
@@ -210,7 +212,17 @@ class Rxb:
         self._chk(self.lib.rxb_get_far(self.h, _p(num), _p(idx), _p(val)))
         return num, idx, val
 
+    def profiler_range(self, start):
+        self._chk(self.lib.rxb_profiler_range(int(start)))
+
+    PHASES = ["neigh", "qeq_farH", "qeq_cg", "bond_list", "bond_orders", "bonded", "nonbonded", "dbond", "spmv",
+              "hbond_items", "angle_torsion_items", "multi_body", "enum"]
+
     def profile(self, enable=None):
-        ms = np.zeros(9)
-        self._chk(self.lib.rxb_profile(self.h, -1 if enable is None else int(enable), _p(ms)))
-        return ms
+        """-> dict phase -> (total ms, calls) accumulated since the last profile(1)."""
+        out = np.zeros(26)
+        self._chk(self.lib.rxb_profile(self.h, -1 if enable is None else int(enable), _p(out)))
+        return {nm: (out[k], int(out[13 + k])) for k, nm in enumerate(self.PHASES)}
+
+    def md_last_run_ms(self):
+        return float(self.lib.rxb_md_last_run_ms(self.h))

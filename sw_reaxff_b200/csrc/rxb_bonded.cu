@@ -222,98 +222,6 @@ __device__ __forceinline__ void calc_dcos(const double4& a, const double4& b, do
   }
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
-k_hbond(DevView v, DevParams P) {
-  __shared__ int s_hb[kWarps][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-  const double hbond_cut = P.ctl.hbond_cut;
-  double e_hb = 0;
-  if (hbond_cut > 0)
-  for (int j = wg; j < v.n; j += nwg) {
-    const int tj = v.type[j];
-    if (tj < 0 || P.atom[tj].p_hbond != 1) continue;
-    const int start = v.b_start[j], cnt = v.b_cnt[j];
-    // acceptor bonds of this hydrogen
-    int top = 0;
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-      const int e = e0 + lane;
-      bool ok = false;
-      if (e < cnt) {
-        const int p = start + e;
-        const int ti = v.type[v.b_nbr[p]];
-        ok = ti >= 0 && P.atom[ti].p_hbond == 2 && v.b_bo[p].x >= kHbThreshold;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) { const int slot = top + __popc(m & ((1u << lane) - 1)); if (slot < 32) s_hb[wib][slot] = start + e; }
-      top += __popc(m);
-    }
-    __syncwarp();
-    if (top > 32) { if (lane == 0) atomicOr(v.overflow, 4); top = 32; }
-    if (top == 0) continue;
-    const double4 xj = v.xq[j];
-    const long long fbeg = v.vl_off[j];
-    const int fnum = v.far_num[j];
-    double fjx = 0, fjy = 0, fjz = 0;
-    for (int itr = 0; itr < top; itr++) {
-      const int pi = s_hb[wib][itr];
-      const int i = v.b_nbr[pi];
-      const int ti = v.type[i], tag_i = v.tag[i];
-      const double4 gij = v.b_geo[pi];
-      const double BOij = v.b_bo[pi].x;
-      double fix = 0, fiy = 0, fiz = 0, cd = 0;
-      for (int k0 = 0; k0 < fnum; k0 += 32) {
-        const int kk = k0 + lane;
-        if (kk >= fnum) continue;
-        const int k = v.far_idx[fbeg + kk];
-        const int tk = v.type[k];
-        if (tk < 0 || P.atom[tk].p_hbond != 2) continue;
-        const double4 xk = v.xq[k];
-        const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
-        const double r_jk = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-        if (!(r_jk <= hbond_cut)) continue;
-        if (tag_i == v.tag[k]) continue;
-        const HbPar hp = P.hb[(ti * P.nt + tj) * P.nt + tk];
-        if (hp.r0_hb <= 0.0) continue;
-        const double4 gjk = make_double4(r_jk, dx, dy, dz);
-        double theta, cos_theta, di[3], dj[3], dk[3];
-        calc_theta(gij, gjk, theta, cos_theta);
-        calc_dcos(gij, gjk, di, dj, dk);
-        const double sin_theta2 = sin(theta / 2.0);
-        double sin_xhz4 = sqr(sin_theta2);
-        sin_xhz4 *= sin_xhz4;
-        const double cos_xhz1 = (1.0 - cos_theta);
-        const double exp_hb2 = exp(-hp.p_hb2 * BOij);
-        const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
-        const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
-        e_hb += ehb;
-        const double CEhb1 = hp.p_hb1 * hp.p_hb2 * exp_hb2 * exp_hb3 * sin_xhz4;
-        const double CEhb2 = -hp.p_hb1 / 2.0 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
-        const double CEhb3 = -hp.p_hb3 * (-hp.r0_hb / sqr(r_jk) + 1.0 / hp.r0_hb) * ehb;
-        cd += CEhb1;
-        // reference accumulates -force in fCdDelta; f is the true force here
-        fix -= CEhb2 * di[0]; fiy -= CEhb2 * di[1]; fiz -= CEhb2 * di[2];
-        const double c3 = CEhb3 / r_jk;
-        fjx -= CEhb2 * dj[0] - c3 * dx; fjy -= CEhb2 * dj[1] - c3 * dy; fjz -= CEhb2 * dj[2] - c3 * dz;
-        atomicAdd(&v.f[3 * k], -(CEhb2 * dk[0] + c3 * dx));
-        atomicAdd(&v.f[3 * k + 1], -(CEhb2 * dk[1] + c3 * dy));
-        atomicAdd(&v.f[3 * k + 2], -(CEhb2 * dk[2] + c3 * dz));
-      }
-      fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz); cd = warp_sum(cd);
-      if (lane == 0) {
-        if (cd != 0.0) atomicAdd(&v.b_Cdbo[pi], cd);
-        atomicAdd(&v.f[3 * i], fix); atomicAdd(&v.f[3 * i + 1], fiy); atomicAdd(&v.f[3 * i + 2], fiz);
-      }
-    }
-    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
-    if (lane == 0) { atomicAdd(&v.f[3 * j], fjx); atomicAdd(&v.f[3 * j + 1], fjy); atomicAdd(&v.f[3 * j + 2], fjz); }
-    __syncwarp();
-  }
-  const int slots[1] = {E_HB};
-  double vals[1] = {e_hb};
-  block_commit<1>(v.en, slots, vals);
-}
-
 // ------------------------------------------------------------------------------------------------------------
 struct Omega { double omega; double di[3], dj[3], dk[3], dl[3]; };
 
@@ -361,291 +269,466 @@ __device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K-enum: light integer pass, one warp per local centre atom.  Emits dense work lists so that the heavy fp64 kernels
+// run one thread per angle / torsion / hydrogen bond with every lane busy (the reference walks 4-deep nested loops per
+// centre atom on one CPE, reaxc_torsion_angles_cpe.h:192-760; on a GPU that shape leaves most lanes idle).
+//   angle item   (j, pk, ph)        : strong bonds pk < ph of j with BO_jk*BO_hj > thb_cutsq      (valence filter :796-801)
+//   torsion item (j, pk, ph, pw)    : bond j-k selected once by tag order, strong ph on j, strong pw on k, i != l,
+//                                     a torsion parameter set exists, BO_hj*BO_jk*BO_kw > thb_cut   (:982-1066)
+//   hbond item   (j, pi, k)         : H atom j, acceptor bond pi with BO >= 0.01, acceptor-type k within hbond_cut,
+//                                     tag_i != tag_k, r0_hb > 0                                    (hydrogen_bonds :313-354)
+// "strong" = BO > thb_cut; every filter of the reference needs it for both bonds of an angle and all three of a torsion.
+// Also stores the per-centre SBO quantities the angle items need (SBO2, CSBO2, dSBO1, dSBO2; :745-787).
 __global__ void __launch_bounds__(kWarps * 32)
-k_valtor(DevView v, DevParams P) {
+k_enum(DevView v, DevParams P, BondedWork W) {
   __shared__ int s_strong[kWarps][32];
+  __shared__ int s_hb[kWarps][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-  const double p_tor2 = P.gp[23], p_tor3 = P.gp[24], p_tor4 = P.gp[25], p_cot2 = P.gp[27];
-  const double p_val6 = P.gp[14], p_val8 = P.gp[33], p_val9 = P.gp[16], p_val10 = P.gp[17];
-  const double p_pen2 = P.gp[19], p_pen3 = P.gp[20], p_pen4 = P.gp[21];
-  const double p_coa2 = P.gp[2], p_coa3 = P.gp[38], p_coa4 = P.gp[30];
-  const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq;
+  const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq, hbond_cut = P.ctl.hbond_cut;
+  const double p_val8 = P.gp[33], p_val9 = P.gp[16];
   const int nt = P.nt;
-  double e_ang = 0, e_pen = 0, e_coa = 0, e_tor = 0, e_con = 0;
-
+  const unsigned lt_mask = (1u << lane) - 1;
   for (int j = wg; j < v.n; j += nwg) {
     const int type_j = v.type[j];
     const int start_j = v.b_start[j], cnt_j = v.b_cnt[j];
     if (type_j < 0 || cnt_j <= 0) continue;
-    const double Delta_boc_j = v.Delta_boc[j];
-    const double p_val3 = P.atom[type_j].p_val3, p_val5 = P.atom[type_j].p_val5;
-    // SBOp / prod_SBO over all bonds of j + list of "strong" bonds (BO > thb_cut): only those can enter an
-    // angle or a torsion (every filter in the reference requires BO_jk > thb_cut and BO_hj > thb_cut)
+    // ---- strong list, acceptor list, SBO sums ----
     double SBOp = 0, prod_SBO = 1;
-    int ns = 0;
+    int ns = 0, top = 0;
+    const bool is_H = P.atom[type_j].p_hbond == 1 && hbond_cut > 0;
     for (int e0 = 0; e0 < cnt_j; e0 += 32) {
       const int e = e0 + lane;
-      bool strong = false;
+      bool strong = false, acc = false;
       if (e < cnt_j) {
         const double4 bo = v.b_bo[start_j + e];
         SBOp += bo.z + bo.w;
         double t8 = bo.x * bo.x; t8 *= t8; t8 *= t8;
         prod_SBO *= exp(-t8);
         strong = bo.x > thb_cut;
+        if (is_H) {
+          const int ti = v.type[v.b_nbr[start_j + e]];
+          acc = ti >= 0 && P.atom[ti].p_hbond == 2 && bo.x >= kHbThreshold;
+        }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, strong);
-      if (strong) { const int slot = ns + __popc(m & ((1u << lane) - 1)); if (slot < 32) s_strong[wib][slot] = start_j + e; }
+      unsigned m = __ballot_sync(0xffffffffu, strong);
+      if (strong) { const int slot = ns + __popc(m & lt_mask); if (slot < 32) s_strong[wib][slot] = start_j + e; }
       ns += __popc(m);
+      m = __ballot_sync(0xffffffffu, acc);
+      if (acc) { const int slot = top + __popc(m & lt_mask); if (slot < 32) s_hb[wib][slot] = start_j + e; }
+      top += __popc(m);
     }
     __syncwarp();
-    if (ns > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = 32; }
+    if (ns > 32 || top > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = min(ns, 32); top = min(top, 32); }
     SBOp = warp_sum(SBOp);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) prod_SBO *= __shfl_xor_sync(0xffffffffu, prod_SBO, o);
-    if (ns < 2) { __syncwarp(); continue; }
+    if (lane == 0) {
+      const double Delta_boc_j = v.Delta_boc[j];
+      double vlpadj, dSBO2;
+      if (v.vlpex[j] >= 0) { vlpadj = 0; dSBO2 = prod_SBO - 1; }
+      else { vlpadj = v.nlp[j]; dSBO2 = (prod_SBO - 1) * (1 - p_val8 * v.dDelta_lp[j]); }
+      const double SBO = SBOp + (1 - prod_SBO) * (-Delta_boc_j - p_val8 * vlpadj);
+      const double dSBO1 = -8 * prod_SBO * (Delta_boc_j + p_val8 * vlpadj);
+      double SBO2, CSBO2;
+      if (SBO <= 0) { SBO2 = 0; CSBO2 = 0; }
+      else if (SBO > 0 && SBO <= 1) { SBO2 = pow(SBO, p_val9); CSBO2 = p_val9 * pow(SBO, p_val9 - 1); }
+      else if (SBO > 1 && SBO < 2) { SBO2 = 2 - pow(2 - SBO, p_val9); CSBO2 = p_val9 * pow(2 - SBO, p_val9 - 1); }
+      else { SBO2 = 2; CSBO2 = 0; }
+      W.sbo[j] = make_double4(SBO2, CSBO2, dSBO1, dSBO2);
+    }
 
-    const double vlpex_j = v.vlpex[j], nlp_j = v.nlp[j], dDelta_lp_j = v.dDelta_lp[j];
-    double vlpadj, dSBO2;
-    if (vlpex_j >= 0) { vlpadj = 0; dSBO2 = prod_SBO - 1; }
-    else { vlpadj = nlp_j; dSBO2 = (prod_SBO - 1) * (1 - p_val8 * dDelta_lp_j); }
-    const double SBO = SBOp + (1 - prod_SBO) * (-Delta_boc_j - p_val8 * vlpadj);
-    const double dSBO1 = -8 * prod_SBO * (Delta_boc_j + p_val8 * vlpadj);
-    double SBO2, CSBO2;
-    if (SBO <= 0) { SBO2 = 0; CSBO2 = 0; }
-    else if (SBO > 0 && SBO <= 1) { SBO2 = pow(SBO, p_val9); CSBO2 = p_val9 * pow(SBO, p_val9 - 1); }
-    else if (SBO > 1 && SBO < 2) { SBO2 = 2 - pow(2 - SBO, p_val9); CSBO2 = p_val9 * pow(2 - SBO, p_val9 - 1); }
-    else { SBO2 = 2; CSBO2 = 0; }
-    const double expval6 = exp(p_val6 * Delta_boc_j);
-    const double Delta_j = v.Delta[j], Delta_val_j = v.Delta_val[j];
-    const double4 xj = v.xq[j];
-    const int tag_j = v.tag[j];
-
-    double fjx = 0, fjy = 0, fjz = 0, cdd_j = 0, sum5 = 0, sum6 = 0;
-    const int npair = ns * ns;
-    for (int q = lane; q < npair; q += 32) {
-      const int a = q / ns, b = q - a * ns;
-      if (a == b) continue;
-      const int pk = s_strong[wib][a], ph = s_strong[wib][b];
-      const int k = v.b_nbr[pk], h = v.b_nbr[ph];
-      const int type_k = v.type[k], type_h = v.type[h];
-      if (type_k < 0 || type_h < 0) continue;
-      const double4 gjk = v.b_geo[pk], ghj = v.b_geo[ph];
-      const double4 bo_jk = v.b_bo[pk], bo_hj = v.b_bo[ph];
-      const double BOA_jk = bo_jk.x - thb_cut, BOA_hj = bo_hj.x - thb_cut;
-      const int start_k = v.b_start[k], cnt_k = v.b_cnt[k];
-      if (cnt_k <= 0) continue;
-      double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
-      calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
-      calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> h
-
-      // ---------------- valence angle k-j-h (each unordered pair once: ph > pk) ----------------
-      if (ph > pk && bo_jk.x * bo_hj.x > thb_cutsq) {
-        double sin_theta_hjk = sin(theta_hjk);
-        if (sin_theta_hjk < 1.0e-5) sin_theta_hjk = 1.0e-5;
-        const AngleSet& as = P.angle[(type_k * nt + type_j) * nt + type_h];
-        const double tbo_k = v.total_bo[k], tbo_h = v.total_bo[h];
-        for (int c = 0; c < as.cnt && c < kMaxAngleSets; c++) {
-          const AnglePar tp = as.prm[c];
-          if (!(fabs(tp.p_val1) > 0.001)) continue;
-          const double p_val1 = tp.p_val1, p_val2 = tp.p_val2, p_val4 = tp.p_val4, p_val7 = tp.p_val7, theta_00 = tp.theta_00;
-          const double exp3jk = exp(-p_val3 * pow(BOA_jk, p_val4));
-          const double f7_jk = 1.0 - exp3jk;
-          const double Cf7jk = p_val3 * p_val4 * pow(BOA_jk, p_val4 - 1.0) * exp3jk;
-          const double exp3hj = exp(-p_val3 * pow(BOA_hj, p_val4));
-          const double f7_hj = 1.0 - exp3hj;
-          const double Cf7hj = p_val3 * p_val4 * pow(BOA_hj, p_val4 - 1.0) * exp3hj;
-          const double expval7 = exp(-p_val7 * Delta_boc_j);
-          const double trm8 = 1.0 + expval6 + expval7;
-          const double f8_Dj = p_val5 - ((p_val5 - 1.0) * (2.0 + expval6) / trm8);
-          const double Cf8j = ((1.0 - p_val5) / sqr(trm8)) *
-                              (p_val6 * expval6 * trm8 - (2.0 + expval6) * (p_val6 * expval6 - p_val7 * expval7));
-          const double ex10 = exp(-p_val10 * (2.0 - SBO2));
-          double theta_0 = 180.0 - theta_00 * (1.0 - ex10);
-          theta_0 = deg2rad(theta_0);
-          const double expval2theta = exp(-p_val2 * sqr(theta_0 - theta_hjk));
-          const double expval12theta = (p_val1 >= 0) ? p_val1 * (1.0 - expval2theta) : p_val1 * -expval2theta;
-          const double CEval1 = Cf7jk * f7_hj * f8_Dj * expval12theta;
-          const double CEval2 = Cf7hj * f7_jk * f8_Dj * expval12theta;
-          const double CEval3 = Cf8j * f7_hj * f7_jk * expval12theta;
-          const double CEval4 = -2.0 * p_val1 * p_val2 * f7_jk * f7_hj * f8_Dj * expval2theta * (theta_0 - theta_hjk);
-          const double Ctheta_0 = p_val10 * deg2rad(theta_00) * ex10;
-          const double CEval5 = -CEval4 * Ctheta_0 * CSBO2;
-          const double CEval6 = CEval5 * dSBO1;
-          const double CEval7 = CEval5 * dSBO2;
-          const double CEval8 = -CEval4 / sin_theta_hjk;
-          e_ang += f7_jk * f7_hj * f8_Dj * expval12theta;
-
-          const double exp_pen2jk = exp(-p_pen2 * sqr(BOA_jk - 2.0));
-          const double exp_pen2hj = exp(-p_pen2 * sqr(BOA_hj - 2.0));
-          const double exp_pen3 = exp(-p_pen3 * Delta_j);
-          const double exp_pen4 = exp(p_pen4 * Delta_j);
-          const double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
-          const double f9_Dj = (2.0 + exp_pen3) / trm_pen34;
-          const double Cf9j = (-p_pen3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-p_pen3 * exp_pen3 + p_pen4 * exp_pen4)) / sqr(trm_pen34);
-          const double epen = tp.p_pen1 * f9_Dj * exp_pen2jk * exp_pen2hj;
-          e_pen += epen;
-          const double CEpen1 = epen * Cf9j / f9_Dj;
-          const double tpen = -2.0 * p_pen2 * epen;
-          const double CEpen2 = tpen * (BOA_jk - 2.0);
-          const double CEpen3 = tpen * (BOA_hj - 2.0);
-
-          const double exp_coa2 = exp(p_coa2 * Delta_val_j);
-          const double ecoa = tp.p_coa1 / (1. + exp_coa2) * exp(-p_coa3 * sqr(tbo_k - BOA_jk)) * exp(-p_coa3 * sqr(tbo_h - BOA_hj)) *
-                              exp(-p_coa4 * sqr(BOA_jk - 1.5)) * exp(-p_coa4 * sqr(BOA_hj - 1.5));
-          e_coa += ecoa;
-          const double CEcoa1 = -2 * p_coa4 * (BOA_jk - 1.5) * ecoa;
-          const double CEcoa2 = -2 * p_coa4 * (BOA_hj - 1.5) * ecoa;
-          const double CEcoa3 = -p_coa2 * exp_coa2 * ecoa / (1 + exp_coa2);
-          const double CEcoa4 = -2 * p_coa3 * (tbo_k - BOA_jk) * ecoa;
-          const double CEcoa5 = -2 * p_coa3 * (tbo_h - BOA_hj) * ecoa;
-
-          atomicAdd(&v.b_Cdbo[pk], (CEval1 + CEpen2 + (CEcoa1 - CEcoa4)));
-          atomicAdd(&v.b_Cdbo[ph], (CEval2 + CEpen3 + (CEcoa2 - CEcoa5)));
-          cdd_j += ((CEval3 + CEval7) + CEpen1 + CEcoa3);
-          atomicAdd(&v.CdDelta[k], CEcoa4);
-          atomicAdd(&v.CdDelta[h], CEcoa5);
-          sum6 += CEval6;  // applied to every bond t of j after the pair loop: Cdbo[t] += CEval6 * BO_t^7
-          sum5 += CEval5;  //                                                  Cdbopi[t], Cdbopi2[t] += CEval5
-          fadd3(v.f, k, -CEval8, hjk_di[0], hjk_di[1], hjk_di[2]);
-          fjx -= CEval8 * hjk_dj[0]; fjy -= CEval8 * hjk_dj[1]; fjz -= CEval8 * hjk_dj[2];
-          fadd3(v.f, h, -CEval8, hjk_dk[0], hjk_dk[1], hjk_dk[2]);
+    // ---- angles and torsions from ordered strong pairs (a, b), a != b ----
+    if (ns >= 2) {
+      const double4 xj = v.xq[j];
+      const int tag_j = v.tag[j];
+      const int npair = ns * ns;
+      for (int q0 = 0; q0 < npair; q0 += 32) {
+        const int q = q0 + lane;
+        bool ang = false;
+        unsigned long long tmask = 0ull;  // matching pw offsets in k's row
+        int pk = -1, ph = -1, start_k = 0;
+        if (q < npair) {
+          const int a = q / ns, b = q - a * ns;
+          if (a != b) {
+            pk = s_strong[wib][a]; ph = s_strong[wib][b];
+            const int k = v.b_nbr[pk], h = v.b_nbr[ph];
+            const int type_k = v.type[k], type_h = v.type[h];
+            const int cnt_k = v.b_cnt[k];
+            start_k = v.b_start[k];
+            if (type_k >= 0 && type_h >= 0 && cnt_k > 0) {
+              const double bo_jk = v.b_bo[pk].x, bo_hj = v.b_bo[ph].x;
+              ang = (ph > pk) && (bo_jk * bo_hj > thb_cutsq);
+              const int pj = v.b_sym[pk];
+              if (pj >= 0 && half_select(tag_j, v.tag[k], xj, v.xq[k])) {
+                const int ne = min(cnt_k, 64);
+                if (cnt_k > 64 && lane == 0) atomicOr(v.overflow, 8);
+                for (int e = 0; e < ne; e++) {
+                  const int pw = start_k + e;
+                  if (pw == pj) continue;
+                  const double bo_kl = v.b_bo[pw].x;
+                  if (!(bo_kl > thb_cut)) continue;
+                  const int l = v.b_nbr[pw];
+                  if (l == h) continue;
+                  const int type_l = v.type[l];
+                  if (type_l < 0) continue;
+                  if (!P.tors[((type_h * nt + type_j) * nt + type_k) * nt + type_l].cnt) continue;
+                  if (!(bo_hj * bo_jk * bo_kl > thb_cut)) continue;
+                  tmask |= 1ull << e;
+                }
+              }
+            }
+          }
+        }
+        // angles
+        unsigned m = __ballot_sync(0xffffffffu, ang);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(W.n_ang, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (ang) {
+            const int o = base + __popc(m & lt_mask);
+            if (o < W.cap_ang) W.ang[o] = make_int4(j, pk, ph, 0);
+          }
+        }
+        // torsions: warp exclusive scan of per-lane counts
+        const int mine = __popcll(tmask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(W.n_tor, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          int o = base + incl - mine;
+          while (tmask) {
+            const int e = __ffsll((long long)tmask) - 1;
+            tmask &= tmask - 1;
+            if (o < W.cap_tor) W.tor[o] = make_int4(j, pk, ph, start_k + e);
+            o++;
+          }
         }
       }
-
-      // ---------------- torsion h-j-k-w, bond j-k taken once by tag order ----------------
-      const double4 xk = v.xq[k];
-      if (!half_select(tag_j, v.tag[k], xj, xk)) continue;
-      const int pj = v.b_sym[pk];  // j on k's row
-      if (pj < 0) continue;
-      const double4 gkj = v.b_geo[pj];
-      const int i = h, type_i = type_h;
-      const double r_ij = ghj.x;
-      const double BOA_ij = BOA_hj;
-      const double sin_ijk = sin(theta_hjk), cos_ijk = cos(theta_hjk);
-      double tan_ijk_i;
-      if (sin_ijk >= 0 && sin_ijk <= kMinSine) tan_ijk_i = cos_ijk / kMinSine;
-      else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) tan_ijk_i = cos_ijk / -kMinSine;
-      else tan_ijk_i = cos_ijk / sin_ijk;
-      const double exp_tor2_ij = exp(-p_tor2 * BOA_ij);
-      const double exp_cot2_ij = exp(-p_cot2 * sqr(BOA_ij - 1.5));
-      const double exp_tor2_jk = exp(-p_tor2 * BOA_jk);
-      const double exp_cot2_jk = exp(-p_cot2 * sqr(BOA_jk - 1.5));
-      const double Delta_k = v.Delta_boc[k];
-      const double exp_tor3_DjDk = exp(-p_tor3 * (Delta_boc_j + Delta_k));
-      const double exp_tor4_DjDk = exp(p_tor4 * (Delta_boc_j + Delta_k));
-      const double exp_tor34_inv = 1.0 / (1.0 + exp_tor3_DjDk + exp_tor4_DjDk);
-      const double f11_DjDk = (2.0 + exp_tor3_DjDk) * exp_tor34_inv;
-      const double4 xi = v.xq[i];
-      double fix = 0, fiy = 0, fiz = 0, fkx = 0, fky = 0, fkz = 0, cdbo_ij = 0, cdbo_jk = 0, cdbopi_jk = 0, cdd_k = 0;
-
-      for (int pw = start_k; pw < start_k + cnt_k; pw++) {
-        if (pw == pj) continue;
-        const double4 bo_kl = v.b_bo[pw];
-        if (!(bo_kl.x > thb_cut)) continue;
-        const int l = v.b_nbr[pw];
-        if (i == l) continue;
-        const int type_l = v.type[l];
-        if (type_l < 0) continue;
-        const TorsPar fp = P.tors[((type_i * nt + type_j) * nt + type_k) * nt + type_l];
-        if (!fp.cnt) continue;
-        if (!(bo_hj.x * bo_jk.x * bo_kl.x > thb_cut)) continue;
-        const double4 gkl = v.b_geo[pw];
-        double theta_jkl, cos_theta_jkl, jkl_di[3], jkl_dj[3], jkl_dk[3];
-        calc_theta(gkj, gkl, theta_jkl, cos_theta_jkl);
-        calc_dcos(gkj, gkl, jkl_di, jkl_dj, jkl_dk);  // di <-> j, dj <-> k, dk <-> l
-        const double r_kl = gkl.x;
-        const double BOA_kl = bo_kl.x - thb_cut;
-        const double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
-        double tan_jkl_i;
-        if (sin_jkl >= 0 && sin_jkl <= kMinSine) tan_jkl_i = cos_jkl / kMinSine;
-        else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) tan_jkl_i = cos_jkl / -kMinSine;
-        else tan_jkl_i = cos_jkl / sin_jkl;
-        const double4 xl = v.xq[l];
-        const double dvec_li[3] = {xi.x - xl.x, xi.y - xl.y, xi.z - xl.z};
-        const double r_li = sqrt(dvec_li[0] * dvec_li[0] + dvec_li[1] * dvec_li[1] + dvec_li[2] * dvec_li[2]);
-        Omega om;
-        calc_omega(ghj, gjk, gkl, dvec_li, r_li, theta_hjk, hjk_di, hjk_dj, hjk_dk, theta_jkl, jkl_di, jkl_dj, jkl_dk, om);
-        const double cos_omega = cos(om.omega), cos2omega = cos(2. * om.omega), cos3omega = cos(3. * om.omega);
-        const double exp_tor1 = exp(fp.p_tor1 * sqr(2.0 - bo_jk.z - f11_DjDk));
-        const double exp_tor2_kl = exp(-p_tor2 * BOA_kl);
-        const double exp_cot2_kl = exp(-p_cot2 * sqr(BOA_kl - 1.5));
-        const double fn10 = (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
-        const double CV = 0.5 * (fp.V1 * (1.0 + cos_omega) + fp.V2 * exp_tor1 * (1.0 - cos2omega) + fp.V3 * (1.0 + cos3omega));
-        e_tor += fn10 * sin_ijk * sin_jkl * CV;
-        const double dfn11 = (-p_tor3 * exp_tor3_DjDk + (p_tor3 * exp_tor3_DjDk - p_tor4 * exp_tor4_DjDk) * (2.0 + exp_tor3_DjDk) * exp_tor34_inv) * exp_tor34_inv;
-        const double CEtors1 = sin_ijk * sin_jkl * CV;
-        const double CEtors2 = -fn10 * 2.0 * fp.p_tor1 * fp.V2 * exp_tor1 * (2.0 - bo_jk.z - f11_DjDk) * (1.0 - sqr(cos_omega)) * sin_ijk * sin_jkl;
-        const double CEtors3 = CEtors2 * dfn11;
-        const double CEtors4 = CEtors1 * p_tor2 * exp_tor2_ij * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
-        const double CEtors5 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * exp_tor2_jk * (1.0 - exp_tor2_kl);
-        const double CEtors6 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * exp_tor2_kl;
-        const double cmn = -fn10 * CV;
-        const double CEtors7 = cmn * sin_jkl * tan_ijk_i;
-        const double CEtors8 = cmn * sin_ijk * tan_jkl_i;
-        const double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * fp.V1 - 2.0 * fp.V2 * exp_tor1 * cos_omega + 1.5 * fp.V3 * (cos2omega + 2.0 * sqr(cos_omega)));
-        const double fn12 = exp_cot2_ij * exp_cot2_jk * exp_cot2_kl;
-        const double cterm = (1.0 + (sqr(cos_omega) - 1.0) * sin_ijk * sin_jkl);
-        e_con += fp.p_cot1 * fn12 * cterm;
-        const double Cconj = -2.0 * fn12 * fp.p_cot1 * p_cot2 * cterm;
-        const double CEconj1 = Cconj * (BOA_ij - 1.5e0);
-        const double CEconj2 = Cconj * (BOA_jk - 1.5e0);
-        const double CEconj3 = Cconj * (BOA_kl - 1.5e0);
-        const double CEconj4 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_jkl * tan_ijk_i;
-        const double CEconj5 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_ijk * tan_jkl_i;
-        const double CEconj6 = 2.0 * fp.p_cot1 * fn12 * cos_omega * sin_ijk * sin_jkl;
-
-        cdbopi_jk += CEtors2;
-        cdd_j += CEtors3;
-        cdd_k += CEtors3;
-        cdbo_ij += (CEtors4 + CEconj1);
-        cdbo_jk += (CEtors5 + CEconj2);
-        atomicAdd(&v.b_Cdbo[pw], (CEtors6 + CEconj3));
-        const double c74 = CEtors7 + CEconj4, c85 = CEtors8 + CEconj5, c96 = CEtors9 + CEconj6;
-        fix -= c74 * hjk_dk[0] + c96 * om.di[0]; fiy -= c74 * hjk_dk[1] + c96 * om.di[1]; fiz -= c74 * hjk_dk[2] + c96 * om.di[2];
-        fjx -= c74 * hjk_dj[0] + c85 * jkl_di[0] + c96 * om.dj[0];
-        fjy -= c74 * hjk_dj[1] + c85 * jkl_di[1] + c96 * om.dj[1];
-        fjz -= c74 * hjk_dj[2] + c85 * jkl_di[2] + c96 * om.dj[2];
-        fkx -= c74 * hjk_di[0] + c85 * jkl_dj[0] + c96 * om.dk[0];
-        fky -= c74 * hjk_di[1] + c85 * jkl_dj[1] + c96 * om.dk[1];
-        fkz -= c74 * hjk_di[2] + c85 * jkl_dj[2] + c96 * om.dk[2];
-        atomicAdd(&v.f[3 * l], -(c85 * jkl_dk[0] + c96 * om.dl[0]));
-        atomicAdd(&v.f[3 * l + 1], -(c85 * jkl_dk[1] + c96 * om.dl[1]));
-        atomicAdd(&v.f[3 * l + 2], -(c85 * jkl_dk[2] + c96 * om.dl[2]));
-      }
-      if (cdbo_ij != 0.0) atomicAdd(&v.b_Cdbo[ph], cdbo_ij);
-      if (cdbo_jk != 0.0) atomicAdd(&v.b_Cdbo[pk], cdbo_jk);
-      if (cdbopi_jk != 0.0) atomicAdd(&v.b_Cdbopi[pk], cdbopi_jk);
-      if (cdd_k != 0.0) atomicAdd(&v.CdDelta[k], cdd_k);
-      if (fix != 0.0 || fiy != 0.0 || fiz != 0.0) { atomicAdd(&v.f[3 * i], fix); atomicAdd(&v.f[3 * i + 1], fiy); atomicAdd(&v.f[3 * i + 2], fiz); }
-      if (fkx != 0.0 || fky != 0.0 || fkz != 0.0) { atomicAdd(&v.f[3 * k], fkx); atomicAdd(&v.f[3 * k + 1], fky); atomicAdd(&v.f[3 * k + 2], fkz); }
     }
-    // warp-level epilogue for the centre atom
-    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
-    cdd_j = warp_sum(cdd_j); sum5 = warp_sum(sum5); sum6 = warp_sum(sum6);
-    if (lane == 0) {
-      atomicAdd(&v.f[3 * j], fjx); atomicAdd(&v.f[3 * j + 1], fjy); atomicAdd(&v.f[3 * j + 2], fjz);
-      if (cdd_j != 0.0) atomicAdd(&v.CdDelta[j], cdd_j);
-    }
-    if (sum5 != 0.0 || sum6 != 0.0)
-      for (int e = lane; e < cnt_j; e += 32) {
-        const int t = start_j + e;
-        const double bo = v.b_bo[t].x;
-        const double b3 = bo * bo * bo;
-        atomicAdd(&v.b_Cdbo[t], sum6 * (b3 * b3 * bo));
-        atomicAdd(&v.b_Cdbopi[t], sum5);
-        atomicAdd(&v.b_Cdbopi2[t], sum5);
+
+    // ---- hydrogen bonds: H atom j, acceptor bonds x acceptor-type far neighbours within hbond_cut ----
+    if (is_H && top > 0) {
+      const double4 xj = v.xq[j];
+      const long long fbeg = v.vl_off[j];
+      const int fnum = v.far_num[j];
+      for (int k0 = 0; k0 < fnum; k0 += 32) {
+        const int kk = k0 + lane;
+        unsigned amask = 0u;  // which acceptor bonds pair with this k
+        int k = -1;
+        if (kk < fnum) {
+          k = v.far_idx[fbeg + kk];
+          const int tk = v.type[k];
+          if (tk >= 0 && P.atom[tk].p_hbond == 2) {
+            const double4 xk = v.xq[k];
+            const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
+            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (r <= hbond_cut) {
+              const int tag_k = v.tag[k];
+              for (int t = 0; t < top; t++) {
+                const int i = v.b_nbr[s_hb[wib][t]];
+                if (v.tag[i] == tag_k) continue;
+                if (P.hb[(v.type[i] * nt + type_j) * nt + tk].r0_hb <= 0.0) continue;
+                amask |= 1u << t;
+              }
+            }
+          }
+        }
+        const int mine = __popc(amask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(W.n_hb, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          int o = base + incl - mine;
+          while (amask) {
+            const int t = __ffs((int)amask) - 1;
+            amask &= amask - 1;
+            if (o < W.cap_hb) W.hb[o] = make_int4(j, s_hb[wib][t], k, 0);
+            o++;
+          }
+        }
       }
+    }
     __syncwarp();
   }
-  const int slots[5] = {E_ANG, E_PEN, E_COA, E_TOR, E_CON};
-  double vals[5] = {e_ang, e_pen, e_coa, e_tor, e_con};
-  block_commit<5>(v.en, slots, vals);
+}
+
+constexpr int kItemThreads = 128;
+
+// ------------------------------------------------------------------------------------------------------------
+// K-hb: one thread per (H j, acceptor bond pi, partner k)   reaxc_hydrogen_bonds_sunway.cpp:355-436
+__global__ void __launch_bounds__(kItemThreads)
+k_hbond_items(DevView v, DevParams P, BondedWork W) {
+  const int nitems = min(*W.n_hb, W.cap_hb);
+  const int nt = P.nt;
+  double e_hb = 0;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const int4 w = W.hb[it];
+    const int j = w.x, pi = w.y, k = w.z;
+    const int i = v.b_nbr[pi];
+    const double4 xj = v.xq[j], xk = v.xq[k];
+    const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
+    const double r_jk = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    const HbPar hp = P.hb[(v.type[i] * nt + v.type[j]) * nt + v.type[k]];
+    const double4 gij = v.b_geo[pi];
+    const double BOij = v.b_bo[pi].x;
+    const double4 gjk = make_double4(r_jk, dx, dy, dz);
+    double theta, cos_theta, di[3], dj[3], dk[3];
+    calc_theta(gij, gjk, theta, cos_theta);
+    calc_dcos(gij, gjk, di, dj, dk);
+    const double sin_theta2 = sin(theta / 2.0);
+    double sin_xhz4 = sqr(sin_theta2);
+    sin_xhz4 *= sin_xhz4;
+    const double cos_xhz1 = (1.0 - cos_theta);
+    const double exp_hb2 = exp(-hp.p_hb2 * BOij);
+    const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
+    const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
+    e_hb += ehb;
+    const double CEhb1 = hp.p_hb1 * hp.p_hb2 * exp_hb2 * exp_hb3 * sin_xhz4;
+    const double CEhb2 = -hp.p_hb1 / 2.0 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
+    const double CEhb3 = -hp.p_hb3 * (-hp.r0_hb / sqr(r_jk) + 1.0 / hp.r0_hb) * ehb;
+    const double c3 = CEhb3 / r_jk;
+    atomicAdd(&v.b_Cdbo[pi], CEhb1);
+    // reference accumulates -force in fCdDelta; f is the true force here
+    fadd3(v.f, i, -CEhb2, di[0], di[1], di[2]);
+    atomicAdd(&v.f[3 * j], -(CEhb2 * dj[0] - c3 * dx));
+    atomicAdd(&v.f[3 * j + 1], -(CEhb2 * dj[1] - c3 * dy));
+    atomicAdd(&v.f[3 * j + 2], -(CEhb2 * dj[2] - c3 * dz));
+    atomicAdd(&v.f[3 * k], -(CEhb2 * dk[0] + c3 * dx));
+    atomicAdd(&v.f[3 * k + 1], -(CEhb2 * dk[1] + c3 * dy));
+    atomicAdd(&v.f[3 * k + 2], -(CEhb2 * dk[2] + c3 * dz));
+  }
+  const int slots[1] = {E_HB};
+  double vals[1] = {e_hb};
+  block_commit<1>(v.en, slots, vals);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K-angle: one thread per valence angle k-j-h   reaxc_torsion_angles_sunway.cpp:803-979
+__global__ void __launch_bounds__(kItemThreads)
+k_angle_items(DevView v, DevParams P, BondedWork W) {
+  const int nitems = min(*W.n_ang, W.cap_ang);
+  const double p_val6 = P.gp[14], p_val10 = P.gp[17];
+  const double p_pen2 = P.gp[19], p_pen3 = P.gp[20], p_pen4 = P.gp[21];
+  const double p_coa2 = P.gp[2], p_coa3 = P.gp[38], p_coa4 = P.gp[30];
+  const double thb_cut = P.ctl.thb_cut;
+  const int nt = P.nt;
+  double e_ang = 0, e_pen = 0, e_coa = 0;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const int4 w = W.ang[it];
+    const int j = w.x, pk = w.y, ph = w.z;
+    const int k = v.b_nbr[pk], h = v.b_nbr[ph];
+    const int type_j = v.type[j], type_k = v.type[k], type_h = v.type[h];
+    const double4 gjk = v.b_geo[pk], ghj = v.b_geo[ph];
+    const double BOA_jk = v.b_bo[pk].x - thb_cut, BOA_hj = v.b_bo[ph].x - thb_cut;
+    const double4 sb = W.sbo[j];
+    const double SBO2 = sb.x, CSBO2 = sb.y, dSBO1 = sb.z, dSBO2 = sb.w;
+    const double Delta_boc_j = v.Delta_boc[j], Delta_j = v.Delta[j], Delta_val_j = v.Delta_val[j];
+    const double p_val3 = P.atom[type_j].p_val3, p_val5 = P.atom[type_j].p_val5;
+    const double expval6 = exp(p_val6 * Delta_boc_j);
+    double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
+    calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
+    calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> h
+    double sin_theta_hjk = sin(theta_hjk);
+    if (sin_theta_hjk < 1.0e-5) sin_theta_hjk = 1.0e-5;
+    const AngleSet& as = P.angle[(type_k * nt + type_j) * nt + type_h];
+    const double tbo_k = v.total_bo[k], tbo_h = v.total_bo[h];
+    double cdbo_k = 0, cdbo_h = 0, cdd_j = 0, cdd_k = 0, cdd_h = 0, s5 = 0, s6 = 0, c8 = 0;
+    for (int c = 0; c < as.cnt && c < kMaxAngleSets; c++) {
+      const AnglePar tp = as.prm[c];
+      if (!(fabs(tp.p_val1) > 0.001)) continue;
+      const double p_val1 = tp.p_val1, p_val2 = tp.p_val2, p_val4 = tp.p_val4, p_val7 = tp.p_val7, theta_00 = tp.theta_00;
+      const double exp3jk = exp(-p_val3 * pow(BOA_jk, p_val4));
+      const double f7_jk = 1.0 - exp3jk;
+      const double Cf7jk = p_val3 * p_val4 * pow(BOA_jk, p_val4 - 1.0) * exp3jk;
+      const double exp3hj = exp(-p_val3 * pow(BOA_hj, p_val4));
+      const double f7_hj = 1.0 - exp3hj;
+      const double Cf7hj = p_val3 * p_val4 * pow(BOA_hj, p_val4 - 1.0) * exp3hj;
+      const double expval7 = exp(-p_val7 * Delta_boc_j);
+      const double trm8 = 1.0 + expval6 + expval7;
+      const double f8_Dj = p_val5 - ((p_val5 - 1.0) * (2.0 + expval6) / trm8);
+      const double Cf8j = ((1.0 - p_val5) / sqr(trm8)) *
+                          (p_val6 * expval6 * trm8 - (2.0 + expval6) * (p_val6 * expval6 - p_val7 * expval7));
+      const double ex10 = exp(-p_val10 * (2.0 - SBO2));
+      double theta_0 = 180.0 - theta_00 * (1.0 - ex10);
+      theta_0 = deg2rad(theta_0);
+      const double expval2theta = exp(-p_val2 * sqr(theta_0 - theta_hjk));
+      const double expval12theta = (p_val1 >= 0) ? p_val1 * (1.0 - expval2theta) : p_val1 * -expval2theta;
+      const double CEval1 = Cf7jk * f7_hj * f8_Dj * expval12theta;
+      const double CEval2 = Cf7hj * f7_jk * f8_Dj * expval12theta;
+      const double CEval3 = Cf8j * f7_hj * f7_jk * expval12theta;
+      const double CEval4 = -2.0 * p_val1 * p_val2 * f7_jk * f7_hj * f8_Dj * expval2theta * (theta_0 - theta_hjk);
+      const double Ctheta_0 = p_val10 * deg2rad(theta_00) * ex10;
+      const double CEval5 = -CEval4 * Ctheta_0 * CSBO2;
+      const double CEval6 = CEval5 * dSBO1;
+      const double CEval7 = CEval5 * dSBO2;
+      const double CEval8 = -CEval4 / sin_theta_hjk;
+      e_ang += f7_jk * f7_hj * f8_Dj * expval12theta;
+
+      const double exp_pen2jk = exp(-p_pen2 * sqr(BOA_jk - 2.0));
+      const double exp_pen2hj = exp(-p_pen2 * sqr(BOA_hj - 2.0));
+      const double exp_pen3 = exp(-p_pen3 * Delta_j);
+      const double exp_pen4 = exp(p_pen4 * Delta_j);
+      const double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
+      const double f9_Dj = (2.0 + exp_pen3) / trm_pen34;
+      const double Cf9j = (-p_pen3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-p_pen3 * exp_pen3 + p_pen4 * exp_pen4)) / sqr(trm_pen34);
+      const double epen = tp.p_pen1 * f9_Dj * exp_pen2jk * exp_pen2hj;
+      e_pen += epen;
+      const double CEpen1 = epen * Cf9j / f9_Dj;
+      const double tpen = -2.0 * p_pen2 * epen;
+      const double CEpen2 = tpen * (BOA_jk - 2.0);
+      const double CEpen3 = tpen * (BOA_hj - 2.0);
+
+      const double exp_coa2 = exp(p_coa2 * Delta_val_j);
+      const double ecoa = tp.p_coa1 / (1. + exp_coa2) * exp(-p_coa3 * sqr(tbo_k - BOA_jk)) * exp(-p_coa3 * sqr(tbo_h - BOA_hj)) *
+                          exp(-p_coa4 * sqr(BOA_jk - 1.5)) * exp(-p_coa4 * sqr(BOA_hj - 1.5));
+      e_coa += ecoa;
+      const double CEcoa1 = -2 * p_coa4 * (BOA_jk - 1.5) * ecoa;
+      const double CEcoa2 = -2 * p_coa4 * (BOA_hj - 1.5) * ecoa;
+      const double CEcoa3 = -p_coa2 * exp_coa2 * ecoa / (1 + exp_coa2);
+      const double CEcoa4 = -2 * p_coa3 * (tbo_k - BOA_jk) * ecoa;
+      const double CEcoa5 = -2 * p_coa3 * (tbo_h - BOA_hj) * ecoa;
+
+      cdbo_k += (CEval1 + CEpen2 + (CEcoa1 - CEcoa4));
+      cdbo_h += (CEval2 + CEpen3 + (CEcoa2 - CEcoa5));
+      cdd_j += ((CEval3 + CEval7) + CEpen1 + CEcoa3);
+      cdd_k += CEcoa4;
+      cdd_h += CEcoa5;
+      s6 += CEval6;  // every bond t of j: Cdbo[t] += CEval6 * BO_t^7          (applied in K-dbond through W.sum56)
+      s5 += CEval5;  //                    Cdbopi[t], Cdbopi2[t] += CEval5
+      c8 += CEval8;
+    }
+    if (cdbo_k != 0.0) atomicAdd(&v.b_Cdbo[pk], cdbo_k);
+    if (cdbo_h != 0.0) atomicAdd(&v.b_Cdbo[ph], cdbo_h);
+    if (cdd_j != 0.0) atomicAdd(&v.CdDelta[j], cdd_j);
+    if (cdd_k != 0.0) atomicAdd(&v.CdDelta[k], cdd_k);
+    if (cdd_h != 0.0) atomicAdd(&v.CdDelta[h], cdd_h);
+    if (s5 != 0.0) atomicAdd(&W.sum56[j].x, s5);
+    if (s6 != 0.0) atomicAdd(&W.sum56[j].y, s6);
+    if (c8 != 0.0) {
+      fadd3(v.f, k, -c8, hjk_di[0], hjk_di[1], hjk_di[2]);
+      fadd3(v.f, j, -c8, hjk_dj[0], hjk_dj[1], hjk_dj[2]);
+      fadd3(v.f, h, -c8, hjk_dk[0], hjk_dk[1], hjk_dk[2]);
+    }
+  }
+  const int slots[3] = {E_ANG, E_PEN, E_COA};
+  double vals[3] = {e_ang, e_pen, e_coa};
+  block_commit<3>(v.en, slots, vals);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K-tors: one thread per torsion h-j-k-l (= i-j-k-l)   reaxc_torsion_angles_sunway.cpp:994-1290
+__global__ void __launch_bounds__(kItemThreads)
+k_torsion_items(DevView v, DevParams P, BondedWork W) {
+  const int nitems = min(*W.n_tor, W.cap_tor);
+  const double p_tor2 = P.gp[23], p_tor3 = P.gp[24], p_tor4 = P.gp[25], p_cot2 = P.gp[27];
+  const double thb_cut = P.ctl.thb_cut;
+  const int nt = P.nt;
+  double e_tor = 0, e_con = 0;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
+    const int4 w = W.tor[it];
+    const int j = w.x, pk = w.y, ph = w.z, pw = w.w;
+    const int k = v.b_nbr[pk], i = v.b_nbr[ph], l = v.b_nbr[pw];
+    const int pj = v.b_sym[pk];
+    const double4 gjk = v.b_geo[pk], ghj = v.b_geo[ph], gkj = v.b_geo[pj], gkl = v.b_geo[pw];
+    const double4 bo_jk = v.b_bo[pk];
+    const double bo_hj = v.b_bo[ph].x, bo_kl = v.b_bo[pw].x;
+    const double BOA_jk = bo_jk.x - thb_cut, BOA_ij = bo_hj - thb_cut, BOA_kl = bo_kl - thb_cut;
+    const TorsPar fp = P.tors[((v.type[i] * nt + v.type[j]) * nt + v.type[k]) * nt + v.type[l]];
+    double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
+    calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
+    calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> i
+    double theta_jkl, cos_theta_jkl, jkl_di[3], jkl_dj[3], jkl_dk[3];
+    calc_theta(gkj, gkl, theta_jkl, cos_theta_jkl);
+    calc_dcos(gkj, gkl, jkl_di, jkl_dj, jkl_dk);  // di <-> j, dj <-> k, dk <-> l
+    const double r_ij = ghj.x, r_kl = gkl.x;
+    (void)r_ij; (void)r_kl;
+    const double sin_ijk = sin(theta_hjk), cos_ijk = cos(theta_hjk);
+    double tan_ijk_i;
+    if (sin_ijk >= 0 && sin_ijk <= kMinSine) tan_ijk_i = cos_ijk / kMinSine;
+    else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) tan_ijk_i = cos_ijk / -kMinSine;
+    else tan_ijk_i = cos_ijk / sin_ijk;
+    const double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
+    double tan_jkl_i;
+    if (sin_jkl >= 0 && sin_jkl <= kMinSine) tan_jkl_i = cos_jkl / kMinSine;
+    else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) tan_jkl_i = cos_jkl / -kMinSine;
+    else tan_jkl_i = cos_jkl / sin_jkl;
+    const double exp_tor2_ij = exp(-p_tor2 * BOA_ij);
+    const double exp_cot2_ij = exp(-p_cot2 * sqr(BOA_ij - 1.5));
+    const double exp_tor2_jk = exp(-p_tor2 * BOA_jk);
+    const double exp_cot2_jk = exp(-p_cot2 * sqr(BOA_jk - 1.5));
+    const double exp_tor2_kl = exp(-p_tor2 * BOA_kl);
+    const double exp_cot2_kl = exp(-p_cot2 * sqr(BOA_kl - 1.5));
+    const double DjDk = v.Delta_boc[j] + v.Delta_boc[k];
+    const double exp_tor3_DjDk = exp(-p_tor3 * DjDk);
+    const double exp_tor4_DjDk = exp(p_tor4 * DjDk);
+    const double exp_tor34_inv = 1.0 / (1.0 + exp_tor3_DjDk + exp_tor4_DjDk);
+    const double f11_DjDk = (2.0 + exp_tor3_DjDk) * exp_tor34_inv;
+    const double4 xi = v.xq[i], xl = v.xq[l];
+    const double dvec_li[3] = {xi.x - xl.x, xi.y - xl.y, xi.z - xl.z};
+    const double r_li = sqrt(dvec_li[0] * dvec_li[0] + dvec_li[1] * dvec_li[1] + dvec_li[2] * dvec_li[2]);
+    Omega om;
+    calc_omega(ghj, gjk, gkl, dvec_li, r_li, theta_hjk, hjk_di, hjk_dj, hjk_dk, theta_jkl, jkl_di, jkl_dj, jkl_dk, om);
+    const double cos_omega = cos(om.omega), cos2omega = cos(2. * om.omega), cos3omega = cos(3. * om.omega);
+    const double exp_tor1 = exp(fp.p_tor1 * sqr(2.0 - bo_jk.z - f11_DjDk));
+    const double fn10 = (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
+    const double CV = 0.5 * (fp.V1 * (1.0 + cos_omega) + fp.V2 * exp_tor1 * (1.0 - cos2omega) + fp.V3 * (1.0 + cos3omega));
+    e_tor += fn10 * sin_ijk * sin_jkl * CV;
+    const double dfn11 = (-p_tor3 * exp_tor3_DjDk + (p_tor3 * exp_tor3_DjDk - p_tor4 * exp_tor4_DjDk) * (2.0 + exp_tor3_DjDk) * exp_tor34_inv) * exp_tor34_inv;
+    const double CEtors1 = sin_ijk * sin_jkl * CV;
+    const double CEtors2 = -fn10 * 2.0 * fp.p_tor1 * fp.V2 * exp_tor1 * (2.0 - bo_jk.z - f11_DjDk) * (1.0 - sqr(cos_omega)) * sin_ijk * sin_jkl;
+    const double CEtors3 = CEtors2 * dfn11;
+    const double CEtors4 = CEtors1 * p_tor2 * exp_tor2_ij * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
+    const double CEtors5 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * exp_tor2_jk * (1.0 - exp_tor2_kl);
+    const double CEtors6 = CEtors1 * p_tor2 * (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * exp_tor2_kl;
+    const double cmn = -fn10 * CV;
+    const double CEtors7 = cmn * sin_jkl * tan_ijk_i;
+    const double CEtors8 = cmn * sin_ijk * tan_jkl_i;
+    const double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * fp.V1 - 2.0 * fp.V2 * exp_tor1 * cos_omega + 1.5 * fp.V3 * (cos2omega + 2.0 * sqr(cos_omega)));
+    const double fn12 = exp_cot2_ij * exp_cot2_jk * exp_cot2_kl;
+    const double cterm = (1.0 + (sqr(cos_omega) - 1.0) * sin_ijk * sin_jkl);
+    e_con += fp.p_cot1 * fn12 * cterm;
+    const double Cconj = -2.0 * fn12 * fp.p_cot1 * p_cot2 * cterm;
+    const double CEconj1 = Cconj * (BOA_ij - 1.5e0);
+    const double CEconj2 = Cconj * (BOA_jk - 1.5e0);
+    const double CEconj3 = Cconj * (BOA_kl - 1.5e0);
+    const double CEconj4 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_jkl * tan_ijk_i;
+    const double CEconj5 = -fp.p_cot1 * fn12 * (sqr(cos_omega) - 1.0) * sin_ijk * tan_jkl_i;
+    const double CEconj6 = 2.0 * fp.p_cot1 * fn12 * cos_omega * sin_ijk * sin_jkl;
+
+    atomicAdd(&v.b_Cdbopi[pk], CEtors2);
+    atomicAdd(&v.CdDelta[j], CEtors3);
+    atomicAdd(&v.CdDelta[k], CEtors3);
+    atomicAdd(&v.b_Cdbo[ph], (CEtors4 + CEconj1));
+    atomicAdd(&v.b_Cdbo[pk], (CEtors5 + CEconj2));
+    atomicAdd(&v.b_Cdbo[pw], (CEtors6 + CEconj3));
+    const double c74 = CEtors7 + CEconj4, c85 = CEtors8 + CEconj5, c96 = CEtors9 + CEconj6;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      atomicAdd(&v.f[3 * i + t], -(c74 * hjk_dk[t] + c96 * om.di[t]));
+      atomicAdd(&v.f[3 * j + t], -(c74 * hjk_dj[t] + c85 * jkl_di[t] + c96 * om.dj[t]));
+      atomicAdd(&v.f[3 * k + t], -(c74 * hjk_di[t] + c85 * jkl_dj[t] + c96 * om.dk[t]));
+      atomicAdd(&v.f[3 * l + t], -(c85 * jkl_dk[t] + c96 * om.dl[t]));
+    }
+  }
+  const int slots[2] = {E_TOR, E_CON};
+  double vals[2] = {e_tor, e_con};
+  block_commit<2>(v.en, slots, vals);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32)
-k_dbond(DevView v) {
+k_dbond(DevView v, BondedWork W) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int i = wg; i < v.N; i += nwg) {
@@ -653,15 +736,24 @@ k_dbond(DevView v) {
     if (cnt <= 0) continue;
     const double dsx = v.dDeltap_self[3 * i], dsy = v.dDeltap_self[3 * i + 1], dsz = v.dDeltap_self[3 * i + 2];
     const double cdd_i = v.CdDelta[i];
+    const double2 s56_i = W.sum56[i];  // (sum CEval5, sum CEval6) of the angles centred on i (zero for ghosts)
     double fx = 0, fy = 0, fz = 0, buf_c = 0;
     for (int e = lane; e < cnt; e += 32) {
       const int p = start + e;
       const int j = v.b_nbr[p];
       const int sym = v.b_sym[p];
       if (sym < 0) continue;
-      const double Cdbo = v.b_Cdbo[p] + v.b_Cdbo[sym];
-      const double Cdbopi = v.b_Cdbopi[p] + v.b_Cdbopi[sym];
-      const double Cdbopi2 = v.b_Cdbopi2[p] + v.b_Cdbopi2[sym];
+      const double2 s56_j = W.sum56[j];
+      double Cdbo = v.b_Cdbo[p] + v.b_Cdbo[sym];
+      double Cdbopi = v.b_Cdbopi[p] + v.b_Cdbopi[sym];
+      double Cdbopi2 = v.b_Cdbopi2[p] + v.b_Cdbopi2[sym];
+      if (s56_i.x != 0.0 || s56_i.y != 0.0 || s56_j.x != 0.0 || s56_j.y != 0.0) {
+        const double bo_p = v.b_bo[p].x, bo_s = v.b_bo[sym].x;
+        const double p3 = bo_p * bo_p * bo_p, q3 = bo_s * bo_s * bo_s;
+        Cdbo += s56_i.y * (p3 * p3 * bo_p) + s56_j.y * (q3 * q3 * bo_s);
+        Cdbopi += s56_i.x + s56_j.x;
+        Cdbopi2 += s56_i.x + s56_j.x;
+      }
       const double cdd = cdd_i + v.CdDelta[j];
       if (Cdbo == 0.0 && Cdbopi == 0.0 && Cdbopi2 == 0.0 && cdd == 0.0) continue;
       const double4 c1 = v.b_c1[p], c2 = v.b_c2[p], c3 = v.b_c3[p], der = v.b_der[p], geo = v.b_geo[p];
@@ -698,16 +790,29 @@ k_dbond(DevView v) {
 
 void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   if (v.n == 0) return;
+  BondedWork W = s.bonded_work();
+  RXB_CUDA(cudaMemsetAsync(W.n_ang, 0, 4 * sizeof(int), st));
+  RXB_CUDA(cudaMemsetAsync(W.sum56, 0, (size_t)v.N * sizeof(double2), st));
+  int t = s.tick(StepTimers::MULTI);
   k_multi<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  k_hbond<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  k_valtor<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  s.kernel_launches += 3;
+  s.tock(t);
+  t = s.tick(StepTimers::ENUM);
+  k_enum<<<kBlocks, kWarps * 32, 0, st>>>(v, P, W);
+  s.tock(t);
+  t = s.tick(StepTimers::HBOND);
+  k_hbond_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
+  s.tock(t);
+  t = s.tick(StepTimers::VALTOR);
+  k_angle_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
+  k_torsion_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
+  s.tock(t);
+  s.kernel_launches += 5;
 }
 
 void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   (void)P;
   if (v.N == 0) return;
-  k_dbond<<<kBlocks, kWarps * 32, 0, st>>>(v);
+  k_dbond<<<kBlocks, kWarps * 32, 0, st>>>(v, s.bonded_work());
   s.kernel_launches++;
 }
 

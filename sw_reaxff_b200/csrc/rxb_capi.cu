@@ -1,4 +1,6 @@
 // extern "C" layer of librxb200.so: thin, exception -> status translation only (see include/rxb200.h).
+#include <cuda_profiler_api.h>
+
 #include <cstring>
 #include <string>
 
@@ -166,6 +168,7 @@ int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x,
   });
 }
 int rxb_md_run(rxb_handle* h, int nsteps) { return guard([&] { h->sys->md_run(nsteps); }); }
+double rxb_md_last_run_ms(rxb_handle* h) { return h->sys->last_run_ms; }
 int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q) { return guard([&] { h->sys->md_get(x, v, f, q); }); }
 int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke) {
   return guard([&] {
@@ -215,6 +218,17 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
     d2h(c2.data(), s.b_c2.p, nb, s.stream()); d2h(c3.data(), s.b_c3.p, nb, s.stream());
     d2h(cd.data(), s.b_Cdbo.p, nb, s.stream()); d2h(cdpi.data(), s.b_Cdbopi.p, nb, s.stream());
     d2h(cdpi2.data(), s.b_Cdbopi2.p, nb, s.stream());
+    // effective coefficients: the per-centre angle sums (CEval5/CEval6) are applied to every bond of the centre inside
+    // K-dbond; fold them in here so that the export equals the reference's Cdbo/Cdbopi/Cdbopi2 arrays
+    std::vector<double2> s56(N);
+    std::vector<int> bs(N), bcn(N);
+    d2h(s56.data(), s.sum56.p, N, s.stream());
+    d2h(bs.data(), s.b_start.p, N, s.stream()); d2h(bcn.data(), s.b_cnt.p, N, s.stream());
+    for (size_t i = 0; i < N; i++)
+      for (int p = bs[i]; p < bs[i] + bcn[i]; p++) {
+        const double b = bo[p].x, b3 = b * b * b;
+        cd[p] += s56[i].y * (b3 * b3 * b); cdpi[p] += s56[i].x; cdpi2[p] += s56[i].x;
+      }
     for (size_t p = 0; p < nb; p++) {
       double* o = fld + 31 * p;
       const double dv[3] = {geo[p].y, geo[p].z, geo[p].w};
@@ -257,9 +271,32 @@ int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val) {
 int rxb_profile(rxb_handle* h, int enable, double* ms9) {
   return guard([&] {
     System& s = *h->sys;
-    if (ms9) for (int k = 0; k < rxb::StepTimers::NUM; k++) ms9[k] = s.timers.ms[k];
+    s.resolve_timers();
+    if (ms9) for (int k = 0; k < rxb::StepTimers::NUM; k++) { ms9[k] = s.timers.ms[k]; ms9[rxb::StepTimers::NUM + k] = (double)s.timers.calls[k]; }
     if (enable >= 0) { s.profile = enable != 0; if (enable) s.timers = rxb::StepTimers(); }
   });
+}
+
+long rxb_parse_dump(const char* control_file, const char* ffield_file, int ntypes, const char* const* elements, int lgvdw,
+                    int enobonds, double* out, long cap) {
+  long count = -1;
+  int rc = guard([&] {
+    rxb::ForceField ff;
+    ff.ctl.lgflag = lgvdw;
+    ff.ctl.enobondsflag = enobonds;
+    std::string e = ff.load_control(control_file);
+    if (e.empty()) e = ff.load_ffield(ffield_file);
+    if (e.empty()) e = ff.set_elements(ntypes, elements);
+    if (!e.empty()) throw std::runtime_error(e);
+    std::vector<double> v = ff.dump();
+    if (out) for (long i = 0; i < (long)v.size() && i < cap; i++) out[i] = v[i];
+    count = (long)v.size();
+  });
+  return rc == 0 ? count : -1;
+}
+
+int rxb_profiler_range(int start) {
+  return guard([&] { if (start) RXB_CUDA(cudaProfilerStart()); else RXB_CUDA(cudaProfilerStop()); });
 }
 
 }  // extern "C"

@@ -67,6 +67,17 @@ struct DevView {
   double* virial;      // 6
 };
 
+// dense work lists of the bonded terms (rxb_bonded.cu: K-enum fills, the item kernels consume)
+struct BondedWork {
+  int4* ang;      // (j, pk, ph, -)
+  int4* tor;      // (j, pk, ph, pw)
+  int4* hb;       // (j, pi, k, -)
+  int* n_ang; int* n_tor; int* n_hb;   // device cursors (contiguous: n_ang, n_tor, n_hb, pad)
+  int cap_ang, cap_tor, cap_hb;
+  double4* sbo;   // per local centre: SBO2, CSBO2, dSBO1, dSBO2
+  double2* sum56; // per atom: sum CEval5, sum CEval6 over the angles centred on it
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

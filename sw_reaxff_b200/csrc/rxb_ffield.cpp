@@ -293,7 +293,12 @@ void ForceField::derive() {
   T[1] = 140.0 * a3 * b3 / d7;
   T[0] = (-35.0 * a3 * b2 * b2 + 21.0 * a2 * b3 * b2 + 7.0 * swa * b3 * b3 + b3 * b3 * swb) / d7;
   const double p_vdW1 = gp.size() > 28 ? gp[28] : 0.0;
-  for (PairPar& x : pair) x.powgi_vdW1 = (x.gamma_w > 0.0) ? pow(1.0 / x.gamma_w, p_vdW1) : 0.0;
+  for (PairPar& x : pair) {
+    x.powgi_vdW1 = (x.gamma_w > 0.0) ? pow(1.0 / x.gamma_w, p_vdW1) : 0.0;
+    x.log_r_s = x.r_s > 0.0 ? log(x.r_s) : 0.0;
+    x.log_r_p = x.r_p > 0.0 ? log(x.r_p) : 0.0;
+    x.log_r_pp = x.r_pp > 0.0 ? log(x.r_pp) : 0.0;
+  }
 }
 
 std::vector<double> ForceField::dump() const {

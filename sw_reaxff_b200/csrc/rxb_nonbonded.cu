@@ -53,7 +53,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
             double T = qc.Tap[7] * r + qc.Tap[6];
             T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
             T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-            const double denom = pow(r * r * r + shld[ti * nt + tj], 0.3333333333333);
+            const double denom = cbrt(r * r * r + shld[ti * nt + tj]);  // reference: pow(x, 0.3333333333333), < 3e-13 rel.
             val = T * kEvToKcal / denom;
           }
         }
@@ -111,13 +111,15 @@ k_nonbonded(DevView v, DevParams P) {
       dT += Tap[1] / r_ij;
       double e_vdW, CEvd, e_core = 0, e_lg = 0;
       if (vdw_type == 1 || vdw_type == 3) {
-        const double powr = pow(r_ij, p_vdW1);
-        const double powgi = tw.powgi_vdW1;
-        const double fn13 = pow(powr + powgi, p_vdW1i);
-        const double exp1 = exp(tw.alpha * (1.0 - fn13 / tw.r_vdW));
+        // r^p, (r^p + g^-p)^(1/p) and the two derivative powers from 2 log + 2 exp (the serial form calls pow 5x);
+        // exp1 = exp2^2.  Each identity holds to ~1e-15 relative, far inside the 1e-8 parity tolerance.
+        const double powr = exp(p_vdW1 * log(r_ij));
+        const double ssum = powr + tw.powgi_vdW1;
+        const double fn13 = exp(p_vdW1i * log(ssum));
         const double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 / tw.r_vdW));
+        const double exp1 = exp2 * exp2;
         e_vdW = tw.D * (exp1 - 2.0 * exp2);
-        const double dfn13 = pow(powr + powgi, p_vdW1i - 1.0) * pow(r_ij, p_vdW1 - 2.0);
+        const double dfn13 = (fn13 / ssum) * (powr / r2);
         CEvd = dT * e_vdW - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) * dfn13;
       } else {
         const double exp1 = exp(tw.alpha * (1.0 - r_ij / tw.r_vdW));
@@ -137,7 +139,7 @@ k_nonbonded(DevView v, DevParams P) {
         }
       }
       const double dr3gamij_1 = r_ij * r_ij * r_ij + tw.gamma;
-      const double dr3gamij_3 = pow(dr3gamij_1, 0.33333333333333);
+      const double dr3gamij_3 = cbrt(dr3gamij_1);  // reference: pow(x, 0.33333333333333); differs by < 3e-14 relative
       const double qq = kCele * pi.w * pj.w;
       const double CEclmb = qq * (dT - T * r_ij / dr3gamij_1) / dr3gamij_3;
       const double ftot = CEvd + CEclmb;  // f_i = +ftot * dvec  (reference: fCdDelta[i] += -ftot*dvec, f = -fCdDelta)

@@ -31,7 +31,7 @@ struct PairPar {  // two_body_parameters
   double rcore, ecore, acore, lgcij, lgre;
   double v13cor, ovc;
   double powgi_vdW1;   // derived: (1/gamma_w)^p_vdW1, hoisted out of the pair loop (reaxc_nonbonded_sw64.c:137)
-  double pad_;
+  double log_r_s, log_r_p, log_r_pp;  // derived: logs of the bond radii, so that (d/r)^p = exp(p (log d - log r))
 };
 
 struct AnglePar { double theta_00, p_val1, p_val2, p_coa1, p_val7, p_pen1, p_val4; };

@@ -293,11 +293,11 @@ void System::qeq_pre_force() {
     Tap[1] = 140.0 * a3 * b3 / d7;
     Tap[0] = (-35.0 * a3 * b2 * b2 + 21.0 * a2 * b3 * b2 + 7.0 * swa * b3 * b3 + b3 * b3 * swb) / d7;
   }
-  tick(StepTimers::QEQ_H);
+  const int t_QEQ_H = tick(StepTimers::QEQ_H);
   launch_far_and_H(*this, v, dp_, Tap, shld_d.p, qeq_swb, st_);
-  tock(StepTimers::QEQ_H);
+  tock(t_QEQ_H);
 
-  tick(StepTimers::QEQ_CG);
+  const int t_QEQ_CG = tick(StepTimers::QEQ_CG);
   const size_t nn = n, NN = N;
   q_x.resize(NN); q_d.resize(NN);
   q_r.resize(nn); q_u.resize(nn); q_w.resize(nn); q_p.resize(nn); q_ss.resize(nn); q_v.resize(nn); q_z.resize(nn);
@@ -308,7 +308,9 @@ void System::qeq_pre_force() {
   const int fb = nghost > 0 ? (nghost + 255) / 256 : 0;
   auto forward = [&](double2* vec) { if (fb) { k_forward2<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, vec); kernel_launches++; } };
   auto spmv = [&](const double2* x, double2* y, const QeqDev* gate, int parity) {
+    const int ts = tick(StepTimers::SPMV);
     k_spmv2<<<kBlocksSpmv, kWarps * 32, 0, st_>>>(n, vl.off.p, far_num.p, far_idx.p, H_val.p, type.p, dp_.atom, x, y, gate, parity);
+    tock(ts);
     kernel_launches++;
   };
   k_qeq_init<<<kVecBlocks, kVecThreads, 0, st_>>>(n, type.p, dp_.atom, q_s_hist.p, q_t_hist.p, q_x.p, q_b.p, q_Hdia_inv.p, Q);
@@ -353,7 +355,7 @@ void System::qeq_pre_force() {
   matvecs_t = iters_host[1];
   qeq_iters_total += (matvecs_s > matvecs_t ? matvecs_s : matvecs_t);
   qeq_ran_this_step_ = true;
-  tock(StepTimers::QEQ_CG);
+  tock(t_QEQ_CG);
 }
 
 }  // namespace rxb

@@ -193,8 +193,6 @@ void Box::set(double xprd, double yprd, double zprd, double xy, double xz, doubl
 System::System(int device) : device_(device) {
   RXB_CUDA(cudaSetDevice(device));
   RXB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
-  RXB_CUDA(cudaEventCreate(&ev_[0]));
-  RXB_CUDA(cudaEventCreate(&ev_[1]));
   b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6);
   RXB_CUDA(cudaMemset(overflow.p, 0, sizeof(int)));
 }
@@ -202,8 +200,7 @@ System::System(int device) : device_(device) {
 System::~System() {
   cudaSetDevice(device_);
   if (h_pin_) cudaFreeHost(h_pin_);
-  cudaEventDestroy(ev_[0]);
-  cudaEventDestroy(ev_[1]);
+  for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   if (st_) cudaStreamDestroy(st_);
 }
 
@@ -216,17 +213,31 @@ double* System::pin(size_t doubles) {
   return h_pin_;
 }
 
-void System::tick(int) {
-  if (profile) RXB_CUDA(cudaEventRecord(ev_[0], st_));
+int System::tick(int which) {
+  if (!profile) return -1;
+  if (ev_used_ + 2 > ev_pool_.size()) {
+    for (int k = 0; k < 64; k++) { cudaEvent_t e; RXB_CUDA(cudaEventCreate(&e)); ev_pool_.push_back(e); }
+  }
+  const int a = (int)ev_used_++, b = (int)ev_used_++;
+  RXB_CUDA(cudaEventRecord(ev_pool_[a], st_));
+  ev_pending_.push_back(Pending{which, a, b});
+  return (int)ev_pending_.size() - 1;
 }
-void System::tock(int which) {
-  if (!profile) return;
-  RXB_CUDA(cudaEventRecord(ev_[1], st_));
-  RXB_CUDA(cudaEventSynchronize(ev_[1]));
-  float ms = 0;
-  RXB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-  timers.ms[which] += ms;
-  timers.calls[which]++;
+void System::tock(int id) {
+  if (id < 0) return;
+  RXB_CUDA(cudaEventRecord(ev_pool_[ev_pending_[id].b], st_));
+}
+void System::resolve_timers() {
+  if (ev_pending_.empty()) return;
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  for (const Pending& p : ev_pending_) {
+    float ms = 0;
+    RXB_CUDA(cudaEventElapsedTime(&ms, ev_pool_[p.a], ev_pool_[p.b]));
+    timers.ms[p.which] += ms;
+    timers.calls[p.which]++;
+  }
+  ev_pending_.clear();
+  ev_used_ = 0;
 }
 
 void System::upload_params() {
@@ -280,6 +291,10 @@ void System::ensure_atom_capacity() {
   Delta.resize(NN); Delta_val.resize(NN); vlpex.resize(NN); nlp.resize(NN); Delta_lp.resize(NN); dDelta_lp.resize(NN);
   Delta_lp_temp.resize(NN);
   far_num.resize(n > 0 ? n : 1);
+  vt_sbo.resize(n > 0 ? n : 1); sum56.resize(NN > 0 ? NN : 1); it_count.resize(4);
+  if (cap_ang < n * 6 + 1024) { cap_ang = n * 6 + 1024; it_ang.resize(cap_ang); }
+  if (cap_tor < n * 16 + 1024) { cap_tor = n * 16 + 1024; it_tor.resize(cap_tor); }
+  if (cap_hb < n * 20 + 1024) { cap_hb = n * 20 + 1024; it_hb.resize(cap_hb); }
   if (cap_bonds < (int)std::min<size_t>(NN * 14 + 1024, 2000000000)) ensure_bond_capacity((int)std::min<size_t>(NN * 14 + 1024, 2000000000));
 }
 
@@ -363,6 +378,15 @@ void System::get_charges(double* q_host) {
   kernel_launches++;
 }
 
+BondedWork System::bonded_work() {
+  BondedWork W{};
+  W.ang = it_ang.p; W.tor = it_tor.p; W.hb = it_hb.p;
+  W.n_ang = it_count.p; W.n_tor = it_count.p + 1; W.n_hb = it_count.p + 2;
+  W.cap_ang = cap_ang; W.cap_tor = cap_tor; W.cap_hb = cap_hb;
+  W.sbo = vt_sbo.p; W.sum56 = sum56.p;
+  return W;
+}
+
 DevView System::view() {
   DevView v{};
   v.n = n; v.N = N; v.cap_bonds = cap_bonds;
@@ -384,7 +408,7 @@ DevView System::view() {
 
 void System::build_neighbors() {
   RXB_CUDA(cudaSetDevice(device_));
-  tick(StepTimers::NEIGH);
+  const int t_NEIGH = tick(StepTimers::NEIGH);
   const double cn = cutneigh();
   // Verlet list for local rows: bins of cn/2, +-2 cells
   cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
@@ -396,7 +420,7 @@ void System::build_neighbors() {
   far_idx.resize((size_t)std::max<long long>(vl.nnz, 1));
   H_val.resize((size_t)std::max<long long>(vl.nnz, 1));
   kernel_launches += 12;
-  tock(StepTimers::NEIGH);
+  tock(t_NEIGH);
 }
 
 void System::step_forces(bool eflag, bool vflag) {
@@ -405,21 +429,21 @@ void System::step_forces(bool eflag, bool vflag) {
   RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(en_d.p, 0, E_NUM * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, 6 * sizeof(double), st_));
-  tick(StepTimers::BONDS);
+  const int t_BONDS = tick(StepTimers::BONDS);
   launch_bond_list(*this, v, dp_, st_);
-  tock(StepTimers::BONDS);
-  tick(StepTimers::NONB);
+  tock(t_BONDS);
+  const int t_NONB = tick(StepTimers::NONB);
   launch_nonbonded(*this, v, dp_, eflag || vflag, st_);
-  tock(StepTimers::NONB);
-  tick(StepTimers::BO);
+  tock(t_NONB);
+  const int t_BO = tick(StepTimers::BO);
   launch_bond_orders(*this, v, dp_, st_);
-  tock(StepTimers::BO);
-  tick(StepTimers::BONDED);
+  tock(t_BO);
+  const int t_BONDED = tick(StepTimers::BONDED);
   launch_bonded(*this, v, dp_, st_);
-  tock(StepTimers::BONDED);
-  tick(StepTimers::DBOND);
+  tock(t_BONDED);
+  const int t_DBOND = tick(StepTimers::DBOND);
   launch_dbond(*this, v, dp_, st_);
-  tock(StepTimers::DBOND);
+  tock(t_DBOND);
   if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
 }
 
@@ -434,9 +458,10 @@ void System::compute(bool eflag, bool vflag) {
   qeq_ran_this_step_ = false;
   for (int attempt = 0; attempt < 4; attempt++) {
     step_forces(eflag, vflag);
-    int h[2];
+    int h[2], wk[4];
     RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
     RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaMemcpyAsync(wk, it_count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
     if (eflag || vflag) {
       RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
       RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
@@ -444,10 +469,16 @@ void System::compute(bool eflag, bool vflag) {
     RXB_CUDA(cudaStreamSynchronize(st_));
     num_bonds = h[0];
     overflow_flag = h[1];
-    if (!(overflow_flag & 2)) break;
-    // bond rows did not fit: grow and replay the force computation of this step (positions are unchanged)
+    num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
+    const bool lists_fit = wk[0] <= cap_ang && wk[1] <= cap_tor && wk[2] <= cap_hb;
+    if (!(overflow_flag & 2) && lists_fit) break;
+    // a list did not fit: grow and replay the force computation of this step (positions are unchanged)
     RXB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st_));
-    ensure_bond_capacity((int)std::min<long long>((long long)h[0] + h[0] / 4 + 1024, 2000000000LL));
+    if (overflow_flag & 2) ensure_bond_capacity((int)std::min<long long>((long long)h[0] + h[0] / 4 + 1024, 2000000000LL));
+    if (wk[0] > cap_ang) { cap_ang = wk[0] + wk[0] / 4 + 1024; it_ang.resize(cap_ang); }
+    if (wk[1] > cap_tor) { cap_tor = wk[1] + wk[1] / 4 + 1024; it_tor.resize(cap_tor); }
+    if (wk[2] > cap_hb) { cap_hb = wk[2] + wk[2] / 4 + 1024; it_hb.resize(cap_hb); }
+    overflow_flag &= ~2;
   }
   if (overflow_flag & ~2)
     throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
@@ -516,6 +547,8 @@ void System::md_run(int nsteps) {
   memcpy(b.h, box.h, sizeof(b.h));
   memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
   const double dtv = md_dt, dtf = 0.5 * md_dt * kFtm2v;
+  if (!run_ev_[0]) { RXB_CUDA(cudaEventCreate(&run_ev_[0])); RXB_CUDA(cudaEventCreate(&run_ev_[1])); }
+  RXB_CUDA(cudaEventRecord(run_ev_[0], st_));
   for (int s = 0; s < nsteps; s++) {
     ntimestep++;
     k_nve_initial<<<nblk(n), 256, 0, st_>>>(n, dtf, dtv, ltype_d.p, mass_d.p, f.p, v_d.p, xq.p);
@@ -531,7 +564,11 @@ void System::md_run(int nsteps) {
     k_nve_final<<<nblk(n), 256, 0, st_>>>(n, dtf, ltype_d.p, mass_d.p, f.p, v_d.p);
     kernel_launches += 3;
   }
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_CUDA(cudaEventRecord(run_ev_[1], st_));
+  RXB_CUDA(cudaEventSynchronize(run_ev_[1]));
+  float ms = 0;
+  RXB_CUDA(cudaEventElapsedTime(&ms, run_ev_[0], run_ev_[1]));
+  last_run_ms = ms;
 }
 
 void System::md_get(double* x, double* v, double* fo, double* q) {

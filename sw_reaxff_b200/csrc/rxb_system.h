@@ -83,7 +83,7 @@ struct Box {  // LAMMPS triclinic box, lo = 0
 struct QeqScalars;  // device-side CG scalars, rxb_qeq.cu
 
 struct StepTimers {
-  enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, OTHER, NUM };
+  enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, SPMV, HBOND, VALTOR, MULTI, ENUM, NUM };
   double ms[NUM] = {0};
   long calls[NUM] = {0};
 };
@@ -147,6 +147,10 @@ class System {
   std::vector<double> params_dump() const { return ff.dump(); }
   cudaStream_t stream() const { return st_; }
   StepTimers timers;
+  int tick(int which);          // lazy CUDA-event timers on the launch stream: no sync inside a step
+  void tock(int id);
+  void resolve_timers();
+  double last_run_ms = 0.0;     // device time of the last md_run (CUDA events on the launch stream)
   bool profile = false;
   long kernel_launches = 0;
 
@@ -163,6 +167,14 @@ class System {
   DBuf<double> total_bop, dDeltap_self, total_bo, Delta_boc, Delta, Delta_val, vlpex, nlp, Delta_lp, dDelta_lp, Delta_lp_temp;
   DBuf<double2> Deltap;
   DBuf<double> en_d, virial_d;
+  // bonded work lists
+  DBuf<int4> it_ang, it_tor, it_hb;
+  DBuf<int> it_count;                 // n_ang, n_tor, n_hb, pad
+  DBuf<double4> vt_sbo;
+  DBuf<double2> sum56;
+  int cap_ang = 0, cap_tor = 0, cap_hb = 0;
+  int num_ang = 0, num_tor = 0, num_hb = 0;
+  BondedWork bonded_work();
   // qeq
   DBuf<double> q_s_hist, q_t_hist;   // [n][5]
   DBuf<double2> q_x, q_r, q_u, q_w, q_p, q_ss, q_v, q_z, q_d, q_q, q_b, q_m;  // (s,t) interleaved; q_x,q_d length N
@@ -179,19 +191,21 @@ class System {
  private:
   int device_;
   cudaStream_t st_ = nullptr;
-  cudaEvent_t ev_[2];
+  std::vector<cudaEvent_t> ev_pool_;
+  struct Pending { int which; int a, b; };
+  std::vector<Pending> ev_pending_;
+  size_t ev_used_ = 0;
   DBuf<char> param_blob_;
   DevParams dp_{};
   CellList cells_a_, cells_b_;
   bool qeq_ran_this_step_ = false;
+  cudaEvent_t run_ev_[2] = {nullptr, nullptr};
   double* h_pin_ = nullptr;  // pinned staging
   size_t h_pin_cap_ = 0;
   double* pin(size_t doubles);
   void step_forces(bool eflag, bool vflag);
   void ensure_atom_capacity();
   void ensure_bond_capacity(int cap);
-  void tick(int which);
-  void tock(int which);
   void md_make_ghosts();
   void md_force();
   friend struct Launch;

@@ -1,0 +1,137 @@
+"""CPU tests of the oracle itself: golden fixtures, finite-difference forces, invariants (no GPU needed).
+
+The reference has no tests: these are the reference-independent pins SURVEY.md §8c asks for.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def eval_static(nx, ny, nz, perturb, seed, scale, tol):
+    cfg = H.static_config(nx, ny, nz, perturb=perturb, seed=seed, scale=scale, qeq=False)
+    o = cfg["oracle"]
+    n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    o.set_atoms(n, x, ty, tg, np.zeros(len(x)))
+    o.build_neighbors(12.5)
+    o.qeq_init(0.0, 10.0, tol)
+    o.qeq_set_hist(np.zeros((n, 5)), np.zeros((n, 5)))
+    mv = o.qeq_pre_force(owner)
+    o.compute()
+    return cfg, o, mv
+
+
+@pytest.mark.parametrize("name", ["tatb_1x1x1", "tatb_1x1x1_perturbed", "tatb_2x1x1_compressed"])
+def test_oracle_matches_golden(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg, o, mv = eval_static(int(g["nx"]), int(g["ny"]), int(g["nz"]), float(g["perturb"]), int(g["seed"]), float(g["scale"]), float(g["tol"]))
+    n, owner = cfg["n"], cfg["owner"]
+    assert n == int(g["n"]) and len(cfg["x"]) == int(g["nall"])
+    e, vir = o.energies()
+    np.testing.assert_allclose(e, g["energies"], rtol=1e-12, atol=1e-9)
+    f = o.forces()
+    fl = f[:n].copy()
+    np.add.at(fl, owner, f[n:])
+    np.testing.assert_allclose(fl, g["f_local"], rtol=0, atol=1e-9 * np.abs(g["f_local"]).max())
+    np.testing.assert_allclose(o.q()[:n], g["q_local"], rtol=0, atol=1e-12)
+    assert tuple(mv) == tuple(g["matvecs"])
+    bs, be, *_ = o.bonds()
+    assert np.array_equal((be - bs)[:n], g["nbonds_per_atom"])  # integer work: exact
+    assert np.array_equal(np.diff(o.get_neighbors()[0])[:n], g["verlet_count"])
+
+
+def test_tatb_step0_energy_and_invariants():
+    cfg, o, mv = eval_static(1, 1, 1, 0.0, 0, 1.0, 1e-6)
+    n, owner = cfg["n"], cfg["owner"]
+    e, _ = o.energies()
+    # step-0 potential energy of data.tatb + ffield.reax (kcal/mol); see make_golden.py for provenance
+    assert abs(e.sum() - (-44760.998)) < 2e-3
+    f = o.forces()
+    fl = f[:n].copy()
+    np.add.at(fl, owner, f[n:])
+    assert np.abs(fl.sum(0)).max() < 1e-9 * np.abs(fl).max() * n      # Newton's third law after reverse_comm
+    q = o.q()
+    assert abs(q[:n].sum()) < 1e-10                                   # charge neutrality (calculate_Q)
+    assert np.allclose(q[n:], q[owner])                               # ghost charges forwarded
+    # symmetric corrected bond orders BO_ij == BO_ji
+    bs, be, nbr, sym, fld = o.bonds()
+    assert (sym >= 0).all()
+    assert np.abs(fld[:, 4] - fld[sym, 4]).max() < 1e-13
+    assert np.array_equal(nbr[sym][bs[0]:be[0]], np.zeros(be[0] - bs[0], dtype=np.int32))
+
+
+def test_replication_invariance():
+    """Energies are extensive: the 2x1x1 replica has exactly twice the 1x1x1 energies (different ghost sets, lists)."""
+    _, o1, _ = eval_static(1, 1, 1, 0.0, 0, 1.0, 1e-12)
+    _, o2, _ = eval_static(2, 1, 1, 0.0, 0, 1.0, 1e-12)
+    e1, _ = o1.energies()
+    e2, _ = o2.energies()
+    np.testing.assert_allclose(e2, 2 * e1, rtol=1e-9, atol=1e-7)
+
+
+def test_finite_difference_forces():
+    """F = -dE/dx at fixed charges, per energy term summed (central differences, h = 1e-5 A)."""
+    cfg, o, _ = eval_static(1, 1, 1, 0.1, 3, 1.0, 1e-10)
+    n, x, ty, tg, owner = cfg["n"], cfg["x"].copy(), cfg["type"], cfg["tag"], cfg["owner"]
+    q = o.q().copy()
+    f = o.forces()
+    fl = f[:n].copy()
+    np.add.at(fl, owner, f[n:])
+    h = 1e-5
+    rng = np.random.default_rng(0)
+    for i in rng.choice(n, size=4, replace=False):
+        images = np.concatenate([[i], n + np.nonzero(owner == i)[0]])
+        for d in range(3):
+            es = []
+            for sgn in (+1, -1):
+                xx = x.copy()
+                xx[images, d] += sgn * h
+                o.set_atoms(n, xx, ty, tg, q)
+                o.compute()                      # neighbour list (12.5 A) still valid for a 1e-5 A move
+                es.append(o.energies()[0].sum())
+            fd = -(es[0] - es[1]) / (2 * h)
+            assert abs(fd - fl[i, d]) < 2e-5 * max(1.0, abs(fl[i, d])), (i, d, fd, fl[i, d])
+
+
+def test_qeq_solution_satisfies_equations():
+    """H s = -chi and H t = -1 to the CG tolerance; q = s - (sum s/sum t) t."""
+    cfg, o, mv = eval_static(1, 1, 1, 0.05, 4, 1.0, 1e-10)
+    n, owner = cfg["n"], cfg["owner"]
+    off, num, col, val = o.qeq_H()
+    s, t = o.qeq_st()
+    # the solver only halo-exchanges the search direction; ghost entries of s/t are stale by design
+    s = np.concatenate([s[:n], s[owner]]); t = np.concatenate([t[:n], t[owner]])
+    ty = cfg["type"]
+    # eta/chi per element from the parameter dump: recompute through the public oracle API instead
+    Hs = np.zeros(n); Ht = np.zeros(n)
+    for i in range(n):
+        c = col[off[i]:off[i] + num[i]]
+        v = val[off[i]:off[i] + num[i]]
+        Hs[i] = (v * s[c]).sum(); Ht[i] = (v * t[c]).sum()
+    # diagonal: eta_i; derive eta from the t equation residual being ~0 for a converged solve
+    eta = (-1.0 - Ht) / t[:n]
+    for k in (1, 2, 3, 4):
+        assert np.ptp(eta[ty[:n] == k]) < 1e-4      # one eta per element
+    chi = -(Hs + eta * s[:n])
+    for k in (1, 2, 3, 4):
+        assert np.ptp(chi[ty[:n] == k]) < 1e-3      # one chi per element
+    q = o.q()[:n]
+    u = s[:n].sum() / t[:n].sum()
+    np.testing.assert_allclose(q, s[:n] - u * t[:n], atol=1e-14)
+    assert mv[0] > 1 and mv[1] > 1
+
+
+def test_md_energy_conservation_cpu():
+    box, x, t, tag = H.tatb_cell(1, 1, 1)
+    v = H.maxwell_velocities(t, 300.0, 12345)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-8)
+    r0 = o.md_get()
+    o.md_run(10)
+    r1 = o.md_get()
+    e0, e1 = r0["pe"] + r0["ke"], r1["pe"] + r1["ke"]
+    assert abs(e1 - e0) < 2e-3 * r0["ke"], (e0, e1)
