@@ -33,9 +33,16 @@ std::string read_force_field(const char* path, Params& p) {
   FILE* fp = fopen(path, "r");
   if (!fp) return std::string("cannot open force field file ") + path;
   char s[1024];
+  // The reference tokenises into a persistent buffer and never clears it (reaxc_tool_box_sunway.cpp:42-57): a field
+  // missing on the current line reads the token a previous, longer line left in that slot (this decides e.g. the
+  // lgcij column of the off-diagonal section, reaxc_ffield_sunway.cpp:512).  Restated as-is.
+  std::vector<std::string> slots;
   auto line = [&]() -> std::vector<std::string> {
     if (!fgets(s, sizeof(s), fp)) s[0] = 0;
-    return tokenize(s);
+    std::vector<std::string> now = tokenize(s);
+    if (slots.size() < now.size()) slots.resize(now.size());
+    for (size_t i = 0; i < now.size(); i++) slots[i] = now[i];
+    return slots;
   };
   line();  // header comment
   auto t = line();
@@ -74,12 +81,12 @@ std::string read_force_field(const char* path, Params& p) {
     e.r_pi_pi = tokd(t, 0); e.p_lp2 = tokd(t, 1); e.b_o_131 = tokd(t, 3); e.b_o_132 = tokd(t, 4);
     e.b_o_133 = tokd(t, 5);
     t = line();
-    if (t.size() < 3) { fclose(fp); return "Inconsistent ffield file"; }
+    if (tokenize(s).size() < 3) { fclose(fp); return "Inconsistent ffield file"; }
     e.p_ovun2 = tokd(t, 0); e.p_val3 = tokd(t, 1); e.valency_val = tokd(t, 3); e.p_val5 = tokd(t, 4);
     e.rcore2 = tokd(t, 5); e.ecore2 = tokd(t, 6); e.acore2 = tokd(t, 7);
     if (p.lgflag) {
       t = line();
-      if (t.size() > 3) { fclose(fp); return "Inconsistent ffield file (lg)"; }
+      if (tokenize(s).size() > 3) { fclose(fp); return "Inconsistent ffield file (lg)"; }
       e.lgcij = tokd(t, 0); e.lgre = tokd(t, 1);
     }
     // vdw_type detection, :241-293

@@ -23,9 +23,10 @@ namespace {
 
 struct Fields {
   std::vector<std::string> tok;
+  size_t count = 0;  // tokens on THIS line; tok may hold more (see LineSource)
   double num(size_t i) const { return i < tok.size() ? atof(tok[i].c_str()) : 0.0; }
   int integer(size_t i) const { return i < tok.size() ? atoi(tok[i].c_str()) : 0; }
-  size_t size() const { return tok.size(); }
+  size_t size() const { return count; }
 };
 
 Fields split_fields(const std::string& line) {
@@ -40,6 +41,7 @@ Fields split_fields(const std::string& line) {
     f.tok.emplace_back(line.substr(b, e - b));
     pos = e;
   }
+  f.count = f.tok.size();
   return f;
 }
 
@@ -48,16 +50,29 @@ class LineSource {
   explicit LineSource(const char* path) : in_(path) {}
   bool ok() const { return in_.good() || in_.eof(); }
   bool opened() const { return in_.is_open(); }
+  // Force-field lines are read the way the reference reads them: columns that are absent on a line keep the token a
+  // previous, longer line left in that slot (the reference's token buffer is persistent and never cleared,
+  // reaxc_tool_box_sunway.cpp:42-57).  Only the unused-without-lgvdw lgcij column of the off-diagonal section depends
+  // on it (reaxc_ffield_sunway.cpp:512), but it keeps the parsed tables identical to the reference's, bit for bit.
   Fields next() {
     std::string line;
-    if (!std::getline(in_, line)) return Fields{};
-    if (line.size() > 1023) line.resize(1023);  // MAX_LINE of the reference's fgets buffer
-    return split_fields(line);
+    Fields now;
+    if (std::getline(in_, line)) {
+      if (line.size() > 1023) line.resize(1023);  // MAX_LINE of the reference's fgets buffer
+      now = split_fields(line);
+    }
+    if (slots_.size() < now.tok.size()) slots_.resize(now.tok.size());
+    for (size_t i = 0; i < now.tok.size(); i++) slots_[i] = now.tok[i];
+    Fields f;
+    f.tok = slots_;
+    f.count = now.count;
+    return f;
   }
   void skip(int n) { for (int i = 0; i < n; i++) next(); }
 
  private:
   std::ifstream in_;
+  std::vector<std::string> slots_;
 };
 
 template <class T>
