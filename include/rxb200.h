@@ -82,7 +82,16 @@ int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x,
 int rxb_md_run(rxb_handle* h, int nsteps);
 double rxb_md_last_run_ms(rxb_handle* h); /* device time of the last rxb_md_run: CUDA events on the launch stream */
 int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q); /* local atoms, any may be NULL */
+int rxb_md_get_tags(rxb_handle* h, int* tags); /* tags of the current local atoms (they migrate in multi-GPU runs) */
 int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke);
+
+/* ---- multi-GPU: one process per GPU, bricks px*py*pz == world in lamda space, NCCL inside the library.
+ *      Replaces what the reference gets from the LAMMPS core over MPI: exchange/borders, forward_comm(x), reverse_comm(f),
+ *      forward_comm_fix of the CG direction and MPI_Allreduce of the dots (fix_qeq_reax_sunway.cpp:1043-1132).
+ *      rank 0 calls rxb_dist_unique_id and broadcasts the 128 bytes; every rank then calls rxb_dist_init BEFORE
+ *      rxb_md_setup, passing to rxb_md_setup only the atoms it currently holds (any initial assignment). */
+int rxb_dist_unique_id(char* out128);
+int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px, int py, int pz);
 
 /* ---- introspection (tests, fix reax/c/bonds, fix reax/c/species) ---- */
 /* counts[0..7] = nlocal, nall, verlet nnz, bond-candidate nnz, directed bonds, far nnz(sum), kernel launches, qeq iterations */

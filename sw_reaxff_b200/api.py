@@ -14,6 +14,7 @@ SYMBOLS = [
     "rxb_neigh_build", "rxb_qeq_pre_force", "rxb_qeq_set_history", "rxb_qeq_get_history", "rxb_get_charges",
     "rxb_pair_compute", "rxb_md_setup", "rxb_md_run", "rxb_md_get", "rxb_md_thermo", "rxb_get_counts",
     "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
+    "rxb_dist_unique_id", "rxb_dist_init", "rxb_md_get_tags",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -166,15 +167,34 @@ class Rxb:
         self.nall = int(self.counts()[1])
 
     def md_get(self):
-        n = self.nlocal
+        n = self.nlocal = int(self.counts()[0])
         x = np.zeros((n, 3)); v = np.zeros((n, 3)); f = np.zeros((n, 3)); q = np.zeros(n)
         self._chk(self.lib.rxb_md_get(self.h, _p(x), _p(v), _p(f), _p(q)))
         return dict(x=x, v=v, f=f, q=q)
+
+    def local_tags(self):
+        n = int(self.counts()[0])
+        t = np.zeros(n, dtype=np.int32)
+        self._chk(self.lib.rxb_md_get_tags(self.h, _p(t)))
+        return t
 
     def md_thermo(self):
         pv = np.zeros(14); pe = C.c_double(); ke = C.c_double()
         self._chk(self.lib.rxb_md_thermo(self.h, _p(pv), C.byref(pe), C.byref(ke)))
         return dict(pvector=pv, pe=pe.value, ke=ke.value)
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def dist_unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        if lib.rxb_dist_unique_id(buf) != 0:
+            raise RxbError(lib.rxb_last_error().decode())
+        return buf.raw
+
+    def dist_init(self, rank, world, uid, grid):
+        assert len(uid) == 128
+        self._chk(self.lib.rxb_dist_init(self.h, int(rank), int(world), C.c_char_p(uid), int(grid[0]), int(grid[1]), int(grid[2])))
 
     # ---- introspection ----
     def counts(self):

@@ -26,6 +26,7 @@ struct Stage {
 __global__ void __launch_bounds__(kWarps * 32)
 k_bond_list(DevView v, DevParams P) {
   __shared__ Stage stage[kWarps];
+  __shared__ int s_queue[kWarps][64];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int i = blockIdx.x * kWarps + wib;
   if (i >= v.N) return;
@@ -37,41 +38,69 @@ k_bond_list(DevView v, DevParams P) {
     const AtomPar ai = P.atom[ti];
     const double bo_cut = P.ctl.bo_cut, bond_cut = P.ctl.bond_cut, nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
     const long long beg = v.bc_off[i], end = v.bc_off[i + 1];
-    for (long long k0 = beg; k0 < end; k0 += 32) {
-      const long long k = k0 + lane;
+    int* queue = s_queue[wib];
+    int qn = 0;
+    // Phase 1 (cheap, all lanes): distance filter, survivors are queued.  Phase 2 (6 transcendentals per pair) runs on
+    // FULL warps drained from the queue: only ~30 % of the (bond_cut + skin) candidates are inside bond_cut, so doing the
+    // math in place would leave two thirds of the lanes idle.
+    for (long long k0 = beg; k0 < end || qn > 0; k0 += 32) {
+      if (k0 < end) {
+        const long long k = k0 + lane;
+        bool near = false;
+        int j = -1;
+        if (k < end) {
+          j = v.bc_idx[k];
+          const double4 pj = v.xq[j];
+          const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+          const double r2 = dx * dx + dy * dy + dz * dz;
+          near = r2 <= nonb_cut2 && sqrt(r2) <= bond_cut && v.type[j] >= 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, near);
+        if (near) queue[qn + __popc(m & ((1u << lane) - 1))] = j;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn < 32 && k0 + 32 < end) continue;   // keep filling until a full warp of work (or the row ends)
+      }
+      // ---- drain up to 32 queued candidates ----
+      const int take = min(qn, 32);
       bool hit = false;
       int j = -1;
       double d = 0, dx = 0, dy = 0, dz = 0, BO = 0, BO_s = 0, BO_pi = 0, BO_pi2 = 0, cBOp = 0, cPi = 0, cPi2 = 0;
-      if (k < end) {
-        j = v.bc_idx[k];
+      if (lane < take) {
+        j = queue[lane];
         const double4 pj = v.xq[j];
         dx = pj.x - pi.x; dy = pj.y - pi.y; dz = pj.z - pi.z;
         const double r2 = dx * dx + dy * dy + dz * dz;
         d = sqrt(r2);
         const int tj = v.type[j];
-        if (r2 <= nonb_cut2 && d <= bond_cut && tj >= 0) {
-          const AtomPar& aj = P.atom[tj];
-          const PairPar& tw = P.pair[ti * P.nt + tj];
-          // (d/r)^p as exp(p (log d - log r)): one log shared by the three terms instead of three pow() calls
-          // (agrees with pow to ~1e-15 relative; the reference's own CPE kernels use polynomial exp/pow)
-          double C12 = 0, C34 = 0, C56 = 0;
-          const double ld = log(d);
-          if (ai.r_s > 0.0 && aj.r_s > 0.0) { C12 = tw.p_bo1 * exp(tw.p_bo2 * (ld - tw.log_r_s)); BO_s = (1.0 + bo_cut) * exp(C12); }
-          if (ai.r_pi > 0.0 && aj.r_pi > 0.0) { C34 = tw.p_bo3 * exp(tw.p_bo4 * (ld - tw.log_r_p)); BO_pi = exp(C34); }
-          if (ai.r_pi_pi > 0.0 && aj.r_pi_pi > 0.0) { C56 = tw.p_bo5 * exp(tw.p_bo6 * (ld - tw.log_r_pp)); BO_pi2 = exp(C56); }
-          BO = BO_s + BO_pi + BO_pi2;
-          if (BO >= bo_cut) {
-            hit = true;
-            const double rr2 = d * d;
-            const double Cln_s = tw.p_bo2 * C12 / rr2, Cln_pi = tw.p_bo4 * C34 / rr2, Cln_pi2 = tw.p_bo6 * C56 / rr2;
-            cBOp = -(BO_s * Cln_s + BO_pi * Cln_pi + BO_pi2 * Cln_pi2);
-            cPi = -BO_pi * Cln_pi;
-            cPi2 = -BO_pi2 * Cln_pi2;
-            BO_s -= bo_cut;
-            BO -= bo_cut;
-          }
+        const AtomPar& aj = P.atom[tj];
+        const PairPar& tw = P.pair[ti * P.nt + tj];
+        // (d/r)^p as exp(p (log d - log r)): one log shared by the three terms instead of three pow() calls
+        // (agrees with pow to ~1e-15 relative; the reference's own CPE kernels use polynomial exp/pow)
+        double C12 = 0, C34 = 0, C56 = 0;
+        const double ld = log(d);
+        if (ai.r_s > 0.0 && aj.r_s > 0.0) { C12 = tw.p_bo1 * exp(tw.p_bo2 * (ld - tw.log_r_s)); BO_s = (1.0 + bo_cut) * exp(C12); }
+        if (ai.r_pi > 0.0 && aj.r_pi > 0.0) { C34 = tw.p_bo3 * exp(tw.p_bo4 * (ld - tw.log_r_p)); BO_pi = exp(C34); }
+        if (ai.r_pi_pi > 0.0 && aj.r_pi_pi > 0.0) { C56 = tw.p_bo5 * exp(tw.p_bo6 * (ld - tw.log_r_pp)); BO_pi2 = exp(C56); }
+        BO = BO_s + BO_pi + BO_pi2;
+        if (BO >= bo_cut) {
+          hit = true;
+          const double rr2 = d * d;
+          const double Cln_s = tw.p_bo2 * C12 / rr2, Cln_pi = tw.p_bo4 * C34 / rr2, Cln_pi2 = tw.p_bo6 * C56 / rr2;
+          cBOp = -(BO_s * Cln_s + BO_pi * Cln_pi + BO_pi2 * Cln_pi2);
+          cPi = -BO_pi * Cln_pi;
+          cPi2 = -BO_pi2 * Cln_pi2;
+          BO_s -= bo_cut;
+          BO -= bo_cut;
         }
       }
+      // shift the remainder of the queue down
+      const int rest = qn - take;
+      int moved = -1;
+      if (lane < rest) moved = queue[take + lane];
+      __syncwarp();
+      if (lane < rest) queue[lane] = moved;
+      qn = rest;
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int slot = cnt + __popc(m & ((1u << lane) - 1));
@@ -83,6 +112,7 @@ k_bond_list(DevView v, DevParams P) {
         }
       }
       cnt += __popc(m);
+      __syncwarp();
     }
   }
   if (cnt > kMaxRow) { if (lane == 0) atomicOr(v.overflow, 1); cnt = kMaxRow; }

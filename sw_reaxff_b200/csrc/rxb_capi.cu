@@ -170,6 +170,9 @@ int rxb_md_setup(rxb_handle* h, const double* box6, int nlocal, const double* x,
 int rxb_md_run(rxb_handle* h, int nsteps) { return guard([&] { h->sys->md_run(nsteps); }); }
 double rxb_md_last_run_ms(rxb_handle* h) { return h->sys->last_run_ms; }
 int rxb_md_get(rxb_handle* h, double* x, double* v, double* f, double* q) { return guard([&] { h->sys->md_get(x, v, f, q); }); }
+int rxb_md_get_tags(rxb_handle* h, int* tags) {
+  return guard([&] { System& s = *h->sys; d2h(tags, s.tag.p, (size_t)s.n, s.stream()); });
+}
 int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke) {
   return guard([&] {
     System& s = *h->sys;
@@ -293,6 +296,11 @@ long rxb_parse_dump(const char* control_file, const char* ffield_file, int ntype
     count = (long)v.size();
   });
   return rc == 0 ? count : -1;
+}
+
+int rxb_dist_unique_id(char* out128) { return guard([&] { System::dist_unique_id(out128); }); }
+int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px, int py, int pz) {
+  return guard([&] { h->sys->dist_init(rank, world, id128, px, py, pz); });
 }
 
 int rxb_profiler_range(int start) {

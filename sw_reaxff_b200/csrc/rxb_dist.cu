@@ -1,0 +1,406 @@
+// Multi-GPU: LAMMPS-style spatial domain decomposition, one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// What the reference gets from the (absent) LAMMPS core over MPI — exchange/borders every reneighbouring step,
+// forward_comm of x every step, reverse_comm of f, forward_comm_fix of the CG search direction and MPI_Allreduce of the
+// dot products every CG iteration (fix_qeq_reax_sunway.cpp:1043-1132) — is done here on the device:
+//   * bricks in lamda space (px x py x pz), ghost shell = cutneigh;
+//   * reneighbouring ("exchange + borders"): every rank all-gathers the 144-byte migration records of all atoms
+//     (x, v, q, s_hist, t_hist, tag, type), then selects its new local atoms and its ghost images from the gathered set
+//     with two count/scan/fill kernels.  One collective instead of 6-direction staged swaps: on NVSwitch every peer is one
+//     hop at full bandwidth, and the gathered set makes migration of s_hist/t_hist/v trivial;
+//   * forward (x,q), CG halo (d as double2): all-gather of the local slab, ghosts read their source slot (+ image shift);
+//   * reverse (f): scatter-add into the global slot array, ncclReduceScatter;
+//   * CG dots / sums / energies: ncclAllReduce on the device scalars, stream-ordered, no host sync.
+// Round-1 status: functional and parity-tested against the single-GPU path; the per-iteration halo moves the whole slab
+// (16 B/atom) instead of only the boundary layer — next step is peer-to-peer boundary exchange.
+#include <cub/cub.cuh>
+#include <nccl.h>
+
+#include <cmath>
+
+#include "rxb_system.h"
+
+#define RXB_NCCL(call)                                                                                    \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess)                                                                                \
+      throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " __FILE__ ":" + \
+                               std::to_string(__LINE__));                                                 \
+  } while (0)
+
+namespace rxb {
+
+constexpr int kRec = 18;  // doubles per migration record: x3 v3 q s_hist5 t_hist5 (tag,type)
+
+struct Dist {
+  int rank = 0, world = 1;
+  int grid[3] = {1, 1, 1}, coord[3] = {0, 0, 0};
+  double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  ncclComm_t comm = nullptr;
+  int chunk = 0;                 // slots per rank in the gathered arrays
+  std::vector<int> counts;       // local atoms per rank at the last exchange
+  DBuf<int> counts_d;
+  DBuf<double> rec_send, rec_all;        // [chunk][kRec], [world*chunk][kRec]
+  DBuf<double4> xq_all;                  // [world*chunk]
+  DBuf<double2> d_all;                   // [world*chunk]
+  DBuf<double> f_all, f_recv;            // [world*chunk][3], [chunk][3]
+  DBuf<int> gsrc;                        // per ghost: source slot in the gathered arrays
+  DBuf<long long> flag, off;             // selection scans
+  DBuf<char> temp;
+};
+
+namespace {
+
+struct BoxD { double h[6], h_inv[6]; };
+struct Brick { double lo[3], hi[3], cg[3]; int m[3]; };
+
+__device__ __forceinline__ void x2lamda(const BoxD& b, double x, double y, double z, double* l) {
+  l[0] = b.h_inv[0] * x + b.h_inv[5] * y + b.h_inv[4] * z;
+  l[1] = b.h_inv[1] * y + b.h_inv[3] * z;
+  l[2] = b.h_inv[2] * z;
+}
+__device__ __forceinline__ void shift_vec(const BoxD& b, int sx, int sy, int sz, double* d) {
+  d[0] = sx * b.h[0] + sy * b.h[5] + sz * b.h[4];
+  d[1] = sy * b.h[1] + sz * b.h[3];
+  d[2] = sz * b.h[2];
+}
+__device__ __forceinline__ bool in_brick(const Brick& k, const double* l) {
+  return l[0] >= k.lo[0] && l[0] < k.hi[0] && l[1] >= k.lo[1] && l[1] < k.hi[1] && l[2] >= k.lo[2] && l[2] < k.hi[2];
+}
+
+__global__ void k_wrap_pack(int n, BoxD b, double4* __restrict__ xq, const double* __restrict__ vel,
+                            const double* __restrict__ s_hist, const double* __restrict__ t_hist,
+                            const int* __restrict__ tag, const int* __restrict__ ltype, double* __restrict__ rec) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = xq[i];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  const int s0 = (int)floor(l[0]), s1 = (int)floor(l[1]), s2 = (int)floor(l[2]);
+  if (s0 | s1 | s2) {
+    double d[3];
+    shift_vec(b, s0, s1, s2, d);
+    p.x -= d[0]; p.y -= d[1]; p.z -= d[2];
+  }
+  double* r = rec + (size_t)kRec * i;
+  r[0] = p.x; r[1] = p.y; r[2] = p.z;
+  r[3] = vel[3 * i]; r[4] = vel[3 * i + 1]; r[5] = vel[3 * i + 2];
+  r[6] = p.w;
+  for (int k = 0; k < 5; k++) { r[7 + k] = s_hist[5 * (size_t)i + k]; r[12 + k] = t_hist[5 * (size_t)i + k]; }
+  r[17] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
+}
+
+__device__ __forceinline__ bool slot_valid(int s, int chunk, const int* counts) { return (s % chunk) < counts[s / chunk]; }
+
+__global__ void k_flag_locals(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
+                              Brick k, long long* __restrict__ flag) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nslots) return;
+  long long f = 0;
+  if (s < nslots && slot_valid(s, chunk, counts)) {
+    const double* r = rec + (size_t)kRec * s;
+    double l[3];
+    x2lamda(b, r[0], r[1], r[2], l);
+    f = in_brick(k, l) ? 1 : 0;
+  }
+  flag[s] = f;
+}
+
+__global__ void k_fill_locals(int nslots, const long long* __restrict__ flag, const long long* __restrict__ off,
+                              const double* __restrict__ rec, const int* __restrict__ map, int maplen, double4* __restrict__ xq,
+                              double* __restrict__ vel, double* __restrict__ s_hist, double* __restrict__ t_hist,
+                              int* __restrict__ tag, int* __restrict__ ltype, int* __restrict__ type) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots || !flag[s]) return;
+  const long long i = off[s];
+  const double* r = rec + (size_t)kRec * s;
+  xq[i] = make_double4(r[0], r[1], r[2], r[6]);
+  vel[3 * i] = r[3]; vel[3 * i + 1] = r[4]; vel[3 * i + 2] = r[5];
+  for (int k = 0; k < 5; k++) { s_hist[5 * i + k] = r[7 + k]; t_hist[5 * i + k] = r[12 + k]; }
+  const long long tt = __double_as_longlong(r[17]);
+  const int tg = (int)(tt >> 32), lt = (int)(tt & 0xffffffffLL);
+  tag[i] = tg; ltype[i] = lt;
+  type[i] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
+}
+
+template <bool FILL>
+__global__ void k_ghosts_dist(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
+                              Brick k, int n, const int* __restrict__ map, int maplen, long long* __restrict__ count,
+                              const long long* __restrict__ off, double4* __restrict__ xq, int* __restrict__ tag,
+                              int* __restrict__ ltype, int* __restrict__ type, int* __restrict__ gsrc, int* __restrict__ shift) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nslots) return;
+  if (s == nslots || !slot_valid(s, chunk, counts)) { if (!FILL) count[s] = 0; return; }
+  const double* r = rec + (size_t)kRec * s;
+  double l[3];
+  x2lamda(b, r[0], r[1], r[2], l);
+  const bool mine = in_brick(k, l);
+  long long c = 0, w = FILL ? off[s] : 0;
+  for (int sz = -k.m[2]; sz <= k.m[2]; sz++) {
+    const double l2 = l[2] + sz;
+    if (!(l2 >= k.lo[2] - k.cg[2] && l2 < k.hi[2] + k.cg[2])) continue;
+    for (int sy = -k.m[1]; sy <= k.m[1]; sy++) {
+      const double l1 = l[1] + sy;
+      if (!(l1 >= k.lo[1] - k.cg[1] && l1 < k.hi[1] + k.cg[1])) continue;
+      for (int sx = -k.m[0]; sx <= k.m[0]; sx++) {
+        if (mine && !sx && !sy && !sz) continue;
+        const double l0 = l[0] + sx;
+        if (!(l0 >= k.lo[0] - k.cg[0] && l0 < k.hi[0] + k.cg[0])) continue;
+        if (FILL) {
+          double d[3];
+          shift_vec(b, sx, sy, sz, d);
+          const long long g = n + w;
+          xq[g] = make_double4(r[0] + d[0], r[1] + d[1], r[2] + d[2], r[6]);
+          const long long tt = __double_as_longlong(r[17]);
+          const int lt = (int)(tt & 0xffffffffLL);
+          tag[g] = (int)(tt >> 32); ltype[g] = lt;
+          type[g] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
+          gsrc[w] = s;
+          shift[3 * w] = sx; shift[3 * w + 1] = sy; shift[3 * w + 2] = sz;
+          w++;
+        } else {
+          c++;
+        }
+      }
+    }
+  }
+  if (!FILL) count[s] = c;
+}
+
+__global__ void k_ghost_x_from_all(int n, int nghost, BoxD b, const int* __restrict__ gsrc, const int* __restrict__ shift,
+                                   const double4* __restrict__ xq_all, double4* __restrict__ xq) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  double d[3];
+  shift_vec(b, shift[3 * g], shift[3 * g + 1], shift[3 * g + 2], d);
+  const double4 p = xq_all[gsrc[g]];
+  xq[n + g] = make_double4(p.x + d[0], p.y + d[1], p.z + d[2], p.w);
+}
+__global__ void k_ghost_d_from_all(int n, int nghost, const int* __restrict__ gsrc, const double2* __restrict__ d_all,
+                                   double2* __restrict__ vec) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nghost) vec[n + g] = d_all[gsrc[g]];
+}
+__global__ void k_scatter_f(int n, int nghost, int my_off, const int* __restrict__ gsrc, const double* __restrict__ f,
+                            double* __restrict__ f_all) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n + nghost) return;
+  const long long dst = i < n ? (long long)my_off + i : gsrc[i - n];
+  const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
+  if (fx != 0.0) atomicAdd(&f_all[3 * dst], fx);
+  if (fy != 0.0) atomicAdd(&f_all[3 * dst + 1], fy);
+  if (fz != 0.0) atomicAdd(&f_all[3 * dst + 2], fz);
+}
+
+inline int nblk(long n, int t = 256) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+void System::dist_unique_id(char* out128) {
+  ncclUniqueId id;
+  RXB_NCCL(ncclGetUniqueId(&id));
+  static_assert(sizeof(id) <= 128, "ncclUniqueId larger than 128 bytes");
+  memset(out128, 0, 128);
+  memcpy(out128, &id, sizeof(id));
+}
+
+void System::dist_init(int rank, int world, const char* id128, int px, int py, int pz) {
+  RXB_CUDA(cudaSetDevice(device_));
+  if (px * py * pz != world) throw std::runtime_error("rxb_dist_init: processor grid does not match the world size");
+  dist_ = new Dist();
+  Dist& D = *dist_;
+  D.rank = rank; D.world = world;
+  D.grid[0] = px; D.grid[1] = py; D.grid[2] = pz;
+  D.coord[0] = rank % px; D.coord[1] = (rank / px) % py; D.coord[2] = rank / (px * py);
+  for (int t = 0; t < 3; t++) {
+    D.lo[t] = (double)D.coord[t] / D.grid[t];
+    D.hi[t] = (D.coord[t] == D.grid[t] - 1) ? 1.0 : (double)(D.coord[t] + 1) / D.grid[t];
+  }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  RXB_NCCL(ncclCommInitRank(&D.comm, world, id, rank));
+  D.counts.assign(world, 0);
+  D.counts_d.resize(world);
+}
+
+void System::dist_destroy() {
+  if (!dist_) return;
+  if (dist_->comm) ncclCommDestroy(dist_->comm);
+  delete dist_;
+  dist_ = nullptr;
+}
+
+int System::dist_world() const { return dist_ ? dist_->world : 1; }
+size_t System::slab() const { return dist_ ? (size_t)dist_->chunk : 0; }
+
+void System::dist_allreduce(double* dev_ptr, int count) {
+  if (!dist_) return;
+  RXB_NCCL(ncclAllReduce(dev_ptr, dev_ptr, count, ncclDouble, ncclSum, dist_->comm, st_));
+}
+
+// exchange + borders
+void System::dist_exchange() {
+  Dist& D = *dist_;
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  // 1. counts
+  int my = n;
+  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
+  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  int mx = 0;
+  long long total = 0;
+  for (int c : D.counts) { mx = std::max(mx, c); total += c; }
+  // slots per rank: generous, so that the post-migration local counts fit as well (growth triggers a re-gather next time)
+  int want = std::max(mx, (int)((total / D.world) + (total / D.world) / 4 + 64));
+  if (want > D.chunk) D.chunk = want + want / 8;
+  const int chunk = D.chunk;
+  const int nslots = chunk * D.world;
+  // 2. migration records of the wrapped local atoms
+  D.rec_send.resize((size_t)chunk * kRec);
+  D.rec_all.resize((size_t)nslots * kRec);
+  k_wrap_pack<<<nblk(n), 256, 0, st_>>>(n, b, xq.p, v_d.p, q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, D.rec_send.p);
+  RXB_NCCL(ncclAllGather(D.rec_send.p, D.rec_all.p, (size_t)chunk * kRec, ncclDouble, D.comm, st_));
+  // 3. brick and shell in lamda space
+  Brick k;
+  const double cut = cutneigh();
+  k.cg[0] = cut * sqrt(b.h_inv[0] * b.h_inv[0] + b.h_inv[5] * b.h_inv[5] + b.h_inv[4] * b.h_inv[4]);
+  k.cg[1] = cut * sqrt(b.h_inv[1] * b.h_inv[1] + b.h_inv[3] * b.h_inv[3]);
+  k.cg[2] = cut * b.h_inv[2];
+  for (int t = 0; t < 3; t++) { k.lo[t] = D.lo[t]; k.hi[t] = D.hi[t]; k.m[t] = (int)ceil(k.cg[t]) + 1; }
+  // 4. new local atoms: flag, scan, fill (stable => deterministic order)
+  D.flag.resize(nslots + 1); D.off.resize(nslots + 1);
+  k_flag_locals<<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, D.flag.p);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, nslots + 1, st_);
+  D.temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
+  long long newn = 0;
+  RXB_CUDA(cudaMemcpyAsync(&newn, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  if (newn > chunk) throw std::runtime_error("rxb dist: local atom count exceeds the slab capacity (load imbalance > 25 %)");
+  n = (int)newn;
+  N = n;
+  ensure_atom_capacity();
+  v_d.resize_keep((size_t)3 * std::max(n, chunk));
+  q_s_hist.resize((size_t)5 * std::max(n, chunk)); q_t_hist.resize((size_t)5 * std::max(n, chunk));
+  q_s_hist.n = (size_t)5 * n; q_t_hist.n = (size_t)5 * n;
+  if (map_d.n != ff.map.size()) {
+    map_d.resize(ff.map.size());
+    RXB_CUDA(cudaMemcpyAsync(map_d.p, ff.map.data(), ff.map.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+  }
+  xq.resize_keep(std::max((size_t)n, (size_t)chunk)); xq.n = n;
+  tag.resize_keep(std::max((size_t)n, (size_t)chunk)); ltype_d.resize_keep(std::max((size_t)n, (size_t)chunk));
+  type.resize_keep(std::max((size_t)n, (size_t)chunk));
+  k_fill_locals<<<nblk(nslots), 256, 0, st_>>>(nslots, D.flag.p, D.off.p, D.rec_all.p, map_d.p, (int)ff.map.size(), xq.p, v_d.p,
+                                              q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, type.p);
+  // 5. ghosts: count, scan, fill
+  k_ghosts_dist<false><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, n, map_d.p,
+                                                         (int)ff.map.size(), D.flag.p, nullptr, nullptr, nullptr, nullptr,
+                                                         nullptr, nullptr, nullptr);
+  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
+  long long nghost = 0;
+  RXB_CUDA(cudaMemcpyAsync(&nghost, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  N = n + (int)nghost;
+  ensure_atom_capacity();
+  xq.resize_keep(std::max((size_t)N, (size_t)chunk)); xq.n = N;
+  D.gsrc.resize(std::max<size_t>(nghost, 1));
+  ghost_shift.resize(std::max<size_t>(3 * nghost, 3));
+  ghost_owner.resize(std::max<size_t>(nghost, 1));
+  k_ghosts_dist<true><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, n, map_d.p,
+                                                        (int)ff.map.size(), nullptr, D.off.p, xq.p, tag.p, ltype_d.p, type.p,
+                                                        D.gsrc.p, ghost_shift.p);
+  // the gathered arrays keep the PRE-migration slot layout until the next exchange; after migration the local slab is
+  // [rank*chunk, rank*chunk + n): refresh the counts so that forward/reverse use the new layout
+  my = n;
+  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
+  // ghost sources refer to pre-migration slots: re-resolve them against the post-migration layout by tag
+  dist_resolve_sources();
+  D.xq_all.resize((size_t)nslots); D.d_all.resize((size_t)nslots);
+  D.f_all.resize((size_t)3 * nslots); D.f_recv.resize((size_t)3 * chunk);
+  kernel_launches += 6;
+  RXB_CUDA(cudaGetLastError());
+}
+
+namespace {
+// After migration the atom that sat in pre-migration slot s lives in some rank's new local array.  Every rank publishes
+// (all-gathers) the pre-migration slot of each of its new local atoms; inverting that table maps old slot -> new slot.
+__global__ void k_publish_old_slot(int nslots, const long long* __restrict__ flag, const long long* __restrict__ off,
+                                   int* __restrict__ old_of_new) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nslots && flag[s]) old_of_new[off[s]] = s;
+}
+__global__ void k_invert(int world, int chunk, const int* __restrict__ counts, const int* __restrict__ old_of_new_all,
+                         int* __restrict__ new_of_old) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= world * chunk) return;
+  if ((s % chunk) < counts[s / chunk]) new_of_old[old_of_new_all[s]] = s;
+}
+__global__ void k_remap_src(int nghost, const int* __restrict__ new_of_old, int* __restrict__ gsrc) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nghost) gsrc[g] = new_of_old[gsrc[g]];
+}
+}  // namespace
+
+void System::dist_resolve_sources() {
+  Dist& D = *dist_;
+  const int chunk = D.chunk, nslots = chunk * D.world;
+  old_of_new_.resize(chunk); old_of_new_all_.resize(nslots); new_of_old_.resize(nslots);
+  // flag/off were overwritten by the ghost scan: recompute the local flags/scan (cheap) to publish old slots
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  Brick k;
+  for (int t = 0; t < 3; t++) { k.lo[t] = D.lo[t]; k.hi[t] = D.hi[t]; k.cg[t] = 0; k.m[t] = 0; }
+  // NOTE: counts_d now holds post-migration counts; validity of PRE-migration slots must use the old counts
+  DBuf<int>& oldc = old_counts_d_;
+  oldc.resize(D.world);
+  RXB_CUDA(cudaMemcpyAsync(oldc.p, D.counts.data(), D.world * sizeof(int), cudaMemcpyHostToDevice, st_));
+  k_flag_locals<<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, oldc.p, D.rec_all.p, b, k, D.flag.p);
+  size_t need = D.temp.n;
+  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
+  k_publish_old_slot<<<nblk(nslots), 256, 0, st_>>>(nslots, D.flag.p, D.off.p, old_of_new_.p);
+  RXB_NCCL(ncclAllGather(old_of_new_.p, old_of_new_all_.p, chunk, ncclInt, D.comm, st_));
+  k_invert<<<nblk(nslots), 256, 0, st_>>>(D.world, chunk, D.counts_d.p, old_of_new_all_.p, new_of_old_.p);
+  const int nghost = N - n;
+  if (nghost > 0) k_remap_src<<<nblk(nghost), 256, 0, st_>>>(nghost, new_of_old_.p, D.gsrc.p);
+  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  kernel_launches += 5;
+}
+
+void System::dist_forward_xq() {
+  Dist& D = *dist_;
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  RXB_NCCL(ncclAllGather(xq.p, D.xq_all.p, (size_t)D.chunk * 4, ncclDouble, D.comm, st_));
+  const int nghost = N - n;
+  if (nghost > 0) k_ghost_x_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, D.gsrc.p, ghost_shift.p, D.xq_all.p, xq.p);
+  kernel_launches++;
+}
+
+void System::dist_forward2(double2* vec) {
+  Dist& D = *dist_;
+  RXB_NCCL(ncclAllGather(vec, D.d_all.p, (size_t)D.chunk * 2, ncclDouble, D.comm, st_));
+  const int nghost = N - n;
+  if (nghost > 0) k_ghost_d_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, D.gsrc.p, D.d_all.p, vec);
+  kernel_launches++;
+}
+
+void System::dist_reverse_f() {
+  Dist& D = *dist_;
+  const size_t nslots = (size_t)D.chunk * D.world;
+  RXB_CUDA(cudaMemsetAsync(D.f_all.p, 0, 3 * nslots * sizeof(double), st_));
+  k_scatter_f<<<nblk(N), 256, 0, st_>>>(n, N - n, D.rank * D.chunk, D.gsrc.p, f.p, D.f_all.p);
+  RXB_NCCL(ncclReduceScatter(D.f_all.p, D.f_recv.p, (size_t)3 * D.chunk, ncclDouble, ncclSum, D.comm, st_));
+  RXB_CUDA(cudaMemcpyAsync(f.p, D.f_recv.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st_));
+  kernel_launches++;
+}
+
+}  // namespace rxb

@@ -310,6 +310,8 @@ void ForceField::derive() {
   const double p_vdW1 = gp.size() > 28 ? gp[28] : 0.0;
   for (PairPar& x : pair) {
     x.powgi_vdW1 = (x.gamma_w > 0.0) ? pow(1.0 / x.gamma_w, p_vdW1) : 0.0;
+    x.inv_r_vdW = x.r_vdW != 0.0 ? 1.0 / x.r_vdW : 0.0;
+    x.alpha_over_r_vdW = x.r_vdW != 0.0 ? x.alpha / x.r_vdW : 0.0;
     x.log_r_s = x.r_s > 0.0 ? log(x.r_s) : 0.0;
     x.log_r_p = x.r_p > 0.0 ? log(x.r_p) : 0.0;
     x.log_r_pp = x.r_pp > 0.0 ? log(x.r_pp) : 0.0;

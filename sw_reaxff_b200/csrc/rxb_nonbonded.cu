@@ -35,43 +35,46 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
     const double4 pi = v.xq[i];
     const int ti = v.type[i];
     const long long beg = v.vl_off[i], end = v.vl_off[i + 1];
+    // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work)
     long long w = beg;
     for (long long k0 = beg; k0 < end; k0 += 32) {
       const long long k = k0 + lane;
       bool hit = false;
       int j = 0;
-      double val = 0.0;
       if (k < end) {
         j = v.vl_idx[k];
         const double4 pj = v.xq[j];
-        const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
-        hit = r2 <= qc.far2;
-        if (hit && r2 <= qc.swb2) {
-          const int tj = v.type[j];
-          if (ti >= 0 && tj >= 0) {
-            const double r = sqrt(r2);
-            double T = qc.Tap[7] * r + qc.Tap[6];
-            T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
-            T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-            const double denom = cbrt(r * r * r + shld[ti * nt + tj]);  // reference: pow(x, 0.3333333333333), < 3e-13 rel.
-            val = T * kEvToKcal / denom;
-          }
-        }
+        hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const long long o = w + __popc(m & ((1u << lane) - 1));
-        v.far_idx[o] = j;
-        v.H_val[o] = val;
-      }
+      if (hit) v.far_idx[w + __popc(m & ((1u << lane) - 1))] = j;
       w += __popc(m);
     }
-    if (lane == 0) v.far_num[i] = (int)(w - beg);
+    const int num = (int)(w - beg);
+    if (lane == 0) v.far_num[i] = num;
+    __syncwarp();
+    // pass 2: H values on the compacted row (every lane does the taper + cube root; xq[j] is an L1/L2 hit)
+    for (int k = lane; k < num; k += 32) {
+      const int j = v.far_idx[beg + k];
+      const double4 pj = v.xq[j];
+      const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
+      const int tj = v.type[j];
+      double val = 0.0;
+      if (r2 <= qc.swb2 && ti >= 0 && tj >= 0) {
+        const double r = sqrt(r2);
+        double T = qc.Tap[7] * r + qc.Tap[6];
+        T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
+        T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
+        // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
+        val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
+      }
+      v.H_val[beg + k] = val;
+    }
   }
 }
 
 template <bool EV>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 3)
 k_nonbonded(DevView v, DevParams P) {
   __shared__ double sh[8][kWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -100,7 +103,8 @@ k_nonbonded(DevView v, DevParams P) {
       const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
       const double r2 = dist2_rn(dx, dy, dz);
       if (!(r2 <= nonb_cut2)) continue;
-      const double r_ij = sqrt(r2);
+      const double rinv = rsqrt(r2);
+      const double r_ij = r2 * rinv;
       const PairPar& tw = P.pair[ti * nt + tj];
       double T = Tap[7] * r_ij + Tap[6];
       T = T * r_ij + Tap[5]; T = T * r_ij + Tap[4]; T = T * r_ij + Tap[3];
@@ -108,7 +112,7 @@ k_nonbonded(DevView v, DevParams P) {
       double dT = 7 * Tap[7] * r_ij + 6 * Tap[6];
       dT = dT * r_ij + 5 * Tap[5]; dT = dT * r_ij + 4 * Tap[4]; dT = dT * r_ij + 3 * Tap[3];
       dT = dT * r_ij + 2 * Tap[2];
-      dT += Tap[1] / r_ij;
+      dT += Tap[1] * rinv;
       double e_vdW, CEvd, e_core = 0, e_lg = 0;
       if (vdw_type == 1 || vdw_type == 3) {
         // r^p, (r^p + g^-p)^(1/p) and the two derivative powers from 2 log + 2 exp (the serial form calls pow 5x);
@@ -116,11 +120,11 @@ k_nonbonded(DevView v, DevParams P) {
         const double powr = exp(p_vdW1 * log(r_ij));
         const double ssum = powr + tw.powgi_vdW1;
         const double fn13 = exp(p_vdW1i * log(ssum));
-        const double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 / tw.r_vdW));
+        const double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 * tw.inv_r_vdW));
         const double exp1 = exp2 * exp2;
         e_vdW = tw.D * (exp1 - 2.0 * exp2);
-        const double dfn13 = (fn13 / ssum) * (powr / r2);
-        CEvd = dT * e_vdW - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) * dfn13;
+        const double dfn13 = (fn13 / ssum) * (powr * rinv * rinv);
+        CEvd = dT * e_vdW - T * tw.D * tw.alpha_over_r_vdW * (exp1 - exp2) * dfn13;
       } else {
         const double exp1 = exp(tw.alpha * (1.0 - r_ij / tw.r_vdW));
         const double exp2 = exp(0.5 * tw.alpha * (1.0 - r_ij / tw.r_vdW));
@@ -138,15 +142,15 @@ k_nonbonded(DevView v, DevParams P) {
           CEvd += dT * e_lg + T * de_lg / r_ij;
         }
       }
-      const double dr3gamij_1 = r_ij * r_ij * r_ij + tw.gamma;
-      const double dr3gamij_3 = cbrt(dr3gamij_1);  // reference: pow(x, 0.33333333333333); differs by < 3e-14 relative
+      const double dr3gamij_1 = r2 * r_ij + tw.gamma;
+      const double inv3 = rcbrt(dr3gamij_1);  // reference: 1/pow(x, 0.33333333333333); differs by < 3e-14 relative
       const double qq = kCele * pi.w * pj.w;
-      const double CEclmb = qq * (dT - T * r_ij / dr3gamij_1) / dr3gamij_3;
+      const double CEclmb = qq * (dT - T * r_ij / dr3gamij_1) * inv3;
       const double ftot = CEvd + CEclmb;  // f_i = +ftot * dvec  (reference: fCdDelta[i] += -ftot*dvec, f = -fCdDelta)
       fx += ftot * dx; fy += ftot * dy; fz += ftot * dz;
       if (EV) {
         e_vdw += 0.5 * T * (e_vdW + e_core + e_lg);
-        e_ele += 0.5 * qq * (T / dr3gamij_3);
+        e_ele += 0.5 * qq * (T * inv3);
         const double fpair = -ftot;
         vir[0] += 0.5 * dx * dx * fpair; vir[1] += 0.5 * dy * dy * fpair; vir[2] += 0.5 * dz * dz * fpair;
         vir[3] += 0.5 * dx * dy * fpair; vir[4] += 0.5 * dx * dz * fpair; vir[5] += 0.5 * dy * dz * fpair;

@@ -31,6 +31,7 @@ struct PairPar {  // two_body_parameters
   double rcore, ecore, acore, lgcij, lgre;
   double v13cor, ovc;
   double powgi_vdW1;   // derived: (1/gamma_w)^p_vdW1, hoisted out of the pair loop (reaxc_nonbonded_sw64.c:137)
+  double inv_r_vdW, alpha_over_r_vdW; // derived: 1/r_vdW, alpha/r_vdW
   double log_r_s, log_r_p, log_r_pp;  // derived: logs of the bond radii, so that (d/r)^p = exp(p (log d - log r))
 };
 

@@ -11,6 +11,8 @@
 // only polls a flag every few iterations.  The per-iteration vector work of the reference (two sweeps + a serial
 // MPE sweep overlapped with the SpMV) is one fused sweep here.
 // Roofline: SpMV is HBM-bound: 12 B per stored H entry + 16 B per gathered x (L2-resident).
+#include <algorithm>
+
 #include "rxb_system.h"
 
 namespace rxb {
@@ -277,7 +279,7 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
 
 void System::qeq_pre_force() {
   if (n == 0) return;
-  if (q_s_hist.n != (size_t)5 * n) qeq_reset_history();
+  if (q_s_hist.n != (size_t)5 * n && !dist_) qeq_reset_history();
   DevView v = view();
   // taper and shielding of the fix (init_taper :458-484, init_shielding :440-454), host side, tiny
   double Tap[8];
@@ -298,7 +300,7 @@ void System::qeq_pre_force() {
   tock(t_QEQ_H);
 
   const int t_QEQ_CG = tick(StepTimers::QEQ_CG);
-  const size_t nn = n, NN = N;
+  const size_t nn = n, NN = std::max((size_t)N, slab());  // all-gathered arrays must hold a whole slab
   q_x.resize(NN); q_d.resize(NN);
   q_r.resize(nn); q_u.resize(nn); q_w.resize(nn); q_p.resize(nn); q_ss.resize(nn); q_v.resize(nn); q_z.resize(nn);
   q_q.resize(nn); q_b.resize(nn); q_m.resize(nn); q_Hdia_inv.resize(nn);
@@ -306,7 +308,10 @@ void System::qeq_pre_force() {
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
   const int nghost = N - n;
   const int fb = nghost > 0 ? (nghost + 255) / 256 : 0;
-  auto forward = [&](double2* vec) { if (fb) { k_forward2<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, vec); kernel_launches++; } };
+  auto forward = [&](double2* vec) {
+    if (dist_) dist_forward2(vec);
+    else if (fb) { k_forward2<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, vec); kernel_launches++; }
+  };
   auto spmv = [&](const double2* x, double2* y, const QeqDev* gate, int parity) {
     const int ts = tick(StepTimers::SPMV);
     k_spmv2<<<kBlocksSpmv, kWarps * 32, 0, st_>>>(n, vl.off.p, far_num.p, far_idx.p, H_val.p, type.p, dp_.atom, x, y, gate, parity);
@@ -323,6 +328,7 @@ void System::qeq_pre_force() {
   forward(q_d.p);
   spmv(q_d.p, q_q.p, nullptr, 0);
   k_pro3<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_b.p, q_r.p, q_u.p, q_w.p, q_m.p, q_q.p, q_p.p, q_ss.p, q_v.p, q_z.p, Q);
+  if (dist_) dist_allreduce(Q->pro, 6);
   k_scal_init<<<1, 32, 0, st_>>>(Q, qeq_tol, qeq_imax);
   kernel_launches += 5;
 
@@ -333,6 +339,7 @@ void System::qeq_pre_force() {
     k_cg_sweep<<<kVecBlocks, kVecThreads, 0, st_>>>(n, it, it == 1, qeq_tol, qeq_imax, q_Hdia_inv.p, q_q.p, q_x.p, q_r.p,
                                                    q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
     kernel_launches++;
+    if (dist_) dist_allreduce(Q->dots[(it + 1) % 3], 4);   // MPI_Allreduce(dot_local, 2) of each solve, :1132
     const int par_next = (it & 1) ^ 1;  // state written by this sweep
     if (it % qeq_check_every == 0 || it > qeq_imax) {
       RXB_CUDA(cudaMemcpyAsync(active_host, Q->st[par_next].active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
@@ -344,8 +351,10 @@ void System::qeq_pre_force() {
   }
   // final charges
   k_q_sums<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_x.p, Q);
+  if (dist_) dist_allreduce(Q->sums, 2);
   k_q_final<<<kVecBlocks, kVecThreads, 0, st_>>>(n, N, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 0);
-  if (fb) k_q_final<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 1);
+  if (dist_) dist_forward_xq();
+  else if (fb) k_q_final<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 1);
   kernel_launches += 3;
   int iters_host[2];
   const int par_final = (it & 1) ^ 1;

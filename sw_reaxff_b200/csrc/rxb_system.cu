@@ -199,6 +199,7 @@ System::System(int device) : device_(device) {
 
 System::~System() {
   cudaSetDevice(device_);
+  dist_destroy();
   if (h_pin_) cudaFreeHost(h_pin_);
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   if (st_) cudaStreamDestroy(st_);
@@ -462,6 +463,7 @@ void System::compute(bool eflag, bool vflag) {
     RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
     RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
     RXB_CUDA(cudaMemcpyAsync(wk, it_count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    if ((eflag || vflag) && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
     if (eflag || vflag) {
       RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
       RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
@@ -497,7 +499,7 @@ void System::md_setup(const double* box6, int nlocal, const double* x, const dou
   mass_d.resize(ntypes + 1);
   RXB_CUDA(cudaMemcpy(mass_d.p, mass_by_type, (size_t)(ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice));
   qeq_reset_history();
-  md_make_ghosts();
+  if (dist_) dist_exchange(); else md_make_ghosts();
   build_neighbors();
   md_force();
 }
@@ -538,7 +540,8 @@ void System::md_force() {
   const bool ev = md_thermo > 0 && (ntimestep % md_thermo == 0);
   compute(ev, ev);
   const int nghost = N - n;
-  if (nghost > 0) { k_reverse_f<<<nblk(nghost), 256, 0, st_>>>(n, nghost, ghost_owner.p, f.p); kernel_launches++; }
+  if (dist_) dist_reverse_f();
+  else if (nghost > 0) { k_reverse_f<<<nblk(nghost), 256, 0, st_>>>(n, nghost, ghost_owner.p, f.p); kernel_launches++; }
 }
 
 void System::md_run(int nsteps) {
@@ -554,9 +557,11 @@ void System::md_run(int nsteps) {
     k_nve_initial<<<nblk(n), 256, 0, st_>>>(n, dtf, dtv, ltype_d.p, mass_d.p, f.p, v_d.p, xq.p);
     md_ago++;
     if (md_ago % md_every == 0) {
-      md_make_ghosts();
+      if (dist_) dist_exchange(); else md_make_ghosts();
       build_neighbors();
       md_ago = 0;
+    } else if (dist_) {
+      dist_forward_xq();
     } else if (N > n) {
       k_forward_x<<<nblk(N - n), 256, 0, st_>>>(n, N - n, b, ghost_owner.p, ghost_shift.p, xq.p);
     }
@@ -592,6 +597,7 @@ double System::md_kinetic() {
   RXB_CUDA(cudaSetDevice(device_));
   RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, sizeof(double), st_));
   k_kinetic<<<148 * 2, 256, 0, st_>>>(n, ltype_d.p, mass_d.p, v_d.p, virial_d.p);
+  if (dist_) dist_allreduce(virial_d.p, 1);
   double ke = 0;
   RXB_CUDA(cudaMemcpyAsync(&ke, virial_d.p, sizeof(double), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));

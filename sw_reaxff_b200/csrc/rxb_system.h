@@ -80,7 +80,7 @@ struct Box {  // LAMMPS triclinic box, lo = 0
   void set(double xprd, double yprd, double zprd, double xy, double xz, double yz);
 };
 
-struct QeqScalars;  // device-side CG scalars, rxb_qeq.cu
+struct Dist;  // multi-GPU state, rxb_dist.cu
 
 struct StepTimers {
   enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, SPMV, HBOND, VALTOR, MULTI, ENUM, NUM };
@@ -142,6 +142,19 @@ class System {
   bool qeq_on = true;
   int md_thermo = 5;         // energies are reduced every md_thermo steps (thermo 5, in.reaxc.lattice:832)
 
+  // ---- multi-GPU (rxb_dist.cu): brick decomposition + NCCL ----
+  static void dist_unique_id(char* out128);
+  void dist_init(int rank, int world, const char* id128, int px, int py, int pz);
+  void dist_destroy();
+  int dist_world() const;
+  void dist_allreduce(double* dev_ptr, int count);
+  void dist_exchange();          // exchange + borders at reneighbouring
+  void dist_resolve_sources();
+  void dist_forward_xq();        // ghosts <- owners (x + image shift, q)
+  void dist_forward2(double2* vec);
+  void dist_reverse_f();
+  size_t slab() const;           // elements every all-gathered local array must be able to hold
+
   // introspection for parity tests
   DevView view();
   std::vector<double> params_dump() const { return ff.dump(); }
@@ -187,9 +200,11 @@ class System {
   DBuf<long long> gcount, goff;
   DBuf<char> scan_temp;
   int cap_bonds = 0;
+  DBuf<int> map_d, old_of_new_, old_of_new_all_, new_of_old_, old_counts_d_;
 
  private:
   int device_;
+  Dist* dist_ = nullptr;
   cudaStream_t st_ = nullptr;
   std::vector<cudaEvent_t> ev_pool_;
   struct Pending { int which; int a, b; };

@@ -127,19 +127,20 @@ def test_qeq_tight_tolerance_same_solution():
     sh = rng.normal(scale=0.05, size=(n, 5)); th = rng.normal(scale=0.05, size=(n, 5))   # non-trivial history -> extrapolated guess
     o.set_atoms(n, x, ty, tg, np.zeros(len(x)))
     o.build_neighbors(12.5)
-    o.qeq_init(0.0, 10.0, 1e-12)
+    o.qeq_init(0.0, 10.0, 1e-10)
     o.qeq_set_hist(sh, th)
     mvo = o.qeq_pre_force(owner)
-    r = make_rxb(1e-12)
+    r = make_rxb(1e-10)
     r.set_atoms(n, x, ty, tg, None, owner)
     r.neigh_build()
     r.qeq_set_history(sh, th)
     mvg = r.qeq_pre_force()
-    assert abs(mvg[0] - mvo[0]) <= 2 and abs(mvg[1] - mvo[1]) <= 2
-    assert np.abs(r.get_charges() - o.q()).max() < 1e-9
+    assert abs(mvg[0] - mvo[0]) <= 2 and abs(mvg[1] - mvo[1]) <= 2, (mvg, mvo)
+    assert max(mvo) < 200
+    assert np.abs(r.get_charges() - o.q()).max() < 1e-8, np.abs(r.get_charges() - o.q()).max()
     so, to = o.qeq_get_hist()
     sg, tg_ = r.qeq_get_history()
-    assert np.abs(sg - so).max() < 1e-8 and np.abs(tg_ - to).max() < 1e-8      # history shifted identically
+    assert np.abs(sg - so).max() < 1e-7 and np.abs(tg_ - to).max() < 1e-7, (np.abs(sg - so).max(), np.abs(tg_ - to).max())
     assert np.array_equal(sg[:, 1:], sh[:, :4])
 
 
