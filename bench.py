@@ -292,7 +292,7 @@ def run_b200(args, rank, world, local_rank):
     cpu, _, _ = cpu_baseline(H) if not args.no_cpu_baseline else ({"value": None, "unit": "atom-timesteps/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0, 0)
     out = {
         "metric": METRIC, "value": value, "unit": "atom-timesteps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (TATB 384-atom cell replicated by lattice translation, Maxwell velocities 300 K seed 12345)",
         "config": {**config_for(cells), "ghost_atoms": nall - natoms,
                    "l2": "inputs larger than L2 (H matrix 1.07 GB, Verlet list 0.69 GB per step vs 126 MB L2)",
@@ -312,7 +312,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the replication (parity-size runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: TATB 16x16x16 (1,572,864 atoms) on any N (configs[2])")
     args = ap.parse_args()
+    if args.strong and not args.cells:
+        args.cells = [16, 16, 16]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

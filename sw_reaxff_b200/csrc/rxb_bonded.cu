@@ -73,7 +73,7 @@ k_multi(DevView v, DevParams P) {
   const double p_lp3 = P.gp[5], p_ovun3 = P.gp[32], p_ovun4 = P.gp[31], p_ovun6 = P.gp[6], p_ovun7 = P.gp[8], p_ovun8 = P.gp[9];
   const double gp3 = P.gp[3], gp4 = P.gp[4], gp7 = P.gp[7], gp10 = P.gp[10];
   const int gp37 = (int)P.gp[37];
-  double e_lp = 0, e_ov = 0, e_un = 0, e_bond = 0, e_pol = 0;
+  double e_lp = 0, e_ov = 0, e_un = 0, e_bond = 0;  // e_pol (needs the new charges) is tallied by k_nonbonded
   for (int i = wg; i < v.n; i += nwg) {
     const int ti = v.type[i];
     if (ti < 0) continue;
@@ -82,7 +82,6 @@ k_multi(DevView v, DevParams P) {
     const int tag_i = v.tag[i];
     const int start = v.b_start[i], cnt = v.b_cnt[i];
     const double dfvl = (ai.mass > 21.0) ? 0.0 : 1.0;
-    if (lane == 0) e_pol += kKcalToEv * (ai.chi * xi.w + (ai.eta / 2.) * sqr(xi.w));
     const double Delta_i = v.Delta[i], Delta_lp_i = v.Delta_lp[i], dDelta_lp_i = v.dDelta_lp[i], Delta_lp_temp_i = v.Delta_lp_temp[i];
     const double total_bo_i = v.total_bo[i];
 
@@ -194,9 +193,9 @@ k_multi(DevView v, DevParams P) {
     cdd_i = warp_sum(cdd_i);
     if (lane == 0 && cdd_i != 0.0) atomicAdd(&v.CdDelta[i], cdd_i);
   }
-  const int slots[5] = {E_LP, E_OV, E_UN, E_BOND, E_POL};
-  double vals[5] = {e_lp, e_ov, e_un, e_bond, e_pol};
-  block_commit<5>(v.en, slots, vals);
+  const int slots[4] = {E_LP, E_OV, E_UN, E_BOND};
+  double vals[4] = {e_lp, e_ov, e_un, e_bond};
+  block_commit<4>(v.en, slots, vals);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -788,25 +787,35 @@ k_dbond(DevView v, BondedWork W) {
 
 }  // namespace
 
-void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
+// part 1 needs only the bond list; part 2 also needs this step's far list (hydrogen-bond partners)
+void launch_bonded_part1(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   if (v.n == 0) return;
   BondedWork W = s.bonded_work();
   RXB_CUDA(cudaMemsetAsync(W.n_ang, 0, 4 * sizeof(int), st));
   RXB_CUDA(cudaMemsetAsync(W.sum56, 0, (size_t)v.N * sizeof(double2), st));
-  int t = s.tick(StepTimers::MULTI);
+  const int t = s.tick(StepTimers::MULTI, st);
   k_multi<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  s.tock(t);
-  t = s.tick(StepTimers::ENUM);
+  s.tock(t, st);
+  s.kernel_launches += 1;
+}
+void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
+  if (v.n == 0) return;
+  BondedWork W = s.bonded_work();
+  int t = s.tick(StepTimers::ENUM, st);
   k_enum<<<kBlocks, kWarps * 32, 0, st>>>(v, P, W);
-  s.tock(t);
-  t = s.tick(StepTimers::HBOND);
+  s.tock(t, st);
+  t = s.tick(StepTimers::HBOND, st);
   k_hbond_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
-  s.tock(t);
-  t = s.tick(StepTimers::VALTOR);
+  s.tock(t, st);
+  t = s.tick(StepTimers::VALTOR, st);
   k_angle_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
   k_torsion_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
-  s.tock(t);
-  s.kernel_launches += 5;
+  s.tock(t, st);
+  s.kernel_launches += 4;
+}
+void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
+  launch_bonded_part1(s, v, P, st);
+  launch_bonded_part2(s, v, P, st);
 }
 
 void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st) {

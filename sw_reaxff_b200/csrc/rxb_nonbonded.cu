@@ -18,6 +18,7 @@ namespace {
 
 constexpr double kCele = 332.06371;  // C_ele
 constexpr double kEvToKcal = 14.4;   // EV_TO_KCAL_PER_MOL
+constexpr double kKcalToEv = 23.02;  // KCALpMOL_to_EV
 constexpr int kWarps = 8;
 constexpr int kBlocks = 148 * 8;
 
@@ -76,7 +77,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
 template <bool EV>
 __global__ void __launch_bounds__(kWarps * 32, 3)
 k_nonbonded(DevView v, DevParams P) {
-  __shared__ double sh[8][kWarps];
+  __shared__ double sh[9][kWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   const double p_vdW1 = P.gp[28], p_vdW1i = 1.0 / p_vdW1;
@@ -85,7 +86,7 @@ k_nonbonded(DevView v, DevParams P) {
   double Tap[8];
 #pragma unroll
   for (int t = 0; t < 8; t++) Tap[t] = P.ctl.Tap[t];
-  double e_vdw = 0, e_ele = 0, vir[6] = {0, 0, 0, 0, 0, 0};
+  double e_vdw = 0, e_ele = 0, e_pol = 0, vir[6] = {0, 0, 0, 0, 0, 0};
   for (int i = wg; i < v.n; i += nwg) {
     const int ti = v.type[i];
     if (ti < 0) continue;
@@ -161,26 +162,30 @@ k_nonbonded(DevView v, DevParams P) {
       // only writer of f[i] so far in the step for local i would be a plain store, but bonded kernels may run
       // concurrently on another stream: keep it an atomic
       atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
-      if (EV) {  // -x_i (x) f_i^nb : cancels this kernel's share of the later f.x sum over all atoms
+      if (EV) {
+        // polarisation energy (reaxc_multi_body_sw64.c:100-103, plain sum) lives here because it needs this step's q
+        e_pol += kKcalToEv * (P.atom[ti].chi * pi.w + (P.atom[ti].eta / 2.) * pi.w * pi.w);
+        // -x_i (x) f_i^nb : cancels this kernel's share of the later f.x sum over all atoms
         vir[0] -= pi.x * fx; vir[1] -= pi.y * fy; vir[2] -= pi.z * fz;
         vir[3] -= pi.x * fy; vir[4] -= pi.x * fz; vir[5] -= pi.y * fz;
       }
     }
   }
   if (EV) {
-    double vals[8] = {e_vdw, e_ele, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5]};
+    double vals[9] = {e_vdw, e_ele, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5], e_pol};
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 9; k++) {
       const double s = warp_sum(vals[k]);
       if (lane == 0) sh[k][wib] = s;
     }
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < 9) {
       double s = 0;
       for (int w = 0; w < kWarps; w++) s += sh[threadIdx.x][w];
       if (s != 0.0) {
         if (threadIdx.x == 0) atomicAdd(&v.en[E_VDW], s);
         else if (threadIdx.x == 1) atomicAdd(&v.en[E_ELE], s);
+        else if (threadIdx.x == 8) atomicAdd(&v.en[E_POL], s);
         else atomicAdd(&v.virial[threadIdx.x - 2], s);
       }
     }

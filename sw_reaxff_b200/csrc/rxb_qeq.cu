@@ -31,7 +31,6 @@ struct QeqDev {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kBlocksSpmv = 148 * 8;
 constexpr int kVecBlocks = 148 * 4;
 constexpr int kVecThreads = 256;
 
@@ -77,8 +76,9 @@ k_spmv2(int n, const long long* __restrict__ off, const int* __restrict__ num, c
     const int m = num[i];
     double ax = 0, ay = 0;
     for (int k = lane; k < m; k += 32) {
-      const double h = val[beg + k];
-      const double2 xj = x[col[beg + k]];
+      // H is streamed exactly once per SpMV: evict-first loads keep the gathered x vector (16 B/atom) resident in L2/L1
+      const double h = __ldcs(val + beg + k);
+      const double2 xj = __ldg(x + __ldcs(col + beg + k));
       ax += h * xj.x; ay += h * xj.y;
     }
     ax = warp_sum(ax); ay = warp_sum(ay);
@@ -298,6 +298,7 @@ void System::qeq_pre_force() {
   const int t_QEQ_H = tick(StepTimers::QEQ_H);
   launch_far_and_H(*this, v, dp_, Tap, shld_d.p, qeq_swb, st_);
   tock(t_QEQ_H);
+  after_far_hook();
 
   const int t_QEQ_CG = tick(StepTimers::QEQ_CG);
   const size_t nn = n, NN = std::max((size_t)N, slab());  // all-gathered arrays must hold a whole slab
@@ -314,7 +315,8 @@ void System::qeq_pre_force() {
   };
   auto spmv = [&](const double2* x, double2* y, const QeqDev* gate, int parity) {
     const int ts = tick(StepTimers::SPMV);
-    k_spmv2<<<kBlocksSpmv, kWarps * 32, 0, st_>>>(n, vl.off.p, far_num.p, far_idx.p, H_val.p, type.p, dp_.atom, x, y, gate, parity);
+    // one row per warp, blocks retire continuously: lets the high-priority bond-chain stream interleave on every SM
+    k_spmv2<<<std::max(1, (n + kWarps - 1) / kWarps), kWarps * 32, 0, st_>>>(n, vl.off.p, far_num.p, far_idx.p, H_val.p, type.p, dp_.atom, x, y, gate, parity);
     tock(ts);
     kernel_launches++;
   };

@@ -193,6 +193,14 @@ void Box::set(double xprd, double yprd, double zprd, double xy, double xz, doubl
 System::System(int device) : device_(device) {
   RXB_CUDA(cudaSetDevice(device));
   RXB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    RXB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RXB_CUDA(cudaStreamCreateWithPriority(&st2_, cudaStreamNonBlocking, hi));
+  }
+  RXB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  RXB_CUDA(cudaEventCreateWithFlags(&ev_far_, cudaEventDisableTiming));
+  RXB_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6);
   RXB_CUDA(cudaMemset(overflow.p, 0, sizeof(int)));
 }
@@ -203,6 +211,8 @@ System::~System() {
   if (h_pin_) cudaFreeHost(h_pin_);
   for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
   if (st_) cudaStreamDestroy(st_);
+  if (st2_) cudaStreamDestroy(st2_);
+  if (ev_fork_) { cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_far_); cudaEventDestroy(ev_join_); }
 }
 
 double* System::pin(size_t doubles) {
@@ -214,19 +224,20 @@ double* System::pin(size_t doubles) {
   return h_pin_;
 }
 
-int System::tick(int which) {
+int System::tick(int which, cudaStream_t st) {
   if (!profile) return -1;
+  if (!st) st = st_;
   if (ev_used_ + 2 > ev_pool_.size()) {
     for (int k = 0; k < 64; k++) { cudaEvent_t e; RXB_CUDA(cudaEventCreate(&e)); ev_pool_.push_back(e); }
   }
   const int a = (int)ev_used_++, b = (int)ev_used_++;
-  RXB_CUDA(cudaEventRecord(ev_pool_[a], st_));
+  RXB_CUDA(cudaEventRecord(ev_pool_[a], st));
   ev_pending_.push_back(Pending{which, a, b});
   return (int)ev_pending_.size() - 1;
 }
-void System::tock(int id) {
+void System::tock(int id, cudaStream_t st) {
   if (id < 0) return;
-  RXB_CUDA(cudaEventRecord(ev_pool_[ev_pending_[id].b], st_));
+  RXB_CUDA(cudaEventRecord(ev_pool_[ev_pending_[id].b], st ? st : st_));
 }
 void System::resolve_timers() {
   if (ev_pending_.empty()) return;
@@ -535,10 +546,65 @@ void System::md_make_ghosts() {
   RXB_CUDA(cudaGetLastError());
 }
 
+// Two-stream step: the bond list -> bond orders -> multi-body -> angle/torsion/hbond chain does not
+// depend on this step's charges, so it runs on st2_ while the latency/HBM-bound CG solve runs on st_.  Only the hydrogen
+// bond enumeration needs this step's far list (event after K-farH); K-nb needs q; K-dbond joins both.
+void System::after_far_hook() {
+  if (!hook_after_far_) return;
+  hook_after_far_ = false;
+  DevView v = view();
+  RXB_CUDA(cudaEventRecord(ev_far_, st_));
+  RXB_CUDA(cudaStreamWaitEvent(st2_, ev_far_, 0));
+  launch_bonded_part2(*this, v, dp_, st2_);
+  RXB_CUDA(cudaEventRecord(ev_join_, st2_));
+}
+
+void System::md_force_overlapped(bool ev) {
+  DevView v = view();
+  RXB_CUDA(cudaMemsetAsync(f.p, 0, (size_t)3 * N * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(en_d.p, 0, E_NUM * sizeof(double), st_));
+  RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, 6 * sizeof(double), st_));
+  RXB_CUDA(cudaEventRecord(ev_fork_, st_));
+  RXB_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+  launch_bond_list(*this, v, dp_, st2_);
+  launch_bond_orders(*this, v, dp_, st2_);
+  launch_bonded_part1(*this, v, dp_, st2_);
+  hook_after_far_ = true;
+  qeq_pre_force();                       // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
+  qeq_ran_this_step_ = false;
+  launch_nonbonded(*this, v, dp_, ev, st_);
+  RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
+  launch_dbond(*this, v, dp_, st_);
+  if (ev) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
+  int h[2], wk[4];
+  RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaMemcpyAsync(wk, it_count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  if (ev && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
+  if (ev) {
+    RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  }
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  num_bonds = h[0]; overflow_flag = h[1];
+  num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
+  if ((overflow_flag & 2) || wk[0] > cap_ang || wk[1] > cap_tor || wk[2] > cap_hb) {
+    qeq_ran_this_step_ = true;           // far list and charges of this step are valid: replay only the force phase
+    compute(ev, ev);                     // sequential path grows the arrays and replays
+  } else if (overflow_flag & ~2) {
+    throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
+  }
+}
+
 void System::md_force() {
-  if (qeq_on) qeq_pre_force();
   const bool ev = md_thermo > 0 && (ntimestep % md_thermo == 0);
-  compute(ev, ev);
+  if (overlap && qeq_on && !profile) {
+    md_force_overlapped(ev);
+  } else {
+    if (qeq_on) qeq_pre_force();
+    compute(ev, ev);
+  }
   const int nghost = N - n;
   if (dist_) dist_reverse_f();
   else if (nghost > 0) { k_reverse_f<<<nblk(nghost), 256, 0, st_>>>(n, nghost, ghost_owner.p, f.p); kernel_launches++; }

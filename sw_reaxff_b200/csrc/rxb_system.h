@@ -140,6 +140,7 @@ class System {
   int md_every = 5, md_ago = 0;
   double md_dt = 0.0625;
   bool qeq_on = true;
+  bool overlap = true;       // run the bond-order chain on a second stream concurrently with the QEq solve
   int md_thermo = 5;         // energies are reduced every md_thermo steps (thermo 5, in.reaxc.lattice:832)
 
   // ---- multi-GPU (rxb_dist.cu): brick decomposition + NCCL ----
@@ -160,8 +161,8 @@ class System {
   std::vector<double> params_dump() const { return ff.dump(); }
   cudaStream_t stream() const { return st_; }
   StepTimers timers;
-  int tick(int which);          // lazy CUDA-event timers on the launch stream: no sync inside a step
-  void tock(int id);
+  int tick(int which, cudaStream_t st = nullptr);  // lazy CUDA-event timers on the launch stream: no sync inside a step
+  void tock(int id, cudaStream_t st = nullptr);
   void resolve_timers();
   double last_run_ms = 0.0;     // device time of the last md_run (CUDA events on the launch stream)
   bool profile = false;
@@ -205,7 +206,11 @@ class System {
  private:
   int device_;
   Dist* dist_ = nullptr;
-  cudaStream_t st_ = nullptr;
+  cudaStream_t st_ = nullptr, st2_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_far_ = nullptr, ev_join_ = nullptr;
+  bool hook_after_far_ = false;
+  void after_far_hook();
+  void md_force_overlapped(bool ev);
   std::vector<cudaEvent_t> ev_pool_;
   struct Pending { int which; int a, b; };
   std::vector<Pending> ev_pending_;
@@ -230,6 +235,8 @@ class System {
 void launch_bond_list(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_bond_orders(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_bonded_part1(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* qeq_tap, const double* shld, double swb,
                       cudaStream_t st);

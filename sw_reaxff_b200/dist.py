@@ -171,7 +171,7 @@ def run_distributed(args, rank, world, local_rank, cells, H):
     th = r.md_thermo()
     out = {
         "metric": METRIC, "value": value, "unit": "atom-timesteps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if getattr(args, "strong", False) else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (TATB 384-atom cell replicated by lattice translation, per-tag Gaussian velocities 300 K)",
         "config": {**config_for(cells), "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} bricks, {natoms_total // world} atoms per GPU, "
                    "ghost shell 12.5 A, NCCL all-gather halo / reduce-scatter reverse / all-reduce dots inside the library",
