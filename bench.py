@@ -266,28 +266,27 @@ def run_b200(args, rank, world, local_rank):
                 "avg_launch_us": spmv_avg * 1e6, "launches_per_step": spmv_calls / nprof,
                 "share_of_step": (spmv_ms / nprof) / step_ms}
 
-    # ---- end to end through the plugin calls with host buffers ----
-    r2 = Rxb(local_rank)
-    r2.pair_settings(H.CONTROL)
-    r2.pair_coeff(H.FFIELD, H.ELEMENTS)
-    r2.fix_qeq(0.0, 10.0, 1e-6)
-    ps = PluginStepper(r2, H, box, x, v, t, tag)
-    for _ in range(max(args.warmup, 3)):
-        ps.step()
-    e2e_steps = min(args.steps, 50)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ps.step()
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
-    nall2 = len(ps.x)
-    e2e = {"value": natoms * e2e_steps / e2e_dt, "unit": "atom-timesteps/s", "h2d_bytes_per_step": nall2 * 24,
-           "d2h_bytes_per_step": nall2 * 24 + 14 * 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-           "note": "rxb_set_positions / rxb_neigh_build / rxb_qeq_pre_force / rxb_pair_compute with host x in and host f out "
-                   "every step; host-side velocity-Verlet, ghost forward and reverse_comm (numpy) inside the timed region; "
-                   "ghost set fixed during the window, lists rebuilt every 5 steps"}
-    del r2
+    # ---- end to end through the LAMMPS-facing plugin calls with HOST buffers (C++ styles in sw_reaxff_b200/host) ----
+    import ctypes as C
+    hostlib = C.CDLL(os.path.join(ROOT, "sw_reaxff_b200", "librxb200_host.so"))
+    script = os.path.join(H.DATA, "in.tatb.b200")
+    if cells[0] == cells[1] == cells[2]:
+        kv = {"S": cells[0], "t": 0, "T": 300.0, "D": H.DATA}
+        names = (C.c_char_p * len(kv))(*[k.encode() for k in kv]); vals = (C.c_char_p * len(kv))(*[str(v).encode() for v in kv.values()])
+        out4 = (C.c_double * 4)(); err = C.create_string_buffer(512)
+        e2e_steps = min(args.steps, 50)
+        rc = hostlib.rxh_bench_script(script.encode(), len(kv), names, vals, local_rank, max(args.warmup, 3), e2e_steps, out4, err, 512)
+        if rc != 0:
+            raise RuntimeError("e2e run failed: " + err.value.decode())
+        nall2, e2e_dt = int(out4[1]), float(out4[2])
+        e2e = {"value": natoms * e2e_steps / e2e_dt, "unit": "atom-timesteps/s", "h2d_bytes_per_step": nall2 * 24,
+               "d2h_bytes_per_step": nall2 * 24 + 22 * 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
+               "note": "C++ host styles (PairReaxCB200::compute, FixQEqReaxB200::pre_force, FixNVEB200) on the LAMMPS-core stand-in, "
+                       "script sw_reaxff_b200/data/tatb/in.tatb.b200: host x uploaded (rxb_set_positions / rxb_set_atoms + "
+                       "rxb_neigh_build on reneighbouring steps), host f downloaded (rxb_pair_compute) every step; host-side "
+                       "integration, borders/forward/reverse comm inside the timed region (wall clock)"}
+    else:
+        e2e = {"value": None, "unit": "atom-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "non-cubic replication: not measured"}
 
     cpu, _, _ = cpu_baseline(H) if not args.no_cpu_baseline else ({"value": None, "unit": "atom-timesteps/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0, 0)
     out = {

@@ -1,0 +1,200 @@
+// See styles_b200.h.  Error texts are the reference's (pair_reaxc_sunway.cpp, fix_qeq_reax_sunway.cpp, fix_nve_sunway.cpp).
+#include "styles_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace LAMMPS_MINI {
+
+// ---------------------------------------------------------------------------------------------------------------
+PairReaxCB200::PairReaxCB200(LAMMPS* l) : Pair(l) {}
+
+PairReaxCB200::~PairReaxCB200() {
+  if (rxb) rxb_destroy(rxb);
+}
+
+void PairReaxCB200::settings(int narg, char** arg) {
+  Error* error = lmp->error;
+  if (narg < 1) error->all(FLERR, "Illegal pair_style command");
+  control_file_ = arg[0];
+  qeqflag = 1; lgflag = 0; enobondsflag = 1; mincap = 50; safezone = 1.2; saferzone = 1.4; maxfar = 1024;
+  int iarg = 1;
+  while (iarg < narg) {
+    auto yesno = [&](int& flag) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal pair_style reax/c command");
+      if (!strcmp(arg[iarg + 1], "yes")) flag = 1;
+      else if (!strcmp(arg[iarg + 1], "no")) flag = 0;
+      else error->all(FLERR, "Illegal pair_style reax/c command");
+      iarg += 2;
+    };
+    if (!strcmp(arg[iarg], "checkqeq")) yesno(qeqflag);
+    else if (!strcmp(arg[iarg], "enobonds")) yesno(enobondsflag);
+    else if (!strcmp(arg[iarg], "lgvdw")) yesno(lgflag);
+    else if (!strcmp(arg[iarg], "safezone")) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal pair_style reax/c command");
+      safezone = atof(arg[iarg + 1]);
+      if (safezone < 0.0) error->all(FLERR, "Illegal pair_style reax/c safezone command");
+      saferzone = safezone * 1.2 + 0.2;
+      iarg += 2;
+    } else if (!strcmp(arg[iarg], "mincap")) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal pair_style reax/c command");
+      mincap = atoi(arg[iarg + 1]);
+      if (mincap < 0) error->all(FLERR, "Illegal pair_style reax/c mincap command");
+      iarg += 2;
+    } else if (!strcmp(arg[iarg], "maxfar")) {
+      if (iarg + 2 > narg) error->all(FLERR, "Illegal pair_style reax/c command");
+      maxfar = atoi(arg[iarg + 1]);   // accepted for script compatibility; rows are carved dynamically on the device
+      if (maxfar < 0) error->all(FLERR, "Illegal pair_style reax/c maxfar command");
+      iarg += 2;
+    } else error->all(FLERR, "Illegal pair_style reax/c command");
+  }
+  if (!rxb && rxb_create(lmp->cuda_device, &rxb)) error->all(FLERR, rxb_last_error());
+  if (rxb_pair_settings(rxb, control_file_.c_str(), lgflag, enobondsflag)) error->all(FLERR, rxb_last_error());
+}
+
+void PairReaxCB200::coeff(int nargs, char** args) {
+  Error* error = lmp->error;
+  Atom* atom = lmp->atom;
+  if (nargs != 3 + atom->ntypes) error->all(FLERR, "Incorrect args for pair coefficients");
+  if (strcmp(args[0], "*") != 0 || strcmp(args[1], "*") != 0) error->all(FLERR, "Incorrect args for pair coefficients");
+  if (rxb_pair_coeff(rxb, args[2], atom->ntypes, args + 3)) {
+    std::string e = rxb_last_error();
+    error->all(FLERR, e);
+  }
+  chi.assign(atom->ntypes + 1, 0); eta.assign(atom->ntypes + 1, 0); gamma.assign(atom->ntypes + 1, 0);
+  rxb_pair_extract(rxb, "chi", chi.data(), atom->ntypes);
+  rxb_pair_extract(rxb, "eta", eta.data(), atom->ntypes);
+  rxb_pair_extract(rxb, "gamma", gamma.data(), atom->ntypes);
+  coeff_done_ = true;
+}
+
+void PairReaxCB200::init_style() {
+  Error* error = lmp->error;
+  Atom* atom = lmp->atom;
+  if (!atom->q_flag) error->all(FLERR, "Pair style reax/c requires atom attribute q");
+  bool have_qeq = false;
+  for (auto& f : lmp->fixes) have_qeq = have_qeq || f->style.find("qeq/reax") != std::string::npos;
+  if (!have_qeq && qeqflag == 1) error->all(FLERR, "Pair reax/c requires use of fix qeq/reax");
+  if (atom->tag_enable == 0) error->all(FLERR, "Pair style reax/c requires atom IDs");
+  if (lmp->force->newton_pair == 0) error->all(FLERR, "Pair style reax/c requires newton pair on");
+  if (!coeff_done_) error->all(FLERR, "All pair coeffs are not set");
+  // cutmax = MAX3(nonb_cut, hbond_cut, 2*bond_cut): read back from the parsed parameters
+  long n = rxb_params_dump(rxb, nullptr, 0);
+  std::vector<double> d(n);
+  rxb_params_dump(rxb, d.data(), n);
+  const int ngp = (int)d[2];
+  const double* ctl = &d[3 + ngp];
+  cutmax = std::max(ctl[2], std::max(ctl[4], 2 * ctl[3]));
+  rxb_neighbor_skin(rxb, lmp->neighbor->skin);
+}
+
+void PairReaxCB200::upload_if_needed() {
+  Atom* atom = lmp->atom;
+  if (uploaded_step == lmp->update->ntimestep) return;
+  if (lmp->neighbor->ago == 0) {
+    // reneighbouring step: new index space (what write_reax_atoms + NPair::build + write_reax_lists do in the reference)
+    if (rxb_set_atoms(rxb, atom->nlocal, atom->nghost, atom->x.data(), atom->type.data(), atom->tag.data(), atom->q.data(),
+                      lmp->comm->ghost_owner.data()))
+      lmp->error->all(FLERR, rxb_last_error());
+    if (rxb_neigh_build(rxb)) lmp->error->all(FLERR, rxb_last_error());
+  } else {
+    if (rxb_set_positions(rxb, atom->x.data())) lmp->error->all(FLERR, rxb_last_error());
+  }
+  uploaded_step = lmp->update->ntimestep;
+}
+
+void PairReaxCB200::compute(int eflag, int vflag) {
+  Atom* atom = lmp->atom;
+  upload_if_needed();
+  const int nall = atom->nall();
+  fbuf_.resize((size_t)3 * nall);
+  double eng[2], vir[6];
+  if (rxb_pair_compute(rxb, eflag, vflag, fbuf_.data(), pvector, eng, vir)) lmp->error->all(FLERR, rxb_last_error());
+  double* f = atom->f.data();
+  for (size_t k = 0; k < (size_t)3 * nall; k++) f[k] += fbuf_[k];
+  if (eflag) { eng_vdwl = eng[0]; eng_coul = eng[1]; }
+  if (vflag) for (int k = 0; k < 6; k++) virial[k] = vir[k];
+}
+
+void* PairReaxCB200::extract(const char* str, int& dim) {
+  dim = 1;
+  if (!strcmp(str, "chi")) return chi.data();
+  if (!strcmp(str, "eta")) return eta.data();
+  if (!strcmp(str, "gamma")) return gamma.data();
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+FixQEqReaxB200::FixQEqReaxB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
+  Error* error = lmp->error;
+  if (narg < 8 || narg > 9) error->all(FLERR, "Illegal fix qeq/reax command");
+  id = arg[0]; style = arg[2];
+  nevery = atoi(arg[3]);
+  if (nevery <= 0) error->all(FLERR, "Illegal fix qeq/reax command");
+  swa = atof(arg[4]); swb = atof(arg[5]); tolerance = atof(arg[6]);
+  if (strcmp(arg[7], "reax/c") != 0) error->all(FLERR, "fix qeq/reax: only the reax/c parameter source is supported by this build");
+  if (narg == 9 && strcmp(arg[8], "dual") != 0) error->all(FLERR, "Illegal fix qeq/reax command");
+  // ("dual" is accepted: both solves always run fused here)
+}
+
+void FixQEqReaxB200::init() {
+  Error* error = lmp->error;
+  if (!lmp->atom->q_flag) error->all(FLERR, "Fix qeq/reax requires atom attribute q");
+  reaxc = dynamic_cast<PairReaxCB200*>(lmp->pair.get());
+  if (!reaxc) error->all(FLERR, "Fix qeq/reax: could not extract params from pair reax/c");
+  if (swb < 0) error->all(FLERR, "Fix qeq/reax has negative upper Taper radius cutoff");
+  if (fabs(swa) > 0.01) error->warning(FLERR, "Fix qeq/reax has non-zero lower Taper radius cutoff");
+  else if (swb < 5) error->warning(FLERR, "Fix qeq/reax has very low Taper radius cutoff");
+  if (rxb_fix_qeq(reaxc->rxb, swa, swb, tolerance, 200)) error->all(FLERR, rxb_last_error());
+}
+
+void FixQEqReaxB200::setup_pre_force(int vflag) { pre_force(vflag); }
+
+void FixQEqReaxB200::pre_force(int) {
+  if (lmp->update->ntimestep % nevery) return;
+  reaxc->upload_if_needed();
+  int mv[2];
+  if (rxb_qeq_pre_force(reaxc->rxb, mv)) lmp->error->all(FLERR, rxb_last_error());
+  matvecs_s = mv[0]; matvecs_t = mv[1]; matvecs = mv[0] + mv[1];
+  if (mv[0] >= 200 || mv[1] >= 200)
+    lmp->error->warning(FLERR, "Fix qeq/reax CG convergence failed after 200 iterations at " + std::to_string(lmp->update->ntimestep) + " step");
+  // atom->q on the host is only needed by host-side consumers (thermo/dump): refresh it on thermo steps
+  if (lmp->thermo_every && lmp->update->ntimestep % lmp->thermo_every == 0)
+    rxb_get_charges(reaxc->rxb, lmp->atom->q.data());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+FixNVEB200::FixNVEB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
+  if (narg < 3) lmp->error->all(FLERR, "Illegal fix nve command");
+  id = arg[0]; style = arg[2];
+}
+
+void FixNVEB200::init() {
+  dtv = lmp->update->dt;
+  dtf = 0.5 * lmp->update->dt * lmp->force->ftm2v;
+}
+
+void FixNVEB200::initial_integrate(int) {
+  Atom* a = lmp->atom;
+  double* x = a->x.data(); double* v = a->v.data(); const double* f = a->f.data();
+  for (int i = 0; i < a->nlocal; i++) {
+    const double dtfm = dtf / a->mass[a->type[i]];
+    for (int t = 0; t < 3; t++) {
+      v[3 * i + t] += dtfm * f[3 * i + t];
+      x[3 * i + t] += dtv * v[3 * i + t];
+    }
+  }
+}
+
+void FixNVEB200::final_integrate() {
+  Atom* a = lmp->atom;
+  double* v = a->v.data(); const double* f = a->f.data();
+  for (int i = 0; i < a->nlocal; i++) {
+    const double dtfm = dtf / a->mass[a->type[i]];
+    for (int t = 0; t < 3; t++) v[3 * i + t] += dtfm * f[3 * i + t];
+  }
+}
+
+}  // namespace LAMMPS_MINI

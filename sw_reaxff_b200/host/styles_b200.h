@@ -1,0 +1,60 @@
+// B200 styles behind the reference's plugin surface: same class roles, member names and argument meaning as
+//   PairReaxCSunway   (/root/reference/pair_reaxc_sunway.{h,cpp})      -> PairReaxCB200      pair_style reax/c
+//   FixQEqReaxSunway  (/root/reference/fix_qeq_reax_sunway.{h,cpp})    -> FixQEqReaxB200     fix qeq/reax
+//   FixNVESunway      (/root/reference/fix_nve_sunway.{h,cpp})         -> FixNVEB200         fix nve
+// Each hook validates its arguments exactly like the reference and then makes ONE call into the C ABI (include/rxb200.h).
+#pragma once
+#include "../../include/rxb200.h"
+#include "mini_lammps.h"
+
+namespace LAMMPS_MINI {
+
+class PairReaxCB200 : public Pair {
+ public:
+  explicit PairReaxCB200(LAMMPS* lmp);
+  ~PairReaxCB200() override;
+  void settings(int narg, char** arg) override;      // pair_reaxc_sunway.cpp:202-290
+  void coeff(int narg, char** arg) override;         // :294-362
+  void init_style() override;                        // :366-424
+  void compute(int eflag, int vflag) override;       // :541-793
+  void* extract(const char* str, int& dim) override; // :1106-1128
+  double cutghost_request() const override { return cutmax; }
+  void upload_if_needed();                            // shared with fix qeq/reax: whoever runs first this step uploads x
+
+  rxb_handle* rxb = nullptr;
+  int qeqflag = 1, lgflag = 0, enobondsflag = 1;
+  double safezone = 1.2, saferzone = 1.4;
+  int mincap = 50, maxfar = 1024;
+  double cutmax = 0.0;
+  std::vector<double> chi, eta, gamma;
+  std::vector<int> map;
+  long uploaded_step = -1;
+  int fixspecies_flag = 0, fixbond_flag = 0;
+
+ private:
+  std::vector<double> fbuf_;
+  std::string control_file_;
+  bool coeff_done_ = false;
+};
+
+class FixQEqReaxB200 : public Fix {
+ public:
+  FixQEqReaxB200(LAMMPS* lmp, int narg, char** arg); // fix_qeq_reax_sunway.cpp:76-140
+  void init() override;                              // :402-436
+  void setup_pre_force(int vflag) override;          // :488-499
+  void pre_force(int vflag) override;                // :539-600
+  int nevery = 1, matvecs = 0, matvecs_s = 0, matvecs_t = 0;
+  double swa = 0.0, swb = 10.0, tolerance = 1e-6;
+  PairReaxCB200* reaxc = nullptr;
+};
+
+class FixNVEB200 : public Fix {
+ public:
+  FixNVEB200(LAMMPS* lmp, int narg, char** arg);     // fix_nve_sunway.cpp:31-40
+  void init() override;                              // :57-65
+  void initial_integrate(int vflag) override;        // fix_nve_sw64.c:43-99
+  void final_integrate() override;                   // :101-170
+  double dtv = 0, dtf = 0;
+};
+
+}  // namespace LAMMPS_MINI

@@ -1,0 +1,97 @@
+"""Host-side C++ styles (sw_reaxff_b200/host): the LAMMPS-facing classes + minimal core stand-in, driven by input
+scripts exactly like `lmp -in ... -var S n` in the reference's run.sh.  CPU part: parser/error behaviour.  GPU part:
+the host-buffer plugin path reproduces the resident path and the golden step-0 energies."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+HOSTLIB = os.path.join(H.ROOT, "sw_reaxff_b200", "librxb200_host.so")
+SCRIPT = os.path.join(H.DATA, "in.tatb.b200")
+
+
+def build_host():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(H.ROOT, "sw_reaxff_b200", "host"), "all"])
+
+
+def run_script(script, **variables):
+    build_host()
+    L = C.CDLL(HOSTLIB)
+    L.rxh_run_script.restype = C.c_long
+    names = (C.c_char_p * len(variables))(*[k.encode() for k in variables])
+    vals = (C.c_char_p * len(variables))(*[str(v).encode() for v in variables.values()])
+    out = np.zeros((4096, 19))
+    err = C.create_string_buffer(1024)
+    n = L.rxh_run_script(script.encode(), len(variables), names, vals, 0, out.ctypes.data_as(C.c_void_p), C.c_long(4096), err, 1024)
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    return out[:n]
+
+
+def lattice_script(tmp_path, t):
+    """Same system expressed the way in.reaxc.lattice does it: lattice custom + region prism + create_atoms basis."""
+    box6, x, ty, _ = H.read_data_tatb()
+    a1 = np.array([box6[0], 0, 0]); a2 = np.array([box6[3], box6[1], 0]); a3 = np.array([box6[4], box6[5], box6[2]])
+    frac = np.linalg.solve(np.stack([a1, a2, a3], axis=1), x.T).T
+    frac -= np.floor(frac)
+    L = ["variable S index 1", "variable t index %d" % t, "units real", "atom_style charge",
+         "variable xhi equal $S*%.10f" % box6[0], "variable yhi equal $S*%.10f" % box6[1], "variable zhi equal $S*%.10f" % box6[2],
+         "variable xy equal $S*%.11f" % box6[3], "variable xz equal $S*%.11f" % box6[4], "variable yz equal $S*%.11f" % box6[5],
+         "lattice custom 1 &", "a1 %.10f 0.0 0.0 &" % a1[0], "a2 %.11f %.10f 0.0 &" % (a2[0], a2[1]), "a3 %.11f %.11f %.10f &" % tuple(a3)]
+    L += ["basis %.15f %.15f %.15f &" % tuple(f) for f in frac]
+    L += ["", "region 1 prism 0.0 ${xhi} 0.0 ${yhi} 0.0 ${zhi} ${xy} ${xz} ${yz} units box", "create_box 4 1", "create_atoms 4 box &"]
+    L += ["basis %d %d &" % (i + 1, t_) for i, t_ in enumerate(ty)]
+    L += ["", "mass 1 12.0000", "mass 2 1.0080", "mass 3 15.9990", "mass 4 14.0000",
+          "pair_style reax/c %s maxfar 512" % H.CONTROL, "pair_coeff * * %s C H O N" % H.FFIELD,
+          "neighbor 2.5 bin", "neigh_modify delay 0 every 5 check no one 1024", "fix 1 all nve",
+          "fix 2 all qeq/reax 1 0.0 10.0 1.0e-6 reax/c", "thermo 5", "timestep 0.0625", "run $t"]
+    p = tmp_path / "in.lattice"
+    p.write_text("\n".join(L) + "\n")
+    return str(p)
+
+
+def test_script_errors_reported(tmp_path):
+    p = tmp_path / "in.bad"
+    p.write_text("units real\natom_style charge\nfrobnicate 1 2 3\n")
+    with pytest.raises(RuntimeError, match="Unknown command: frobnicate"):
+        run_script(str(p))
+    p.write_text("units lj\n")
+    with pytest.raises(RuntimeError, match="units real"):
+        run_script(str(p))
+    p.write_text("units real\natom_style charge\nread_data %s\nfix 2 all qeq/reax 0 0.0 10.0 1e-6 reax/c\n" % H.DATAFILE)
+    with pytest.raises(RuntimeError, match="Illegal fix qeq/reax command"):
+        run_script(str(p))
+    p.write_text("units real\natom_style charge\nread_data %s\nfix 1 all nve\nrun 1\n" % H.DATAFILE)
+    with pytest.raises(RuntimeError, match="No pair style defined"):
+        run_script(str(p))
+
+
+@pytest.mark.gpu
+def test_plugin_run_matches_resident_run_and_golden():
+    th = run_script(SCRIPT, S=1, t=10, T=0, D=H.DATA)
+    assert [int(r[0]) for r in th] == [0, 5, 10]
+    g = np.load(os.path.join(H.ROOT, "tests", "golden", "tatb_1x1x1.npz"))
+    assert abs(th[0, 2] - g["energies"].sum()) < 1e-6 * abs(g["energies"].sum())      # step-0 PotEng -44760.998
+    from sw_reaxff_b200 import Rxb
+    box, x, t, tag = H.tatb_cell(1, 1, 1)
+    r = Rxb(0)
+    r.pair_settings(H.CONTROL); r.pair_coeff(H.FFIELD, H.ELEMENTS); r.fix_qeq(0.0, 10.0, 1e-6)
+    r.md_setup(box, x, np.zeros_like(x), t, tag, H.MASS, dt=0.0625, every=5, thermo=5)
+    r.md_run(10)
+    res = r.md_thermo()
+    assert abs(th[2, 2] - res["pe"]) < 1e-7 * abs(res["pe"])
+    assert abs(th[2, 3] - res["ke"]) < 1e-4 * max(res["ke"], 1e-3)
+    np.testing.assert_allclose(th[2, 5:], res["pvector"], rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_reference_style_lattice_script(tmp_path):
+    a = run_script(lattice_script(tmp_path, 5), S=1)
+    b = run_script(SCRIPT, S=1, t=5, T=0, D=H.DATA)
+    assert abs(a[0, 2] - b[0, 2]) < 1e-7 * abs(b[0, 2])       # same crystal from lattice custom + create_atoms basis
+    a2 = run_script(lattice_script(tmp_path, 0), S=2)
+    assert abs(a2[0, 2] - 8 * b[0, 2]) < 1e-7 * abs(8 * b[0, 2])
