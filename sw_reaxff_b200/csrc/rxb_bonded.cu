@@ -66,10 +66,10 @@ __device__ __forceinline__ void block_commit(double* en, const int (&slots)[K], 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// one thread per local atom: the per-atom scalar chain (13 exp) dominates, a warp per atom would redo it 32x
 __global__ void __launch_bounds__(kWarps * 32)
 k_multi(DevView v, DevParams P) {
-  const int lane = threadIdx.x & 31;
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const int wg = blockIdx.x * blockDim.x + threadIdx.x, nwg = gridDim.x * blockDim.x;
   const double p_lp3 = P.gp[5], p_ovun3 = P.gp[32], p_ovun4 = P.gp[31], p_ovun6 = P.gp[6], p_ovun7 = P.gp[8], p_ovun8 = P.gp[9];
   const double gp3 = P.gp[3], gp4 = P.gp[4], gp7 = P.gp[7], gp10 = P.gp[10];
   const int gp37 = (int)P.gp[37];
@@ -86,7 +86,7 @@ k_multi(DevView v, DevParams P) {
     const double total_bo_i = v.total_bo[i];
 
     double sum_ovun1 = 0, sum_ovun2 = 0, cdd_i = 0;
-    for (int e = lane; e < cnt; e += 32) {
+    for (int e = 0; e < cnt; e++) {
       const int p = start + e;
       const int j = v.b_nbr[p], tj = v.type[j];
       if (tj < 0) continue;
@@ -95,8 +95,6 @@ k_multi(DevView v, DevParams P) {
       sum_ovun1 += tw.p_ovun1 * tw.De_s * bo.x;
       sum_ovun2 += (v.Delta[j] - dfvl * v.Delta_lp_temp[j]) * (bo.z + bo.w);
     }
-    sum_ovun1 = warp_sum(sum_ovun1);
-    sum_ovun2 = warp_sum(sum_ovun2);
 
     const double p_lp2 = ai.p_lp2, p_ovun2 = ai.p_ovun2, p_ovun5 = ai.p_ovun5;
     const double expvd2 = exp(-75 * Delta_lp_i);
@@ -126,7 +124,7 @@ k_multi(DevView v, DevParams P) {
     const double CEunder2 = -eun * p_ovun8 * exp_ovun8 * inv_exp_ovun8;
     const double CEunder3 = CEunder1 * (1.0 - dfvl * dDelta_lp_i * inv_exp_ovun1);
     const double CEunder4 = CEunder1 * (dfvl * Delta_lp_temp_i) * p_ovun4 * exp_ovun1 * sqr(inv_exp_ovun1) + CEunder2;
-    if (lane == 0) {
+    {
       e_ov += sum_ovun1 * CEover1;
       cdd_i += CEover3;
       if (active) {
@@ -138,7 +136,7 @@ k_multi(DevView v, DevParams P) {
     }
 
     const bool c2corr = p_lp3 > 0.001 && ai.is_carbon;
-    for (int e = lane; e < cnt; e += 32) {
+    for (int e = 0; e < cnt; e++) {
       const int p = start + e;
       const int j = v.b_nbr[p], tj = v.type[j];
       if (tj < 0) continue;
@@ -190,8 +188,7 @@ k_multi(DevView v, DevParams P) {
       v.b_Cdbopi2[p] += cdbopi2;
       if (cdd_j != 0.0) atomicAdd(&v.CdDelta[j], cdd_j);
     }
-    cdd_i = warp_sum(cdd_i);
-    if (lane == 0 && cdd_i != 0.0) atomicAdd(&v.CdDelta[i], cdd_i);
+    if (cdd_i != 0.0) atomicAdd(&v.CdDelta[i], cdd_i);
   }
   const int slots[4] = {E_LP, E_OV, E_UN, E_BOND};
   double vals[4] = {e_lp, e_ov, e_un, e_bond};
@@ -282,10 +279,9 @@ __device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, 
 __global__ void __launch_bounds__(kWarps * 32)
 k_enum(DevView v, DevParams P, BondedWork W) {
   __shared__ int s_strong[kWarps][32];
-  __shared__ int s_hb[kWarps][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-  const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq, hbond_cut = P.ctl.hbond_cut;
+  const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq;
   const double p_val8 = P.gp[33], p_val9 = P.gp[16];
   const int nt = P.nt;
   const unsigned lt_mask = (1u << lane) - 1;
@@ -293,33 +289,25 @@ k_enum(DevView v, DevParams P, BondedWork W) {
     const int type_j = v.type[j];
     const int start_j = v.b_start[j], cnt_j = v.b_cnt[j];
     if (type_j < 0 || cnt_j <= 0) continue;
-    // ---- strong list, acceptor list, SBO sums ----
+    // ---- strong list, SBO sums ----
     double SBOp = 0, prod_SBO = 1;
-    int ns = 0, top = 0;
-    const bool is_H = P.atom[type_j].p_hbond == 1 && hbond_cut > 0;
+    int ns = 0;
     for (int e0 = 0; e0 < cnt_j; e0 += 32) {
       const int e = e0 + lane;
-      bool strong = false, acc = false;
+      bool strong = false;
       if (e < cnt_j) {
         const double4 bo = v.b_bo[start_j + e];
         SBOp += bo.z + bo.w;
         double t8 = bo.x * bo.x; t8 *= t8; t8 *= t8;
         prod_SBO *= exp(-t8);
         strong = bo.x > thb_cut;
-        if (is_H) {
-          const int ti = v.type[v.b_nbr[start_j + e]];
-          acc = ti >= 0 && P.atom[ti].p_hbond == 2 && bo.x >= kHbThreshold;
-        }
       }
-      unsigned m = __ballot_sync(0xffffffffu, strong);
+      const unsigned m = __ballot_sync(0xffffffffu, strong);
       if (strong) { const int slot = ns + __popc(m & lt_mask); if (slot < 32) s_strong[wib][slot] = start_j + e; }
       ns += __popc(m);
-      m = __ballot_sync(0xffffffffu, acc);
-      if (acc) { const int slot = top + __popc(m & lt_mask); if (slot < 32) s_hb[wib][slot] = start_j + e; }
-      top += __popc(m);
     }
     __syncwarp();
-    if (ns > 32 || top > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = min(ns, 32); top = min(top, 32); }
+    if (ns > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = 32; }
     SBOp = warp_sum(SBOp);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) prod_SBO *= __shfl_xor_sync(0xffffffffu, prod_SBO, o);
@@ -412,52 +400,6 @@ k_enum(DevView v, DevParams P, BondedWork W) {
       }
     }
 
-    // ---- hydrogen bonds: H atom j, acceptor bonds x acceptor-type far neighbours within hbond_cut ----
-    if (is_H && top > 0) {
-      const double4 xj = v.xq[j];
-      const long long fbeg = v.vl_off[j];
-      const int fnum = v.far_num[j];
-      for (int k0 = 0; k0 < fnum; k0 += 32) {
-        const int kk = k0 + lane;
-        unsigned amask = 0u;  // which acceptor bonds pair with this k
-        int k = -1;
-        if (kk < fnum) {
-          k = v.far_idx[fbeg + kk];
-          const int tk = v.type[k];
-          if (tk >= 0 && P.atom[tk].p_hbond == 2) {
-            const double4 xk = v.xq[k];
-            const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
-            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            if (r <= hbond_cut) {
-              const int tag_k = v.tag[k];
-              for (int t = 0; t < top; t++) {
-                const int i = v.b_nbr[s_hb[wib][t]];
-                if (v.tag[i] == tag_k) continue;
-                if (P.hb[(v.type[i] * nt + type_j) * nt + tk].r0_hb <= 0.0) continue;
-                amask |= 1u << t;
-              }
-            }
-          }
-        }
-        const int mine = __popc(amask);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(W.n_hb, total);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          int o = base + incl - mine;
-          while (amask) {
-            const int t = __ffs((int)amask) - 1;
-            amask &= amask - 1;
-            if (o < W.cap_hb) W.hb[o] = make_int4(j, s_hb[wib][t], k, 0);
-            o++;
-          }
-        }
-      }
-    }
     __syncwarp();
   }
 }
@@ -465,7 +407,8 @@ k_enum(DevView v, DevParams P, BondedWork W) {
 constexpr int kItemThreads = 128;
 
 // ------------------------------------------------------------------------------------------------------------
-// K-hb: one thread per (H j, acceptor bond pi, partner k)   reaxc_hydrogen_bonds_sunway.cpp:355-436
+// K-hb: one thread per (H atom j, partner k) candidate emitted by K-farH; loops over the acceptor bonds of j
+// (p_hbond == 2, BO >= HB_THRESHOLD; usually exactly one)   reaxc_hydrogen_bonds_sunway.cpp:313-436
 __global__ void __launch_bounds__(kItemThreads)
 k_hbond_items(DevView v, DevParams P, BondedWork W) {
   const int nitems = min(*W.n_hb, W.cap_hb);
@@ -473,39 +416,49 @@ k_hbond_items(DevView v, DevParams P, BondedWork W) {
   double e_hb = 0;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += gridDim.x * blockDim.x) {
     const int4 w = W.hb[it];
-    const int j = w.x, pi = w.y, k = w.z;
-    const int i = v.b_nbr[pi];
+    const int j = w.x, k = w.y;
+    const int start = v.b_start[j], cnt = v.b_cnt[j];
+    const int tj = v.type[j], tk = v.type[k], tag_k = v.tag[k];
     const double4 xj = v.xq[j], xk = v.xq[k];
     const double dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
     const double r_jk = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-    const HbPar hp = P.hb[(v.type[i] * nt + v.type[j]) * nt + v.type[k]];
-    const double4 gij = v.b_geo[pi];
-    const double BOij = v.b_bo[pi].x;
     const double4 gjk = make_double4(r_jk, dx, dy, dz);
-    double theta, cos_theta, di[3], dj[3], dk[3];
-    calc_theta(gij, gjk, theta, cos_theta);
-    calc_dcos(gij, gjk, di, dj, dk);
-    const double sin_theta2 = sin(theta / 2.0);
-    double sin_xhz4 = sqr(sin_theta2);
-    sin_xhz4 *= sin_xhz4;
-    const double cos_xhz1 = (1.0 - cos_theta);
-    const double exp_hb2 = exp(-hp.p_hb2 * BOij);
-    const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
-    const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
-    e_hb += ehb;
-    const double CEhb1 = hp.p_hb1 * hp.p_hb2 * exp_hb2 * exp_hb3 * sin_xhz4;
-    const double CEhb2 = -hp.p_hb1 / 2.0 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
-    const double CEhb3 = -hp.p_hb3 * (-hp.r0_hb / sqr(r_jk) + 1.0 / hp.r0_hb) * ehb;
-    const double c3 = CEhb3 / r_jk;
-    atomicAdd(&v.b_Cdbo[pi], CEhb1);
-    // reference accumulates -force in fCdDelta; f is the true force here
-    fadd3(v.f, i, -CEhb2, di[0], di[1], di[2]);
-    atomicAdd(&v.f[3 * j], -(CEhb2 * dj[0] - c3 * dx));
-    atomicAdd(&v.f[3 * j + 1], -(CEhb2 * dj[1] - c3 * dy));
-    atomicAdd(&v.f[3 * j + 2], -(CEhb2 * dj[2] - c3 * dz));
-    atomicAdd(&v.f[3 * k], -(CEhb2 * dk[0] + c3 * dx));
-    atomicAdd(&v.f[3 * k + 1], -(CEhb2 * dk[1] + c3 * dy));
-    atomicAdd(&v.f[3 * k + 2], -(CEhb2 * dk[2] + c3 * dz));
+    double fjx = 0, fjy = 0, fjz = 0, fkx = 0, fky = 0, fkz = 0;
+    for (int pi = start; pi < start + cnt; pi++) {
+      const double BOij = v.b_bo[pi].x;
+      if (!(BOij >= kHbThreshold)) continue;
+      const int i = v.b_nbr[pi];
+      const int ti = v.type[i];
+      if (ti < 0 || P.atom[ti].p_hbond != 2) continue;
+      if (v.tag[i] == tag_k) continue;
+      const HbPar hp = P.hb[(ti * nt + tj) * nt + tk];
+      if (hp.r0_hb <= 0.0) continue;
+      const double4 gij = v.b_geo[pi];
+      double theta, cos_theta, di[3], dj[3], dk[3];
+      calc_theta(gij, gjk, theta, cos_theta);
+      calc_dcos(gij, gjk, di, dj, dk);
+      const double sin_theta2 = sin(theta / 2.0);
+      double sin_xhz4 = sqr(sin_theta2);
+      sin_xhz4 *= sin_xhz4;
+      const double cos_xhz1 = (1.0 - cos_theta);
+      const double exp_hb2 = exp(-hp.p_hb2 * BOij);
+      const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
+      const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
+      e_hb += ehb;
+      const double CEhb1 = hp.p_hb1 * hp.p_hb2 * exp_hb2 * exp_hb3 * sin_xhz4;
+      const double CEhb2 = -hp.p_hb1 / 2.0 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
+      const double CEhb3 = -hp.p_hb3 * (-hp.r0_hb / sqr(r_jk) + 1.0 / hp.r0_hb) * ehb;
+      const double c3 = CEhb3 / r_jk;
+      atomicAdd(&v.b_Cdbo[pi], CEhb1);
+      // reference accumulates -force in fCdDelta; f is the true force here
+      fadd3(v.f, i, -CEhb2, di[0], di[1], di[2]);
+      fjx -= CEhb2 * dj[0] - c3 * dx; fjy -= CEhb2 * dj[1] - c3 * dy; fjz -= CEhb2 * dj[2] - c3 * dz;
+      fkx -= CEhb2 * dk[0] + c3 * dx; fky -= CEhb2 * dk[1] + c3 * dy; fkz -= CEhb2 * dk[2] + c3 * dz;
+    }
+    if (fjx != 0.0 || fjy != 0.0 || fjz != 0.0) {
+      atomicAdd(&v.f[3 * j], fjx); atomicAdd(&v.f[3 * j + 1], fjy); atomicAdd(&v.f[3 * j + 2], fjz);
+      atomicAdd(&v.f[3 * k], fkx); atomicAdd(&v.f[3 * k + 1], fky); atomicAdd(&v.f[3 * k + 2], fkz);
+    }
   }
   const int slots[1] = {E_HB};
   double vals[1] = {e_hb};
@@ -791,10 +744,10 @@ k_dbond(DevView v, BondedWork W) {
 void launch_bonded_part1(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   if (v.n == 0) return;
   BondedWork W = s.bonded_work();
-  RXB_CUDA(cudaMemsetAsync(W.n_ang, 0, 4 * sizeof(int), st));
+  RXB_CUDA(cudaMemsetAsync(W.n_ang, 0, 2 * sizeof(int), st));   // n_ang, n_tor (n_hb belongs to K-farH)
   RXB_CUDA(cudaMemsetAsync(W.sum56, 0, (size_t)v.N * sizeof(double2), st));
   const int t = s.tick(StepTimers::MULTI, st);
-  k_multi<<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  k_multi<<<(v.n + kWarps * 32 - 1) / (kWarps * 32), kWarps * 32, 0, st>>>(v, P);
   s.tock(t, st);
   s.kernel_launches += 1;
 }

@@ -139,6 +139,7 @@ k_bond_list(DevView v, DevParams P) {
       if (fits) {
         const int p = start + rank;
         v.b_nbr[p] = mine;
+        v.b_owner[p] = i;
         v.b_sym[p] = -1;
         v.b_geo[p] = make_double4(o[0], o[1], o[2], o[3]);
         v.b_bo[p] = make_double4(o[4], o[5], o[6], o[7]);
@@ -159,20 +160,17 @@ k_bond_list(DevView v, DevParams P) {
   }
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+// One thread per DIRECTED bond (dense: ~7.5 bonds/atom would leave 3/4 of a warp-per-atom idle in this 8-exp kernel)
+__global__ void __launch_bounds__(256)
 k_bond_orders(DevView v, DevParams P) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * kWarps + wib;
-  if (i >= v.N) return;
-  const int ti = v.type[i];
-  double tot = 0.0;
-  if (ti >= 0) {
-    const double p_boc1 = P.gp[0], p_boc2 = P.gp[1];
-    const double val_i = P.atom[ti].valency;
-    const double2 Dpi = v.Deltap[i];
-    const int start = v.b_start[i], cnt = v.b_cnt[i];
-    for (int e = lane; e < cnt; e += 32) {
-      const int p = start + e;
+  const int nb = min(*v.b_cursor, v.cap_bonds);
+  const double p_boc1 = P.gp[0], p_boc2 = P.gp[1];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nb; p += gridDim.x * blockDim.x) {
+    {
+      const int i = v.b_owner[p];
+      const int ti = v.type[i];
+      const double val_i = P.atom[ti].valency;
+      const double2 Dpi = v.Deltap[i];
       const int j = v.b_nbr[p];
       const int tj = v.type[j];
       if (tj < 0) continue;
@@ -182,9 +180,9 @@ k_bond_orders(DevView v, DevParams P) {
         int lo = 0, hi = cj - 1, found = -1;
         while (lo <= hi) {
           const int mid = (lo + hi) >> 1;
-          const int nb = v.b_nbr[sj + mid];
-          if (nb == i) { found = sj + mid; break; }
-          if (nb < i) lo = mid + 1; else hi = mid - 1;
+          const int cand = v.b_nbr[sj + mid];
+          if (cand == i) { found = sj + mid; break; }
+          if (cand < i) lo = mid + 1; else hi = mid - 1;
         }
         v.b_sym[p] = found;
       }
@@ -249,12 +247,22 @@ k_bond_orders(DevView v, DevParams P) {
       v.b_c1[p] = make_double4(C1dbo, C2dbo, C3dbo, C1dbopi);
       v.b_c2[p] = make_double4(C2dbopi, C3dbopi, C4dbopi, C1dbopi2);
       v.b_c3[p] = make_double4(C2dbopi2, C3dbopi2, C4dbopi2, 0.0);
-      tot += bo.x;
     }
   }
-  tot = warp_sum(tot);
-  if (lane == 0) {
-    // section 3, reaxc_bond_orders_sw64.c:449-482
+}
+
+// BO section 3 (reaxc_bond_orders_sw64.c:449-482): one thread per atom, row sum in slot order (deterministic)
+__global__ void __launch_bounds__(256)
+k_bond_order_atoms(DevView v, DevParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.N) return;
+  const int ti = v.type[i];
+  double tot = 0.0;
+  {
+    const int start = v.b_start[i], cnt = v.b_cnt[i];
+    for (int e = 0; e < cnt; e++) tot += v.b_bo[start + e].x;
+  }
+  {
     v.total_bo[i] = tot;
     if (ti >= 0) {
       const AtomPar& a = P.atom[ti];
@@ -291,8 +299,9 @@ void launch_bond_list(System& s, DevView& v, const DevParams& P, cudaStream_t st
 
 void launch_bond_orders(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   if (v.N == 0) return;
-  k_bond_orders<<<(v.N + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(v, P);
-  s.kernel_launches++;
+  k_bond_orders<<<148 * 8, 256, 0, st>>>(v, P);
+  k_bond_order_atoms<<<(v.N + 255) / 256, 256, 0, st>>>(v, P);
+  s.kernel_launches += 2;
 }
 
 }  // namespace rxb

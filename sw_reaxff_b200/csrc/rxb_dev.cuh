@@ -48,7 +48,7 @@ struct DevView {
   int* far_num; int* far_idx; double* H_val;
   // bonds
   int* b_start; int* b_cnt; int* b_cursor; int* overflow;
-  int* b_nbr; int* b_sym;
+  int* b_nbr; int* b_sym; int* b_owner;
   double4* b_geo;      // d, dx, dy, dz          (dvec = x_nbr - x_i)
   double4* b_bo;       // BO, BO_s, BO_pi, BO_pi2
   double4* b_der;      // cBOp, cPi, cPi2, unused :  dBOp = cBOp*dvec, dln_BOp_pi = cPi*dvec, dln_BOp_pi2 = cPi2*dvec

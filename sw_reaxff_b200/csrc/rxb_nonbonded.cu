@@ -29,7 +29,8 @@ __device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
 struct QeqConst { double Tap[8]; double swb2; double far2; };
 
 __global__ void __launch_bounds__(kWarps * 32)
-k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
+k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const AtomPar* __restrict__ atom, double hbond_cut,
+        BondedWork W) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int i = wg; i < v.n; i += nwg) {
@@ -54,22 +55,45 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld) {
     const int num = (int)(w - beg);
     if (lane == 0) v.far_num[i] = num;
     __syncwarp();
-    // pass 2: H values on the compacted row (every lane does the taper + cube root; xq[j] is an L1/L2 hit)
-    for (int k = lane; k < num; k += 32) {
-      const int j = v.far_idx[beg + k];
-      const double4 pj = v.xq[j];
-      const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
-      const int tj = v.type[j];
-      double val = 0.0;
-      if (r2 <= qc.swb2 && ti >= 0 && tj >= 0) {
-        const double r = sqrt(r2);
-        double T = qc.Tap[7] * r + qc.Tap[6];
-        T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
-        T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-        // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
-        val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
+    // pass 2: H values on the compacted row (every lane does the taper + cube root; xq[j] is an L1/L2 hit).
+    // Rows of hydrogen atoms also emit their hydrogen-bond partner candidates here (acceptor-type j within hbond_cut:
+    // Init_Forces_noQEq_HB_Full_C, reaxc_forces_sw64.c:787-863) while x_j, type_j and r are in registers.
+    const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
+    for (int k0 = 0; k0 < num; k0 += 32) {
+      const int k = k0 + lane;
+      bool cand = false;
+      int j = -1;
+      if (k < num) {
+        j = v.far_idx[beg + k];
+        const double4 pj = v.xq[j];
+        const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
+        const int tj = v.type[j];
+        double val = 0.0;
+        if (ti >= 0 && tj >= 0) {
+          const double r = sqrt(r2);
+          if (r2 <= qc.swb2) {
+            double T = qc.Tap[7] * r + qc.Tap[6];
+            T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
+            T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
+            // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
+            val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
+          }
+          cand = is_H && atom[tj].p_hbond == 2 && r <= hbond_cut;
+        }
+        v.H_val[beg + k] = val;
       }
-      v.H_val[beg + k] = val;
+      if (is_H) {
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(W.n_hb, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (cand) {
+            const int o = base + __popc(m & ((1u << lane) - 1));
+            if (o < W.cap_hb) W.hb[o] = make_int4(i, j, 0, 0);
+          }
+        }
+      }
     }
   }
 }
@@ -202,7 +226,9 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   qc.swb2 = swb * swb;
   const double far = swb > P.ctl.nonb_cut ? swb : P.ctl.nonb_cut;
   qc.far2 = far * far;
-  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld);
+  BondedWork W = s.bonded_work();
+  RXB_CUDA(cudaMemsetAsync(W.n_hb, 0, sizeof(int), st));
+  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, P.ctl.hbond_cut, W);
   s.kernel_launches++;
 }
 

@@ -297,6 +297,7 @@ void System::qeq_pre_force() {
   }
   const int t_QEQ_H = tick(StepTimers::QEQ_H);
   launch_far_and_H(*this, v, dp_, Tap, shld_d.p, qeq_swb, st_);
+  memcpy(last_tap_, Tap, sizeof(last_tap_)); last_swb_ = qeq_swb;
   tock(t_QEQ_H);
   after_far_hook();
 

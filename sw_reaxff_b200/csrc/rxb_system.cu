@@ -313,7 +313,7 @@ void System::ensure_atom_capacity() {
 void System::ensure_bond_capacity(int cap) {
   if (cap <= cap_bonds) return;
   const size_t c = cap;
-  b_nbr.resize(c); b_sym.resize(c); b_geo.resize(c); b_bo.resize(c); b_der.resize(c); b_c1.resize(c); b_c2.resize(c);
+  b_nbr.resize(c); b_sym.resize(c); b_owner.resize(c); b_geo.resize(c); b_bo.resize(c); b_der.resize(c); b_c1.resize(c); b_c2.resize(c);
   b_c3.resize(c); b_Cdbo.resize(c); b_Cdbopi.resize(c); b_Cdbopi2.resize(c);
   cap_bonds = cap;
 }
@@ -408,7 +408,7 @@ DevView System::view() {
   v.hc_off = nullptr; v.hc_idx = nullptr;
   v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
   v.b_start = b_start.p; v.b_cnt = b_cnt.p; v.b_cursor = b_cursor.p; v.overflow = overflow.p;
-  v.b_nbr = b_nbr.p; v.b_sym = b_sym.p; v.b_geo = b_geo.p; v.b_bo = b_bo.p; v.b_der = b_der.p;
+  v.b_nbr = b_nbr.p; v.b_sym = b_sym.p; v.b_owner = b_owner.p; v.b_geo = b_geo.p; v.b_bo = b_bo.p; v.b_der = b_der.p;
   v.b_c1 = b_c1.p; v.b_c2 = b_c2.p; v.b_c3 = b_c3.p;
   v.b_Cdbo = b_Cdbo.p; v.b_Cdbopi = b_Cdbopi.p; v.b_Cdbopi2 = b_Cdbopi2.p;
   v.total_bop = total_bop.p; v.Deltap = Deltap.p; v.dDeltap_self = dDeltap_self.p; v.total_bo = total_bo.p;
@@ -466,6 +466,7 @@ void System::compute(bool eflag, bool vflag) {
     DevView v = view();
     double Tap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     launch_far_and_H(*this, v, dp_, Tap, shld_d.p, 0.0, st_);
+    memcpy(last_tap_, Tap, sizeof(last_tap_)); last_swb_ = 0.0;
   }
   qeq_ran_this_step_ = false;
   for (int attempt = 0; attempt < 4; attempt++) {
@@ -490,7 +491,11 @@ void System::compute(bool eflag, bool vflag) {
     if (overflow_flag & 2) ensure_bond_capacity((int)std::min<long long>((long long)h[0] + h[0] / 4 + 1024, 2000000000LL));
     if (wk[0] > cap_ang) { cap_ang = wk[0] + wk[0] / 4 + 1024; it_ang.resize(cap_ang); }
     if (wk[1] > cap_tor) { cap_tor = wk[1] + wk[1] / 4 + 1024; it_tor.resize(cap_tor); }
-    if (wk[2] > cap_hb) { cap_hb = wk[2] + wk[2] / 4 + 1024; it_hb.resize(cap_hb); }
+    if (wk[2] > cap_hb) {   // the candidate list is produced by K-farH: grow it and rebuild the far list of this step
+      cap_hb = wk[2] + wk[2] / 4 + 1024; it_hb.resize(cap_hb);
+      DevView v2 = view();
+      launch_far_and_H(*this, v2, dp_, last_tap_, shld_d.p, last_swb_, st_);
+    }
     overflow_flag &= ~2;
   }
   if (overflow_flag & ~2)

@@ -175,7 +175,7 @@ class System {
   Csr vl, bc;
   DBuf<int> far_num, far_idx;
   DBuf<double> H_val;
-  DBuf<int> b_start, b_cnt, b_cursor, overflow, b_nbr, b_sym;
+  DBuf<int> b_start, b_cnt, b_cursor, overflow, b_nbr, b_sym, b_owner;
   DBuf<double4> b_geo, b_bo, b_der, b_c1, b_c2, b_c3;
   DBuf<double> b_Cdbo, b_Cdbopi, b_Cdbopi2;
   DBuf<double> total_bop, dDeltap_self, total_bo, Delta_boc, Delta, Delta_val, vlpex, nlp, Delta_lp, dDelta_lp, Delta_lp_temp;
@@ -219,6 +219,7 @@ class System {
   DevParams dp_{};
   CellList cells_a_, cells_b_;
   bool qeq_ran_this_step_ = false;
+  double last_tap_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_swb_ = 0.0;   // what K-farH was last launched with (replays)
   cudaEvent_t run_ev_[2] = {nullptr, nullptr};
   double* h_pin_ = nullptr;  // pinned staging
   size_t h_pin_cap_ = 0;
