@@ -40,6 +40,8 @@ k_bond_list(DevView v, DevParams P) {
     const long long beg = v.bc_off[i], end = v.bc_off[i + 1];
     int* queue = s_queue[wib];
     int qn = 0;
+    const float4 fi = v.xf[i];
+    const float bc2_hi = (float)(bond_cut * bond_cut) + v.bond_band;
     // Phase 1 (cheap, all lanes): distance filter, survivors are queued.  Phase 2 (6 transcendentals per pair) runs on
     // FULL warps drained from the queue: only ~30 % of the (bond_cut + skin) candidates are inside bond_cut, so doing the
     // math in place would leave two thirds of the lanes idle.
@@ -50,10 +52,11 @@ k_bond_list(DevView v, DevParams P) {
         int j = -1;
         if (k < end) {
           j = v.bc_idx[k];
-          const double4 pj = v.xq[j];
-          const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-          const double r2 = dx * dx + dy * dy + dz * dz;
-          near = r2 <= nonb_cut2 && sqrt(r2) <= bond_cut && v.type[j] >= 0;
+          // fp32 shadow (position + type in 16 bytes): a conservative superset goes to the queue, the exact fp64 test
+          // d <= bond_cut is applied when the candidate is drained
+          const float4 fj = v.xf[j];
+          const float ex = fj.x - fi.x, ey = fj.y - fi.y, ez = fj.z - fi.z;
+          near = (ex * ex + ey * ey + ez * ez) <= bc2_hi && __float_as_int(fj.w) >= 0;
         }
         const unsigned m = __ballot_sync(0xffffffffu, near);
         if (near) queue[qn + __popc(m & ((1u << lane) - 1))] = j;
@@ -73,6 +76,7 @@ k_bond_list(DevView v, DevParams P) {
         const double r2 = dx * dx + dy * dy + dz * dz;
         d = sqrt(r2);
         const int tj = v.type[j];
+        const bool inside = r2 <= nonb_cut2 && d <= bond_cut;   // exact test (the queue holds an fp32 superset)
         const AtomPar& aj = P.atom[tj];
         const PairPar& tw = P.pair[ti * P.nt + tj];
         // (d/r)^p as exp(p (log d - log r)): one log shared by the three terms instead of three pow() calls
@@ -83,7 +87,7 @@ k_bond_list(DevView v, DevParams P) {
         if (ai.r_pi > 0.0 && aj.r_pi > 0.0) { C34 = tw.p_bo3 * exp(tw.p_bo4 * (ld - tw.log_r_p)); BO_pi = exp(C34); }
         if (ai.r_pi_pi > 0.0 && aj.r_pi_pi > 0.0) { C56 = tw.p_bo5 * exp(tw.p_bo6 * (ld - tw.log_r_pp)); BO_pi2 = exp(C56); }
         BO = BO_s + BO_pi + BO_pi2;
-        if (BO >= bo_cut) {
+        if (inside && BO >= bo_cut) {
           hit = true;
           const double rr2 = d * d;
           const double Cln_s = tw.p_bo2 * C12 / rr2, Cln_pi = tw.p_bo4 * C34 / rr2, Cln_pi2 = tw.p_bo6 * C56 / rr2;

@@ -34,6 +34,8 @@ struct DevView {
   int cap_bonds;       // capacity of the bond arrays (directed bonds)
   // atoms
   double4* xq;         // N
+  const float4* xf;    // N: fp32 shadow (x,y,z relative to the list origin, element type bits in .w), refreshed every step
+  float far_band, bond_band;   // fp32 rounding bands (in r^2) around nonb_cut^2 / bond_cut^2, see CellList::fp32_band
   const int* type;     // N element index (-1 = NULL)
   const int* tag;      // N
   double* f;           // N*3, true forces

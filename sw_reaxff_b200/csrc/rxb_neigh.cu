@@ -10,6 +10,8 @@
 // HBM-bound by design (28(N+G) read + 4 nnz written); the stencil re-reads hit L1/L2.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "rxb_system.h"
 
 namespace rxb {
@@ -65,12 +67,16 @@ __global__ void k_bin_ids(const double4* __restrict__ xq, int N, Grid g, int* __
   atomicAdd(&bin_count[id], 1);
 }
 
-__global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __restrict__ sorted_idx, int N,
-                                double4* __restrict__ spos) {
+// sorted copies: exact fp64 positions (spos) and an fp32 shadow relative to the grid origin with the atom index in .w
+// (sposf).  The stencil sweep reads the 16-byte shadow; only pairs whose fp32 distance falls inside the rounding band
+// around the cut-off touch the 32-byte exact record, so the list is still decided by the oracle's fp64 arithmetic.
+__global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __restrict__ sorted_idx, int N, Grid g,
+                                double4* __restrict__ spos, float4* __restrict__ sposf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N) return;
   int i = sorted_idx[k];
   double4 p = xq[i];
+  sposf[k] = make_float4((float)(p.x - g.lo[0]), (float)(p.y - g.lo[1]), (float)(p.z - g.lo[2]), __int_as_float(i));
   p.w = __longlong_as_double((long long)i);
   spos[k] = p;
 }
@@ -78,13 +84,16 @@ __global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __res
 // One warp per row atom.  FILL=false: count hits -> cnt[i];  FILL=true: write columns at off[i].
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const int* __restrict__ bin_start, Grid g,
-        int nrows, double cut, int reach, int* __restrict__ cnt, const long long* __restrict__ off, int* __restrict__ idx) {
+k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const float4* __restrict__ sposf,
+        const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band, int reach, int* __restrict__ cnt,
+        const long long* __restrict__ off, int* __restrict__ idx) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nrows) return;
   const double4 pi = xq[i];
   const double c2 = cut * cut;
+  const float fx = (float)(pi.x - g.lo[0]), fy = (float)(pi.y - g.lo[1]), fz = (float)(pi.z - g.lo[2]);
+  const float c2lo = (float)c2 - band, c2hi = (float)c2 + band;
   const int bx = bin_coord(pi.x, g.lo[0], g.inv[0], g.nb[0]);
   const int by = bin_coord(pi.y, g.lo[1], g.inv[1], g.nb[1]);
   const int bz = bin_coord(pi.z, g.lo[2], g.inv[2], g.nb[2]);
@@ -116,12 +125,19 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
         bool hit = false;
         int j = -1;
         if (k < kend) {
-          const double4 pj = spos[k];
-          j = (int)__double_as_longlong(pj.w);
-          // explicit rn ops: no FMA contraction, so the r^2 <= cut^2 test is the oracle's arithmetic bit for bit
-          const double ddx = __dsub_rn(pi.x, pj.x), ddy = __dsub_rn(pi.y, pj.y), ddz = __dsub_rn(pi.z, pj.z);
-          const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-          hit = (j != i) && (r2 <= c2);
+          const float4 qj = sposf[k];
+          j = __float_as_int(qj.w);
+          const float ex = qj.x - fx, ey = qj.y - fy, ez = qj.z - fz;
+          const float r2f = ex * ex + ey * ey + ez * ez;
+          if (r2f < c2lo) hit = (j != i);
+          else if (r2f <= c2hi) {
+            // inside the fp32 rounding band: decide with the exact record.  Explicit rn ops: no FMA contraction, so the
+            // r^2 <= cut^2 test is the oracle's arithmetic bit for bit
+            const double4 pj = spos[k];
+            const double ddx = __dsub_rn(pi.x, pj.x), ddy = __dsub_rn(pi.y, pj.y), ddz = __dsub_rn(pi.z, pj.z);
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+            hit = (j != i) && (r2 <= c2);
+          }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (FILL) {
@@ -143,6 +159,14 @@ __global__ void k_cnt_to_ll(const int* __restrict__ cnt, int n, long long* __res
 }
 
 }  // namespace
+
+// Half-width (in r^2) of the band in which an fp32 distance cannot decide r^2 <= cut^2: each shadow coordinate carries
+// a rounding error <= extent * 2^-24, a difference twice that, r^2 therefore ~ 2 r sqrt(3) * that, plus the fp32 arithmetic
+// of the sum (relative 2^-22).  A factor 2 of slack is added on top.
+float CellList::fp32_band(double cut) const {
+  const double coord = (extent + 8.0) * 5.97e-8;
+  return (float)(2.0 * (2.0 * cut * 1.7320508 * 2.0 * coord + cut * cut * 2.4e-7));
+}
 
 void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaStream_t st) {
   reach = reach_;
@@ -172,7 +196,7 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   memcpy(grid_blob, &g, sizeof(g));
   static_assert(sizeof(Grid) <= sizeof(grid_blob), "grid blob too small");
   num_bins = (int)nbins;
-  key.resize(N); val.resize(N); key2.resize(N); sorted_idx.resize(N); spos.resize(N);
+  key.resize(N); val.resize(N); key2.resize(N); sorted_idx.resize(N); spos.resize(N); sposf.resize(N);
   bin_count.resize(num_bins + 1); bin_start.resize(num_bins + 1);
   RXB_CUDA(cudaMemsetAsync(bin_count.p, 0, (num_bins + 1) * sizeof(int), st));
   k_bin_ids<<<(N + 255) / 256, 256, 0, st>>>(xq, N, g, key.p, val.p, bin_count.p);
@@ -185,19 +209,22 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   temp.resize(need + 16);
   cub::DeviceRadixSort::SortPairs(temp.p, need, key.p, key2.p, val.p, sorted_idx.p, N, 0, bits, st);
   cub::DeviceScan::ExclusiveSum(temp.p, need, bin_count.p, bin_start.p, num_bins + 1, st);
-  k_gather_sorted<<<(N + 255) / 256, 256, 0, st>>>(xq, sorted_idx.p, N, spos.p);
+  k_gather_sorted<<<(N + 255) / 256, 256, 0, st>>>(xq, sorted_idx.p, N, g, spos.p, sposf.p);
+  extent = 0.0;
+  for (int t = 0; t < 3; t++) { origin[t] = g.lo[t]; extent = std::max(extent, got[3 + t] - got[t]); }
   RXB_CUDA(cudaGetLastError());
 }
 
 void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st) {
   Grid g;
   memcpy(&g, grid_blob, sizeof(g));
+  const float band = fp32_band(cut);
   cnt.resize(nrows + 1);
   out.off.resize(nrows + 1);
   const int warps_per_block = 8;
   const int blocks = (nrows + warps_per_block - 1) / warps_per_block;
   if (nrows > 0)
-    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, bin_start.p, g, nrows, cut, reach, cnt.p, nullptr, nullptr);
+    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, cnt.p, nullptr, nullptr);
   cntll.resize(nrows + 1);
   k_cnt_to_ll<<<(nrows + 256) / 256, 256, 0, st>>>(cnt.p, nrows, cntll.p);
   size_t need = 0;
@@ -211,7 +238,7 @@ void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStr
   out.nrows = nrows;
   out.idx.resize((size_t)(total > 0 ? total : 1));
   if (nrows > 0)
-    k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, bin_start.p, g, nrows, cut, reach, nullptr, out.off.p, out.idx.p);
+    k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, nullptr, out.off.p, out.idx.p);
   RXB_CUDA(cudaGetLastError());
 }
 

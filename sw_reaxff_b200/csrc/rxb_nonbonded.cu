@@ -39,14 +39,24 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
     const long long beg = v.vl_off[i], end = v.vl_off[i + 1];
     // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work)
     long long w = beg;
+    const float4 fi = v.xf[i];
+    const float lo2 = (float)qc.far2 - v.far_band, hi2 = (float)qc.far2 + v.far_band;
     for (long long k0 = beg; k0 < end; k0 += 32) {
       const long long k = k0 + lane;
       bool hit = false;
       int j = 0;
       if (k < end) {
         j = v.vl_idx[k];
-        const double4 pj = v.xq[j];
-        hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
+        // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
+        // r^2 <= cut^2 decision is still the fp64 one
+        const float4 fj = v.xf[j];
+        const float ex = fj.x - fi.x, ey = fj.y - fi.y, ez = fj.z - fi.z;
+        const float r2f = ex * ex + ey * ey + ez * ez;
+        if (r2f < lo2) hit = true;
+        else if (r2f <= hi2) {
+          const double4 pj = v.xq[j];
+          hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
+        }
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) v.far_idx[w + __popc(m & ((1u << lane) - 1))] = j;

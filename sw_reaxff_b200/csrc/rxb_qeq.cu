@@ -280,7 +280,9 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
 void System::qeq_pre_force() {
   if (n == 0) return;
   if (q_s_hist.n != (size_t)5 * n && !dist_) qeq_reset_history();
+  last_swb_ = qeq_swb;
   DevView v = view();
+  update_shadow(st_);
   // taper and shielding of the fix (init_taper :458-484, init_shielding :440-454), host side, tiny
   double Tap[8];
   {

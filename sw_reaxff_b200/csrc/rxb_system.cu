@@ -41,6 +41,14 @@ __global__ void k_get_xyz(int N, const double4* __restrict__ xq, double* __restr
   x[3 * i] = p.x; x[3 * i + 1] = p.y; x[3 * i + 2] = p.z;
 }
 
+__global__ void k_shadow(int N, const double4* __restrict__ xq, const int* __restrict__ type, double ox, double oy, double oz,
+                         float4* __restrict__ xf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double4 p = xq[i];
+  xf[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(type[i]));
+}
+
 // virial_fdotr over all atoms, pair_reaxc_sunway.cpp:674-702
 __global__ void k_fdotr(int N, const double4* __restrict__ xq, const double* __restrict__ f, double* __restrict__ virial) {
   double v[6] = {0, 0, 0, 0, 0, 0};
@@ -399,9 +407,23 @@ BondedWork System::bonded_work() {
   return W;
 }
 
+void System::update_shadow(cudaStream_t st) {
+  if (N == 0) return;
+  xf.resize((size_t)N);
+  k_shadow<<<nblk(N), 256, 0, st>>>(N, xq.p, type.p, cells_a_.origin[0], cells_a_.origin[1], cells_a_.origin[2], xf.p);
+  kernel_launches++;
+}
+
 DevView System::view() {
   DevView v{};
   v.n = n; v.N = N; v.cap_bonds = cap_bonds;
+  xf.resize((size_t)(N > 0 ? N : 1));
+  v.xf = xf.p;
+  {
+    const double far = std::max(ff.ctl.nonb_cut, last_swb_ > 0 ? last_swb_ : qeq_swb);
+    v.far_band = cells_a_.fp32_band(far);
+    v.bond_band = cells_a_.fp32_band(ff.ctl.bond_cut);
+  }
   v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
   v.vl_off = vl.off.p; v.vl_idx = vl.idx.p;
   v.bc_off = bc.off.p; v.bc_idx = bc.idx.p;
@@ -461,6 +483,7 @@ void System::step_forces(bool eflag, bool vflag) {
 
 void System::compute(bool eflag, bool vflag) {
   RXB_CUDA(cudaSetDevice(device_));
+  update_shadow(st_);
   if (!qeq_ran_this_step_) {
     // pair style without fix qeq/reax this step (checkqeq no): the far list is still needed
     DevView v = view();
@@ -566,6 +589,7 @@ void System::after_far_hook() {
 
 void System::md_force_overlapped(bool ev) {
   DevView v = view();
+  update_shadow(st_);
   RXB_CUDA(cudaMemsetAsync(f.p, 0, (size_t)3 * N * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(en_d.p, 0, E_NUM * sizeof(double), st_));

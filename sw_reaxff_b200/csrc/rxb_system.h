@@ -67,9 +67,12 @@ struct CellList {
   DBuf<int> key, key2, val, sorted_idx, bin_count, bin_start, cnt;
   DBuf<long long> cntll;
   DBuf<double4> spos;
+  DBuf<float4> sposf;
   DBuf<char> temp;
   char grid_blob[96];
   int num_bins = 0, reach = 2;
+  double origin[3] = {0, 0, 0}, extent = 0.0;   // bounding box of the last bin() (origin of the fp32 shadows)
+  float fp32_band(double cut) const;
   void bin(const double4* xq, int N, double bin_size, int reach, cudaStream_t st);
   void build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st);
 };
@@ -170,6 +173,8 @@ class System {
 
   // raw buffers (public: the C ABI copies them out for tests / fix reax/c/bonds)
   DBuf<double4> xq;
+  DBuf<float4> xf;
+  void update_shadow(cudaStream_t st);   // xq -> xf
   DBuf<int> type, tag, ltype_d, ghost_owner;
   DBuf<double> f, CdDelta;
   Csr vl, bc;
