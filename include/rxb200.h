@@ -92,6 +92,8 @@ int rxb_md_thermo(rxb_handle* h, double* pvector, double* pe, double* ke);
  *      rxb_md_setup, passing to rxb_md_setup only the atoms it currently holds (any initial assignment). */
 int rxb_dist_unique_id(char* out128);
 int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px, int py, int pz);
+/* halo transport: 1 (default) peer-to-peer boundary exchange with ncclSend/ncclRecv, 0 whole-slab all-gather */
+int rxb_dist_set_p2p(rxb_handle* h, int on);
 
 /* ---- introspection (tests, fix reax/c/bonds, fix reax/c/species) ---- */
 /* counts[0..7] = nlocal, nall, verlet nnz, bond-candidate nnz, directed bonds, far nnz(sum), kernel launches, qeq iterations */

@@ -14,7 +14,7 @@ SYMBOLS = [
     "rxb_neigh_build", "rxb_qeq_pre_force", "rxb_qeq_set_history", "rxb_qeq_get_history", "rxb_get_charges",
     "rxb_pair_compute", "rxb_md_setup", "rxb_md_run", "rxb_md_get", "rxb_md_thermo", "rxb_get_counts",
     "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
-    "rxb_dist_unique_id", "rxb_dist_init", "rxb_md_get_tags",
+    "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -195,6 +195,9 @@ class Rxb:
     def dist_init(self, rank, world, uid, grid):
         assert len(uid) == 128
         self._chk(self.lib.rxb_dist_init(self.h, int(rank), int(world), C.c_char_p(uid), int(grid[0]), int(grid[1]), int(grid[2])))
+
+    def dist_set_p2p(self, on):
+        self._chk(self.lib.rxb_dist_set_p2p(self.h, int(on)))
 
     # ---- introspection ----
     def counts(self):

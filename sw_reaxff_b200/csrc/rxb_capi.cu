@@ -303,6 +303,8 @@ int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px,
   return guard([&] { h->sys->dist_init(rank, world, id128, px, py, pz); });
 }
 
+int rxb_dist_set_p2p(rxb_handle* h, int on) { return guard([&] { h->sys->dist_set_p2p(on != 0); }); }
+
 int rxb_profiler_range(int start) {
   return guard([&] { if (start) RXB_CUDA(cudaProfilerStart()); else RXB_CUDA(cudaProfilerStop()); });
 }

@@ -41,12 +41,20 @@ struct Dist {
   std::vector<int> counts;       // local atoms per rank at the last exchange
   DBuf<int> counts_d;
   DBuf<double> rec_send, rec_all;        // [chunk][kRec], [world*chunk][kRec]
+  DBuf<double> rec2_send, rec2_all;      // compact post-migration records [..][5]
   DBuf<double4> xq_all;                  // [world*chunk]
   DBuf<double2> d_all;                   // [world*chunk]
   DBuf<double> f_all, f_recv;            // [world*chunk][3], [chunk][3]
   DBuf<int> gsrc;                        // per ghost: source slot in the gathered arrays
   DBuf<long long> flag, off;             // selection scans
   DBuf<char> temp;
+  // peer-to-peer boundary exchange plan (rebuilt at every exchange): ghosts are ordered by source slot, hence grouped by
+  // source rank; rank r sends me exactly the local atoms I listed, in my ghost order, so receives land in place
+  bool p2p = true;
+  std::vector<int> need_from, send_to, goff, soff;   // per peer: ghosts I need / atoms I send, and their offsets
+  int nsend = 0;
+  DBuf<int> greq, sendlist, cnt_d, cnt_all_d;
+  DBuf<double> sendbuf, recvbuf;
 };
 
 namespace {
@@ -90,6 +98,16 @@ __global__ void k_wrap_pack(int n, BoxD b, double4* __restrict__ xq, const doubl
   r[17] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
 }
 
+__global__ void k_pack_compact(int n, const double4* __restrict__ xq, const int* __restrict__ tag, const int* __restrict__ ltype,
+                               double* __restrict__ rec) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  double* r = rec + (size_t)5 * i;
+  r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
+  r[4] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
+}
+
 __device__ __forceinline__ bool slot_valid(int s, int chunk, const int* counts) { return (s % chunk) < counts[s / chunk]; }
 
 __global__ void k_flag_locals(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
@@ -123,7 +141,8 @@ __global__ void k_fill_locals(int nslots, const long long* __restrict__ flag, co
   type[i] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
 }
 
-template <bool FILL>
+// STRIDE doubles per record, charge at QOFF, packed (tag,type) at TOFF
+template <bool FILL, int STRIDE, int QOFF, int TOFF>
 __global__ void k_ghosts_dist(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
                               Brick k, int n, const int* __restrict__ map, int maplen, long long* __restrict__ count,
                               const long long* __restrict__ off, double4* __restrict__ xq, int* __restrict__ tag,
@@ -131,7 +150,7 @@ __global__ void k_ghosts_dist(int nslots, int chunk, const int* __restrict__ cou
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nslots) return;
   if (s == nslots || !slot_valid(s, chunk, counts)) { if (!FILL) count[s] = 0; return; }
-  const double* r = rec + (size_t)kRec * s;
+  const double* r = rec + (size_t)STRIDE * s;
   double l[3];
   x2lamda(b, r[0], r[1], r[2], l);
   const bool mine = in_brick(k, l);
@@ -150,8 +169,8 @@ __global__ void k_ghosts_dist(int nslots, int chunk, const int* __restrict__ cou
           double d[3];
           shift_vec(b, sx, sy, sz, d);
           const long long g = n + w;
-          xq[g] = make_double4(r[0] + d[0], r[1] + d[1], r[2] + d[2], r[6]);
-          const long long tt = __double_as_longlong(r[17]);
+          xq[g] = make_double4(r[0] + d[0], r[1] + d[1], r[2] + d[2], r[QOFF]);
+          const long long tt = __double_as_longlong(r[TOFF]);
           const int lt = (int)(tt & 0xffffffffLL);
           tag[g] = (int)(tt >> 32); ltype[g] = lt;
           type[g] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
@@ -297,13 +316,22 @@ void System::dist_exchange() {
   type.resize_keep(std::max((size_t)n, (size_t)chunk));
   k_fill_locals<<<nblk(nslots), 256, 0, st_>>>(nslots, D.flag.p, D.off.p, D.rec_all.p, map_d.p, (int)ff.map.size(), xq.p, v_d.p,
                                               q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, type.p);
-  // 5. ghosts: count, scan, fill
-  k_ghosts_dist<false><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, n, map_d.p,
-                                                         (int)ff.map.size(), D.flag.p, nullptr, nullptr, nullptr, nullptr,
-                                                         nullptr, nullptr, nullptr);
+  // 5. post-migration layout: all-gather the new counts and a compact (x,y,z,q,tag|type) record of the NEW local atoms;
+  //    ghosts are selected from that, so their source slots refer to the layout every later halo exchange uses and come
+  //    out sorted by slot, i.e. grouped by source rank (what the peer-to-peer plan relies on)
+  my = n;
+  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
+  D.rec2_send.resize((size_t)chunk * 5); D.rec2_all.resize((size_t)nslots * 5);
+  k_pack_compact<<<nblk(n), 256, 0, st_>>>(n, xq.p, tag.p, ltype_d.p, D.rec2_send.p);
+  RXB_NCCL(ncclAllGather(D.rec2_send.p, D.rec2_all.p, (size_t)chunk * 5, ncclDouble, D.comm, st_));
+  k_ghosts_dist<false, 5, 3, 4><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec2_all.p, b, k, n, map_d.p,
+                                                                  (int)ff.map.size(), D.flag.p, nullptr, nullptr, nullptr,
+                                                                  nullptr, nullptr, nullptr, nullptr);
   cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
   long long nghost = 0;
   RXB_CUDA(cudaMemcpyAsync(&nghost, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
   N = n + (int)nghost;
   ensure_atom_capacity();
@@ -311,16 +339,10 @@ void System::dist_exchange() {
   D.gsrc.resize(std::max<size_t>(nghost, 1));
   ghost_shift.resize(std::max<size_t>(3 * nghost, 3));
   ghost_owner.resize(std::max<size_t>(nghost, 1));
-  k_ghosts_dist<true><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, n, map_d.p,
-                                                        (int)ff.map.size(), nullptr, D.off.p, xq.p, tag.p, ltype_d.p, type.p,
-                                                        D.gsrc.p, ghost_shift.p);
-  // the gathered arrays keep the PRE-migration slot layout until the next exchange; after migration the local slab is
-  // [rank*chunk, rank*chunk + n): refresh the counts so that forward/reverse use the new layout
-  my = n;
-  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
-  // ghost sources refer to pre-migration slots: re-resolve them against the post-migration layout by tag
-  dist_resolve_sources();
+  k_ghosts_dist<true, 5, 3, 4><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec2_all.p, b, k, n, map_d.p,
+                                                                 (int)ff.map.size(), nullptr, D.off.p, xq.p, tag.p, ltype_d.p,
+                                                                 type.p, D.gsrc.p, ghost_shift.p);
+  dist_build_plan();
   D.xq_all.resize((size_t)nslots); D.d_all.resize((size_t)nslots);
   D.f_all.resize((size_t)3 * nslots); D.f_recv.resize((size_t)3 * chunk);
   kernel_launches += 6;
@@ -328,50 +350,106 @@ void System::dist_exchange() {
 }
 
 namespace {
-// After migration the atom that sat in pre-migration slot s lives in some rank's new local array.  Every rank publishes
-// (all-gathers) the pre-migration slot of each of its new local atoms; inverting that table maps old slot -> new slot.
-__global__ void k_publish_old_slot(int nslots, const long long* __restrict__ flag, const long long* __restrict__ off,
-                                   int* __restrict__ old_of_new) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < nslots && flag[s]) old_of_new[off[s]] = s;
-}
-__global__ void k_invert(int world, int chunk, const int* __restrict__ counts, const int* __restrict__ old_of_new_all,
-                         int* __restrict__ new_of_old) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= world * chunk) return;
-  if ((s % chunk) < counts[s / chunk]) new_of_old[old_of_new_all[s]] = s;
-}
-__global__ void k_remap_src(int nghost, const int* __restrict__ new_of_old, int* __restrict__ gsrc) {
+__global__ void k_plan_count(int nghost, int chunk, const int* __restrict__ gsrc, int* __restrict__ greq, int* __restrict__ cnt) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < nghost) gsrc[g] = new_of_old[gsrc[g]];
+  if (g >= nghost) return;
+  const int s = gsrc[g];
+  greq[g] = s % chunk;
+  atomicAdd(&cnt[s / chunk], 1);
+}
+template <int W>
+__global__ void k_pack(int m, const int* __restrict__ list, const double* __restrict__ src, double* __restrict__ dst) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const int i = list[e];
+#pragma unroll
+  for (int t = 0; t < W; t++) dst[(size_t)W * e + t] = src[(size_t)W * i + t];
+}
+template <int W>
+__global__ void k_self_ghosts(int n, int g0, int g1, const int* __restrict__ greq, double* __restrict__ vec) {
+  int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= g1) return;
+  const int i = greq[g];
+#pragma unroll
+  for (int t = 0; t < W; t++) vec[(size_t)W * (n + g) + t] = vec[(size_t)W * i + t];
+}
+__global__ void k_shift_ghosts(int n, int nghost, BoxD b, const int* __restrict__ shift, double4* __restrict__ xq) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int sx = shift[3 * g], sy = shift[3 * g + 1], sz = shift[3 * g + 2];
+  if (!(sx | sy | sz)) return;
+  double d[3];
+  shift_vec(b, sx, sy, sz, d);
+  double4 p = xq[n + g];
+  p.x += d[0]; p.y += d[1]; p.z += d[2];
+  xq[n + g] = p;
+}
+__global__ void k_unpack_add_f(int m, const int* __restrict__ list, const double* __restrict__ recv, double* __restrict__ f) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const int i = list[e];
+  const double fx = recv[3 * (size_t)e], fy = recv[3 * (size_t)e + 1], fz = recv[3 * (size_t)e + 2];
+  if (fx != 0.0) atomicAdd(&f[3 * i], fx);
+  if (fy != 0.0) atomicAdd(&f[3 * i + 1], fy);
+  if (fz != 0.0) atomicAdd(&f[3 * i + 2], fz);
+}
+__global__ void k_self_reverse_f(int n, int g0, int g1, const int* __restrict__ greq, double* __restrict__ f) {
+  int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= g1) return;
+  const int i = greq[g];
+  for (int t = 0; t < 3; t++) { const double v = f[3 * (size_t)(n + g) + t]; if (v != 0.0) atomicAdd(&f[3 * i + t], v); }
 }
 }  // namespace
 
-void System::dist_resolve_sources() {
+// Build the peer-to-peer plan: who needs which of my atoms (one small all-gather of counts + one grouped send/recv of
+// index lists per reneighbouring).
+void System::dist_build_plan() {
   Dist& D = *dist_;
-  const int chunk = D.chunk, nslots = chunk * D.world;
-  old_of_new_.resize(chunk); old_of_new_all_.resize(nslots); new_of_old_.resize(nslots);
-  // flag/off were overwritten by the ghost scan: recompute the local flags/scan (cheap) to publish old slots
-  BoxD b;
-  memcpy(b.h, box.h, sizeof(b.h));
-  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
-  Brick k;
-  for (int t = 0; t < 3; t++) { k.lo[t] = D.lo[t]; k.hi[t] = D.hi[t]; k.cg[t] = 0; k.m[t] = 0; }
-  // NOTE: counts_d now holds post-migration counts; validity of PRE-migration slots must use the old counts
-  DBuf<int>& oldc = old_counts_d_;
-  oldc.resize(D.world);
-  RXB_CUDA(cudaMemcpyAsync(oldc.p, D.counts.data(), D.world * sizeof(int), cudaMemcpyHostToDevice, st_));
-  k_flag_locals<<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, oldc.p, D.rec_all.p, b, k, D.flag.p);
-  size_t need = D.temp.n;
-  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
-  k_publish_old_slot<<<nblk(nslots), 256, 0, st_>>>(nslots, D.flag.p, D.off.p, old_of_new_.p);
-  RXB_NCCL(ncclAllGather(old_of_new_.p, old_of_new_all_.p, chunk, ncclInt, D.comm, st_));
-  k_invert<<<nblk(nslots), 256, 0, st_>>>(D.world, chunk, D.counts_d.p, old_of_new_all_.p, new_of_old_.p);
-  const int nghost = N - n;
-  if (nghost > 0) k_remap_src<<<nblk(nghost), 256, 0, st_>>>(nghost, new_of_old_.p, D.gsrc.p);
-  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  const int W = D.world, nghost = N - n;
+  D.cnt_d.resize(W); D.cnt_all_d.resize((size_t)W * W);
+  D.greq.resize(std::max(nghost, 1));
+  RXB_CUDA(cudaMemsetAsync(D.cnt_d.p, 0, W * sizeof(int), st_));
+  if (nghost > 0) k_plan_count<<<nblk(nghost), 256, 0, st_>>>(nghost, D.chunk, D.gsrc.p, D.greq.p, D.cnt_d.p);
+  RXB_NCCL(ncclAllGather(D.cnt_d.p, D.cnt_all_d.p, W, ncclInt, D.comm, st_));
+  std::vector<int> all((size_t)W * W);
+  RXB_CUDA(cudaMemcpyAsync(all.data(), D.cnt_all_d.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
-  kernel_launches += 5;
+  D.need_from.assign(W, 0); D.send_to.assign(W, 0); D.goff.assign(W + 1, 0); D.soff.assign(W + 1, 0);
+  for (int r = 0; r < W; r++) {
+    D.need_from[r] = all[(size_t)D.rank * W + r];      // row a = what rank a needs from each rank
+    D.send_to[r] = (r == D.rank) ? 0 : all[(size_t)r * W + D.rank];
+    D.goff[r + 1] = D.goff[r] + D.need_from[r];
+    D.soff[r + 1] = D.soff[r] + D.send_to[r];
+  }
+  D.nsend = D.soff[W];
+  D.sendlist.resize(std::max(D.nsend, 1));
+  D.sendbuf.resize((size_t)4 * std::max(D.nsend, 1));
+  D.recvbuf.resize((size_t)3 * std::max(D.nsend, 1));
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    if (D.need_from[r] > 0) RXB_NCCL(ncclSend(D.greq.p + D.goff[r], D.need_from[r], ncclInt, r, D.comm, st_));
+    if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.sendlist.p + D.soff[r], D.send_to[r], ncclInt, r, D.comm, st_));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  kernel_launches++;
+}
+
+// forward: my atoms -> peers' ghost slots (width doubles per atom), then my own periodic images
+template <int WD>
+static void p2p_forward(System& s, Dist& D, double* vec, int n, cudaStream_t st) {
+  const int W = D.world;
+  if (D.nsend > 0) k_pack<WD><<<nblk(D.nsend), 256, 0, st>>>(D.nsend, D.sendlist.p, vec, D.sendbuf.p);
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.sendbuf.p + (size_t)WD * D.soff[r], (size_t)WD * D.send_to[r], ncclDouble, r, D.comm, st));
+    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(vec + (size_t)WD * (n + D.goff[r]), (size_t)WD * D.need_from[r], ncclDouble, r, D.comm, st));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
+  if (g1 > g0) k_self_ghosts<WD><<<nblk(g1 - g0), 256, 0, st>>>(n, g0, g1, D.greq.p, vec);
+  s.kernel_launches += 2;
 }
 
 void System::dist_forward_xq() {
@@ -379,14 +457,21 @@ void System::dist_forward_xq() {
   BoxD b;
   memcpy(b.h, box.h, sizeof(b.h));
   memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
-  RXB_NCCL(ncclAllGather(xq.p, D.xq_all.p, (size_t)D.chunk * 4, ncclDouble, D.comm, st_));
   const int nghost = N - n;
+  if (D.p2p) {
+    p2p_forward<4>(*this, D, reinterpret_cast<double*>(xq.p), n, st_);
+    if (nghost > 0) k_shift_ghosts<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, ghost_shift.p, xq.p);
+    kernel_launches++;
+    return;
+  }
+  RXB_NCCL(ncclAllGather(xq.p, D.xq_all.p, (size_t)D.chunk * 4, ncclDouble, D.comm, st_));
   if (nghost > 0) k_ghost_x_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, D.gsrc.p, ghost_shift.p, D.xq_all.p, xq.p);
   kernel_launches++;
 }
 
 void System::dist_forward2(double2* vec) {
   Dist& D = *dist_;
+  if (D.p2p) { p2p_forward<2>(*this, D, reinterpret_cast<double*>(vec), n, st_); return; }
   RXB_NCCL(ncclAllGather(vec, D.d_all.p, (size_t)D.chunk * 2, ncclDouble, D.comm, st_));
   const int nghost = N - n;
   if (nghost > 0) k_ghost_d_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, D.gsrc.p, D.d_all.p, vec);
@@ -395,6 +480,21 @@ void System::dist_forward2(double2* vec) {
 
 void System::dist_reverse_f() {
   Dist& D = *dist_;
+  if (D.p2p) {
+    const int W = D.world;
+    RXB_NCCL(ncclGroupStart());
+    for (int r = 0; r < W; r++) {
+      if (r == D.rank) continue;
+      if (D.need_from[r] > 0) RXB_NCCL(ncclSend(f.p + (size_t)3 * (n + D.goff[r]), (size_t)3 * D.need_from[r], ncclDouble, r, D.comm, st_));
+      if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.recvbuf.p + (size_t)3 * D.soff[r], (size_t)3 * D.send_to[r], ncclDouble, r, D.comm, st_));
+    }
+    RXB_NCCL(ncclGroupEnd());
+    if (D.nsend > 0) k_unpack_add_f<<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, D.recvbuf.p, f.p);
+    const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
+    if (g1 > g0) k_self_reverse_f<<<nblk(g1 - g0), 256, 0, st_>>>(n, g0, g1, D.greq.p, f.p);
+    kernel_launches += 2;
+    return;
+  }
   const size_t nslots = (size_t)D.chunk * D.world;
   RXB_CUDA(cudaMemsetAsync(D.f_all.p, 0, 3 * nslots * sizeof(double), st_));
   k_scatter_f<<<nblk(N), 256, 0, st_>>>(n, N - n, D.rank * D.chunk, D.gsrc.p, f.p, D.f_all.p);
@@ -402,5 +502,7 @@ void System::dist_reverse_f() {
   RXB_CUDA(cudaMemcpyAsync(f.p, D.f_recv.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st_));
   kernel_launches++;
 }
+
+void System::dist_set_p2p(bool on) { if (dist_) dist_->p2p = on; }
 
 }  // namespace rxb

@@ -153,7 +153,8 @@ class System {
   int dist_world() const;
   void dist_allreduce(double* dev_ptr, int count);
   void dist_exchange();          // exchange + borders at reneighbouring
-  void dist_resolve_sources();
+  void dist_build_plan();        // peer-to-peer send lists for the boundary exchange
+  void dist_set_p2p(bool on);    // false: whole-slab all-gather halos (debug / comparison)
   void dist_forward_xq();        // ghosts <- owners (x + image shift, q)
   void dist_forward2(double2* vec);
   void dist_reverse_f();

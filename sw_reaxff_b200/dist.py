@@ -116,7 +116,7 @@ def sum_over_ranks(dist, values, device):
     return t.cpu().tolist()
 
 
-def setup_distributed(H, rank, world, local_rank, cells, tol=1e-6, thermo=5, T=300.0):
+def setup_distributed(H, rank, world, local_rank, cells, tol=1e-6, thermo=5, T=300.0, p2p=1):
     import torch
     import torch.distributed as dist
     from .api import Rxb
@@ -129,6 +129,7 @@ def setup_distributed(H, rank, world, local_rank, cells, tol=1e-6, thermo=5, T=3
     r.fix_qeq(0.0, 10.0, tol)
     uid = broadcast_unique_id(dist, Rxb, rank, dev)
     r.dist_init(rank, world, uid, grid)
+    r.dist_set_p2p(p2p)
     r.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=5, thermo=thermo)
     return r, grid, len(x)
 

@@ -24,11 +24,13 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
     cells = tuple(int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (4, 2, 2)
     steps = int(sys.argv[4]) if len(sys.argv) >= 5 else 12
+    T = float(sys.argv[5]) if len(sys.argv) >= 6 else 300.0
+    p2p = int(sys.argv[6]) if len(sys.argv) >= 7 else 1
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     dev = torch.device("cuda", lr)
     tol = 1e-10
-    r, grid, n0 = D.setup_distributed(H, rank, world, lr, cells, tol=tol, thermo=1)
+    r, grid, n0 = D.setup_distributed(H, rank, world, lr, cells, tol=tol, thermo=1, T=T, p2p=p2p)
     th0 = r.md_thermo()
     r.md_run(steps)
     th = r.md_thermo()
@@ -52,7 +54,7 @@ def main():
         natoms = 384 * cells[0] * cells[1] * cells[2]
         assert len(allr) == natoms and np.array_equal(allr[:, 0].astype(np.int64), np.arange(1, natoms + 1)), "atoms lost or duplicated"
         box, x, t, tag = H.tatb_cell(*cells)
-        v = D.velocities_by_tag(H, t, tag, 300.0, 12345)
+        v = D.velocities_by_tag(H, t, tag, T, 12345)
         s = Rxb(lr)
         s.pair_settings(H.CONTROL); s.pair_coeff(H.FFIELD, H.ELEMENTS); s.fix_qeq(0.0, 10.0, tol)
         s.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=5, thermo=1)
@@ -72,7 +74,8 @@ def main():
         ee0 = abs(th0["pe"] - s0["pe"]) / abs(s0["pe"])
         ee = abs(th["pe"] - sth["pe"]) / abs(sth["pe"])
         ek = abs(th["ke"] - sth["ke"]) / abs(sth["ke"])
-        print(f"dist check {world} ranks grid {grid} cells {cells} steps {steps}: |dx| {ex:.2e}  f rel {ef:.2e}  |dq| {eq:.2e}  "
+        moved = int((np.abs(lam) > 0.5).any(axis=1).sum())
+        print(f"dist check {world} ranks grid {grid} cells {cells} steps {steps} T {T} p2p {p2p} n_local(rank0) {n} vs {n0} at start, wrapped {moved}: |dx| {ex:.2e}  f rel {ef:.2e}  |dq| {eq:.2e}  "
               f"pe0 rel {ee0:.2e}  pe rel {ee:.2e}  ke rel {ek:.2e}  pe {th['pe']:.6f} vs {sth['pe']:.6f}")
         ok = ex < 1e-8 and ef < 1e-6 and eq < 1e-7 and ee0 < 1e-9 and ee < 1e-8 and ek < 1e-6
         print("DIST CHECK", "PASSED" if ok else "FAILED")
