@@ -12,8 +12,10 @@ from sw_reaxff_b200 import Rxb
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-box, x, t, tag = tatb_cell(nx, nx, nx)
-v = maxwell_velocities(t, 300.0, 12345)
+scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+T = float(sys.argv[4]) if len(sys.argv) > 4 else 300.0
+box, x, t, tag = tatb_cell(nx, nx, nx, scale=scale)
+v = maxwell_velocities(t, T, 12345)
 r = Rxb(0)
 r.pair_settings(CONTROL)
 r.pair_coeff(FFIELD, ELEMENTS)

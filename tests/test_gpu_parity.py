@@ -220,6 +220,27 @@ def test_md_trajectory_vs_oracle():
     assert abs(th["ke"] - ro["ke"]) < 1e-7 * abs(ro["ke"])
 
 
+def test_md_trajectory_hot_compressed_vs_oracle():
+    """BASELINE.json's hot-compressed case (0.90 linear scale, 3000 K) at a size the oracle runs in seconds: more
+    bonds/angles/torsions per atom, atoms crossing the box faces, QEq far from its initial guess."""
+    box, x, t, tag = H.tatb_cell(1, 1, 1, scale=0.90)
+    v = H.maxwell_velocities(t, 3000.0, 4242)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-10)
+    o.md_run(12)
+    ro = o.md_get()
+    r = make_rxb(1e-10)
+    r.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=5, thermo=1)
+    r.md_run(12)
+    rg = r.md_get()
+    th = r.md_thermo()
+    assert np.abs(rg["x"] - ro["x"]).max() < 1e-8
+    assert rel(rg["f"], ro["f"]) < 1e-6
+    assert np.abs(rg["q"] - ro["q"]).max() < 1e-7
+    assert abs(th["pe"] - ro["pe"]) < 1e-8 * abs(ro["pe"])
+    assert abs(th["ke"] - ro["ke"]) < 1e-7 * abs(ro["ke"])
+
+
 def test_md_energy_conservation_gpu():
     box, x, t, tag = H.tatb_cell(2, 2, 2)
     v = H.maxwell_velocities(t, 300.0, 777)
