@@ -107,6 +107,32 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
 int rxb_get_workspace(rxb_handle* h, double* w16);
 /* far list == H pattern: num[nlocal], and for row i the entries off_verlet[i] .. +num[i] of idx/val */
 int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val);
+/* ---- fix reax/c/bonds (replaces FixReaxCBondsSunway::FindBond + PassBuffer, fix_reaxc_bonds_sunway.cpp:187-260) ----
+ * Builds, on the device, the connection table of the local atoms from the bond list of the last force evaluation:
+ * neighbours with BO > bo_cut (bo_cut < 0: the control file's bond_graph_cutoff, as the reference uses), in bond-row
+ * order.  rxb_bond_table returns the sizes; rxb_bond_table_get copies tag/type[nlocal], CSR offsets off[nlocal+1],
+ * neighbour IDs and bond orders [nentries], and abo (= total bond order), nlp, q [nlocal].  Any pointer may be NULL. */
+int rxb_bond_table(rxb_handle* h, double bo_cut, int* nlocal, int* nentries, int* max_per_atom);
+int rxb_bond_table_get(rxb_handle* h, int* tag, int* type, int* off, int* nbr_tag, double* bo, double* abo, double* nlp,
+                       double* q);
+
+/* ---- fix reax/c/species nevery nrepeat nfreq (fix_reaxc_species_sunway.cpp:60-117, 425-717; tmpid/tmpbo of
+ * pair_reaxc_sunway.cpp:1170-1198; the averaging of the hidden fix ave/atom SPECBOND) ----
+ * bocut = (ntypes+1)^2 matrix of BOCut[itype][jtype] (default 0.30 everywhere), natoms = global atom count (IDs must
+ * be 1..natoms).  *reneighbor_reset = 1 when the reneighbouring period of the resident run had to be changed so that
+ * lists stay frozen inside an averaging window (the reference prints "Resetting reneighboring criteria ...").
+ * rxb_md_run calls the post_integrate hook itself and appends one record per output step to a log;
+ * a host-driven loop calls rxb_species_step(ntimestep) after initial_integrate instead.
+ * Result: nmole molecules ordered by their smallest atom ID; composition[m*ntypes + t] = atoms of type t+1 in molecule m
+ * (summed over ranks when decomposed); cluster_of_local = molecule number 1..nmole per local atom. */
+int rxb_species_config(rxb_handle* h, int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms,
+                       long ntimestep_now /* <0: the resident run's own counter */, int* reneighbor_reset);
+int rxb_species_step(rxb_handle* h, long ntimestep, int* found);
+int rxb_species_result(rxb_handle* h, int* nmole, int* composition, long cap);
+int rxb_species_cluster(rxb_handle* h, int* cluster_of_local);
+int rxb_species_log_size(rxb_handle* h);
+int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* composition, long cap);
+
 /* CUDA-event timers on the launch stream (no sync inside a step).  out26 = 13 accumulated ms then 13 call counts for:
  * neigh, qeq far+H, qeq CG (whole solve), bond list, BO, bonded (all), nonbonded, dBond, SpMV (per launch), hbond items,
  * angle+torsion items, multi-body, enumeration.  enable: 1 reset+start, 0 stop, -1 read only. */

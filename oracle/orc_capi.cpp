@@ -4,13 +4,16 @@
 #include <cstring>
 #include <string>
 
+#include "orc_analysis.h"
 #include "orc_md.h"
 
 using namespace orc;
 
 struct OrcHandle {
   MD md;
+  SpeciesFix species;
   std::string err;
+  std::string text;
 };
 
 static void put_err(char* err, int errlen, const std::string& s) {
@@ -253,6 +256,41 @@ void orc_md_get_ghosts(void* hh, double* xall, int* typeall, int* tagall, int* o
   for (int i = 0; i < s.N; i++) { typeall[i] = i < md.nlocal ? md.ltype[i] : md.ltype[md.ghost_owner[i - md.nlocal]]; tagall[i] = s.tag[i]; }
   for (int g = 0; g < s.N - md.nlocal; g++) owner[g] = md.ghost_owner[g];
 }
+// ---- fix reax/c/bonds, fix reax/c/species on the MD state ----
+static long copy_text(const std::string& t, char* out, long cap) {
+  if (out && cap > 0) { long m = std::min((long)t.size(), cap - 1); memcpy(out, t.data(), m); out[m] = 0; }
+  return (long)t.size();
+}
+long orc_md_bonds_text(void* hh, long ntimestep, char* out, long cap) {
+  OrcHandle* h = (OrcHandle*)hh;
+  h->text = bonds_text(h->md, ntimestep);
+  return copy_text(h->text, out, cap);
+}
+void orc_md_species_init(void* hh, int nevery, int nrepeat, int nfreq, const double* bocut) {
+  OrcHandle* h = (OrcHandle*)hh;
+  int nt = (int)h->md.mass.size() - 1;
+  h->species.init(h->md, nevery, nrepeat, nfreq, std::vector<double>(bocut, bocut + (size_t)(nt + 1) * (nt + 1)));
+}
+// post_integrate hook of timestep `step`; returns 1 when molecules were found (an output step), -1 on error
+int orc_md_species_step(void* hh, long step) {
+  OrcHandle* h = (OrcHandle*)hh;
+  bool f = h->species.post_integrate(h->md, step);
+  if (!h->species.error.empty()) return -1;
+  return f ? 1 : 0;
+}
+int orc_md_species_nmole(void* hh) { return ((OrcHandle*)hh)->species.Nmole; }
+void orc_md_species_get(void* hh, int* composition, int* cluster_of_local) {
+  OrcHandle* h = (OrcHandle*)hh;
+  const SpeciesFix& S = h->species;
+  if (composition) memcpy(composition, S.composition.data(), S.composition.size() * sizeof(int));
+  if (cluster_of_local) for (int i = 0; i < h->md.nlocal; i++) cluster_of_local[i] = (int)S.clusterID[i];
+}
+long orc_md_species_text(void* hh, long ntimestep, char* out, long cap) {
+  OrcHandle* h = (OrcHandle*)hh;
+  h->text = h->species.formulas_text(ntimestep);
+  return copy_text(h->text, out, cap);
+}
+
 int orc_md_matvecs(void* hh, int which) { QEq& q = ((OrcHandle*)hh)->md.qeq; return which ? q.matvecs_t : q.matvecs_s; }
 
 }  // extern "C"

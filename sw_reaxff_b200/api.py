@@ -15,6 +15,8 @@ SYMBOLS = [
     "rxb_pair_compute", "rxb_md_setup", "rxb_md_run", "rxb_md_get", "rxb_md_thermo", "rxb_get_counts",
     "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
+    "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
+    "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -182,6 +184,56 @@ class Rxb:
         pv = np.zeros(14); pe = C.c_double(); ke = C.c_double()
         self._chk(self.lib.rxb_md_thermo(self.h, _p(pv), C.byref(pe), C.byref(ke)))
         return dict(pvector=pv, pe=pe.value, ke=ke.value)
+
+    # ---- fix reax/c/bonds / fix reax/c/species ----
+    def bond_table(self, bo_cut=-1.0):
+        """Connection table of the local atoms (fix_reaxc_bonds_sunway.cpp:187-260); bo_cut < 0 = control bg_cut."""
+        n = C.c_int(); m = C.c_int(); mx = C.c_int()
+        self._chk(self.lib.rxb_bond_table(self.h, C.c_double(bo_cut), C.byref(n), C.byref(m), C.byref(mx)))
+        n, m = n.value, m.value
+        t = dict(tag=np.zeros(n, dtype=np.int32), type=np.zeros(n, dtype=np.int32), off=np.zeros(n + 1, dtype=np.int32),
+                 nbr=np.zeros(m, dtype=np.int32), bo=np.zeros(m), abo=np.zeros(n), nlp=np.zeros(n), q=np.zeros(n),
+                 max_nb=mx.value)
+        self._chk(self.lib.rxb_bond_table_get(self.h, _p(t["tag"]), _p(t["type"]), _p(t["off"]), _p(t["nbr"]), _p(t["bo"]),
+                                              _p(t["abo"]), _p(t["nlp"]), _p(t["q"])))
+        return t
+
+    def species_config(self, nevery, nrepeat, nfreq, natoms, ntypes=4, bocut=None, ntimestep=-1):
+        """fix reax/c/species nevery nrepeat nfreq; bocut = (ntypes+1)^2 BOCut matrix (default 0.30).  Returns True
+        when the reneighbouring period of the resident run was reset (the reference's warning)."""
+        bc = np.full((ntypes + 1, ntypes + 1), 0.30) if bocut is None else np.ascontiguousarray(bocut, dtype=np.float64)
+        self._sp_ntypes = ntypes
+        r = C.c_int()
+        self._chk(self.lib.rxb_species_config(self.h, int(nevery), int(nrepeat), int(nfreq), int(ntypes), _p(bc),
+                                              C.c_long(int(natoms)), C.c_long(int(ntimestep)), C.byref(r)))
+        return bool(r.value)
+
+    def species_step(self, ntimestep):
+        f = C.c_int()
+        self._chk(self.lib.rxb_species_step(self.h, C.c_long(int(ntimestep)), C.byref(f)))
+        return bool(f.value)
+
+    def species_result(self):
+        nm = C.c_int()
+        self._chk(self.lib.rxb_species_result(self.h, C.byref(nm), None, C.c_long(0)))
+        comp = np.zeros((nm.value, self._sp_ntypes), dtype=np.int32)
+        self._chk(self.lib.rxb_species_result(self.h, C.byref(nm), _p(comp), C.c_long(comp.size)))
+        return dict(nmole=nm.value, composition=comp)
+
+    def species_cluster(self):
+        c = np.zeros(int(self.counts()[0]), dtype=np.int32)
+        self._chk(self.lib.rxb_species_cluster(self.h, _p(c)))
+        return c
+
+    def species_log(self):
+        out = []
+        for k in range(self.lib.rxb_species_log_size(self.h)):
+            st = C.c_long(); nm = C.c_int()
+            self._chk(self.lib.rxb_species_log_get(self.h, k, C.byref(st), C.byref(nm), None, C.c_long(0)))
+            comp = np.zeros((nm.value, self._sp_ntypes), dtype=np.int32)
+            self._chk(self.lib.rxb_species_log_get(self.h, k, C.byref(st), C.byref(nm), _p(comp), C.c_long(comp.size)))
+            out.append(dict(step=st.value, nmole=nm.value, composition=comp))
+        return out
 
     # ---- multi-GPU ----
     @staticmethod

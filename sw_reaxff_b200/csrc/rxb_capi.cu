@@ -305,6 +305,50 @@ int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px,
 
 int rxb_dist_set_p2p(rxb_handle* h, int on) { return guard([&] { h->sys->dist_set_p2p(on != 0); }); }
 
+int rxb_bond_table(rxb_handle* h, double bo_cut, int* nlocal, int* nentries, int* max_per_atom) {
+  return guard([&] {
+    auto t = h->sys->bond_table_build(bo_cut);
+    if (nlocal) *nlocal = t.n;
+    if (nentries) *nentries = t.entries;
+    if (max_per_atom) *max_per_atom = t.max_nb;
+  });
+}
+int rxb_bond_table_get(rxb_handle* h, int* tag, int* type, int* off, int* nbr_tag, double* bo, double* abo, double* nlp,
+                       double* q) {
+  return guard([&] { h->sys->bond_table_get(tag, type, off, nbr_tag, bo, abo, nlp, q); });
+}
+
+int rxb_species_config(rxb_handle* h, int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms,
+                       long ntimestep_now, int* reneighbor_reset) {
+  return guard([&] {
+    int r = h->sys->species_config(nevery, nrepeat, nfreq, ntypes, bocut, natoms, ntimestep_now);
+    if (reneighbor_reset) *reneighbor_reset = r;
+  });
+}
+int rxb_species_step(rxb_handle* h, long ntimestep, int* found) {
+  return guard([&] { bool f = h->sys->species_step(ntimestep); if (found) *found = f ? 1 : 0; });
+}
+int rxb_species_result(rxb_handle* h, int* nmole, int* composition, long cap) {
+  return guard([&] {
+    const auto& S = h->sys->species;
+    if (nmole) *nmole = S.nmole;
+    if (composition) for (long i = 0; i < (long)S.composition.size() && i < cap; i++) composition[i] = S.composition[i];
+  });
+}
+int rxb_species_cluster(rxb_handle* h, int* cluster_of_local) {
+  return guard([&] { h->sys->species_get_cluster(cluster_of_local); });
+}
+int rxb_species_log_size(rxb_handle* h) { return (int)h->sys->species_log.size(); }
+int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* composition, long cap) {
+  return guard([&] {
+    const auto& L = h->sys->species_log;
+    if (k < 0 || k >= (int)L.size()) throw std::runtime_error("rxb_species_log_get: no such record");
+    if (step) *step = L[k].step;
+    if (nmole) *nmole = L[k].nmole;
+    if (composition) for (long i = 0; i < (long)L[k].composition.size() && i < cap; i++) composition[i] = L[k].composition[i];
+  });
+}
+
 int rxb_profiler_range(int start) {
   return guard([&] { if (start) RXB_CUDA(cudaProfilerStart()); else RXB_CUDA(cudaProfilerStop()); });
 }

@@ -258,6 +258,19 @@ void System::dist_allreduce(double* dev_ptr, int count) {
   RXB_NCCL(ncclAllReduce(dev_ptr, dev_ptr, count, ncclDouble, ncclSum, dist_->comm, st_));
 }
 
+int System::dist_rank() const { return dist_ ? dist_->rank : 0; }
+void System::dist_allreduce_int(int* dev_ptr, size_t count) {
+  if (!dist_) return;
+  RXB_NCCL(ncclAllReduce(dev_ptr, dev_ptr, count, ncclInt, ncclSum, dist_->comm, st_));
+}
+void System::dist_allgather_int(const int* send, int* recv, size_t count_per_rank) {
+  if (!dist_) {
+    if (send != recv) RXB_CUDA(cudaMemcpyAsync(recv, send, count_per_rank * sizeof(int), cudaMemcpyDeviceToDevice, st_));
+    return;
+  }
+  RXB_NCCL(ncclAllGather(send, recv, count_per_rank, ncclInt, dist_->comm, st_));
+}
+
 // exchange + borders
 void System::dist_exchange() {
   Dist& D = *dist_;

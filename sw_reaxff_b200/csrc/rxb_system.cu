@@ -650,6 +650,8 @@ void System::md_run(int nsteps) {
   for (int s = 0; s < nsteps; s++) {
     ntimestep++;
     k_nve_initial<<<nblk(n), 256, 0, st_>>>(n, dtf, dtv, ltype_d.p, mass_d.p, f.p, v_d.p, xq.p);
+    if (species.on && species_step(ntimestep))   // post_integrate: reads the bond list of the previous force evaluation
+      species_log.push_back({ntimestep, species.nmole, species.composition});
     md_ago++;
     if (md_ago % md_every == 0) {
       if (dist_) dist_exchange(); else md_make_ghosts();

@@ -152,6 +152,9 @@ class System {
   void dist_destroy();
   int dist_world() const;
   void dist_allreduce(double* dev_ptr, int count);
+  int dist_rank() const;
+  void dist_allreduce_int(int* dev_ptr, size_t count);
+  void dist_allgather_int(const int* send, int* recv, size_t count_per_rank);
   void dist_exchange();          // exchange + borders at reneighbouring
   void dist_build_plan();        // peer-to-peer send lists for the boundary exchange
   void dist_set_p2p(bool on);    // false: whole-slab all-gather halos (debug / comparison)
@@ -159,6 +162,33 @@ class System {
   void dist_forward2(double2* vec);
   void dist_reverse_f();
   size_t slab() const;           // elements every all-gathered local array must be able to hold
+
+  // ---- analysis outputs (rxb_analysis.cu): fix reax/c/bonds table, fix reax/c/species molecules ----
+  struct BondTable { int n = 0, entries = 0, max_nb = 0; };
+  BondTable bond_table_build(double bo_cut);   // bo_cut < 0: control file bond_graph_cutoff
+  void bond_table_get(int* tag_out, int* type_out, int* off_out, int* nbr_tag, double* bo, double* abo, double* nlp_out,
+                      double* q_out);
+  struct Species {
+    bool on = false;
+    int nevery = 1, nrepeat = 1, nfreq = 1, ntypes = 0;
+    long nvalid_ave = -1, nvalid_out = -1;   // next sampling step (fix ave/atom) and next output step (fix reax/c/species)
+    int irepeat = 0;
+    int nmole = 0;
+    long natoms = 0;
+    std::vector<int> composition;            // [nmole][ntypes], molecules in ascending order of their smallest atom ID
+  } species;
+  struct SpeciesRecord { long step; int nmole; std::vector<int> composition; };
+  std::vector<SpeciesRecord> species_log;      // one record per output step reached inside md_run
+  // returns 1 when the reneighbouring period had to be reset (the reference's warning, fix_reaxc_species_sunway.cpp:84-108)
+  int species_config(int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms_total, long now = -1);
+  bool species_step(long step);                // the post_integrate hook of timestep `step`; true when molecules were found
+  void species_sample();
+  void species_find();
+  void species_get_cluster(int* cluster_of_local);   // 1..nmole per local atom (vector_atom of the reference fix)
+  DBuf<int> bt_cnt, bt_off, bt_tag, sp_id, sp_edges, sp_edges_all, sp_parent, sp_flag, sp_molidx, sp_comp, sp_misc;
+  DBuf<double> bt_bo, sp_acc, sp_bocut;
+  BondTable bt_last_;
+  int sp_n_ = -1;
 
   // introspection for parity tests
   DevView view();

@@ -29,6 +29,24 @@ extern "C" long rxh_run_script(const char* script, int nvars, const char* const*
   }
 }
 
+// velocities that `velocity all create T seed` gives the atoms of a data file (tests feed them to the CPU oracle)
+extern "C" long rxh_velocities(const char* datafile, double T, long seed, double* v, long cap_atoms) {
+  try {
+    LAMMPS lmp;
+    lmp.echo_thermo = false;
+    lmp.one("units real");
+    lmp.one("atom_style charge");
+    lmp.one(std::string("read_data ") + datafile);
+    lmp.one("velocity all create " + std::to_string(T) + " " + std::to_string(seed));
+    const long n = lmp.atom->nlocal;
+    if (n > cap_atoms) return -2;
+    memcpy(v, lmp.atom->v.data(), (size_t)3 * n * sizeof(double));
+    return n;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+
 // e2e benchmark hook: executes `script` (which must NOT contain a run command), then setup + `warm` untimed steps +
 // `steps` timed steps of the Verlet loop with host buffers.  out4 = natoms, nall, seconds, last PotEng.
 extern "C" int rxh_bench_script(const char* script, int nvars, const char* const* names, const char* const* values, int device,

@@ -345,6 +345,8 @@ void LAMMPS::one(const std::string& raw) {
     need(4);
     if (w[3] == "nve" || w[3] == "nve/b200") fixes.emplace_back(new FixNVEB200(this, (int)argv.size(), argv.data()));
     else if (w[3] == "qeq/reax" || w[3] == "qeq/reax/b200") fixes.emplace_back(new FixQEqReaxB200(this, (int)argv.size(), argv.data()));
+    else if (w[3] == "reax/c/bonds" || w[3] == "reax/c/bonds/b200") fixes.emplace_back(new FixReaxCBondsB200(this, (int)argv.size(), argv.data()));
+    else if (w[3] == "reax/c/species" || w[3] == "reax/c/species/b200") fixes.emplace_back(new FixReaxCSpeciesB200(this, (int)argv.size(), argv.data()));
     else error->all(FLERR, "Unknown fix style " + w[3]);
   } else if (c == "velocity") {
     need(5);
@@ -400,6 +402,7 @@ void LAMMPS::setup() {
   std::fill(atom->f.begin(), atom->f.end(), 0.0);
   pair->compute(ev, ev);
   comm->reverse_comm(*atom);
+  for (auto& f : fixes) f->setup(ev);
   if (echo_thermo) printf("    Step           Temp             PotEng             TotEng\n");
   thermo_line(ev);
   setup_done_ = true;
@@ -415,6 +418,7 @@ void LAMMPS::iterate(long nsteps) {
     update->ntimestep++;
     const int ev = (thermo_every && update->ntimestep % thermo_every == 0) || s == nsteps - 1;
     for (auto& f : fixes) f->initial_integrate(ev);
+    for (auto& f : fixes) f->post_integrate();
     if (neighbor->decide()) {
       domain->remap(*atom);
       comm->borders(*domain, *atom, pair->cutghost_request() + neighbor->skin);
@@ -427,6 +431,7 @@ void LAMMPS::iterate(long nsteps) {
     pair->compute(ev, ev);
     comm->reverse_comm(*atom);
     for (auto& f : fixes) f->final_integrate();
+    for (auto& f : fixes) if (f->nevery > 0 && update->ntimestep % f->nevery == 0) f->end_of_step();
     if (ev) thermo_line(ev);
   }
 }

@@ -74,7 +74,11 @@ struct Fix {
   virtual ~Fix() {}
   virtual void init() {}
   virtual void setup_pre_force(int) {}
+  virtual void setup(int) {}
   virtual void initial_integrate(int) {}
+  virtual void post_integrate() {}
+  virtual void end_of_step() {}
+  int nevery = 0;                                 // end_of_step() runs when ntimestep % nevery == 0 (0: never)
   virtual void pre_force(int) {}
   virtual void final_integrate() {}
 };

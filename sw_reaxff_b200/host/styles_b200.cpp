@@ -87,6 +87,7 @@ void PairReaxCB200::init_style() {
   const int ngp = (int)d[2];
   const double* ctl = &d[3 + ngp];
   cutmax = std::max(ctl[2], std::max(ctl[4], 2 * ctl[3]));
+  bg_cut = ctl[5];
   rxb_neighbor_skin(rxb, lmp->neighbor->skin);
 }
 
@@ -123,6 +124,7 @@ void* PairReaxCB200::extract(const char* str, int& dim) {
   if (!strcmp(str, "chi")) return chi.data();
   if (!strcmp(str, "eta")) return eta.data();
   if (!strcmp(str, "gamma")) return gamma.data();
+  if (!strcmp(str, "bg_cut")) { dim = 0; return &bg_cut; }
   return nullptr;
 }
 
@@ -163,6 +165,183 @@ void FixQEqReaxB200::pre_force(int) {
   // atom->q on the host is only needed by host-side consumers (thermo/dump): refresh it on thermo steps
   if (lmp->thermo_every && lmp->update->ntimestep % lmp->thermo_every == 0)
     rxb_get_charges(reaxc->rxb, lmp->atom->q.data());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+FixReaxCBondsB200::FixReaxCBondsB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
+  Error* error = lmp->error;
+  if (narg != 5) error->all(FLERR, "Illegal fix reax/c/bonds command");
+  id = arg[0]; style = arg[2];
+  nevery = atoi(arg[3]);
+  if (nevery <= 0) error->all(FLERR, "Illegal fix reax/c/bonds command");
+  const char* suffix = strrchr(arg[4], '.');
+  if (suffix && strcmp(suffix, ".gz") == 0) error->all(FLERR, "Cannot open gzipped file");
+  fp = fopen(arg[4], "w");
+  if (!fp) error->all(FLERR, std::string("Cannot open fix reax/c/bonds file ") + arg[4]);
+  for (int i = 0; i < lmp->atom->nlocal; i++)   // tag_consecutive()
+    if (lmp->atom->tag[i] < 1 || lmp->atom->tag[i] > lmp->atom->natoms)
+      error->all(FLERR, "Atom IDs must be consecutive for fix reax/c bonds");
+}
+
+FixReaxCBondsB200::~FixReaxCBondsB200() { if (fp) fclose(fp); }
+
+void FixReaxCBondsB200::init() {
+  reaxc = dynamic_cast<PairReaxCB200*>(lmp->pair.get());
+  if (!reaxc) lmp->error->all(FLERR, "Cannot use fix reax/c/bonds without pair_style reax/c, reax/c/kk, or reax/c/omp");
+}
+
+void FixReaxCBondsB200::end_of_step() {
+  Error* error = lmp->error;
+  int n = 0, m = 0, maxnum = 0;
+  if (rxb_bond_table(reaxc->rxb, -1.0, &n, &m, &maxnum)) error->all(FLERR, rxb_last_error());
+  tag_.resize(n); type_.resize(n); off_.resize(n + 1); nbr_.resize(m > 0 ? m : 1); bo_.resize(m > 0 ? m : 1);
+  abo_.resize(n); nlp_.resize(n); q_.resize(n);
+  if (rxb_bond_table_get(reaxc->rxb, tag_.data(), type_.data(), off_.data(), nbr_.data(), bo_.data(), abo_.data(),
+                         nlp_.data(), q_.data()))
+    error->all(FLERR, rxb_last_error());
+  int dim;
+  double bg_cut = 0.3;
+  if (double* c = (double*)reaxc->extract("bg_cut", dim)) bg_cut = *c;
+  // RecvBuffer, fix_reaxc_bonds_sunway.cpp:264-330 (one rank)
+  fprintf(fp, "# Timestep %ld \n", lmp->update->ntimestep);
+  fprintf(fp, "# \n");
+  fprintf(fp, "# Number of particles %d \n", (int)lmp->atom->natoms);
+  fprintf(fp, "# \n");
+  fprintf(fp, "# Max number of bonds per atom %d with coarse bond order cutoff %5.3f \n", maxnum, bg_cut);
+  fprintf(fp, "# Particle connection table and bond orders \n");
+  fprintf(fp, "# id type nb id_1...id_nb mol bo_1...bo_nb abo nlp q \n");
+  for (int i = 0; i < n; i++) {
+    const int a = off_[i], b = off_[i + 1];
+    fprintf(fp, " %d %d %d", tag_[i], type_[i], b - a);
+    for (int k = a; k < b; k++) fprintf(fp, " %d", nbr_[k]);
+    fprintf(fp, " %d", 0);
+    for (int k = a; k < b; k++) fprintf(fp, "%14.3f", bo_[k]);
+    fprintf(fp, "%14.3f%14.3f%14.3f\n", abo_[i], nlp_[i], q_[i]);
+  }
+  fprintf(fp, "# \n");
+  fflush(fp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+FixReaxCSpeciesB200::FixReaxCSpeciesB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
+  Error* error = lmp->error;
+  if (narg < 7) error->all(FLERR, "Illegal fix reax/c/species command");
+  id = arg[0]; style = arg[2];
+  ntypes = lmp->atom->ntypes;
+  const int nev = atoi(arg[3]);
+  nrepeat = atoi(arg[4]);
+  nfreq = atoi(arg[5]);
+  if (nev <= 0 || nrepeat <= 0 || nfreq <= 0) error->all(FLERR, "Illegal fix reax/c/species command");
+  if (nfreq % nev || nrepeat * nev > nfreq) error->all(FLERR, "Illegal fix reax/c/species command");
+  nevery = 0;            // POST_INTEGRATE only; the sampling period lives in nev_
+  // neighbour lists must stay unchanged while bond orders are averaged (fix_reaxc_species_sunway.cpp:81-108)
+  Neighbor* neighbor = lmp->neighbor;
+  int rene_flag = 0;
+  if (nev * nrepeat != 1 && (nfreq % neighbor->every != 0 || neighbor->every < nev * nrepeat)) {
+    int newevery = nev * nrepeat;
+    while (nfreq % newevery != 0 && newevery <= nfreq / 2) newevery++;
+    if (nfreq % newevery != 0) newevery = nfreq;
+    neighbor->every = newevery;
+    rene_flag = 1;
+  }
+  if (nev * nrepeat != 1 && (neighbor->delay != 0 || neighbor->dist_check != 0)) {
+    neighbor->delay = 0;
+    neighbor->dist_check = 0;
+    rene_flag = 1;
+  }
+  if (rene_flag) error->warning(FLERR, "Resetting reneighboring criteria for fix reax/c/species");
+  const char* suffix = strrchr(arg[6], '.');
+  if (suffix && strcmp(suffix, ".gz") == 0) error->all(FLERR, "Cannot open gzipped file");
+  fp = fopen(arg[6], "w");
+  if (!fp) error->all(FLERR, std::string("Cannot open fix reax/c/species file ") + arg[6]);
+  const int n = ntypes + 1;
+  BOCut.assign((size_t)n * n, 0.30);
+  int iarg = 7;
+  while (iarg < narg) {
+    if (strcmp(arg[iarg], "cutoff") == 0) {
+      if (iarg + 4 > narg) error->all(FLERR, "Illegal fix reax/c/species command");
+      const int itype = atoi(arg[iarg + 1]), jtype = atoi(arg[iarg + 2]);
+      const double bo_cut = atof(arg[iarg + 3]);
+      if (itype > ntypes || jtype > ntypes) error->all(FLERR, "Illegal fix reax/c/species command");
+      if (itype <= 0 || jtype <= 0) error->all(FLERR, "Illegal fix reax/c/species command");
+      if (bo_cut > 1.0 || bo_cut < 0.0) error->all(FLERR, "Illegal fix reax/c/species command");
+      BOCut[(size_t)itype * n + jtype] = bo_cut;
+      BOCut[(size_t)jtype * n + itype] = bo_cut;
+      iarg += 4;
+    } else if (strcmp(arg[iarg], "element") == 0) {
+      if (iarg + ntypes + 1 > narg) error->all(FLERR, "Illegal fix reax/c/species command");
+      for (int i = 0; i < ntypes; i++) eletype.push_back(arg[iarg + 1 + i]);
+      iarg += ntypes + 1;
+    } else if (strcmp(arg[iarg], "position") == 0) {
+      error->all(FLERR, "fix reax/c/species: the position keyword is not supported by this build");
+    } else error->all(FLERR, "Illegal fix reax/c/species command");
+  }
+  if (eletype.empty()) { const char* d[4] = {"C", "H", "O", "N"}; for (int i = 0; i < ntypes && i < 4; i++) eletype.push_back(d[i]); }
+  nev_ = nev;
+}
+
+FixReaxCSpeciesB200::~FixReaxCSpeciesB200() { if (fp) fclose(fp); }
+
+void FixReaxCSpeciesB200::init() {
+  Error* error = lmp->error;
+  if (lmp->atom->tag_enable == 0) error->all(FLERR, "Cannot use fix reax/c/species unless atoms have IDs");
+  reaxc = dynamic_cast<PairReaxCB200*>(lmp->pair.get());
+  if (!reaxc) error->all(FLERR, "Cannot use fix reax/c/species without pair_style reax/c, reax/c/kk, or reax/c/omp");
+  reaxc->fixspecies_flag = 1;
+  int count = 0;
+  for (auto& f : lmp->fixes) if (f->style == "reax/c/species" || f->style == "reax/c/species/b200") count++;
+  if (count > 1) error->warning(FLERR, "More than one fix reax/c/species");
+  configured_ = false;   // the handle exists only after pair init_style: configure at the first hook
+}
+
+void FixReaxCSpeciesB200::post_integrate() {
+  Error* error = lmp->error;
+  if (!configured_) {
+    int reset = 0;
+    if (rxb_species_config(reaxc->rxb, nev_, nrepeat, nfreq, ntypes, BOCut.data(), lmp->atom->natoms,
+                           lmp->update->ntimestep, &reset))
+      error->all(FLERR, rxb_last_error());
+    configured_ = true;
+  }
+  int found = 0;
+  if (rxb_species_step(reaxc->rxb, lmp->update->ntimestep, &found)) error->all(FLERR, rxb_last_error());
+  if (!found) return;
+  if (rxb_species_result(reaxc->rxb, &Nmole, nullptr, 0)) error->all(FLERR, rxb_last_error());
+  std::vector<int> comp((size_t)Nmole * ntypes);
+  if (rxb_species_result(reaxc->rxb, &Nmole, comp.data(), (long)comp.size())) error->all(FLERR, rxb_last_error());
+  clusterID.resize(lmp->atom->nlocal);
+  if (rxb_species_cluster(reaxc->rxb, clusterID.data())) error->all(FLERR, rxb_last_error());
+  write_formulas(comp);
+  fflush(fp);
+}
+
+// FindSpecies + WriteFormulas, fix_reaxc_species_sunway.cpp:652-717, 745-780
+void FixReaxCSpeciesB200::write_formulas(const std::vector<int>& comp) {
+  std::vector<int> MolName, NMol;
+  Nspec = 0;
+  for (int m = 0; m < Nmole; m++) {
+    const int* Name = &comp[(size_t)m * ntypes];
+    int k = 0;
+    for (; k < Nspec; k++) if (std::equal(Name, Name + ntypes, &MolName[(size_t)k * ntypes])) break;
+    if (k < Nspec) NMol[k]++;
+    else { MolName.insert(MolName.end(), Name, Name + ntypes); NMol.push_back(1); Nspec++; }
+  }
+  fprintf(fp, "# Timestep     No_Moles     No_Specs     ");
+  for (int i = 0; i < Nspec; i++) {
+    for (int j = 0; j < ntypes; j++) {
+      const int itemp = MolName[(size_t)ntypes * i + j];
+      if (itemp != 0) {
+        fprintf(fp, "%s", eletype[j].c_str());
+        if (itemp != 1) fprintf(fp, "%d", itemp);
+      }
+    }
+    fprintf(fp, "\t");
+  }
+  fprintf(fp, "\n");
+  fprintf(fp, "%ld", lmp->update->ntimestep);
+  fprintf(fp, "%11d%11d\t", Nmole, Nspec);
+  for (int i = 0; i < Nspec; i++) fprintf(fp, " %d\t", NMol[i]);
+  fprintf(fp, "\n");
 }
 
 // ---------------------------------------------------------------------------------------------------------------

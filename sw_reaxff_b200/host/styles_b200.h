@@ -25,7 +25,7 @@ class PairReaxCB200 : public Pair {
   int qeqflag = 1, lgflag = 0, enobondsflag = 1;
   double safezone = 1.2, saferzone = 1.4;
   int mincap = 50, maxfar = 1024;
-  double cutmax = 0.0;
+  double cutmax = 0.0, bg_cut = 0.3;
   std::vector<double> chi, eta, gamma;
   std::vector<int> map;
   long uploaded_step = -1;
@@ -55,6 +55,40 @@ class FixNVEB200 : public Fix {
   void initial_integrate(int vflag) override;        // fix_nve_sw64.c:43-99
   void final_integrate() override;                   // :101-170
   double dtv = 0, dtf = 0;
+};
+
+class FixReaxCBondsB200 : public Fix {               // fix ID all reax/c/bonds Nevery file
+ public:
+  FixReaxCBondsB200(LAMMPS* lmp, int narg, char** arg);  // fix_reaxc_bonds_sunway.cpp:45-91
+  ~FixReaxCBondsB200() override;
+  void init() override;                              // :121-127
+  void setup(int vflag) override { end_of_step(); }  // :114-117
+  void end_of_step() override;                       // :131-135  Output_ReaxC_Bonds
+  PairReaxCB200* reaxc = nullptr;
+  FILE* fp = nullptr;
+ private:
+  std::vector<int> tag_, type_, off_, nbr_;
+  std::vector<double> bo_, abo_, nlp_, q_;
+};
+
+class FixReaxCSpeciesB200 : public Fix {             // fix ID all reax/c/species Nevery Nrepeat Nfreq file [cutoff i j v] [element ...]
+ public:
+  FixReaxCSpeciesB200(LAMMPS* lmp, int narg, char** arg);  // fix_reaxc_species_sunway.cpp:50-252
+  ~FixReaxCSpeciesB200() override;
+  void init() override;                              // :301-329
+  void setup(int vflag) override { post_integrate(); }   // :291-297
+  void post_integrate() override;                    // :419-423  Output_ReaxC_Bonds
+  PairReaxCB200* reaxc = nullptr;
+  FILE* fp = nullptr;
+  int nrepeat = 1, nfreq = 1, ntypes = 0;
+  int Nmole = 0, Nspec = 0;                          // vector_nmole, vector_nspec
+  std::vector<double> BOCut;
+  std::vector<std::string> eletype;
+  std::vector<int> clusterID;                        // vector_atom
+ private:
+  bool configured_ = false;
+  int nev_ = 1;
+  void write_formulas(const std::vector<int>& comp);
 };
 
 }  // namespace LAMMPS_MINI

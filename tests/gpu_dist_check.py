@@ -32,7 +32,12 @@ def main():
     tol = 1e-10
     r, grid, n0 = D.setup_distributed(H, rank, world, lr, cells, tol=tol, thermo=1, T=T, p2p=p2p)
     th0 = r.md_thermo()
+    natoms = 384 * cells[0] * cells[1] * cells[2]
+    r.species_config(1, 5, 5, natoms=natoms)
     r.md_run(steps)
+    sp_log = r.species_log()
+    bt = r.bond_table()
+    bt_entries = int(D.sum_over_ranks(dist, [float(len(bt["nbr"]))], dev)[0])
     th = r.md_thermo()
     out = r.md_get()
     c = r.counts()
@@ -51,7 +56,6 @@ def main():
         allr = torch.cat(bufs).cpu().numpy()
         allr = allr[allr[:, 0] > 0]
         allr = allr[np.argsort(allr[:, 0])]
-        natoms = 384 * cells[0] * cells[1] * cells[2]
         assert len(allr) == natoms and np.array_equal(allr[:, 0].astype(np.int64), np.arange(1, natoms + 1)), "atoms lost or duplicated"
         box, x, t, tag = H.tatb_cell(*cells)
         v = D.velocities_by_tag(H, t, tag, T, 12345)
@@ -59,7 +63,14 @@ def main():
         s.pair_settings(H.CONTROL); s.pair_coeff(H.FFIELD, H.ELEMENTS); s.fix_qeq(0.0, 10.0, tol)
         s.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=5, thermo=1)
         s0 = s.md_thermo()
+        s.species_config(1, 5, 5, natoms=natoms)
         s.md_run(steps)
+        ref_log = s.species_log()
+        ok_sp = len(ref_log) == len(sp_log) and len(ref_log) == steps // 5 and all(
+            a["step"] == b["step"] and a["nmole"] == b["nmole"] and np.array_equal(a["composition"], b["composition"])
+            for a, b in zip(ref_log, sp_log))
+        ok_sp = ok_sp and len(s.bond_table()["nbr"]) == bt_entries
+        print(f"bond table entries {bt_entries}; species: {len(sp_log)} outputs, last nmole {sp_log[-1]['nmole'] if sp_log else None}, identical to 1 GPU: {ok_sp}")
         ref = s.md_get(); sth = s.md_thermo()
         # single-GPU run keeps atoms in tag order (no migration of indices)
         # positions may differ by a box vector after wrapping: compare through lamda-space minimum image
@@ -77,7 +88,7 @@ def main():
         moved = int((np.abs(lam) > 0.5).any(axis=1).sum())
         print(f"dist check {world} ranks grid {grid} cells {cells} steps {steps} T {T} p2p {p2p} n_local(rank0) {n} vs {n0} at start, wrapped {moved}: |dx| {ex:.2e}  f rel {ef:.2e}  |dq| {eq:.2e}  "
               f"pe0 rel {ee0:.2e}  pe rel {ee:.2e}  ke rel {ek:.2e}  pe {th['pe']:.6f} vs {sth['pe']:.6f}")
-        ok = ex < 1e-8 and ef < 1e-6 and eq < 1e-7 and ee0 < 1e-9 and ee < 1e-8 and ek < 1e-6
+        ok = ok_sp and ex < 1e-8 and ef < 1e-6 and eq < 1e-7 and ee0 < 1e-9 and ee < 1e-8 and ek < 1e-6
         print("DIST CHECK", "PASSED" if ok else "FAILED")
     flag = torch.tensor([1.0 if ok else 0.0], device=dev, dtype=torch.float64)
     dist.broadcast(flag, src=0)

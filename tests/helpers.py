@@ -254,6 +254,36 @@ class Oracle:
     def md_matvecs(self):
         return self.L.orc_md_matvecs(self.h, 0), self.L.orc_md_matvecs(self.h, 1)
 
+    # ---- fix reax/c/bonds, fix reax/c/species ----
+    def _text(self, fn, step):
+        self.L[fn].restype = C.c_long
+        need = self.L[fn](self.h, C.c_long(step), None, C.c_long(0))
+        buf = C.create_string_buffer(need + 1)
+        self.L[fn](self.h, C.c_long(step), buf, C.c_long(need + 1))
+        return buf.value.decode()
+
+    def md_bonds_text(self, step):
+        return self._text("orc_md_bonds_text", step)
+
+    def md_species_init(self, nevery, nrepeat, nfreq, ntypes=4, bocut=None):
+        bc = np.full((ntypes + 1, ntypes + 1), 0.30) if bocut is None else np.ascontiguousarray(bocut, dtype=np.float64)
+        self._sp_ntypes = ntypes
+        self.L.orc_md_species_init(self.h, nevery, nrepeat, nfreq, _c(bc))
+
+    def md_species_step(self, step):
+        r = self.L.orc_md_species_step(self.h, C.c_long(step))
+        assert r >= 0, "oracle species error"
+        return r == 1
+
+    def md_species_get(self):
+        nm = self.L.orc_md_species_nmole(self.h)
+        comp = np.zeros((nm, self._sp_ntypes), dtype=np.int32); cl = np.zeros(self.nlocal, dtype=np.int32)
+        self.L.orc_md_species_get(self.h, _p(comp), _p(cl))
+        return dict(nmole=nm, composition=comp, cluster=cl)
+
+    def md_species_text(self, step):
+        return self._text("orc_md_species_text", step)
+
 
 def _c(a):
     a = np.ascontiguousarray(a, dtype=np.float64)

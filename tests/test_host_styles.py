@@ -70,6 +70,69 @@ def test_script_errors_reported(tmp_path):
         run_script(str(p))
 
 
+def test_analysis_fix_argument_errors(tmp_path):
+    """Argument validation of fix reax/c/bonds / fix reax/c/species (fix_reaxc_bonds_sunway.cpp:48-58,
+    fix_reaxc_species_sunway.cpp:54-79, 193-227) happens before any GPU work."""
+    head = "units real\natom_style charge\nread_data %s\n" % H.DATAFILE
+    p = tmp_path / "in.bad"
+    out = tmp_path / "o.txt"
+    for line, msg in [("fix 3 all reax/c/bonds 0 %s" % out, "Illegal fix reax/c/bonds command"),
+                      ("fix 3 all reax/c/bonds 5", "Illegal fix reax/c/bonds command"),
+                      ("fix 3 all reax/c/bonds 5 %s.gz" % out, "Cannot open gzipped file"),
+                      ("fix 3 all reax/c/bonds 5 /nonexistent_dir/x", "Cannot open fix reax/c/bonds file"),
+                      ("fix 4 all reax/c/species 1 25 20 %s" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 2 5 25 %s" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s cutoff 1 9 0.5" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s cutoff 1 2 1.5" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s bogus" % out, "Illegal fix reax/c/species command")]:
+        p.write_text(head + line + "\n")
+        with pytest.raises(RuntimeError, match=msg):
+            run_script(str(p))
+    p.write_text(head + "fix 1 all nve\nfix 3 all reax/c/bonds 5 %s\nrun 1\n" % out)
+    with pytest.raises(RuntimeError, match="No pair style defined"):
+        run_script(str(p))
+
+
+@pytest.mark.gpu
+def test_script_with_bonds_and_species_fixes_matches_oracle(tmp_path):
+    """The reference's C5-style input (fix reax/c/bonds N file + fix reax/c/species nevery nrepeat nfreq file) through the
+    plugin path: both output files are byte-identical to the oracle's restatement of the reference writers."""
+    fb, fs = tmp_path / "bonds.out", tmp_path / "species.out"
+    lines = ["units real", "atom_style charge", "read_data %s" % H.DATAFILE,
+             "pair_style reax/c %s" % H.CONTROL, "pair_coeff * * %s C H O N" % H.FFIELD,
+             "neighbor 2.5 bin", "neigh_modify delay 0 every 5 check no", "fix 1 all nve",
+             "fix 2 all qeq/reax 1 0.0 10.0 1.0e-10 reax/c", "fix 3 all reax/c/bonds 4 %s" % fb,
+             "fix 4 all reax/c/species 1 4 4 %s" % fs, "velocity all create 1500.0 4928459", "thermo 4", "timestep 0.0625", "run 8"]
+    p = tmp_path / "in.c5"
+    p.write_text("\n".join(lines) + "\n")
+    run_script(str(p))
+    # the same run on the oracle (velocities from the driver's own `velocity all create` generator)
+    box, x, t, tag = H.tatb_cell(1, 1, 1)
+    v = host_velocities(1500.0, 4928459)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-10, every=4)    # the species fix resets reneighbouring to every 4
+    o.md_species_init(1, 4, 4)
+    bonds, species = o.md_bonds_text(0), ""                            # setup(): end_of_step() / post_integrate()
+    o.md_species_step(0)
+    for step in range(1, 9):
+        if o.md_species_step(step):          # post_integrate of this step: reads the previous step's bond list
+            species += o.md_species_text(step)
+        o.md_run(1)
+        if step % 4 == 0:
+            bonds += o.md_bonds_text(step)   # end_of_step
+    assert fb.read_text() == bonds
+    assert fs.read_text() == species and species.count("# Timestep") == 2
+
+
+def host_velocities(T, seed):
+    L = C.CDLL(HOSTLIB)
+    L.rxh_velocities.restype = C.c_long
+    v = np.zeros((384, 3))
+    n = L.rxh_velocities(H.DATAFILE.encode(), C.c_double(T), C.c_long(seed), v.ctypes.data_as(C.c_void_p), C.c_long(384))
+    assert n == 384
+    return v
+
+
 @pytest.mark.gpu
 def test_plugin_run_matches_resident_run_and_golden():
     th = run_script(SCRIPT, S=1, t=10, T=0, D=H.DATA)

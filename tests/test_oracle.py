@@ -135,3 +135,43 @@ def test_md_energy_conservation_cpu():
     r1 = o.md_get()
     e0, e1 = r0["pe"] + r0["ke"], r1["pe"] + r1["ke"]
     assert abs(e1 - e0) < 2e-3 * r0["ke"], (e0, e1)
+
+
+def test_bonds_table_and_species_of_the_tatb_crystal():
+    """fix reax/c/bonds / fix reax/c/species restatement, pinned by chemistry: the 384-atom TATB cell holds 16
+    C6H6O6N6 molecules of 24 atoms, each atom bonded only inside its molecule at bond order > 0.3."""
+    box, x, t, tag = H.tatb_cell(1, 1, 1)
+    v = H.maxwell_velocities(t, 300.0, 12345)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-8, every=5)
+    o.md_species_init(1, 1, 1)
+    assert not o.md_species_step(0)          # setup(): sampled, first output is at step nfreq
+    assert o.md_species_step(1)              # post_integrate of step 1
+    o.md_run(1)
+    sp = o.md_species_get()
+    assert sp["nmole"] == 16
+    assert (sp["composition"] == np.array([6, 6, 6, 6])).all()
+    assert (np.bincount(sp["cluster"])[1:] == 24).all()
+    txt = o.md_species_text(1)
+    assert txt == "# Timestep     No_Moles     No_Specs     C6H6O6N6\t\n1         16          1\t 16\t\n"
+    # connection table: parse the text block back
+    lines = o.md_bonds_text(1).splitlines()
+    assert lines[0] == "# Timestep 1 " and lines[2] == "# Number of particles 384 " and lines[-1] == "# "
+    rows = [ln.split() for ln in lines if not ln.startswith("#")]
+    assert len(rows) == 384
+    nbonds = 0
+    table = {}
+    for r in rows:
+        i, ty, nb = int(r[0]), int(r[1]), int(r[2])
+        ids = [int(a) for a in r[3:3 + nb]]
+        bos = [float(a) for a in r[4 + nb:4 + 2 * nb]]
+        assert len(r) == 3 + nb + 1 + nb + 3 and ty == t[i - 1]
+        assert all(b > 0.3 for b in bos)
+        assert all(sp["cluster"][j - 1] == sp["cluster"][i - 1] for j in ids)   # bonded only inside the molecule
+        assert 1 <= nb <= 4
+        table[i] = dict(zip(ids, bos))
+        nbonds += nb
+    assert nbonds % 2 == 0
+    for i, row in table.items():                # every bond is listed from both ends with the same (printed) bond order
+        for j, bo in row.items():
+            assert table[j][i] == bo
