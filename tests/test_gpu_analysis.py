@@ -80,21 +80,22 @@ def test_species_averaged_hot_compressed_matches_oracle():
     v = H.maxwell_velocities(t, 4000.0, 99)
     o = H.Oracle()
     o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-10, every=5)
-    o.md_species_init(1, 5, 5)
+    bc = np.full((5, 5), 0.30); bc[1, 4] = bc[4, 1] = 0.9       # `cutoff 1 4 0.9`: C-N bonds below 0.9 do not count
+    o.md_species_init(1, 5, 5, bocut=bc)
     r = make_rxb(1e-10)
     r.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=10, thermo=1)
-    assert r.species_config(1, 5, 5, natoms=len(x)) is True      # every 10 -> 5: "Resetting reneighboring criteria"
+    assert r.species_config(1, 5, 5, natoms=len(x), bocut=bc) is True      # every 10 -> 5: "Resetting reneighboring criteria"
     o.md_species_step(0); r.species_step(0)
     outs = []
-    for step in range(1, 16):
+    for step in range(1, 11):
         if o.md_species_step(step):      # post_integrate: before this step's force evaluation
             outs.append((step, o.md_species_get(), o.md_species_text(step)))
         o.md_run(1)
-    r.md_run(15)
+    r.md_run(10)
     log = r.species_log()
-    assert [rec["step"] for rec in log] == [s for s, _, _ in outs] == [5, 10, 15]
+    assert [rec["step"] for rec in log] == [s for s, _, _ in outs] == [5, 10]
     for rec, (step, so, txt) in zip(log, outs):
         assert rec["nmole"] == so["nmole"]
         assert np.array_equal(rec["composition"], so["composition"])
         assert analysis.species_text(step, rec["composition"]) == txt
-    assert len(analysis.find_species(log[-1]["composition"])[0]) > 1     # the compressed hot cell has reacted
+    assert len(analysis.find_species(log[-1]["composition"])[0]) >= 4    # several fragment species
