@@ -13,6 +13,8 @@
 #ifndef RXB200_H
 #define RXB200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -107,6 +109,13 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
 int rxb_get_workspace(rxb_handle* h, double* w16);
 /* far list == H pattern: num[nlocal], and for row i the entries off_verlet[i] .. +num[i] of idx/val */
 int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val);
+/* ---- optional: page-lock the caller's per-atom arrays (atom->x, the force buffer) so that rxb_set_positions /
+ * rxb_set_atoms / rxb_pair_compute copy them directly over PCIe instead of staging through an internal pinned buffer.
+ * Pageable pointers keep working.  A page-locked x passed to rxb_set_positions must stay unchanged until the next
+ * rxb_qeq_pre_force / rxb_pair_compute returns (LAMMPS' Verlet order guarantees that). */
+int rxb_host_register(void* p, size_t bytes);
+int rxb_host_unregister(void* p);
+
 /* ---- fix reax/c/bonds (replaces FixReaxCBondsSunway::FindBond + PassBuffer, fix_reaxc_bonds_sunway.cpp:187-260) ----
  * Builds, on the device, the connection table of the local atoms from the bond list of the last force evaluation:
  * neighbours with BO > bo_cut (bo_cut < 0: the control file's bond_graph_cutoff, as the reference uses), in bond-row

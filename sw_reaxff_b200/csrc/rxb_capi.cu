@@ -349,6 +349,11 @@ int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* compo
   });
 }
 
+int rxb_host_register(void* p, size_t bytes) {
+  return guard([&] { RXB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
+}
+int rxb_host_unregister(void* p) { return guard([&] { RXB_CUDA(cudaHostUnregister(p)); }); }
+
 int rxb_profiler_range(int start) {
   return guard([&] { if (start) RXB_CUDA(cudaProfilerStart()); else RXB_CUDA(cudaProfilerStop()); });
 }

@@ -26,6 +26,16 @@ __global__ void k_set_xyz(int N, const double* __restrict__ x, double4* __restri
   p.x = x[3 * i]; p.y = x[3 * i + 1]; p.z = x[3 * i + 2];
   xq[i] = p;
 }
+// set_atoms: (x[3], q, LAMMPS type) -> xq record + force-field element index (write_reax_atoms_and_pack, pair_reaxc_sw64.c:114-190)
+__global__ void k_pack_atoms(int N, const double* __restrict__ x, const double* __restrict__ q, const int* __restrict__ ltype,
+                             const int* __restrict__ map, int nmap, double4* __restrict__ xq, int* __restrict__ type) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  xq[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], q ? q[i] : 0.0);
+  const int lt = ltype[i];
+  type[i] = (lt >= 1 && lt < nmap) ? map[lt] : -1;
+}
+
 __global__ void k_set_q(int N, const double* __restrict__ q, double4* __restrict__ xq) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) xq[i].w = q[i];
@@ -326,21 +336,33 @@ void System::ensure_bond_capacity(int cap) {
   cap_bonds = cap;
 }
 
+// true when the CUDA runtime knows `p` as page-locked host memory (cudaHostRegister / cudaMallocHost): such buffers are
+// copied directly, pageable ones go through the pinned staging buffer
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+void System::h2d(void* dst, const void* src, size_t bytes, size_t stage_off_doubles) {
+  if (!bytes) return;
+  if (is_pinned(src)) {
+    RXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st_));
+  } else {
+    char* pp = (char*)h_pin_ + stage_off_doubles * sizeof(double);
+    memcpy(pp, src, bytes);
+    RXB_CUDA(cudaMemcpyAsync(dst, pp, bytes, cudaMemcpyHostToDevice, st_));
+  }
+}
+
 void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype, const int* tg, const double* q,
                        const int* owner_in) {
   RXB_CUDA(cudaSetDevice(device_));
   n = nlocal; N = nlocal + nghost;
   ensure_atom_capacity();
-  std::vector<double4> hx(N);
-  std::vector<int> ht(N), hown(std::max(nghost, 1), -1);
-  for (int i = 0; i < N; i++) {
-    hx[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], q ? q[i] : 0.0);
-    const int lt = ltype[i];
-    ht[i] = (lt >= 1 && lt < (int)ff.map.size()) ? ff.map[lt] : -1;
-  }
-  if (owner_in) {
-    for (int g = 0; g < nghost; g++) hown[g] = owner_in[g];
-  } else {  // single-rank LAMMPS: the ghost's owner is the local atom with the same tag (atom->map)
+  std::vector<int> hown;
+  if (!owner_in && nghost > 0) {  // single-rank LAMMPS: the ghost's owner is the local atom with the same tag (atom->map)
+    hown.assign(nghost, -1);
     std::unordered_map<int, int> by_tag;
     by_tag.reserve(nlocal * 2);
     for (int i = 0; i < nlocal; i++) by_tag.emplace(tg[i], i);
@@ -348,22 +370,34 @@ void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype
       auto it = by_tag.find(tg[nlocal + g]);
       hown[g] = it == by_tag.end() ? -1 : it->second;
     }
+    owner_in = hown.data();
   }
   ghost_owner.resize(std::max(nghost, 1));
-  RXB_CUDA(cudaMemcpyAsync(xq.p, hx.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaMemcpyAsync(type.p, ht.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaMemcpyAsync(tag.p, tg, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaMemcpyAsync(ltype_d.p, ltype, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaMemcpyAsync(ghost_owner.p, hown.data(), hown.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+  map_d.resize(std::max<size_t>(ff.map.size(), 1));
+  RXB_CUDA(cudaMemcpyAsync(map_d.p, ff.map.data(), ff.map.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+  // raw arrays up (x 24 B, q 8 B, type/tag 4 B per atom), packed into xq/type on the device
+  const size_t NN = N;
+  pin(5 * NN + 64);
+  x_stage.resize(4 * NN + 16);
+  h2d(x_stage.p, x, 3 * NN * sizeof(double), 0);
+  if (q) h2d(x_stage.p + 3 * NN, q, NN * sizeof(double), 3 * NN);
+  h2d(ltype_d.p, ltype, NN * sizeof(int), 4 * NN);
+  h2d(tag.p, tg, NN * sizeof(int), 4 * NN + NN / 2 + 1);
+  if (nghost > 0) RXB_CUDA(cudaMemcpyAsync(ghost_owner.p, owner_in, (size_t)nghost * sizeof(int), cudaMemcpyHostToDevice, st_));
+  if (N > 0)
+    k_pack_atoms<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, q ? x_stage.p + 3 * NN : nullptr, ltype_d.p, map_d.p, (int)ff.map.size(),
+                                           xq.p, type.p);
+  kernel_launches++;
   RXB_CUDA(cudaStreamSynchronize(st_));
 }
 
+// x_host must stay unchanged until the next synchronising call on this handle (rxb_qeq_pre_force / rxb_pair_compute)
+// when it is page-locked memory; pageable memory is staged before returning.
 void System::set_positions(const double* x_host) {
   RXB_CUDA(cudaSetDevice(device_));
-  double* pp = pin((size_t)3 * N);
-  memcpy(pp, x_host, (size_t)3 * N * sizeof(double));
+  pin((size_t)3 * N);
   x_stage.resize((size_t)3 * N);
-  RXB_CUDA(cudaMemcpyAsync(x_stage.p, pp, (size_t)3 * N * sizeof(double), cudaMemcpyHostToDevice, st_));
+  h2d(x_stage.p, x_host, (size_t)3 * N * sizeof(double), 0);
   k_set_xyz<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, xq.p);
   kernel_launches++;
 }
@@ -381,10 +415,16 @@ void System::set_charges(const double* q_host) {
 
 void System::get_forces(double* f_host) {
   RXB_CUDA(cudaSetDevice(device_));
+  const size_t bytes = (size_t)3 * N * sizeof(double);
+  if (is_pinned(f_host)) {
+    RXB_CUDA(cudaMemcpyAsync(f_host, f.p, bytes, cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaStreamSynchronize(st_));
+    return;
+  }
   double* pp = pin((size_t)3 * N);
-  RXB_CUDA(cudaMemcpyAsync(pp, f.p, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaMemcpyAsync(pp, f.p, bytes, cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
-  memcpy(f_host, pp, (size_t)3 * N * sizeof(double));
+  memcpy(f_host, pp, bytes);
 }
 
 void System::get_charges(double* q_host) {

@@ -260,6 +260,7 @@ class System {
   double* h_pin_ = nullptr;  // pinned staging
   size_t h_pin_cap_ = 0;
   double* pin(size_t doubles);
+  void h2d(void* dst, const void* src, size_t bytes, size_t stage_off_doubles);
   void step_forces(bool eflag, bool vflag);
   void ensure_atom_capacity();
   void ensure_bond_capacity(int cap);

@@ -1,6 +1,7 @@
 // lmp_b200 — minimal LAMMPS-like driver for the B200 ReaxFF styles:  lmp_b200 -in in.reaxc.lattice -var S 2 -var t 20
 // (same command line as the reference's run.sh:2 minus the Sunway launcher).  Also exports rxh_run_script for tests.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "mini_lammps.h"
@@ -59,11 +60,16 @@ extern "C" int rxh_bench_script(const char* script, int nvars, const char* const
     lmp.file(script);
     lmp.setup();
     lmp.iterate(warm);
+    for (double& p : lmp.phase_s) p = 0.0;
     auto t0 = std::chrono::steady_clock::now();
     lmp.iterate(steps);
     out4[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     out4[0] = (double)lmp.atom->natoms; out4[1] = (double)lmp.atom->nall();
     out4[3] = lmp.thermo_log.empty() ? 0.0 : lmp.thermo_log.back().pe;
+    if (getenv("RXH_PHASES")) {
+      static const char* nm[8] = {"integrate", "borders", "forward_comm", "zero_f", "pre_force", "pair_compute", "reverse_comm", "final+output"};
+      for (int k = 0; k < 8; k++) fprintf(stderr, "  host phase %-14s %8.3f ms/step\n", nm[k], 1e3 * lmp.phase_s[k] / steps);
+    }
     return 0;
   } catch (const std::exception& e) {
     if (err && errlen > 0) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }

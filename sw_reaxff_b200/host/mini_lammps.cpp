@@ -4,6 +4,7 @@
 #include "mini_lammps.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -33,6 +34,7 @@ void Domain::image_shift(int sx, int sy, int sz, double* d) const {
   d[2] = sz * h[2];
 }
 void Domain::remap(Atom& a) const {
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < a.nlocal; i++) {
     double l[3];
     x2lamda(&a.x[3 * i], l);
@@ -45,39 +47,66 @@ void Domain::remap(Atom& a) const {
   }
 }
 
+// Ghost atoms = periodic images within `cut` of the box, ordered shift-major (z, y, x shift loops outermost, atoms
+// innermost) like the oracle's stand-in.  Selection runs per shift in parallel; the fill keeps that order.
 void Comm::borders(const Domain& dom, Atom& a, double cut) {
   const double* hi = dom.h_inv;
   const double cg[3] = {cut * sqrt(hi[0] * hi[0] + hi[5] * hi[5] + hi[4] * hi[4]), cut * sqrt(hi[1] * hi[1] + hi[3] * hi[3]), cut * hi[2]};
   const int m[3] = {(int)ceil(cg[0]), (int)ceil(cg[1]), (int)ceil(cg[2])};
   const int n = a.nlocal;
-  a.x.resize((size_t)3 * n); a.type.resize(n); a.tag.resize(n); a.q.resize(n);
-  ghost_owner.clear(); ghost_shift.clear();
   std::vector<double> lam((size_t)3 * n);
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < n; i++) dom.x2lamda(&a.x[3 * i], &lam[3 * i]);
+  struct Shift { int s[3]; double d[3]; std::vector<int> who; };
+  std::vector<Shift> shifts;
   for (int sz = -m[2]; sz <= m[2]; sz++)
     for (int sy = -m[1]; sy <= m[1]; sy++)
       for (int sx = -m[0]; sx <= m[0]; sx++) {
         if (!sx && !sy && !sz) continue;
-        double d[3];
-        dom.image_shift(sx, sy, sz, d);
-        for (int i = 0; i < n; i++) {
-          const double l0 = lam[3 * i] + sx, l1 = lam[3 * i + 1] + sy, l2 = lam[3 * i + 2] + sz;
-          if (l0 >= -cg[0] && l0 < 1.0 + cg[0] && l1 >= -cg[1] && l1 < 1.0 + cg[1] && l2 >= -cg[2] && l2 < 1.0 + cg[2]) {
-            ghost_owner.push_back(i);
-            for (int t = 0; t < 3; t++) { ghost_shift.push_back(d[t]); a.x.push_back(a.x[3 * i + t] + d[t]); }
-            a.type.push_back(a.type[i]); a.tag.push_back(a.tag[i]); a.q.push_back(a.q[i]);
-          }
-        }
+        Shift sh;
+        sh.s[0] = sx; sh.s[1] = sy; sh.s[2] = sz;
+        dom.image_shift(sx, sy, sz, sh.d);
+        shifts.push_back(std::move(sh));
       }
-  a.nghost = (int)ghost_owner.size();
-  a.f.assign((size_t)3 * a.nall(), 0.0);
+  const int ns = (int)shifts.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < ns; k++) {
+    Shift& sh = shifts[k];
+    for (int i = 0; i < n; i++) {
+      const double l0 = lam[3 * i] + sh.s[0], l1 = lam[3 * i + 1] + sh.s[1], l2 = lam[3 * i + 2] + sh.s[2];
+      if (l0 >= -cg[0] && l0 < 1.0 + cg[0] && l1 >= -cg[1] && l1 < 1.0 + cg[1] && l2 >= -cg[2] && l2 < 1.0 + cg[2]) sh.who.push_back(i);
+    }
+  }
+  std::vector<size_t> off(ns + 1, 0);
+  for (int k = 0; k < ns; k++) off[k + 1] = off[k] + shifts[k].who.size();
+  const size_t ng = off[ns], nall = n + ng;
+  auto grow = [&](auto& v, size_t want) { if (v.capacity() < want) v.reserve(want + want / 4); v.resize(want); };
+  grow(a.x, 3 * nall); grow(a.type, nall); grow(a.tag, nall); grow(a.q, nall);
+  grow(ghost_owner, ng); grow(ghost_shift, 3 * ng);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < ns; k++) {
+    const Shift& sh = shifts[k];
+    size_t g = off[k];
+    for (int i : sh.who) {
+      ghost_owner[g] = i;
+      for (int t = 0; t < 3; t++) { ghost_shift[3 * g + t] = sh.d[t]; a.x[3 * (n + g) + t] = a.x[3 * i + t] + sh.d[t]; }
+      a.type[n + g] = a.type[i]; a.tag[n + g] = a.tag[i]; a.q[n + g] = a.q[i];
+      g++;
+    }
+  }
+  a.nghost = (int)ng;
+  grow(a.f, 3 * nall);
+  std::fill(a.f.begin(), a.f.end(), 0.0);
 }
 void Comm::forward_comm(Atom& a) const {
   const int n = a.nlocal;
+#pragma omp parallel for schedule(static)
   for (int g = 0; g < a.nghost; g++)
     for (int t = 0; t < 3; t++) a.x[3 * (n + g) + t] = a.x[3 * ghost_owner[g] + t] + ghost_shift[3 * g + t];
 }
 void Comm::reverse_comm(Atom& a) const {
+  // several images of one atom may be summed by different threads: accumulate in ghost order per owner would need a
+  // sort, and the sum order changes the last bits; keep the serial ghost order (0.3 ms for 160 k ghosts)
   const int n = a.nlocal;
   for (int g = 0; g < a.nghost; g++)
     for (int t = 0; t < 3; t++) a.f[3 * ghost_owner[g] + t] += a.f[3 * (n + g) + t];
@@ -414,25 +443,41 @@ void LAMMPS::run(long nsteps) {
 }
 
 void LAMMPS::iterate(long nsteps) {
+  using clk = std::chrono::steady_clock;
+  auto lap = [&](int k, clk::time_point& t0) { auto t1 = clk::now(); phase_s[k] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; };
   for (long s = 0; s < nsteps; s++) {
+    auto t0 = clk::now();
     update->ntimestep++;
     const int ev = (thermo_every && update->ntimestep % thermo_every == 0) || s == nsteps - 1;
     for (auto& f : fixes) f->initial_integrate(ev);
     for (auto& f : fixes) f->post_integrate();
+    lap(0, t0);
     if (neighbor->decide()) {
       domain->remap(*atom);
       comm->borders(*domain, *atom, pair->cutghost_request() + neighbor->skin);
       neighbor->ago = 0;
+      lap(1, t0);
     } else {
       comm->forward_comm(*atom);
+      lap(2, t0);
     }
-    std::fill(atom->f.begin(), atom->f.end(), 0.0);
+    {
+      double* f = atom->f.data();
+      const long n3 = (long)atom->f.size();
+#pragma omp parallel for schedule(static)
+      for (long k = 0; k < n3; k++) f[k] = 0.0;
+    }
+    lap(3, t0);
     for (auto& f : fixes) f->pre_force(ev);
+    lap(4, t0);
     pair->compute(ev, ev);
+    lap(5, t0);
     comm->reverse_comm(*atom);
+    lap(6, t0);
     for (auto& f : fixes) f->final_integrate();
     for (auto& f : fixes) if (f->nevery > 0 && update->ntimestep % f->nevery == 0) f->end_of_step();
     if (ev) thermo_line(ev);
+    lap(7, t0);
   }
 }
 

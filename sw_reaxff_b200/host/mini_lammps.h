@@ -114,6 +114,9 @@ struct LAMMPS {
   int cuda_device = 0;
   bool echo_thermo = true;
   std::vector<Thermo> thermo_log;
+  // wall seconds per phase of iterate(): integrate, borders, forward_comm, zero f, pre_force (upload + QEq), pair compute
+  // (+ force download), reverse_comm, final integrate + output
+  double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::map<std::string, std::string> vars;
 
   void file(const std::string& path);            // execute an input script

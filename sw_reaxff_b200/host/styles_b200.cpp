@@ -94,6 +94,7 @@ void PairReaxCB200::init_style() {
 void PairReaxCB200::upload_if_needed() {
   Atom* atom = lmp->atom;
   if (uploaded_step == lmp->update->ntimestep) return;
+  pin_x_.ensure(atom->x.data(), atom->x.capacity() * sizeof(double));   // direct PCIe copies of atom->x
   if (lmp->neighbor->ago == 0) {
     // reneighbouring step: new index space (what write_reax_atoms + NPair::build + write_reax_lists do in the reference)
     if (rxb_set_atoms(rxb, atom->nlocal, atom->nghost, atom->x.data(), atom->type.data(), atom->tag.data(), atom->q.data(),
@@ -110,11 +111,16 @@ void PairReaxCB200::compute(int eflag, int vflag) {
   Atom* atom = lmp->atom;
   upload_if_needed();
   const int nall = atom->nall();
+  if (fbuf_.capacity() < (size_t)3 * nall) fbuf_.reserve((size_t)3 * nall + (size_t)3 * nall / 4);
   fbuf_.resize((size_t)3 * nall);
+  pin_f_.ensure(fbuf_.data(), fbuf_.capacity() * sizeof(double));
   double eng[2], vir[6];
   if (rxb_pair_compute(rxb, eflag, vflag, fbuf_.data(), pvector, eng, vir)) lmp->error->all(FLERR, rxb_last_error());
   double* f = atom->f.data();
-  for (size_t k = 0; k < (size_t)3 * nall; k++) f[k] += fbuf_[k];
+  const double* fb = fbuf_.data();
+  const long n3 = 3L * nall;
+#pragma omp parallel for schedule(static)
+  for (long k = 0; k < n3; k++) f[k] += fb[k];
   if (eflag) { eng_vdwl = eng[0]; eng_coul = eng[1]; }
   if (vflag) for (int k = 0; k < 6; k++) virial[k] = vir[k];
 }
@@ -358,6 +364,7 @@ void FixNVEB200::init() {
 void FixNVEB200::initial_integrate(int) {
   Atom* a = lmp->atom;
   double* x = a->x.data(); double* v = a->v.data(); const double* f = a->f.data();
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < a->nlocal; i++) {
     const double dtfm = dtf / a->mass[a->type[i]];
     for (int t = 0; t < 3; t++) {
@@ -370,6 +377,7 @@ void FixNVEB200::initial_integrate(int) {
 void FixNVEB200::final_integrate() {
   Atom* a = lmp->atom;
   double* v = a->v.data(); const double* f = a->f.data();
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < a->nlocal; i++) {
     const double dtfm = dtf / a->mass[a->type[i]];
     for (int t = 0; t < 3; t++) v[3 * i + t] += dtfm * f[3 * i + t];

@@ -9,6 +9,19 @@
 
 namespace LAMMPS_MINI {
 
+// keeps one host array page-locked (rxb_host_register) across reallocations
+struct PinnedRegion {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(void* np, size_t nbytes) {
+    if (np == p && nbytes <= bytes) return;
+    release();
+    if (np && nbytes && rxb_host_register(np, nbytes) == 0) { p = np; bytes = nbytes; }
+  }
+  void release() { if (p) rxb_host_unregister(p); p = nullptr; bytes = 0; }
+  ~PinnedRegion() { release(); }
+};
+
 class PairReaxCB200 : public Pair {
  public:
   explicit PairReaxCB200(LAMMPS* lmp);
@@ -33,6 +46,7 @@ class PairReaxCB200 : public Pair {
 
  private:
   std::vector<double> fbuf_;
+  PinnedRegion pin_x_, pin_f_;
   std::string control_file_;
   bool coeff_done_ = false;
 };
