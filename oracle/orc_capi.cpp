@@ -163,6 +163,10 @@ void orc_get_workspace(void* hh, double* w16) {
     o[14] = s.dDelta_lp_temp[i]; o[15] = 0;
   }
 }
+void orc_get_ddeltap_self(void* hh, double* d3) {
+  System& s = ((OrcHandle*)hh)->md.sys;
+  memcpy(d3, s.dDeltap_self.data(), (size_t)3 * s.N * sizeof(double));
+}
 int orc_num_hbonds(void* hh) { return (int)((OrcHandle*)hh)->md.sys.hbonds.size(); }
 void orc_get_hbonds(void* hh, int* Hindex, int* hb_start, int* hb_end, int* nbr) {
   System& s = ((OrcHandle*)hh)->md.sys;

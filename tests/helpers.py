@@ -183,6 +183,11 @@ class Oracle:
         self.L.orc_get_workspace(self.h, _p(w))
         return w
 
+    def ddeltap_self(self):
+        d = np.zeros((self.N, 3))
+        self.L.orc_get_ddeltap_self(self.h, _p(d))
+        return d
+
     def hbonds(self):
         nh = self.L.orc_num_hbonds(self.h)
         Hindex = np.zeros(self.N, dtype=np.int32)

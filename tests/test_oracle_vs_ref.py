@@ -68,3 +68,214 @@ def test_reference_parser_on_modified_force_field(tmp_path):
     mine = parse_dump(H.CONTROL, str(p), H.ELEMENTS)
     assert np.array_equal(mask_taper(orc), ref)
     assert np.array_equal(mask_taper(mine), ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's LIVE serial energy routines (BOp_single, Torsion_Angles with control->virial = 1, Hydrogen_Bonds with
+# virial = 1, Add_dBond_to_Forces) compiled unmodified into oracle/_ref and driven on the oracle's own intermediate
+# state (oracle/ref/ref_bonded.cpp).  This pins the oracle's bond-order, valence-angle, torsion, hydrogen-bond and
+# bond-order chain-rule restatements against the reference itself, term by term.
+def _ref_lib():
+    L = C.CDLL(LIBREF)
+    L.ref_load.restype = C.c_void_p
+    return L, C.c_void_p(L.ref_load(H.CONTROL.encode(), H.FFIELD.encode()))
+
+
+def _ip(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _state(perturb, seed, scale=1.0):
+    """Oracle after bond list + hbond list + bond orders (phases 0,1,2,4) on a perturbed TATB cell with ghosts."""
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, scale=scale, qeq=False)
+    o = cfg["oracle"]
+    o.set_atoms(cfg["n"], cfg["x"], cfg["type"], cfg["tag"], np.zeros(len(cfg["x"])))
+    o.build_neighbors(12.5)
+    for ph in (0, 1, 2, 4):
+        o.phase(ph)
+    return cfg, o
+
+
+def _call_ref(L, P, which, cfg, o, Cd_in=None, CdDelta_in=None):
+    n, x = cfg["n"], cfg["x"]
+    N = len(x)
+    etype = _ip([{1: 0, 2: 1, 3: 2, 4: 3}[t] for t in cfg["type"]])      # pair_coeff * * ffield C H O N: type k -> element k-1
+    bs, be, nbr, sym, fld = o.bonds()
+    nb = len(nbr)
+    w = o.workspace(); dd = o.ddeltap_self()
+    Hindex, hs, he, hnbr = o.hbonds()
+    numH = int((Hindex[:n] >= 0).sum())
+    hrow = np.full(len(hnbr), -1, dtype=np.int64)
+    for j in range(n):
+        if Hindex[j] >= 0:
+            hrow[hs[Hindex[j]]:he[Hindex[j]]] = j
+    hvec = x[hnbr] - x[hrow]
+    hd = np.sqrt((hvec ** 2).sum(1))
+    en = np.zeros(6); fcd = np.zeros((N, 4)); cd = np.zeros((3, nb))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    keep = [np.ascontiguousarray(a) for a in (x, fld, w, dd, hd, hvec)]
+    ints = [_ip(a) for a in (cfg["tag"], bs, be, nbr, sym, Hindex, hs[:numH], he[:numH], hnbr)]
+    Cd = None if Cd_in is None else np.ascontiguousarray(Cd_in)
+    CdD = None if CdDelta_in is None else np.ascontiguousarray(CdDelta_in)
+    rc = L.ref_bonded(P, which, n, N, p(keep[0]), p(etype), p(ints[0]), p(ints[1]), p(ints[2]), nb, p(ints[3]), p(ints[4]),
+                      p(keep[1]), p(keep[2]), p(keep[3]), p(ints[5]), numH, p(ints[6]), p(ints[7]), len(hnbr), p(ints[8]),
+                      p(keep[4]), p(keep[5]), None if Cd is None else p(Cd), None if CdD is None else p(CdD), p(en), p(fcd), p(cd))
+    assert rc == 0
+    return en, fcd, cd
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("perturb,seed,scale", [(0.0, 0, 1.0), (0.1, 3, 1.0), (0.1, 4, 0.9)])
+def test_uncorrected_bond_orders_equal_reference_BOp_single(perturb, seed, scale):
+    """a4: every pair within bond_cut goes through the reference's BOp_single; the accepted set and BO', BO_s, BO_pi,
+    BO_pi2, dBOp, dln_BOp_pi, dln_BOp_pi2 of the oracle's bond list must match."""
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, scale=scale, qeq=False)
+    o = cfg["oracle"]
+    x = cfg["x"]
+    o.set_atoms(cfg["n"], x, cfg["type"], cfg["tag"], np.zeros(len(x)))
+    o.build_neighbors(12.5)
+    o.phase(0); o.phase(1)
+    bs, be, nbr, sym, fld = o.bonds()
+    off, idx = o.get_neighbors()
+    N = len(x)
+    rows = np.repeat(np.arange(N), np.diff(off))
+    dv = x[idx] - x[rows]
+    d = np.sqrt((dv ** 2).sum(1))
+    sel = d <= 4.5                                    # control bond_cut
+    rows, cols, dv, d = rows[sel], idx[sel], np.ascontiguousarray(dv[sel]), np.ascontiguousarray(d[sel])
+    et = np.array([{1: 0, 2: 1, 3: 2, 4: 3}[t] for t in cfg["type"]], dtype=np.int32)
+    ti, tj = _ip(et[rows]), _ip(et[cols])
+    L, P = _ref_lib()
+    out = np.zeros((len(d), 15))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.ref_bop_pairs(P, len(d), p(ti), p(tj), p(d), p(dv), p(out))
+    acc = out[:, 0] > 0
+    ref_pairs = set(zip(rows[acc].tolist(), cols[acc].tolist()))
+    brow = np.repeat(np.arange(N), be - bs) if np.array_equal(bs[1:], be[:-1]) else None
+    orc_pairs = set()
+    by_pair = {}
+    for i in range(N):
+        for pp in range(bs[i], be[i]):
+            orc_pairs.add((i, int(nbr[pp]))); by_pair[(i, int(nbr[pp]))] = pp
+    assert orc_pairs == ref_pairs and len(orc_pairs) > 1000
+    k = np.nonzero(acc)[0]
+    pp = np.array([by_pair[(int(rows[a]), int(cols[a]))] for a in k])
+    ref = out[k]
+    assert relerr(fld[pp, 4], ref[:, 1]) < 1e-13      # BO' - bo_cut
+    assert relerr(fld[pp, 5], ref[:, 2]) < 1e-13      # BO_s
+    assert relerr(fld[pp, 6], ref[:, 3]) < 1e-13 and relerr(fld[pp, 7], ref[:, 4]) < 1e-13
+    assert relerr(fld[pp, 8:11], ref[:, 5:8]) < 1e-12     # dBOp
+    assert relerr(fld[pp, 11:14], ref[:, 8:11]) < 1e-12 and relerr(fld[pp, 14:17], ref[:, 11:14]) < 1e-12
+
+
+@pytest.mark.parametrize("perturb,seed,scale", [(0.0, 0, 1.0), (0.1, 1, 1.0), (0.1, 2, 0.9)])
+def test_valence_torsion_hbond_dbond_equal_reference_serial_routines(perturb, seed, scale):
+    L, P = _ref_lib()
+    cfg, o = _state(perturb, seed, scale)
+    n = cfg["n"]
+    # --- valence angles + torsions (a10): reference Torsion_Angles, serial virial path
+    en, fcd, cd = _call_ref(L, P, 1, cfg, o)
+    o.phase(0); o.phase(7)
+    e, _ = o.energies()
+    bs, be, nbr, sym, fld = o.bonds()
+    for k_ref, k_orc in ((0, 4), (1, 5), (2, 6), (3, 8), (4, 9)):     # e_ang e_pen e_coa e_tor e_con
+        assert abs(en[k_ref] - e[k_orc]) <= 1e-10 * max(1.0, abs(e[k_orc])), (k_ref, en[k_ref], e[k_orc])
+    assert relerr(-fcd[:, :3], o.forces()) < 1e-10
+    assert relerr(fcd[:, 3], o.cddelta()) < 1e-10
+    assert relerr(cd.T, fld[:, 28:31]) < 1e-10
+    Cd_vt, CdD_vt = fld[:, 28:31].T.copy(), o.cddelta().copy()
+    # --- hydrogen bonds (a8), accumulating on top of the valence/torsion coefficients like Compute_Bonded_Forces does
+    f_before = o.forces().copy()
+    en2, fcd2, cd2 = _call_ref(L, P, 2, cfg, o, Cd_in=Cd_vt, CdDelta_in=CdD_vt)
+    o.phase(6)
+    e, _ = o.energies()
+    assert abs(en2[5] - e[7]) <= 1e-10 * max(1.0, abs(e[7])) and abs(e[7]) > 1.0
+    assert relerr(-fcd2[:, :3], o.forces() - f_before) < 1e-10
+    bs, be, nbr, sym, fld = o.bonds()
+    assert relerr(cd2.T, fld[:, 28:31]) < 1e-10
+    # --- bond-order chain rule (a11): reference Add_dBond_to_Forces over every bond once
+    Cd_all, CdD_all = fld[:, 28:31].T.copy(), o.cddelta().copy()
+    f_before = o.forces().copy()
+    en3, fcd3, cd3 = _call_ref(L, P, 4, cfg, o, Cd_in=Cd_all, CdDelta_in=CdD_all)
+    o.phase(8)
+    df = o.forces() - f_before
+    assert np.abs(df).max() > 10.0
+    assert relerr(-fcd3[:, :3], df) < 1e-10
+
+
+def test_taper_equals_reference_Init_Taper():
+    L, P = _ref_lib()
+    tap = np.zeros(8)
+    L.ref_taper(P, tap.ctypes.data_as(C.c_void_p))
+    d = H.Oracle().params_dump()
+    ngp = int(d[2])
+    assert np.array_equal(d[3 + ngp + 10:3 + ngp + 18], tap) and tap[7] != 0.0
+    mine = parse_dump(H.CONTROL, H.FFIELD, H.ELEMENTS)
+    assert np.array_equal(mine[3 + ngp + 10:3 + ngp + 18], tap)
+
+
+@pytest.mark.parametrize("perturb,seed,scale", [(0.0, 0, 1.0), (0.1, 5, 1.0), (0.1, 6, 0.9)])
+def test_bond_and_atom_energies_equal_reference_MPE_serial_routine(perturb, seed, scale):
+    """a7: Merge_Bonds_Atom_Energy_C_New (reaxc_multi_body_sw64.c:21-333), the routine the production run executes."""
+    L, P = _ref_lib()
+    cfg, o = _state(perturb, seed, scale)
+    n, N = cfg["n"], len(cfg["x"])
+    q = np.ascontiguousarray(np.random.default_rng(seed).uniform(-0.5, 0.5, N))
+    etype = _ip([t - 1 for t in cfg["type"]])
+    bs, be, nbr, sym, fld = o.bonds()
+    nb = len(nbr)
+    w = o.workspace()
+    en = np.zeros(5); ev = np.zeros(2); fcd = np.zeros((N, 4)); cd = np.zeros((3, nb))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ints = [_ip(a) for a in (cfg["tag"], bs, be, nbr, sym)]
+    fl, wl = np.ascontiguousarray(fld), np.ascontiguousarray(w)
+    assert L.ref_atom_energy(P, 1, n, N, p(q), p(etype), p(ints[0]), p(ints[1]), p(ints[2]), nb, p(ints[3]), p(ints[4]), p(fl), p(wl),
+                             p(en), p(ev), p(fcd), p(cd)) == 0
+    o.phase(0); o.phase(5)
+    e, _ = o.energies()
+    for k_ref, k_orc in ((0, 0), (1, 3), (2, 1), (3, 2)):       # e_bond, e_lp, e_ov, e_un
+        assert abs(en[k_ref] - e[k_orc]) <= 1e-10 * max(1.0, abs(e[k_orc])), (k_ref, en[k_ref], e[k_orc])
+    assert abs(e[0]) > 1e3 and abs(e[1]) > 1.0
+    bs, be, nbr, sym, fld2 = o.bonds()
+    assert relerr(cd.T, fld2[:, 28:31]) < 1e-10
+    assert relerr(fcd[:, 3], o.cddelta()) < 1e-10
+    assert np.abs(fcd[:, :3]).max() == 0.0        # this routine produces no direct forces
+
+
+@pytest.mark.parametrize("perturb,seed", [(0.0, 0), (0.1, 7)])
+def test_nonbonded_equals_reference_MPE_serial_routine(perturb, seed):
+    """a9: vdW_Coulomb_Energy_Full_C_test_err (reaxc_nonbonded_sw64.c:40-258), full list, owner computes."""
+    L, P = _ref_lib()
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, qeq=True)
+    o = cfg["oracle"]
+    n, x, q = cfg["n"], cfg["x"], cfg["q"]
+    N = len(x)
+    o.set_atoms(n, x, cfg["type"], cfg["tag"], q)
+    o.build_neighbors(12.5)
+    off, idx = o.get_neighbors()
+    rows = np.repeat(np.arange(N), np.diff(off))
+    loc = rows < n
+    rows, cols = rows[loc], idx[loc]
+    dv = x[cols] - x[rows]
+    d = np.sqrt((dv ** 2).sum(1))
+    sel = d <= 10.0
+    rows, cols, dv, d = rows[sel], _ip(cols[sel]), np.ascontiguousarray(dv[sel]), np.ascontiguousarray(d[sel])
+    far_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=far_off[1:])
+    tap = np.zeros(8)
+    L.ref_taper(P, tap.ctypes.data_as(C.c_void_p))
+    etype = _ip([t - 1 for t in cfg["type"]])
+    en = np.zeros(2); fcd = np.zeros((N, 4))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    xx, qq, tg = np.ascontiguousarray(x), np.ascontiguousarray(q), _ip(cfg["tag"])
+    assert L.ref_nonbonded(P, n, N, p(xx), p(qq), p(etype), p(tg), p(far_off), p(cols), p(d), p(dv), p(tap), p(en), p(fcd)) == 0
+    o.phase(0); o.phase(3)
+    e, _ = o.energies()
+    # the reference adds the FULL pair energy for every directed pair (SURVEY.md §8 "Semantics"): 2x the stock sum
+    assert abs(en[0] - 2 * e[10]) <= 1e-10 * abs(2 * e[10]) and abs(en[1] - 2 * e[11]) <= 1e-10 * abs(2 * e[11])
+    assert abs(e[10]) > 100 and abs(e[11]) > 100
+    assert relerr(-fcd[:n, :3], o.forces()[:n]) < 1e-10
+    assert np.abs(o.forces()[n:]).max() == 0.0 and np.abs(fcd[n:]).max() == 0.0     # ghosts receive no nonbonded force
