@@ -310,6 +310,28 @@ def _p(a):
 _keep = []  # keep temporaries alive across the ctypes call (bounded: cleared opportunistically)
 
 
+def ffield_variant(path, vdw_type):
+    """Write a copy of the TATB force field whose element block selects another van der Waals form
+    (reaxc_ffield_sunway.cpp:240-293): 3 = shielding + inner wall (rcore2/ecore2/acore2 set), 2 = inner wall only
+    (gamma_w <= 0.5 as well).  Exercises the branches the shipped force field (type 1) never takes."""
+    src = open(FFIELD).read().splitlines()
+    ia = next(i for i, l in enumerate(src) if "Nr of atoms" in l)
+    nel = int(src[ia].split()[0])
+    for e in range(nel):
+        l2 = ia + 4 + 4 * e + 1          # alfa; gammavdW; ...
+        l4 = ia + 4 + 4 * e + 3          # ov/un; val1; n.u.; val3; vval4; rcore2; ecore2; acore2
+        w4 = src[l4].split()
+        w4[5:8] = ["%.4f" % (1.2 + 0.15 * e), "%.4f" % (0.08 + 0.02 * e), "%.4f" % (10.0 + e)]
+        src[l4] = "     " + "  ".join(w4)
+        if vdw_type == 2:
+            w2 = src[l2].split()
+            w2[1] = "0.4000"
+            src[l2] = "     " + "  ".join(w2)
+    with open(path, "w") as f:
+        f.write("\n".join(src) + "\n")
+    return str(path)
+
+
 def static_config(nx=1, ny=1, nz=1, perturb=0.0, seed=0, scale=1.0, qeq=True, oracle=None):
     """Build (n, xall, typeall, tagall, qall, ghost_owner) exactly as the LAMMPS core would hand it to the pair style,
     using the oracle's mini-MD setup (remap + periodic ghosts) and, optionally, equilibrated charges."""

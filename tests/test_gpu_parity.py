@@ -296,3 +296,66 @@ def test_empty_and_tiny_inputs():
     o.build_neighbors(12.5)
     o.compute()
     assert rel(out["f"], o.forces()) < 1e-9
+
+
+def _forces_and_energies(ffield, elements, perturb, seed, qeq=True):
+    """One (QEq +) force evaluation on the oracle and on the GPU with the same force field / element map.
+    qeq=False: the pair style alone with fixed charges (a run without fix qeq/reax)."""
+    from sw_reaxff_b200 import Rxb
+    orc = H.Oracle(ffield=ffield, elements=elements)
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, qeq=False, oracle=orc)
+    o = cfg["oracle"]
+    n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    q0 = np.zeros(len(x))
+    if not qeq:
+        ql = np.random.default_rng(seed).uniform(-0.4, 0.4, n)
+        q0 = np.concatenate([ql, ql[owner]])
+    o.set_atoms(n, x, ty, tg, q0)
+    o.build_neighbors(12.5)
+    if qeq:
+        o.qeq_init(0.0, 10.0, 1e-10)
+        o.qeq_set_hist(np.zeros((n, 5)), np.zeros((n, 5)))
+        o.qeq_pre_force(owner)
+    o.compute()
+    r = Rxb(0)
+    r.pair_settings(H.CONTROL)
+    r.pair_coeff(ffield, elements)
+    r.fix_qeq(0.0, 10.0, 1e-10)
+    r.set_atoms(n, x, ty, tg, q0, owner)
+    r.neigh_build()
+    if qeq:
+        r.qeq_pre_force()
+    qg = r.get_charges()
+    res = r.pair_compute(True, True)
+    return cfg, o, qg, res
+
+
+@pytest.mark.parametrize("vdw_type", [3, 2])
+def test_inner_wall_vdw_forms(vdw_type, tmp_path):
+    """Force-field variants that select vdw_type 3 (shielding + inner wall) and 2 (inner wall only): branches of
+    reaxc_nonbonded_sw64.c:118-165 the shipped TATB force field never takes."""
+    ff = H.ffield_variant(tmp_path / "ffield.v", vdw_type)
+    cfg, o, qg, res = _forces_and_energies(ff, H.ELEMENTS, 0.1, 11)
+    assert int(o.params_dump()[1]) == vdw_type
+    eo, vo = o.energies()
+    assert np.abs(qg[:cfg["n"]] - o.q()[:cfg["n"]]).max() < 1e-8
+    assert rel(res["pvector"], pvector_from_oracle(eo)) < 1e-8 and abs(eo[10]) > 10.0
+    assert abs(res["eng"].sum() - eo.sum()) < 1e-8 * abs(eo.sum())
+    assert rel(res["f"], o.forces()) < 1e-7
+    assert rel(res["virial"], vo) < 1e-7
+
+
+def test_null_mapped_element_is_ignored_like_the_reference():
+    """pair_coeff * * ffield C H O NULL: atoms of the unmapped LAMMPS type take part in no interaction
+    (type < 0 skips in every reference loop, e.g. reaxc_nonbonded_sw64.c:78,87).  Run without fix qeq/reax: the
+    reference's QEq divides by eta = 0 for such atoms (Pair::extract gives chi = eta = 0, Hdia_inv = 1/eta), so the
+    combination is only defined with fixed charges."""
+    cfg, o, qg, res = _forces_and_energies(H.FFIELD, ["C", "H", "O", "NULL"], 0.05, 12, qeq=False)
+    eo, vo = o.energies()
+    n = cfg["n"]
+    null_atoms = np.nonzero(cfg["type"][:n] == 4)[0]
+    assert len(null_atoms) == 96
+    assert np.abs(res["f"][null_atoms]).max() == 0.0 and np.abs(o.forces()[null_atoms]).max() == 0.0
+    assert rel(res["pvector"], pvector_from_oracle(eo)) < 1e-8
+    assert rel(res["f"], o.forces()) < 1e-7
+    assert np.array_equal(qg[:n], o.q()[:n])

@@ -75,10 +75,10 @@ def test_reference_parser_on_modified_force_field(tmp_path):
 # virial = 1, Add_dBond_to_Forces) compiled unmodified into oracle/_ref and driven on the oracle's own intermediate
 # state (oracle/ref/ref_bonded.cpp).  This pins the oracle's bond-order, valence-angle, torsion, hydrogen-bond and
 # bond-order chain-rule restatements against the reference itself, term by term.
-def _ref_lib():
+def _ref_lib(ffield=None):
     L = C.CDLL(LIBREF)
     L.ref_load.restype = C.c_void_p
-    return L, C.c_void_p(L.ref_load(H.CONTROL.encode(), H.FFIELD.encode()))
+    return L, C.c_void_p(L.ref_load(H.CONTROL.encode(), (ffield or H.FFIELD).encode()))
 
 
 def _ip(a):
@@ -245,11 +245,15 @@ def test_bond_and_atom_energies_equal_reference_MPE_serial_routine(perturb, seed
     assert np.abs(fcd[:, :3]).max() == 0.0        # this routine produces no direct forces
 
 
-@pytest.mark.parametrize("perturb,seed", [(0.0, 0), (0.1, 7)])
-def test_nonbonded_equals_reference_MPE_serial_routine(perturb, seed):
-    """a9: vdW_Coulomb_Energy_Full_C_test_err (reaxc_nonbonded_sw64.c:40-258), full list, owner computes."""
-    L, P = _ref_lib()
-    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, qeq=True)
+@pytest.mark.parametrize("perturb,seed,vdw_type", [(0.0, 0, 1), (0.1, 7, 1), (0.1, 8, 3), (0.1, 9, 2)])
+def test_nonbonded_equals_reference_MPE_serial_routine(perturb, seed, vdw_type, tmp_path):
+    """a9: vdW_Coulomb_Energy_Full_C_test_err (reaxc_nonbonded_sw64.c:40-258), full list, owner computes; the shipped
+    force field (shielded vdW, type 1) and variants that take the inner-wall branches (types 3 and 2)."""
+    ff = H.FFIELD if vdw_type == 1 else H.ffield_variant(tmp_path / "ffield.v", vdw_type)
+    L, P = _ref_lib(ff)
+    orc = H.Oracle(ffield=ff)
+    assert int(orc.params_dump()[1]) == vdw_type
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, qeq=True, oracle=orc)
     o = cfg["oracle"]
     n, x, q = cfg["n"], cfg["x"], cfg["q"]
     N = len(x)
