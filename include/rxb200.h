@@ -47,6 +47,11 @@ long rxb_params_dump(rxb_handle* h, double* out, long cap);
 /* host-only: parse control + ffield + element map without touching a GPU and dump as above; -1 on error */
 long rxb_parse_dump(const char* control_file, const char* ffield_file, int ntypes, const char* const* elements,
                     int lgvdw, int enobonds, double* out, long cap);
+/* Host-only: the spline tables of the tabulated long-range mode (control: tabulate_long_range N > 0; algorithm of the
+ * reference's commented-out reaxc_lookup_sunway.cpp:157-285).  Layout [nt*nt][n = N+2][CEvd,CEclmb,e_vdW,e_ele][a,b,c,d];
+ * returns the number of doubles (0 when tabulate is 0, -1 on error). */
+long rxb_lookup_dump(const char* control_file, const char* ffield_file, int ntypes, const char* const* elements, int* n_out,
+                     double* out, long cap);
 
 /* ---- atoms: local [0,nlocal) then ghost [nlocal,nlocal+nghost)
  *      replaces write_reax_atoms_and_pack, pair_reaxc_sw64.c:114-190.

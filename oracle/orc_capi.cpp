@@ -163,6 +163,14 @@ void orc_get_workspace(void* hh, double* w16) {
     o[14] = s.dDelta_lp_temp[i]; o[15] = 0;
   }
 }
+// spline tables of the tabulated mode: returns n (= tabulate + 2); out = [nt*nt][5][n][4] (a,b,c,d)
+int orc_lookup_tables(void* hh, double* out) {
+  Params& P = ((OrcHandle*)hh)->md.sys.prm;
+  if (P.tabulate <= 0) return 0;
+  if (P.lookup.n != P.tabulate + 2) build_lookup_tables(P);
+  if (out) memcpy(out, P.lookup.tables.data(), P.lookup.tables.size() * sizeof(SplineCoef));
+  return P.lookup.n;
+}
 void orc_get_ddeltap_self(void* hh, double* d3) {
   System& s = ((OrcHandle*)hh)->md.sys;
   memcpy(d3, s.dDeltap_self.data(), (size_t)3 * s.N * sizeof(double));

@@ -149,9 +149,200 @@ void build_hbond_list(System& s) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// a9' / f4: tabulated long-range interactions.  NOT executed by the reference (reaxc_lookup_sunway.cpp is commented out in
+// full and Init_Lookup_Tables is never called); restated from those comments because BASELINE's north_star names the
+// spline tables: Tridiagonal_Solve :37-54, Natural_Cubic_Spline :57-106, Complete_Cubic_Spline :110-157,
+// Init_Lookup_Tables :157-285 (including its quirks: v0 = CEvd / CEclmb at the first knot, vlast_ele = fele[last],
+// the operator-precedence slip in d[n-1]), LR_vdW_Coulomb reaxc_nonbonded_sunway.cpp:573-668, and the evaluation form
+// of Tabulated_vdW_Coulomb_Energy :498-519.  Parity unpinned (dead code); the deviation from the analytic form is measured
+// in tests/test_oracle.py.
+namespace {
+struct LRpoint { double H, e_vdW, CEvd, e_ele, CEclmb; };
+
+LRpoint lr_vdw_coulomb(const Params& P, int i, int j, double r_ij) {
+  const double p_vdW1 = P.gp[28], p_vdW1i = 1.0 / p_vdW1;
+  const double* Tap = P.Tap;
+  const Tbp& tw = P.tb(i, j);
+  LRpoint lr;
+  double T = Tap[7] * r_ij + Tap[6];
+  T = T * r_ij + Tap[5]; T = T * r_ij + Tap[4]; T = T * r_ij + Tap[3];
+  T = T * r_ij + Tap[2]; T = T * r_ij + Tap[1]; T = T * r_ij + Tap[0];
+  double dT = 7 * Tap[7] * r_ij + 6 * Tap[6];
+  dT = dT * r_ij + 5 * Tap[5]; dT = dT * r_ij + 4 * Tap[4]; dT = dT * r_ij + 3 * Tap[3];
+  dT = dT * r_ij + 2 * Tap[2];
+  dT += Tap[1] / r_ij;
+  if (P.vdw_type == 1 || P.vdw_type == 3) {
+    double powr = pow(r_ij, p_vdW1);
+    double powgi = pow(1.0 / tw.gamma_w, p_vdW1);
+    double fn13 = pow(powr + powgi, p_vdW1i);
+    double exp1 = exp(tw.alpha * (1.0 - fn13 / tw.r_vdW));
+    double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 / tw.r_vdW));
+    lr.e_vdW = T * tw.D * (exp1 - 2.0 * exp2);
+    double dfn13 = pow(powr + powgi, p_vdW1i - 1.0) * pow(r_ij, p_vdW1 - 2.0);
+    lr.CEvd = dT * tw.D * (exp1 - 2.0 * exp2) - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) * dfn13;
+  } else {
+    double exp1 = exp(tw.alpha * (1.0 - r_ij / tw.r_vdW));
+    double exp2 = exp(0.5 * tw.alpha * (1.0 - r_ij / tw.r_vdW));
+    lr.e_vdW = T * tw.D * (exp1 - 2.0 * exp2);
+    lr.CEvd = dT * tw.D * (exp1 - 2.0 * exp2) - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) / r_ij;
+  }
+  if (P.vdw_type == 2 || P.vdw_type == 3) {
+    double e_core = tw.ecore * exp(tw.acore * (1.0 - (r_ij / tw.rcore)));
+    lr.e_vdW += T * e_core;
+    double de_core = -(tw.acore / tw.rcore) * e_core;
+    lr.CEvd += dT * e_core + T * de_core / r_ij;
+    if (P.lgflag) {
+      double r5 = pow(r_ij, 5.0), r6 = pow(r_ij, 6.0), re6 = pow(tw.lgre, 6.0);
+      double e_lg = -(tw.lgcij / (r6 + re6));
+      lr.e_vdW += T * e_lg;
+      double de_lg = -6.0 * e_lg * r5 / (r6 + re6);
+      lr.CEvd += dT * e_lg + T * de_lg / r_ij;
+    }
+  }
+  double dr3gamij_1 = r_ij * r_ij * r_ij + tw.gamma;
+  double dr3gamij_3 = pow(dr3gamij_1, 0.33333333333333);
+  double tmp = T / dr3gamij_3;
+  lr.H = 14.40 * tmp;   // EV_to_KCALpMOL
+  lr.e_ele = C_ele * tmp;
+  lr.CEclmb = C_ele * (dT - T * r_ij / dr3gamij_1) / dr3gamij_3;
+  return lr;
+}
+
+void tridiagonal_solve(const double* a, const double* b, double* c, double* d, double* x, int n) {
+  c[0] /= b[0];
+  d[0] /= b[0];
+  for (int i = 1; i < n; i++) {
+    double id = (b[i] - c[i - 1] * a[i]);
+    c[i] /= id;
+    d[i] = (d[i] - d[i - 1] * a[i]) / id;
+  }
+  x[n - 1] = d[n - 1];
+  for (int i = n - 2; i >= 0; i--) x[i] = d[i] - c[i] * x[i + 1];
+}
+
+void spline_coefs(const double* h, const double* f, const double* v, SplineCoef* coef, int n) {
+  for (int i = 1; i < n; ++i) {
+    coef[i - 1].d = (v[i] - v[i - 1]) / (6 * h[i - 1]);
+    coef[i - 1].c = v[i] / 2;
+    coef[i - 1].b = (f[i] - f[i - 1]) / h[i - 1] + h[i - 1] * (2 * v[i] + v[i - 1]) / 6;
+    coef[i - 1].a = f[i];
+  }
+}
+
+void natural_cubic_spline(const double* h, const double* f, SplineCoef* coef, int n) {
+  std::vector<double> a(n), b(n), c(n), d(n), v(n);
+  a[0] = a[1] = a[n - 1] = 0;
+  for (int i = 2; i < n - 1; ++i) a[i] = h[i - 1];
+  b[0] = b[n - 1] = 0;
+  for (int i = 1; i < n - 1; ++i) b[i] = 2 * (h[i - 1] + h[i]);
+  c[0] = c[n - 2] = c[n - 1] = 0;
+  for (int i = 1; i < n - 2; ++i) c[i] = h[i];
+  d[0] = d[n - 1] = 0;
+  for (int i = 1; i < n - 1; ++i) d[i] = 6 * ((f[i + 1] - f[i]) / h[i] - (f[i] - f[i - 1]) / h[i - 1]);
+  v[0] = 0;
+  v[n - 1] = 0;
+  tridiagonal_solve(&a[1], &b[1], &c[1], &d[1], &v[1], n - 2);
+  spline_coefs(h, f, v.data(), coef, n);
+}
+
+void complete_cubic_spline(const double* h, const double* f, double v0, double vlast, SplineCoef* coef, int n) {
+  std::vector<double> a(n), b(n), c(n), d(n), v(n);
+  a[0] = 0;
+  for (int i = 1; i < n; ++i) a[i] = h[i - 1];
+  b[0] = 2 * h[0];
+  for (int i = 1; i < n; ++i) b[i] = 2 * (h[i - 1] + h[i]);
+  c[n - 1] = 0;
+  for (int i = 0; i < n - 1; ++i) c[i] = h[i];
+  d[0] = 6 * (f[1] - f[0]) / h[0] - 6 * v0;
+  d[n - 1] = 6 * vlast - 6 * (f[n - 1] - f[n - 2] / h[n - 2]);   // sic (:143)
+  for (int i = 1; i < n - 1; ++i) d[i] = 6 * ((f[i + 1] - f[i]) / h[i] - (f[i] - f[i - 1]) / h[i - 1]);
+  tridiagonal_solve(&a[0], &b[0], &c[0], &d[0], &v[0], n);
+  spline_coefs(h, f, v.data(), coef, n);
+}
+}  // namespace
+
+void build_lookup_tables(Params& P) {
+  Lookup& L = P.lookup;
+  const int nt = P.nt, tab = P.tabulate;
+  L.n = tab + 2;
+  L.dx = P.nonb_cut / tab;
+  L.inv_dx = tab / P.nonb_cut;
+  L.tables.assign((size_t)nt * nt * 5 * L.n, SplineCoef{0, 0, 0, 0});
+  // h[r] spans r = 1 .. tab+1 (the reference sets h[tab+1] too); one spare slot because Complete_Cubic_Spline reads h[n-1]
+  std::vector<double> h(tab + 3, L.dx), fh(tab + 2), fvdw(tab + 2), fCEvd(tab + 2), fele(tab + 2), fCEclmb(tab + 2);
+  for (int i = 0; i < nt; i++)
+    for (int j = i; j < nt; j++) {
+      LRpoint first{};
+      int r;
+      for (r = 1; r <= tab; ++r) {
+        LRpoint y = lr_vdw_coulomb(P, i, j, r * L.dx);
+        if (r == 1) first = y;
+        fh[r] = y.H; fvdw[r] = y.e_vdW; fCEvd[r] = y.CEvd; fele[r] = y.e_ele; fCEclmb[r] = y.CEclmb;
+      }
+      const double v0_vdw = first.CEvd, v0_ele = first.CEclmb;
+      fh[r] = fh[r - 1]; fvdw[r] = fvdw[r - 1]; fCEvd[r] = fCEvd[r - 1]; fele[r] = fele[r - 1]; fCEclmb[r] = fCEclmb[r - 1];
+      const double vlast_vdw = fCEvd[r - 1], vlast_ele = fele[r - 1];
+      natural_cubic_spline(&h[1], &fh[1], L.at(nt, i, j, 0) + 1, tab + 1);
+      complete_cubic_spline(&h[1], &fvdw[1], v0_vdw, vlast_vdw, L.at(nt, i, j, 1) + 1, tab + 1);
+      natural_cubic_spline(&h[1], &fCEvd[1], L.at(nt, i, j, 2) + 1, tab + 1);
+      complete_cubic_spline(&h[1], &fele[1], v0_ele, vlast_ele, L.at(nt, i, j, 3) + 1, tab + 1);
+      natural_cubic_spline(&h[1], &fCEclmb[1], L.at(nt, i, j, 4) + 1, tab + 1);
+    }
+}
+
+// Tabulated_vdW_Coulomb_Energy evaluation (:498-519) in the production full-list / owner-computes form of a9
+static void nonbonded_tabulated(System& s) {
+  Params& P = s.prm;
+  if (P.lookup.n != P.tabulate + 2) build_lookup_tables(P);
+  const Lookup& L = P.lookup;
+  const int nt = P.nt;
+  double e_vdW_tot = 0, e_ele_tot = 0;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+#pragma omp parallel for schedule(dynamic, 32) reduction(+ : e_vdW_tot, e_ele_tot, v0, v1, v2, v3, v4, v5)
+  for (int i = 0; i < s.n; i++) {
+    int ti = s.type[i];
+    if (ti < 0) continue;
+    double fi[3] = {0, 0, 0};
+    for (long pj = s.nb_off[i]; pj < s.nb_off[i + 1]; pj++) {
+      int j = s.nb[pj];
+      int tj = s.type[j];
+      double dv[3] = {s.x[3 * j] - s.x[3 * i], s.x[3 * j + 1] - s.x[3 * i + 1], s.x[3 * j + 2] - s.x[3 * i + 2]};
+      double r2 = dot3(dv, dv);
+      if (!(r2 <= P.nonb_cut * P.nonb_cut)) continue;
+      if (tj < 0) continue;
+      double r_ij = sqrt(r2);
+      const int tmin = std::min(ti, tj), tmax = std::max(ti, tj);
+      int r = (int)(r_ij * L.inv_dx);
+      if (r == 0) ++r;
+      const double base = (double)(r + 1) * L.dx;
+      const double dif = r_ij - base;
+      auto ev = [&](int which) {
+        const SplineCoef& c = L.at(nt, tmin, tmax, which)[r];
+        return ((c.d * dif + c.c) * dif + c.b) * dif + c.a;
+      };
+      const double qq = s.q[i] * s.q[j];
+      const double e_vdW = ev(1), e_ele = ev(3) * qq, CEvd = ev(2), CEclmb = ev(4) * qq;
+      e_vdW_tot += 0.5 * e_vdW;
+      e_ele_tot += 0.5 * e_ele;
+      double fpair = -(CEvd + CEclmb);
+      v0 += 0.5 * dv[0] * dv[0] * fpair; v1 += 0.5 * dv[1] * dv[1] * fpair; v2 += 0.5 * dv[2] * dv[2] * fpair;
+      v3 += 0.5 * dv[0] * dv[1] * fpair; v4 += 0.5 * dv[0] * dv[2] * fpair; v5 += 0.5 * dv[1] * dv[2] * fpair;
+      for (int t = 0; t < 3; t++) fi[t] += -(CEvd + CEclmb) * dv[t];
+    }
+    for (int t = 0; t < 3; t++) s.fCd[4 * i + t] += fi[t];
+    v0 += s.x[3 * i] * fi[0]; v1 += s.x[3 * i + 1] * fi[1]; v2 += s.x[3 * i + 2] * fi[2];
+    v3 += s.x[3 * i] * fi[1]; v4 += s.x[3 * i] * fi[2];     v5 += s.x[3 * i + 1] * fi[2];
+  }
+  s.en.e_vdW += e_vdW_tot;
+  s.en.e_ele += e_ele_tot;
+  s.virial[0] += v0; s.virial[1] += v1; s.virial[2] += v2; s.virial[3] += v3; s.virial[4] += v4; s.virial[5] += v5;
+}
+
 // a9: vdW_Coulomb_Energy_Full_C  serial twin reaxc_nonbonded_sw64.c:40-258
 //     (full list, local i only, force on i only; pair virial via ev_tally_full reaxc_inlines_sw64.h:178-222)
 void nonbonded(System& s) {
+  if (s.prm.tabulate > 0) { nonbonded_tabulated(s); return; }   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables
   const Params& P = s.prm;
   const double p_vdW1 = P.gp[28], p_vdW1i = 1.0 / p_vdW1;
   const double* Tap = P.Tap;

@@ -37,6 +37,17 @@ struct Tbp {
   double v13cor, ovc;
 };
 
+// cubic-spline tables of the tabulated long-range mode (LR_lookup_table, reaxc_ctypes_sunway.h:846-860):
+// per type pair (i <= j) five tables H, vdW, CEvd, ele, CEclmb of n = tabulate + 2 coefficient sets
+struct SplineCoef { double a, b, c, d; };
+struct Lookup {
+  int n = 0;
+  double dx = 0, inv_dx = 0;
+  std::vector<SplineCoef> tables;
+  SplineCoef* at(int nt, int i, int j, int which) { return &tables[(((size_t)i * nt + j) * 5 + which) * n]; }
+  const SplineCoef* at(int nt, int i, int j, int which) const { return &tables[(((size_t)i * nt + j) * 5 + which) * n]; }
+};
+
 struct Thbp { double theta_00, p_val1, p_val2, p_coa1, p_val7, p_pen1, p_val4; };
 struct ThbHeader { int cnt; Thbp prm[5]; };
 struct Fbp { double V1, V2, V3, p_tor1, p_cot1; };
@@ -57,6 +68,7 @@ struct Params {
   double bond_cut = 5.0, hbond_cut = 7.5, bg_cut = 0.3, thb_cut = 0.001, thb_cutsq = 0.00001;
   int tabulate = 0, lgflag = 0, enobondsflag = 1, energy_update_freq = 0;
   double Tap[8];
+  Lookup lookup;               // built on first use when tabulate > 0
   // LAMMPS type (1-based) -> ff element index, or -1 (NULL)
   std::vector<int> map;
 

@@ -55,6 +55,7 @@ struct System {
 
 void build_bond_list(System& s);       // a4  Init_Forces_noQEq_Full / BOp_single
 void build_hbond_list(System& s);      // a5
+void build_lookup_tables(Params& P);    // a9' (dead code in the reference, restated)
 void nonbonded(System& s);             // a9
 void bond_orders(System& s);           // a6
 void bonds_atom_energy(System& s);     // a7

@@ -298,6 +298,26 @@ long rxb_parse_dump(const char* control_file, const char* ffield_file, int ntype
   return rc == 0 ? count : -1;
 }
 
+long rxb_lookup_dump(const char* control_file, const char* ffield_file, int ntypes, const char* const* elements, int* n_out,
+                     double* out, long cap) {
+  long count = -1;
+  int rc = guard([&] {
+    rxb::ForceField ff;
+    std::string e = ff.load_control(control_file);
+    if (e.empty()) e = ff.load_ffield(ffield_file);
+    if (e.empty()) e = ff.set_elements(ntypes, elements);
+    if (!e.empty()) throw std::runtime_error(e);
+    ff.derive();
+    if (ff.ctl.tabulate <= 0) { count = 0; if (n_out) *n_out = 0; return; }
+    int n = 0; double dx = 0;
+    std::vector<double> v = ff.lookup_tables(&n, &dx);
+    if (n_out) *n_out = n;
+    if (out) for (long i = 0; i < (long)v.size() && i < cap; i++) out[i] = v[i];
+    count = (long)v.size();
+  });
+  return rc == 0 ? count : -1;
+}
+
 int rxb_dist_unique_id(char* out128) { return guard([&] { System::dist_unique_id(out128); }); }
 int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px, int py, int pz) {
   return guard([&] { h->sys->dist_init(rank, world, id128, px, py, pz); });

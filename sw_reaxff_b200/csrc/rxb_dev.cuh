@@ -24,6 +24,10 @@ struct DevParams {  // pointers into one HBM blob
   const AngleSet* angle;
   const TorsPar* tors;
   const HbPar* hb;
+  // tabulated long-range mode (ctl.tabulate > 0): 128-byte records [type pair][interval]{CEvd, CEclmb, e_vdW, e_ele}
+  const double4* lut;
+  int lut_n;
+  double lut_dx, lut_inv_dx;
 };
 
 // energy accumulator slots (simulation_data::my_en order used by pvector, pair_reaxc_sunway.cpp:657-670)

@@ -226,6 +226,94 @@ k_nonbonded(DevView v, DevParams P) {
   }
 }
 
+// Tabulated long-range mode (control: tabulate_long_range N): the same owner-computes full-list sweep, but the pair terms
+// come from the cubic-spline records built by ForceField::lookup_tables (evaluation form of Tabulated_vdW_Coulomb_Energy,
+// reaxc_nonbonded_sunway.cpp:498-519).  One or two 64-byte reads per pair from a table that stays L2-resident
+// (nt^2 x (N+2) x 128 B = 20 MB for N = 10000) replace 2 log + 3 exp + cbrt; the kernel becomes L2-gather bound.
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <bool EV>
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_nonbonded_tab(DevView v, DevParams P) {
+  __shared__ double sh[9][kWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
+  const int nt = P.nt, ln = P.lut_n;
+  const double dx = P.lut_dx, inv_dx = P.lut_inv_dx;
+  double e_vdw = 0, e_ele = 0, e_pol = 0, vir[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = wg; i < v.n; i += nwg) {
+    const int ti = v.type[i];
+    if (ti < 0) continue;
+    const double4 pi = v.xq[i];
+    const long long beg = v.vl_off[i];
+    const int num = v.far_num[i];
+    double fx = 0, fy = 0, fz = 0;
+    for (int k0 = 0; k0 < num; k0 += 32) {
+      const int k = k0 + lane;
+      if (k >= num) continue;
+      const int j = v.far_idx[beg + k];
+      const int tj = v.type[j];
+      if (tj < 0) continue;
+      const double4 pj = v.xq[j];
+      const double dx_ = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      const double r2 = dist2_rn(dx_, dy, dz);
+      if (!(r2 <= nonb_cut2)) continue;
+      const double r_ij = sqrt(r2);
+      int r = (int)(r_ij * inv_dx);
+      if (r == 0) ++r;
+      const double dif = r_ij - (double)(r + 1) * dx;
+      const double4* rec = P.lut + ((size_t)(ti * nt + tj) * ln + r) * 4;
+      const double4 cv = ldg4(rec), cc = ldg4(rec + 1);
+      const double qq = pi.w * pj.w;
+      const double CEvd = ((cv.w * dif + cv.z) * dif + cv.y) * dif + cv.x;
+      const double CEclmb = (((cc.w * dif + cc.z) * dif + cc.y) * dif + cc.x) * qq;
+      const double ftot = CEvd + CEclmb;
+      fx += ftot * dx_; fy += ftot * dy; fz += ftot * dz;
+      if (EV) {
+        const double4 ce = ldg4(rec + 2), cl = ldg4(rec + 3);
+        e_vdw += 0.5 * (((ce.w * dif + ce.z) * dif + ce.y) * dif + ce.x);
+        e_ele += 0.5 * qq * (((cl.w * dif + cl.z) * dif + cl.y) * dif + cl.x);
+        const double fpair = -ftot;
+        vir[0] += 0.5 * dx_ * dx_ * fpair; vir[1] += 0.5 * dy * dy * fpair; vir[2] += 0.5 * dz * dz * fpair;
+        vir[3] += 0.5 * dx_ * dy * fpair; vir[4] += 0.5 * dx_ * dz * fpair; vir[5] += 0.5 * dy * dz * fpair;
+      }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+      atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
+      if (EV) {
+        e_pol += kKcalToEv * (P.atom[ti].chi * pi.w + (P.atom[ti].eta / 2.) * pi.w * pi.w);
+        vir[0] -= pi.x * fx; vir[1] -= pi.y * fy; vir[2] -= pi.z * fz;
+        vir[3] -= pi.x * fy; vir[4] -= pi.x * fz; vir[5] -= pi.y * fz;
+      }
+    }
+  }
+  if (EV) {
+    double vals[9] = {e_vdw, e_ele, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5], e_pol};
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const double s = warp_sum(vals[k]);
+      if (lane == 0) sh[k][wib] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      double s = 0;
+      for (int w = 0; w < kWarps; w++) s += sh[threadIdx.x][w];
+      if (s != 0.0) {
+        if (threadIdx.x == 0) atomicAdd(&v.en[E_VDW], s);
+        else if (threadIdx.x == 1) atomicAdd(&v.en[E_ELE], s);
+        else if (threadIdx.x == 8) atomicAdd(&v.en[E_POL], s);
+        else atomicAdd(&v.virial[threadIdx.x - 2], s);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* qeq_tap, const double* shld, double swb,
@@ -244,7 +332,10 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
 
 void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st) {
   if (v.n == 0) return;
-  if (evflag) k_nonbonded<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  if (P.lut) {   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables (reaxc_forces_sunway.cpp:148-160)
+    if (evflag) k_nonbonded_tab<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+    else k_nonbonded_tab<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  } else if (evflag) k_nonbonded<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
   else k_nonbonded<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
   s.kernel_launches++;
 }

@@ -11,6 +11,8 @@ namespace rxb {
 
 constexpr int kMaxAngleSets = 5;  // MAX_3BODY_PARAM, reaxc_defs_sunway.h:113
 
+constexpr double kCeleConst = 332.06371;   // C_ele, reaxc_defs_sunway.h:62
+
 struct AtomPar {  // single_body_parameters
   double r_s, r_pi, r_pi_pi;
   double valency, valency_e, valency_boc, valency_val, nlp_opt, mass;
@@ -65,6 +67,8 @@ struct ForceField {
   std::string set_elements(int ntypes, const char* const* names); // "" on success
   void derive();                                                  // taper + hoisted constants
   std::vector<double> dump() const;                               // canonical flat dump (parity tests)
+  // tabulated long-range mode (ctl.tabulate > 0): [nt*nt][n = tabulate+2][4 sets CEvd,CEclmb,e_vdW,e_ele][a,b,c,d]
+  std::vector<double> lookup_tables(int* n_out, double* dx_out) const;
 };
 
 }  // namespace rxb

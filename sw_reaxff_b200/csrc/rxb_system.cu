@@ -298,6 +298,14 @@ void System::upload_params() {
   dp_.angle = reinterpret_cast<const AngleSet*>(param_blob_.p + o_angle);
   dp_.tors = reinterpret_cast<const TorsPar*>(param_blob_.p + o_tors);
   dp_.hb = reinterpret_cast<const HbPar*>(param_blob_.p + o_hb);
+  dp_.lut = nullptr; dp_.lut_n = 0; dp_.lut_dx = dp_.lut_inv_dx = 0.0;
+  if (ff.ctl.tabulate > 0) {
+    int ln = 0; double ldx = 0;
+    const std::vector<double> t = ff.lookup_tables(&ln, &ldx);
+    lut_d.resize(t.size() / 4);
+    RXB_CUDA(cudaMemcpy(lut_d.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    dp_.lut = lut_d.p; dp_.lut_n = ln; dp_.lut_dx = ldx; dp_.lut_inv_dx = ff.ctl.tabulate / ff.ctl.nonb_cut;
+  }
   // fix qeq/reax shielding: shld = (gamma_i gamma_j)^-1.5 from Pair::extract("gamma"), fix_qeq_reax_sunway.cpp:440-454
   std::vector<double> sh((size_t)nt * nt);
   for (int i = 0; i < nt; i++)

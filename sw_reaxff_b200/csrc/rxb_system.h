@@ -231,6 +231,7 @@ class System {
   DBuf<double> q_Hdia_inv;
   DBuf<double> q_scal;               // device scalars
   DBuf<double> shld_d;               // nt*nt shielding (gamma_i gamma_j)^-1.5
+  DBuf<double4> lut_d;               // spline tables of the tabulated long-range mode
   // md
   DBuf<double> v_d, mass_d, x_stage;
   DBuf<int> ghost_shift;             // per ghost 3 ints

@@ -16,6 +16,9 @@ scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 T = float(sys.argv[4]) if len(sys.argv) > 4 else 300.0
 box, x, t, tag = tatb_cell(nx, nx, nx, scale=scale)
 v = maxwell_velocities(t, T, 12345)
+tab = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+if tab > 0:
+    CONTROL = control_variant("/tmp/control.tab%d" % tab, tab)
 r = Rxb(0)
 r.pair_settings(CONTROL)
 r.pair_coeff(FFIELD, ELEMENTS)

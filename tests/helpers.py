@@ -310,6 +310,15 @@ def _p(a):
 _keep = []  # keep temporaries alive across the ctypes call (bounded: cleared opportunistically)
 
 
+def control_variant(path, tabulate):
+    """Copy of the TATB control file with `tabulate_long_range N` (spline-table mode of the long-range terms)."""
+    src = open(CONTROL).read().splitlines()
+    src = [("tabulate_long_range     %d" % tabulate) if l.startswith("tabulate_long_range") else l for l in src]
+    with open(path, "w") as f:
+        f.write("\n".join(src) + "\n")
+    return str(path)
+
+
 def ffield_variant(path, vdw_type):
     """Write a copy of the TATB force field whose element block selects another van der Waals form
     (reaxc_ffield_sunway.cpp:240-293): 3 = shielding + inner wall (rcore2/ecore2/acore2 set), 2 = inner wall only

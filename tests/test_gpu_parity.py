@@ -359,3 +359,30 @@ def test_null_mapped_element_is_ignored_like_the_reference():
     assert rel(res["pvector"], pvector_from_oracle(eo)) < 1e-8
     assert rel(res["f"], o.forces()) < 1e-7
     assert np.array_equal(qg[:n], o.q()[:n])
+
+
+def test_tabulated_long_range_mode(tmp_path):
+    """control: tabulate_long_range 10000 -> the nonbonded kernel evaluates the cubic-spline tables (a9' / f4).  GPU vs
+    the oracle's table mode to 1e-8, and — because the spline error at N = 10000 is ~1e-12 — also vs the analytic form."""
+    from sw_reaxff_b200 import Rxb
+    ctl = H.control_variant(tmp_path / "control.tab", 10000)
+    out = {}
+    for name, control in (("table", ctl), ("analytic", H.CONTROL)):
+        cfg = H.static_config(1, 1, 1, perturb=0.1, seed=21, qeq=True, oracle=H.Oracle(control=control))
+        o = cfg["oracle"]
+        n, x, ty, tg, owner, q = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"], cfg["q"]
+        o.set_atoms(n, x, ty, tg, q)
+        o.build_neighbors(12.5)
+        o.compute()
+        out[name] = (o.energies()[0], o.forces(), o.energies()[1])
+    r = Rxb(0)
+    r.pair_settings(ctl)
+    r.pair_coeff(H.FFIELD, H.ELEMENTS)
+    r.set_atoms(n, x, ty, tg, q, owner)
+    r.neigh_build()
+    res = r.pair_compute(True, True)
+    for name, tol in (("table", 1e-8), ("analytic", 1e-8)):
+        eo, fo, vo = out[name]
+        assert rel(res["pvector"], pvector_from_oracle(eo)) < tol, name
+        assert rel(res["f"], fo) < 10 * tol, name
+        assert rel(res["virial"], vo) < 10 * tol, name

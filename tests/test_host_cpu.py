@@ -112,3 +112,34 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pkg, "librxb200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_lookup_tables_equal_oracle_and_track_the_analytic_form(tmp_path):
+    """Tabulated long-range mode (control: tabulate_long_range N; reaxc_lookup_sunway.cpp:157-285, dead code in the
+    reference): the product's table builder (host C++, device layout) against the oracle's restatement."""
+    import helpers as H
+    N = 2000
+    ctl = H.control_variant(tmp_path / "control.tab", N)
+    L = lib()
+    L.rxb_lookup_dump.restype = C.c_long
+    arr = (C.c_char_p * 4)(*[e.encode() for e in H.ELEMENTS])
+    n = C.c_int()
+    cnt = L.rxb_lookup_dump(ctl.encode(), H.FFIELD.encode(), 4, arr, C.byref(n), None, C.c_long(0))
+    assert cnt == 16 * (N + 2) * 16 and n.value == N + 2
+    mine = np.zeros(cnt)
+    L.rxb_lookup_dump(ctl.encode(), H.FFIELD.encode(), 4, arr, C.byref(n), mine.ctypes.data_as(C.c_void_p), C.c_long(cnt))
+    mine = mine.reshape(4, 4, N + 2, 4, 4)
+    o = H.Oracle(control=ctl)
+    o.L.orc_lookup_tables.restype = C.c_int
+    assert o.L.orc_lookup_tables(o.h, None) == N + 2
+    orc = np.zeros((4, 4, 5, N + 2, 4))
+    o.L.orc_lookup_tables(o.h, orc.ctypes.data_as(C.c_void_p))
+    for t_mine, t_orc in ((0, 2), (1, 4), (2, 1), (3, 3)):          # CEvd, CEclmb, e_vdW, e_ele
+        for i in range(4):
+            for j in range(i, 4):
+                a = mine[i, j, 1:N + 1, t_mine, :]; b = orc[i, j, t_orc, 1:N + 1, :]
+                scale = np.abs(b).max(axis=0) + 1e-300
+                assert (np.abs(a - b) / scale).max() < 1e-9, (t_mine, i, j)
+                assert np.array_equal(mine[j, i, :, t_mine, :], mine[i, j, :, t_mine, :])
+    # tabulate 0 -> no tables
+    assert L.rxb_lookup_dump(H.CONTROL.encode(), H.FFIELD.encode(), 4, arr, C.byref(n), None, C.c_long(0)) == 0

@@ -175,3 +175,22 @@ def test_bonds_table_and_species_of_the_tatb_crystal():
     for i, row in table.items():                # every bond is listed from both ends with the same (printed) bond order
         for j, bo in row.items():
             assert table[j][i] == bo
+
+
+@pytest.mark.parametrize("N,bound", [(1000, 1e-7), (10000, 1e-11)])
+def test_tabulated_long_range_mode_deviation_from_analytic(N, bound, tmp_path):
+    """a9' / f4: the spline-table evaluation is an approximation of the analytic pair terms; its error is measured here
+    (forces relative to the largest nonbonded force, energies relative): 7.6e-9 at N = 1000, 8.7e-13 at N = 10000."""
+    ctl = H.control_variant(tmp_path / "control.tab", N)
+    res = {}
+    for name, c in (("analytic", H.CONTROL), ("table", ctl)):
+        cfg = H.static_config(1, 1, 1, perturb=0.1, seed=3, qeq=True, oracle=H.Oracle(control=c))
+        o, n = cfg["oracle"], cfg["n"]
+        o.set_atoms(n, cfg["x"], cfg["type"], cfg["tag"], cfg["q"])
+        o.build_neighbors(12.5)
+        o.phase(0); o.phase(3)
+        e, _ = o.energies()
+        res[name] = (e[10], e[11], o.forces()[:n].copy())
+    a, b = res["analytic"], res["table"]
+    assert abs(a[0] - b[0]) < bound * abs(a[0]) and abs(a[1] - b[1]) < bound * abs(a[1])
+    assert np.abs(a[2] - b[2]).max() < bound * np.abs(a[2]).max()
