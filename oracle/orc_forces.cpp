@@ -5,6 +5,14 @@
 // listed in SURVEY.md §8a:  (1) e_vdW/e_ele take 1/2 per directed pair (stock-correct) instead of
 // the reference's double-counted my_en (reaxc_nonbonded_cpe.h:314,346);  (2) e_pol is the plain sum,
 // not the running-prefix sum of reaxc_multi_body_sw64.c:102-103.
+//
+// Pinning (tests/test_oracle_vs_ref.py, against the reference's own code compiled unmodified into oracle/_ref/libref.so):
+//   build_bond_list (BO') == BOp_single;  valence_torsion == Torsion_Angles (serial virial path);
+//   hydrogen_bonds == Hydrogen_Bonds (serial virial path);  add_dbond_forces == Add_dBond_to_Forces;
+//   bonds_atom_energy == Merge_Bonds_Atom_Energy_C_New;  nonbonded == vdW_Coulomb_Energy_Full_C_test_err  — all to 1e-10.
+//   PARITY UNPINNED by reference execution: bond_orders (a6; the reference's serial BO() body is dead code behind `return;`)
+//   and the tabulated mode (a9', commented out in the reference).  Those are pinned by finite-difference forces of the
+//   total energy, BO symmetry and the invariants in tests/test_oracle.py.
 #include <algorithm>
 #include <cmath>
 #include <cstring>

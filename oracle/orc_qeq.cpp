@@ -6,6 +6,9 @@
 //   init_matvec :696-717 (s cubic / t quadratic extrapolation), sparse_matvec :1601-1622,
 //   CG_v2 :983-1167 (pipelined Jacobi-PCG, imax 200), calculate_Q :1697-1755.
 // Single rank: forward_comm_fix == copy owner -> ghost (ghost_owner map).
+// PARITY UNPINNED by reference execution: FixQEqReaxSunway needs the LAMMPS core and its H / SpMV kernels exist only as
+// Sunway slave-core code.  Pinned by restatement and by tests/test_oracle.py (H s = -chi and H t = -1 residuals, sum q = 0,
+// Hellmann-Feynman finite differences with consistent constants).
 #include <cmath>
 #include <cstdio>
 

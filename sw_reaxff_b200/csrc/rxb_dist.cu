@@ -8,11 +8,13 @@
 //     (x, v, q, s_hist, t_hist, tag, type), then selects its new local atoms and its ghost images from the gathered set
 //     with two count/scan/fill kernels.  One collective instead of 6-direction staged swaps: on NVSwitch every peer is one
 //     hop at full bandwidth, and the gathered set makes migration of s_hist/t_hist/v trivial;
-//   * forward (x,q), CG halo (d as double2): all-gather of the local slab, ghosts read their source slot (+ image shift);
-//   * reverse (f): scatter-add into the global slot array, ncclReduceScatter;
+//   * forward (x,q), CG halo (d as double2), reverse (f): peer-to-peer boundary exchange.  At every exchange each rank
+//     lists, per peer, the local atoms that peer holds as ghosts (dist_build_plan); a step then packs those atoms,
+//     issues one grouped ncclSend/ncclRecv per peer pair and unpacks (+ image shift) — only the boundary layer moves
+//     (8-24 B per ghost).  rxb_dist_set_p2p(0) falls back to whole-slab all-gathers / reduce-scatter for comparison;
 //   * CG dots / sums / energies: ncclAllReduce on the device scalars, stream-ordered, no host sync.
-// Round-1 status: functional and parity-tested against the single-GPU path; the per-iteration halo moves the whole slab
-// (16 B/atom) instead of only the boundary layer — next step is peer-to-peer boundary exchange.
+// Parity-tested against the single-GPU path (positions, forces, charges, energies, species; incl. migration).  What is
+// left on the table at N > 1 is NCCL launch latency per CG iteration (halo + all-reduce are serial with the SpMV).
 #include <cub/cub.cuh>
 #include <nccl.h>
 

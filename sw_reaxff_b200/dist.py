@@ -2,9 +2,11 @@
 hand-off to the library, max-over-ranks timing.  The halo exchange / all-reduce themselves run inside librxb200.so
 (csrc/rxb_dist.cu); torch.distributed is only the rendezvous + result plumbing.
 
-Round-1 status: spatial decomposition over px*py*pz bricks with NCCL all-gather halos (whole local slab per exchange),
-reduce-scatter force reverse and device-side all-reduce of the CG dots; verified against the single-GPU path at N=2
-(tests/gpu_dist_check.py).  Host-side logic in this file is covered by the world_size-2 gloo test (tests/test_dist_gloo.py).
+Status: spatial decomposition over px*py*pz bricks; migration records all-gathered at reneighbouring, peer-to-peer
+boundary halos (grouped ncclSend/ncclRecv) for x/q, the CG direction and the reverse force sum, device-side all-reduce of
+the CG dots; verified against the single-GPU path at N = 2 and 4 incl. atom migration and fix reax/c/species
+(tests/gpu_dist_check.py, profiles/r01_dist_checks.txt); weak scaling 117 M atom-steps/s on 8 GPUs.  Host-side logic in
+this file is covered by the world_size-2 gloo test (tests/test_dist_gloo.py).
 """
 import os
 import time
