@@ -163,50 +163,6 @@ def run_reference(args, rank, world):
     }))
 
 
-# ----------------------------------------------------------------------------------------------------------------
-class PluginStepper:
-    """Drives the LAMMPS-facing C ABI exactly as the LAMMPS core would: host x in, host f out, every step."""
-
-    def __init__(self, r, H, box, x, v, t, tag):
-        self.r, self.H = r, H
-        o = H.Oracle()   # only used to generate the periodic ghost set (LAMMPS Comm::borders stand-in, CPU, untimed)
-        o.md_init(box, x, v, t, tag, qeq=False)
-        xall, ty, tg, owner = o.md_ghosts()
-        del o
-        self.n, self.owner = len(x), owner.astype(np.int64)
-        self.x = np.ascontiguousarray(xall)
-        self.shift = self.x[self.n:] - self.x[self.owner]
-        self.v = np.ascontiguousarray(v.copy())
-        self.f_all = np.zeros_like(self.x)
-        self.f = np.zeros((self.n, 3))
-        self.dtfm = (0.5 * 0.0625 * FTM2V / H.MASS[t])[:, None]
-        r.set_atoms(self.n, self.x, ty, tg, None, owner)
-        r.neigh_build()
-        self.step_no = 0
-        self.force()
-
-    def force(self):
-        r = self.r
-        r.qeq_pre_force()
-        ev = self.step_no % 5 == 0
-        r.pair_compute(ev, ev, f_out=self.f_all)
-        f = self.f_all[:self.n].copy()
-        for k in range(3):  # reverse_comm
-            f[:, k] += np.bincount(self.owner, weights=self.f_all[self.n:, k], minlength=self.n)
-        self.f = f
-
-    def step(self):
-        self.step_no += 1
-        self.v += self.dtfm * self.f
-        self.x[:self.n] += 0.0625 * self.v
-        self.x[self.n:] = self.x[self.owner] + self.shift          # forward_comm
-        self.r.set_positions(self.x)                                # H2D from pinned staging
-        if self.step_no % 5 == 0:
-            self.r.neigh_build()
-        self.force()                                                # D2H of the forces inside
-        self.v += self.dtfm * self.f
-
-
 def run_b200(args, rank, world, local_rank):
     import torch
     import helpers as H

@@ -123,7 +123,7 @@ int rxb_neigh_build(rxb_handle* h) { return guard([&] { h->sys->build_neighbors(
 
 int rxb_qeq_pre_force(rxb_handle* h, int* matvecs2) {
   return guard([&] {
-    h->sys->qeq_pre_force();
+    h->sys->plugin_qeq_pre_force();
     if (matvecs2) { matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t; }
   });
 }
@@ -152,7 +152,7 @@ static void fill_pvector(const double* e, double* pvector, double* eng2) {
 int rxb_pair_compute(rxb_handle* h, int eflag, int vflag, double* f_out, double* pvector, double* eng2, double* virial6) {
   return guard([&] {
     System& s = *h->sys;
-    s.compute(eflag != 0, vflag != 0);
+    s.plugin_compute(eflag != 0, vflag != 0);
     if (f_out) s.get_forces(f_out);
     fill_pvector(s.energies, pvector, eng2);
     if (virial6) memcpy(virial6, s.virial, 6 * sizeof(double));

@@ -366,6 +366,7 @@ void System::h2d(void* dst, const void* src, size_t bytes, size_t stage_off_doub
 void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype, const int* tg, const double* q,
                        const int* owner_in) {
   RXB_CUDA(cudaSetDevice(device_));
+  if (chain_inflight_) cancel_inflight();
   n = nlocal; N = nlocal + nghost;
   ensure_atom_capacity();
   std::vector<int> hown;
@@ -403,6 +404,7 @@ void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype
 // when it is page-locked memory; pageable memory is staged before returning.
 void System::set_positions(const double* x_host) {
   RXB_CUDA(cudaSetDevice(device_));
+  if (chain_inflight_) cancel_inflight();
   pin((size_t)3 * N);
   x_stage.resize((size_t)3 * N);
   h2d(x_stage.p, x_host, (size_t)3 * N * sizeof(double), 0);
@@ -635,7 +637,11 @@ void System::after_far_hook() {
   RXB_CUDA(cudaEventRecord(ev_join_, st2_));
 }
 
-void System::md_force_overlapped(bool ev) {
+// The step's force evaluation in two halves so that the bond list -> bond order -> bonded chain (second stream) overlaps
+// the bandwidth-bound QEq solve.  The resident run calls both back to back; the plugin path calls the front half from
+// fix qeq/reax's pre_force hook and the back half from the pair style's compute hook.
+void System::overlapped_front() {
+  if (chain_inflight_) cancel_inflight();
   DevView v = view();
   update_shadow(st_);
   RXB_CUDA(cudaMemsetAsync(f.p, 0, (size_t)3 * N * sizeof(double), st_));
@@ -648,12 +654,24 @@ void System::md_force_overlapped(bool ev) {
   launch_bond_orders(*this, v, dp_, st2_);
   launch_bonded_part1(*this, v, dp_, st2_);
   hook_after_far_ = true;
+  chain_inflight_ = true;
   qeq_pre_force();                       // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
+}
+
+void System::cancel_inflight() {         // the atoms change before the pair style consumed the chain: just join the streams
+  RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
+  chain_inflight_ = false;
+}
+
+void System::overlapped_back(bool eflag, bool vflag) {
+  const bool ev = eflag || vflag;
+  DevView v = view();
+  chain_inflight_ = false;
   qeq_ran_this_step_ = false;
   launch_nonbonded(*this, v, dp_, ev, st_);
   RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
   launch_dbond(*this, v, dp_, st_);
-  if (ev) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
+  if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
   int h[2], wk[4];
   RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
@@ -668,10 +686,25 @@ void System::md_force_overlapped(bool ev) {
   num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
   if ((overflow_flag & 2) || wk[0] > cap_ang || wk[1] > cap_tor || wk[2] > cap_hb) {
     qeq_ran_this_step_ = true;           // far list and charges of this step are valid: replay only the force phase
-    compute(ev, ev);                     // sequential path grows the arrays and replays
+    compute(eflag, vflag);               // sequential path grows the arrays and replays
   } else if (overflow_flag & ~2) {
     throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
   }
+}
+
+void System::md_force_overlapped(bool ev) {
+  overlapped_front();
+  overlapped_back(ev, ev);
+}
+
+// plugin path (C ABI): fix qeq/reax pre_force, then pair compute
+void System::plugin_qeq_pre_force() {
+  if (overlap && !profile && !dist_ && n > 0) overlapped_front();
+  else { if (chain_inflight_) cancel_inflight(); qeq_pre_force(); }
+}
+void System::plugin_compute(bool eflag, bool vflag) {
+  if (chain_inflight_) overlapped_back(eflag, vflag);
+  else compute(eflag, vflag);
 }
 
 void System::md_force() {

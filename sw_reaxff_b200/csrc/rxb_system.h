@@ -122,6 +122,8 @@ class System {
   void qeq_set_history(const double* s_hist, const double* t_hist);  // [n][5] host
   void qeq_get_history(double* s_hist, double* t_hist);
   void qeq_pre_force();
+  void plugin_qeq_pre_force();          // C ABI entry: QEq with the bonded chain started on the second stream
+  void plugin_compute(bool eflag, bool vflag);
   int matvecs_s = 0, matvecs_t = 0;
   long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
 
@@ -248,6 +250,10 @@ class System {
   bool hook_after_far_ = false;
   void after_far_hook();
   void md_force_overlapped(bool ev);
+  void overlapped_front();
+  void overlapped_back(bool eflag, bool vflag);
+  void cancel_inflight();
+  bool chain_inflight_ = false;          // the bonded chain of this step is queued on st2_ and not yet consumed
   std::vector<cudaEvent_t> ev_pool_;
   struct Pending { int which; int a, b; };
   std::vector<Pending> ev_pending_;

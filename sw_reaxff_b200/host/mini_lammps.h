@@ -52,6 +52,7 @@ struct Comm {   // single rank: ghosts are periodic images
   double cutghostuser = 0.0;
   std::vector<int> ghost_owner;
   std::vector<double> ghost_shift;               // [nghost][3] cartesian
+  std::vector<size_t> block_off;                 // ghost range of every image shift (distinct owners inside a block)
   void borders(const Domain& d, Atom& a, double cutghost);   // (re)creates the ghost atoms
   void forward_comm(Atom& a) const;              // x of ghosts
   void reverse_comm(Atom& a) const;              // f of ghosts -> owners
