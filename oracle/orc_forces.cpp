@@ -10,9 +10,10 @@
 //   build_bond_list (BO') == BOp_single;  valence_torsion == Torsion_Angles (serial virial path);
 //   hydrogen_bonds == Hydrogen_Bonds (serial virial path);  add_dbond_forces == Add_dBond_to_Forces;
 //   bonds_atom_energy == Merge_Bonds_Atom_Energy_C_New;  nonbonded == vdW_Coulomb_Energy_Full_C_test_err  — all to 1e-10.
-//   PARITY UNPINNED by reference execution: bond_orders (a6; the reference's serial BO() body is dead code behind `return;`)
-//   and the tabulated mode (a9', commented out in the reference).  Those are pinned by finite-difference forces of the
-//   total energy, BO symmetry and the invariants in tests/test_oracle.py.
+//   bond_orders == the serial body of BO() (reaxc_bond_orders_sunway.cpp:460-774, reached through
+//   oracle/ref/stubs/prelude_bo_serial.h) to 1e-11.
+//   PARITY UNPINNED by reference execution: only the tabulated mode (a9', commented out in the reference); its deviation
+//   from the analytic form is measured in tests/test_oracle.py.
 #include <algorithm>
 #include <cmath>
 #include <cstring>

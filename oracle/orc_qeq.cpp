@@ -6,9 +6,10 @@
 //   init_matvec :696-717 (s cubic / t quadratic extrapolation), sparse_matvec :1601-1622,
 //   CG_v2 :983-1167 (pipelined Jacobi-PCG, imax 200), calculate_Q :1697-1755.
 // Single rank: forward_comm_fix == copy owner -> ghost (ghost_owner map).
-// PARITY UNPINNED by reference execution: FixQEqReaxSunway needs the LAMMPS core and its H / SpMV kernels exist only as
-// Sunway slave-core code.  Pinned by restatement and by tests/test_oracle.py (H s = -chi and H t = -1 residuals, sum q = 0,
-// Hellmann-Feynman finite differences with consistent constants).
+// Pinned (tests/test_oracle_vs_ref.py::test_qeq_equals_reference_fix_qeq_reax): the reference's FixQEqReaxSunway, compiled
+// unmodified against a LAMMPS-core stand-in (oracle/ref/ref_qeq.cpp), gives the same CG_v2 iteration counts, charges
+// (1e-10), s/t and histories (1e-9) and H rows (1e-13) on identical inputs.  Its H build and SpMV exist only as Sunway
+// slave-core kernels; the harness supplies serial loops for those two.
 #include <cmath>
 #include <cstdio>
 

@@ -10,6 +10,11 @@
 //                                         under-coordination energies (a7)
 //   * vdW_Coulomb_Energy_Full_C_test_err  reaxc_nonbonded_sw64.c:40-258 (MPE-side serial C)   tapered vdW + Coulomb (a9)
 //   * Init_Taper                          reaxc_init_md_sunway.cpp:100-136           Taper polynomial (a16)
+//   * BO(), serial body                   reaxc_bond_orders_sunway.cpp:460-774       bond-order corrections (a6).  That body sits
+//                                         behind an early `return;` in the live build; the Makefile compiles the same
+//                                         unmodified file a second time with stubs/prelude_bo_serial.h, which defines the
+//                                         single `return` of the file away, so BO() falls through into it after the
+//                                         (no-op here) slave-core call.
 // so that the CPU oracle (oracle/orc_forces.cpp) is pinned against the reference itself for these terms.  The Sunway
 // slave-core entry points the same files reference (…_C) are never reached on these paths; they are defined below as
 // traps so the library links.
@@ -32,10 +37,12 @@
 using namespace REAXC_SUNWAY_NS;
 
 #define TRAP(name) { fprintf(stderr, "oracle/_ref: Sunway-only entry point %s reached\n", name); abort(); }
+static bool g_bo_serial_run = false;   // set only while ref_bond_orders drives BO_serial_body
+#define NOOP_IN_BO_SERIAL(name) { if (g_bo_serial_run) return; TRAP(name) }
 extern "C" {
 void Add_All_dBond_to_Forces_C(void*) TRAP("Add_All_dBond_to_Forces_C")
 void Add_All_dBond_to_Forces_C_org(void*) TRAP("Add_All_dBond_to_Forces_C_org")
-void BO_C(void*) TRAP("BO_C")
+void BO_C(void*) NOOP_IN_BO_SERIAL("BO_C")
 void Hydrogen_Bonds_C(void*) TRAP("Hydrogen_Bonds_C")
 void Init_Forces_noQEq_Full_C(void*) TRAP("Init_Forces_noQEq_Full_C")
 void Init_Forces_noQEq_HB_Full_C(void*) TRAP("Init_Forces_noQEq_HB_Full_C")
@@ -56,8 +63,10 @@ void Bonds(reax_system*, control_params*, simulation_data*, storage*, reax_list*
 void Init_Output_Files(reax_system*, control_params*, output_controls*, mpi_datatypes*, char*) TRAP("Init_Output_Files")
 int Allocate_Workspace(reax_system*, control_params*, storage*, int, int, int, char*) TRAP("Allocate_Workspace")
 void Init_Taper(control_params* control, storage* workspace, MPI_Comm comm);   // reaxc_init_md_sunway.cpp:100
-void _reax_system::to_c_sys(reax_system_c*) TRAP("to_c_sys")
-void _reax_system::from_c_sys(reax_system_c*) TRAP("from_c_sys")
+void _reax_system::to_c_sys(reax_system_c*) NOOP_IN_BO_SERIAL("to_c_sys")
+void _reax_system::from_c_sys(reax_system_c*) NOOP_IN_BO_SERIAL("from_c_sys")
+// second compile of reaxc_bond_orders_sunway.cpp (see header): BO() with its serial body reachable
+void BO_serial_body(reax_system*, control_params*, simulation_data*, storage*, reax_list**, output_controls*);
 }
 
 namespace {
@@ -349,6 +358,71 @@ int ref_nonbonded(void* hp, int n, int N, const double* x, const double* q, cons
   vdW_Coulomb_Energy_Full_C_test_err(&param);
   en2[0] = data.my_en.e_vdW; en2[1] = data.my_en.e_ele;
   for (int i = 0; i < N; i++) for (int t = 0; t < 4; t++) fCd[4 * i + t] = fcd[i][t];
+  return 0;
+}
+
+// a6: bond-order corrections on the oracle's post-bond-list state.  fields31 in: uncorrected BO', BO_s, BO_pi, BO_pi2 (and
+// the geometric fields); total_bop[N] = sum of BO' per atom (bo_dboc[i][0] as Init_Forces leaves it).
+// Out: fields31 with BO, BO_s, BO_pi, BO_pi2 and C1dbo..C4dbopi2 replaced; w16 as orc_get_workspace lays it out.
+int ref_bond_orders(void* hp, int n, int N, const int* type, const int* tag, const int* b_start, const int* b_end, int nb,
+                    const int* nbr, const int* sym, const double* total_bop, double* fields31, double* w16) {
+  Params* P = (Params*)hp;
+  reax_system* sys = P->sys;
+  LAMMPS_NS::Pair pair(nullptr);
+  sys->pair_ptr = &pair;
+  sys->n = n; sys->N = N;
+  std::vector<atom_pack_t> atoms(N);
+  for (int i = 0; i < N; i++) { atoms[i].orig_id = tag[i]; atoms[i].type = type[i]; atoms[i].q = 0; atoms[i].x[0] = atoms[i].x[1] = atoms[i].x[2] = 0; }
+  sys->packed_atoms = atoms.data();
+  simulation_data data;
+  memset(&data, 0, sizeof(data));
+  storage ws;
+  memset(&ws, 0, sizeof(ws));
+  std::vector<rvec2> bo_dboc(N);
+  std::vector<double> Deltap(N, 0.0), Deltap_boc(N, 0.0), Delta(N, 0.0), Delta_lp(N, 0.0), Delta_lp_temp(N, 0.0), Delta_e(N, 0.0),
+      Delta_val(N, 0.0), dDelta_lp(N, 0.0), dDelta_lp_temp(N, 0.0), nlp(N, 0.0), nlp_temp(N, 0.0), Clp(N, 0.0), vlpex(N, 0.0);
+  for (int i = 0; i < N; i++) { bo_dboc[i][0] = total_bop[i]; bo_dboc[i][1] = 0.0; }
+  ws.bo_dboc = bo_dboc.data(); ws.Deltap = Deltap.data(); ws.Deltap_boc = Deltap_boc.data(); ws.Delta = Delta.data();
+  ws.Delta_lp = Delta_lp.data(); ws.Delta_lp_temp = Delta_lp_temp.data(); ws.Delta_e = Delta_e.data(); ws.Delta_val = Delta_val.data();
+  ws.dDelta_lp = dDelta_lp.data(); ws.dDelta_lp_temp = dDelta_lp_temp.data(); ws.nlp = nlp.data(); ws.nlp_temp = nlp_temp.data();
+  ws.Clp = Clp.data(); ws.vlpex = vlpex.data();
+  std::vector<reax_list> lists(LIST_N);
+  memset(lists.data(), 0, sizeof(reax_list) * LIST_N);
+  reax_list* bonds = &lists[BONDS];
+  std::vector<int> bidx(b_start, b_start + N), bend(b_end, b_end + N);
+  std::vector<bond_data> bd(nb > 0 ? nb : 1);
+  std::vector<bond_order_data> bod(nb > 0 ? nb : 1);
+  std::vector<double> Cdbo(nb > 0 ? nb : 1, 0.0), Cdbopi(nb > 0 ? nb : 1, 0.0), Cdbopi2(nb > 0 ? nb : 1, 0.0), BO(nb > 0 ? nb : 1);
+  std::vector<rvec2> BOpi(nb > 0 ? nb : 1);
+  memset(bd.data(), 0, sizeof(bond_data) * bd.size());
+  memset(bod.data(), 0, sizeof(bond_order_data) * bod.size());
+  for (int p = 0; p < nb; p++) {
+    const double* o = fields31 + 31 * p;
+    bd[p].nbr = nbr[p]; bd[p].sym_index = sym[p]; bd[p].dbond_index = p; bd[p].d = o[0];
+    for (int t = 0; t < 3; t++) bd[p].dvec[t] = o[1 + t];
+    BO[p] = o[4]; bod[p].BO_s = o[5]; BOpi[p][0] = o[6]; BOpi[p][1] = o[7];
+  }
+  bonds->n = N; bonds->num_intrs = nb; bonds->index = bidx.data(); bonds->end_index = bend.data(); bonds->type = TYP_BOND;
+  bonds->select.bond_list = bd.data(); bonds->bo_data_list = bod.data();
+  bonds->Cdbo_list = Cdbo.data(); bonds->Cdbopi_list = Cdbopi.data(); bonds->Cdbopi2_list = Cdbopi2.data();
+  bonds->BO_list = BO.data(); bonds->BOpi_list = BOpi.data();
+  reax_list* lp = lists.data();
+  g_bo_serial_run = true;
+  BO_serial_body(sys, &P->control, &data, &ws, &lp, &P->oc);
+  g_bo_serial_run = false;
+  for (int p = 0; p < nb; p++) {
+    double* o = fields31 + 31 * p;
+    o[4] = BO[p]; o[5] = bod[p].BO_s; o[6] = BOpi[p][0]; o[7] = BOpi[p][1];
+    o[17] = bod[p].C1dbo; o[18] = bod[p].C2dbo; o[19] = bod[p].C3dbo;
+    o[20] = bod[p].C1dbopi; o[21] = bod[p].C2dbopi; o[22] = bod[p].C3dbopi; o[23] = bod[p].C4dbopi;
+    o[24] = bod[p].C1dbopi2; o[25] = bod[p].C2dbopi2; o[26] = bod[p].C3dbopi2; o[27] = bod[p].C4dbopi2;
+  }
+  for (int i = 0; i < N; i++) {
+    double* w = w16 + 16 * i;
+    w[0] = bo_dboc[i][0]; w[1] = bo_dboc[i][1]; w[2] = Deltap[i]; w[3] = Deltap_boc[i]; w[4] = Delta[i]; w[5] = Delta_e[i];
+    w[6] = Delta_val[i]; w[7] = vlpex[i]; w[8] = nlp[i]; w[9] = Delta_lp[i]; w[10] = Clp[i]; w[11] = dDelta_lp[i];
+    w[12] = nlp_temp[i]; w[13] = Delta_lp_temp[i]; w[14] = dDelta_lp_temp[i]; w[15] = 0.0;
+  }
   return 0;
 }
 

@@ -283,3 +283,90 @@ def test_nonbonded_equals_reference_MPE_serial_routine(perturb, seed, vdw_type, 
     assert abs(e[10]) > 100 and abs(e[11]) > 100
     assert relerr(-fcd[:n, :3], o.forces()[:n]) < 1e-10
     assert np.abs(o.forces()[n:]).max() == 0.0 and np.abs(fcd[n:]).max() == 0.0     # ghosts receive no nonbonded force
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fix qeq/reax: the reference's own FixQEqReaxSunway (fix_qeq_reax_sunway.cpp compiled unmodified against a LAMMPS-core
+# stand-in, oracle/ref/ref_qeq.cpp) against the oracle's restatement: init_taper, init_matvec extrapolation, CG_v2 and
+# its iteration counts, calculate_Q and the history shift.
+def _ref_qeq(cfg, o, tol, s_hist, t_hist, swb=10.0):
+    L = C.CDLL(LIBREF)
+    n, x = cfg["n"], np.ascontiguousarray(cfg["x"])
+    N = len(x)
+    d = o.params_dump()
+    ngp = int(d[2]); base = 3 + ngp + 18
+    el = d[base:base + 4 * 30].reshape(4, 30)
+    chi = np.concatenate([[0.0], el[:, 13]]); eta = np.concatenate([[0.0], el[:, 14]]); gam = np.concatenate([[0.0], el[:, 5]])
+    off, idx = o.get_neighbors()
+    off = np.ascontiguousarray(off[:n + 1], dtype=np.int64); idx = _ip(idx[:off[n]])
+    sh, th = np.ascontiguousarray(s_hist.copy()), np.ascontiguousarray(t_hist.copy())
+    q = np.zeros(N); s = np.zeros(n); t = np.zeros(n); mv = np.zeros(2, dtype=np.int32); tap = np.zeros(8)
+    cnt = C.c_long(); rows = np.zeros(n)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ty, tg, ow = _ip(cfg["type"]), _ip(cfg["tag"]), _ip(cfg["owner"])
+    rc = L.ref_qeq_pre_force(n, N - n, 4, p(x), p(ty), p(tg), p(off), p(idx), p(ow), p(chi), p(eta), p(gam), C.c_double(0.0),
+                             C.c_double(swb), C.c_double(tol), p(sh), p(th), p(q), p(s), p(t), p(mv), p(tap), C.byref(cnt), p(rows))
+    assert rc == 0
+    return dict(q=q, s=s, t=t, mv=(int(mv[0]), int(mv[1])), tap=tap, s_hist=sh, t_hist=th, nnz=cnt.value, rowsum=rows)
+
+
+@pytest.mark.parametrize("perturb,seed,tol,history", [(0.0, 0, 1e-6, False), (0.1, 13, 1e-6, True), (0.1, 14, 1e-10, True)])
+def test_qeq_equals_reference_fix_qeq_reax(perturb, seed, tol, history):
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, qeq=False)
+    o = cfg["oracle"]
+    n, x = cfg["n"], cfg["x"]
+    o.set_atoms(n, x, cfg["type"], cfg["tag"], np.zeros(len(x)))
+    o.build_neighbors(12.5)
+    rng = np.random.default_rng(seed)
+    sh = rng.normal(scale=0.05, size=(n, 5)) if history else np.zeros((n, 5))
+    th = rng.normal(scale=0.05, size=(n, 5)) if history else np.zeros((n, 5))
+    ref = _ref_qeq(cfg, o, tol, sh, th)
+    o.qeq_init(0.0, 10.0, tol)
+    o.qeq_set_hist(sh, th)
+    mv = o.qeq_pre_force(cfg["owner"])
+    # the pipelined-CG iteration counts of both solves are the reference's, exactly
+    assert mv == ref["mv"] and max(mv) < 200 and min(mv) > 3
+    offH, numH, colH, valH = o.qeq_H()
+    assert int(numH.sum()) == ref["nnz"]
+    rows = np.array([valH[offH[i]:offH[i] + numH[i]].sum() for i in range(n)])
+    assert relerr(rows, ref["rowsum"]) < 1e-13            # H through the reference's calculate_H + init_taper
+    s, t = o.qeq_st()
+    assert relerr(s[:n], ref["s"]) < 1e-9 and relerr(t[:n], ref["t"]) < 1e-9
+    assert np.abs(o.q() - ref["q"]).max() < 1e-10 and np.abs(ref["q"][:n]).max() > 0.1
+    so, to = o.qeq_get_hist()
+    assert relerr(so, ref["s_hist"]) < 1e-9 and relerr(to, ref["t_hist"]) < 1e-9
+    assert np.array_equal(ref["s_hist"][:, 1:], sh[:, :4])  # history shifted by one
+
+
+@pytest.mark.parametrize("perturb,seed,scale", [(0.0, 0, 1.0), (0.1, 15, 1.0), (0.1, 16, 0.9)])
+def test_bond_order_corrections_equal_reference_BO_serial_body(perturb, seed, scale):
+    """a6: the serial bond-order correction code of BO() (reaxc_bond_orders_sunway.cpp:460-774), which the live build
+    skips with an early `return;` in favour of the slave-core kernels — compiled from the unmodified file with that one
+    `return` defined away (oracle/ref/stubs/prelude_bo_serial.h) and run on the oracle's uncorrected bond list."""
+    L, P = _ref_lib()
+    cfg = H.static_config(1, 1, 1, perturb=perturb, seed=seed, scale=scale, qeq=False)
+    o = cfg["oracle"]
+    n, x = cfg["n"], cfg["x"]
+    N = len(x)
+    o.set_atoms(n, x, cfg["type"], cfg["tag"], np.zeros(N))
+    o.build_neighbors(12.5)
+    o.phase(0); o.phase(1)
+    bs, be, nbr, sym, fld = o.bonds()
+    nb = len(nbr)
+    total_bop = np.ascontiguousarray(o.workspace()[:, 0])          # sum of BO' per atom after the bond-list build
+    assert total_bop.max() > 2.0
+    fref = np.ascontiguousarray(fld.copy()); wref = np.zeros((N, 16))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ints = [_ip(a) for a in ([t - 1 for t in cfg["type"]], cfg["tag"], bs, be, nbr, sym)]
+    assert L.ref_bond_orders(P, n, N, p(ints[0]), p(ints[1]), p(ints[2]), p(ints[3]), nb, p(ints[4]), p(ints[5]), p(total_bop),
+                             p(fref), p(wref)) == 0
+    o.phase(4)
+    _, _, _, _, forc = o.bonds()
+    worc = o.workspace()
+    for c in (4, 5, 6, 7) + tuple(range(17, 28)):                  # BO, BO_s, BO_pi, BO_pi2, C1dbo .. C4dbopi2
+        den = max(np.abs(forc[:, c]).max(), 1e-300)
+        assert np.abs(fref[:, c] - forc[:, c]).max() / den < 1e-11, c
+    assert np.abs(forc[:, 4] - fld[:, 4]).max() > 1e-3             # the corrections did change the bond orders
+    for c in range(15):                                            # total_bo, Delta_boc, Deltap, ..., dDelta_lp_temp
+        den = max(np.abs(worc[:, c]).max(), 1e-300)
+        assert np.abs(wref[:, c] - worc[:, c]).max() / den < 1e-11, c
