@@ -7,8 +7,9 @@
 //     FixAveAtom itself is LAMMPS core, absent from /root/reference: stock semantics restated), FindMolecule (:498-566)
 //     with its iterated min-label sweeps and ghost forward_comm, SortMolecule (:570-648), FindSpecies (:652-717),
 //     WriteFormulas (:745-780).
-// Parity unpinned by the reference (it ships no bond/species output files); pinned here by construction from the live
-// source and by the invariants in tests/test_oracle.py (TATB crystal = 16 C6H6O6N6 molecules per cell).
+// Pinned (tests/test_oracle_vs_ref.py): the reference's own FixReaxCBondsSunway / FixReaxCSpeciesSunway, compiled unmodified
+// against a LAMMPS-core stand-in (oracle/ref/ref_analysis.cpp), write byte-identical files from the same state.  Only the
+// sampling schedule of the hidden fix ave/atom (LAMMPS core, absent from /root/reference) is restated from stock semantics.
 #include "orc_analysis.h"
 
 #include <algorithm>

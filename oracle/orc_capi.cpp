@@ -297,6 +297,13 @@ void orc_md_species_get(void* hh, int* composition, int* cluster_of_local) {
   if (composition) memcpy(composition, S.composition.data(), S.composition.size() * sizeof(int));
   if (cluster_of_local) for (int i = 0; i < h->md.nlocal; i++) cluster_of_local[i] = (int)S.clusterID[i];
 }
+// raw inputs of FindMolecule: tmpid [nlocal][12] (local index of the partner, 0 = none) and the averaged abo columns
+void orc_md_species_raw(void* hh, int* tmpid, double* avg) {
+  OrcHandle* h = (OrcHandle*)hh;
+  const SpeciesFix& S = h->species;
+  const size_t m = (size_t)h->md.nlocal * MAXSPECBOND;
+  for (size_t k = 0; k < m; k++) { tmpid[k] = S.tmpid[k]; avg[k] = S.array[k]; }
+}
 long orc_md_species_text(void* hh, long ntimestep, char* out, long cap) {
   OrcHandle* h = (OrcHandle*)hh;
   h->text = h->species.formulas_text(ntimestep);

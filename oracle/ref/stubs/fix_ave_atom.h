@@ -1,0 +1,3 @@
+// stub (written for this repo): see lammps_stub.h
+#pragma once
+#include "lammps_stub.h"

@@ -36,6 +36,7 @@ class NeighRequest {
 class Neighbor {
  public:
   NeighRequest** requests = nullptr;
+  int every = 1, delay = 10, dist_check = 1;
   int request(void*, int = 0) { return 0; }
 };
 
@@ -73,7 +74,11 @@ class Atom {
   int *type = nullptr, *mask = nullptr;
   tagint* tag = nullptr;
   double* q = nullptr;
-  int nlocal = 0, nghost = 0, nmax = 0, ntypes = 0, q_flag = 1;
+  int nlocal = 0, nghost = 0, nmax = 0, ntypes = 0, q_flag = 1, tag_enable = 1;
+  bigint natoms = 0;
+  tagint* molecule = nullptr;          // atom_style charge: no molecule IDs
+  double** v = nullptr;
+  int tag_consecutive() { return 1; }
   void add_callback(int) {}
   void delete_callback(const char*, int) {}
 };
@@ -122,8 +127,23 @@ class CiteMe {
   void add(const char*) {}
 };
 
-class Domain {};
-class Modify {};
+class Domain {
+ public:
+  double boxlo[3] = {0, 0, 0}, boxhi[3] = {0, 0, 0};
+};
+class Compute;
+class Modify {
+ public:
+  int nfix = 0, ncompute = 0;
+  Fix** fix = nullptr;
+  Compute** compute = nullptr;
+  void add_compute(int, char**, int = 1) {}
+  void add_fix(int, char**, int = 1) {}
+  void delete_compute(const char*) {}
+  void delete_fix(const char*) {}
+  int find_compute(const char*) { return -1; }
+  int find_fix(const char*) { return -1; }
+};
 
 class LAMMPS {
  public:
@@ -166,7 +186,16 @@ class Fix : protected Pointers {
     if (narg > 2) style = arg[2];
   }
   virtual ~Fix() {}
+  int nevery = 1, peratom_flag = 0, size_peratom_cols = 0, peratom_freq = 1, global_freq = 1, vector_flag = 0, size_vector = 0,
+      extvector = 0, restart_global = 0, time_integrate = 0, box_change = 0;
+  int force_reneighbor = 0, next_reneighbor = 0;
+  double* vector_atom = nullptr;
+  double** array_atom = nullptr;
   virtual int setmask() = 0;
+  virtual void setup(int) {}
+  virtual void end_of_step() {}
+  virtual void post_integrate() {}
+  virtual double compute_vector(int) { return 0.0; }
   virtual void post_constructor() {}
   virtual void init() {}
   virtual void init_list(int, NeighList*) {}
@@ -185,6 +214,18 @@ class Fix : protected Pointers {
   virtual void copy_arrays(int, int, int) {}
   virtual int pack_exchange(int, double*) { return 0; }
   virtual int unpack_exchange(int, double*) { return 0; }
+};
+
+// fix ave/atom (LAMMPS core): only what fix reax/c/species reads — the averaged per-atom array and the end_of_step hook
+class FixAveAtom : public Fix {
+ public:
+  FixAveAtom(LAMMPS* l, int narg, char** arg) : Fix(l, narg, arg) {}
+  int setmask() { return FixConst::END_OF_STEP; }
+};
+
+class Compute : protected Pointers {
+ public:
+  explicit Compute(LAMMPS* l) : Pointers(l) {}
 };
 
 // one swap: every ghost receives its owner's value(s)

@@ -22,3 +22,11 @@ static inline int MPI_Allreduce(const void* s, void* r, int count, MPI_Datatype 
 }
 static inline int MPI_Bcast(void* b, int count, MPI_Datatype t, int root, MPI_Comm c) { (void)b; (void)count; (void)t; (void)root; (void)c; return 0; }
 static inline double MPI_Wtime(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+typedef int MPI_Request;
+typedef int MPI_Status;
+#define MPI_STATUS_IGNORE ((MPI_Status*)0)
+#define MPI_CHAR 1
+static inline int MPI_Irecv(void* b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Request* r) { (void)b; (void)n; (void)t; (void)src; (void)tag; (void)c; (void)r; return 0; }
+static inline int MPI_Isend(const void* b, int n, MPI_Datatype t, int dst, int tag, MPI_Comm c, MPI_Request* r) { (void)b; (void)n; (void)t; (void)dst; (void)tag; (void)c; (void)r; return 0; }
+static inline int MPI_Wait(MPI_Request* r, MPI_Status* s) { (void)r; (void)s; return 0; }
+static inline int MPI_Reduce(const void* s, void* r, int count, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) { (void)op; (void)root; (void)c; memcpy(r, s, (size_t)count * (size_t)t); return 0; }

@@ -19,6 +19,7 @@ class Pair {
   virtual void init_style() {}
   virtual void init_list(int, NeighList*) {}
   virtual void* extract(const char*, int&) { return nullptr; }
+  NeighList* list = nullptr;       // Pair::list of the LAMMPS core
   NeighList* listfull = nullptr;   // the Sunway-patched LAMMPS core adds this member
   int evflag = 0, eflag_either = 0, eflag_global = 0, eflag_atom = 0, vflag_either = 0, vflag_global = 0, vflag_atom = 0;
   double eng_vdwl = 0, eng_coul = 0;

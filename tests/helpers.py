@@ -286,6 +286,11 @@ class Oracle:
         self.L.orc_md_species_get(self.h, _p(comp), _p(cl))
         return dict(nmole=nm, composition=comp, cluster=cl)
 
+    def md_species_raw(self):
+        ids = np.zeros((self.nlocal, 12), dtype=np.int32); avg = np.zeros((self.nlocal, 12))
+        self.L.orc_md_species_raw(self.h, _p(ids), _p(avg))
+        return ids, avg
+
     def md_species_text(self, step):
         return self._text("orc_md_species_text", step)
 

@@ -370,3 +370,69 @@ def test_bond_order_corrections_equal_reference_BO_serial_body(perturb, seed, sc
     for c in range(15):                                            # total_bo, Delta_boc, Deltap, ..., dDelta_lp_temp
         den = max(np.abs(worc[:, c]).max(), 1e-300)
         assert np.abs(wref[:, c] - worc[:, c]).max() / den < 1e-11, c
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f1 / f2: the reference's own output fixes (fix_reaxc_bonds_sunway.cpp, fix_reaxc_species_sunway.cpp compiled unmodified
+# against the LAMMPS-core stand-in, oracle/ref/ref_analysis.cpp) write their files from the oracle's state; the oracle's
+# restated writers (oracle/orc_analysis.cpp) must produce the same bytes.
+@pytest.mark.parametrize("scale,T", [(1.0, 300.0), (0.9, 3000.0)])
+def test_bond_table_file_equals_reference_fix_reaxc_bonds(scale, T, tmp_path):
+    L = C.CDLL(LIBREF)
+    box, x, t, tag = H.tatb_cell(1, 1, 1, scale=scale)
+    v = H.maxwell_velocities(t, T, 31)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-8)
+    o.md_run(3)
+    n = o.nlocal
+    xall, ty, tg, owner = o.md_ghosts()
+    N = len(xall)
+    o.n, o.N = n, N
+    bs, be, nbr, sym, fld = o.bonds()
+    w = o.workspace()
+    q = np.ascontiguousarray(o.q())
+    path = str(tmp_path / "bonds.ref")
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    BO, tbo, nlp = np.ascontiguousarray(fld[:, 4]), np.ascontiguousarray(w[:, 0]), np.ascontiguousarray(w[:, 8])
+    ints = [_ip(a) for a in (ty, tg, bs, be, nbr)]
+    assert L.ref_bonds_write(path.encode(), C.c_long(3), C.c_double(0.3), n, N - n, 4, p(ints[0]), p(ints[1]), p(q), p(ints[2]),
+                             p(ints[3]), len(nbr), p(ints[4]), p(BO), p(tbo), p(nlp)) == 0
+    ref = open(path).read()
+    assert ref == o.md_bonds_text(3) and ref.count("\n") == 384 + 8
+
+
+@pytest.mark.parametrize("scale,T,cut", [(1.0, 300.0, None), (0.8, 4000.0, (1, 4, 0.9))])
+def test_species_file_equals_reference_fix_reaxc_species(scale, T, cut, tmp_path):
+    L = C.CDLL(LIBREF)
+    box, x, t, tag = H.tatb_cell(1, 1, 1, scale=scale)
+    v = H.maxwell_velocities(t, T, 99)
+    o = H.Oracle()
+    o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-8, every=5)
+    bc = np.full((5, 5), 0.30)
+    if cut:
+        bc[cut[0], cut[1]] = bc[cut[1], cut[0]] = cut[2]
+    o.md_species_init(1, 5, 5, bocut=bc)
+    o.md_species_step(0)
+    found = False
+    for step in range(1, 6):
+        found = o.md_species_step(step)
+        if step < 5:
+            o.md_run(1)
+    assert found
+    sp = o.md_species_get()
+    ids, avg = o.md_species_raw()
+    xall, ty, tg, owner = o.md_ghosts()
+    n, N = o.nlocal, len(xall)
+    path = str(tmp_path / "species.ref")
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    cuts = np.array([[cut[0], cut[1], cut[2]]], dtype=np.float64) if cut else np.zeros((0, 3))
+    nmole = C.c_int(); every = C.c_int()
+    cl = np.zeros(n, dtype=np.int32)
+    ints = [_ip(a) for a in (ty, tg, owner)]
+    assert L.ref_species_write(path.encode(), 1, 5, 5, n, N - n, 4, p(ints[0]), p(ints[1]), p(ints[2]), p(ids), p(avg), len(cuts),
+                               p(cuts) if len(cuts) else None, C.byref(nmole), p(cl), C.byref(every)) == 0
+    assert every.value == 5                                   # the reference keeps `every 5` for nevery*nrepeat = 5
+    assert nmole.value == sp["nmole"] and np.array_equal(cl, sp["cluster"])
+    assert open(path).read() == o.md_species_text(5)
+    if cut:
+        assert sp["nmole"] > 16
