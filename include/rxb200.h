@@ -106,6 +106,9 @@ int rxb_dist_set_p2p(rxb_handle* h, int on);
 /* counts[0..7] = nlocal, nall, verlet nnz, bond-candidate nnz, directed bonds, far nnz(sum), kernel launches, qeq iterations */
 int rxb_get_counts(rxb_handle* h, long long* counts8);
 int rxb_get_neighbors(rxb_handle* h, int which /*0 verlet, 1 bond candidates*/, long long* off, int* idx);
+/* list cut-offs in use: out3 = Verlet list (cutmax + skin), bond-candidate list (bond reach + skin), bond reach = the
+ * largest distance at which any element pair can still have BO' >= bo_cut (<= the control file's bond cutoff) */
+int rxb_get_cutoffs(rxb_handle* h, double* out3);
 /* bonds, CSR by atom (row = b_start[i] .. +b_cnt[i], ascending neighbour index), 31 doubles per directed bond:
  * d,dvec3,BO,BO_s,BO_pi,BO_pi2,dBOp3,dln_BOp_pi3,dln_BOp_pi2_3,C1..3dbo,C1..4dbopi,C1..4dbopi2,Cdbo,Cdbopi,Cdbopi2 */
 int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, double* fields31);

@@ -16,7 +16,7 @@ SYMBOLS = [
     "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
-    "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump",
+    "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -253,6 +253,11 @@ class Rxb:
         self._chk(self.lib.rxb_dist_set_p2p(self.h, int(on)))
 
     # ---- introspection ----
+    def cutoffs(self):
+        c = np.zeros(3)
+        self._chk(self.lib.rxb_get_cutoffs(self.h, _p(c)))
+        return dict(verlet=c[0], bond_candidates=c[1], bond_reach=c[2])
+
     def counts(self):
         c = np.zeros(8, dtype=np.int64)
         self._chk(self.lib.rxb_get_counts(self.h, _p(c)))

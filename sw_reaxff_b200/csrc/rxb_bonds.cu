@@ -23,7 +23,7 @@ struct Stage {
   double val[kMaxRow][11];  // d,dx,dy,dz, BO,BO_s,BO_pi,BO_pi2, cBOp,cPi,cPi2
 };
 
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 6)
 k_bond_list(DevView v, DevParams P) {
   __shared__ Stage stage[kWarps];
   __shared__ int s_queue[kWarps][64];
@@ -41,7 +41,13 @@ k_bond_list(DevView v, DevParams P) {
     int* queue = s_queue[wib];
     int qn = 0;
     const float4 fi = v.xf[i];
-    const float bc2_hi = (float)(bond_cut * bond_cut) + v.bond_band;
+    // per partner element: (reach of a bond of this pair)^2 + fp32 rounding band; lane t holds the threshold of element t
+    const int nt = P.nt;
+    float thr_lane = 0.0f;
+    if (lane < nt) {
+      const double dm = P.pair[ti * nt + lane].d_bond_max;
+      thr_lane = __double2float_ru(dm * dm) + v.bond_band;
+    }
     // Phase 1 (cheap, all lanes): distance filter, survivors are queued.  Phase 2 (6 transcendentals per pair) runs on
     // FULL warps drained from the queue: only ~30 % of the (bond_cut + skin) candidates are inside bond_cut, so doing the
     // math in place would leave two thirds of the lanes idle.
@@ -49,15 +55,20 @@ k_bond_list(DevView v, DevParams P) {
       if (k0 < end) {
         const long long k = k0 + lane;
         bool near = false;
-        int j = -1;
+        int j = -1, tjf = -1;
+        float r2f = 0.0f;
         if (k < end) {
           j = v.bc_idx[k];
-          // fp32 shadow (position + type in 16 bytes): a conservative superset goes to the queue, the exact fp64 test
-          // d <= bond_cut is applied when the candidate is drained
+          // fp32 shadow (position + type in 16 bytes): a conservative superset goes to the queue, the exact fp64 tests
+          // (d <= bond_cut, BO' >= bo_cut) are applied when the candidate is drained
           const float4 fj = v.xf[j];
           const float ex = fj.x - fi.x, ey = fj.y - fi.y, ez = fj.z - fi.z;
-          near = (ex * ex + ey * ey + ez * ez) <= bc2_hi && __float_as_int(fj.w) >= 0;
+          r2f = ex * ex + ey * ey + ez * ez;
+          tjf = __float_as_int(fj.w);
         }
+        float thr = __shfl_sync(0xffffffffu, thr_lane, tjf & 31);
+        if (tjf >= 32) { const double dm = P.pair[ti * nt + tjf].d_bond_max; thr = __double2float_ru(dm * dm) + v.bond_band; }
+        near = tjf >= 0 && r2f <= thr;
         const unsigned m = __ballot_sync(0xffffffffu, near);
         if (near) queue[qn + __popc(m & ((1u << lane) - 1))] = j;
         qn += __popc(m);

@@ -369,6 +369,13 @@ int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* compo
   });
 }
 
+int rxb_get_cutoffs(rxb_handle* h, double* out3) {
+  return guard([&] {
+    const System& s = *h->sys;
+    out3[0] = s.cutneigh(); out3[1] = s.bond_reach() + s.skin; out3[2] = s.bond_reach();
+  });
+}
+
 int rxb_host_register(void* p, size_t bytes) {
   return guard([&] { RXB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
 }

@@ -8,6 +8,7 @@
 //   element map : /root/reference/pair_reaxc_sunway.cpp:318-336
 // Unlike the reference (MPI_Abort / error->all) errors are returned as strings and surface as negative
 // status codes through the C ABI.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -316,6 +317,36 @@ void ForceField::derive() {
     x.log_r_p = x.r_p > 0.0 ? log(x.r_p) : 0.0;
     x.log_r_pp = x.r_pp > 0.0 ? log(x.r_pp) : 0.0;
   }
+  // Reach of a bond per element pair: the uncorrected bond order of BOp_single (reaxc_forces_sunway.cpp:694-720) is a sum
+  // of terms exp(p (d/r)^q) with p < 0 < q, i.e. it falls monotonically with d, so the distance where it crosses bo_cut
+  // bounds every bond of that pair.  k_bond_list uses it (plus a 1e-6 relative margin) to keep candidates that cannot
+  // bond away from the transcendental work; the accept test itself stays the exact one.
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j < nt; j++) {
+      PairPar& x = pair[(size_t)i * nt + j];
+      const AtomPar &ai = atom[i], &aj = atom[j];
+      const bool use_s = ai.r_s > 0.0 && aj.r_s > 0.0, use_p = ai.r_pi > 0.0 && aj.r_pi > 0.0,
+                 use_pp = ai.r_pi_pi > 0.0 && aj.r_pi_pi > 0.0;
+      const bool monotone = (!use_s || (x.p_bo1 < 0.0 && x.p_bo2 > 0.0)) && (!use_p || (x.p_bo3 < 0.0 && x.p_bo4 > 0.0)) &&
+                            (!use_pp || (x.p_bo5 < 0.0 && x.p_bo6 > 0.0));
+      auto bop = [&](double d) {
+        double b = 0.0;
+        if (use_s) b += (1.0 + ctl.bo_cut) * exp(x.p_bo1 * pow(d / x.r_s, x.p_bo2));
+        if (use_p) b += exp(x.p_bo3 * pow(d / x.r_p, x.p_bo4));
+        if (use_pp) b += exp(x.p_bo5 * pow(d / x.r_pp, x.p_bo6));
+        return b;
+      };
+      double reach = ctl.bond_cut;
+      if (monotone && bop(ctl.bond_cut) < ctl.bo_cut) {
+        double lo = 0.0, hi = ctl.bond_cut;          // bop(lo) >= bo_cut > bop(hi)
+        for (int it = 0; it < 200; it++) {
+          const double mid = 0.5 * (lo + hi);
+          if (bop(mid) >= ctl.bo_cut) lo = mid; else hi = mid;
+        }
+        reach = std::min(ctl.bond_cut, hi * (1.0 + 1e-6));
+      }
+      x.d_bond_max = reach;
+    }
 }
 
 std::vector<double> ForceField::dump() const {

@@ -35,6 +35,7 @@ struct PairPar {  // two_body_parameters
   double powgi_vdW1;   // derived: (1/gamma_w)^p_vdW1, hoisted out of the pair loop (reaxc_nonbonded_sw64.c:137)
   double inv_r_vdW, alpha_over_r_vdW; // derived: 1/r_vdW, alpha/r_vdW
   double log_r_s, log_r_p, log_r_pp;  // derived: logs of the bond radii, so that (d/r)^p = exp(p (log d - log r))
+  double d_bond_max;   // derived: beyond this distance BO' < bo_cut for certain (BOp_single would reject), <= bond_cut
 };
 
 struct AnglePar { double theta_00, p_val1, p_val2, p_coa1, p_val7, p_pen1, p_val4; };

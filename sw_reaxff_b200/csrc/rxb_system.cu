@@ -314,6 +314,14 @@ void System::upload_params() {
   RXB_CUDA(cudaMemcpy(shld_d.p, sh.data(), sh.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 
+// Largest distance at which any element pair of the force field can still have BO' >= bo_cut (PairPar::d_bond_max,
+// never more than the control file's bond_cut): no bond of BOp_single lies beyond it.
+double System::bond_reach() const {
+  double r = 0.0;
+  for (const PairPar& p : ff.pair) r = std::max(r, p.d_bond_max);
+  return (r > 0.0 && r < ff.ctl.bond_cut) ? r : ff.ctl.bond_cut;
+}
+
 double System::cutneigh() const {
   const Control& c = ff.ctl;
   const double cutmax = std::max(c.nonb_cut, std::max(c.hbond_cut, 2 * c.bond_cut));  // pair_reaxc_sunway.cpp:410
@@ -497,8 +505,8 @@ void System::build_neighbors() {
   // Verlet list for local rows: bins of cn/2, +-2 cells
   cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
   cells_a_.build(xq.p, n, cn, vl, st_);
-  // bond candidates for all rows (ghosts too): bond_cut + skin
-  const double cb = ff.ctl.bond_cut + skin;
+  // bond candidates for all rows (ghosts too): (reach of the longest possible bond <= bond_cut) + skin
+  const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
   cells_b_.build(xq.p, N, cb, bc, st_);
   far_idx.resize((size_t)std::max<long long>(vl.nnz, 1));

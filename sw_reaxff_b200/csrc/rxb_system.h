@@ -116,6 +116,7 @@ class System {
   // ---- lists ----
   void build_neighbors();   // a1: Verlet (local rows) + bond-candidate (all rows) lists
   double cutneigh() const;
+  double bond_reach() const;
 
   // ---- QEq (fix qeq/reax pre_force) ----
   void qeq_reset_history();

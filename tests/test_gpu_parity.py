@@ -83,12 +83,15 @@ def test_neighbor_list_exact(case):
     assert np.array_equal(np.diff(off_g), np.diff(off_o)[:n])
     for i in range(n):
         assert np.array_equal(np.sort(nb_g[off_g[i]:off_g[i + 1]]), nb_o[off_o[i]:off_o[i + 1]])
-    # bond-candidate rows (all atoms, ghosts too) must contain every pair within bond_cut
+    # bond-candidate rows (all atoms, ghosts too) hold exactly the pairs within (bond reach + skin), where the reach is the
+    # largest distance at which any element pair can have BO' >= bo_cut (3.354 A for this force field, N-N)
+    cut = r.cutoffs()
+    assert abs(cut["verlet"] - 12.5) < 1e-12 and 3.35 < cut["bond_reach"] < 3.36 and abs(cut["bond_candidates"] - cut["bond_reach"] - 2.5) < 1e-12
     off_b, nb_b = r.neighbors(1)
     x = case["cfg"]["x"]
     for i in list(range(0, len(x), 97)):
         row = set(nb_b[off_b[i]:off_b[i + 1]].tolist())
-        close = [j for j in nb_o[off_o[i]:off_o[i + 1]] if np.linalg.norm(x[j] - x[i]) <= 7.0]
+        close = [j for j in nb_o[off_o[i]:off_o[i + 1]] if np.linalg.norm(x[j] - x[i]) <= cut["bond_candidates"]]
         assert set(close) == row
 
 
