@@ -37,7 +37,7 @@ k_bond_list(DevView v, DevParams P) {
     const double4 pi = v.xq[i];
     const AtomPar ai = P.atom[ti];
     const double bo_cut = P.ctl.bo_cut, bond_cut = P.ctl.bond_cut, nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
-    const long long beg = v.bc_off[i], end = v.bc_off[i + 1];
+    const long long beg = v.bc_off[i], end = beg + v.bc_cnt[i];
     int* queue = s_queue[wib];
     int qn = 0;
     const float4 fi = v.xf[i];

@@ -201,8 +201,17 @@ int rxb_get_neighbors(rxb_handle* h, int which, long long* off, int* idx) {
   return guard([&] {
     System& s = *h->sys;
     rxb::Csr& c = which == 0 ? s.vl : s.bc;
-    d2h(off, c.off.p, (size_t)c.nrows + 1, s.stream());
-    d2h(idx, c.idx.p, (size_t)c.nnz, s.stream());
+    // the device rows sit at a fixed stride: hand out a compact CSR
+    std::vector<int> cnt(c.nrows), raw((size_t)std::max<long long>(c.slots, 1));
+    d2h(cnt.data(), c.cnt.p, (size_t)c.nrows, s.stream());
+    d2h(raw.data(), c.idx.p, (size_t)c.slots, s.stream());
+    long long w = 0;
+    for (int i = 0; i < c.nrows; i++) {
+      off[i] = w;
+      memcpy(idx + w, raw.data() + (size_t)i * c.stride, (size_t)cnt[i] * sizeof(int));
+      w += cnt[i];
+    }
+    off[c.nrows] = w;
   });
 }
 
@@ -266,8 +275,19 @@ int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val) {
   return guard([&] {
     System& s = *h->sys;
     d2h(num, s.far_num.p, (size_t)s.n, s.stream());
-    d2h(idx, s.far_idx.p, (size_t)s.vl.nnz, s.stream());
-    d2h(val, s.H_val.p, (size_t)s.vl.nnz, s.stream());
+    // compact like rxb_get_neighbors(0): row i of the output starts at the compact Verlet offset of row i
+    const rxb::Csr& c = s.vl;
+    std::vector<int> cnt(c.nrows), ri((size_t)std::max<long long>(c.slots, 1));
+    std::vector<double> rv((size_t)std::max<long long>(c.slots, 1));
+    d2h(cnt.data(), c.cnt.p, (size_t)c.nrows, s.stream());
+    d2h(ri.data(), s.far_idx.p, (size_t)c.slots, s.stream());
+    d2h(rv.data(), s.H_val.p, (size_t)c.slots, s.stream());
+    long long w = 0;
+    for (int i = 0; i < c.nrows; i++) {
+      memcpy(idx + w, ri.data() + (size_t)i * c.stride, (size_t)num[i] * sizeof(int));
+      memcpy(val + w, rv.data() + (size_t)i * c.stride, (size_t)num[i] * sizeof(double));
+      w += cnt[i];
+    }
   });
 }
 

@@ -45,9 +45,9 @@ struct DevView {
   double* f;           // N*3, true forces
   double* CdDelta;     // N
   // Verlet list r <= cutneigh, local rows          (a1)
-  const long long* vl_off; const int* vl_idx;
+  const long long* vl_off; const int* vl_idx; const int* vl_cnt;   // row i: vl_idx[vl_off[i] .. + vl_cnt[i])
   // bond candidates r <= bond_cut + skin, all rows (a1, ghost rows included)
-  const long long* bc_off; const int* bc_idx;
+  const long long* bc_off; const int* bc_idx; const int* bc_cnt;
   // hbond candidates r <= hbond_cut + skin, local H rows only
   const long long* hc_off; const int* hc_idx;
   // far list == H sparsity pattern: r <= nonb_cut / swb, local rows, slots vl_off[i] .. +far_num[i]

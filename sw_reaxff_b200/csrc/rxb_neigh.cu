@@ -82,11 +82,13 @@ __global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __res
 }
 
 // One warp per row atom.  FILL=false: count hits -> cnt[i];  FILL=true: write columns at off[i].
+// FILL = false: count only.  FILL = true: write row i at i * stride (entries beyond the stride are dropped but still counted,
+// the host then re-runs with a larger stride) and store the row length.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const float4* __restrict__ sposf,
         const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band, int reach, int* __restrict__ cnt,
-        const long long* __restrict__ off, int* __restrict__ idx) {
+        long long* __restrict__ off, int* __restrict__ idx, int stride) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nrows) return;
@@ -97,7 +99,7 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
   const int bx = bin_coord(pi.x, g.lo[0], g.inv[0], g.nb[0]);
   const int by = bin_coord(pi.y, g.lo[1], g.inv[1], g.nb[1]);
   const int bz = bin_coord(pi.z, g.lo[2], g.inv[2], g.nb[2]);
-  long long w = FILL ? off[i] : 0;
+  const long long base = (long long)i * stride;
   int total = 0;
   for (int cz = max(bz - reach, 0); cz <= min(bz + reach, g.nb[2] - 1); cz++) {
     double dz = 0.0;
@@ -140,16 +142,31 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
           }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (FILL) {
-          if (hit) idx[w + __popc(m & ((1u << lane) - 1))] = j;
-          w += __popc(m);
-        } else {
-          total += __popc(m);
+        if (FILL && hit) {
+          const int pos = total + __popc(m & ((1u << lane) - 1));
+          if (pos < stride) idx[base + pos] = j;
         }
+        total += __popc(m);
       }
     }
   }
-  if (!FILL && lane == 0) cnt[i] = total;
+  if (lane == 0) {
+    cnt[i] = total;
+    if (FILL) off[i] = base;
+    if (FILL && i == nrows - 1) off[nrows] = base + stride;
+  }
+}
+
+// max and sum of the row lengths
+__global__ void k_cnt_stats(const int* __restrict__ cnt, int n, long long* __restrict__ stats) {
+  long long s = 0;
+  int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { s += cnt[i]; m = max(m, cnt[i]); }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax((unsigned long long*)&stats[0], (unsigned long long)m);
+    atomicAdd((unsigned long long*)&stats[1], (unsigned long long)s);
+  }
 }
 
 __global__ void k_cnt_to_ll(const int* __restrict__ cnt, int n, long long* __restrict__ out) {
@@ -219,26 +236,37 @@ void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStr
   Grid g;
   memcpy(&g, grid_blob, sizeof(g));
   const float band = fp32_band(cut);
-  cnt.resize(nrows + 1);
-  out.off.resize(nrows + 1);
   const int warps_per_block = 8;
   const int blocks = (nrows + warps_per_block - 1) / warps_per_block;
-  if (nrows > 0)
-    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, cnt.p, nullptr, nullptr);
-  cntll.resize(nrows + 1);
-  k_cnt_to_ll<<<(nrows + 256) / 256, 256, 0, st>>>(cnt.p, nrows, cntll.p);
-  size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, cntll.p, out.off.p, nrows + 1, st);
-  temp.resize(need + 16);
-  cub::DeviceScan::ExclusiveSum(temp.p, need, cntll.p, out.off.p, nrows + 1, st);
-  long long total = 0;
-  RXB_CUDA(cudaMemcpyAsync(&total, out.off.p + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  RXB_CUDA(cudaStreamSynchronize(st));
-  out.nnz = total;
+  out.cnt.resize(nrows + 1);
+  out.off.resize(nrows + 1);
+  out.stats.resize(2);
   out.nrows = nrows;
-  out.idx.resize((size_t)(total > 0 ? total : 1));
-  if (nrows > 0)
-    k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, nullptr, out.off.p, out.idx.p);
+  auto stats = [&](long long* host2) {
+    RXB_CUDA(cudaMemsetAsync(out.stats.p, 0, 2 * sizeof(long long), st));
+    if (nrows > 0) k_cnt_stats<<<std::min(1024, (nrows + 255) / 256), 256, 0, st>>>(out.cnt.p, nrows, out.stats.p);
+    RXB_CUDA(cudaMemcpyAsync(host2, out.stats.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    RXB_CUDA(cudaStreamSynchronize(st));
+  };
+  auto stride_for = [](long long longest) { return (int)(((longest + longest / 16 + 32) + 31) / 32 * 32); };
+  long long got[2] = {0, 0};
+  if (out.stride == 0 && nrows > 0) {   // first build: one counting pass sizes the stride
+    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, out.cnt.p, nullptr, nullptr, 0);
+    stats(got);
+    out.stride = stride_for(got[0]);
+  }
+  if (out.stride == 0) out.stride = 32;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    out.slots = (long long)nrows * out.stride;
+    out.idx.resize((size_t)std::max<long long>(out.slots, 1));
+    if (nrows > 0)
+      k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, out.cnt.p, out.off.p,
+                                            out.idx.p, out.stride);
+    stats(got);
+    if (got[0] <= out.stride) break;
+    out.stride = stride_for(got[0]);     // a row outgrew the stride of the previous build: run the pass again
+  }
+  out.nnz = got[1];
   RXB_CUDA(cudaGetLastError());
 }
 

@@ -36,7 +36,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
   for (int i = wg; i < v.n; i += nwg) {
     const double4 pi = v.xq[i];
     const int ti = v.type[i];
-    const long long beg = v.vl_off[i], end = v.vl_off[i + 1];
+    const long long beg = v.vl_off[i], end = beg + v.vl_cnt[i];
     // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work)
     long long w = beg;
     const float4 fi = v.xf[i];

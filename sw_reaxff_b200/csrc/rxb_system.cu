@@ -483,8 +483,8 @@ DevView System::view() {
     v.bond_band = cells_a_.fp32_band(ff.ctl.bond_cut);
   }
   v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
-  v.vl_off = vl.off.p; v.vl_idx = vl.idx.p;
-  v.bc_off = bc.off.p; v.bc_idx = bc.idx.p;
+  v.vl_off = vl.off.p; v.vl_idx = vl.idx.p; v.vl_cnt = vl.cnt.p;
+  v.bc_off = bc.off.p; v.bc_idx = bc.idx.p; v.bc_cnt = bc.cnt.p;
   v.hc_off = nullptr; v.hc_idx = nullptr;
   v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
   v.b_start = b_start.p; v.b_cnt = b_cnt.p; v.b_cursor = b_cursor.p; v.overflow = overflow.p;
@@ -509,8 +509,8 @@ void System::build_neighbors() {
   const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
   cells_b_.build(xq.p, N, cb, bc, st_);
-  far_idx.resize((size_t)std::max<long long>(vl.nnz, 1));
-  H_val.resize((size_t)std::max<long long>(vl.nnz, 1));
+  far_idx.resize((size_t)std::max<long long>(vl.slots, 1));
+  H_val.resize((size_t)std::max<long long>(vl.slots, 1));
   kernel_launches += 12;
   tock(t_NEIGH);
 }

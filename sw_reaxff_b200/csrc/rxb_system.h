@@ -55,11 +55,17 @@ struct DBuf {  // grow-only device buffer (contents are NOT preserved across gro
   size_t bytes() const { return cap * sizeof(T); }
 };
 
+// Neighbour rows at a fixed stride: row i occupies idx[off[i] .. off[i] + cnt[i]) with off[i] = i * stride.  The stride
+// (max row length of the previous build + slack, a multiple of 32 ints so rows start on 128-byte lines) lets a rebuild run
+// ONE pass — no count pass, no scan; a row that outgrows it triggers a re-run with a larger stride.
 struct Csr {
   DBuf<long long> off;
-  DBuf<int> idx;
-  long long nnz = 0;
+  DBuf<int> idx, cnt;
+  DBuf<long long> stats;   // device: [0] max row length, [1] sum of row lengths
+  long long nnz = 0;       // sum of cnt
+  long long slots = 0;     // nrows * stride
   int nrows = 0;
+  int stride = 0;
 };
 
 struct CellList {
