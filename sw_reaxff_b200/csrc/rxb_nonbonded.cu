@@ -37,30 +37,41 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
     const double4 pi = v.xq[i];
     const int ti = v.type[i];
     const long long beg = v.vl_off[i], end = beg + v.vl_cnt[i];
-    // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work)
+    // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work).
+    // The chain index load -> position gather is pure latency, so four chunks of 32 candidates are kept in flight:
+    // all index loads are issued first, then all gathers, then the tests.
     long long w = beg;
     const float4 fi = v.xf[i];
     const float lo2 = (float)qc.far2 - v.far_band, hi2 = (float)qc.far2 + v.far_band;
-    for (long long k0 = beg; k0 < end; k0 += 32) {
-      const long long k = k0 + lane;
-      bool hit = false;
-      int j = 0;
-      if (k < end) {
-        j = v.vl_idx[k];
-        // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
-        // r^2 <= cut^2 decision is still the fp64 one
-        const float4 fj = v.xf[j];
-        const float ex = fj.x - fi.x, ey = fj.y - fi.y, ez = fj.z - fi.z;
-        const float r2f = ex * ex + ey * ey + ez * ez;
-        if (r2f < lo2) hit = true;
-        else if (r2f <= hi2) {
-          const double4 pj = v.xq[j];
-          hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
-        }
+    constexpr int kU = 4;
+    for (long long k0 = beg; k0 < end; k0 += 32 * kU) {
+      int jj[kU];
+      float4 fj[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const long long k = k0 + 32 * u + lane;
+        jj[u] = k < end ? __ldcs(v.vl_idx + k) : -1;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) v.far_idx[w + __popc(m & ((1u << lane) - 1))] = j;
-      w += __popc(m);
+#pragma unroll
+      for (int u = 0; u < kU; u++) fj[u] = jj[u] >= 0 ? v.xf[jj[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        bool hit = false;
+        if (jj[u] >= 0) {
+          // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
+          // r^2 <= cut^2 decision is still the fp64 one
+          const float ex = fj[u].x - fi.x, ey = fj[u].y - fi.y, ez = fj[u].z - fi.z;
+          const float r2f = ex * ex + ey * ey + ez * ez;
+          if (r2f < lo2) hit = true;
+          else if (r2f <= hi2) {
+            const double4 pj = v.xq[jj[u]];
+            hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) v.far_idx[w + __popc(m & ((1u << lane) - 1))] = jj[u];
+        w += __popc(m);
+      }
     }
     const int num = (int)(w - beg);
     if (lane == 0) v.far_num[i] = num;
@@ -69,38 +80,54 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
     // Rows of hydrogen atoms also emit their hydrogen-bond partner candidates here (acceptor-type j within hbond_cut:
     // Init_Forces_noQEq_HB_Full_C, reaxc_forces_sw64.c:787-863) while x_j, type_j and r are in registers.
     const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
-    for (int k0 = 0; k0 < num; k0 += 32) {
-      const int k = k0 + lane;
-      bool cand = false;
-      int j = -1;
-      if (k < num) {
-        j = v.far_idx[beg + k];
-        const double4 pj = v.xq[j];
-        const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
-        const int tj = v.type[j];
-        double val = 0.0;
-        if (ti >= 0 && tj >= 0) {
-          const double r = sqrt(r2);
-          if (r2 <= qc.swb2) {
-            double T = qc.Tap[7] * r + qc.Tap[6];
-            T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
-            T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-            // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
-            val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
-          }
-          cand = is_H && atom[tj].p_hbond == 2 && r <= hbond_cut;
-        }
-        v.H_val[beg + k] = val;
+    constexpr int kV = 2;
+    for (int k0 = 0; k0 < num; k0 += 32 * kV) {
+      int jj[kV];
+      double4 pjv[kV];
+      int tjv[kV];
+#pragma unroll
+      for (int u = 0; u < kV; u++) {
+        const int k = k0 + 32 * u + lane;
+        jj[u] = k < num ? v.far_idx[beg + k] : -1;
       }
-      if (is_H) {
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(W.n_hb, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (cand) {
-            const int o = base + __popc(m & ((1u << lane) - 1));
-            if (o < W.cap_hb) W.hb[o] = make_int4(i, j, 0, 0);
+#pragma unroll
+      for (int u = 0; u < kV; u++) {
+        pjv[u] = jj[u] >= 0 ? v.xq[jj[u]] : make_double4(0, 0, 0, 0);
+        tjv[u] = jj[u] >= 0 ? v.type[jj[u]] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kV; u++) {
+        const int k = k0 + 32 * u + lane;
+        bool cand = false;
+        const int j = jj[u];
+        if (j >= 0) {
+          const double4 pj = pjv[u];
+          const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
+          const int tj = tjv[u];
+          double val = 0.0;
+          if (ti >= 0 && tj >= 0) {
+            const double r = sqrt(r2);
+            if (r2 <= qc.swb2) {
+              double T = qc.Tap[7] * r + qc.Tap[6];
+              T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
+              T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
+              // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
+              val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
+            }
+            cand = is_H && atom[tj].p_hbond == 2 && r <= hbond_cut;
+          }
+          v.H_val[beg + k] = val;
+        }
+        if (is_H) {
+          const unsigned m = __ballot_sync(0xffffffffu, cand);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(W.n_hb, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) {
+              const int o = base + __popc(m & ((1u << lane) - 1));
+              if (o < W.cap_hb) W.hb[o] = make_int4(i, j, 0, 0);
+            }
           }
         }
       }
