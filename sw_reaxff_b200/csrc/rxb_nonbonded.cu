@@ -136,7 +136,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
 }
 
 template <bool EV>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 k_nonbonded(DevView v, DevParams P) {
   __shared__ double sh[9][kWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -155,13 +155,23 @@ k_nonbonded(DevView v, DevParams P) {
     const long long beg = v.vl_off[i];
     const int num = v.far_num[i];
     double fx = 0, fy = 0, fz = 0;
+    // two-stage software pipeline over the row: the column index of chunk t+2 and the (position, type) gather of chunk
+    // t+1 are in flight while chunk t does its ~250 fp64 instructions per pair
+    const int* __restrict__ cols = v.far_idx + beg;
+    int j_cur = lane < num ? cols[lane] : -1;
+    int j_nxt = 32 + lane < num ? cols[32 + lane] : -1;
+    double4 p_cur = make_double4(0, 0, 0, 0);
+    int t_cur = -1;
+    if (j_cur >= 0) { p_cur = v.xq[j_cur]; t_cur = v.type[j_cur]; }
     for (int k0 = 0; k0 < num; k0 += 32) {
-      const int k = k0 + lane;
-      if (k >= num) continue;
-      const int j = v.far_idx[beg + k];
-      const int tj = v.type[j];
+      const int j_nn = k0 + 64 + lane < num ? cols[k0 + 64 + lane] : -1;
+      double4 p_nxt = make_double4(0, 0, 0, 0);
+      int t_nxt = -1;
+      if (j_nxt >= 0) { p_nxt = v.xq[j_nxt]; t_nxt = v.type[j_nxt]; }
+      const int tj = t_cur;
+      const double4 pj = p_cur;
+      j_cur = j_nxt; p_cur = p_nxt; t_cur = t_nxt; j_nxt = j_nn;
       if (tj < 0) continue;
-      const double4 pj = v.xq[j];
       const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
       const double r2 = dist2_rn(dx, dy, dz);
       if (!(r2 <= nonb_cut2)) continue;
