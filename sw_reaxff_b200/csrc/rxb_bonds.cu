@@ -51,21 +51,27 @@ k_bond_list(DevView v, DevParams P) {
     // Phase 1 (cheap, all lanes): distance filter, survivors are queued.  Phase 2 (6 transcendentals per pair) runs on
     // FULL warps drained from the queue: only ~30 % of the (bond_cut + skin) candidates are inside bond_cut, so doing the
     // math in place would leave two thirds of the lanes idle.
+    // the candidate index of chunk c+2 and the shadow-position gather of chunk c+1 are issued while chunk c is tested
+    int j_cur = beg + lane < end ? v.bc_idx[beg + lane] : -1;
+    int j_nxt = beg + 32 + lane < end ? v.bc_idx[beg + 32 + lane] : -1;
+    float4 f_cur = j_cur >= 0 ? v.xf[j_cur] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long k0 = beg; k0 < end || qn > 0; k0 += 32) {
       if (k0 < end) {
-        const long long k = k0 + lane;
+        const int j_nn = k0 + 64 + lane < end ? v.bc_idx[k0 + 64 + lane] : -1;
+        const float4 f_nxt = j_nxt >= 0 ? v.xf[j_nxt] : make_float4(0.f, 0.f, 0.f, 0.f);
         bool near = false;
-        int j = -1, tjf = -1;
+        const int j = j_cur;
+        int tjf = -1;
         float r2f = 0.0f;
-        if (k < end) {
-          j = v.bc_idx[k];
+        if (j >= 0) {
           // fp32 shadow (position + type in 16 bytes): a conservative superset goes to the queue, the exact fp64 tests
           // (d <= bond_cut, BO' >= bo_cut) are applied when the candidate is drained
-          const float4 fj = v.xf[j];
+          const float4 fj = f_cur;
           const float ex = fj.x - fi.x, ey = fj.y - fi.y, ez = fj.z - fi.z;
           r2f = ex * ex + ey * ey + ez * ez;
           tjf = __float_as_int(fj.w);
         }
+        j_cur = j_nxt; f_cur = f_nxt; j_nxt = j_nn;
         float thr = __shfl_sync(0xffffffffu, thr_lane, tjf & 31);
         if (tjf >= 32) { const double dm = P.pair[ti * nt + tjf].d_bond_max; thr = __double2float_ru(dm * dm) + v.bond_band; }
         near = tjf >= 0 && r2f <= thr;
