@@ -635,14 +635,27 @@ void System::md_make_ghosts() {
 // Two-stream step: the bond list -> bond orders -> multi-body -> angle/torsion/hbond chain does not
 // depend on this step's charges, so it runs on st2_ while the latency/HBM-bound CG solve runs on st_.  Only the hydrogen
 // bond enumeration needs this step's far list (event after K-farH); K-nb needs q; K-dbond joins both.
+// RXB_OVERLAP_DEBUG=1: time the two streams of the overlapped step with CUDA events (development aid)
+namespace {
+struct OverlapDbg {
+  bool on = getenv("RXB_OVERLAP_DEBUG") != nullptr;
+  cudaEvent_t e[8] = {};
+  double acc[8] = {};
+  long steps = 0;
+  void init() { if (!e[0]) for (auto& x : e) cudaEventCreate(&x); }
+} g_odbg;
+}  // namespace
+
 void System::after_far_hook() {
   if (!hook_after_far_) return;
   hook_after_far_ = false;
   DevView v = view();
   RXB_CUDA(cudaEventRecord(ev_far_, st_));
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[2], st_);    // end of K-farH
   RXB_CUDA(cudaStreamWaitEvent(st2_, ev_far_, 0));
   launch_bonded_part2(*this, v, dp_, st2_);
   RXB_CUDA(cudaEventRecord(ev_join_, st2_));
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[4], st2_);   // end of the bonded chain
 }
 
 // The step's force evaluation in two halves so that the bond list -> bond order -> bonded chain (second stream) overlaps
@@ -651,6 +664,7 @@ void System::after_far_hook() {
 void System::overlapped_front() {
   if (chain_inflight_) cancel_inflight();
   DevView v = view();
+  if (g_odbg.on) { g_odbg.init(); cudaEventRecord(g_odbg.e[0], st_); }
   update_shadow(st_);
   RXB_CUDA(cudaMemsetAsync(f.p, 0, (size_t)3 * N * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
@@ -661,9 +675,11 @@ void System::overlapped_front() {
   launch_bond_list(*this, v, dp_, st2_);
   launch_bond_orders(*this, v, dp_, st2_);
   launch_bonded_part1(*this, v, dp_, st2_);
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[1], st2_);   // end of bond list + BO + multi
   hook_after_far_ = true;
   chain_inflight_ = true;
   qeq_pre_force();                       // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[3], st_);    // end of CG
 }
 
 void System::cancel_inflight() {         // the atoms change before the pair style consumed the chain: just join the streams
@@ -677,8 +693,10 @@ void System::overlapped_back(bool eflag, bool vflag) {
   chain_inflight_ = false;
   qeq_ran_this_step_ = false;
   launch_nonbonded(*this, v, dp_, ev, st_);
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[5], st_);    // end of nonbonded
   RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
   launch_dbond(*this, v, dp_, st_);
+  if (g_odbg.on) cudaEventRecord(g_odbg.e[6], st_);    // end of dbond
   if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
   int h[2], wk[4];
   RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
@@ -690,6 +708,16 @@ void System::overlapped_back(bool eflag, bool vflag) {
     RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
   }
   RXB_CUDA(cudaStreamSynchronize(st_));
+  if (g_odbg.on) {
+    cudaStreamSynchronize(st2_);
+    float ms;
+    for (int k = 1; k <= 6; k++) { cudaEventElapsedTime(&ms, g_odbg.e[0], g_odbg.e[k]); g_odbg.acc[k] += ms; }
+    if (++g_odbg.steps % 20 == 0) {
+      const double s = (double)g_odbg.steps;
+      fprintf(stderr, "overlap dbg (ms after step start): chain1 %.3f  farH %.3f  CG %.3f  chain2 %.3f  nonbonded %.3f  dbond %.3f\n",
+              g_odbg.acc[1] / s, g_odbg.acc[2] / s, g_odbg.acc[3] / s, g_odbg.acc[4] / s, g_odbg.acc[5] / s, g_odbg.acc[6] / s);
+    }
+  }
   num_bonds = h[0]; overflow_flag = h[1];
   num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
   if ((overflow_flag & 2) || wk[0] > cap_ang || wk[1] > cap_tor || wk[2] > cap_hb) {
