@@ -219,15 +219,15 @@ def run_b200(args, rank, world, local_rank):
     spmv_bytes = 12.0 * nnz_far + 16.0 * nall + 16.0 * natoms + 8.0 * natoms
     spmv_avg = spmv_ms * 1e-3 / max(spmv_calls, 1)
     # DRAM bytes of one k_spmv2 launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
-    # capture of this workload, profiles/r01c_ncu_full_k_spmv2.csv: 1.1302 GB + 4.6 MB
-    spmv_traffic = 1.1348e9 if tuple(cells) == (8, 8, 8) else None
+    # capture of this workload, profiles/r01d_ncu_full_k_spmv2.csv: 1.1138 GB + 4.4 MB
+    spmv_traffic = 1.1183e9 if tuple(cells) == (8, 8, 8) else None
     achieved = spmv_bytes / spmv_avg / 1e9
     step_ms = sum(prof[k][0] for k in ("neigh", "qeq_farH", "qeq_cg", "bond_list", "bond_orders", "bonded", "nonbonded", "dbond")) / nprof
     breakdown = {k: round(prof[k][0] / nprof, 4) for k in prof}
     roofline = {"kernel": "k_spmv2 (dual-RHS QEq SpMV, the largest single-kernel share of the step)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": spmv_traffic,
-                "traffic_source": "ncu --set full, profiles/r01c_ncu_full_k_spmv2.csv (dram read + write per launch)" if spmv_traffic else None,
+                "traffic_source": "ncu --set full, profiles/r01d_ncu_full_k_spmv2.csv (dram read + write per launch)" if spmv_traffic else None,
                 "algorithmic_bytes_per_launch": spmv_bytes,
                 "avg_launch_us": spmv_avg * 1e6, "launches_per_step": spmv_calls / nprof,
                 "share_of_step": (spmv_ms / nprof) / step_ms}
