@@ -467,7 +467,7 @@ k_hbond_items(DevView v, DevParams P, BondedWork W) {
 
 // ------------------------------------------------------------------------------------------------------------
 // K-angle: one thread per valence angle k-j-h   reaxc_torsion_angles_sunway.cpp:803-979
-__global__ void __launch_bounds__(kItemThreads)
+__global__ void __launch_bounds__(kItemThreads, 3)
 k_angle_items(DevView v, DevParams P, BondedWork W) {
   const int nitems = min(*W.n_ang, W.cap_ang);
   const double p_val6 = P.gp[14], p_val10 = P.gp[17];
@@ -580,7 +580,7 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
 
 // ------------------------------------------------------------------------------------------------------------
 // K-tors: one thread per torsion h-j-k-l (= i-j-k-l)   reaxc_torsion_angles_sunway.cpp:994-1290
-__global__ void __launch_bounds__(kItemThreads)
+__global__ void __launch_bounds__(kItemThreads, 4)
 k_torsion_items(DevView v, DevParams P, BondedWork W) {
   const int nitems = min(*W.n_tor, W.cap_tor);
   const double p_tor2 = P.gp[23], p_tor3 = P.gp[24], p_tor4 = P.gp[25], p_cot2 = P.gp[27];
