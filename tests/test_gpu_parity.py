@@ -389,3 +389,39 @@ def test_tabulated_long_range_mode(tmp_path):
         assert rel(res["pvector"], pvector_from_oracle(eo)) < tol, name
         assert rel(res["f"], fo) < 10 * tol, name
         assert rel(res["virial"], vo) < 10 * tol, name
+
+
+def test_neighbor_rows_outgrowing_the_stride_are_rebuilt():
+    """Neighbour rows live at a fixed stride sized by the previous build.  Re-using one handle for a configuration whose
+    rows are ~60 % longer (1.05 -> 0.90 linear scale) must trigger the re-run with a larger stride and still give the
+    oracle's list and energies."""
+    from sw_reaxff_b200 import Rxb
+    r = Rxb(0)
+    r.pair_settings(H.CONTROL)
+    r.pair_coeff(H.FFIELD, H.ELEMENTS)
+    r.fix_qeq(0.0, 10.0, 1e-8)
+    for scale in (1.05, 0.90):
+        cfg = H.static_config(1, 1, 1, perturb=0.05, seed=31, scale=scale, qeq=False)
+        o = cfg["oracle"]
+        n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+        q0 = np.zeros(len(x))
+        o.set_atoms(n, x, ty, tg, q0)
+        o.build_neighbors(12.5)
+        o.qeq_init(0.0, 10.0, 1e-8)
+        o.qeq_set_hist(np.zeros((n, 5)), np.zeros((n, 5)))
+        o.qeq_pre_force(owner)
+        o.compute()
+        r.set_atoms(n, x, ty, tg, q0, owner)
+        r.qeq_set_history(np.zeros((n, 5)), np.zeros((n, 5)))
+        r.neigh_build()
+        off_o, nb_o = o.get_neighbors()
+        off_g, nb_g = r.neighbors(0)
+        assert np.array_equal(np.diff(off_g), np.diff(off_o)[:n])
+        for i in range(0, n, 7):
+            assert np.array_equal(np.sort(nb_g[off_g[i]:off_g[i + 1]]), nb_o[off_o[i]:off_o[i + 1]])
+        r.qeq_pre_force()
+        res = r.pair_compute(True, True)
+        eo, _ = o.energies()
+        assert rel(res["pvector"], pvector_from_oracle(eo)) < 1e-7
+        assert rel(res["f"], o.forces()) < 1e-5          # charges converged to 1e-8 on both sides
+    assert np.diff(off_g).max() > 1200                    # the compressed rows are far longer than the first build's stride
