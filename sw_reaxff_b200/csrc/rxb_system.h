@@ -247,7 +247,7 @@ class System {
   DBuf<long long> gcount, goff;
   DBuf<char> scan_temp;
   int cap_bonds = 0;
-  DBuf<int> map_d, old_of_new_, old_of_new_all_, new_of_old_, old_counts_d_;
+  DBuf<int> map_d;
 
  private:
   int device_;
