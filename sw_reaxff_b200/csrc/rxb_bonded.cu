@@ -405,6 +405,7 @@ k_enum(DevView v, DevParams P, BondedWork W) {
 }
 
 constexpr int kItemThreads = 128;
+constexpr int kItemBlocksPerSm = 8;   // 2 (to leave registers for a co-running SpMV) was measured: no gain for the step
 
 // ------------------------------------------------------------------------------------------------------------
 // K-hb: one thread per (H atom j, partner k) candidate emitted by K-farH; loops over the acceptor bonds of j
@@ -758,11 +759,11 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
   k_enum<<<kBlocks, kWarps * 32, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::HBOND, st);
-  k_hbond_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
+  k_hbond_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::VALTOR, st);
-  k_angle_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
-  k_torsion_items<<<148 * 8, kItemThreads, 0, st>>>(v, P, W);
+  k_angle_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
+  k_torsion_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   s.kernel_launches += 4;
 }

@@ -716,6 +716,8 @@ void System::overlapped_back(bool eflag, bool vflag) {
       const double s = (double)g_odbg.steps;
       fprintf(stderr, "overlap dbg (ms after step start): chain1 %.3f  farH %.3f  CG %.3f  chain2 %.3f  nonbonded %.3f  dbond %.3f\n",
               g_odbg.acc[1] / s, g_odbg.acc[2] / s, g_odbg.acc[3] / s, g_odbg.acc[4] / s, g_odbg.acc[5] / s, g_odbg.acc[6] / s);
+      for (double& a : g_odbg.acc) a = 0.0;
+      g_odbg.steps = 0;
     }
   }
   num_bonds = h[0]; overflow_flag = h[1];
