@@ -11,6 +11,7 @@
 //            pair virial + (-x_i (x) f_i) correction as reaxc_nonbonded_cpe.h:531-536 / reaxc_nonbonded_sw64.c:247-252.
 // Roofline: K-farH is HBM-bound (4 B/Verlet entry read, 12 B/far entry written); K-nb is fp64-compute bound
 // (2 pow + 2 exp + 1 cube-root-like pow per pair).
+#include "rxb_math.cuh"
 #include "rxb_system.h"
 
 namespace rxb {
@@ -30,56 +31,58 @@ struct QeqConst { double Tap[8]; double swb2; double far2; };
 
 __global__ void __launch_bounds__(kWarps * 32)
 k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const AtomPar* __restrict__ atom, double hbond_cut,
-        BondedWork W) {
+        double hbond_r2max, BondedWork W) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int i = wg; i < v.n; i += nwg) {
     const double4 pi = v.xq[i];
     const int ti = v.type[i];
-    const long long beg = v.vl_off[i], end = beg + v.vl_cnt[i];
+    const long long beg = v.vl_off[i];
     // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work).
     // The chain index load -> position gather is pure latency, so four chunks of 32 candidates are kept in flight:
-    // all index loads are issued first, then all gathers, then the tests.
-    long long w = beg;
+    // all index loads are issued first, then all gathers, then the tests.  Row-relative 32-bit offsets throughout.
+    const int* __restrict__ vl = v.vl_idx + beg;
+    int* __restrict__ far = v.far_idx + beg;
+    const int cnt_i = v.vl_cnt[i];
+    int w = 0;
     const float4 fi = v.xf[i];
     const float lo2 = (float)qc.far2 - v.far_band, hi2 = (float)qc.far2 + v.far_band;
+    const unsigned lt_mask = (1u << lane) - 1;
     constexpr int kU = 4;
-    for (long long k0 = beg; k0 < end; k0 += 32 * kU) {
+    for (int k0 = 0; k0 < cnt_i; k0 += 32 * kU) {
       int jj[kU];
       float4 fj[kU];
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        const long long k = k0 + 32 * u + lane;
-        jj[u] = k < end ? __ldcs(v.vl_idx + k) : -1;
+        const int k = k0 + 32 * u + lane;
+        jj[u] = k < cnt_i ? __ldcs(vl + k) : -1;
       }
 #pragma unroll
-      for (int u = 0; u < kU; u++) fj[u] = jj[u] >= 0 ? v.xf[jj[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < kU; u++) fj[u] = jj[u] >= 0 ? v.xf[jj[u]] : make_float4(1e18f, 1e18f, 1e18f, 0.f);
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        bool hit = false;
-        if (jj[u] >= 0) {
-          // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
-          // r^2 <= cut^2 decision is still the fp64 one
-          const float ex = fj[u].x - fi.x, ey = fj[u].y - fi.y, ez = fj[u].z - fi.z;
-          const float r2f = ex * ex + ey * ey + ez * ez;
-          if (r2f < lo2) hit = true;
-          else if (r2f <= hi2) {
-            const double4 pj = v.xq[jj[u]];
-            hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
-          }
+        // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
+        // r^2 <= cut^2 decision is still the fp64 one.  Idle lanes carry a far-away dummy position.
+        const float ex = fj[u].x - fi.x, ey = fj[u].y - fi.y, ez = fj[u].z - fi.z;
+        const float r2f = ex * ex + ey * ey + ez * ez;
+        bool hit = r2f < lo2;
+        if (!hit && r2f <= hi2) {
+          const double4 pj = v.xq[jj[u]];
+          hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) v.far_idx[w + __popc(m & ((1u << lane) - 1))] = jj[u];
+        if (hit) far[w + __popc(m & lt_mask)] = jj[u];
         w += __popc(m);
       }
     }
-    const int num = (int)(w - beg);
+    const int num = w;
     if (lane == 0) v.far_num[i] = num;
     __syncwarp();
     // pass 2: H values on the compacted row (every lane does the taper + cube root; xq[j] is an L1/L2 hit).
     // Rows of hydrogen atoms also emit their hydrogen-bond partner candidates here (acceptor-type j within hbond_cut:
     // Init_Forces_noQEq_HB_Full_C, reaxc_forces_sw64.c:787-863) while x_j, type_j and r are in registers.
     const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
+    double* __restrict__ hv = v.H_val + beg;
     constexpr int kV = 2;
     for (int k0 = 0; k0 < num; k0 += 32 * kV) {
       int jj[kV];
@@ -88,7 +91,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
 #pragma unroll
       for (int u = 0; u < kV; u++) {
         const int k = k0 + 32 * u + lane;
-        jj[u] = k < num ? v.far_idx[beg + k] : -1;
+        jj[u] = k < num ? far[k] : -1;
       }
 #pragma unroll
       for (int u = 0; u < kV; u++) {
@@ -106,17 +109,20 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
           const int tj = tjv[u];
           double val = 0.0;
           if (ti >= 0 && tj >= 0) {
-            const double r = sqrt(r2);
+            // r to 1 ulp from rsqrt, the 7-op cube root of rxb_math.cuh, and the hydrogen-bond reach tested on r^2
+            // against the largest r^2 whose correctly rounded root is <= hbond_cut (the same decision as sqrt(r2) <= cut)
+            const double r = r2 * rsqrt(r2);
             if (r2 <= qc.swb2) {
               double T = qc.Tap[7] * r + qc.Tap[6];
               T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
               T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-              // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); rcbrt differs by < 3e-13 relative
-              val = T * kEvToKcal * rcbrt(r2 * r + shld[ti * nt + tj]);
+              const double x3 = r2 * r + shld[ti * nt + tj];
+              // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); the cube root differs by < 3e-13 relative
+              val = T * kEvToKcal * fm::rcbrt_b(x3);
             }
-            cand = is_H && atom[tj].p_hbond == 2 && r <= hbond_cut;
+            cand = is_H && atom[tj].p_hbond == 2 && r2 <= hbond_r2max;
           }
-          v.H_val[beg + k] = val;
+          hv[k] = val;
         }
         if (is_H) {
           const unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -135,15 +141,40 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
   }
 }
 
+// K-nb.  One warp per row, one pair per lane, owner computes.  The kernel is bound by fp64 instruction issue (ncu: fp64
+// pipe 50 % busy with library exp/log at ~450 instructions per pair), so the work per pair is cut instead:
+//   * the straight-line table exp / log / cube root of rxb_math.cuh (11 / 10 / 7 DP ops instead of ~22 / ~35 / ~28),
+//     tables staged in shared memory,
+//   * r^p, (r^p + g^-p)^(1/p) and the derivative powers from 2 log + 2 exp (the serial form calls pow 5x), exp1 = exp2^2,
+//     1/(r^3 + g) = (cube root)^-3: each identity holds to ~1e-15 relative, far inside the 1e-8 parity tolerance,
+//   * the per-type-pair constants sit in shared memory (12 doubles per pair),
+//   * the column index of chunk t+2 and the (position, type) gather of chunk t+1 are in flight while chunk t computes.
+// 1.97 -> 1.44 ms at 89.5 M pairs.  (Carrying two pairs per lane for more ILP was measured slower: 168 registers, 12 warps/SM.)
+constexpr int kNbPar = 12;  // D, alpha, inv_r_vdW, powgi | alpha_over_r_vdW, gamma, r_vdW, rcore | ecore, acore, lgcij, lgre
+constexpr int kNbThreads = 256, kNbCtas = 2, kNbWarps = kNbThreads / 32;
+
 template <bool EV>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kNbThreads, kNbCtas)
 k_nonbonded(DevView v, DevParams P) {
-  __shared__ double sh[9][kWarps];
+  extern __shared__ __align__(16) double nb_smem[];
+  double* tab = nb_smem;                                   // fm::kTabDoubles
+  double* red = nb_smem + fm::kTabDoubles;                 // 9 * kNbWarps
+  const double2* pt = reinterpret_cast<const double2*>(red + 9 * kNbWarps);   // nt * nt * kNbPar doubles
+  const int nt = P.nt;
+  for (int t = threadIdx.x; t < fm::kTabDoubles; t += kNbThreads) tab[t] = fm::d_fm_tab[t];
+  for (int t = threadIdx.x; t < nt * nt; t += kNbThreads) {
+    const PairPar& w = P.pair[t];
+    double2* o = reinterpret_cast<double2*>(red + 9 * kNbWarps) + t * (kNbPar / 2);
+    o[0] = make_double2(w.D, w.alpha); o[1] = make_double2(w.inv_r_vdW, w.powgi_vdW1);
+    o[2] = make_double2(w.alpha_over_r_vdW, w.gamma); o[3] = make_double2(w.r_vdW, w.rcore);
+    o[4] = make_double2(w.ecore, w.acore); o[5] = make_double2(w.lgcij, w.lgre);
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   const double p_vdW1 = P.gp[28], p_vdW1i = 1.0 / p_vdW1;
   const double nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
-  const int vdw_type = P.ctl.vdw_type, lgflag = P.ctl.lgflag, nt = P.nt;
+  const int vdw_type = P.ctl.vdw_type, lgflag = P.ctl.lgflag;
   double Tap[8];
 #pragma unroll
   for (int t = 0; t < 8; t++) Tap[t] = P.ctl.Tap[t];
@@ -155,8 +186,6 @@ k_nonbonded(DevView v, DevParams P) {
     const long long beg = v.vl_off[i];
     const int num = v.far_num[i];
     double fx = 0, fy = 0, fz = 0;
-    // two-stage software pipeline over the row: the column index of chunk t+2 and the (position, type) gather of chunk
-    // t+1 are in flight while chunk t does its ~250 fp64 instructions per pair
     const int* __restrict__ cols = v.far_idx + beg;
     int j_cur = lane < num ? cols[lane] : -1;
     int j_nxt = 32 + lane < num ? cols[32 + lane] : -1;
@@ -177,7 +206,7 @@ k_nonbonded(DevView v, DevParams P) {
       if (!(r2 <= nonb_cut2)) continue;
       const double rinv = rsqrt(r2);
       const double r_ij = r2 * rinv;
-      const PairPar& tw = P.pair[ti * nt + tj];
+      const double2* w = pt + (ti * nt + tj) * (kNbPar / 2);
       double T = Tap[7] * r_ij + Tap[6];
       T = T * r_ij + Tap[5]; T = T * r_ij + Tap[4]; T = T * r_ij + Tap[3];
       T = T * r_ij + Tap[2]; T = T * r_ij + Tap[1]; T = T * r_ij + Tap[0];
@@ -185,39 +214,46 @@ k_nonbonded(DevView v, DevParams P) {
       dT = dT * r_ij + 5 * Tap[5]; dT = dT * r_ij + 4 * Tap[4]; dT = dT * r_ij + 3 * Tap[3];
       dT = dT * r_ij + 2 * Tap[2];
       dT += Tap[1] * rinv;
+      const double2 w0 = w[0];   // D, alpha
       double e_vdW, CEvd, e_core = 0, e_lg = 0;
       if (vdw_type == 1 || vdw_type == 3) {
-        // r^p, (r^p + g^-p)^(1/p) and the two derivative powers from 2 log + 2 exp (the serial form calls pow 5x);
-        // exp1 = exp2^2.  Each identity holds to ~1e-15 relative, far inside the 1e-8 parity tolerance.
-        const double powr = exp(p_vdW1 * log(r_ij));
-        const double ssum = powr + tw.powgi_vdW1;
-        const double fn13 = exp(p_vdW1i * log(ssum));
-        const double exp2 = exp(0.5 * tw.alpha * (1.0 - fn13 * tw.inv_r_vdW));
+        const double2 w1 = w[1];   // inv_r_vdW, powgi_vdW1
+        // arguments: p log r <= p log(nonb_cut); (1/p) log(r^p + g^-p) is bounded on both sides; the exp2 argument is
+        // <= alpha/2.  Only the two that can run away for r -> 0 / huge alpha are clamped (from below).
+        const double powr = fm::exp_b(fmax(p_vdW1 * (0.5 * fm::log_b(r2, tab)), -700.0), tab);
+        const double ssum = powr + w1.y;
+        const double fn13 = fm::exp_b(p_vdW1i * fm::log_b(ssum, tab), tab);
+        const double exp2 = fm::exp_b(fmax(0.5 * w0.y * (1.0 - fn13 * w1.x), -700.0), tab);
         const double exp1 = exp2 * exp2;
-        e_vdW = tw.D * (exp1 - 2.0 * exp2);
+        e_vdW = w0.x * (exp1 - 2.0 * exp2);
         const double dfn13 = (fn13 / ssum) * (powr * rinv * rinv);
-        CEvd = dT * e_vdW - T * tw.D * tw.alpha_over_r_vdW * (exp1 - exp2) * dfn13;
+        CEvd = dT * e_vdW - T * w0.x * w[2].x * (exp1 - exp2) * dfn13;
       } else {
-        const double exp1 = exp(tw.alpha * (1.0 - r_ij / tw.r_vdW));
-        const double exp2 = exp(0.5 * tw.alpha * (1.0 - r_ij / tw.r_vdW));
-        e_vdW = tw.D * (exp1 - 2.0 * exp2);
-        CEvd = dT * e_vdW - T * tw.D * (tw.alpha / tw.r_vdW) * (exp1 - exp2) / r_ij;
+        const double r_vdW = w[3].x;
+        const double exp2 = fm::exp_c(0.5 * w0.y * (1.0 - r_ij / r_vdW), tab);
+        const double exp1 = exp2 * exp2;
+        e_vdW = w0.x * (exp1 - 2.0 * exp2);
+        CEvd = dT * e_vdW - T * w0.x * (w0.y / r_vdW) * (exp1 - exp2) / r_ij;
       }
       if (vdw_type == 2 || vdw_type == 3) {
-        e_core = tw.ecore * exp(tw.acore * (1.0 - (r_ij / tw.rcore)));
-        const double de_core = -(tw.acore / tw.rcore) * e_core;
+        const double rcore = w[3].y;
+        const double2 w4 = w[4];   // ecore, acore
+        e_core = w4.x * fm::exp_c(w4.y * (1.0 - (r_ij / rcore)), tab);
+        const double de_core = -(w4.y / rcore) * e_core;
         CEvd += dT * e_core + T * de_core / r_ij;
         if (lgflag) {
-          const double r5 = pow(r_ij, 5.0), r6 = pow(r_ij, 6.0), re6 = pow(tw.lgre, 6.0);
-          e_lg = -(tw.lgcij / (r6 + re6));
+          const double2 w5 = w[5];   // lgcij, lgre
+          const double r5 = pow(r_ij, 5.0), r6 = pow(r_ij, 6.0), re6 = pow(w5.y, 6.0);
+          e_lg = -(w5.x / (r6 + re6));
           const double de_lg = -6.0 * e_lg * r5 / (r6 + re6);
           CEvd += dT * e_lg + T * de_lg / r_ij;
         }
       }
-      const double dr3gamij_1 = r2 * r_ij + tw.gamma;
-      const double inv3 = rcbrt(dr3gamij_1);  // reference: 1/pow(x, 0.33333333333333); differs by < 3e-14 relative
+      const double dr3gamij_1 = r2 * r_ij + w[2].y;
+      // reference: 1/pow(x, 0.33333333333333); the cube root differs from it by < 3e-14 relative.  1/x = inv3^3.
+      const double inv3 = fm::rcbrt_b(dr3gamij_1);
       const double qq = kCele * pi.w * pj.w;
-      const double CEclmb = qq * (dT - T * r_ij / dr3gamij_1) * inv3;
+      const double CEclmb = qq * (dT - T * r_ij * (inv3 * inv3 * inv3)) * inv3;
       const double ftot = CEvd + CEclmb;  // f_i = +ftot * dvec  (reference: fCdDelta[i] += -ftot*dvec, f = -fCdDelta)
       fx += ftot * dx; fy += ftot * dy; fz += ftot * dz;
       if (EV) {
@@ -247,12 +283,12 @@ k_nonbonded(DevView v, DevParams P) {
 #pragma unroll
     for (int k = 0; k < 9; k++) {
       const double s = warp_sum(vals[k]);
-      if (lane == 0) sh[k][wib] = s;
+      if (lane == 0) red[k * kNbWarps + wib] = s;
     }
     __syncthreads();
     if (threadIdx.x < 9) {
       double s = 0;
-      for (int w = 0; w < kWarps; w++) s += sh[threadIdx.x][w];
+      for (int q = 0; q < kNbWarps; q++) s += red[threadIdx.x * kNbWarps + q];
       if (s != 0.0) {
         if (threadIdx.x == 0) atomicAdd(&v.en[E_VDW], s);
         else if (threadIdx.x == 1) atomicAdd(&v.en[E_ELE], s);
@@ -363,7 +399,12 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   qc.far2 = far * far;
   BondedWork W = s.bonded_work();
   RXB_CUDA(cudaMemsetAsync(W.n_hb, 0, sizeof(int), st));
-  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, P.ctl.hbond_cut, W);
+  // largest r^2 with sqrt(r^2) <= hbond_cut in round-to-nearest
+  const double hc = P.ctl.hbond_cut;
+  double hb2 = hc * hc;
+  while (std::sqrt(std::nextafter(hb2, INFINITY)) <= hc) hb2 = std::nextafter(hb2, INFINITY);
+  while (hb2 > 0.0 && std::sqrt(hb2) > hc) hb2 = std::nextafter(hb2, 0.0);
+  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
   s.kernel_launches++;
 }
 
@@ -372,8 +413,13 @@ void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cu
   if (P.lut) {   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables (reaxc_forces_sunway.cpp:148-160)
     if (evflag) k_nonbonded_tab<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
     else k_nonbonded_tab<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  } else if (evflag) k_nonbonded<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-  else k_nonbonded<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+  } else {
+    // math tables + block reduction scratch + 12 constants per type pair (96 B x nt^2: 4 types 1.5 KB, 40 types 154 KB)
+    const size_t smem = sizeof(double) * (fm::kTabDoubles + 9 * kNbWarps + (size_t)P.nt * P.nt * kNbPar);
+    auto kern = evflag ? k_nonbonded<true> : k_nonbonded<false>;
+    if (smem > 48 * 1024) RXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<148 * kNbCtas * 4, kNbThreads, smem, st>>>(v, P);
+  }
   s.kernel_launches++;
 }
 
