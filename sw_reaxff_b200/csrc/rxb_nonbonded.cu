@@ -144,7 +144,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
 // K-nb.  One warp per row, one pair per lane, owner computes.  The kernel is bound by fp64 instruction issue (ncu: fp64
 // pipe 50 % busy with library exp/log at ~450 instructions per pair), so the work per pair is cut instead:
 //   * the straight-line table exp / log / cube root of rxb_math.cuh (11 / 10 / 7 DP ops instead of ~22 / ~35 / ~28),
-//     tables staged in shared memory,
+//     tables staged in shared memory and small enough that a warp's 32 lookups never conflict,
 //   * r^p, (r^p + g^-p)^(1/p) and the derivative powers from 2 log + 2 exp (the serial form calls pow 5x), exp1 = exp2^2,
 //     1/(r^3 + g) = (cube root)^-3: each identity holds to ~1e-15 relative, far inside the 1e-8 parity tolerance,
 //   * the per-type-pair constants sit in shared memory (12 doubles per pair),
@@ -156,7 +156,7 @@ constexpr int kNbThreads = 256, kNbCtas = 2, kNbWarps = kNbThreads / 32;
 template <bool EV>
 __global__ void __launch_bounds__(kNbThreads, kNbCtas)
 k_nonbonded(DevView v, DevParams P) {
-  extern __shared__ __align__(16) double nb_smem[];
+  extern __shared__ __align__(128) double nb_smem[];
   double* tab = nb_smem;                                   // fm::kTabDoubles
   double* red = nb_smem + fm::kTabDoubles;                 // 9 * kNbWarps
   const double2* pt = reinterpret_cast<const double2*>(red + 9 * kNbWarps);   // nt * nt * kNbPar doubles
@@ -404,7 +404,11 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   double hb2 = hc * hc;
   while (std::sqrt(std::nextafter(hb2, INFINITY)) <= hc) hb2 = std::nextafter(hb2, INFINITY);
   while (hb2 > 0.0 && std::sqrt(hb2) > hc) hb2 = std::nextafter(hb2, 0.0);
-  k_far_H<<<kBlocks, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  // rows are dealt round-robin to the warps of a grid that is a whole number of waves of resident CTAs (measured:
+  // 1 / 2 / 4 waves 0.997 / 0.985 / 0.977 ms; the former fixed 1184 CTAs were 1.6 waves at this register count: 1.12 ms)
+  static int per_sm = 0;
+  if (!per_sm) RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_far_H, kWarps * 32, 0));
+  k_far_H<<<148 * per_sm * 4, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
   s.kernel_launches++;
 }
 
