@@ -22,7 +22,6 @@ constexpr double kKcalToEv = 23.02;      // KCALpMOL_to_EV
 constexpr double kHbThreshold = 1e-2;    // HB_THRESHOLD
 constexpr double kMinSine = 1e-10;       // MIN_SINE
 constexpr int kWarps = 8;
-constexpr int kBlocks = 148 * 4;
 
 __device__ __forceinline__ double sqr(double a) { return a * a; }
 __device__ __forceinline__ double deg2rad(double a) { return a * kConstPI / 180.0; }
@@ -405,7 +404,6 @@ k_enum(DevView v, DevParams P, BondedWork W) {
 }
 
 constexpr int kItemThreads = 128;
-constexpr int kItemBlocksPerSm = 8;   // 2 (to leave registers for a co-running SpMV) was measured: no gain for the step
 
 // ------------------------------------------------------------------------------------------------------------
 // K-hb: one thread per (H atom j, partner k) candidate emitted by K-farH; loops over the acceptor bonds of j
@@ -756,14 +754,18 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
   if (v.n == 0) return;
   BondedWork W = s.bonded_work();
   int t = s.tick(StepTimers::ENUM, st);
-  k_enum<<<kBlocks, kWarps * 32, 0, st>>>(v, P, W);
+  static int occ_enum = 0, occ_hb = 0, occ_ang = 0, occ_tor = 0;
+  // one wave of resident CTAs each (measured for the item kernels: 1 / 2 / 3 waves 1.81 / 1.82 / 1.84 ms for the chain;
+  // the former fixed 148 x 8 grids were 1.6 - 2.7 waves: 1.96 ms)
+  constexpr int kItemWaves = 1;
+  k_enum<<<wave_grid(k_enum, kWarps * 32, 1, occ_enum), kWarps * 32, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::HBOND, st);
-  k_hbond_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
+  k_hbond_items<<<wave_grid(k_hbond_items, kItemThreads, kItemWaves, occ_hb), kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::VALTOR, st);
-  k_angle_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
-  k_torsion_items<<<148 * kItemBlocksPerSm, kItemThreads, 0, st>>>(v, P, W);
+  k_angle_items<<<wave_grid(k_angle_items, kItemThreads, kItemWaves, occ_ang), kItemThreads, 0, st>>>(v, P, W);
+  k_torsion_items<<<wave_grid(k_torsion_items, kItemThreads, kItemWaves, occ_tor), kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   s.kernel_launches += 4;
 }
@@ -775,7 +777,8 @@ void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
 void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   (void)P;
   if (v.N == 0) return;
-  k_dbond<<<kBlocks, kWarps * 32, 0, st>>>(v, s.bonded_work());
+  static int occ_dbond = 0;
+  k_dbond<<<wave_grid(k_dbond, kWarps * 32, 1, occ_dbond), kWarps * 32, 0, st>>>(v, s.bonded_work());
   s.kernel_launches++;
 }
 

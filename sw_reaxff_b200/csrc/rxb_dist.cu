@@ -57,6 +57,7 @@ struct Dist {
   int nsend = 0;
   DBuf<int> greq, sendlist, cnt_d, cnt_all_d;
   DBuf<double> sendbuf, recvbuf;
+  DBuf<double> dots_all;                 // [world][4]: every rank's partial CG dot products (dist_forward2_dots)
 };
 
 namespace {
@@ -491,6 +492,42 @@ void System::dist_forward2(double2* vec) {
   const int nghost = N - n;
   if (nghost > 0) k_ghost_d_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, D.gsrc.p, D.d_all.p, vec);
   kernel_launches++;
+}
+
+// sum of the per-rank partials in rank order: every rank adds the same numbers in the same order, so all ranks hold the
+// bit-identical result (and take the same convergence decisions)
+__global__ void k_sum_dots(int world, int rank, const double* __restrict__ all, double* __restrict__ dots) {
+  const int c = threadIdx.x;
+  if (c >= 4) return;
+  const double mine = dots[c];
+  double s = 0.0;
+  for (int r = 0; r < world; r++) s += (r == rank) ? mine : all[4 * r + c];
+  dots[c] = s;
+}
+
+// One exchange per CG iteration instead of two: the 4 partial dot products of the sweep travel in the SAME grouped
+// send/recv as the boundary values of d (to every rank, 32 bytes each), replacing the separate ncclAllReduce
+// (the reference: MPI_Allreduce + comm->forward_comm_fix per iteration, fix_qeq_reax_sunway.cpp:1108-1140).
+void System::dist_forward2_dots(double2* vec, double* dots) {
+  Dist& D = *dist_;
+  if (!D.p2p) { dist_allreduce(dots, 4); dist_forward2(vec); return; }
+  const int W = D.world;
+  D.dots_all.resize((size_t)4 * W);
+  double* v = reinterpret_cast<double*>(vec);
+  if (D.nsend > 0) k_pack<2><<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, v, D.sendbuf.p);
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    RXB_NCCL(ncclSend(dots, 4, ncclDouble, r, D.comm, st_));
+    RXB_NCCL(ncclRecv(D.dots_all.p + (size_t)4 * r, 4, ncclDouble, r, D.comm, st_));
+    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.sendbuf.p + (size_t)2 * D.soff[r], (size_t)2 * D.send_to[r], ncclDouble, r, D.comm, st_));
+    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(v + (size_t)2 * (n + D.goff[r]), (size_t)2 * D.need_from[r], ncclDouble, r, D.comm, st_));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  k_sum_dots<<<1, 32, 0, st_>>>(W, D.rank, D.dots_all.p, dots);
+  const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
+  if (g1 > g0) k_self_ghosts<2><<<nblk(g1 - g0), 256, 0, st_>>>(n, g0, g1, D.greq.p, v);
+  kernel_launches += 3;
 }
 
 void System::dist_reverse_f() {

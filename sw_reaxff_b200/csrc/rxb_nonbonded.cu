@@ -21,7 +21,6 @@ constexpr double kCele = 332.06371;  // C_ele
 constexpr double kEvToKcal = 14.4;   // EV_TO_KCAL_PER_MOL
 constexpr double kKcalToEv = 23.02;  // KCALpMOL_to_EV
 constexpr int kWarps = 8;
-constexpr int kBlocks = 148 * 8;
 
 __device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -406,17 +405,17 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   while (hb2 > 0.0 && std::sqrt(hb2) > hc) hb2 = std::nextafter(hb2, 0.0);
   // rows are dealt round-robin to the warps of a grid that is a whole number of waves of resident CTAs (measured:
   // 1 / 2 / 4 waves 0.997 / 0.985 / 0.977 ms; the former fixed 1184 CTAs were 1.6 waves at this register count: 1.12 ms)
-  static int per_sm = 0;
-  if (!per_sm) RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_far_H, kWarps * 32, 0));
-  k_far_H<<<148 * per_sm * 4, kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  static int occ = 0;
+  k_far_H<<<wave_grid(k_far_H, kWarps * 32, 4, occ), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
   s.kernel_launches++;
 }
 
 void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st) {
   if (v.n == 0) return;
   if (P.lut) {   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables (reaxc_forces_sunway.cpp:148-160)
-    if (evflag) k_nonbonded_tab<true><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
-    else k_nonbonded_tab<false><<<kBlocks, kWarps * 32, 0, st>>>(v, P);
+    static int occ_t = 0, occ_f = 0;
+    if (evflag) k_nonbonded_tab<true><<<wave_grid(k_nonbonded_tab<true>, kWarps * 32, 2, occ_t), kWarps * 32, 0, st>>>(v, P);
+    else k_nonbonded_tab<false><<<wave_grid(k_nonbonded_tab<false>, kWarps * 32, 2, occ_f), kWarps * 32, 0, st>>>(v, P);
   } else {
     // math tables + block reduction scratch + 12 constants per type pair (96 B x nt^2: 4 types 1.5 KB, 40 types 154 KB)
     const size_t smem = sizeof(double) * (fm::kTabDoubles + 9 * kNbWarps + (size_t)P.nt * P.nt * kNbPar);

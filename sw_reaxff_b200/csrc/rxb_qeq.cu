@@ -344,14 +344,15 @@ void System::qeq_pre_force() {
     k_cg_sweep<<<kVecBlocks, kVecThreads, 0, st_>>>(n, it, it == 1, qeq_tol, qeq_imax, q_Hdia_inv.p, q_q.p, q_x.p, q_r.p,
                                                    q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
     kernel_launches++;
-    if (dist_) dist_allreduce(Q->dots[(it + 1) % 3], 4);   // MPI_Allreduce(dot_local, 2) of each solve, :1132
-    const int par_next = (it & 1) ^ 1;  // state written by this sweep
+    const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
     if (it % qeq_check_every == 0 || it > qeq_imax) {
       RXB_CUDA(cudaMemcpyAsync(active_host, Q->st[par_next].active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
       RXB_CUDA(cudaStreamSynchronize(st_));
       if (!(active_host[0] | active_host[1])) break;
     }
-    forward(q_d.p);
+    // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange
+    if (dist_) dist_forward2_dots(q_d.p, Q->dots[(it + 1) % 3]);
+    else forward(q_d.p);
     spmv(q_d.p, q_q.p, Q, par_next);
   }
   // final charges

@@ -169,6 +169,7 @@ class System {
   void dist_set_p2p(bool on);    // false: whole-slab all-gather halos (debug / comparison)
   void dist_forward_xq();        // ghosts <- owners (x + image shift, q)
   void dist_forward2(double2* vec);
+  void dist_forward2_dots(double2* vec, double* dots);   // halo of vec + all-reduce of 4 dot products in one exchange
   void dist_reverse_f();
   size_t slab() const;           // elements every all-gathered local array must be able to hold
 
@@ -290,6 +291,15 @@ void launch_bonded(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_bonded_part1(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st);
+// Grid of a grid-stride kernel: a whole number of waves of the CTAs that fit on the 148 SMs at this kernel's register and
+// shared-memory footprint (a fixed 148 x k grid is a fractional number of waves whenever the footprint changes: measured
+// 13 % on the far-list kernel).  The occupancy is queried once per call site.
+template <class Kernel>
+inline int wave_grid(Kernel kernel, int threads, int waves, int& cache) {
+  if (!cache) RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cache, kernel, threads, 0));
+  return 148 * (cache > 0 ? cache : 1) * waves;
+}
+
 void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* qeq_tap, const double* shld, double swb,
                       cudaStream_t st);
 void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st);
