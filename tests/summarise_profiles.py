@@ -1,6 +1,7 @@
 """Turn the raw evidence of tests/gpu_profile_round.sh (gpurun_out/*) into the committed summaries under profiles/:
     python tests/summarise_profiles.py r01d
-  * profiles/<tag>_ncu_full_<kernel>.csv      selected metrics of every captured launch (from `ncu -i ... --page raw --csv`)
+  * profiles/<tag>_ncu_full_<kernel>.csv      selected metrics of the captured launches (raw pages exported on the box)
+  * profiles/<tag>_stalls.txt                 one line per kernel: utilisations and warp-stall mix
   * profiles/<tag>_launches_8x8x8.csv         the ncu launch list of bench.py's timed region, verbatim
   * profiles/<tag>_launches_8x8x8_summary.txt per-kernel totals and shares of that list
   * profiles/<tag>_bench_8x8x8.json, profiles/<tag>_bench_reference_arm.json
@@ -21,23 +22,61 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size",
-        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second"]
+        "lts__t_bytes.sum", "l1tex__t_bytes.sum", "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active"] + [
+        f"smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio" for r in
+        ("long_scoreboard", "wait", "short_scoreboard", "math_pipe_throttle", "not_selected", "selected", "branch_resolving",
+         "lg_throttle", "barrier")]
 
+def num(r, ix, k):
+    try:
+        return float(r[ix[k]].replace(",", ""))
+    except (ValueError, KeyError):
+        return 0.0
+
+
+def gbs(r, ix, units, k):
+    scale = {"Tbyte/s": 1e3, "Gbyte/s": 1.0, "Mbyte/s": 1e-3, "Kbyte/s": 1e-6, "byte/s": 1e-9}
+    return num(r, ix, k) * scale.get(units[ix[k]], 0.0) if k in ix else 0.0
+
+
+stall_lines, seen = [], set()
 for f in sorted(os.listdir(OUT)):
-    if not (f.startswith(f"ncu_{TAG}_") and f.endswith(".ncu-rep")):
+    if not (f.startswith(f"ncu_{TAG}_") and f.endswith(".raw.csv")):
         continue
-    kernel = f[len(f"ncu_{TAG}_"):-len(".ncu-rep")]
-    raw = subprocess.run(["ncu", "-i", os.path.join(OUT, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+    rows = list(csv.reader(open(os.path.join(OUT, f))))
     hdr, units, data = rows[0], rows[1], rows[2:]
-    with open(os.path.join(PROF, f"{TAG}_ncu_full_{kernel}.csv"), "w", newline="") as fo:
-        w = csv.writer(fo)
-        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(data))])
-        for name in WANT:
-            if name in hdr:
-                i = hdr.index(name)
-                w.writerow([hdr[i], units[i]] + [d[i] for d in data])
-    print("wrote", kernel)
+    ix = {h: i for i, h in enumerate(hdr)}
+    by_kernel = collections.OrderedDict()
+    for r in data:
+        by_kernel.setdefault(r[ix["Kernel Name"]].split("(")[0].split("::")[-1].replace("<", "_").replace(">", ""), []).append(r)
+    stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+    for kernel, launches in by_kernel.items():
+        launches = launches[-2:]       # the last two captured launches of each kernel
+        with open(os.path.join(PROF, f"{TAG}_ncu_full_{kernel}.csv"), "w", newline="") as fo:
+            w = csv.writer(fo)
+            w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(launches))])
+            for name in WANT:
+                if name in ix:
+                    w.writerow([name, units[ix[name]]] + [d[ix[name]] for d in launches])
+        r = launches[-1]
+        tot = sum(num(r, ix, h) for h in stall) or 1.0
+        top = sorted(((num(r, ix, h), h) for h in stall), reverse=True)[:5]
+        stall_lines.append(
+            f"{kernel:18s} {r[ix['gpu__time_duration.sum']]:>9s} {units[ix['gpu__time_duration.sum']]}  regs {r[ix['launch__registers_per_thread']]:>3s}  "
+            f"grid {r[ix['launch__grid_size']]:>6s}  warps {num(r, ix, 'sm__warps_active.avg.pct_of_peak_sustained_active'):4.1f}%  "
+            f"issue {num(r, ix, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):4.1f}%  "
+            f"fp64 {num(r, ix, 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):4.1f}%  "
+            f"L1pipe {num(r, ix, 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'):4.1f}%  "
+            f"dram {gbs(r, ix, units, 'dram__bytes_read.sum.per_second') + gbs(r, ix, units, 'dram__bytes_write.sum.per_second'):6.0f} GB/s | "
+            + "  ".join(f"{h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {100 * v / tot:.0f}%" for v, h in top))
+        print("wrote", kernel)
+if stall_lines:
+    head = ["# ncu --set full (TATB 8x8x8, steady-state steps): per kernel, duration, registers, grid, resident warps, issue / fp64 /",
+            "# L1 data-pipe utilisation (% of peak), DRAM read+write rate, and the share of each warp-stall reason"]
+    open(os.path.join(PROF, f"{TAG}_stalls.txt"), "w").write("\n".join(head + stall_lines) + "\n")
+    print("\n".join(stall_lines))
 
 src = os.path.join(OUT, f"launches_{TAG}.csv")
 if os.path.exists(src):
