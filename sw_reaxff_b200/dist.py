@@ -177,7 +177,8 @@ def run_distributed(args, rank, world, local_rank, cells, H):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if getattr(args, "strong", False) else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (TATB 384-atom cell replicated by lattice translation, per-tag Gaussian velocities 300 K)",
         "config": {**config_for(cells), "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} bricks, {natoms_total // world} atoms per GPU, "
-                   "ghost shell 12.5 A, NCCL all-gather halo / reduce-scatter reverse / all-reduce dots inside the library",
+                   "ghost shell 12.5 A, grouped ncclSend/ncclRecv boundary exchange between neighbouring bricks (forward x/q/d, reverse f), "
+                   "the CG dot products ride in the same exchange, all inside the library",
                    "l2": "inputs larger than L2", "timing": "CUDA events on each rank's launch stream, max over ranks"},
         "clocks": cs.summary(), "gpu_launches": int(launches), "qeq_iterations_per_step": qeq_it / world / args.steps,
         "wall_ms_per_step": 1e3 * wall / args.steps,
