@@ -19,6 +19,7 @@ namespace rxb {
 namespace {
 
 constexpr double kSlack = 1e-6;  // Angstrom
+constexpr int kXFine = 2;        // x bins are bin_size / kXFine wide (x is the contiguous direction of the sorted order)
 
 struct Grid {
   double lo[3], inv[3], size[3];
@@ -114,12 +115,14 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
       dy = fmax(dy - kSlack, 0.0);
       const double rem = c2 - dz * dz - dy * dy;
       if (rem < 0.0) continue;
-      // trim the x run to the chord of the cutoff sphere (one bin of slack for rounding)
+      // trim the x run to the chord of the cutoff sphere.  bin_coord is monotonic in x, so the bins of x_i -+ half (same
+      // arithmetic, kSlack = 1e-6 A against the ulp-level rounding of the edges) bracket every atom inside the chord; the
+      // x bins are kXFine times finer than the y/z bins, so the run overshoots the chord by half a coarse bin on average
       const double half = sqrt(rem) + kSlack;
-      int x0 = (int)floor((pi.x - half - g.lo[0]) * g.inv[0]) - 1;
-      int x1 = (int)floor((pi.x + half - g.lo[0]) * g.inv[0]) + 1;
-      x0 = max(max(x0, bx - reach), 0);
-      x1 = min(min(x1, bx + reach), g.nb[0] - 1);
+      int x0 = (int)floor((pi.x - half - g.lo[0]) * g.inv[0]);
+      int x1 = (int)floor((pi.x + half - g.lo[0]) * g.inv[0]);
+      x0 = max(max(x0, bx - kXFine * reach), 0);
+      x1 = min(min(x1, bx + kXFine * reach), g.nb[0] - 1);
       const int rowbase = (cz * g.nb[1] + cy) * g.nb[0];
       const int kbeg = bin_start[rowbase + x0], kend = bin_start[rowbase + x1 + 1];
       for (int k0 = kbeg; k0 < kend; k0 += 32) {
@@ -205,7 +208,7 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   for (int t = 0; t < 3; t++) {
     double ext = got[3 + t] - got[t];
     if (!(ext > 1e-9)) ext = 1e-9;
-    int nb = (int)(ext / bin_size);
+    int nb = (int)(ext / (t == 0 ? bin_size / kXFine : bin_size));
     if (nb < 1) nb = 1;
     g.nb[t] = nb; g.lo[t] = got[t]; g.size[t] = ext / nb; g.inv[t] = nb / ext;
     nbins *= nb;
