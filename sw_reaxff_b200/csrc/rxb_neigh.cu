@@ -100,31 +100,46 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
   const int bx = bin_coord(pi.x, g.lo[0], g.inv[0], g.nb[0]);
   const int by = bin_coord(pi.y, g.lo[1], g.inv[1], g.nb[1]);
   const int bz = bin_coord(pi.z, g.lo[2], g.inv[2], g.nb[2]);
-  const long long base = (long long)i * stride;
+  const long long base_off = (long long)i * stride;
   int total = 0;
-  for (int cz = max(bz - reach, 0); cz <= min(bz + reach, g.nb[2] - 1); cz++) {
-    double dz = 0.0;
-    if (cz > bz) dz = (g.lo[2] + cz * g.size[2]) - pi.z;
-    else if (cz < bz) dz = pi.z - (g.lo[2] + (cz + 1) * g.size[2]);
-    dz = fmax(dz - kSlack, 0.0);  // bin edges are rounded; never prune a run that could hold a boundary pair
-    if (dz * dz > c2) continue;
-    for (int cy = max(by - reach, 0); cy <= min(by + reach, g.nb[1] - 1); cy++) {
-      double dy = 0.0;
-      if (cy > by) dy = (g.lo[1] + cy * g.size[1]) - pi.y;
-      else if (cy < by) dy = pi.y - (g.lo[1] + (cy + 1) * g.size[1]);
-      dy = fmax(dy - kSlack, 0.0);
-      const double rem = c2 - dz * dz - dy * dy;
-      if (rem < 0.0) continue;
-      // trim the x run to the chord of the cutoff sphere.  bin_coord is monotonic in x, so the bins of x_i -+ half (same
-      // arithmetic, kSlack = 1e-6 A against the ulp-level rounding of the edges) bracket every atom inside the chord; the
-      // x bins are kXFine times finer than the y/z bins, so the run overshoots the chord by half a coarse bin on average
-      const double half = sqrt(rem) + kSlack;
-      int x0 = (int)floor((pi.x - half - g.lo[0]) * g.inv[0]);
-      int x1 = (int)floor((pi.x + half - g.lo[0]) * g.inv[0]);
-      x0 = max(max(x0, bx - kXFine * reach), 0);
-      x1 = min(min(x1, bx + kXFine * reach), g.nb[0] - 1);
-      const int rowbase = (cz * g.nb[1] + cy) * g.nb[0];
-      const int kbeg = bin_start[rowbase + x0], kend = bin_start[rowbase + x1 + 1];
+  // The (2 reach + 1)^2 bin rows (cz, cy) of the stencil: lane t works out the x run [kbeg, kend) of row t in the sorted
+  // order once (fp64 chord, two floors, two bin_start loads), then the warp walks the runs in (cz, cy) order.  Doing this
+  // per row inside the loops cost as many instructions as the candidate tests themselves (ncu: issue slots 78 % busy).
+  const int span = 2 * reach + 1, nrun = span * span;
+  for (int base = 0; base < nrun; base += 32) {
+    int kbeg_l = 0, kend_l = 0;
+    const int t_l = base + lane;
+    if (t_l < nrun) {
+      const int cz = bz - reach + t_l / span, cy = by - reach + t_l % span;
+      if (cz >= 0 && cz < g.nb[2] && cy >= 0 && cy < g.nb[1]) {
+        double dz = 0.0, dy = 0.0;
+        if (cz > bz) dz = (g.lo[2] + cz * g.size[2]) - pi.z;
+        else if (cz < bz) dz = pi.z - (g.lo[2] + (cz + 1) * g.size[2]);
+        dz = fmax(dz - kSlack, 0.0);  // bin edges are rounded; never prune a run that could hold a boundary pair
+        if (cy > by) dy = (g.lo[1] + cy * g.size[1]) - pi.y;
+        else if (cy < by) dy = pi.y - (g.lo[1] + (cy + 1) * g.size[1]);
+        dy = fmax(dy - kSlack, 0.0);
+        const double rem = c2 - dz * dz - dy * dy;
+        if (dz * dz <= c2 && rem >= 0.0) {
+          // trim the x run to the chord of the cutoff sphere.  bin_coord is monotonic in x, so the bins of x_i -+ half
+          // (same arithmetic, kSlack = 1e-6 A against the ulp-level rounding of the edges) bracket every atom inside the
+          // chord; the x bins are kXFine times finer than the y/z bins, so the run overshoots the chord by half a coarse
+          // bin on average
+          const double half = sqrt(rem) + kSlack;
+          int x0 = (int)floor((pi.x - half - g.lo[0]) * g.inv[0]);
+          int x1 = (int)floor((pi.x + half - g.lo[0]) * g.inv[0]);
+          x0 = max(max(x0, bx - kXFine * reach), 0);
+          x1 = min(min(x1, bx + kXFine * reach), g.nb[0] - 1);
+          if (x1 >= x0) {
+            const int rowbase = (cz * g.nb[1] + cy) * g.nb[0];
+            kbeg_l = bin_start[rowbase + x0]; kend_l = bin_start[rowbase + x1 + 1];
+          }
+        }
+      }
+    }
+    const int nhere = min(32, nrun - base);
+    for (int t = 0; t < nhere; t++) {
+      const int kbeg = __shfl_sync(0xffffffffu, kbeg_l, t), kend = __shfl_sync(0xffffffffu, kend_l, t);
       for (int k0 = kbeg; k0 < kend; k0 += 32) {
         const int k = k0 + lane;
         bool hit = false;
@@ -147,7 +162,7 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (FILL && hit) {
           const int pos = total + __popc(m & ((1u << lane) - 1));
-          if (pos < stride) idx[base + pos] = j;
+          if (pos < stride) idx[base_off + pos] = j;
         }
         total += __popc(m);
       }
@@ -155,8 +170,8 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
   }
   if (lane == 0) {
     cnt[i] = total;
-    if (FILL) off[i] = base;
-    if (FILL && i == nrows - 1) off[nrows] = base + stride;
+    if (FILL) off[i] = base_off;
+    if (FILL && i == nrows - 1) off[nrows] = base_off + stride;
   }
 }
 
