@@ -680,55 +680,66 @@ k_torsion_items(DevView v, DevParams P, BondedWork W) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarps * 32)
 k_dbond(DevView v, BondedWork W) {
-  const int lane = threadIdx.x & 31;
+  // 8 lanes per atom, 4 atoms per warp: a bond row has ~7.5 entries (20 when hot-compressed), so a warp per atom left
+  // three quarters of the lanes idle
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-  for (int i = wg; i < v.N; i += nwg) {
-    const int start = v.b_start[i], cnt = v.b_cnt[i];
-    if (cnt <= 0) continue;
-    const double dsx = v.dDeltap_self[3 * i], dsy = v.dDeltap_self[3 * i + 1], dsz = v.dDeltap_self[3 * i + 2];
-    const double cdd_i = v.CdDelta[i];
-    const double2 s56_i = W.sum56[i];  // (sum CEval5, sum CEval6) of the angles centred on i (zero for ghosts)
+  for (int i0 = 4 * wg; i0 < v.N; i0 += 4 * nwg) {
+    const int i = i0 + grp;
+    const bool live = i < v.N;
+    const int start = live ? v.b_start[i] : 0, cnt = live ? v.b_cnt[i] : 0;
     double fx = 0, fy = 0, fz = 0, buf_c = 0;
-    for (int e = lane; e < cnt; e += 32) {
-      const int p = start + e;
-      const int j = v.b_nbr[p];
-      const int sym = v.b_sym[p];
-      if (sym < 0) continue;
-      const double2 s56_j = W.sum56[j];
-      double Cdbo = v.b_Cdbo[p] + v.b_Cdbo[sym];
-      double Cdbopi = v.b_Cdbopi[p] + v.b_Cdbopi[sym];
-      double Cdbopi2 = v.b_Cdbopi2[p] + v.b_Cdbopi2[sym];
-      if (s56_i.x != 0.0 || s56_i.y != 0.0 || s56_j.x != 0.0 || s56_j.y != 0.0) {
-        const double bo_p = v.b_bo[p].x, bo_s = v.b_bo[sym].x;
-        const double p3 = bo_p * bo_p * bo_p, q3 = bo_s * bo_s * bo_s;
-        Cdbo += s56_i.y * (p3 * p3 * bo_p) + s56_j.y * (q3 * q3 * bo_s);
-        Cdbopi += s56_i.x + s56_j.x;
-        Cdbopi2 += s56_i.x + s56_j.x;
+    if (cnt > 0) {
+      const double dsx = v.dDeltap_self[3 * i], dsy = v.dDeltap_self[3 * i + 1], dsz = v.dDeltap_self[3 * i + 2];
+      const double cdd_i = v.CdDelta[i];
+      const double2 s56_i = W.sum56[i];  // (sum CEval5, sum CEval6) of the angles centred on i (zero for ghosts)
+      for (int e = sub; e < cnt; e += 8) {
+        const int p = start + e;
+        const int j = v.b_nbr[p];
+        const int sym = v.b_sym[p];
+        if (sym < 0) continue;
+        const double2 s56_j = W.sum56[j];
+        double Cdbo = v.b_Cdbo[p] + v.b_Cdbo[sym];
+        double Cdbopi = v.b_Cdbopi[p] + v.b_Cdbopi[sym];
+        double Cdbopi2 = v.b_Cdbopi2[p] + v.b_Cdbopi2[sym];
+        if (s56_i.x != 0.0 || s56_i.y != 0.0 || s56_j.x != 0.0 || s56_j.y != 0.0) {
+          const double bo_p = v.b_bo[p].x, bo_s = v.b_bo[sym].x;
+          const double p3 = bo_p * bo_p * bo_p, q3 = bo_s * bo_s * bo_s;
+          Cdbo += s56_i.y * (p3 * p3 * bo_p) + s56_j.y * (q3 * q3 * bo_s);
+          Cdbopi += s56_i.x + s56_j.x;
+          Cdbopi2 += s56_i.x + s56_j.x;
+        }
+        const double cdd = cdd_i + v.CdDelta[j];
+        if (Cdbo == 0.0 && Cdbopi == 0.0 && Cdbopi2 == 0.0 && cdd == 0.0) continue;
+        const double4 c1 = v.b_c1[p], c2 = v.b_c2[p], c3 = v.b_c3[p], der = v.b_der[p], geo = v.b_geo[p];
+        const double C1dbo = c1.x * Cdbo, C2dbo = c1.y * Cdbo;
+        const double C1dbopi = c1.w * Cdbopi, C2dbopi = c2.x * Cdbopi, C3dbopi = c2.y * Cdbopi;
+        const double C1dbopi2 = c2.w * Cdbopi2, C2dbopi2 = c3.x * Cdbopi2, C3dbopi2 = c3.y * Cdbopi2;
+        const double C1dDelta = c1.x * cdd, C2dDelta = c1.y * cdd;
+        // temp = sum coef * vector; dBOp = der.x*dvec, dln_BOp_pi = der.y*dvec, dln_BOp_pi2 = der.z*dvec
+        const double a_dbop = C1dbo + C1dDelta + C2dbopi + C2dbopi2;
+        const double a_self = C2dbo + C2dDelta + C3dbopi + C3dbopi2;
+        const double along = a_dbop * der.x + C1dbopi * der.y + C1dbopi2 * der.z;
+        // reference adds temp to fCdDelta (= -force)
+        fx -= along * geo.y + a_self * dsx;
+        fy -= along * geo.z + a_self * dsy;
+        fz -= along * geo.w + a_self * dsz;
+        buf_c += -a_self;
       }
-      const double cdd = cdd_i + v.CdDelta[j];
-      if (Cdbo == 0.0 && Cdbopi == 0.0 && Cdbopi2 == 0.0 && cdd == 0.0) continue;
-      const double4 c1 = v.b_c1[p], c2 = v.b_c2[p], c3 = v.b_c3[p], der = v.b_der[p], geo = v.b_geo[p];
-      const double C1dbo = c1.x * Cdbo, C2dbo = c1.y * Cdbo;
-      const double C1dbopi = c1.w * Cdbopi, C2dbopi = c2.x * Cdbopi, C3dbopi = c2.y * Cdbopi;
-      const double C1dbopi2 = c2.w * Cdbopi2, C2dbopi2 = c3.x * Cdbopi2, C3dbopi2 = c3.y * Cdbopi2;
-      const double C1dDelta = c1.x * cdd, C2dDelta = c1.y * cdd;
-      // temp = sum coef * vector; dBOp = der.x*dvec, dln_BOp_pi = der.y*dvec, dln_BOp_pi2 = der.z*dvec
-      const double a_dbop = C1dbo + C1dDelta + C2dbopi + C2dbopi2;
-      const double a_self = C2dbo + C2dDelta + C3dbopi + C3dbopi2;
-      const double along = a_dbop * der.x + C1dbopi * der.y + C1dbopi2 * der.z;
-      // reference adds temp to fCdDelta (= -force)
-      fx -= along * geo.y + a_self * dsx;
-      fy -= along * geo.z + a_self * dsy;
-      fz -= along * geo.w + a_self * dsz;
-      buf_c += -a_self;
     }
-    buf_c = warp_sum(buf_c);
-    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0 && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
+    // sums over the 8 lanes of the atom (all 32 lanes take part)
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      buf_c += __shfl_xor_sync(0xffffffffu, buf_c, o, 8);
+      fx += __shfl_xor_sync(0xffffffffu, fx, o, 8);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o, 8);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o, 8);
+    }
+    if (sub == 0 && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
       atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
     }
     if (buf_c != 0.0)
-      for (int e = lane; e < cnt; e += 32) {
+      for (int e = sub; e < cnt; e += 8) {
         const int p = start + e;
         const double4 geo = v.b_geo[p];
         const double c = -buf_c * v.b_der[p].x;
