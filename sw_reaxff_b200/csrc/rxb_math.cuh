@@ -8,12 +8,13 @@
 //              t = m rc - 1 is EXACT in one fma) and -log(rc);  log1p(t), |t| < 2^-6, degree 9.   11 DP ops,
 //              absolute error <= 1 ulp of the result + 2e-17 (NOT relative near x = 1: use it only under exp/pow)
 //   The sub-tables are 128 / 256 bytes, so the 32 lookups of a warp hit one or two shared-memory rows whatever the
-//   indices are (ncu on a 64/128-entry version: the L1 data pipe was 61 % busy with the bank conflicts of the lookups).
+//   indices are (a 64/128-entry version with shorter polynomials ran at the same speed; this one cannot bank-conflict).
 //   rcbrt_b(x): fp32 seed + one fourth-order correction step (below).
 // No branches, no special cases: arguments must be finite, exp_b needs |x| <= 700, log_b needs a normal x > 0.
 // The table (640 bytes) is passed in by the caller (shared memory on the device).  The same source compiles for the
 // host (tests/test_fast_math.py builds it with g++ and checks it against libm), and because every operation is an
-// explicit fma/add/mul the host and device results are bit-identical.
+// explicit fma/add/mul the host and device results are bit-identical (the cube root's fp32 seed aside, whose error the
+// correction step removes: the test perturbs the seed).
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -9,8 +9,9 @@
 //   K-nb   : vdW_Coulomb_Energy_Full_C                   /root/reference/reaxc_nonbonded_sw64.c:40-258 (serial twin)
 //            full list, local i only, force on i only (no scatter), 1/2 energy per directed pair,
 //            pair virial + (-x_i (x) f_i) correction as reaxc_nonbonded_cpe.h:531-536 / reaxc_nonbonded_sw64.c:247-252.
-// Roofline: K-farH is HBM-bound (4 B/Verlet entry read, 12 B/far entry written); K-nb is fp64-compute bound
-// (2 pow + 2 exp + 1 cube-root-like pow per pair).
+// Roofline: K-farH streams 4 B/Verlet entry in and 12 B/far entry out (HBM target) but is bound by the L1 data pipe (a 16-byte
+// gather per candidate, a 32-byte gather per survivor: ncu 78 % busy, DRAM 23 %); K-nb is fp64-issue bound (143 DP
+// instructions per pair: 2 log + 3 exp + cube root + rsqrt + 1 division, all from rxb_math.cuh).  Numbers: DESIGN.md 3.
 #include "rxb_math.cuh"
 #include "rxb_system.h"
 
