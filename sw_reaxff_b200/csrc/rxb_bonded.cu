@@ -275,24 +275,28 @@ __device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, 
 //                                     tag_i != tag_k, r0_hb > 0                                    (hydrogen_bonds :313-354)
 // "strong" = BO > thb_cut; every filter of the reference needs it for both bonds of an angle and all three of a torsion.
 // Also stores the per-centre SBO quantities the angle items need (SBO2, CSBO2, dSBO1, dSBO2; :745-787).
+// Eight lanes per centre, four centres per warp: a bond row has ~7.5 entries and a centre 0 - 16 ordered strong pairs, so a
+// warp per centre left most lanes idle (and lane 0 alone did the pow() calls of the SBO block for the whole warp).
 __global__ void __launch_bounds__(kWarps * 32)
 k_enum(DevView v, DevParams P, BondedWork W) {
-  __shared__ int s_strong[kWarps][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  __shared__ int s_strong[kWarps][4][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq;
   const double p_val8 = P.gp[33], p_val9 = P.gp[16];
   const int nt = P.nt;
-  const unsigned lt_mask = (1u << lane) - 1;
-  for (int j = wg; j < v.n; j += nwg) {
-    const int type_j = v.type[j];
-    const int start_j = v.b_start[j], cnt_j = v.b_cnt[j];
-    if (type_j < 0 || cnt_j <= 0) continue;
+  const unsigned lt_mask = (1u << lane) - 1, lt_sub = (1u << sub) - 1;
+  int* strong_list = s_strong[wib][grp];
+  for (int j0 = 4 * wg; j0 < v.n; j0 += 4 * nwg) {   // warp-uniform trip count: the ballots below need all 32 lanes
+    const int j = j0 + grp;
+    const int type_j = j < v.n ? v.type[j] : -1;
+    const int start_j = type_j >= 0 ? v.b_start[j] : 0, cnt_j = type_j >= 0 ? max(v.b_cnt[j], 0) : 0;
     // ---- strong list, SBO sums ----
     double SBOp = 0, prod_SBO = 1;
     int ns = 0;
-    for (int e0 = 0; e0 < cnt_j; e0 += 32) {
-      const int e = e0 + lane;
+    const int max_cnt = __reduce_max_sync(0xffffffffu, cnt_j);
+    for (int e0 = 0; e0 < max_cnt; e0 += 8) {
+      const int e = e0 + sub;
       bool strong = false;
       if (e < cnt_j) {
         const double4 bo = v.b_bo[start_j + e];
@@ -301,16 +305,18 @@ k_enum(DevView v, DevParams P, BondedWork W) {
         prod_SBO *= exp(-t8);
         strong = bo.x > thb_cut;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, strong);
-      if (strong) { const int slot = ns + __popc(m & lt_mask); if (slot < 32) s_strong[wib][slot] = start_j + e; }
+      const unsigned m = (__ballot_sync(0xffffffffu, strong) >> (8 * grp)) & 0xffu;   // this centre's 8 lanes
+      if (strong) { const int slot = ns + __popc(m & lt_sub); if (slot < 32) strong_list[slot] = start_j + e; }
       ns += __popc(m);
     }
     __syncwarp();
-    if (ns > 32) { if (lane == 0) atomicOr(v.overflow, 8); ns = 32; }
-    SBOp = warp_sum(SBOp);
+    if (ns > 32) { if (sub == 0) atomicOr(v.overflow, 8); ns = 32; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) prod_SBO *= __shfl_xor_sync(0xffffffffu, prod_SBO, o);
-    if (lane == 0) {
+    for (int o = 4; o > 0; o >>= 1) {
+      SBOp += __shfl_xor_sync(0xffffffffu, SBOp, o, 8);
+      prod_SBO *= __shfl_xor_sync(0xffffffffu, prod_SBO, o, 8);
+    }
+    if (sub == 0 && cnt_j > 0) {
       const double Delta_boc_j = v.Delta_boc[j];
       double vlpadj, dSBO2;
       if (v.vlpex[j] >= 0) { vlpadj = 0; dSBO2 = prod_SBO - 1; }
@@ -326,79 +332,78 @@ k_enum(DevView v, DevParams P, BondedWork W) {
     }
 
     // ---- angles and torsions from ordered strong pairs (a, b), a != b ----
-    if (ns >= 2) {
-      const double4 xj = v.xq[j];
-      const int tag_j = v.tag[j];
-      const int npair = ns * ns;
-      for (int q0 = 0; q0 < npair; q0 += 32) {
-        const int q = q0 + lane;
-        bool ang = false;
-        unsigned long long tmask = 0ull;  // matching pw offsets in k's row
-        int pk = -1, ph = -1, start_k = 0;
-        if (q < npair) {
-          const int a = q / ns, b = q - a * ns;
-          if (a != b) {
-            pk = s_strong[wib][a]; ph = s_strong[wib][b];
-            const int k = v.b_nbr[pk], h = v.b_nbr[ph];
-            const int type_k = v.type[k], type_h = v.type[h];
-            const int cnt_k = v.b_cnt[k];
-            start_k = v.b_start[k];
-            if (type_k >= 0 && type_h >= 0 && cnt_k > 0) {
-              const double bo_jk = v.b_bo[pk].x, bo_hj = v.b_bo[ph].x;
-              ang = (ph > pk) && (bo_jk * bo_hj > thb_cutsq);
-              const int pj = v.b_sym[pk];
-              if (pj >= 0 && half_select(tag_j, v.tag[k], xj, v.xq[k])) {
-                const int ne = min(cnt_k, 64);
-                if (cnt_k > 64 && lane == 0) atomicOr(v.overflow, 8);
-                for (int e = 0; e < ne; e++) {
-                  const int pw = start_k + e;
-                  if (pw == pj) continue;
-                  const double bo_kl = v.b_bo[pw].x;
-                  if (!(bo_kl > thb_cut)) continue;
-                  const int l = v.b_nbr[pw];
-                  if (l == h) continue;
-                  const int type_l = v.type[l];
-                  if (type_l < 0) continue;
-                  if (!P.tors[((type_h * nt + type_j) * nt + type_k) * nt + type_l].cnt) continue;
-                  if (!(bo_hj * bo_jk * bo_kl > thb_cut)) continue;
-                  tmask |= 1ull << e;
-                }
+    const int npair = ns >= 2 ? ns * ns : 0;
+    const int max_np = __reduce_max_sync(0xffffffffu, npair);
+    double4 xj = make_double4(0, 0, 0, 0);
+    int tag_j = 0;
+    if (npair > 0) { xj = v.xq[j]; tag_j = v.tag[j]; }
+    for (int q0 = 0; q0 < max_np; q0 += 8) {
+      const int q = q0 + sub;
+      bool ang = false;
+      unsigned long long tmask = 0ull;  // matching pw offsets in k's row
+      int pk = -1, ph = -1, start_k = 0;
+      if (q < npair) {
+        const int a = q / ns, b = q - a * ns;
+        if (a != b) {
+          pk = strong_list[a]; ph = strong_list[b];
+          const int k = v.b_nbr[pk], h = v.b_nbr[ph];
+          const int type_k = v.type[k], type_h = v.type[h];
+          const int cnt_k = v.b_cnt[k];
+          start_k = v.b_start[k];
+          if (type_k >= 0 && type_h >= 0 && cnt_k > 0) {
+            const double bo_jk = v.b_bo[pk].x, bo_hj = v.b_bo[ph].x;
+            ang = (ph > pk) && (bo_jk * bo_hj > thb_cutsq);
+            const int pj = v.b_sym[pk];
+            if (pj >= 0 && half_select(tag_j, v.tag[k], xj, v.xq[k])) {
+              const int ne = min(cnt_k, 64);
+              if (cnt_k > 64) atomicOr(v.overflow, 8);
+              for (int e = 0; e < ne; e++) {
+                const int pw = start_k + e;
+                if (pw == pj) continue;
+                const double bo_kl = v.b_bo[pw].x;
+                if (!(bo_kl > thb_cut)) continue;
+                const int l = v.b_nbr[pw];
+                if (l == h) continue;
+                const int type_l = v.type[l];
+                if (type_l < 0) continue;
+                if (!P.tors[((type_h * nt + type_j) * nt + type_k) * nt + type_l].cnt) continue;
+                if (!(bo_hj * bo_jk * bo_kl > thb_cut)) continue;
+                tmask |= 1ull << e;
               }
             }
           }
         }
-        // angles
-        unsigned m = __ballot_sync(0xffffffffu, ang);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(W.n_ang, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (ang) {
-            const int o = base + __popc(m & lt_mask);
-            if (o < W.cap_ang) W.ang[o] = make_int4(j, pk, ph, 0);
-          }
+      }
+      // angles: one atomic for the four centres of the warp
+      const unsigned m = __ballot_sync(0xffffffffu, ang);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(W.n_ang, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ang) {
+          const int o = base + __popc(m & lt_mask);
+          if (o < W.cap_ang) W.ang[o] = make_int4(j, pk, ph, 0);
         }
-        // torsions: warp exclusive scan of per-lane counts
-        const int mine = __popcll(tmask);
-        int incl = mine;
+      }
+      // torsions: warp exclusive scan of per-lane counts
+      const int mine = __popcll(tmask);
+      int incl = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(W.n_tor, total);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          int o = base + incl - mine;
-          while (tmask) {
-            const int e = __ffsll((long long)tmask) - 1;
-            tmask &= tmask - 1;
-            if (o < W.cap_tor) W.tor[o] = make_int4(j, pk, ph, start_k + e);
-            o++;
-          }
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(W.n_tor, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int o = base + incl - mine;
+        while (tmask) {
+          const int e = __ffsll((long long)tmask) - 1;
+          tmask &= tmask - 1;
+          if (o < W.cap_tor) W.tor[o] = make_int4(j, pk, ph, start_k + e);
+          o++;
         }
       }
     }
-
     __syncwarp();
   }
 }
