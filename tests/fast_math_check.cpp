@@ -35,6 +35,31 @@ int main() {
   }
   printf("exp_rel %.3e\nlog_abs_over_max1 %.3e\nlog_abs_near_1 %.3e\npow_rel %.3e\nrcbrt_rel %.3e\nrcbrt_seed1e-5_rel %.3e\n", e_exp, e_log,
          e_log1, e_pow, e_cbrt, e_cbrt_seed);
+  // edges: exponent boundaries of log (2^k and its neighbours), the clamp ends of exp, table-interval boundaries
+  double e_edge_log = 0, e_edge_exp = 0;
+  for (int k = -1000; k <= 1000; k += 7) {
+    const double base = ldexp(1.0, k);
+    const double xs[5] = {base, nextafter(base, 0.0), nextafter(base, INFINITY), base * (1.0 + 1.0 / 32.0), nextafter(base * (1.0 + 1.0 / 32.0), 0.0)};
+    for (double x : xs) {
+      const long double ll = logl((long double)x);
+      e_edge_log = fmax(e_edge_log, fabs((double)(log_b(x, tab) - ll)) / fmax(1.0, fabs((double)ll)));
+    }
+  }
+  const double ends[8] = {-700.0, 700.0, -699.999999, 699.999999, -0.0, 5e-324, 0.021660849392498291, -0.021660849392498291};
+  for (double x : ends) {
+    const long double ex = expl((long double)x);
+    e_edge_exp = fmax(e_edge_exp, fabs((double)((exp_b(x, tab) - ex) / ex)));
+  }
+  // monotonic where the kernels rely on it (a larger distance never gives a larger r^p)
+  int mono_bad = 0;
+  double prev = 0.0;
+  for (int i = 0; i < 200000; i++) {
+    const double r = 0.5 + 12.0 * i / 200000.0;
+    const double y = exp_b(1.5591 * log_b(r, tab), tab);
+    if (y < prev * (1.0 - 4e-16)) mono_bad++;
+    prev = y;
+  }
+  printf("edge_log %.3e\nedge_exp %.3e\nmono_bad %d\n", e_edge_log, e_edge_exp, mono_bad);
   printf("exp0 %.17g\nlog1 %.17g\n", exp_b(0.0, tab), log_b(1.0, tab));
   return 0;
 }

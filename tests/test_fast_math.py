@@ -24,6 +24,8 @@ def test_fast_math_accuracy(tmp_path):
     assert r["pow_rel"] < 2e-15            # exp(p log r): what the vdW kernel evaluates
     assert r["rcbrt_rel"] < 3e-16
     assert r["rcbrt_seed1e-5_rel"] < 3e-16
+    assert r["edge_log"] < 4e-16 and r["edge_exp"] < 3e-16   # powers of two, interval boundaries, the clamp ends
+    assert r["mono_bad"] == 0                                # r -> r^p never decreases beyond rounding
     assert r["exp0"] == 1.0 and r["log1"] == 0.0
 
 
