@@ -46,6 +46,10 @@ struct DevView {
   double* CdDelta;     // N
   // Verlet list r <= cutneigh, local rows          (a1)
   const long long* vl_off; const int* vl_idx; const int* vl_cnt;   // row i: vl_idx[vl_off[i] .. + vl_cnt[i])
+  // inner partition of the Verlet rows: the first vl_cnt_in[i] entries were within vl_cut_in (> the far cut-off) when the
+  // list was built; *disp2 = max |x - x_build|^2 over all atoms this step.  A pair inside the far cut-off now was within
+  // far + 2 sqrt(*disp2) at the build, so while that is <= vl_cut_in the far-list sweep reads only the inner block.
+  const int* vl_cnt_in; const double* disp2; double vl_cut_in;
   // bond candidates r <= bond_cut + skin, all rows (a1, ghost rows included)
   const long long* bc_off; const int* bc_idx; const int* bc_cnt;
   // hbond candidates r <= hbond_cut + skin, local H rows only

@@ -88,8 +88,8 @@ __global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __res
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const float4* __restrict__ sposf,
-        const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band, int reach, int* __restrict__ cnt,
-        long long* __restrict__ off, int* __restrict__ idx, int stride) {
+        const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band, float in2hi, int reach,
+        int* __restrict__ cnt, int* __restrict__ cnt_in, long long* __restrict__ off, int* __restrict__ idx, int stride) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nrows) return;
@@ -101,7 +101,10 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
   const int by = bin_coord(pi.y, g.lo[1], g.inv[1], g.nb[1]);
   const int bz = bin_coord(pi.z, g.lo[2], g.inv[2], g.nb[2]);
   const long long base_off = (long long)i * stride;
-  int total = 0;
+  // inner entries (fp32 r^2 <= in2hi, a superset of r <= cut_in) fill the row from the front, the others from the back;
+  // the back block is moved down behind the inner one at the end, so the row stays contiguous
+  int n_in = 0, n_out = 0;
+  const unsigned lt = (1u << lane) - 1;
   // The (2 reach + 1)^2 bin rows (cz, cy) of the stencil: lane t works out the x run [kbeg, kend) of row t in the sorted
   // order once (fp64 chord, two floors, two bin_start loads), then the warp walks the runs in (cz, cy) order.  Doing this
   // per row inside the loops cost as many instructions as the candidate tests themselves (ncu: issue slots 78 % busy).
@@ -142,13 +145,14 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
       const int kbeg = __shfl_sync(0xffffffffu, kbeg_l, t), kend = __shfl_sync(0xffffffffu, kend_l, t);
       for (int k0 = kbeg; k0 < kend; k0 += 32) {
         const int k = k0 + lane;
-        bool hit = false;
+        bool hit = false, inner = false;
         int j = -1;
         if (k < kend) {
           const float4 qj = sposf[k];
           j = __float_as_int(qj.w);
           const float ex = qj.x - fx, ey = qj.y - fy, ez = qj.z - fz;
           const float r2f = ex * ex + ey * ey + ez * ez;
+          inner = r2f <= in2hi;
           if (r2f < c2lo) hit = (j != i);
           else if (r2f <= c2hi) {
             // inside the fp32 rounding band: decide with the exact record.  Explicit rn ops: no FMA contraction, so the
@@ -159,17 +163,40 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
             hit = (j != i) && (r2 <= c2);
           }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const unsigned m_in = __ballot_sync(0xffffffffu, hit && inner), m_out = __ballot_sync(0xffffffffu, hit && !inner);
         if (FILL && hit) {
-          const int pos = total + __popc(m & ((1u << lane) - 1));
-          if (pos < stride) idx[base_off + pos] = j;
+          if (inner) {
+            const int pos = n_in + __popc(m_in & lt);
+            if (pos < stride) idx[base_off + pos] = j;
+          } else {
+            const int pos = n_out + __popc(m_out & lt);
+            if (pos < stride) idx[base_off + (stride - 1 - pos)] = j;
+          }
         }
-        total += __popc(m);
+        n_in += __popc(m_in); n_out += __popc(m_out);
+      }
+    }
+  }
+  const int total = n_in + n_out;
+  if (FILL && total <= stride && n_out > 0) {
+    // move the back block [stride - n_out, stride) down to [n_in, n_in + n_out): ascending chunks, destination never ahead of
+    // the unread source (n_in <= stride - n_out), loads of a chunk complete before its stores
+    const int src0 = stride - n_out;
+    if (src0 > n_in) {
+      __syncwarp();
+      for (int t0 = 0; t0 < n_out; t0 += 32) {
+        const int t = t0 + lane;
+        int val = 0;
+        if (t < n_out) val = idx[base_off + src0 + t];
+        __syncwarp();
+        if (t < n_out) idx[base_off + n_in + t] = val;
+        __syncwarp();
       }
     }
   }
   if (lane == 0) {
     cnt[i] = total;
+    if (cnt_in) cnt_in[i] = n_in;
     if (FILL) off[i] = base_off;
     if (FILL && i == nrows - 1) off[nrows] = base_off + stride;
   }
@@ -250,10 +277,15 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   RXB_CUDA(cudaGetLastError());
 }
 
-void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st) {
+void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st) {
   Grid g;
   memcpy(&g, grid_blob, sizeof(g));
   const float band = fp32_band(cut);
+  // inner class: fp32 r^2 <= cut_in^2 + band is a superset of r <= cut_in (the band bounds the fp32 error of r^2)
+  const bool part = cut_in > 0.0 && cut_in < cut;
+  const float in2hi = part ? __builtin_nextafterf((float)(cut_in * cut_in), INFINITY) + band : 3.0e38f;
+  out.cut_in = part ? cut_in : 0.0;
+  out.cnt_in.resize(nrows + 1);
   const int warps_per_block = 8;
   const int blocks = (nrows + warps_per_block - 1) / warps_per_block;
   out.cnt.resize(nrows + 1);
@@ -269,7 +301,8 @@ void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStr
   auto stride_for = [](long long longest) { return (int)(((longest + longest / 16 + 32) + 31) / 32 * 32); };
   long long got[2] = {0, 0};
   if (out.stride == 0 && nrows > 0) {   // first build: one counting pass sizes the stride
-    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, out.cnt.p, nullptr, nullptr, 0);
+    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach, out.cnt.p, nullptr,
+                                           nullptr, nullptr, 0);
     stats(got);
     out.stride = stride_for(got[0]);
   }
@@ -278,8 +311,8 @@ void CellList::build(const double4* xq, int nrows, double cut, Csr& out, cudaStr
     out.slots = (long long)nrows * out.stride;
     out.idx.resize((size_t)std::max<long long>(out.slots, 1));
     if (nrows > 0)
-      k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, reach, out.cnt.p, out.off.p,
-                                            out.idx.p, out.stride);
+      k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach, out.cnt.p,
+                                            out.cnt_in.p, out.off.p, out.idx.p, out.stride);
     stats(got);
     if (got[0] <= out.stride) break;
     out.stride = stride_for(got[0]);     // a row outgrew the stride of the previous build: run the pass again

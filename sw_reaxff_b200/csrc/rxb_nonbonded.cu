@@ -27,13 +27,14 @@ __device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-struct QeqConst { double Tap[8]; double swb2; double far2; };
+struct QeqConst { double Tap[8]; double swb2; double far2; double inner_lim2; };
 
 __global__ void __launch_bounds__(kWarps * 32)
 k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const AtomPar* __restrict__ atom, double hbond_cut,
         double hbond_r2max, BondedWork W) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const bool inner_ok = *v.disp2 <= qc.inner_lim2;
   for (int i = wg; i < v.n; i += nwg) {
     const double4 pi = v.xq[i];
     const int ti = v.type[i];
@@ -43,7 +44,9 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
     // all index loads are issued first, then all gathers, then the tests.  Row-relative 32-bit offsets throughout.
     const int* __restrict__ vl = v.vl_idx + beg;
     int* __restrict__ far = v.far_idx + beg;
-    const int cnt_i = v.vl_cnt[i];
+    // adaptive inner skin: while no atom has moved more than half the margin since the build, every pair inside the far
+    // cut-off is in the inner block of its row
+    const int cnt_i = inner_ok ? v.vl_cnt_in[i] : v.vl_cnt[i];
     int w = 0;
     const float4 fi = v.xf[i];
     const float lo2 = (float)qc.far2 - v.far_band, hi2 = (float)qc.far2 + v.far_band;
@@ -397,6 +400,10 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   qc.swb2 = swb * swb;
   const double far = swb > P.ctl.nonb_cut ? swb : P.ctl.nonb_cut;
   qc.far2 = far * far;
+  // the inner block holds every pair that was within vl_cut_in at the build; a pair inside `far` now was within
+  // far + 2 max|dx| then: usable while max|dx| <= (vl_cut_in - far) / 2 (0.1 % slack for the roundings)
+  const double margin = v.vl_cut_in - far;
+  qc.inner_lim2 = (v.vl_cut_in > 0.0 && margin > 0.0) ? 0.25 * 0.998 * margin * margin : -1.0;
   BondedWork W = s.bonded_work();
   RXB_CUDA(cudaMemsetAsync(W.n_hb, 0, sizeof(int), st));
   // largest r^2 with sqrt(r^2) <= hbond_cut in round-to-nearest

@@ -51,12 +51,28 @@ __global__ void k_get_xyz(int N, const double4* __restrict__ xq, double* __restr
   x[3 * i] = p.x; x[3 * i + 1] = p.y; x[3 * i + 2] = p.z;
 }
 
+// fp32 shadow of the positions + (xb != null) the largest squared displacement since the neighbour build.  Squared
+// distances are non-negative doubles, whose bit patterns order like unsigned integers: one atomicMax per warp.
 __global__ void k_shadow(int N, const double4* __restrict__ xq, const int* __restrict__ type, double ox, double oy, double oz,
-                         float4* __restrict__ xf) {
+                         float4* __restrict__ xf, const double4* __restrict__ xb, double* __restrict__ disp2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const double4 p = xq[i];
-  xf[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(type[i]));
+  double d2 = 0.0;
+  if (i < N) {
+    const double4 p = xq[i];
+    xf[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(type[i]));
+    if (xb) {
+      const double4 b = xb[i];
+      const double dx = p.x - b.x, dy = p.y - b.y, dz = p.z - b.z;
+      d2 = dx * dx + dy * dy + dz * dz;
+      if (!(d2 >= 0.0)) d2 = 1e300;   // NaN positions: never trust the inner block
+    }
+  }
+  if (xb) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if ((threadIdx.x & 31) == 0 && d2 > 0.0)
+      atomicMax(reinterpret_cast<unsigned long long*>(disp2), (unsigned long long)__double_as_longlong(d2));
+  }
 }
 
 // virial_fdotr over all atoms, pair_reaxc_sunway.cpp:674-702
@@ -468,7 +484,13 @@ BondedWork System::bonded_work() {
 void System::update_shadow(cudaStream_t st) {
   if (N == 0) return;
   xf.resize((size_t)N);
-  k_shadow<<<nblk(N), 256, 0, st>>>(N, xq.p, type.p, cells_a_.origin[0], cells_a_.origin[1], cells_a_.origin[2], xf.p);
+  disp2_d.resize(1);
+  // displacement since the build is only meaningful for the atom set the lists were built for
+  const bool track = x_build.n == (size_t)N && vl.cut_in > 0.0;
+  if (track) RXB_CUDA(cudaMemsetAsync(disp2_d.p, 0, sizeof(double), st));
+  else { static const double huge = 1e300; RXB_CUDA(cudaMemcpyAsync(disp2_d.p, &huge, sizeof(double), cudaMemcpyHostToDevice, st)); }
+  k_shadow<<<nblk(N), 256, 0, st>>>(N, xq.p, type.p, cells_a_.origin[0], cells_a_.origin[1], cells_a_.origin[2], xf.p,
+                                    track ? x_build.p : nullptr, disp2_d.p);
   kernel_launches++;
 }
 
@@ -484,6 +506,8 @@ DevView System::view() {
   }
   v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
   v.vl_off = vl.off.p; v.vl_idx = vl.idx.p; v.vl_cnt = vl.cnt.p;
+  disp2_d.resize(1);
+  v.vl_cnt_in = vl.cnt_in.p; v.disp2 = disp2_d.p; v.vl_cut_in = vl.cut_in;
   v.bc_off = bc.off.p; v.bc_idx = bc.idx.p; v.bc_cnt = bc.cnt.p;
   v.hc_off = nullptr; v.hc_idx = nullptr;
   v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
@@ -504,11 +528,17 @@ void System::build_neighbors() {
   const double cn = cutneigh();
   // Verlet list for local rows: bins of cn/2, +-2 cells
   cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
-  cells_a_.build(xq.p, n, cn, vl, st_);
+  // rows partitioned at far cut-off + kInnerSkin: between rebuilds the per-step far-list sweep reads only that block while
+  // no atom has moved more than kInnerSkin / 2 (checked on the device every step)
+  const double far = std::max(ff.ctl.nonb_cut, qeq_swb);
+  cells_a_.build(xq.p, n, cn, far + kInnerSkin, vl, st_);
+  x_build.resize((size_t)std::max(N, 1));
+  RXB_CUDA(cudaMemcpyAsync(x_build.p, xq.p, (size_t)N * sizeof(double4), cudaMemcpyDeviceToDevice, st_));
+  x_build.n = (size_t)N;
   // bond candidates for all rows (ghosts too): (reach of the longest possible bond <= bond_cut) + skin
   const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
-  cells_b_.build(xq.p, N, cb, bc, st_);
+  cells_b_.build(xq.p, N, cb, 0.0, bc, st_);
   far_idx.resize((size_t)std::max<long long>(vl.slots, 1));
   H_val.resize((size_t)std::max<long long>(vl.slots, 1));
   kernel_launches += 12;

@@ -58,9 +58,13 @@ struct DBuf {  // grow-only device buffer (contents are NOT preserved across gro
 // Neighbour rows at a fixed stride: row i occupies idx[off[i] .. off[i] + cnt[i]) with off[i] = i * stride.  The stride
 // (max row length of the previous build + slack, a multiple of 32 ints so rows start on 128-byte lines) lets a rebuild run
 // ONE pass — no count pass, no scan; a row that outgrows it triggers a re-run with a larger stride.
+constexpr double kInnerSkin = 0.5;   // Angstrom: inner block of a Verlet row = far cut-off + this (adaptive skin, rxb_dev.cuh)
+
 struct Csr {
   DBuf<long long> off;
   DBuf<int> idx, cnt;
+  DBuf<int> cnt_in;        // rows are partitioned: the first cnt_in[i] entries were within cut_in at the build
+  double cut_in = 0.0;     // 0: not partitioned
   DBuf<long long> stats;   // device: [0] max row length, [1] sum of row lengths
   long long nnz = 0;       // sum of cnt
   long long slots = 0;     // nrows * stride
@@ -80,7 +84,8 @@ struct CellList {
   double origin[3] = {0, 0, 0}, extent = 0.0;   // bounding box of the last bin() (origin of the fp32 shadows)
   float fp32_band(double cut) const;
   void bin(const double4* xq, int N, double bin_size, int reach, cudaStream_t st);
-  void build(const double4* xq, int nrows, double cut, Csr& out, cudaStream_t st);
+  // cut_in < cut: every row is partitioned, entries within cut_in (at the build) first; cut_in >= cut: no partition
+  void build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st);
 };
 
 struct Box {  // LAMMPS triclinic box, lo = 0
@@ -215,6 +220,8 @@ class System {
   // raw buffers (public: the C ABI copies them out for tests / fix reax/c/bonds)
   DBuf<double4> xq;
   DBuf<float4> xf;
+  DBuf<double4> x_build;     // positions at the last neighbour build (adaptive inner skin, rxb_dev.cuh)
+  DBuf<double> disp2_d;      // [1]: max squared displacement from x_build, refreshed with the shadow positions
   void update_shadow(cudaStream_t st);   // xq -> xf
   DBuf<int> type, tag, ltype_d, ghost_owner;
   DBuf<double> f, CdDelta;
