@@ -59,7 +59,9 @@ long rxb_lookup_dump(const char* control_file, const char* ffield_file, int ntyp
  *      tags (atom->map); -1 = owned by another rank (the caller's comm layer must then refresh ghost values). */
 int rxb_set_atoms(rxb_handle* h, int nlocal, int nghost, const double* x, const int* type, const int* tag,
                   const double* q, const int* ghost_owner);
-int rxb_set_positions(rxb_handle* h, const double* x);  /* every step, after forward_comm */
+/* every step, after forward_comm.  nall must be the nlocal + nghost of the last rxb_set_atoms (the index space the device
+ * holds); a mismatch is an error, not a silent overrun. */
+int rxb_set_positions(rxb_handle* h, int nall, const double* x);
 int rxb_set_charges(rxb_handle* h, const double* q);
 
 /* ---- neighbour build (every reneighbouring step)
@@ -79,7 +81,8 @@ int rxb_get_charges(rxb_handle* h, double* q); /* nall */
  *      f_out   : [nall][3] forces to ADD INTO atom->f by the caller (ghost rows included: caller reverse_comm's), or NULL
  *      pvector : 14 per-term energies in the reference's order (pair_reaxc_sunway.cpp:657-670), or NULL
  *      eng2    : eng_vdwl, eng_coul, or NULL ; virial6 : xx,yy,zz,xy,xz,yz, or NULL */
-int rxb_pair_compute(rxb_handle* h, int eflag, int vflag, double* f_out, double* pvector, double* eng2, double* virial6);
+int rxb_pair_compute(rxb_handle* h, int nall, int eflag, int vflag, double* f_out, double* pvector, double* eng2,
+                     double* virial6); /* nall: rows of f_out, checked against the device's atom count */
 
 /* ---- device-resident run: fix nve (fix_nve_sw64.c:25-170) + periodic ghosts + the calls above, nothing leaves HBM.
  *      box6 = xprd,yprd,zprd,xy,xz,yz ; mass[0..ntypes] indexed by LAMMPS type */
@@ -154,6 +157,11 @@ int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* compo
  * neigh, qeq far+H, qeq CG (whole solve), bond list, BO, bonded (all), nonbonded, dBond, SpMV (per launch), hbond items,
  * angle+torsion items, multi-body, enumeration.  enable: 1 reset+start, 0 stop, -1 read only. */
 int rxb_profile(rxb_handle* h, int enable, double* out26);
+/* Storage format of one off-diagonal H entry (what the SpMV streams per non-zero): bytes per entry and a short name. */
+int rxb_get_h_format(rxb_handle* h, int* bytes_per_entry, char* name, int cap);
+/* Measured fp64 FMA throughput of the device in TFLOP/s (a pure DFMA kernel, best of 5): the roofline denominator of the
+ * fp64-issue-bound kernels (bond orders, angles, torsions, nonbonded).  < 0 on error. */
+double rxb_measure_fp64_tflops(int cuda_device);
 /* cudaProfilerStart/Stop, so that `ncu --profile-from-start off` captures only the steady-state steps */
 int rxb_profiler_range(int start);
 

@@ -1,5 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under sw_reaxff_b200/ may include, link or call this.
 // Plain C entry points for ctypes (tests/, __graft_entry__.smoke(), bench.py cpu_baseline only).
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -308,6 +311,24 @@ long orc_md_species_text(void* hh, long ntimestep, char* out, long cap) {
   OrcHandle* h = (OrcHandle*)hh;
   h->text = h->species.formulas_text(ntimestep);
   return copy_text(h->text, out, cap);
+}
+
+// OpenMP threads of this library: set > 0 sets the count (independent of OMP_NUM_THREADS, which launchers such as torchrun
+// force to 1); returns the number of threads a parallel region actually gets (1 for the serial build).
+int orc_omp_threads(int set) {
+#ifdef _OPENMP
+  if (set > 0) omp_set_num_threads(set);
+  int got = 1;
+#pragma omp parallel
+  {
+#pragma omp master
+    got = omp_get_num_threads();
+  }
+  return got;
+#else
+  (void)set;
+  return 1;
+#endif
 }
 
 int orc_md_matvecs(void* hh, int which) { QEq& q = ((OrcHandle*)hh)->md.qeq; return which ? q.matvecs_t : q.matvecs_s; }

@@ -16,7 +16,7 @@ SYMBOLS = [
     "rxb_get_neighbors", "rxb_get_bonds", "rxb_get_workspace", "rxb_get_far", "rxb_profile", "rxb_profiler_range", "rxb_md_last_run_ms", "rxb_parse_dump",
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
-    "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs",
+    "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -42,6 +42,7 @@ def load_library(path=LIB_PATH):
     lib.rxb_md_last_run_ms.restype = C.c_double
     lib.rxb_parse_dump.restype = C.c_long
     lib.rxb_lookup_dump.restype = C.c_long
+    lib.rxb_measure_fp64_tflops.restype = C.c_double
     _lib = lib
     return lib
 
@@ -121,7 +122,7 @@ class Rxb:
 
     def set_positions(self, x):
         x = _f(x)
-        self._chk(self.lib.rxb_set_positions(self.h, _p(x)))
+        self._chk(self.lib.rxb_set_positions(self.h, int(x.size // 3), _p(x)))
 
     def set_charges(self, q):
         q = _f(q)
@@ -154,7 +155,7 @@ class Rxb:
     def pair_compute(self, eflag=True, vflag=True, want_forces=True, f_out=None):
         f = f_out if f_out is not None else (np.zeros((self.nall, 3)) if want_forces else None)
         pv = np.zeros(14); eng = np.zeros(2); vir = np.zeros(6)
-        self._chk(self.lib.rxb_pair_compute(self.h, int(eflag), int(vflag), _p(f), _p(pv), _p(eng), _p(vir)))
+        self._chk(self.lib.rxb_pair_compute(self.h, int(self.nall if f is None else f.size // 3), int(eflag), int(vflag), _p(f), _p(pv), _p(eng), _p(vir)))
         return dict(f=f, pvector=pv, eng=eng, virial=vir)
 
     # ---- resident MD ----
@@ -304,6 +305,15 @@ class Rxb:
         out = np.zeros(26)
         self._chk(self.lib.rxb_profile(self.h, -1 if enable is None else int(enable), _p(out)))
         return {nm: (out[k], int(out[13 + k])) for k, nm in enumerate(self.PHASES)}
+
+    def h_format(self):
+        b = C.c_int(); nm = C.create_string_buffer(128)
+        self._chk(self.lib.rxb_get_h_format(self.h, C.byref(b), nm, 128))
+        return {"bytes_per_entry": b.value, "name": nm.value.decode()}
+
+    @staticmethod
+    def measure_fp64_tflops(device=0):
+        return float(load_library().rxb_measure_fp64_tflops(int(device)))
 
     def md_last_run_ms(self):
         return float(self.lib.rxb_md_last_run_ms(self.h))

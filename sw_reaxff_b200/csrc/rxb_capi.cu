@@ -38,9 +38,49 @@ void d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
   RXB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
   RXB_CUDA(cudaStreamSynchronize(st));
 }
+
+// fp64 FMA throughput of this GPU, measured: 8 independent dependent-FMA chains per thread (enough ILP to cover the DFMA
+// latency at full occupancy), nothing but DFMA in the loop.  The roofline denominator of the fp64-issue-bound kernels.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double a, double b, double* __restrict__ out) {
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) r[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = fma(r[k], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += r[k];
+  if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
 }  // namespace
 
 extern "C" {
+
+double rxb_measure_fp64_tflops(int cuda_device) {
+  double best = -1.0;
+  guard([&] {
+    RXB_CUDA(cudaSetDevice(cuda_device));
+    double* out = nullptr;
+    RXB_CUDA(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1;
+    RXB_CUDA(cudaEventCreate(&e0)); RXB_CUDA(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    for (int rep = 0; rep < 6; rep++) {
+      RXB_CUDA(cudaEventRecord(e0));
+      k_dfma_peak<<<blocks, threads>>>(iters, 0.999999, 1e-7, out);
+      RXB_CUDA(cudaEventRecord(e1));
+      RXB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      RXB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  });
+  return best;
+}
 
 const char* rxb_last_error(void) { return g_err.c_str(); }
 
@@ -117,7 +157,14 @@ int rxb_set_atoms(rxb_handle* h, int nlocal, int nghost, const double* x, const 
                   const int* ghost_owner) {
   return guard([&] { h->sys->set_atoms(nlocal, nghost, x, type, tag, q, ghost_owner); });
 }
-int rxb_set_positions(rxb_handle* h, const double* x) { return guard([&] { h->sys->set_positions(x); }); }
+static void check_nall(const System& s, int nall, const char* who) {
+  if (nall != s.N)
+    throw std::runtime_error(std::string(who) + ": caller passes nall = " + std::to_string(nall) + " but the device holds " +
+                             std::to_string(s.N) + " atoms (rxb_set_atoms + rxb_neigh_build must follow every borders/exchange)");
+}
+int rxb_set_positions(rxb_handle* h, int nall, const double* x) {
+  return guard([&] { check_nall(*h->sys, nall, "rxb_set_positions"); h->sys->set_positions(x); });
+}
 int rxb_set_charges(rxb_handle* h, const double* q) { return guard([&] { h->sys->set_charges(q); }); }
 int rxb_neigh_build(rxb_handle* h) { return guard([&] { h->sys->build_neighbors(); }); }
 
@@ -149,9 +196,11 @@ static void fill_pvector(const double* e, double* pvector, double* eng2) {
   }
 }
 
-int rxb_pair_compute(rxb_handle* h, int eflag, int vflag, double* f_out, double* pvector, double* eng2, double* virial6) {
+int rxb_pair_compute(rxb_handle* h, int nall, int eflag, int vflag, double* f_out, double* pvector, double* eng2,
+                     double* virial6) {
   return guard([&] {
     System& s = *h->sys;
+    check_nall(s, nall, "rxb_pair_compute");
     s.plugin_compute(eflag != 0, vflag != 0);
     if (f_out) s.get_forces(f_out);
     fill_pvector(s.energies, pvector, eng2);
@@ -400,6 +449,14 @@ int rxb_host_register(void* p, size_t bytes) {
   return guard([&] { RXB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
 }
 int rxb_host_unregister(void* p) { return guard([&] { RXB_CUDA(cudaHostUnregister(p)); }); }
+
+int rxb_get_h_format(rxb_handle* h, int* bytes_per_entry, char* name, int cap) {
+  return guard([&] {
+    const char* nm = h->sys->h_format_name();
+    if (bytes_per_entry) *bytes_per_entry = h->sys->h_bytes_per_entry();
+    if (name && cap > 0) { strncpy(name, nm, cap - 1); name[cap - 1] = 0; }
+  });
+}
 
 int rxb_profiler_range(int start) {
   return guard([&] { if (start) RXB_CUDA(cudaProfilerStart()); else RXB_CUDA(cudaProfilerStop()); });

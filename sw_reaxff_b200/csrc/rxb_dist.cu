@@ -266,6 +266,10 @@ void System::dist_allreduce_int(int* dev_ptr, size_t count) {
   if (!dist_) return;
   RXB_NCCL(ncclAllReduce(dev_ptr, dev_ptr, count, ncclInt, ncclSum, dist_->comm, st_));
 }
+void System::dist_allreduce_max_int(int* dev_ptr, size_t count) {
+  if (!dist_) return;
+  RXB_NCCL(ncclAllReduce(dev_ptr, dev_ptr, count, ncclInt, ncclMax, dist_->comm, st_));
+}
 void System::dist_allgather_int(const int* send, int* recv, size_t count_per_rank) {
   if (!dist_) {
     if (send != recv) RXB_CUDA(cudaMemcpyAsync(recv, send, count_per_rank * sizeof(int), cudaMemcpyDeviceToDevice, st_));
@@ -292,8 +296,8 @@ void System::dist_exchange() {
   // slots per rank: generous, so that the post-migration local counts fit as well (growth triggers a re-gather next time)
   int want = std::max(mx, (int)((total / D.world) + (total / D.world) / 4 + 64));
   if (want > D.chunk) D.chunk = want + want / 8;
-  const int chunk = D.chunk;
-  const int nslots = chunk * D.world;
+  int chunk = D.chunk;
+  int nslots = chunk * D.world;
   // 2. migration records of the wrapped local atoms
   D.rec_send.resize((size_t)chunk * kRec);
   D.rec_all.resize((size_t)nslots * kRec);
@@ -316,7 +320,8 @@ void System::dist_exchange() {
   long long newn = 0;
   RXB_CUDA(cudaMemcpyAsync(&newn, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
-  if (newn > chunk) throw std::runtime_error("rxb dist: local atom count exceeds the slab capacity (load imbalance > 25 %)");
+  // (a brick may end up with more atoms than a slab slot holds: the slab is re-sized below, identically on every rank,
+  // from the all-gathered post-migration counts - no rank-local abort that would leave the others in a collective)
   n = (int)newn;
   N = n;
   ensure_atom_capacity();
@@ -338,6 +343,23 @@ void System::dist_exchange() {
   my = n;
   RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
   RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
+  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  {
+    int mx2 = 0;
+    for (int c : D.counts) mx2 = std::max(mx2, c);
+    if (mx2 > D.chunk) {           // same numbers on every rank, hence the same new slab size everywhere
+      D.chunk = mx2 + mx2 / 8 + 64;
+      chunk = D.chunk; nslots = chunk * D.world;
+      D.flag.resize(nslots + 1); D.off.resize(nslots + 1);
+      cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, nslots + 1, st_);
+      D.temp.resize(need + 16);
+      xq.resize_keep((size_t)chunk); tag.resize_keep((size_t)chunk); ltype_d.resize_keep((size_t)chunk); type.resize_keep((size_t)chunk);
+      xq.n = n;
+      v_d.resize_keep((size_t)3 * chunk);
+      { const size_t keep = q_s_hist.n; q_s_hist.resize_keep((size_t)5 * chunk); q_t_hist.resize_keep((size_t)5 * chunk); q_s_hist.n = keep; q_t_hist.n = keep; }
+    }
+  }
   D.rec2_send.resize((size_t)chunk * 5); D.rec2_all.resize((size_t)nslots * 5);
   k_pack_compact<<<nblk(n), 256, 0, st_>>>(n, xq.p, tag.p, ltype_d.p, D.rec2_send.p);
   RXB_NCCL(ncclAllGather(D.rec2_send.p, D.rec2_all.p, (size_t)chunk * 5, ncclDouble, D.comm, st_));
@@ -347,7 +369,6 @@ void System::dist_exchange() {
   cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
   long long nghost = 0;
   RXB_CUDA(cudaMemcpyAsync(&nghost, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
   N = n + (int)nghost;
   ensure_atom_capacity();

@@ -569,6 +569,43 @@ void System::step_forces(bool eflag, bool vflag) {
   if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
 }
 
+// End-of-force-phase status: bond cursor, overflow bits and work-list counts of this rank (h, wk) plus, in need_, the
+// maxima over all ranks (one small ncclAllReduce(max) in multi-GPU runs), energies / virial on ev steps.  ONE host
+// synchronisation.  Every replay decision is taken on need_ / overflow_flag, which are identical on all ranks.
+namespace {
+// slots: 0 bond cursor, 1..3 n_ang n_tor n_hb, 4 bond arrays too small, 5 fatal per-atom bits, 6..8 work list too small.
+// Slots 4..8 are 0/1 (or a bit mask whose any-non-zero matters), so the maximum over ranks is the OR over ranks.
+__global__ void k_gather_status(const int* __restrict__ cursor, const int* __restrict__ overflow, const int* __restrict__ counts,
+                                int cap_ang, int cap_tor, int cap_hb, int* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    const int ov = overflow[0];
+    out[0] = cursor[0]; out[1] = counts[0]; out[2] = counts[1]; out[3] = counts[2];
+    out[4] = (ov & 2) ? 1 : 0; out[5] = ov & ~2;
+    out[6] = counts[0] > cap_ang; out[7] = counts[1] > cap_tor; out[8] = counts[2] > cap_hb;
+    for (int k = 0; k < 9; k++) out[16 + k] = out[k];
+  }
+}
+}  // namespace
+
+void System::read_step_status(bool ev, int* h, int* wk) {
+  status_d_.resize(32);
+  k_gather_status<<<1, 32, 0, st_>>>(b_cursor.p, overflow.p, it_count.p, cap_ang, cap_tor, cap_hb, status_d_.p);
+  kernel_launches++;
+  if (dist_) dist_allreduce_max_int(status_d_.p + 16, 9);
+  int host[32];
+  RXB_CUDA(cudaMemcpyAsync(host, status_d_.p, 32 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  if (ev && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
+  if (ev) {
+    RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  }
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  h[0] = host[0]; h[1] = host[5] | (host[4] ? 2 : 0);
+  wk[0] = host[1]; wk[1] = host[2]; wk[2] = host[3]; wk[3] = 0;
+  for (int k = 0; k < 9; k++) need_[k] = host[16 + k];
+  overflow_flag = need_[5] | (need_[4] ? 2 : 0);      // over all ranks
+}
+
 void System::compute(bool eflag, bool vflag) {
   RXB_CUDA(cudaSetDevice(device_));
   update_shadow(st_);
@@ -583,22 +620,17 @@ void System::compute(bool eflag, bool vflag) {
   for (int attempt = 0; attempt < 4; attempt++) {
     step_forces(eflag, vflag);
     int h[2], wk[4];
-    RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaMemcpyAsync(wk, it_count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    if ((eflag || vflag) && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
-    if (eflag || vflag) {
-      RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
-      RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
-    }
-    RXB_CUDA(cudaStreamSynchronize(st_));
+    read_step_status(eflag || vflag, h, wk);
     num_bonds = h[0];
-    overflow_flag = h[1];
     num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
-    const bool lists_fit = wk[0] <= cap_ang && wk[1] <= cap_tor && wk[2] <= cap_hb;
+    // (multi-GPU: overflow_flag and the needed capacities below are the maxima over all ranks, so every rank replays the
+    // same number of times and the collectives inside the loop stay matched)
+    const bool lists_fit = !(need_[6] | need_[7] | need_[8]);
     if (!(overflow_flag & 2) && lists_fit) break;
-    // a list did not fit: grow and replay the force computation of this step (positions are unchanged)
+    // a list did not fit (on some rank): grow to the largest need of any rank and replay the force computation of this
+    // step (positions are unchanged)
     RXB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st_));
+    h[0] = need_[0]; wk[0] = need_[1]; wk[1] = need_[2]; wk[2] = need_[3];
     if (overflow_flag & 2) ensure_bond_capacity((int)std::min<long long>((long long)h[0] + h[0] / 4 + 1024, 2000000000LL));
     if (wk[0] > cap_ang) { cap_ang = wk[0] + wk[0] / 4 + 1024; it_ang.resize(cap_ang); }
     if (wk[1] > cap_tor) { cap_tor = wk[1] + wk[1] / 4 + 1024; it_tor.resize(cap_tor); }
@@ -729,15 +761,7 @@ void System::overlapped_back(bool eflag, bool vflag) {
   if (g_odbg.on) cudaEventRecord(g_odbg.e[6], st_);    // end of dbond
   if (vflag) { k_fdotr<<<148 * 4, 256, 0, st_>>>(N, xq.p, f.p, virial_d.p); kernel_launches++; }
   int h[2], wk[4];
-  RXB_CUDA(cudaMemcpyAsync(&h[0], b_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaMemcpyAsync(&h[1], overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaMemcpyAsync(wk, it_count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  if (ev && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
-  if (ev) {
-    RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  }
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  read_step_status(ev, h, wk);
   if (g_odbg.on) {
     cudaStreamSynchronize(st2_);
     float ms;
@@ -750,9 +774,9 @@ void System::overlapped_back(bool eflag, bool vflag) {
       g_odbg.steps = 0;
     }
   }
-  num_bonds = h[0]; overflow_flag = h[1];
+  num_bonds = h[0];
   num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
-  if ((overflow_flag & 2) || wk[0] > cap_ang || wk[1] > cap_tor || wk[2] > cap_hb) {
+  if ((overflow_flag & 2) || need_[6] || need_[7] || need_[8]) {
     qeq_ran_this_step_ = true;           // far list and charges of this step are valid: replay only the force phase
     compute(eflag, vflag);               // sequential path grows the arrays and replays
   } else if (overflow_flag & ~2) {

@@ -139,6 +139,9 @@ class System {
   int matvecs_s = 0, matvecs_t = 0;
   long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
 
+  int h_bytes_per_entry() const { return 12; }
+  const char* h_format_name() const { return "fp64 value + int32 column (12 B)"; }
+
   // ---- pair compute ----
   void compute(bool eflag, bool vflag);
   double energies[E_NUM] = {0};
@@ -168,6 +171,7 @@ class System {
   void dist_allreduce(double* dev_ptr, int count);
   int dist_rank() const;
   void dist_allreduce_int(int* dev_ptr, size_t count);
+  void dist_allreduce_max_int(int* dev_ptr, size_t count);
   void dist_allgather_int(const int* send, int* recv, size_t count_per_rank);
   void dist_exchange();          // exchange + borders at reneighbouring
   void dist_build_plan();        // peer-to-peer send lists for the boundary exchange
@@ -284,6 +288,9 @@ class System {
   double* pin(size_t doubles);
   void h2d(void* dst, const void* src, size_t bytes, size_t stage_off_doubles);
   void step_forces(bool eflag, bool vflag);
+  void read_step_status(bool ev, int* h2, int* wk4);
+  DBuf<int> status_d_;
+  int need_[9] = {0};                    // status slots of k_gather_status, maximum over all ranks
   void ensure_atom_capacity();
   void ensure_bond_capacity(int cap);
   void md_make_ghosts();

@@ -432,6 +432,7 @@ void LAMMPS::setup() {
   domain->remap(*atom);
   comm->borders(*domain, *atom, pair->cutghost_request() + neighbor->skin);
   neighbor->ago = 0;
+  neighbor->ncalls++;
   const int ev = 1;
   for (auto& f : fixes) f->setup_pre_force(ev);
   std::fill(atom->f.begin(), atom->f.end(), 0.0);
@@ -462,6 +463,7 @@ void LAMMPS::iterate(long nsteps) {
       domain->remap(*atom);
       comm->borders(*domain, *atom, pair->cutghost_request() + neighbor->skin);
       neighbor->ago = 0;
+      neighbor->ncalls++;
       lap(1, t0);
     } else {
       comm->forward_comm(*atom);

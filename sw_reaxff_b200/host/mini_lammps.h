@@ -62,6 +62,7 @@ struct Comm {   // single rank: ghosts are periodic images
 struct Neighbor {
   double skin = 2.0;
   int every = 1, delay = 10, dist_check = 1, ago = 0;
+  long ncalls = 0;   // number of borders/neighbour builds so far (LAMMPS Neighbor::ncalls): a new index space each time
   int decide() { ago++; return (ago >= delay && ago % every == 0) ? 1 : 0; }   // 'check no' semantics
 };
 

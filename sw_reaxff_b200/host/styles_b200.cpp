@@ -93,18 +93,36 @@ void PairReaxCB200::init_style() {
 
 void PairReaxCB200::upload_if_needed() {
   Atom* atom = lmp->atom;
-  if (uploaded_step == lmp->update->ntimestep) return;
+  // Keyed on the timestep AND the build generation: LAMMPS::setup() of a second `run` re-does remap + borders without
+  // advancing ntimestep, which gives a new ghost set / index space that must reach the device.
+  if (uploaded_step == lmp->update->ntimestep && uploaded_build == lmp->neighbor->ncalls) return;
   pin_x_.ensure(atom->x.data(), atom->x.capacity() * sizeof(double));   // direct PCIe copies of atom->x
-  if (lmp->neighbor->ago == 0) {
-    // reneighbouring step: new index space (what write_reax_atoms + NPair::build + write_reax_lists do in the reference)
+  if (uploaded_build != lmp->neighbor->ncalls) {
+    // reneighbouring step: new index space (what write_reax_atoms + NPair::build + write_reax_lists do in the reference).
+    // atom->q goes up with it, so it must be the device's latest solution (fix qeq/reax with nevery > 1 skips steps, and
+    // the host copy is otherwise refreshed on thermo steps only): the old index space is still the host's local order.
+    if (device_q_newer && uploaded_build >= 0) {
+      std::vector<double> qd((size_t)device_nall_);
+      if (rxb_get_charges(rxb, qd.data())) lmp->error->all(FLERR, rxb_last_error());
+      // local atoms keep their order across exchange in this stand-in core; ghosts are rebuilt from their owners
+      const int nl = std::min(device_nlocal_, atom->nlocal);
+      for (int i = 0; i < nl; i++) atom->q[i] = qd[i];
+      for (int g = 0; g < atom->nghost; g++) {
+        const int o = lmp->comm->ghost_owner[g];
+        if (o >= 0) atom->q[atom->nlocal + g] = atom->q[o];
+      }
+      device_q_newer = false;
+    }
     if (rxb_set_atoms(rxb, atom->nlocal, atom->nghost, atom->x.data(), atom->type.data(), atom->tag.data(), atom->q.data(),
                       lmp->comm->ghost_owner.data()))
       lmp->error->all(FLERR, rxb_last_error());
     if (rxb_neigh_build(rxb)) lmp->error->all(FLERR, rxb_last_error());
+    device_nlocal_ = atom->nlocal; device_nall_ = atom->nall();
   } else {
-    if (rxb_set_positions(rxb, atom->x.data())) lmp->error->all(FLERR, rxb_last_error());
+    if (rxb_set_positions(rxb, atom->nall(), atom->x.data())) lmp->error->all(FLERR, rxb_last_error());
   }
   uploaded_step = lmp->update->ntimestep;
+  uploaded_build = lmp->neighbor->ncalls;
 }
 
 void PairReaxCB200::compute(int eflag, int vflag) {
@@ -115,7 +133,7 @@ void PairReaxCB200::compute(int eflag, int vflag) {
   fbuf_.resize((size_t)3 * nall);
   pin_f_.ensure(fbuf_.data(), fbuf_.capacity() * sizeof(double));
   double eng[2], vir[6];
-  if (rxb_pair_compute(rxb, eflag, vflag, fbuf_.data(), pvector, eng, vir)) lmp->error->all(FLERR, rxb_last_error());
+  if (rxb_pair_compute(rxb, nall, eflag, vflag, fbuf_.data(), pvector, eng, vir)) lmp->error->all(FLERR, rxb_last_error());
   double* f = atom->f.data();
   const double* fb = fbuf_.data();
   const long n3 = 3L * nall;
@@ -169,8 +187,11 @@ void FixQEqReaxB200::pre_force(int) {
   if (mv[0] >= 200 || mv[1] >= 200)
     lmp->error->warning(FLERR, "Fix qeq/reax CG convergence failed after 200 iterations at " + std::to_string(lmp->update->ntimestep) + " step");
   // atom->q on the host is only needed by host-side consumers (thermo/dump): refresh it on thermo steps
-  if (lmp->thermo_every && lmp->update->ntimestep % lmp->thermo_every == 0)
+  reaxc->device_q_newer = true;
+  if (lmp->thermo_every && lmp->update->ntimestep % lmp->thermo_every == 0) {
     rxb_get_charges(reaxc->rxb, lmp->atom->q.data());
+    reaxc->device_q_newer = false;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

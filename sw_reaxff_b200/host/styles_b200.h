@@ -41,7 +41,9 @@ class PairReaxCB200 : public Pair {
   double cutmax = 0.0, bg_cut = 0.3;
   std::vector<double> chi, eta, gamma;
   std::vector<int> map;
-  long uploaded_step = -1;
+  int device_nlocal_ = 0, device_nall_ = 0;
+  long uploaded_step = -1, uploaded_build = -1;   // what the device currently holds: (ntimestep, neighbor->ncalls)
+  bool device_q_newer = false;                    // the device ran QEq since atom->q was last refreshed on the host
   int fixspecies_flag = 0, fixbond_flag = 0;
 
  private:

@@ -1,22 +1,22 @@
 """Decomposition-invariance check (run under torchrun on N GPUs of one box):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/gpu_dist_check.py [nx ny nz steps]
+        tests/gpu_dist_check.py [nx ny nz steps T p2p]
 
 The N-rank domain-decomposed run and a single-GPU run of the same global system (rank 0) must agree on positions,
-forces, charges and energies by atom tag.  Exits non-zero on mismatch.
+forces, charges and energies by atom tag; the comparison itself is sw_reaxff_b200.dist.parity_check,
+the same function bench.py runs before timing anything at N > 1.  Exits non-zero on mismatch.
 """
+import json
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import helpers as H  # noqa: E402
-from sw_reaxff_b200 import Rxb  # noqa: E402
 from sw_reaxff_b200 import dist as D  # noqa: E402
 
 
@@ -28,73 +28,13 @@ def main():
     p2p = int(sys.argv[6]) if len(sys.argv) >= 7 else 1
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    dev = torch.device("cuda", lr)
-    tol = 1e-10
-    r, grid, n0 = D.setup_distributed(H, rank, world, lr, cells, tol=tol, thermo=1, T=T, p2p=p2p)
-    th0 = r.md_thermo()
-    natoms = 384 * cells[0] * cells[1] * cells[2]
-    r.species_config(1, 5, 5, natoms=natoms)
-    r.md_run(steps)
-    sp_log = r.species_log()
-    bt = r.bond_table()
-    bt_entries = int(D.sum_over_ranks(dist, [float(len(bt["nbr"]))], dev)[0])
-    th = r.md_thermo()
-    out = r.md_get()
-    c = r.counts()
-    n = int(c[0])
-    # gather (tag, x, f, q) on every rank
-    nmax = int(D.max_over_ranks(dist, float(n), dev))
-    # tags of the current local atoms: md_get returns arrays in local order; fetch tags through a charge-like channel
-    tags = r.local_tags()
-    pad = torch.zeros(nmax, 8, dtype=torch.float64, device=dev)
-    blk = np.concatenate([tags[:, None].astype(np.float64), out["x"], out["f"], out["q"][:, None]], axis=1)
-    pad[:n] = torch.from_numpy(blk).to(dev)
-    bufs = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
-    ok = True
+    out = D.parity_check(H, rank, world, lr, cells=cells, steps=steps, T=T, p2p=p2p)
     if rank == 0:
-        allr = torch.cat(bufs).cpu().numpy()
-        allr = allr[allr[:, 0] > 0]
-        allr = allr[np.argsort(allr[:, 0])]
-        assert len(allr) == natoms and np.array_equal(allr[:, 0].astype(np.int64), np.arange(1, natoms + 1)), "atoms lost or duplicated"
-        box, x, t, tag = H.tatb_cell(*cells)
-        v = D.velocities_by_tag(H, t, tag, T, 12345)
-        s = Rxb(lr)
-        s.pair_settings(H.CONTROL); s.pair_coeff(H.FFIELD, H.ELEMENTS); s.fix_qeq(0.0, 10.0, tol)
-        s.md_setup(box, x, v, t, tag, H.MASS, dt=0.0625, every=5, thermo=1)
-        s0 = s.md_thermo()
-        s.species_config(1, 5, 5, natoms=natoms)
-        s.md_run(steps)
-        ref_log = s.species_log()
-        ok_sp = len(ref_log) == len(sp_log) and len(ref_log) == steps // 5 and all(
-            a["step"] == b["step"] and a["nmole"] == b["nmole"] and np.array_equal(a["composition"], b["composition"])
-            for a, b in zip(ref_log, sp_log))
-        ok_sp = ok_sp and len(s.bond_table()["nbr"]) == bt_entries
-        print(f"bond table entries {bt_entries}; species: {len(sp_log)} outputs, last nmole {sp_log[-1]['nmole'] if sp_log else None}, identical to 1 GPU: {ok_sp}")
-        ref = s.md_get(); sth = s.md_thermo()
-        # single-GPU run keeps atoms in tag order (no migration of indices)
-        # positions may differ by a box vector after wrapping: compare through lamda-space minimum image
-        dx = allr[:, 1:4] - ref["x"]
-        a = np.array([box[0], 0, 0]); b = np.array([box[3], box[1], 0]); cc = np.array([box[4], box[5], box[2]])
-        Hm = np.stack([a, b, cc], axis=1)
-        lam = np.linalg.solve(Hm, dx.T).T
-        dx = (Hm @ (lam - np.round(lam)).T).T
-        ex = np.abs(dx).max()
-        ef = np.abs(allr[:, 4:7] - ref["f"]).max() / np.abs(ref["f"]).max()
-        eq = np.abs(allr[:, 7] - ref["q"]).max()
-        ee0 = abs(th0["pe"] - s0["pe"]) / abs(s0["pe"])
-        ee = abs(th["pe"] - sth["pe"]) / abs(sth["pe"])
-        ek = abs(th["ke"] - sth["ke"]) / abs(sth["ke"])
-        moved = int((np.abs(lam) > 0.5).any(axis=1).sum())
-        print(f"dist check {world} ranks grid {grid} cells {cells} steps {steps} T {T} p2p {p2p} n_local(rank0) {n} vs {n0} at start, wrapped {moved}: |dx| {ex:.2e}  f rel {ef:.2e}  |dq| {eq:.2e}  "
-              f"pe0 rel {ee0:.2e}  pe rel {ee:.2e}  ke rel {ek:.2e}  pe {th['pe']:.6f} vs {sth['pe']:.6f}")
-        ok = ok_sp and ex < 1e-8 and ef < 1e-6 and eq < 1e-7 and ee0 < 1e-9 and ee < 1e-8 and ek < 1e-6
-        print("DIST CHECK", "PASSED" if ok else "FAILED")
-    flag = torch.tensor([1.0 if ok else 0.0], device=dev, dtype=torch.float64)
-    dist.broadcast(flag, src=0)
+        print("dist check", json.dumps(out))
+        print("DIST CHECK", "PASSED" if out["ok"] else "FAILED")
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    sys.exit(0 if out["ok"] else 1)
 
 
 if __name__ == "__main__":

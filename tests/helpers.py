@@ -259,6 +259,11 @@ class Oracle:
     def md_matvecs(self):
         return self.L.orc_md_matvecs(self.h, 0), self.L.orc_md_matvecs(self.h, 1)
 
+    def omp_threads(self, n=0):
+        """Set (n > 0) and return the OpenMP thread count the oracle library really runs with (torchrun exports
+        OMP_NUM_THREADS=1, so the environment variable alone is not to be trusted)."""
+        return int(self.L.orc_omp_threads(int(n)))
+
     # ---- fix reax/c/bonds, fix reax/c/species ----
     def _text(self, fn, step):
         self.L[fn].restype = C.c_long

@@ -425,3 +425,53 @@ def test_neighbor_rows_outgrowing_the_stride_are_rebuilt():
         assert rel(res["pvector"], pvector_from_oracle(eo)) < 1e-7
         assert rel(res["f"], o.forces()) < 1e-5          # charges converged to 1e-8 on both sides
     assert np.diff(off_g).max() > 1200                    # the compressed rows are far longer than the first build's stride
+
+
+def test_nall_mismatch_is_an_error_not_an_overrun():
+    """rxb_set_positions / rxb_pair_compute refuse a caller whose nall differs from the device's atom count."""
+    from sw_reaxff_b200.api import RxbError
+    cfg = H.static_config(1, 1, 1, qeq=False)
+    r = make_rxb()
+    r.set_atoms(cfg["n"], cfg["x"], cfg["type"], cfg["tag"], np.zeros(len(cfg["x"])), cfg["owner"])
+    r.neigh_build()
+    with pytest.raises(RxbError, match="nall"):
+        r.set_positions(cfg["x"][:-3])
+    r.qeq_pre_force()
+    with pytest.raises(RxbError, match="nall"):
+        r.pair_compute(True, True, f_out=np.zeros((len(cfg["x"]) + 5, 3)))
+
+
+def test_inner_skin_fallback_far_list_exact_beyond_the_margin():
+    """Adaptive inner skin (rxb_nonbonded.cu): the far-list sweep reads only the inner block of each Verlet row while no
+    atom has moved more than (cut_in - far)/2 = 0.25 A since the build, and must fall back to the full rows beyond that.
+    Atoms are displaced WITHOUT rebuilding the lists, just below and well above the threshold; far list and H must equal
+    the oracle's (which filters a fresh 12.5 A list) in both regimes."""
+    cfg = H.static_config(1, 1, 1, perturb=0.05, seed=11, qeq=False)
+    n, x0, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    r = make_rxb(1e-6)
+    r.set_atoms(n, x0, ty, tg, np.zeros(len(x0)), owner)
+    r.neigh_build()
+    rng = np.random.default_rng(5)
+    for amp in (0.2, 0.9):     # max displacement: 0.2*sqrt(3)/... below 0.25 A per atom norm is enforced explicitly
+        d = rng.uniform(-1, 1, size=(n, 3))
+        d *= (amp / np.linalg.norm(d, axis=1).max())
+        x = x0.copy()
+        x[:n] += d
+        x[n:] = x[owner] + (x0[n:] - x0[owner])            # ghosts follow their owners
+        r.set_positions(x)
+        r.qeq_pre_force()
+        num_g, idx_g, val_g = r.far()
+        off_g, _ = r.neighbors(0)
+        o = H.Oracle()
+        o.set_atoms(n, x, ty, tg, np.zeros(len(x)))
+        o.build_neighbors(12.5 + 2 * amp)                  # every pair within 10 A now is in this list
+        o.qeq_init(0.0, 10.0, 1e-6)
+        o.qeq_set_hist(np.zeros((n, 5)), np.zeros((n, 5)))
+        o.qeq_pre_force(owner)
+        offH, numH, colH, valH = o.qeq_H()
+        assert np.array_equal(num_g, numH), amp
+        for i in range(0, n, 7):
+            a = dict(zip(idx_g[off_g[i]:off_g[i] + num_g[i]].tolist(), val_g[off_g[i]:off_g[i] + num_g[i]].tolist()))
+            b = dict(zip(colH[offH[i]:offH[i] + numH[i]].tolist(), valH[offH[i]:offH[i] + numH[i]].tolist()))
+            assert a.keys() == b.keys(), (amp, i)
+            assert max(abs(a[k] - b[k]) for k in b) < 1e-11 * np.abs(valH).max()

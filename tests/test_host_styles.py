@@ -158,3 +158,22 @@ def test_reference_style_lattice_script(tmp_path):
     assert abs(a[0, 2] - b[0, 2]) < 1e-7 * abs(b[0, 2])       # same crystal from lattice custom + create_atoms basis
     a2 = run_script(lattice_script(tmp_path, 0), S=2)
     assert abs(a2[0, 2] - 8 * b[0, 2]) < 1e-7 * abs(8 * b[0, 2])
+
+
+@pytest.mark.gpu
+def test_two_runs_in_one_script_reupload_after_setup(tmp_path):
+    """`run 8` then `run 8` with `every 5`: LAMMPS::setup() of the second run re-does remap + borders WITHOUT advancing
+    the timestep (new ghost set, new index space).  The pair style must re-upload atoms and rebuild the lists then; the
+    thermo of the split run equals the thermo of one `run 16` wherever both print (styles_b200.cpp)."""
+    base = open(SCRIPT).read()
+    one = tmp_path / "in.one"; two = tmp_path / "in.two"
+    one.write_text(base.replace("run             $t", "run             16"))
+    two.write_text(base.replace("run             $t", "run             8\nrun             8"))
+    a = run_script(str(one), S=1, T=1500.0, D=H.DATA, dt=0.25)
+    b = run_script(str(two), S=1, T=1500.0, D=H.DATA, dt=0.25)
+    sa = {int(r[0]): r for r in a}; sb = {int(r[0]): r for r in b}
+    assert 16 in sa and 16 in sb and 8 in sb
+    for step in (5, 10, 15, 16):
+        if step in sa and step in sb:
+            assert abs(sa[step][2] - sb[step][2]) < 1e-8 * abs(sa[step][2]), (step, sa[step][2], sb[step][2])
+            np.testing.assert_allclose(sa[step][5:], sb[step][5:], rtol=1e-6, atol=1e-6)
