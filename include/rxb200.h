@@ -73,6 +73,15 @@ int rxb_neigh_build(rxb_handle* h);
 /* ---- FixQEqReaxSunway::pre_force (fix_qeq_reax_sunway.cpp:539-600): H build + dual-RHS pipelined CG + q.
  *      matvecs2[0..1] = iterations of the s and t solves (the reference's matvecs_s, matvecs_t). */
 int rxb_qeq_pre_force(rxb_handle* h, int* matvecs2);
+/* matvecs2 == NULL: the solve is only enqueued (as many iterations as the previous step took, plus a margin; iterations
+ * past convergence are gated off on the device) and its convergence is checked together with the end-of-step status of
+ * rxb_pair_compute, which continues it in the rare case the prediction fell short - no host round trip inside the step.
+ * rxb_qeq_matvecs then returns the counts of that solve. */
+int rxb_qeq_matvecs(rxb_handle* h, int* matvecs2);
+/* H entry storage (SpMV stream): 0 (default) = packed 8-byte entries (22-bit column + 42-bit fixed-point value, absolute
+ * quantisation 2^-39 ~ 1.8e-12 for TATB) whenever the taper starts at 0 and nall < 2^22; 1 = always fp64 value + int32
+ * column (12 bytes).  Takes effect at the next rxb_qeq_pre_force. */
+int rxb_set_h_exact(rxb_handle* h, int on);
 int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist); /* [nlocal][5] */
 int rxb_qeq_get_history(rxb_handle* h, double* s_hist, double* t_hist);
 int rxb_get_charges(rxb_handle* h, double* q); /* nall */

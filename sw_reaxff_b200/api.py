@@ -17,6 +17,7 @@ SYMBOLS = [
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
+    "rxb_qeq_matvecs", "rxb_set_h_exact",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -136,6 +137,18 @@ class Rxb:
         mv = np.zeros(2, dtype=np.int32)
         self._chk(self.lib.rxb_qeq_pre_force(self.h, _p(mv)))
         return int(mv[0]), int(mv[1])
+
+    def qeq_pre_force_async(self):
+        """Enqueue the solve without a host round trip (settled inside pair_compute); counts via qeq_matvecs()."""
+        self._chk(self.lib.rxb_qeq_pre_force(self.h, None))
+
+    def qeq_matvecs(self):
+        mv = np.zeros(2, dtype=np.int32)
+        self._chk(self.lib.rxb_qeq_matvecs(self.h, _p(mv)))
+        return int(mv[0]), int(mv[1])
+
+    def set_h_exact(self, on=True):
+        self._chk(self.lib.rxb_set_h_exact(self.h, int(on)))
 
     def qeq_set_history(self, s_hist, t_hist):
         s = _f(s_hist); t = _f(t_hist)

@@ -170,10 +170,19 @@ int rxb_neigh_build(rxb_handle* h) { return guard([&] { h->sys->build_neighbors(
 
 int rxb_qeq_pre_force(rxb_handle* h, int* matvecs2) {
   return guard([&] {
-    h->sys->plugin_qeq_pre_force();
+    // matvecs2 == NULL: nobody needs the iteration counts now, so the solve is enqueued without a host round trip and
+    // settled inside rxb_pair_compute (rxb_qeq_matvecs reports the counts afterwards)
+    h->sys->plugin_qeq_pre_force(matvecs2 != nullptr);
     if (matvecs2) { matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t; }
   });
 }
+int rxb_qeq_matvecs(rxb_handle* h, int* matvecs2) {
+  return guard([&] {
+    h->sys->qeq_settle_now();
+    matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t;
+  });
+}
+int rxb_set_h_exact(rxb_handle* h, int on) { return guard([&] { h->sys->h_exact_request = on != 0; }); }
 int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist) {
   return guard([&] { h->sys->qeq_set_history(s_hist, t_hist); });
 }
@@ -249,7 +258,8 @@ int rxb_get_counts(rxb_handle* h, long long* c) {
 int rxb_get_neighbors(rxb_handle* h, int which, long long* off, int* idx) {
   return guard([&] {
     System& s = *h->sys;
-    rxb::Csr& c = which == 0 ? s.vl : s.bc;
+    if (which == 0) { s.export_verlet(off, idx); return; }   // the Verlet list lives in S space: translated on the host
+    rxb::Csr& c = s.bc;
     // the device rows sit at a fixed stride: hand out a compact CSR
     std::vector<int> cnt(c.nrows), raw((size_t)std::max<long long>(c.slots, 1));
     d2h(cnt.data(), c.cnt.p, (size_t)c.nrows, s.stream());
@@ -322,21 +332,8 @@ int rxb_get_workspace(rxb_handle* h, double* w16) {
 
 int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val) {
   return guard([&] {
-    System& s = *h->sys;
-    d2h(num, s.far_num.p, (size_t)s.n, s.stream());
-    // compact like rxb_get_neighbors(0): row i of the output starts at the compact Verlet offset of row i
-    const rxb::Csr& c = s.vl;
-    std::vector<int> cnt(c.nrows), ri((size_t)std::max<long long>(c.slots, 1));
-    std::vector<double> rv((size_t)std::max<long long>(c.slots, 1));
-    d2h(cnt.data(), c.cnt.p, (size_t)c.nrows, s.stream());
-    d2h(ri.data(), s.far_idx.p, (size_t)c.slots, s.stream());
-    d2h(rv.data(), s.H_val.p, (size_t)c.slots, s.stream());
-    long long w = 0;
-    for (int i = 0; i < c.nrows; i++) {
-      memcpy(idx + w, ri.data() + (size_t)i * c.stride, (size_t)num[i] * sizeof(int));
-      memcpy(val + w, rv.data() + (size_t)i * c.stride, (size_t)num[i] * sizeof(double));
-      w += cnt[i];
-    }
+    // compact like rxb_get_neighbors(0): the entries of atom i start at the compact Verlet offset of atom i
+    h->sys->export_far(num, idx, val);
   });
 }
 

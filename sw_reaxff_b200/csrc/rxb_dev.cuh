@@ -45,7 +45,9 @@ struct DevView {
   double* f;           // N*3, true forces
   double* CdDelta;     // N
   // Verlet list r <= cutneigh, local rows          (a1)
-  const long long* vl_off; const int* vl_idx; const int* vl_cnt;   // row i: vl_idx[vl_off[i] .. + vl_cnt[i])
+  // rows sit at a fixed stride: row r = vl_idx[r * vl_stride .. + vl_cnt[r]); rows = local atoms in S order, columns = sorted
+  // positions (see "S space" below)
+  const long long* vl_off; const int* vl_idx; const int* vl_cnt; int vl_stride;
   // inner partition of the Verlet rows: the first vl_cnt_in[i] entries were within vl_cut_in (> the far cut-off) when the
   // list was built; *disp2 = max |x - x_build|^2 over all atoms this step.  A pair inside the far cut-off now was within
   // far + 2 sqrt(*disp2) at the build, so while that is <= vl_cut_in the far-list sweep reads only the inner block.
@@ -54,8 +56,23 @@ struct DevView {
   const long long* bc_off; const int* bc_idx; const int* bc_cnt;
   // hbond candidates r <= hbond_cut + skin, local H rows only
   const long long* hc_off; const int* hc_idx;
-  // far list == H sparsity pattern: r <= nonb_cut / swb, local rows, slots vl_off[i] .. +far_num[i]
+  // ---- S space: the cell-sorted order of the last neighbour build.  The long-range machinery (Verlet list, far list, H,
+  // nonbonded sweep, CG vectors) lives in it: row r = the r-th LOCAL atom in sorted order, columns = sorted positions of
+  // all atoms (locals and ghosts interleaved as they lie in space).  Neighbours of a row are then runs of consecutive
+  // integers, so the per-pair gathers of positions / charges / CG vectors touch whole cache lines instead of one sector
+  // per lane.  The bonded machinery keeps the caller's atom order; s2a / row_atom translate.
+  const int* s2a;        // N: sorted position -> atom index
+  const int* rowpos;     // n: row -> sorted position
+  const int* row_atom;   // n: row -> atom index
+  const float4* xs;      // N: fp32 shadow in S order (origin-relative x,y,z; element type bits in .w), refreshed every step
+  double4* xqs;          // N: exact (x,y,z,q) in S order, refreshed every step (q again after the QEq solve)
+  const int* type_s;     // N: element index in S order
+  // far list == H sparsity pattern: r <= nonb_cut / swb, row r in slots vl_off[r] .. +far_num[r].  Two storage formats:
+  //  packed (default): one 64-bit word per entry = column (22 bits) << 42 | round(H * 2^h_shift) (42-bit fixed point);
+  //  exact           : int32 column in far_idx + fp64 value in H_val (systems beyond 2^22 atoms per GPU, parity tests).
   int* far_num; int* far_idx; double* H_val;
+  unsigned long long* hpk;
+  double h_quant;        // 2^h_shift (packed format); the SpMV multiplies its row sums by 1 / h_quant
   // bonds
   int* b_start; int* b_cnt; int* b_cursor; int* overflow;
   int* b_nbr; int* b_sym; int* b_owner;
@@ -86,6 +103,21 @@ struct BondedWork {
   int cap_ang, cap_tor, cap_hb;
   double4* sbo;   // per local centre: SBO2, CSBO2, dSBO1, dSBO2
   double2* sum56; // per atom: sum CEval5, sum CEval6 over the angles centred on it
+};
+
+// packed H entry (rxb_nonbonded.cu writes, rxb_qeq.cu / rxb_nonbonded.cu read)
+constexpr int kHColShift = 42;
+constexpr unsigned long long kHValMask = (1ULL << kHColShift) - 1;
+
+struct QeqState {       // device-resident CG scalars, double-buffered by iteration parity
+  double alpha[2], heta[2], sig_old[2], b_norm[2], dot0[2];
+  int active[2], iters[2];
+};
+struct QeqDev {
+  QeqState st[2];
+  double dots[3][4];    // rotating accumulators: (u.r)_s, (u.r)_t, (u.w)_s, (u.w)_t
+  double pro[6];        // prologue: b.b, u.r, u.w for s and t
+  double sums[2];       // sum s, sum t
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

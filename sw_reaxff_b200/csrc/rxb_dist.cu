@@ -58,6 +58,8 @@ struct Dist {
   DBuf<int> greq, sendlist, cnt_d, cnt_all_d;
   DBuf<double> sendbuf, recvbuf;
   DBuf<double> dots_all;                 // [world][4]: every rank's partial CG dot products (dist_forward2_dots)
+  DBuf<int> send_s, self_s;              // sorted positions of the atoms I send / of the sources of my own periodic images
+  DBuf<double> recv2;                    // staging of received double2 ghost values, ghost order
 };
 
 namespace {
@@ -506,13 +508,58 @@ void System::dist_forward_xq() {
   kernel_launches++;
 }
 
-void System::dist_forward2(double2* vec) {
+// ---- S-space vectors (the CG search direction): locals and ghosts are interleaved in cell-sorted order, so the boundary
+// values are packed through send_s (sorted positions of the atoms each peer needs), received into a staging buffer in ghost
+// order and scattered to the ghosts' sorted positions by one kernel that also serves this rank's own periodic images.
+namespace {
+__global__ void k_map_idx(int m, const int* __restrict__ list, const int* __restrict__ a2s, int* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m) out[e] = a2s[list[e]];
+}
+__global__ void k_unpack_ghosts2(int nghost, int g0, int g1, const int* __restrict__ gs_pos, const int* __restrict__ self_s,
+                                 const double2* __restrict__ recv, double2* __restrict__ vec) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  vec[gs_pos[g]] = (g >= g0 && g < g1) ? vec[self_s[g - g0]] : recv[g];
+}
+}  // namespace
+
+void System::dist_sorted_maps() {
   Dist& D = *dist_;
-  if (D.p2p) { p2p_forward<2>(*this, D, reinterpret_cast<double*>(vec), n, st_); return; }
-  RXB_NCCL(ncclAllGather(vec, D.d_all.p, (size_t)D.chunk * 2, ncclDouble, D.comm, st_));
   const int nghost = N - n;
-  if (nghost > 0) k_ghost_d_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, D.gsrc.p, D.d_all.p, vec);
-  kernel_launches++;
+  D.send_s.resize(std::max(D.nsend, 1));
+  if (D.nsend > 0) k_map_idx<<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, a2s.p, D.send_s.p);
+  const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
+  D.self_s.resize(std::max(g1 - g0, 1));
+  if (g1 > g0) k_map_idx<<<nblk(g1 - g0), 256, 0, st_>>>(g1 - g0, D.greq.p + g0, a2s.p, D.self_s.p);
+  D.recv2.resize((size_t)2 * std::max(nghost, 1));
+  kernel_launches += 2;
+}
+
+static void s_forward2(System& s, Dist& D, double2* vec, int n, int nghost, const int* gs_pos, double* dots, cudaStream_t st) {
+  const int W = D.world;
+  double* v = reinterpret_cast<double*>(vec);
+  if (D.nsend > 0) k_pack<2><<<nblk(D.nsend), 256, 0, st>>>(D.nsend, D.send_s.p, v, D.sendbuf.p);
+  if (dots) D.dots_all.resize((size_t)4 * W);
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    if (dots) {
+      RXB_NCCL(ncclSend(dots, 4, ncclDouble, r, D.comm, st));
+      RXB_NCCL(ncclRecv(D.dots_all.p + (size_t)4 * r, 4, ncclDouble, r, D.comm, st));
+    }
+    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.sendbuf.p + (size_t)2 * D.soff[r], (size_t)2 * D.send_to[r], ncclDouble, r, D.comm, st));
+    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(D.recv2.p + (size_t)2 * D.goff[r], (size_t)2 * D.need_from[r], ncclDouble, r, D.comm, st));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  if (nghost > 0)
+    k_unpack_ghosts2<<<nblk(nghost), 256, 0, st>>>(nghost, D.goff[D.rank], D.goff[D.rank + 1], gs_pos, D.self_s.p,
+                                                  reinterpret_cast<const double2*>(D.recv2.p), vec);
+  s.kernel_launches += 2;
+}
+
+void System::dist_forward2(double2* vec) {
+  s_forward2(*this, *dist_, vec, n, N - n, gs_pos.p, nullptr, st_);
 }
 
 // sum of the per-rank partials in rank order: every rank adds the same numbers in the same order, so all ranks hold the
@@ -531,24 +578,9 @@ __global__ void k_sum_dots(int world, int rank, const double* __restrict__ all, 
 // (the reference: MPI_Allreduce + comm->forward_comm_fix per iteration, fix_qeq_reax_sunway.cpp:1108-1140).
 void System::dist_forward2_dots(double2* vec, double* dots) {
   Dist& D = *dist_;
-  if (!D.p2p) { dist_allreduce(dots, 4); dist_forward2(vec); return; }
-  const int W = D.world;
-  D.dots_all.resize((size_t)4 * W);
-  double* v = reinterpret_cast<double*>(vec);
-  if (D.nsend > 0) k_pack<2><<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, v, D.sendbuf.p);
-  RXB_NCCL(ncclGroupStart());
-  for (int r = 0; r < W; r++) {
-    if (r == D.rank) continue;
-    RXB_NCCL(ncclSend(dots, 4, ncclDouble, r, D.comm, st_));
-    RXB_NCCL(ncclRecv(D.dots_all.p + (size_t)4 * r, 4, ncclDouble, r, D.comm, st_));
-    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.sendbuf.p + (size_t)2 * D.soff[r], (size_t)2 * D.send_to[r], ncclDouble, r, D.comm, st_));
-    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(v + (size_t)2 * (n + D.goff[r]), (size_t)2 * D.need_from[r], ncclDouble, r, D.comm, st_));
-  }
-  RXB_NCCL(ncclGroupEnd());
-  k_sum_dots<<<1, 32, 0, st_>>>(W, D.rank, D.dots_all.p, dots);
-  const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
-  if (g1 > g0) k_self_ghosts<2><<<nblk(g1 - g0), 256, 0, st_>>>(n, g0, g1, D.greq.p, v);
-  kernel_launches += 3;
+  s_forward2(*this, D, vec, n, N - n, gs_pos.p, dots, st_);
+  k_sum_dots<<<1, 32, 0, st_>>>(D.world, D.rank, D.dots_all.p, dots);
+  kernel_launches++;
 }
 
 void System::dist_reverse_f() {

@@ -5,7 +5,8 @@
 // same list semantics (full list, j != i, r^2 <= cut^2 in fp64, rows for ghost atoms when asked),
 // different machinery: atoms are radix-sorted by cell (x fastest) so that every (y,z) stencil row is ONE
 // contiguous run of the sorted position array; a warp owns a row atom, sweeps the runs with coalesced
-// 32-byte loads and ballot-compacts the hits.  No per-atom pages, no fixed row stride.
+// 16-byte loads and ballot-compacts the hits.  Rows sit at a fixed stride (one pass, no count pass).  The Verlet list is
+// emitted in "S space": rows = local atoms in cell-sorted order, columns = sorted positions (rxb_dev.cuh).
 //
 // HBM-bound by design (28(N+G) read + 4 nnz written); the stencil re-reads hit L1/L2.
 #include <cub/cub.cuh>
@@ -82,18 +83,23 @@ __global__ void k_gather_sorted(const double4* __restrict__ xq, const int* __res
   spos[k] = p;
 }
 
-// One warp per row atom.  FILL=false: count hits -> cnt[i];  FILL=true: write columns at off[i].
-// FILL = false: count only.  FILL = true: write row i at i * stride (entries beyond the stride are dropped but still counted,
-// the host then re-runs with a larger stride) and store the row length.
-template <bool FILL>
+// One warp per row.  FILL = false: count only.  FILL = true: write row i at i * stride (entries beyond the stride are dropped
+// but still counted, the host then re-runs with a larger stride) and store the row length.
+// SORTED = false: row i is atom i (position xq[i]) and the columns are atom indices.
+// SORTED = true : row i is the i-th LOCAL atom in cell-sorted order, sitting at sorted position rowpos[i]; the columns are
+//                 sorted positions too ("S space", rxb_dev.cuh), so a row's neighbours are runs of consecutive integers and
+//                 every later gather through this list (shadow positions, charges, CG vectors) touches whole cache lines.
+template <bool FILL, bool SORTED>
 __global__ void __launch_bounds__(256)
-k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const float4* __restrict__ sposf,
-        const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band, float in2hi, int reach,
-        int* __restrict__ cnt, int* __restrict__ cnt_in, long long* __restrict__ off, int* __restrict__ idx, int stride) {
+k_build(const double4* __restrict__ xq, const int* __restrict__ rowpos, const double4* __restrict__ spos,
+        const float4* __restrict__ sposf, const int* __restrict__ bin_start, Grid g, int nrows, double cut, float band,
+        float in2hi, int reach, int* __restrict__ cnt, int* __restrict__ cnt_in, long long* __restrict__ off,
+        int* __restrict__ idx, int stride) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nrows) return;
-  const double4 pi = xq[i];
+  const int self = SORTED ? rowpos[i] : i;          // the row's own identity in the column index space
+  const double4 pi = SORTED ? spos[self] : xq[i];
   const double c2 = cut * cut;
   const float fx = (float)(pi.x - g.lo[0]), fy = (float)(pi.y - g.lo[1]), fz = (float)(pi.z - g.lo[2]);
   const float c2lo = (float)c2 - band, c2hi = (float)c2 + band;
@@ -149,18 +155,18 @@ k_build(const double4* __restrict__ xq, const double4* __restrict__ spos, const 
         int j = -1;
         if (k < kend) {
           const float4 qj = sposf[k];
-          j = __float_as_int(qj.w);
+          j = SORTED ? k : __float_as_int(qj.w);
           const float ex = qj.x - fx, ey = qj.y - fy, ez = qj.z - fz;
           const float r2f = ex * ex + ey * ey + ez * ez;
           inner = r2f <= in2hi;
-          if (r2f < c2lo) hit = (j != i);
+          if (r2f < c2lo) hit = (j != self);
           else if (r2f <= c2hi) {
             // inside the fp32 rounding band: decide with the exact record.  Explicit rn ops: no FMA contraction, so the
             // r^2 <= cut^2 test is the oracle's arithmetic bit for bit
             const double4 pj = spos[k];
             const double ddx = __dsub_rn(pi.x, pj.x), ddy = __dsub_rn(pi.y, pj.y), ddz = __dsub_rn(pi.z, pj.z);
             const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-            hit = (j != i) && (r2 <= c2);
+            hit = (j != self) && (r2 <= c2);
           }
         }
         const unsigned m_in = __ballot_sync(0xffffffffu, hit && inner), m_out = __ballot_sync(0xffffffffu, hit && !inner);
@@ -277,7 +283,7 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   RXB_CUDA(cudaGetLastError());
 }
 
-void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st) {
+void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st, const int* rowpos) {
   Grid g;
   memcpy(&g, grid_blob, sizeof(g));
   const float band = fp32_band(cut);
@@ -301,8 +307,12 @@ void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Cs
   auto stride_for = [](long long longest) { return (int)(((longest + longest / 16 + 32) + 31) / 32 * 32); };
   long long got[2] = {0, 0};
   if (out.stride == 0 && nrows > 0) {   // first build: one counting pass sizes the stride
-    k_build<false><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach, out.cnt.p, nullptr,
-                                           nullptr, nullptr, 0);
+    if (rowpos)
+      k_build<false, true><<<blocks, 256, 0, st>>>(xq, rowpos, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach,
+                                                   out.cnt.p, nullptr, nullptr, nullptr, 0);
+    else
+      k_build<false, false><<<blocks, 256, 0, st>>>(xq, nullptr, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach,
+                                                    out.cnt.p, nullptr, nullptr, nullptr, 0);
     stats(got);
     out.stride = stride_for(got[0]);
   }
@@ -310,9 +320,12 @@ void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Cs
   for (int attempt = 0; attempt < 4; attempt++) {
     out.slots = (long long)nrows * out.stride;
     out.idx.resize((size_t)std::max<long long>(out.slots, 1));
-    if (nrows > 0)
-      k_build<true><<<blocks, 256, 0, st>>>(xq, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach, out.cnt.p,
-                                            out.cnt_in.p, out.off.p, out.idx.p, out.stride);
+    if (nrows > 0 && rowpos)
+      k_build<true, true><<<blocks, 256, 0, st>>>(xq, rowpos, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach,
+                                                  out.cnt.p, out.cnt_in.p, out.off.p, out.idx.p, out.stride);
+    else if (nrows > 0)
+      k_build<true, false><<<blocks, 256, 0, st>>>(xq, nullptr, spos.p, sposf.p, bin_start.p, g, nrows, cut, band, in2hi, reach,
+                                                   out.cnt.p, out.cnt_in.p, out.off.p, out.idx.p, out.stride);
     stats(got);
     if (got[0] <= out.stride) break;
     out.stride = stride_for(got[0]);     // a row outgrew the stride of the previous build: run the pass again

@@ -9,9 +9,12 @@
 //   K-nb   : vdW_Coulomb_Energy_Full_C                   /root/reference/reaxc_nonbonded_sw64.c:40-258 (serial twin)
 //            full list, local i only, force on i only (no scatter), 1/2 energy per directed pair,
 //            pair virial + (-x_i (x) f_i) correction as reaxc_nonbonded_cpe.h:531-536 / reaxc_nonbonded_sw64.c:247-252.
-// Roofline: K-farH streams 4 B/Verlet entry in and 12 B/far entry out (HBM target) but is bound by the L1 data pipe (a 16-byte
-// gather per candidate, a 32-byte gather per survivor: ncu 78 % busy, DRAM 23 %); K-nb is fp64-issue bound (143 DP
-// instructions per pair: 2 log + 3 exp + cube root + rsqrt + 1 division, all from rxb_math.cuh).  Numbers: DESIGN.md 3.
+// Both kernels work in S space (rxb_dev.cuh): rows are the local atoms in cell-sorted order, columns are sorted positions,
+// so the per-pair gathers (16-byte shadow per candidate, 32-byte record per survivor) fall into runs of consecutive
+// addresses instead of one sector per lane (round 1: L1 data pipe 78 % busy, DRAM 23 %).
+// Roofline: K-farH streams 4 B/Verlet entry in and 8 B (packed) or 12 B (exact) per far entry out (HBM target); K-nb is
+// fp64-issue bound (143 DP instructions per pair: 2 log + 3 exp + cube root + rsqrt + 1 division, all from rxb_math.cuh).
+// Numbers: DESIGN.md 3.
 #include "rxb_math.cuh"
 #include "rxb_system.h"
 
@@ -27,28 +30,44 @@ __device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-struct QeqConst { double Tap[8]; double swb2; double far2; double inner_lim2; };
+struct QeqConst { double Tap[8]; double swb2; double far2; double inner_lim2; double h_quant; };
 
+// Packed H entry: column (22 bits) << 42 | round(H * 2^shift) in 42 bits.  H = Tap(r) * 14.4 / cbrt(r^3 + shld) lies in
+// [0, 14.4 / cbrt(min shld)] for a taper that starts at 0 (Tap in [0,1]); the host picks the shift so that this bound fits, so
+// the absolute quantisation error is 2^-(shift+1) (1.8e-12 for the TATB force field) - relative to the diagonal eta ~ 7
+// that is 3e-13, the size of the cube-root identity already in use, and five orders below the CG tolerance.
+__device__ __forceinline__ unsigned long long h_pack(int col, double val, double quant) {
+  long long m = __double2ll_rn(val * quant);
+  m = m < 0 ? 0 : (m > (long long)kHValMask ? (long long)kHValMask : m);
+  return ((unsigned long long)(unsigned)col << kHColShift) | (unsigned long long)m;
+}
+
+template <bool PACKED>
 __global__ void __launch_bounds__(kWarps * 32)
 k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const AtomPar* __restrict__ atom, double hbond_cut,
         double hbond_r2max, BondedWork W) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   const bool inner_ok = *v.disp2 <= qc.inner_lim2;
-  for (int i = wg; i < v.n; i += nwg) {
-    const double4 pi = v.xq[i];
-    const int ti = v.type[i];
-    const long long beg = v.vl_off[i];
+  const int stride = v.vl_stride;
+  for (int r = wg; r < v.n; r += nwg) {
+    const int kself = v.rowpos[r];
+    const double4 pi = v.xqs[kself];
+    const float4 fi = v.xs[kself];
+    const int ti = __float_as_int(fi.w);
+    const long long beg = (long long)r * stride;
     // pass 1: distance filter + ballot compaction of the column indices (all lanes busy, no transcendental work).
     // The chain index load -> position gather is pure latency, so four chunks of 32 candidates are kept in flight:
-    // all index loads are issued first, then all gathers, then the tests.  Row-relative 32-bit offsets throughout.
+    // all index loads are issued first, then all gathers, then the tests.  Columns are sorted positions: the candidates of
+    // a row are runs of consecutive integers, so the 32 shadow gathers of a chunk fall into a handful of 128-byte lines.
     const int* __restrict__ vl = v.vl_idx + beg;
-    int* __restrict__ far = v.far_idx + beg;
+    // compacted columns: exact format -> far_idx row; packed format -> the upper half of the row's own 64-bit slots (read
+    // back by pass 2 before the packed words, written from the bottom, reach them: see pass 2)
+    int* far = PACKED ? reinterpret_cast<int*>(v.hpk + beg) + stride : v.far_idx + beg;   // (aliases hpk: no __restrict__)
     // adaptive inner skin: while no atom has moved more than half the margin since the build, every pair inside the far
     // cut-off is in the inner block of its row
-    const int cnt_i = inner_ok ? v.vl_cnt_in[i] : v.vl_cnt[i];
+    const int cnt_i = inner_ok ? v.vl_cnt_in[r] : v.vl_cnt[r];
     int w = 0;
-    const float4 fi = v.xf[i];
     const float lo2 = (float)qc.far2 - v.far_band, hi2 = (float)qc.far2 + v.far_band;
     const unsigned lt_mask = (1u << lane) - 1;
     constexpr int kU = 4;
@@ -61,7 +80,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
         jj[u] = k < cnt_i ? __ldcs(vl + k) : -1;
       }
 #pragma unroll
-      for (int u = 0; u < kU; u++) fj[u] = jj[u] >= 0 ? v.xf[jj[u]] : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+      for (int u = 0; u < kU; u++) fj[u] = jj[u] >= 0 ? v.xs[jj[u]] : make_float4(1e18f, 1e18f, 1e18f, 0.f);
 #pragma unroll
       for (int u = 0; u < kU; u++) {
         // 16-byte fp32 shadow first; only distances inside the rounding band load the exact 32-byte record, so the
@@ -70,7 +89,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
         const float r2f = ex * ex + ey * ey + ez * ez;
         bool hit = r2f < lo2;
         if (!hit && r2f <= hi2) {
-          const double4 pj = v.xq[jj[u]];
+          const double4 pj = v.xqs[jj[u]];
           hit = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z) <= qc.far2;
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -79,13 +98,16 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
       }
     }
     const int num = w;
-    if (lane == 0) v.far_num[i] = num;
+    if (lane == 0) v.far_num[r] = num;
     __syncwarp();
-    // pass 2: H values on the compacted row (every lane does the taper + cube root; xq[j] is an L1/L2 hit).
+    // pass 2: H values on the compacted row (every lane does the taper + cube root; xqs[j] is an L1/L2 hit).
     // Rows of hydrogen atoms also emit their hydrogen-bond partner candidates here (acceptor-type j within hbond_cut:
     // Init_Forces_noQEq_HB_Full_C, reaxc_forces_sw64.c:787-863) while x_j, type_j and r are in registers.
+    // Packed format: word k of the row overwrites the int slots 2k, 2k+1, i.e. compacted columns 2k - stride and
+    // 2k + 1 - stride <= k: columns of this or an earlier chunk, all of which are in registers by then (the __syncwarp
+    // orders the chunk's loads before its stores).
     const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
-    double* __restrict__ hv = v.H_val + beg;
+    const int i_atom = is_H ? v.row_atom[r] : 0;
     constexpr int kV = 2;
     for (int k0 = 0; k0 < num; k0 += 32 * kV) {
       int jj[kV];
@@ -96,10 +118,11 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
         const int k = k0 + 32 * u + lane;
         jj[u] = k < num ? far[k] : -1;
       }
+      if (PACKED) __syncwarp();
 #pragma unroll
       for (int u = 0; u < kV; u++) {
-        pjv[u] = jj[u] >= 0 ? v.xq[jj[u]] : make_double4(0, 0, 0, 0);
-        tjv[u] = jj[u] >= 0 ? v.type[jj[u]] : -1;
+        pjv[u] = jj[u] >= 0 ? v.xqs[jj[u]] : make_double4(0, 0, 0, 0);
+        tjv[u] = jj[u] >= 0 ? v.type_s[jj[u]] : -1;
       }
 #pragma unroll
       for (int u = 0; u < kV; u++) {
@@ -112,9 +135,10 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
           const int tj = tjv[u];
           double val = 0.0;
           if (ti >= 0 && tj >= 0) {
-            // r to 1 ulp from rsqrt, the 7-op cube root of rxb_math.cuh, and the hydrogen-bond reach tested on r^2
-            // against the largest r^2 whose correctly rounded root is <= hbond_cut (the same decision as sqrt(r2) <= cut)
-            const double r = r2 * rsqrt(r2);
+            // r to 1 ulp from rsqrt (coincident atoms: r = 0 as sqrt gives, not NaN), the 7-op cube root of rxb_math.cuh,
+            // and the hydrogen-bond reach tested on r^2 against the largest r^2 whose correctly rounded root is
+            // <= hbond_cut (the same decision as sqrt(r2) <= cut)
+            const double r = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;
             if (r2 <= qc.swb2) {
               double T = qc.Tap[7] * r + qc.Tap[6];
               T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
@@ -125,7 +149,8 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
             }
             cand = is_H && atom[tj].p_hbond == 2 && r2 <= hbond_r2max;
           }
-          hv[k] = val;
+          if (PACKED) v.hpk[beg + k] = h_pack(j, val, qc.h_quant);
+          else v.H_val[beg + k] = val;
         }
         if (is_H) {
           const unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -135,7 +160,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
             base = __shfl_sync(0xffffffffu, base, 0);
             if (cand) {
               const int o = base + __popc(m & ((1u << lane) - 1));
-              if (o < W.cap_hb) W.hb[o] = make_int4(i, j, 0, 0);
+              if (o < W.cap_hb) W.hb[o] = make_int4(i_atom, v.s2a[j], 0, 0);
             }
           }
         }
@@ -156,7 +181,15 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
 constexpr int kNbPar = 12;  // D, alpha, inv_r_vdW, powgi | alpha_over_r_vdW, gamma, r_vdW, rcore | ecore, acore, lgcij, lgre
 constexpr int kNbThreads = 256, kNbCtas = 2, kNbWarps = kNbThreads / 32;
 
-template <bool EV>
+// column of far-list entry k of a row (packed: the top 22 bits of the 64-bit word)
+template <bool PACKED>
+__device__ __forceinline__ int far_col(const DevView& v, long long beg, int k) {
+  // streamed once per sweep: evict-first, so the column stream does not push the gathered positions out of L1
+  if (PACKED) return (int)(__ldcs(v.hpk + beg + k) >> kHColShift);
+  return __ldcs(v.far_idx + beg + k);
+}
+
+template <bool EV, bool PACKED>
 __global__ void __launch_bounds__(kNbThreads, kNbCtas)
 k_nonbonded(DevView v, DevParams P) {
   extern __shared__ __align__(128) double nb_smem[];
@@ -182,24 +215,25 @@ k_nonbonded(DevView v, DevParams P) {
 #pragma unroll
   for (int t = 0; t < 8; t++) Tap[t] = P.ctl.Tap[t];
   double e_vdw = 0, e_ele = 0, e_pol = 0, vir[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = wg; i < v.n; i += nwg) {
-    const int ti = v.type[i];
+  const int stride = v.vl_stride;
+  for (int i = wg; i < v.n; i += nwg) {      // i = row (the i-th local atom in sorted order)
+    const int kself = v.rowpos[i];
+    const int ti = v.type_s[kself];
     if (ti < 0) continue;
-    const double4 pi = v.xq[i];
-    const long long beg = v.vl_off[i];
+    const double4 pi = v.xqs[kself];
+    const long long beg = (long long)i * stride;
     const int num = v.far_num[i];
     double fx = 0, fy = 0, fz = 0;
-    const int* __restrict__ cols = v.far_idx + beg;
-    int j_cur = lane < num ? cols[lane] : -1;
-    int j_nxt = 32 + lane < num ? cols[32 + lane] : -1;
+    int j_cur = lane < num ? far_col<PACKED>(v, beg, lane) : -1;
+    int j_nxt = 32 + lane < num ? far_col<PACKED>(v, beg, 32 + lane) : -1;
     double4 p_cur = make_double4(0, 0, 0, 0);
     int t_cur = -1;
-    if (j_cur >= 0) { p_cur = v.xq[j_cur]; t_cur = v.type[j_cur]; }
+    if (j_cur >= 0) { p_cur = v.xqs[j_cur]; t_cur = v.type_s[j_cur]; }
     for (int k0 = 0; k0 < num; k0 += 32) {
-      const int j_nn = k0 + 64 + lane < num ? cols[k0 + 64 + lane] : -1;
+      const int j_nn = k0 + 64 + lane < num ? far_col<PACKED>(v, beg, k0 + 64 + lane) : -1;
       double4 p_nxt = make_double4(0, 0, 0, 0);
       int t_nxt = -1;
-      if (j_nxt >= 0) { p_nxt = v.xq[j_nxt]; t_nxt = v.type[j_nxt]; }
+      if (j_nxt >= 0) { p_nxt = v.xqs[j_nxt]; t_nxt = v.type_s[j_nxt]; }
       const int tj = t_cur;
       const double4 pj = p_cur;
       j_cur = j_nxt; p_cur = p_nxt; t_cur = t_nxt; j_nxt = j_nn;
@@ -207,7 +241,7 @@ k_nonbonded(DevView v, DevParams P) {
       const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
       const double r2 = dist2_rn(dx, dy, dz);
       if (!(r2 <= nonb_cut2)) continue;
-      const double rinv = rsqrt(r2);
+      const double rinv = r2 > 0.0 ? rsqrt(r2) : 0.0;   // coincident atoms: r = 0 like sqrt, not NaN
       const double r_ij = r2 * rinv;
       const double2* w = pt + (ti * nt + tj) * (kNbPar / 2);
       double T = Tap[7] * r_ij + Tap[6];
@@ -269,9 +303,10 @@ k_nonbonded(DevView v, DevParams P) {
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
-      // only writer of f[i] so far in the step for local i would be a plain store, but bonded kernels may run
+      // only writer of f[atom] so far in the step for a local atom would be a plain store, but bonded kernels may run
       // concurrently on another stream: keep it an atomic
-      atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
+      const int ia = v.row_atom[i];
+      atomicAdd(&v.f[3 * ia], fx); atomicAdd(&v.f[3 * ia + 1], fy); atomicAdd(&v.f[3 * ia + 2], fz);
       if (EV) {
         // polarisation energy (reaxc_multi_body_sw64.c:100-103, plain sum) lives here because it needs this step's q
         e_pol += kKcalToEv * (P.atom[ti].chi * pi.w + (P.atom[ti].eta / 2.) * pi.w * pi.w);
@@ -312,7 +347,7 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-template <bool EV>
+template <bool EV, bool PACKED>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 k_nonbonded_tab(DevView v, DevParams P) {
   __shared__ double sh[9][kWarps];
@@ -322,20 +357,22 @@ k_nonbonded_tab(DevView v, DevParams P) {
   const int nt = P.nt, ln = P.lut_n;
   const double dx = P.lut_dx, inv_dx = P.lut_inv_dx;
   double e_vdw = 0, e_ele = 0, e_pol = 0, vir[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = wg; i < v.n; i += nwg) {
-    const int ti = v.type[i];
+  const int stride = v.vl_stride;
+  for (int i = wg; i < v.n; i += nwg) {      // i = row
+    const int kself = v.rowpos[i];
+    const int ti = v.type_s[kself];
     if (ti < 0) continue;
-    const double4 pi = v.xq[i];
-    const long long beg = v.vl_off[i];
+    const double4 pi = v.xqs[kself];
+    const long long beg = (long long)i * stride;
     const int num = v.far_num[i];
     double fx = 0, fy = 0, fz = 0;
     for (int k0 = 0; k0 < num; k0 += 32) {
       const int k = k0 + lane;
       if (k >= num) continue;
-      const int j = v.far_idx[beg + k];
-      const int tj = v.type[j];
+      const int j = far_col<PACKED>(v, beg, k);
+      const int tj = v.type_s[j];
       if (tj < 0) continue;
-      const double4 pj = v.xq[j];
+      const double4 pj = v.xqs[j];
       const double dx_ = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
       const double r2 = dist2_rn(dx_, dy, dz);
       if (!(r2 <= nonb_cut2)) continue;
@@ -361,7 +398,8 @@ k_nonbonded_tab(DevView v, DevParams P) {
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
-      atomicAdd(&v.f[3 * i], fx); atomicAdd(&v.f[3 * i + 1], fy); atomicAdd(&v.f[3 * i + 2], fz);
+      const int ia = v.row_atom[i];
+      atomicAdd(&v.f[3 * ia], fx); atomicAdd(&v.f[3 * ia + 1], fy); atomicAdd(&v.f[3 * ia + 2], fz);
       if (EV) {
         e_pol += kKcalToEv * (P.atom[ti].chi * pi.w + (P.atom[ti].eta / 2.) * pi.w * pi.w);
         vir[0] -= pi.x * fx; vir[1] -= pi.y * fy; vir[2] -= pi.z * fz;
@@ -404,6 +442,7 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   // far + 2 max|dx| then: usable while max|dx| <= (vl_cut_in - far) / 2 (0.1 % slack for the roundings)
   const double margin = v.vl_cut_in - far;
   qc.inner_lim2 = (v.vl_cut_in > 0.0 && margin > 0.0) ? 0.25 * 0.998 * margin * margin : -1.0;
+  qc.h_quant = v.h_quant;
   BondedWork W = s.bonded_work();
   RXB_CUDA(cudaMemsetAsync(W.n_hb, 0, sizeof(int), st));
   // largest r^2 with sqrt(r^2) <= hbond_cut in round-to-nearest
@@ -413,21 +452,24 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   while (hb2 > 0.0 && std::sqrt(hb2) > hc) hb2 = std::nextafter(hb2, 0.0);
   // rows are dealt round-robin to the warps of a grid that is a whole number of waves of resident CTAs (measured:
   // 1 / 2 / 4 waves 0.997 / 0.985 / 0.977 ms; the former fixed 1184 CTAs were 1.6 waves at this register count: 1.12 ms)
-  static int occ = 0;
-  k_far_H<<<wave_grid(k_far_H, kWarps * 32, 4, occ), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  static int occ_p = 0, occ_e = 0;
+  if (v.hpk) k_far_H<true><<<wave_grid(k_far_H<true>, kWarps * 32, 4, occ_p), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  else k_far_H<false><<<wave_grid(k_far_H<false>, kWarps * 32, 4, occ_e), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
   s.kernel_launches++;
 }
 
 void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st) {
   if (v.n == 0) return;
   if (P.lut) {   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables (reaxc_forces_sunway.cpp:148-160)
-    static int occ_t = 0, occ_f = 0;
-    if (evflag) k_nonbonded_tab<true><<<wave_grid(k_nonbonded_tab<true>, kWarps * 32, 2, occ_t), kWarps * 32, 0, st>>>(v, P);
-    else k_nonbonded_tab<false><<<wave_grid(k_nonbonded_tab<false>, kWarps * 32, 2, occ_f), kWarps * 32, 0, st>>>(v, P);
+    static int occ[4] = {0, 0, 0, 0};
+    auto kt = v.hpk ? (evflag ? k_nonbonded_tab<true, true> : k_nonbonded_tab<false, true>)
+                    : (evflag ? k_nonbonded_tab<true, false> : k_nonbonded_tab<false, false>);
+    kt<<<wave_grid(kt, kWarps * 32, 2, occ[(v.hpk ? 2 : 0) + (evflag ? 1 : 0)]), kWarps * 32, 0, st>>>(v, P);
   } else {
     // math tables + block reduction scratch + 12 constants per type pair (96 B x nt^2: 4 types 1.5 KB, 40 types 154 KB)
     const size_t smem = sizeof(double) * (fm::kTabDoubles + 9 * kNbWarps + (size_t)P.nt * P.nt * kNbPar);
-    auto kern = evflag ? k_nonbonded<true> : k_nonbonded<false>;
+    auto kern = v.hpk ? (evflag ? k_nonbonded<true, true> : k_nonbonded<false, true>)
+                      : (evflag ? k_nonbonded<true, false> : k_nonbonded<false, false>);
     if (smem > 48 * 1024) RXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<148 * kNbCtas * 4, kNbThreads, smem, st>>>(v, P);
   }

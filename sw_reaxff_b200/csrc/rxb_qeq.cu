@@ -7,26 +7,22 @@
 //   CG_v2 :983-1167 (Ghysels-Vanroose pipelined PCG, one reduction per iteration, imax = 200, test on sqrt(u.r)/|b|),
 //   calculate_Q :1697-1755 (q = s - (sum s / sum t) t, 5-deep history).
 // Each right-hand side keeps its own alpha/beta/eta and its own convergence flag ON THE DEVICE, so the fused solve
-// performs exactly the iterations the reference's two sequential solves would (same matvec counts), and the host
-// only polls a flag every few iterations.  The per-iteration vector work of the reference (two sweeps + a serial
-// MPE sweep overlapped with the SpMV) is one fused sweep here.
-// Roofline: SpMV is HBM-bound: 12 B per stored H entry + 16 B per gathered x (L2-resident).
+// performs exactly the iterations the reference's two sequential solves would (same matvec counts).  The per-iteration
+// vector work of the reference (two sweeps + a serial MPE sweep overlapped with the SpMV) is one fused sweep here.
+//
+// Index spaces (rxb_dev.cuh): the solve runs in S space.  Row vectors (r, u, w, p, ...) are indexed by row = local atom in
+// cell-sorted order; the two gathered vectors (the initial guess and the search direction d) are indexed by sorted
+// position over all atoms, so the SpMV's x[col] gathers walk runs of consecutive 16-byte elements.
+// H entries are 8 bytes (22-bit column + 42-bit fixed-point value in one word, rxb_nonbonded.cu) or 12 bytes (exact).
+// Host involvement: none inside the solve.  The host launches as many iterations as the previous step needed (+ margin;
+// converged iterations are gated off on the device and cost ~2 us each), and the convergence state is read with the
+// end-of-step status; only an under-prediction (rare) continues the solve and replays the force phase.
+// Roofline: the SpMV is HBM-bound: bytes per stored H entry + 16 B per gathered x (L1/L2-resident).
 #include <algorithm>
 
 #include "rxb_system.h"
 
 namespace rxb {
-
-struct QeqState {       // device-resident CG scalars, double-buffered by iteration parity
-  double alpha[2], heta[2], sig_old[2], b_norm[2], dot0[2];
-  int active[2], iters[2];
-};
-struct QeqDev {
-  QeqState st[2];
-  double dots[3][4];    // rotating accumulators: (u.r)_s, (u.r)_t, (u.w)_s, (u.w)_t
-  double pro[6];        // prologue: b.b, u.r, u.w for s and t
-  double sums[2];       // sum s, sum t
-};
 
 namespace {
 
@@ -34,20 +30,24 @@ constexpr int kWarps = 8;
 constexpr int kVecBlocks = 148 * 4;
 constexpr int kVecThreads = 256;
 
-__device__ __forceinline__ double2 operator*(double a, double2 b) { return make_double2(a * b.x, a * b.y); }
-
-__global__ void k_qeq_init(int n, const int* __restrict__ type, const AtomPar* __restrict__ atom,
-                           const double* __restrict__ s_hist, const double* __restrict__ t_hist, double2* __restrict__ x,
-                           double2* __restrict__ b, double* __restrict__ Hdia_inv, QeqDev* __restrict__ Q) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int ti = type[i];
+__global__ void k_qeq_init(int n, const int* __restrict__ rowpos, const int* __restrict__ row_atom,
+                           const int* __restrict__ type_s, const AtomPar* __restrict__ atom,
+                           const double* __restrict__ s_hist, const double* __restrict__ t_hist, double2* __restrict__ x_row,
+                           double2* __restrict__ xS, double2* __restrict__ b, double* __restrict__ Hdia_inv,
+                           double* __restrict__ eta_row, QeqDev* __restrict__ Q) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int k = rowpos[j], i = row_atom[j];
+    const int ti = type_s[k];
     double eta = 1.0, chi = 0.0;
     if (ti >= 0) { eta = atom[ti].eta; chi = atom[ti].chi; }
-    Hdia_inv[i] = 1. / eta;
-    b[i] = make_double2(-chi, -1.0);
+    Hdia_inv[j] = 1. / eta;
+    eta_row[j] = ti >= 0 ? eta : 0.0;
+    b[j] = make_double2(-chi, -1.0);
     const double* sh = s_hist + 5 * (size_t)i;
     const double* th = t_hist + 5 * (size_t)i;
-    x[i] = make_double2(4 * (sh[0] + sh[2]) - (6 * sh[1] + sh[3]), th[2] + 3 * (th[0] - th[1]));
+    const double2 x0 = make_double2(4 * (sh[0] + sh[2]) - (6 * sh[1] + sh[3]), th[2] + 3 * (th[0] - th[1]));
+    x_row[j] = x0;
+    xS[k] = x0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int k = 0; k < 3; k++) for (int c = 0; c < 4; c++) Q->dots[k][c] = 0.0;
@@ -56,57 +56,73 @@ __global__ void k_qeq_init(int n, const int* __restrict__ type, const AtomPar* _
   }
 }
 
-__global__ void k_forward2(int n, int N, const int* __restrict__ owner, double2* __restrict__ vec) {
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N - n; g += gridDim.x * blockDim.x) {
-    const int o = owner[g];
-    if (o >= 0) vec[n + g] = vec[o];
+// periodic-image ghosts of an S-space vector <- their owners (single-rank forward_comm_fix)
+__global__ void k_forward2S(int nghost, const int* __restrict__ gs_pos, const int* __restrict__ gs_own, double2* __restrict__ vec) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nghost; g += gridDim.x * blockDim.x) {
+    const int o = gs_own[g];
+    if (o >= 0) vec[gs_pos[g]] = vec[o];
   }
 }
 
-// y[i] = eta_i x_i + sum_j H_ij x_j for local rows; gate != null: skip when neither system is active
+// y[row] = eta x[rowpos[row]] + sum_k H_k x[col_k] for the local rows; gate != null: skip when neither system is active
+template <bool PACKED>
 __global__ void __launch_bounds__(kWarps * 32)
-k_spmv2(int n, const long long* __restrict__ off, const int* __restrict__ num, const int* __restrict__ col,
-        const double* __restrict__ val, const int* __restrict__ type, const AtomPar* __restrict__ atom,
+k_spmv2(int n, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk, const int* __restrict__ col,
+        const double* __restrict__ val, double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row,
         const double2* __restrict__ x, double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
   if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int i = wg; i < n; i += nwg) {
-    const long long beg = off[i];
+    const long long beg = (long long)i * stride;
     const int m = num[i];
     double ax = 0, ay = 0;
-    for (int k = lane; k < m; k += 32) {
-      // H is streamed exactly once per SpMV: evict-first loads keep the gathered x vector (16 B/atom) resident in L2/L1
-      const double h = __ldcs(val + beg + k);
-      const double2 xj = __ldg(x + __ldcs(col + beg + k));
-      ax += h * xj.x; ay += h * xj.y;
+    if (PACKED) {
+      // H is streamed exactly once per SpMV (evict-first), 8 bytes per entry: the column is the top 22 bits, the value the
+      // low 42 as an integer multiple of 1 / quant.  The integer becomes a double without a conversion instruction:
+      // OR it into the mantissa of 2^52 and subtract 2^52 (exact); the row sum is scaled by 1 / quant once at the end.
+      const unsigned long long* __restrict__ hp = hpk + beg;
+#pragma unroll 4
+      for (int k = lane; k < m; k += 32) {
+        const unsigned long long w = __ldcs(hp + k);
+        const double h = __longlong_as_double((long long)((w & kHValMask) | 0x4330000000000000ULL)) - 4503599627370496.0;
+        const double2 xj = __ldg(x + (int)(w >> kHColShift));
+        ax += h * xj.x; ay += h * xj.y;
+      }
+      ax *= inv_quant; ay *= inv_quant;
+    } else {
+#pragma unroll 4
+      for (int k = lane; k < m; k += 32) {
+        const double h = __ldcs(val + beg + k);
+        const double2 xj = __ldg(x + __ldcs(col + beg + k));
+        ax += h * xj.x; ay += h * xj.y;
+      }
     }
     ax = warp_sum(ax); ay = warp_sum(ay);
     if (lane == 0) {
-      const int ti = type[i];
-      const double eta = ti >= 0 ? atom[ti].eta : 0.0;
-      const double2 xi = x[i];
+      const double eta = eta_row[i];
+      const double2 xi = x[rowpos[i]];
       y[i] = make_double2(eta * xi.x + ax, eta * xi.y + ay);
     }
   }
 }
 
 // prologue steps (fix_qeq_reax_sunway.cpp:1024-1105)
-__global__ void k_pro1(int n, const double2* __restrict__ b, const double2* __restrict__ q, const double* __restrict__ Hd,
-                       double2* __restrict__ r, double2* __restrict__ u, double2* __restrict__ d) {
+__global__ void k_pro1(int n, const int* __restrict__ rowpos, const double2* __restrict__ b, const double2* __restrict__ q,
+                       const double* __restrict__ Hd, double2* __restrict__ r, double2* __restrict__ u, double2* __restrict__ dS) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const double2 bj = b[j], qj = q[j];
     const double2 rj = make_double2(bj.x - 1 * qj.x, bj.y - 1 * qj.y);
     const double2 uj = make_double2(rj.x * Hd[j], rj.y * Hd[j]);
-    r[j] = rj; u[j] = uj; d[j] = uj;
+    r[j] = rj; u[j] = uj; dS[rowpos[j]] = uj;
   }
 }
-__global__ void k_pro2(int n, const double2* __restrict__ q, const double* __restrict__ Hd, double2* __restrict__ w,
-                       double2* __restrict__ m, double2* __restrict__ d) {
+__global__ void k_pro2(int n, const int* __restrict__ rowpos, const double2* __restrict__ q, const double* __restrict__ Hd,
+                       double2* __restrict__ w, double2* __restrict__ m, double2* __restrict__ dS) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const double2 qj = q[j];
     const double2 mj = make_double2(qj.x * Hd[j], qj.y * Hd[j]);
-    w[j] = qj; m[j] = mj; d[j] = mj;
+    w[j] = qj; m[j] = mj; dS[rowpos[j]] = mj;
   }
 }
 
@@ -158,11 +174,12 @@ __global__ void k_scal_init(QeqDev* Q, double tol, int imax) {
 
 // Fused sweep for loop index `it` (>= 1):  [B_{it-1}: x,p,ss,v,z update with the SpMV result]  then
 // [A_it: r,u,w update, the two dot products, d = M^-1 w].  `first` skips the B part (it == 1).
+// d lives in S space (dS[rowpos[j]]); everything else is a row vector.
 __global__ void __launch_bounds__(kVecThreads)
-k_cg_sweep(int n, int it, int first, double tol, int imax, const double* __restrict__ Hd, const double2* __restrict__ q,
-           double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ u, double2* __restrict__ w,
-           double2* __restrict__ p, double2* __restrict__ ss, double2* __restrict__ v, double2* __restrict__ z,
-           double2* __restrict__ d, QeqDev* __restrict__ Q) {
+k_cg_sweep(int n, int it, int first, double tol, int imax, const int* __restrict__ rowpos, const double* __restrict__ Hd,
+           const double2* __restrict__ q, double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ u,
+           double2* __restrict__ w, double2* __restrict__ p, double2* __restrict__ ss, double2* __restrict__ v,
+           double2* __restrict__ z, double2* __restrict__ dS, QeqDev* __restrict__ Q) {
   const int par = it & 1;
   const QeqState S = Q->st[par];
   QeqState T = S;  // state after the B part; identical in every thread
@@ -188,7 +205,8 @@ k_cg_sweep(int n, int it, int first, double tol, int imax, const double* __restr
   double acc[4] = {0, 0, 0, 0};
   if (doB[0] | doB[1] | actA0 | actA1)
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-      double2 xj = x[j], rj = r[j], uj = u[j], wj = w[j], pj = p[j], sj = ss[j], vj = v[j], zj = z[j], dj = d[j];
+      const int kj = rowpos[j];
+      double2 xj = x[j], rj = r[j], uj = u[j], wj = w[j], pj = p[j], sj = ss[j], vj = v[j], zj = z[j], dj = dS[kj];
       if (doB[0] | doB[1]) {
         const double2 qj = q[j];
         if (doB[0]) {
@@ -215,7 +233,7 @@ k_cg_sweep(int n, int it, int first, double tol, int imax, const double* __restr
           acc[1] += uj.y * rj.y; acc[3] += uj.y * wj.y;
           dj.y = wj.y * hd;
         }
-        r[j] = rj; u[j] = uj; w[j] = wj; d[j] = dj;
+        r[j] = rj; u[j] = uj; w[j] = wj; dS[kj] = dj;
       }
     }
   if (actA0 | actA1) block_reduce_add<4>(acc, Q->dots[(it + 1) % 3]);
@@ -236,17 +254,20 @@ k_q_sums(int n, const double2* __restrict__ x, QeqDev* __restrict__ Q) {
   block_reduce_add<2>(acc, Q->sums);
 }
 
-__global__ void k_q_final(int n, int N, const int* __restrict__ owner, const double2* __restrict__ x,
-                          const QeqDev* __restrict__ Q, double* __restrict__ s_hist, double* __restrict__ t_hist,
-                          double4* __restrict__ xq, int phase) {
+// phase 0: q of the local atoms + history (shift = 0: the solve was continued after the history had already been shifted
+// for this step, only slot 0 is overwritten); phase 1: ghost charges <- owners (single rank)
+__global__ void k_q_final(int n, int N, const int* __restrict__ row_atom, const int* __restrict__ owner,
+                          const double2* __restrict__ x, const QeqDev* __restrict__ Q, double* __restrict__ s_hist,
+                          double* __restrict__ t_hist, double4* __restrict__ xq, int phase, int shift) {
   if (phase == 0) {
     const double uu = Q->sums[0] / Q->sums[1];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const double2 xi = x[i];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+      const int i = row_atom[j];
+      const double2 xi = x[j];
       xq[i].w = xi.x - uu * xi.y;
       double* sh = s_hist + 5 * (size_t)i;
       double* th = t_hist + 5 * (size_t)i;
-      for (int k = 4; k > 0; --k) { sh[k] = sh[k - 1]; th[k] = th[k - 1]; }
+      if (shift) for (int k = 4; k > 0; --k) { sh[k] = sh[k - 1]; th[k] = th[k - 1]; }
       sh[0] = xi.x; th[0] = xi.y;
     }
   } else {
@@ -256,6 +277,12 @@ __global__ void k_q_final(int n, int N, const int* __restrict__ owner, const dou
     }
   }
 }
+
+__global__ void k_q_to_S(int N, const int* __restrict__ s2a, const double4* __restrict__ xq, double4* __restrict__ xqs) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) xqs[k].w = xq[s2a[k]].w;
+}
+
+__global__ void k_zero2(double* p) { if (threadIdx.x == 0) { p[0] = 0.0; p[1] = 0.0; } }
 
 }  // namespace
 
@@ -277,10 +304,87 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
   RXB_CUDA(cudaStreamSynchronize(st_));
 }
 
-void System::qeq_pre_force() {
+// one CG iteration of loop index `it`: fused sweep, halo of d (+ the dot products in multi-GPU runs), gated SpMV
+void System::qeq_iteration(int it) {
+  QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
+  k_cg_sweep<<<kVecBlocks, kVecThreads, 0, st_>>>(n, it, it == 1, qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p, q_x.p, q_r.p,
+                                                 q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
+  kernel_launches++;
+  const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
+  // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange
+  if (dist_) dist_forward2_dots(q_d.p, Q->dots[(it + 1) % 3]);
+  else qeq_forward_S(q_d.p);
+  qeq_spmv(q_d.p, q_q.p, true, par_next);
+}
+
+void System::qeq_forward_S(double2* vecS) {
+  if (dist_) { dist_forward2(vecS); return; }
+  const int nghost = N - n;
+  if (nghost > 0) {
+    k_forward2S<<<std::min(148 * 8, (nghost + 255) / 256), 256, 0, st_>>>(nghost, gs_pos.p, gs_own.p, vecS);
+    kernel_launches++;
+  }
+}
+
+void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity) {
+  const QeqDev* Q = reinterpret_cast<const QeqDev*>(q_scal.p);
+  const int ts = tick(StepTimers::SPMV);
+  // one row per warp, blocks retire continuously: lets the high-priority bond-chain stream interleave on every SM
+  const int grid = std::max(1, (n + kWarps - 1) / kWarps);
+  // RXB_SPMV_SMEM=<bytes> (development knob): an unused dynamic shared-memory request per CTA caps the CTAs resident per SM,
+  // i.e. how many warp slots the SpMV leaves to the bonded chain running beside it on the second stream
+  static const int smem = [] {
+    const char* e = getenv("RXB_SPMV_SMEM");
+    const int b = e ? atoi(e) : 0;
+    if (b > 48 * 1024) {
+      cudaFuncSetAttribute(k_spmv2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+      cudaFuncSetAttribute(k_spmv2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    }
+    return b;
+  }();
+  if (h_packed_)
+    k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(n, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_, rowpos.p,
+                                                    q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+  else
+    k_spmv2<false><<<grid, kWarps * 32, smem, st_>>>(n, vl.stride, far_num.p, nullptr, far_idx.p, H_val.p, 1.0, rowpos.p,
+                                                     q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+  tock(ts);
+  kernel_launches++;
+}
+
+// final charges from the current x (calculate_Q); shift_hist = false when this step's history slot was already opened
+void System::qeq_finish(bool shift_hist) {
+  QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
+  const int nghost = N - n;
+  k_zero2<<<1, 32, 0, st_>>>(Q->sums);
+  k_q_sums<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_x.p, Q);
+  if (dist_) dist_allreduce(Q->sums, 2);
+  k_q_final<<<kVecBlocks, kVecThreads, 0, st_>>>(n, N, row_atom.p, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 0,
+                                                shift_hist ? 1 : 0);
+  if (dist_) dist_forward_xq();
+  else if (nghost > 0)
+    k_q_final<<<std::min(148 * 8, (nghost + 255) / 256), 256, 0, st_>>>(n, N, row_atom.p, ghost_owner.p, q_x.p, Q, q_s_hist.p,
+                                                                     q_t_hist.p, xq.p, 1, 0);
+  k_q_to_S<<<kVecBlocks, kVecThreads, 0, st_>>>(N, s2a.p, xq.p, xqs.p);
+  kernel_launches += 5;
+}
+
+// Reads the convergence state written by the last launched sweep.  Returns true when both solves have stopped.
+bool System::qeq_poll() {
+  QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
+  const int par_next = (qeq_it_ & 1) ^ 1;
+  int host[4];
+  RXB_CUDA(cudaMemcpyAsync(host, Q->st[par_next].active, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));   // active[2], iters[2]
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  matvecs_s = host[2]; matvecs_t = host[3];
+  return !(host[0] | host[1]);
+}
+
+void System::qeq_pre_force(bool wait_for_convergence) {
   if (n == 0) return;
   if (q_s_hist.n != (size_t)5 * n && !dist_) qeq_reset_history();
   last_swb_ = qeq_swb;
+  choose_h_format();                    // (taper start / exact request may have changed since the build)
   DevView v = view();
   update_shadow(st_);
   // taper and shielding of the fix (init_taper :458-484, init_shielding :440-454), host side, tiny
@@ -304,73 +408,71 @@ void System::qeq_pre_force() {
   after_far_hook();
 
   const int t_QEQ_CG = tick(StepTimers::QEQ_CG);
-  const size_t nn = n, NN = std::max((size_t)N, slab());  // all-gathered arrays must hold a whole slab
-  q_x.resize(NN); q_d.resize(NN);
-  q_r.resize(nn); q_u.resize(nn); q_w.resize(nn); q_p.resize(nn); q_ss.resize(nn); q_v.resize(nn); q_z.resize(nn);
-  q_q.resize(nn); q_b.resize(nn); q_m.resize(nn); q_Hdia_inv.resize(nn);
+  const size_t nn = n, NN = std::max((size_t)N, slab());
+  q_xS.resize(NN); q_d.resize(NN);
+  q_x.resize(nn); q_r.resize(nn); q_u.resize(nn); q_w.resize(nn); q_p.resize(nn); q_ss.resize(nn); q_v.resize(nn); q_z.resize(nn);
+  q_q.resize(nn); q_b.resize(nn); q_m.resize(nn); q_Hdia_inv.resize(nn); q_eta.resize(nn);
   q_scal.resize(sizeof(QeqDev) / sizeof(double) + 8);
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
-  const int nghost = N - n;
-  const int fb = nghost > 0 ? (nghost + 255) / 256 : 0;
-  auto forward = [&](double2* vec) {
-    if (dist_) dist_forward2(vec);
-    else if (fb) { k_forward2<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, vec); kernel_launches++; }
-  };
-  auto spmv = [&](const double2* x, double2* y, const QeqDev* gate, int parity) {
-    const int ts = tick(StepTimers::SPMV);
-    // one row per warp, blocks retire continuously: lets the high-priority bond-chain stream interleave on every SM
-    k_spmv2<<<std::max(1, (n + kWarps - 1) / kWarps), kWarps * 32, 0, st_>>>(n, vl.off.p, far_num.p, far_idx.p, H_val.p, type.p, dp_.atom, x, y, gate, parity);
-    tock(ts);
-    kernel_launches++;
-  };
-  k_qeq_init<<<kVecBlocks, kVecThreads, 0, st_>>>(n, type.p, dp_.atom, q_s_hist.p, q_t_hist.p, q_x.p, q_b.p, q_Hdia_inv.p, Q);
-  forward(q_x.p);
-  spmv(q_x.p, q_q.p, nullptr, 0);
-  k_pro1<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_b.p, q_q.p, q_Hdia_inv.p, q_r.p, q_u.p, q_d.p);
-  forward(q_d.p);
-  spmv(q_d.p, q_q.p, nullptr, 0);
-  k_pro2<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_q.p, q_Hdia_inv.p, q_w.p, q_m.p, q_d.p);
-  forward(q_d.p);
-  spmv(q_d.p, q_q.p, nullptr, 0);
+  k_qeq_init<<<kVecBlocks, kVecThreads, 0, st_>>>(n, rowpos.p, row_atom.p, type_s.p, dp_.atom, q_s_hist.p, q_t_hist.p, q_x.p,
+                                                 q_xS.p, q_b.p, q_Hdia_inv.p, q_eta.p, Q);
+  qeq_forward_S(q_xS.p);
+  qeq_spmv(q_xS.p, q_q.p, false, 0);
+  k_pro1<<<kVecBlocks, kVecThreads, 0, st_>>>(n, rowpos.p, q_b.p, q_q.p, q_Hdia_inv.p, q_r.p, q_u.p, q_d.p);
+  qeq_forward_S(q_d.p);
+  qeq_spmv(q_d.p, q_q.p, false, 0);
+  k_pro2<<<kVecBlocks, kVecThreads, 0, st_>>>(n, rowpos.p, q_q.p, q_Hdia_inv.p, q_w.p, q_m.p, q_d.p);
+  qeq_forward_S(q_d.p);
+  qeq_spmv(q_d.p, q_q.p, false, 0);
   k_pro3<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_b.p, q_r.p, q_u.p, q_w.p, q_m.p, q_q.p, q_p.p, q_ss.p, q_v.p, q_z.p, Q);
   if (dist_) dist_allreduce(Q->pro, 6);
   k_scal_init<<<1, 32, 0, st_>>>(Q, qeq_tol, qeq_imax);
   kernel_launches += 5;
 
-  // main loop: sweep(it) ; halo ; SpMV.  The sweep after the last active iteration applies the final x update.
-  int active_host[2] = {1, 1};
-  int it = 1;
-  for (; it <= qeq_imax + 1; it++) {
-    k_cg_sweep<<<kVecBlocks, kVecThreads, 0, st_>>>(n, it, it == 1, qeq_tol, qeq_imax, q_Hdia_inv.p, q_q.p, q_x.p, q_r.p,
-                                                   q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
-    kernel_launches++;
-    const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
-    if (it % qeq_check_every == 0 || it > qeq_imax) {
-      RXB_CUDA(cudaMemcpyAsync(active_host, Q->st[par_next].active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-      RXB_CUDA(cudaStreamSynchronize(st_));
-      if (!(active_host[0] | active_host[1])) break;
+  // main loop: sweep(it) ; halo ; SpMV.  The sweep after the last active iteration applies the final x update; sweeps
+  // and SpMVs launched beyond convergence are gated off on the device.
+  //  * resident run: as many iterations as the previous solve needed + a margin are enqueued WITHOUT a host round trip;
+  //    the convergence state is read with the end-of-step status (System::qeq_settle), which continues the solve and
+  //    replays the force phase in the rare case the prediction fell short;
+  //  * plugin call (the caller wants matvecs back) / first solve: the host polls after the predicted count, then every
+  //    few iterations.
+  const int cap = qeq_imax + 1;
+  const int target = std::min(cap, qeq_predict_ > 0 ? qeq_predict_ + 2 : 8);
+  qeq_it_ = 0;
+  for (int it = 1; it <= target; it++) { qeq_iteration(it); qeq_it_ = it; }
+  qeq_unsettled_ = false;
+  if (wait_for_convergence || qeq_predict_ <= 0) {
+    while (!qeq_poll() && qeq_it_ < cap) {
+      const int more = std::min(cap - qeq_it_, qeq_check_every);
+      for (int k = 0; k < more; k++) { qeq_iteration(qeq_it_ + 1); qeq_it_++; }
     }
-    // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange
-    if (dist_) dist_forward2_dots(q_d.p, Q->dots[(it + 1) % 3]);
-    else forward(q_d.p);
-    spmv(q_d.p, q_q.p, Q, par_next);
+    qeq_predict_ = std::max(matvecs_s, matvecs_t);
+    qeq_iters_total += qeq_predict_;
+  } else {
+    qeq_unsettled_ = true;          // settled by qeq_settle() at the end-of-step synchronisation
   }
-  // final charges
-  k_q_sums<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_x.p, Q);
-  if (dist_) dist_allreduce(Q->sums, 2);
-  k_q_final<<<kVecBlocks, kVecThreads, 0, st_>>>(n, N, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 0);
-  if (dist_) dist_forward_xq();
-  else if (fb) k_q_final<<<fb, 256, 0, st_>>>(n, N, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 1);
-  kernel_launches += 3;
-  int iters_host[2];
-  const int par_final = (it & 1) ^ 1;
-  RXB_CUDA(cudaMemcpyAsync(iters_host, Q->st[par_final].iters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  matvecs_s = iters_host[0];
-  matvecs_t = iters_host[1];
-  qeq_iters_total += (matvecs_s > matvecs_t ? matvecs_s : matvecs_t);
+  qeq_finish(true);
   qeq_ran_this_step_ = true;
   tock(t_QEQ_CG);
+}
+
+// End-of-step: has the solve that was enqueued without polling converged?  (Called right after the end-of-step
+// synchronisation, so the poll below costs one small copy.)  Returns true when it had to be continued - the charges
+// changed and the caller must replay the force phase.
+bool System::qeq_settle() {
+  if (!qeq_unsettled_) return false;
+  qeq_unsettled_ = false;
+  const int cap = qeq_imax + 1;
+  bool continued = false;
+  while (!qeq_poll() && qeq_it_ < cap) {
+    const int more = std::min(cap - qeq_it_, qeq_check_every);
+    for (int k = 0; k < more; k++) { qeq_iteration(qeq_it_ + 1); qeq_it_++; }
+    continued = true;
+  }
+  qeq_predict_ = std::max(matvecs_s, matvecs_t);
+  qeq_iters_total += qeq_predict_;
+  if (continued) qeq_finish(false);
+  return continued;
 }
 
 }  // namespace rxb

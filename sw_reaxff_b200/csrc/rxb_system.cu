@@ -53,15 +53,20 @@ __global__ void k_get_xyz(int N, const double4* __restrict__ xq, double* __restr
 
 // fp32 shadow of the positions + (xb != null) the largest squared displacement since the neighbour build.  Squared
 // distances are non-negative doubles, whose bit patterns order like unsigned integers: one atomicMax per warp.
-__global__ void k_shadow(int N, const double4* __restrict__ xq, const int* __restrict__ type, double ox, double oy, double oz,
-                         float4* __restrict__ xf, const double4* __restrict__ xb, double* __restrict__ disp2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per sorted position k (atom s2a[k]): the S-order copies xs (fp32 shadow) / xqs (exact x,y,z,q) are written
+// coalesced, the atom-order shadow xf is scattered; xb = S-order positions at the last build.
+__global__ void k_shadow(int N, const int* __restrict__ s2a, const double4* __restrict__ xq, const int* __restrict__ type,
+                         double ox, double oy, double oz, float4* __restrict__ xf, float4* __restrict__ xs,
+                         double4* __restrict__ xqs, const double4* __restrict__ xb, double* __restrict__ disp2) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
   double d2 = 0.0;
-  if (i < N) {
+  if (k < N) {
+    const int i = s2a[k];
     const double4 p = xq[i];
-    xf[i] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(type[i]));
+    const float4 sh = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float(type[i]));
+    xf[i] = sh; xs[k] = sh; xqs[k] = p;
     if (xb) {
-      const double4 b = xb[i];
+      const double4 b = xb[k];
       const double dx = p.x - b.x, dy = p.y - b.y, dz = p.z - b.z;
       d2 = dx * dx + dy * dy + dz * dz;
       if (!(d2 >= 0.0)) d2 = 1e300;   // NaN positions: never trust the inner block
@@ -73,6 +78,34 @@ __global__ void k_shadow(int N, const double4* __restrict__ xq, const int* __res
     if ((threadIdx.x & 31) == 0 && d2 > 0.0)
       atomicMax(reinterpret_cast<unsigned long long*>(disp2), (unsigned long long)__double_as_longlong(d2));
   }
+}
+
+// S-space maps of a fresh cell sort: inverse permutation, element per sorted position, "is a local atom" flags
+__global__ void k_sorted_maps(int N, int n, const int* __restrict__ s2a, const int* __restrict__ type, int* __restrict__ a2s,
+                              int* __restrict__ type_s, long long* __restrict__ row_flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > N) return;
+  if (k == N) { row_flag[N] = 0; return; }
+  const int i = s2a[k];
+  a2s[i] = k;
+  type_s[k] = type[i];
+  row_flag[k] = i < n ? 1 : 0;
+}
+__global__ void k_sorted_rows(int N, const int* __restrict__ s2a, const long long* __restrict__ row_flag,
+                              const long long* __restrict__ row_scan, int* __restrict__ rowpos, int* __restrict__ row_atom) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N || !row_flag[k]) return;
+  const long long r = row_scan[k];
+  rowpos[r] = k;
+  row_atom[r] = s2a[k];
+}
+__global__ void k_sorted_ghosts(int n, int nghost, const int* __restrict__ a2s, const int* __restrict__ owner,
+                                int* __restrict__ gs_pos, int* __restrict__ gs_own) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  gs_pos[g] = a2s[n + g];
+  const int o = owner ? owner[g] : -1;       // multi-GPU runs: ghosts are filled by the boundary exchange instead
+  gs_own[g] = o >= 0 ? a2s[o] : -1;
 }
 
 // virial_fdotr over all atoms, pair_reaxc_sunway.cpp:674-702
@@ -391,6 +424,8 @@ void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype
                        const int* owner_in) {
   RXB_CUDA(cudaSetDevice(device_));
   if (chain_inflight_) cancel_inflight();
+  positions_changed();
+  s2a.n = 0; x_build.n = 0;              // the sorted space and the lists belong to the previous atom set
   n = nlocal; N = nlocal + nghost;
   ensure_atom_capacity();
   std::vector<int> hown;
@@ -429,6 +464,7 @@ void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype
 void System::set_positions(const double* x_host) {
   RXB_CUDA(cudaSetDevice(device_));
   if (chain_inflight_) cancel_inflight();
+  positions_changed();
   pin((size_t)3 * N);
   x_stage.resize((size_t)3 * N);
   h2d(x_stage.p, x_host, (size_t)3 * N * sizeof(double), 0);
@@ -438,6 +474,7 @@ void System::set_positions(const double* x_host) {
 
 void System::set_charges(const double* q_host) {
   RXB_CUDA(cudaSetDevice(device_));
+  positions_changed();                   // xqs carries q: refresh the S-order copy
   double* pp = pin((size_t)N);
   memcpy(pp, q_host, (size_t)N * sizeof(double));
   x_stage.resize((size_t)3 * N);
@@ -482,16 +519,60 @@ BondedWork System::bonded_work() {
 }
 
 void System::update_shadow(cudaStream_t st) {
-  if (N == 0) return;
-  xf.resize((size_t)N);
+  if (N == 0 || shadow_valid_) return;        // once per set of positions / charges (reset by positions_changed())
+  if (s2a.n != (size_t)N)
+    throw std::runtime_error("rxb: no neighbour build for the current atom set (rxb_neigh_build must follow rxb_set_atoms)");
+  xf.resize((size_t)N); xs.resize((size_t)N); xqs.resize((size_t)N);
   disp2_d.resize(1);
   // displacement since the build is only meaningful for the atom set the lists were built for
   const bool track = x_build.n == (size_t)N && vl.cut_in > 0.0;
   if (track) RXB_CUDA(cudaMemsetAsync(disp2_d.p, 0, sizeof(double), st));
   else { static const double huge = 1e300; RXB_CUDA(cudaMemcpyAsync(disp2_d.p, &huge, sizeof(double), cudaMemcpyHostToDevice, st)); }
-  k_shadow<<<nblk(N), 256, 0, st>>>(N, xq.p, type.p, cells_a_.origin[0], cells_a_.origin[1], cells_a_.origin[2], xf.p,
-                                    track ? x_build.p : nullptr, disp2_d.p);
+  k_shadow<<<nblk(N), 256, 0, st>>>(N, s2a.p, xq.p, type.p, cells_a_.origin[0], cells_a_.origin[1], cells_a_.origin[2], xf.p,
+                                    xs.p, xqs.p, track ? x_build.p : nullptr, disp2_d.p);
   kernel_launches++;
+  shadow_valid_ = true;
+}
+
+// S space of a fresh cell sort (cells_a_): permutation and its inverse, rows = local atoms in sorted order, ghost maps
+void System::build_sorted_space() {
+  const size_t NN = std::max(N, 1);
+  s2a.resize(NN); a2s.resize(NN); type_s.resize(NN); row_flag.resize(NN + 1); row_scan.resize(NN + 1);
+  rowpos.resize(std::max(n, 1)); row_atom.resize(std::max(n, 1));
+  s2a.n = (size_t)N;
+  if (N == 0) return;
+  RXB_CUDA(cudaMemcpyAsync(s2a.p, cells_a_.sorted_idx.p, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, st_));
+  k_sorted_maps<<<nblk(N + 1), 256, 0, st_>>>(N, n, s2a.p, type.p, a2s.p, type_s.p, row_flag.p);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, row_flag.p, row_scan.p, N + 1, st_);
+  scan_temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(scan_temp.p, need, row_flag.p, row_scan.p, N + 1, st_);
+  k_sorted_rows<<<nblk(N), 256, 0, st_>>>(N, s2a.p, row_flag.p, row_scan.p, rowpos.p, row_atom.p);
+  const int nghost = N - n;
+  gs_pos.resize(std::max(nghost, 1)); gs_own.resize(std::max(nghost, 1));
+  if (nghost > 0)
+    k_sorted_ghosts<<<nblk(nghost), 256, 0, st_>>>(n, nghost, a2s.p, dist_ ? nullptr : ghost_owner.p, gs_pos.p, gs_own.p);
+  kernel_launches += 4;
+}
+
+// H entry format for the current settings (see rxb_dev.cuh); (re)allocates the far-list storage of the chosen format
+void System::choose_h_format() {
+  double shld_min = 1e300;
+  for (int i = 0; i < ff.nt; i++)
+    for (int j = 0; j < ff.nt; j++) shld_min = std::min(shld_min, pow(ff.atom[i].gamma * ff.atom[j].gamma, -1.5));
+  const double bound = 14.4 / cbrt(shld_min > 0 ? shld_min : 1e-300);          // Tap in [0,1] when the taper starts at 0
+  const bool packed = !h_exact_request && qeq_swa == 0.0 && N < (1 << 22) && bound > 0 && bound < 1e6 && std::isfinite(bound);
+  h_packed_ = packed;
+  const size_t slots = (size_t)std::max<long long>(vl.slots, 1);
+  if (packed) {
+    int shift = 0;
+    while (shift < 60 && bound * 1.0001 * ldexp(1.0, shift + 1) < ldexp(1.0, kHColShift)) shift++;
+    h_quant_ = ldexp(1.0, shift);
+    hpk.resize(slots);
+  } else {
+    h_quant_ = 1.0;
+    far_idx.resize(slots); H_val.resize(slots);
+  }
 }
 
 DevView System::view() {
@@ -505,12 +586,14 @@ DevView System::view() {
     v.bond_band = cells_a_.fp32_band(ff.ctl.bond_cut);
   }
   v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
-  v.vl_off = vl.off.p; v.vl_idx = vl.idx.p; v.vl_cnt = vl.cnt.p;
+  v.vl_off = vl.off.p; v.vl_idx = vl.idx.p; v.vl_cnt = vl.cnt.p; v.vl_stride = vl.stride;
+  v.s2a = s2a.p; v.rowpos = rowpos.p; v.row_atom = row_atom.p; v.xs = xs.p; v.xqs = xqs.p; v.type_s = type_s.p;
   disp2_d.resize(1);
   v.vl_cnt_in = vl.cnt_in.p; v.disp2 = disp2_d.p; v.vl_cut_in = vl.cut_in;
   v.bc_off = bc.off.p; v.bc_idx = bc.idx.p; v.bc_cnt = bc.cnt.p;
   v.hc_off = nullptr; v.hc_idx = nullptr;
   v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
+  v.hpk = h_packed_ ? hpk.p : nullptr; v.h_quant = h_quant_;
   v.b_start = b_start.p; v.b_cnt = b_cnt.p; v.b_cursor = b_cursor.p; v.overflow = overflow.p;
   v.b_nbr = b_nbr.p; v.b_sym = b_sym.p; v.b_owner = b_owner.p; v.b_geo = b_geo.p; v.b_bo = b_bo.p; v.b_der = b_der.p;
   v.b_c1 = b_c1.p; v.b_c2 = b_c2.p; v.b_c3 = b_c3.p;
@@ -528,19 +611,27 @@ void System::build_neighbors() {
   const double cn = cutneigh();
   // Verlet list for local rows: bins of cn/2, +-2 cells
   cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
+  build_sorted_space();
   // rows partitioned at far cut-off + kInnerSkin: between rebuilds the per-step far-list sweep reads only that block while
   // no atom has moved more than kInnerSkin / 2 (checked on the device every step)
   const double far = std::max(ff.ctl.nonb_cut, qeq_swb);
-  cells_a_.build(xq.p, n, cn, far + kInnerSkin, vl, st_);
+  cells_a_.build(xq.p, n, cn, far + kInnerSkin, vl, st_, rowpos.p);
+  // S-order copies of the positions; they are also the reference positions of the displacement tracking (zero now)
   x_build.resize((size_t)std::max(N, 1));
-  RXB_CUDA(cudaMemcpyAsync(x_build.p, xq.p, (size_t)N * sizeof(double4), cudaMemcpyDeviceToDevice, st_));
+  x_build.n = 0;
+  shadow_valid_ = false;
+  update_shadow(st_);
+  if (N > 0) {
+    RXB_CUDA(cudaMemcpyAsync(x_build.p, xqs.p, (size_t)N * sizeof(double4), cudaMemcpyDeviceToDevice, st_));
+    RXB_CUDA(cudaMemsetAsync(disp2_d.p, 0, sizeof(double), st_));
+  }
   x_build.n = (size_t)N;
+  if (dist_) dist_sorted_maps();
   // bond candidates for all rows (ghosts too): (reach of the longest possible bond <= bond_cut) + skin
   const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
   cells_b_.build(xq.p, N, cb, 0.0, bc, st_);
-  far_idx.resize((size_t)std::max<long long>(vl.slots, 1));
-  H_val.resize((size_t)std::max<long long>(vl.slots, 1));
+  choose_h_format();
   kernel_launches += 12;
   tock(t_NEIGH);
 }
@@ -611,22 +702,25 @@ void System::compute(bool eflag, bool vflag) {
   update_shadow(st_);
   if (!qeq_ran_this_step_) {
     // pair style without fix qeq/reax this step (checkqeq no): the far list is still needed
+    choose_h_format();
     DevView v = view();
     double Tap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     launch_far_and_H(*this, v, dp_, Tap, shld_d.p, 0.0, st_);
     memcpy(last_tap_, Tap, sizeof(last_tap_)); last_swb_ = 0.0;
   }
   qeq_ran_this_step_ = false;
-  for (int attempt = 0; attempt < 4; attempt++) {
+  for (int attempt = 0; attempt < 6; attempt++) {
     step_forces(eflag, vflag);
     int h[2], wk[4];
     read_step_status(eflag || vflag, h, wk);
     num_bonds = h[0];
     num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
+    // a QEq solve enqueued without polling that had not converged yet is continued now: new charges, replay
+    const bool q_changed = qeq_settle();
     // (multi-GPU: overflow_flag and the needed capacities below are the maxima over all ranks, so every rank replays the
     // same number of times and the collectives inside the loop stay matched)
     const bool lists_fit = !(need_[6] | need_[7] | need_[8]);
-    if (!(overflow_flag & 2) && lists_fit) break;
+    if (!(overflow_flag & 2) && lists_fit && !q_changed) break;
     // a list did not fit (on some rank): grow to the largest need of any rank and replay the force computation of this
     // step (positions are unchanged)
     RXB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st_));
@@ -723,7 +817,7 @@ void System::after_far_hook() {
 // The step's force evaluation in two halves so that the bond list -> bond order -> bonded chain (second stream) overlaps
 // the bandwidth-bound QEq solve.  The resident run calls both back to back; the plugin path calls the front half from
 // fix qeq/reax's pre_force hook and the back half from the pair style's compute hook.
-void System::overlapped_front() {
+void System::overlapped_front(bool wait_for_convergence) {
   if (chain_inflight_) cancel_inflight();
   DevView v = view();
   if (g_odbg.on) { g_odbg.init(); cudaEventRecord(g_odbg.e[0], st_); }
@@ -740,7 +834,7 @@ void System::overlapped_front() {
   if (g_odbg.on) cudaEventRecord(g_odbg.e[1], st2_);   // end of bond list + BO + multi
   hook_after_far_ = true;
   chain_inflight_ = true;
-  qeq_pre_force();                       // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
+  qeq_pre_force(wait_for_convergence);   // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
   if (g_odbg.on) cudaEventRecord(g_odbg.e[3], st_);    // end of CG
 }
 
@@ -754,6 +848,7 @@ void System::overlapped_back(bool eflag, bool vflag) {
   DevView v = view();
   chain_inflight_ = false;
   qeq_ran_this_step_ = false;
+  update_shadow(st_);                    // no-op unless rxb_set_charges replaced the charges after the QEq hook (xqs carries q)
   launch_nonbonded(*this, v, dp_, ev, st_);
   if (g_odbg.on) cudaEventRecord(g_odbg.e[5], st_);    // end of nonbonded
   RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
@@ -776,7 +871,8 @@ void System::overlapped_back(bool eflag, bool vflag) {
   }
   num_bonds = h[0];
   num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
-  if ((overflow_flag & 2) || need_[6] || need_[7] || need_[8]) {
+  const bool q_changed = qeq_settle();   // a solve enqueued without polling that had to be continued: new charges
+  if (q_changed || (overflow_flag & 2) || need_[6] || need_[7] || need_[8]) {
     qeq_ran_this_step_ = true;           // far list and charges of this step are valid: replay only the force phase
     compute(eflag, vflag);               // sequential path grows the arrays and replays
   } else if (overflow_flag & ~2) {
@@ -785,14 +881,14 @@ void System::overlapped_back(bool eflag, bool vflag) {
 }
 
 void System::md_force_overlapped(bool ev) {
-  overlapped_front();
+  overlapped_front(false);
   overlapped_back(ev, ev);
 }
 
 // plugin path (C ABI): fix qeq/reax pre_force, then pair compute
-void System::plugin_qeq_pre_force() {
-  if (overlap && !profile && !dist_ && n > 0) overlapped_front();
-  else { if (chain_inflight_) cancel_inflight(); qeq_pre_force(); }
+void System::plugin_qeq_pre_force(bool wait_for_convergence) {
+  if (overlap && !profile && !dist_ && n > 0) overlapped_front(wait_for_convergence);
+  else { if (chain_inflight_) cancel_inflight(); qeq_pre_force(wait_for_convergence); }
 }
 void System::plugin_compute(bool eflag, bool vflag) {
   if (chain_inflight_) overlapped_back(eflag, vflag);
@@ -804,7 +900,7 @@ void System::md_force() {
   if (overlap && qeq_on && !profile) {
     md_force_overlapped(ev);
   } else {
-    if (qeq_on) qeq_pre_force();
+    if (qeq_on) qeq_pre_force(false);
     compute(ev, ev);
   }
   const int nghost = N - n;
@@ -823,6 +919,7 @@ void System::md_run(int nsteps) {
   for (int s = 0; s < nsteps; s++) {
     ntimestep++;
     k_nve_initial<<<nblk(n), 256, 0, st_>>>(n, dtf, dtv, ltype_d.p, mass_d.p, f.p, v_d.p, xq.p);
+    positions_changed();
     if (species.on && species_step(ntimestep))   // post_integrate: reads the bond list of the previous force evaluation
       species_log.push_back({ntimestep, species.nmole, species.composition});
     md_ago++;
@@ -872,6 +969,68 @@ double System::md_kinetic() {
   RXB_CUDA(cudaMemcpyAsync(&ke, virial_d.p, sizeof(double), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
   return 0.5 * kMvv2e * ke;
+}
+
+// ---- introspection: the S-space lists translated into the caller's index space on the host (parity tests only) ----
+namespace {
+template <class T>
+std::vector<T> fetch(const T* dev, size_t count, cudaStream_t st) {
+  std::vector<T> h(std::max<size_t>(count, 1));
+  if (count) {
+    RXB_CUDA(cudaMemcpyAsync(h.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+    RXB_CUDA(cudaStreamSynchronize(st));
+  }
+  return h;
+}
+}  // namespace
+
+// compact CSR over the local atoms (row i = atom i), columns = atom indices in the order the device row holds them
+void System::export_verlet(long long* off, int* idx) {
+  RXB_CUDA(cudaSetDevice(device_));
+  const std::vector<int> cnt = fetch(vl.cnt.p, (size_t)n, st_), ra = fetch(row_atom.p, (size_t)n, st_),
+                         sa = fetch(s2a.p, (size_t)N, st_), raw = fetch(vl.idx.p, (size_t)vl.slots, st_);
+  std::vector<int> row_of(std::max(n, 1));
+  for (int r = 0; r < n; r++) row_of[ra[r]] = r;
+  long long w = 0;
+  for (int i = 0; i < n; i++) {
+    const int r = row_of[i];
+    off[i] = w;
+    const int* src = raw.data() + (size_t)r * vl.stride;
+    for (int k = 0; k < cnt[r]; k++) idx[w + k] = sa[src[k]];
+    w += cnt[r];
+  }
+  off[n] = w;
+}
+
+// far list / H: num[i] entries for atom i, written at the compact Verlet offset of atom i (the layout rxb_get_far documents)
+void System::export_far(int* num, int* idx, double* val) {
+  RXB_CUDA(cudaSetDevice(device_));
+  const std::vector<int> cnt = fetch(vl.cnt.p, (size_t)n, st_), ra = fetch(row_atom.p, (size_t)n, st_),
+                         sa = fetch(s2a.p, (size_t)N, st_), fn = fetch(far_num.p, (size_t)n, st_);
+  std::vector<unsigned long long> pk;
+  std::vector<int> fi;
+  std::vector<double> hv;
+  if (h_packed_) pk = fetch(hpk.p, (size_t)vl.slots, st_);
+  else { fi = fetch(far_idx.p, (size_t)vl.slots, st_); hv = fetch(H_val.p, (size_t)vl.slots, st_); }
+  std::vector<int> row_of(std::max(n, 1));
+  for (int r = 0; r < n; r++) row_of[ra[r]] = r;
+  long long w = 0;
+  for (int i = 0; i < n; i++) {
+    const int r = row_of[i];
+    num[i] = fn[r];
+    const size_t base = (size_t)r * vl.stride;
+    for (int k = 0; k < fn[r]; k++) {
+      if (h_packed_) {
+        const unsigned long long e = pk[base + k];
+        idx[w + k] = sa[(int)(e >> kHColShift)];
+        val[w + k] = (double)(long long)(e & kHValMask) / h_quant_;
+      } else {
+        idx[w + k] = sa[fi[base + k]];
+        val[w + k] = hv[base + k];
+      }
+    }
+    w += cnt[r];
+  }
 }
 
 }  // namespace rxb

@@ -85,7 +85,8 @@ struct CellList {
   float fp32_band(double cut) const;
   void bin(const double4* xq, int N, double bin_size, int reach, cudaStream_t st);
   // cut_in < cut: every row is partitioned, entries within cut_in (at the build) first; cut_in >= cut: no partition
-  void build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st);
+  // rowpos != null: "S space" output (rxb_dev.cuh): row i = the local atom at sorted position rowpos[i], columns = sorted positions
+  void build(const double4* xq, int nrows, double cut, double cut_in, Csr& out, cudaStream_t st, const int* rowpos = nullptr);
 };
 
 struct Box {  // LAMMPS triclinic box, lo = 0
@@ -133,14 +134,31 @@ class System {
   void qeq_reset_history();
   void qeq_set_history(const double* s_hist, const double* t_hist);  // [n][5] host
   void qeq_get_history(double* s_hist, double* t_hist);
-  void qeq_pre_force();
-  void plugin_qeq_pre_force();          // C ABI entry: QEq with the bonded chain started on the second stream
+  // wait_for_convergence: poll the device flags before returning (the caller wants matvecs_s/t now); false: enqueue the
+  // predicted number of iterations and settle with the end-of-step status (qeq_settle)
+  void qeq_pre_force(bool wait_for_convergence = true);
+  bool qeq_settle();                    // true: the solve had to be continued, charges changed, replay the force phase
+  void qeq_settle_now() { (void)qeq_settle(); }
+  void qeq_iteration(int it);
+  void qeq_forward_S(double2* vecS);    // ghosts of an S-space vector <- owners (periodic images / peer ranks)
+  void qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity);
+  void qeq_finish(bool shift_hist);
+  bool qeq_poll();
+  void plugin_qeq_pre_force(bool wait_for_convergence = true);   // C ABI entry: QEq with the bonded chain started on the second stream
   void plugin_compute(bool eflag, bool vflag);
   int matvecs_s = 0, matvecs_t = 0;
   long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
 
-  int h_bytes_per_entry() const { return 12; }
-  const char* h_format_name() const { return "fp64 value + int32 column (12 B)"; }
+  // storage format of the off-diagonal H entries (rxb_dev.cuh): packed 8-byte words unless exact is requested, the taper
+  // does not start at 0 (values then leave [0, bound]) or the atom count exceeds the 22-bit column field
+  bool h_exact_request = false;
+  int h_bytes_per_entry() const { return h_packed_ ? 8 : 12; }
+  const char* h_format_name() const {
+    return h_packed_ ? "22-bit column + 42-bit fixed-point value in one 64-bit word (8 B)" : "fp64 value + int32 column (12 B)";
+  }
+  // introspection in the caller's index space (tests): compact CSR over local atoms, columns = atom indices
+  void export_verlet(long long* off, int* idx);
+  void export_far(int* num, int* idx, double* val);
 
   // ---- pair compute ----
   void compute(bool eflag, bool vflag);
@@ -223,15 +241,23 @@ class System {
 
   // raw buffers (public: the C ABI copies them out for tests / fix reax/c/bonds)
   DBuf<double4> xq;
-  DBuf<float4> xf;
-  DBuf<double4> x_build;     // positions at the last neighbour build (adaptive inner skin, rxb_dev.cuh)
+  DBuf<float4> xf;           // fp32 shadow in atom order (bond-candidate prefilter)
+  // S space (rxb_dev.cuh): cell-sorted order of the last neighbour build
+  DBuf<int> s2a, a2s, rowpos, row_atom, type_s, gs_pos, gs_own;
+  DBuf<long long> row_flag, row_scan;
+  DBuf<float4> xs;
+  DBuf<double4> xqs;
+  void build_sorted_space();
+  DBuf<double4> x_build;     // S-space positions at the last neighbour build (adaptive inner skin, rxb_dev.cuh)
   DBuf<double> disp2_d;      // [1]: max squared displacement from x_build, refreshed with the shadow positions
-  void update_shadow(cudaStream_t st);   // xq -> xf
+  void update_shadow(cudaStream_t st);   // xq -> xf (atom order), xs / xqs (S order), max displacement since the build
+  void positions_changed() { shadow_valid_ = false; }
   DBuf<int> type, tag, ltype_d, ghost_owner;
   DBuf<double> f, CdDelta;
   Csr vl, bc;
   DBuf<int> far_num, far_idx;
   DBuf<double> H_val;
+  DBuf<unsigned long long> hpk;
   DBuf<int> b_start, b_cnt, b_cursor, overflow, b_nbr, b_sym, b_owner;
   DBuf<double4> b_geo, b_bo, b_der, b_c1, b_c2, b_c3;
   DBuf<double> b_Cdbo, b_Cdbopi, b_Cdbopi2;
@@ -248,7 +274,9 @@ class System {
   BondedWork bonded_work();
   // qeq
   DBuf<double> q_s_hist, q_t_hist;   // [n][5]
-  DBuf<double2> q_x, q_r, q_u, q_w, q_p, q_ss, q_v, q_z, q_d, q_q, q_b, q_m;  // (s,t) interleaved; q_x,q_d length N
+  DBuf<double2> q_x, q_r, q_u, q_w, q_p, q_ss, q_v, q_z, q_q, q_b, q_m;  // (s,t) interleaved row vectors (length n)
+  DBuf<double2> q_xS, q_d;           // S-space vectors (length N): initial guess, search direction
+  DBuf<double> q_eta;
   DBuf<double> q_Hdia_inv;
   DBuf<double> q_scal;               // device scalars
   DBuf<double> shld_d;               // nt*nt shielding (gamma_i gamma_j)^-1.5
@@ -269,7 +297,9 @@ class System {
   bool hook_after_far_ = false;
   void after_far_hook();
   void md_force_overlapped(bool ev);
-  void overlapped_front();
+  void overlapped_front(bool wait_for_convergence);
+  void choose_h_format();
+  void dist_sorted_maps();               // S positions of the send lists / ghosts of the boundary exchange (rxb_dist.cu)
   void overlapped_back(bool eflag, bool vflag);
   void cancel_inflight();
   bool chain_inflight_ = false;          // the bonded chain of this step is queued on st2_ and not yet consumed
@@ -281,6 +311,11 @@ class System {
   DevParams dp_{};
   CellList cells_a_, cells_b_;
   bool qeq_ran_this_step_ = false;
+  bool shadow_valid_ = false;            // xf / xs / xqs hold the current positions
+  bool h_packed_ = false;
+  double h_quant_ = 1.0;
+  int qeq_predict_ = 0, qeq_it_ = 0;     // iterations of the previous solve; loop index of the last launched sweep
+  bool qeq_unsettled_ = false;
   double last_tap_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_swb_ = 0.0;   // what K-farH was last launched with (replays)
   cudaEvent_t run_ev_[2] = {nullptr, nullptr};
   double* h_pin_ = nullptr;  // pinned staging

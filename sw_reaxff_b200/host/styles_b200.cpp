@@ -181,8 +181,12 @@ void FixQEqReaxB200::setup_pre_force(int vflag) { pre_force(vflag); }
 void FixQEqReaxB200::pre_force(int) {
   if (lmp->update->ntimestep % nevery) return;
   reaxc->upload_if_needed();
-  int mv[2];
-  if (rxb_qeq_pre_force(reaxc->rxb, mv)) lmp->error->all(FLERR, rxb_last_error());
+  // The iteration counts (and a host copy of q) are only consumed on thermo steps: there the call waits for convergence
+  // and reports matvecs like the reference; on the other steps the solve is enqueued without a host round trip and is
+  // settled with the end-of-step status inside rxb_pair_compute (include/rxb200.h).
+  const bool thermo_step = !lmp->thermo_every || lmp->update->ntimestep % lmp->thermo_every == 0;
+  int mv[2] = {matvecs_s, matvecs_t};
+  if (rxb_qeq_pre_force(reaxc->rxb, thermo_step ? mv : nullptr)) lmp->error->all(FLERR, rxb_last_error());
   matvecs_s = mv[0]; matvecs_t = mv[1]; matvecs = mv[0] + mv[1];
   if (mv[0] >= 200 || mv[1] >= 200)
     lmp->error->warning(FLERR, "Fix qeq/reax CG convergence failed after 200 iterations at " + std::to_string(lmp->update->ntimestep) + " step");

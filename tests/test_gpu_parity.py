@@ -121,8 +121,12 @@ def test_qeq_charges_and_iterations(case):
     assert np.array_equal(case["qg"][n:], case["qg"][case["cfg"]["owner"]])   # ghost charges forwarded
 
 
-def test_qeq_tight_tolerance_same_solution():
-    """With the tolerance driven to 1e-12 the dual-RHS device solve and the oracle's two serial solves meet."""
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_H", "packed_H"])
+def test_qeq_tight_tolerance_same_solution(exact):
+    """With the tolerance driven to 1e-10 the dual-RHS device solve and the oracle's two serial solves meet.  With the
+    exact 12-byte H entries the iteration counts are the reference's (+-2 at the threshold); with the default packed
+    8-byte entries (H quantised to 2^-38) the solution is the same to 1e-8 and the counts may differ by a few iterations,
+    because a 1e-10 relative residual sits only two orders above the quantisation."""
     cfg = H.static_config(1, 1, 1, perturb=0.1, seed=11, qeq=False)
     o = cfg["oracle"]
     n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
@@ -134,11 +138,13 @@ def test_qeq_tight_tolerance_same_solution():
     o.qeq_set_hist(sh, th)
     mvo = o.qeq_pre_force(owner)
     r = make_rxb(1e-10)
+    r.set_h_exact(exact)
     r.set_atoms(n, x, ty, tg, None, owner)
     r.neigh_build()
     r.qeq_set_history(sh, th)
     mvg = r.qeq_pre_force()
-    assert abs(mvg[0] - mvo[0]) <= 2 and abs(mvg[1] - mvo[1]) <= 2, (mvg, mvo)
+    slack = 2 if exact else 8
+    assert abs(mvg[0] - mvo[0]) <= slack and abs(mvg[1] - mvo[1]) <= slack, (mvg, mvo)
     assert max(mvo) < 200
     assert np.abs(r.get_charges() - o.q()).max() < 1e-8, np.abs(r.get_charges() - o.q()).max()
     so, to = o.qeq_get_hist()
@@ -475,3 +481,47 @@ def test_inner_skin_fallback_far_list_exact_beyond_the_margin():
             b = dict(zip(colH[offH[i]:offH[i] + numH[i]].tolist(), valH[offH[i]:offH[i] + numH[i]].tolist()))
             assert a.keys() == b.keys(), (amp, i)
             assert max(abs(a[k] - b[k]) for k in b) < 1e-11 * np.abs(valH).max()
+
+
+def test_packed_and_exact_h_formats_agree():
+    """The SpMV streams H as 8-byte packed entries (22-bit column + 42-bit fixed point) by default; the exact 12-byte
+    format (fp64 value + int32 column) must give the same far list, H to the quantisation step, the same iteration
+    counts and charges far inside the CG tolerance."""
+    cfg = H.static_config(2, 1, 1, perturb=0.1, seed=21, qeq=False)
+    n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    out = {}
+    for exact in (False, True):
+        r = make_rxb(1e-10)
+        r.set_h_exact(exact)
+        r.set_atoms(n, x, ty, tg, np.zeros(len(x)), owner)
+        r.neigh_build()
+        mv = r.qeq_pre_force()
+        assert r.h_format()["bytes_per_entry"] == (12 if exact else 8)
+        out[exact] = dict(mv=mv, q=r.get_charges(), far=r.far(), f=r.pair_compute(True, True)["f"])
+    a, b = out[False], out[True]
+    assert np.array_equal(a["far"][0], b["far"][0]) and np.array_equal(a["far"][1], b["far"][1])
+    assert np.abs(a["far"][2] - b["far"][2]).max() < 2e-12          # half a quantisation step of 2^-38
+    assert abs(a["mv"][0] - b["mv"][0]) <= 1 and abs(a["mv"][1] - b["mv"][1]) <= 1
+    assert np.abs(a["q"] - b["q"]).max() < 1e-10
+    assert np.abs(a["f"] - b["f"]).max() < 1e-8 * np.abs(b["f"]).max()
+
+
+def test_qeq_async_enqueue_settles_in_pair_compute():
+    """rxb_qeq_pre_force(NULL): the solve is enqueued without polling and settled inside rxb_pair_compute; first with no
+    prediction (polls), then with a prediction from a much EASIER solve (under-prediction -> continued + force replay)."""
+    cfg = H.static_config(1, 1, 1, perturb=0.1, seed=3, qeq=False)
+    n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    ref = make_rxb(1e-10)
+    ref.set_atoms(n, x, ty, tg, np.zeros(len(x)), owner); ref.neigh_build()
+    mv_ref = ref.qeq_pre_force(); q_ref = ref.get_charges(); f_ref = ref.pair_compute(True, True)["f"]
+    r = make_rxb(1e-2)                                      # a loose solve first: its iteration count is the prediction
+    r.set_atoms(n, x, ty, tg, np.zeros(len(x)), owner); r.neigh_build()
+    mv_easy = r.qeq_pre_force()
+    assert max(mv_easy) + 4 < max(mv_ref)
+    r.fix_qeq(0.0, 10.0, 1e-10)
+    r.qeq_set_history(np.zeros((n, 5)), np.zeros((n, 5)))   # same starting guess as the reference handle
+    r.qeq_pre_force_async()
+    f = r.pair_compute(True, True)["f"]
+    assert r.qeq_matvecs() == mv_ref
+    assert np.abs(r.get_charges() - q_ref).max() < 1e-12
+    assert np.abs(f - f_ref).max() < 1e-9 * np.abs(f_ref).max()

@@ -175,5 +175,7 @@ def test_two_runs_in_one_script_reupload_after_setup(tmp_path):
     assert 16 in sa and 16 in sb and 8 in sb
     for step in (5, 10, 15, 16):
         if step in sa and step in sb:
-            assert abs(sa[step][2] - sb[step][2]) < 1e-8 * abs(sa[step][2]), (step, sa[step][2], sb[step][2])
-            np.testing.assert_allclose(sa[step][5:], sb[step][5:], rtol=1e-6, atol=1e-6)
+            assert abs(sa[step][2] - sb[step][2]) < 1e-7 * abs(sa[step][2]), (step, sa[step][2], sb[step][2])
+            # the second run's setup() re-solves QEq from the extrapolated history to the same 1e-6 tolerance: charges, hence
+            # e_ele / e_pol, agree to the solver tolerance, not to round-off
+            np.testing.assert_allclose(sa[step][5:], sb[step][5:], rtol=5e-5, atol=1e-5)
