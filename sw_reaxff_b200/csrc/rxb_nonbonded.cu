@@ -15,6 +15,8 @@
 // Roofline: K-farH streams 4 B/Verlet entry in and 8 B (packed) or 12 B (exact) per far entry out (HBM target); K-nb is
 // fp64-issue bound (143 DP instructions per pair: 2 log + 3 exp + cube root + rsqrt + 1 division, all from rxb_math.cuh).
 // Numbers: DESIGN.md 3.
+#include <type_traits>
+
 #include "rxb_math.cuh"
 #include "rxb_system.h"
 
@@ -189,6 +191,18 @@ __device__ __forceinline__ int far_col(const DevView& v, long long beg, int k) {
   return __ldcs(v.far_idx + beg + k);
 }
 
+template <bool PACKED> using FarRaw = typename std::conditional<PACKED, unsigned long long, int>::type;
+template <bool PACKED>
+__device__ __forceinline__ FarRaw<PACKED> far_raw(const DevView& v, long long beg, int k) {
+  if constexpr (PACKED) return __ldcs(v.hpk + beg + k);
+  else return __ldcs(v.far_idx + beg + k);
+}
+template <bool PACKED>
+__device__ __forceinline__ int raw_col(FarRaw<PACKED> r) {
+  if constexpr (PACKED) return (int)(r >> kHColShift);
+  else return r;
+}
+
 template <bool EV, bool PACKED>
 __global__ void __launch_bounds__(kNbThreads, kNbCtas)
 k_nonbonded(DevView v, DevParams P) {
@@ -224,19 +238,21 @@ k_nonbonded(DevView v, DevParams P) {
     const long long beg = (long long)i * stride;
     const int num = v.far_num[i];
     double fx = 0, fy = 0, fz = 0;
-    int j_cur = lane < num ? far_col<PACKED>(v, beg, lane) : -1;
-    int j_nxt = 32 + lane < num ? far_col<PACKED>(v, beg, 32 + lane) : -1;
+    // software pipeline: the raw list word of chunk t+2 and the (position, type) gather of chunk t+1 are in flight while
+    // chunk t computes.  The word stays RAW (packed: column still in its top bits) until the gather that needs it, so no
+    // instruction touches the register of the in-flight load before then.
     double4 p_cur = make_double4(0, 0, 0, 0);
     int t_cur = -1;
-    if (j_cur >= 0) { p_cur = v.xqs[j_cur]; t_cur = v.type_s[j_cur]; }
+    if (lane < num) { const int j0 = far_col<PACKED>(v, beg, lane); p_cur = v.xqs[j0]; t_cur = v.type_s[j0]; }
+    FarRaw<PACKED> r_nxt = 32 + lane < num ? far_raw<PACKED>(v, beg, 32 + lane) : FarRaw<PACKED>(0);
     for (int k0 = 0; k0 < num; k0 += 32) {
-      const int j_nn = k0 + 64 + lane < num ? far_col<PACKED>(v, beg, k0 + 64 + lane) : -1;
+      const FarRaw<PACKED> r_nn = k0 + 64 + lane < num ? far_raw<PACKED>(v, beg, k0 + 64 + lane) : FarRaw<PACKED>(0);
       double4 p_nxt = make_double4(0, 0, 0, 0);
       int t_nxt = -1;
-      if (j_nxt >= 0) { p_nxt = v.xqs[j_nxt]; t_nxt = v.type_s[j_nxt]; }
+      if (k0 + 32 + lane < num) { const int jn = raw_col<PACKED>(r_nxt); p_nxt = v.xqs[jn]; t_nxt = v.type_s[jn]; }
       const int tj = t_cur;
       const double4 pj = p_cur;
-      j_cur = j_nxt; p_cur = p_nxt; t_cur = t_nxt; j_nxt = j_nn;
+      p_cur = p_nxt; t_cur = t_nxt; r_nxt = r_nn;
       if (tj < 0) continue;
       const double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
       const double r2 = dist2_rn(dx, dy, dz);
