@@ -60,6 +60,17 @@ struct Dist {
   DBuf<double> dots_all;                 // [world][4]: every rank's partial CG dot products (dist_forward2_dots)
   DBuf<int> send_s, self_s;              // sorted positions of the atoms I send / of the sources of my own periodic images
   DBuf<double> recv2;                    // staging of received double2 ghost values, ghost order
+  // ---- peer-memory exchange (NVLink P2P stores, no NCCL in the CG iteration): see "peer exchange" below
+  bool peer_ok = false;                  // every rank mapped every other rank's window
+  bool peer_plan_ok = false;             // ... and the current plan fits the halo capacity on every rank
+  bool peer_use = true;                  // RXB_PEER=0 keeps the NCCL path (A/B, debugging)
+  char* win = nullptr;                   // my window (cudaMalloc): flags | dots | halo
+  std::vector<char*> win_of;             // mapped window of every rank (win_of[rank] = win)
+  size_t cap_g = 0;                      // ghost entries (double2) per parity the halo region holds
+  unsigned long long seq = 0;            // exchange sequence number (flags are monotonic)
+  DBuf<int> dst_off_d, soff_d;           // per peer: where my values land in its halo; my send offsets (W + 1)
+  DBuf<unsigned int> done_d;             // CTA completion counter of the push kernel
+  DBuf<int> peer_err_d;                  // set when a wait timed out (a peer died): checked with the end-of-step status
 };
 
 namespace {
@@ -246,10 +257,23 @@ void System::dist_init(int rank, int world, const char* id128, int px, int py, i
   RXB_NCCL(ncclCommInitRank(&D.comm, world, id, rank));
   D.counts.assign(world, 0);
   D.counts_d.resize(world);
+  dist_peer_setup();
 }
 
 void System::dist_destroy() {
   if (!dist_) return;
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < (int)dist_->win_of.size(); r++)
+    if (r != dist_->rank && dist_->win_of[r]) cudaIpcCloseMemHandle(dist_->win_of[r]);
+  if (dist_->comm) {                     // nobody may unmap or free a window a peer could still be storing into
+    DBuf<int> bar;
+    bar.resize(1);
+    cudaMemsetAsync(bar.p, 0, sizeof(int), st_);
+    ncclAllReduce(bar.p, bar.p, 1, ncclInt, ncclSum, dist_->comm, st_);
+    cudaStreamSynchronize(st_);
+  }
+  if (dist_->win) cudaFree(dist_->win);
   if (dist_->comm) ncclCommDestroy(dist_->comm);
   delete dist_;
   dist_ = nullptr;
@@ -461,6 +485,25 @@ void System::dist_build_plan() {
     D.soff[r + 1] = D.soff[r] + D.send_to[r];
   }
   D.nsend = D.soff[W];
+  // peer exchange: where my values land in each consumer's halo (its ghost offset for source = me), and whether every
+  // rank's ghosts fit the halo windows (decided from the all-gathered table: the same answer on every rank)
+  {
+    std::vector<int> dst_off(W, 0);
+    long long max_ghosts = 0;
+    for (int p = 0; p < W; p++) {
+      long long tot = 0;
+      for (int r = 0; r < W; r++) {
+        if (r == D.rank) dst_off[p] = (int)tot;
+        tot += all[(size_t)p * W + r];
+      }
+      max_ghosts = std::max(max_ghosts, tot);
+    }
+    D.peer_plan_ok = D.peer_ok && max_ghosts <= (long long)D.cap_g;
+    D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
+    RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
+    RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+    RXB_CUDA(cudaStreamSynchronize(st_));          // dst_off is a local that dies with this scope
+  }
   D.sendlist.resize(std::max(D.nsend, 1));
   D.sendbuf.resize((size_t)4 * std::max(D.nsend, 1));
   D.recvbuf.resize((size_t)3 * std::max(D.nsend, 1));
@@ -508,6 +551,193 @@ void System::dist_forward_xq() {
   kernel_launches++;
 }
 
+// ---- peer exchange -------------------------------------------------------------------------------------------------
+// Each rank owns one window (cudaMalloc, exported through CUDA IPC, mapped by every other rank of the node):
+//   [0, 2 KB)              flags[W]      : flags[r] = sequence number of the last exchange rank r completed towards me
+//   [2 KB, + 2*W*8 doubles) dots[2][W][8] : partial sums from every rank, double-buffered by exchange parity
+//   [halo_off, ...)        halo[2][cap_g] double2: incoming ghost values in my ghost order, double-buffered
+// One exchange = k_peer_push (boundary values stored straight into the consumers' halo over NVLink, partial sums into their
+// dots, then - after a system-scope fence by every thread and a last-CTA election - the sequence number into their flags)
+// + k_peer_pull on the consumer (acquire-spin on its own flags, ghosts <- halo, partial sums added in rank order so all
+// ranks hold bit-identical totals).  Remote stores, local loads; no NCCL call and no host involvement per CG iteration
+// (the reference: MPI_Allreduce + forward_comm_fix per iteration, fix_qeq_reax_sunway.cpp:1108-1140).
+// Double buffering is sufficient: a rank can only start exchange s+2 after pulling s+1, which needs every peer's push
+// s+1, which each peer issues (stream order) after its own pull s - the last reader of the parity-s buffers.
+namespace {
+constexpr int kMaxPeers = 16;
+constexpr size_t kFlagBytes = 2048;
+constexpr int kDotSlots = 8;
+struct PeerView {
+  int W, me;
+  char* base[kMaxPeers];
+  size_t dots_off, halo_off, cap_g;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_push(PeerView P, int par, unsigned long long seq, int nsend, const int* __restrict__ send_s, const int* __restrict__ soff,
+            const int* __restrict__ dst_off, double2* vec, int g0, int g1, const int* __restrict__ gs_pos,
+            const int* __restrict__ self_s, int ndots, const double* __restrict__ dots, unsigned int* __restrict__ done) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // boundary values -> the consumers' halo (their ghost order)
+  for (int e = tid; e < nsend; e += nth) {
+    int p = 0;
+    while (e >= soff[p + 1]) p++;                       // W <= 16: a short scan
+    double2* halo = reinterpret_cast<double2*>(P.base[p] + P.halo_off) + (size_t)par * P.cap_g;
+    halo[dst_off[p] + (e - soff[p])] = vec[send_s[e]];
+  }
+  // my own periodic images (local copy; sources are local atoms, destinations ghosts: disjoint)
+  for (int g = g0 + tid; g < g1; g += nth) vec[gs_pos[g]] = vec[self_s[g - g0]];
+  // partial sums -> every peer
+  if (blockIdx.x == 0 && threadIdx.x < ndots * P.W) {
+    const int p = threadIdx.x / ndots, k = threadIdx.x % ndots;
+    if (p != P.me) {
+      double* d = reinterpret_cast<double*>(P.base[p] + P.dots_off) + ((size_t)par * P.W + P.me) * kDotSlots;
+      d[k] = dots[k];
+    }
+  }
+  __threadfence_system();                               // every thread: its remote stores are visible system-wide ...
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(done, 1u);
+    if (t == gridDim.x - 1) {                           // ... before the last CTA publishes the sequence number
+      *done = 0;
+      __threadfence_system();
+      for (int p = 0; p < P.W; p++)
+        if (p != P.me) st_release_sys(reinterpret_cast<unsigned long long*>(P.base[p]) + P.me, seq);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_pull(PeerView P, int par, unsigned long long seq, int nghost, int g0, int g1, const int* __restrict__ gs_pos,
+            double2* __restrict__ vec, int ndots, double* __restrict__ dots, int* __restrict__ err) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = 1;
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(P.base[P.me]);
+    const unsigned long long t0 = globaltimer_ns();
+    for (int r = 0; r < P.W && ok; r++) {
+      if (r == P.me) continue;
+      while (ld_acquire_sys(flags + r) < seq) {
+        if (globaltimer_ns() - t0 > 10000000000ULL) { ok = 0; atomicExch(err, 1); break; }   // 10 s: a peer is gone
+      }
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  const double2* halo = reinterpret_cast<const double2*>(P.base[P.me] + P.halo_off) + (size_t)par * P.cap_g;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nghost; g += gridDim.x * blockDim.x)
+    if (g < g0 || g >= g1) vec[gs_pos[g]] = halo[g];
+  if (blockIdx.x == 0 && threadIdx.x < ndots) {
+    const double* d = reinterpret_cast<const double*>(P.base[P.me] + P.dots_off) + (size_t)par * P.W * kDotSlots;
+    const double mine = dots[threadIdx.x];
+    double s = 0.0;
+    for (int r = 0; r < P.W; r++) s += (r == P.me) ? mine : d[(size_t)r * kDotSlots + threadIdx.x];
+    dots[threadIdx.x] = s;                              // the same numbers added in the same (rank) order on every rank
+  }
+}
+
+PeerView peer_view(const Dist& D) {
+  PeerView P{};
+  P.W = D.world; P.me = D.rank;
+  for (int r = 0; r < D.world; r++) P.base[r] = D.win_of[r];
+  P.dots_off = kFlagBytes;
+  P.halo_off = kFlagBytes + (((size_t)2 * D.world * kDotSlots * sizeof(double) + 255) / 256) * 256;
+  P.cap_g = D.cap_g;
+  return P;
+}
+
+// vec: S-space double2 vector whose ghosts are refreshed (null: pure reduction); dots[ndots]: partial sums -> totals
+void peer_exchange(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
+  D.seq++;
+  const int par = (int)(D.seq & 1);
+  const PeerView P = peer_view(D);
+  const int g0 = vec ? D.goff[D.rank] : 0, g1 = vec ? D.goff[D.rank + 1] : 0;
+  const int nsend = vec ? D.nsend : 0;
+  const int work = std::max(nsend, g1 - g0);
+  k_peer_push<<<std::max(1, std::min(148, (work + 255) / 256)), 256, 0, st>>>(P, par, D.seq, nsend, D.send_s.p, D.soff_d.p,
+                                                                           D.dst_off_d.p, vec, g0, g1, gs_pos, D.self_s.p,
+                                                                           ndots, dots, D.done_d.p);
+  const int ng = vec ? nghost : 0;
+  k_peer_pull<<<std::max(1, std::min(296, (ng + 255) / 256)), 256, 0, st>>>(P, par, D.seq, ng, g0, g1, gs_pos, vec, ndots, dots,
+                                                                         D.peer_err_d.p);
+  s.kernel_launches += 2;
+}
+}  // namespace
+
+// Map every rank's window (CUDA IPC; all ranks are processes on one node).  Any failure on any rank (no peer access,
+// IPC disabled in the container, more than 16 ranks) leaves the NCCL send/recv path in place on ALL ranks.
+void System::dist_peer_setup() {
+  Dist& D = *dist_;
+  const int W = D.world;
+  const char* e = getenv("RXB_PEER");
+  D.peer_use = e ? atoi(e) != 0 : true;
+  D.peer_ok = false;
+  D.done_d.resize(1); D.peer_err_d.resize(1);
+  RXB_CUDA(cudaMemsetAsync(D.done_d.p, 0, sizeof(unsigned int), st_));
+  RXB_CUDA(cudaMemsetAsync(D.peer_err_d.p, 0, sizeof(int), st_));
+  int ok = (D.peer_use && W <= kMaxPeers) ? 1 : 0;
+  const char* ce = getenv("RXB_PEER_CAP");
+  D.cap_g = ce ? (size_t)atol(ce) : ((size_t)1 << 20);
+  D.win_of.assign(W, nullptr);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    const size_t bytes = peer_view(D).halo_off + (size_t)2 * D.cap_g * sizeof(double2);
+    if (cudaMalloc(&D.win, bytes) != cudaSuccess) { cudaGetLastError(); D.win = nullptr; ok = 0; }
+    else {
+      RXB_CUDA(cudaMemsetAsync(D.win, 0, bytes, st_));
+      if (cudaIpcGetMemHandle(&mine, D.win) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+  }
+  // all-gather the handles (64 bytes each) through NCCL
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  DBuf<char> hs, ha;
+  hs.resize(64); ha.resize((size_t)64 * W);
+  RXB_CUDA(cudaMemcpyAsync(hs.p, &mine, 64, cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllGather(hs.p, ha.p, 64, ncclChar, D.comm, st_));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  RXB_CUDA(cudaMemcpyAsync(all.data(), ha.p, (size_t)64 * W, cudaMemcpyDeviceToHost, st_));
+  // does every rank have a window?
+  DBuf<int> flag;
+  flag.resize(1);
+  RXB_CUDA(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, D.comm, st_));
+  RXB_CUDA(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  if (ok) {
+    for (int r = 0; r < W; r++) {
+      if (r == D.rank) { D.win_of[r] = D.win; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      D.win_of[r] = (char*)p;
+    }
+  }
+  RXB_CUDA(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, D.comm, st_));
+  RXB_CUDA(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  D.peer_ok = ok != 0;
+  if (getenv("RXB_PEER_VERBOSE") && D.rank == 0)
+    fprintf(stderr, "rxb dist: peer-memory exchange %s (%d ranks, halo capacity %zu ghosts)\n", D.peer_ok ? "ON" : "off (NCCL send/recv)",
+            W, D.cap_g);
+}
+
+bool System::dist_peer_active() const { return dist_ && dist_->peer_ok && dist_->peer_plan_ok; }
+
 // ---- S-space vectors (the CG search direction): locals and ghosts are interleaved in cell-sorted order, so the boundary
 // values are packed through send_s (sorted positions of the atoms each peer needs), received into a staging buffer in ghost
 // order and scattered to the ghosts' sorted positions by one kernel that also serves this rank's own periodic images.
@@ -538,6 +768,7 @@ void System::dist_sorted_maps() {
 
 static void s_forward2(System& s, Dist& D, double2* vec, int n, int nghost, const int* gs_pos, double* dots, cudaStream_t st) {
   const int W = D.world;
+  if (D.peer_ok && D.peer_plan_ok) { peer_exchange(s, D, vec, nghost, gs_pos, dots, dots ? 4 : 0, st); return; }
   double* v = reinterpret_cast<double*>(vec);
   if (D.nsend > 0) k_pack<2><<<nblk(D.nsend), 256, 0, st>>>(D.nsend, D.send_s.p, v, D.sendbuf.p);
   if (dots) D.dots_all.resize((size_t)4 * W);
@@ -579,8 +810,26 @@ __global__ void k_sum_dots(int world, int rank, const double* __restrict__ all, 
 void System::dist_forward2_dots(double2* vec, double* dots) {
   Dist& D = *dist_;
   s_forward2(*this, D, vec, n, N - n, gs_pos.p, dots, st_);
+  if (D.peer_ok && D.peer_plan_ok) return;         // the pull kernel has already formed the totals
   k_sum_dots<<<1, 32, 0, st_>>>(D.world, D.rank, D.dots_all.p, dots);
   kernel_launches++;
+}
+
+// sum of a few device scalars over all ranks, identical bits on every rank (count <= 8)
+void System::dist_sum_small(double* dev_ptr, int count) {
+  if (!dist_) return;
+  Dist& D = *dist_;
+  if (D.peer_ok && D.peer_plan_ok && count <= kDotSlots) { peer_exchange(*this, D, nullptr, 0, nullptr, dev_ptr, count, st_); return; }
+  dist_allreduce(dev_ptr, count);
+}
+
+// a wait of the peer exchange timed out (a peer process died): reported with the end-of-step status
+void System::dist_peer_check() {
+  if (!dist_ || !dist_->peer_ok) return;
+  int err = 0;
+  RXB_CUDA(cudaMemcpyAsync(&err, dist_->peer_err_d.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  if (err) throw std::runtime_error("rxb dist: peer-memory exchange timed out (a peer rank stopped responding)");
 }
 
 void System::dist_reverse_f() {

@@ -358,7 +358,7 @@ void System::qeq_finish(bool shift_hist) {
   const int nghost = N - n;
   k_zero2<<<1, 32, 0, st_>>>(Q->sums);
   k_q_sums<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_x.p, Q);
-  if (dist_) dist_allreduce(Q->sums, 2);
+  if (dist_) dist_sum_small(Q->sums, 2);
   k_q_final<<<kVecBlocks, kVecThreads, 0, st_>>>(n, N, row_atom.p, ghost_owner.p, q_x.p, Q, q_s_hist.p, q_t_hist.p, xq.p, 0,
                                                 shift_hist ? 1 : 0);
   if (dist_) dist_forward_xq();
@@ -425,7 +425,7 @@ void System::qeq_pre_force(bool wait_for_convergence) {
   qeq_forward_S(q_d.p);
   qeq_spmv(q_d.p, q_q.p, false, 0);
   k_pro3<<<kVecBlocks, kVecThreads, 0, st_>>>(n, q_b.p, q_r.p, q_u.p, q_w.p, q_m.p, q_q.p, q_p.p, q_ss.p, q_v.p, q_z.p, Q);
-  if (dist_) dist_allreduce(Q->pro, 6);
+  if (dist_) dist_sum_small(Q->pro, 6);
   k_scal_init<<<1, 32, 0, st_>>>(Q, qeq_tol, qeq_imax);
   kernel_launches += 5;
 

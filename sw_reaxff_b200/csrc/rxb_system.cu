@@ -691,6 +691,7 @@ void System::read_step_status(bool ev, int* h, int* wk) {
     RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
   }
   RXB_CUDA(cudaStreamSynchronize(st_));
+  if (dist_) dist_peer_check();
   h[0] = host[0]; h[1] = host[5] | (host[4] ? 2 : 0);
   wk[0] = host[1]; wk[1] = host[2]; wk[2] = host[3]; wk[3] = 0;
   for (int k = 0; k < 9; k++) need_[k] = host[16 + k];

@@ -189,6 +189,10 @@ class System {
   void dist_allreduce(double* dev_ptr, int count);
   int dist_rank() const;
   void dist_allreduce_int(int* dev_ptr, size_t count);
+  void dist_sum_small(double* dev_ptr, int count);   // <= 8 scalars; through the peer windows when they are active
+  void dist_peer_setup();
+  bool dist_peer_active() const;
+  void dist_peer_check();
   void dist_allreduce_max_int(int* dev_ptr, size_t count);
   void dist_allgather_int(const int* send, int* recv, size_t count_per_rank);
   void dist_exchange();          // exchange + borders at reneighbouring
