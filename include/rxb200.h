@@ -166,6 +166,11 @@ int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* compo
  * neigh, qeq far+H, qeq CG (whole solve), bond list, BO, bonded (all), nonbonded, dBond, SpMV (per launch), hbond items,
  * angle+torsion items, multi-body, enumeration.  enable: 1 reset+start, 0 stop, -1 read only. */
 int rxb_profile(rxb_handle* h, int enable, double* out26);
+/* Tests only: shrink the capacities of the growable lists (directed bonds, angle / torsion / hydrogen-bond work lists) and
+ * of the per-atom shared-memory staging (bonds per atom, strong bonds per centre) so that every grow-and-replay branch
+ * of the force phase can be driven on an ordinary cell (values <= 0 are left alone); read the current values back. */
+int rxb_debug_set_caps(rxb_handle* h, int row_cap, int strong_cap, int cap_bonds, int cap_ang, int cap_tor, int cap_hb);
+int rxb_debug_get_caps(rxb_handle* h, int* out6);
 /* Storage format of one off-diagonal H entry (what the SpMV streams per non-zero): bytes per entry and a short name. */
 int rxb_get_h_format(rxb_handle* h, int* bytes_per_entry, char* name, int cap);
 /* Measured fp64 FMA throughput of the device in TFLOP/s (a pure DFMA kernel, best of 5): the roofline denominator of the

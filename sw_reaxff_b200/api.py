@@ -17,7 +17,7 @@ SYMBOLS = [
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
-    "rxb_qeq_matvecs", "rxb_set_h_exact",
+    "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -146,6 +146,14 @@ class Rxb:
         mv = np.zeros(2, dtype=np.int32)
         self._chk(self.lib.rxb_qeq_matvecs(self.h, _p(mv)))
         return int(mv[0]), int(mv[1])
+
+    def debug_set_caps(self, row_cap=0, strong_cap=0, cap_bonds=0, cap_ang=0, cap_tor=0, cap_hb=0):
+        self._chk(self.lib.rxb_debug_set_caps(self.h, int(row_cap), int(strong_cap), int(cap_bonds), int(cap_ang), int(cap_tor), int(cap_hb)))
+
+    def debug_get_caps(self):
+        o = np.zeros(6, dtype=np.int32)
+        self._chk(self.lib.rxb_debug_get_caps(self.h, _p(o)))
+        return dict(zip(["row_cap", "strong_cap", "cap_bonds", "cap_ang", "cap_tor", "cap_hb"], o.tolist()))
 
     def set_h_exact(self, on=True):
         self._chk(self.lib.rxb_set_h_exact(self.h, int(on)))

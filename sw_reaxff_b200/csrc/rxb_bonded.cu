@@ -279,14 +279,15 @@ __device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, 
 // warp per centre left most lanes idle (and lane 0 alone did the pow() calls of the SBO block for the whole warp).
 __global__ void __launch_bounds__(kWarps * 32)
 k_enum(DevView v, DevParams P, BondedWork W) {
-  __shared__ int s_strong[kWarps][4][32];
+  extern __shared__ int s_strong[];   // [kWarps][4][strong_cap]: the strong bonds of each centre (grown on overflow bit 8)
+  const int strong_cap = v.strong_cap;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   const double thb_cut = P.ctl.thb_cut, thb_cutsq = P.ctl.thb_cutsq;
   const double p_val8 = P.gp[33], p_val9 = P.gp[16];
   const int nt = P.nt;
   const unsigned lt_mask = (1u << lane) - 1, lt_sub = (1u << sub) - 1;
-  int* strong_list = s_strong[wib][grp];
+  int* strong_list = s_strong + (size_t)(wib * 4 + grp) * strong_cap;
   for (int j0 = 4 * wg; j0 < v.n; j0 += 4 * nwg) {   // warp-uniform trip count: the ballots below need all 32 lanes
     const int j = j0 + grp;
     const int type_j = j < v.n ? v.type[j] : -1;
@@ -306,11 +307,11 @@ k_enum(DevView v, DevParams P, BondedWork W) {
         strong = bo.x > thb_cut;
       }
       const unsigned m = (__ballot_sync(0xffffffffu, strong) >> (8 * grp)) & 0xffu;   // this centre's 8 lanes
-      if (strong) { const int slot = ns + __popc(m & lt_sub); if (slot < 32) strong_list[slot] = start_j + e; }
+      if (strong) { const int slot = ns + __popc(m & lt_sub); if (slot < strong_cap) strong_list[slot] = start_j + e; }
       ns += __popc(m);
     }
     __syncwarp();
-    if (ns > 32) { if (sub == 0) atomicOr(v.overflow, 8); ns = 32; }
+    if (ns > strong_cap) { if (sub == 0) { atomicOr(v.overflow, 8); atomicMax(v.need_row + 1, ns); } ns = strong_cap; }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
       SBOp += __shfl_xor_sync(0xffffffffu, SBOp, o, 8);
@@ -340,8 +341,10 @@ k_enum(DevView v, DevParams P, BondedWork W) {
     for (int q0 = 0; q0 < max_np; q0 += 8) {
       const int q = q0 + sub;
       bool ang = false;
-      unsigned long long tmask = 0ull;  // matching pw offsets in k's row
       int pk = -1, ph = -1, start_k = 0;
+      // torsion scan of k's row (done below, 64 entries per round): what this lane needs for it
+      int t_rounds = 0, t_cnt_k = 0, t_pj = -1, t_h = -1, t_base = 0;
+      double t_bo2 = 0.0;   // bo_hj * bo_jk
       if (q < npair) {
         const int a = q / ns, b = q - a * ns;
         if (a != b) {
@@ -355,21 +358,8 @@ k_enum(DevView v, DevParams P, BondedWork W) {
             ang = (ph > pk) && (bo_jk * bo_hj > thb_cutsq);
             const int pj = v.b_sym[pk];
             if (pj >= 0 && half_select(tag_j, v.tag[k], xj, v.xq[k])) {
-              const int ne = min(cnt_k, 64);
-              if (cnt_k > 64) atomicOr(v.overflow, 8);
-              for (int e = 0; e < ne; e++) {
-                const int pw = start_k + e;
-                if (pw == pj) continue;
-                const double bo_kl = v.b_bo[pw].x;
-                if (!(bo_kl > thb_cut)) continue;
-                const int l = v.b_nbr[pw];
-                if (l == h) continue;
-                const int type_l = v.type[l];
-                if (type_l < 0) continue;
-                if (!P.tors[((type_h * nt + type_j) * nt + type_k) * nt + type_l].cnt) continue;
-                if (!(bo_hj * bo_jk * bo_kl > thb_cut)) continue;
-                tmask |= 1ull << e;
-              }
+              t_rounds = (cnt_k + 63) >> 6; t_cnt_k = cnt_k; t_pj = pj; t_h = h; t_bo2 = bo_hj * bo_jk;
+              t_base = ((type_h * nt + type_j) * nt + type_k) * nt;
             }
           }
         }
@@ -385,22 +375,44 @@ k_enum(DevView v, DevParams P, BondedWork W) {
           if (o < W.cap_ang) W.ang[o] = make_int4(j, pk, ph, 0);
         }
       }
-      // torsions: warp exclusive scan of per-lane counts
-      const int mine = __popcll(tmask);
-      int incl = mine;
+      // torsions: k's row is scanned 64 entries per round (a 64-bit match mask per lane; rows of more than 64 bonds
+      // simply take more rounds), then a warp exclusive scan of the per-lane counts carves the output slots
+      const int rounds = __reduce_max_sync(0xffffffffu, t_rounds);
+      for (int c = 0; c < rounds; c++) {
+        unsigned long long tmask = 0ull;  // matching pw offsets in this 64-entry window of k's row
+        const int e0 = c << 6;
+        if (c < t_rounds) {
+          const int ne = min(t_cnt_k - e0, 64);
+          for (int e = 0; e < ne; e++) {
+            const int pw = start_k + e0 + e;
+            if (pw == t_pj) continue;
+            const double bo_kl = v.b_bo[pw].x;
+            if (!(bo_kl > thb_cut)) continue;
+            const int l = v.b_nbr[pw];
+            if (l == t_h) continue;
+            const int type_l = v.type[l];
+            if (type_l < 0) continue;
+            if (!P.tors[t_base + type_l].cnt) continue;
+            if (!(t_bo2 * bo_kl > thb_cut)) continue;
+            tmask |= 1ull << e;
+          }
+        }
+        const int mine = __popcll(tmask);
+        int incl = mine;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(W.n_tor, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        int o = base + incl - mine;
-        while (tmask) {
-          const int e = __ffsll((long long)tmask) - 1;
-          tmask &= tmask - 1;
-          if (o < W.cap_tor) W.tor[o] = make_int4(j, pk, ph, start_k + e);
-          o++;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(W.n_tor, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          int o = base + incl - mine;
+          while (tmask) {
+            const int e = __ffsll((long long)tmask) - 1;
+            tmask &= tmask - 1;
+            if (o < W.cap_tor) W.tor[o] = make_int4(j, pk, ph, start_k + e0 + e);
+            o++;
+          }
         }
       }
     }
@@ -774,7 +786,13 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
   // one wave of resident CTAs each (measured for the item kernels: 1 / 2 / 3 waves 1.81 / 1.82 / 1.84 ms for the chain;
   // the former fixed 148 x 8 grids were 1.6 - 2.7 waves: 1.96 ms)
   constexpr int kItemWaves = 1;
-  k_enum<<<wave_grid(k_enum, kWarps * 32, 1, occ_enum), kWarps * 32, 0, st>>>(v, P, W);
+  const size_t smem_enum = (size_t)kWarps * 4 * v.strong_cap * sizeof(int);
+  static size_t smem_enum_set = 0;
+  if (smem_enum > 48 * 1024 && smem_enum > smem_enum_set) {
+    RXB_CUDA(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_enum));
+    smem_enum_set = smem_enum;
+  }
+  k_enum<<<wave_grid(k_enum, kWarps * 32, 1, occ_enum), kWarps * 32, smem_enum, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::HBOND, st);
   k_hbond_items<<<wave_grid(k_hbond_items, kItemThreads, kItemWaves, occ_hb), kItemThreads, 0, st>>>(v, P, W);

@@ -16,21 +16,24 @@ namespace rxb {
 namespace {
 
 constexpr int kWarps = 4;      // warps per block
-constexpr int kMaxRow = 64;    // bonds per atom held in shared staging (reference: 35 while building, 20 later)
-
-struct Stage {
-  int nbr[kMaxRow];
-  double val[kMaxRow][11];  // d,dx,dy,dz, BO,BO_s,BO_pi,BO_pi2, cBOp,cPi,cPi2
-};
+// Bonds per atom held in shared staging: v.row_cap entries per warp (dynamic shared memory; 64 to start with - the
+// reference allows 35 while building and 20 later).  A row that outgrows it is not fatal: the kernel raises overflow bit 1,
+// the host doubles row_cap and replays the force phase (System::compute), like every other list of this path.
+constexpr int kStageDoubles = 11;   // d,dx,dy,dz, BO,BO_s,BO_pi,BO_pi2, cBOp,cPi,cPi2
+inline size_t bond_stage_bytes(int row_cap) {
+  return (size_t)kWarps * ((size_t)row_cap * (kStageDoubles * sizeof(double) + sizeof(int)) + 64 * sizeof(int));
+}
 
 __global__ void __launch_bounds__(kWarps * 32, 7)   // 6 / 7 / 8 CTAs per SM measured: 0.692 / 0.676 / 0.689 ms
 k_bond_list(DevView v, DevParams P) {
-  __shared__ Stage stage[kWarps];
-  __shared__ int s_queue[kWarps][64];
+  extern __shared__ __align__(16) double bl_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int row_cap = v.row_cap;
+  double* S_val = bl_smem + (size_t)wib * row_cap * kStageDoubles;                       // [row_cap][11]
+  int* S_nbr = reinterpret_cast<int*>(bl_smem + (size_t)kWarps * row_cap * kStageDoubles) + (size_t)wib * row_cap;
+  int* s_queue = reinterpret_cast<int*>(bl_smem + (size_t)kWarps * row_cap * kStageDoubles) + (size_t)kWarps * row_cap;
   const int i = blockIdx.x * kWarps + wib;
   if (i >= v.N) return;
-  Stage& S = stage[wib];
   const int ti = v.type[i];
   int cnt = 0;
   if (ti >= 0) {
@@ -38,7 +41,7 @@ k_bond_list(DevView v, DevParams P) {
     const AtomPar ai = P.atom[ti];
     const double bo_cut = P.ctl.bo_cut, bond_cut = P.ctl.bond_cut, nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
     const long long beg = v.bc_off[i], end = beg + v.bc_cnt[i];
-    int* queue = s_queue[wib];
+    int* queue = s_queue + wib * 64;
     int qn = 0;
     const float4 fi = v.xf[i];
     // per partner element: (reach of a bond of this pair)^2 + fp32 rounding band; lane t holds the threshold of element t
@@ -125,9 +128,9 @@ k_bond_list(DevView v, DevParams P) {
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int slot = cnt + __popc(m & ((1u << lane) - 1));
-        if (slot < kMaxRow) {
-          S.nbr[slot] = j;
-          double* o = S.val[slot];
+        if (slot < row_cap) {
+          S_nbr[slot] = j;
+          double* o = S_val + (size_t)slot * kStageDoubles;
           o[0] = d; o[1] = dx; o[2] = dy; o[3] = dz; o[4] = BO; o[5] = BO_s; o[6] = BO_pi; o[7] = BO_pi2;
           o[8] = cBOp; o[9] = cPi; o[10] = cPi2;
         }
@@ -136,15 +139,18 @@ k_bond_list(DevView v, DevParams P) {
       __syncwarp();
     }
   }
-  if (cnt > kMaxRow) { if (lane == 0) atomicOr(v.overflow, 1); cnt = kMaxRow; }
+  if (cnt > row_cap) { if (lane == 0) { atomicOr(v.overflow, 1); atomicMax(v.need_row, cnt); } cnt = row_cap; }
   __syncwarp();
   // carve the row
   int start = 0;
   if (lane == 0) {
     start = atomicAdd(v.b_cursor, cnt);
-    if (start + cnt > v.cap_bonds) { atomicOr(v.overflow, 2); }
-    v.b_start[i] = start;
-    v.b_cnt[i] = cnt;
+    // a row that does not fit the bond arrays is published EMPTY: the kernels that still run before the host grows the
+    // arrays and replays the step must not walk rows that were never written (the cursor keeps the true total)
+    const bool fits_row = start + cnt <= v.cap_bonds;
+    if (!fits_row) atomicOr(v.overflow, 2);
+    v.b_start[i] = fits_row ? start : 0;
+    v.b_cnt[i] = fits_row ? cnt : 0;
   }
   start = __shfl_sync(0xffffffffu, start, 0);
   const bool fits = start + cnt <= v.cap_bonds;
@@ -153,10 +159,10 @@ k_bond_list(DevView v, DevParams P) {
   for (int e0 = 0; e0 < cnt; e0 += 32) {
     const int e = e0 + lane;
     if (e < cnt) {
-      const int mine = S.nbr[e];
+      const int mine = S_nbr[e];
       int rank = 0;
-      for (int t = 0; t < cnt; t++) rank += (S.nbr[t] < mine);
-      const double* o = S.val[e];
+      for (int t = 0; t < cnt; t++) rank += (S_nbr[t] < mine);
+      const double* o = S_val + (size_t)e * kStageDoubles;
       if (fits) {
         const int p = start + rank;
         v.b_nbr[p] = mine;
@@ -314,7 +320,13 @@ k_bond_order_atoms(DevView v, DevParams P) {
 void launch_bond_list(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   RXB_CUDA(cudaMemsetAsync(v.b_cursor, 0, sizeof(int), st));
   if (v.N == 0) return;
-  k_bond_list<<<(v.N + kWarps - 1) / kWarps, kWarps * 32, 0, st>>>(v, P);
+  const size_t smem = bond_stage_bytes(v.row_cap);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    RXB_CUDA(cudaFuncSetAttribute(k_bond_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  k_bond_list<<<(v.N + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(v, P);
   s.kernel_launches++;
 }
 

@@ -182,6 +182,12 @@ int rxb_qeq_matvecs(rxb_handle* h, int* matvecs2) {
     matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t;
   });
 }
+int rxb_debug_set_caps(rxb_handle* h, int row_cap, int strong_cap, int cap_bonds, int cap_ang, int cap_tor, int cap_hb) {
+  return guard([&] { h->sys->debug_set_caps(row_cap, strong_cap, cap_bonds, cap_ang, cap_tor, cap_hb); });
+}
+int rxb_debug_get_caps(rxb_handle* h, int* out6) {
+  return guard([&] { h->sys->debug_get_caps(out6); });
+}
 int rxb_set_h_exact(rxb_handle* h, int on) { return guard([&] { h->sys->h_exact_request = on != 0; }); }
 int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist) {
   return guard([&] { h->sys->qeq_set_history(s_hist, t_hist); });

@@ -75,6 +75,9 @@ struct DevView {
   double h_quant;        // 2^h_shift (packed format); the SpMV multiplies its row sums by 1 / h_quant
   // bonds
   int* b_start; int* b_cnt; int* b_cursor; int* overflow;
+  // per-atom staging capacities of the bond-list / enumeration kernels (grown by the host on overflow bits 1 / 8, then the
+  // force phase is replayed) and the largest need seen: need_row[0] bonds of one atom, need_row[1] strong bonds of one centre
+  int row_cap, strong_cap; int* need_row;
   int* b_nbr; int* b_sym; int* b_owner;
   double4* b_geo;      // d, dx, dy, dz          (dvec = x_nbr - x_i)
   double4* b_bo;       // BO, BO_s, BO_pi, BO_pi2

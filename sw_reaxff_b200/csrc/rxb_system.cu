@@ -268,8 +268,9 @@ System::System(int device) : device_(device) {
   RXB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   RXB_CUDA(cudaEventCreateWithFlags(&ev_far_, cudaEventDisableTiming));
   RXB_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
-  b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6);
+  b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6); need_row_d.resize(2);
   RXB_CUDA(cudaMemset(overflow.p, 0, sizeof(int)));
+  RXB_CUDA(cudaMemset(need_row_d.p, 0, 2 * sizeof(int)));
 }
 
 System::~System() {
@@ -595,6 +596,7 @@ DevView System::view() {
   v.far_num = far_num.p; v.far_idx = far_idx.p; v.H_val = H_val.p;
   v.hpk = h_packed_ ? hpk.p : nullptr; v.h_quant = h_quant_;
   v.b_start = b_start.p; v.b_cnt = b_cnt.p; v.b_cursor = b_cursor.p; v.overflow = overflow.p;
+  v.row_cap = row_cap_; v.strong_cap = strong_cap_; v.need_row = need_row_d.p;
   v.b_nbr = b_nbr.p; v.b_sym = b_sym.p; v.b_owner = b_owner.p; v.b_geo = b_geo.p; v.b_bo = b_bo.p; v.b_der = b_der.p;
   v.b_c1 = b_c1.p; v.b_c2 = b_c2.p; v.b_c3 = b_c3.p;
   v.b_Cdbo = b_Cdbo.p; v.b_Cdbopi = b_Cdbopi.p; v.b_Cdbopi2 = b_Cdbopi2.p;
@@ -667,22 +669,23 @@ namespace {
 // slots: 0 bond cursor, 1..3 n_ang n_tor n_hb, 4 bond arrays too small, 5 fatal per-atom bits, 6..8 work list too small.
 // Slots 4..8 are 0/1 (or a bit mask whose any-non-zero matters), so the maximum over ranks is the OR over ranks.
 __global__ void k_gather_status(const int* __restrict__ cursor, const int* __restrict__ overflow, const int* __restrict__ counts,
-                                int cap_ang, int cap_tor, int cap_hb, int* __restrict__ out) {
+                                const int* __restrict__ need_row, int cap_ang, int cap_tor, int cap_hb, int* __restrict__ out) {
   if (threadIdx.x == 0) {
     const int ov = overflow[0];
     out[0] = cursor[0]; out[1] = counts[0]; out[2] = counts[1]; out[3] = counts[2];
     out[4] = (ov & 2) ? 1 : 0; out[5] = ov & ~2;
     out[6] = counts[0] > cap_ang; out[7] = counts[1] > cap_tor; out[8] = counts[2] > cap_hb;
-    for (int k = 0; k < 9; k++) out[16 + k] = out[k];
+    out[9] = need_row[0]; out[10] = need_row[1];       // longest bond row / strong list that did not fit its staging
+    for (int k = 0; k < 11; k++) out[16 + k] = out[k];
   }
 }
 }  // namespace
 
 void System::read_step_status(bool ev, int* h, int* wk) {
   status_d_.resize(32);
-  k_gather_status<<<1, 32, 0, st_>>>(b_cursor.p, overflow.p, it_count.p, cap_ang, cap_tor, cap_hb, status_d_.p);
+  k_gather_status<<<1, 32, 0, st_>>>(b_cursor.p, overflow.p, it_count.p, need_row_d.p, cap_ang, cap_tor, cap_hb, status_d_.p);
   kernel_launches++;
-  if (dist_) dist_allreduce_max_int(status_d_.p + 16, 9);
+  if (dist_) dist_allreduce_max_int(status_d_.p + 16, 11);
   int host[32];
   RXB_CUDA(cudaMemcpyAsync(host, status_d_.p, 32 * sizeof(int), cudaMemcpyDeviceToHost, st_));
   if (ev && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
@@ -694,7 +697,7 @@ void System::read_step_status(bool ev, int* h, int* wk) {
   if (dist_) dist_peer_check();
   h[0] = host[0]; h[1] = host[5] | (host[4] ? 2 : 0);
   wk[0] = host[1]; wk[1] = host[2]; wk[2] = host[3]; wk[3] = 0;
-  for (int k = 0; k < 9; k++) need_[k] = host[16 + k];
+  for (int k = 0; k < 11; k++) need_[k] = host[16 + k];
   overflow_flag = need_[5] | (need_[4] ? 2 : 0);      // over all ranks
 }
 
@@ -721,7 +724,10 @@ void System::compute(bool eflag, bool vflag) {
     // (multi-GPU: overflow_flag and the needed capacities below are the maxima over all ranks, so every rank replays the
     // same number of times and the collectives inside the loop stay matched)
     const bool lists_fit = !(need_[6] | need_[7] | need_[8]);
-    if (!(overflow_flag & 2) && lists_fit && !q_changed) break;
+    const bool staging_fits = !(overflow_flag & (1 | 8));
+    if (!(overflow_flag & 2) && lists_fit && staging_fits && !q_changed) { overflow_flag = 0; break; }
+    if (attempt == 5) { overflow_flag |= 64; break; }           // still not fitting after five replays: reported below
+    if (!staging_fits) grow_staging();
     // a list did not fit (on some rank): grow to the largest need of any rank and replay the force computation of this
     // step (positions are unchanged)
     RXB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st_));
@@ -736,8 +742,24 @@ void System::compute(bool eflag, bool vflag) {
     }
     overflow_flag &= ~2;
   }
-  if (overflow_flag & ~2)
-    throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
+  if (overflow_flag)
+    throw std::runtime_error("rxb: the force phase did not fit its lists after 6 grow-and-replay attempts (overflow bits " +
+                             std::to_string(overflow_flag) + ")");
+}
+
+// A bond row / strong-bond list outgrew its shared-memory staging (overflow bits 1 / 8): size it for the largest need seen
+// on any rank (+ slack, doubled at least) before the replay.  Bounded by the 227 KB of shared memory a CTA can have
+// (~600 bonds per atom, an order of magnitude beyond any physical density).
+void System::grow_staging() {
+  if (overflow_flag & 1) {
+    row_cap_ = std::max(2 * row_cap_, (need_[9] + 8 + 31) / 32 * 32);
+    if (row_cap_ > 576) throw std::runtime_error("rxb: more than 576 bonds on one atom (" + std::to_string(need_[9]) + "): unphysical input");
+  }
+  if (overflow_flag & 8) {
+    strong_cap_ = std::max(2 * strong_cap_, need_[10] + 8);
+    if (strong_cap_ > 1536) throw std::runtime_error("rxb: more than 1536 strong bonds on one atom: unphysical input");
+  }
+  RXB_CUDA(cudaMemsetAsync(need_row_d.p, 0, 2 * sizeof(int), st_));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -873,11 +895,9 @@ void System::overlapped_back(bool eflag, bool vflag) {
   num_bonds = h[0];
   num_ang = wk[0]; num_tor = wk[1]; num_hb = wk[2];
   const bool q_changed = qeq_settle();   // a solve enqueued without polling that had to be continued: new charges
-  if (q_changed || (overflow_flag & 2) || need_[6] || need_[7] || need_[8]) {
+  if (q_changed || overflow_flag || need_[6] || need_[7] || need_[8]) {
     qeq_ran_this_step_ = true;           // far list and charges of this step are valid: replay only the force phase
     compute(eflag, vflag);               // sequential path grows the arrays and replays
-  } else if (overflow_flag & ~2) {
-    throw std::runtime_error("rxb: per-atom capacity exceeded (bonds per atom > 64, hbond acceptors > 32 or strong bonds > 32)");
   }
 }
 

@@ -156,6 +156,17 @@ class System {
   const char* h_format_name() const {
     return h_packed_ ? "22-bit column + 42-bit fixed-point value in one 64-bit word (8 B)" : "fp64 value + int32 column (12 B)";
   }
+  // tests: shrink the list / staging capacities (values <= 0 are left alone) so that every grow-and-replay branch of
+  // compute() can be driven on an ordinary cell; read them back (row_cap, strong_cap, cap_bonds, cap_ang, cap_tor, cap_hb)
+  void debug_set_caps(int row_cap, int strong_cap, int cap_bonds_, int cap_ang_, int cap_tor_, int cap_hb_) {
+    if (row_cap > 0) row_cap_ = row_cap;
+    if (strong_cap > 0) strong_cap_ = strong_cap;
+    if (cap_bonds_ > 0) cap_bonds = cap_bonds_;
+    if (cap_ang_ > 0) cap_ang = cap_ang_;
+    if (cap_tor_ > 0) cap_tor = cap_tor_;
+    if (cap_hb_ > 0) cap_hb = cap_hb_;
+  }
+  void debug_get_caps(int* o) const { o[0] = row_cap_; o[1] = strong_cap_; o[2] = cap_bonds; o[3] = cap_ang; o[4] = cap_tor; o[5] = cap_hb; }
   // introspection in the caller's index space (tests): compact CSR over local atoms, columns = atom indices
   void export_verlet(long long* off, int* idx);
   void export_far(int* num, int* idx, double* val);
@@ -329,7 +340,10 @@ class System {
   void step_forces(bool eflag, bool vflag);
   void read_step_status(bool ev, int* h2, int* wk4);
   DBuf<int> status_d_;
-  int need_[9] = {0};                    // status slots of k_gather_status, maximum over all ranks
+  int need_[11] = {0};                   // status slots of k_gather_status, maximum over all ranks
+  int row_cap_ = 64, strong_cap_ = 32;   // shared-memory staging of the bond-list / enumeration kernels (grown on demand)
+  DBuf<int> need_row_d;
+  void grow_staging();
   void ensure_atom_capacity();
   void ensure_bond_capacity(int cap);
   void md_make_ghosts();
