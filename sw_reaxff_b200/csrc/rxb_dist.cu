@@ -4,17 +4,17 @@
 // forward_comm of x every step, reverse_comm of f, forward_comm_fix of the CG search direction and MPI_Allreduce of the
 // dot products every CG iteration (fix_qeq_reax_sunway.cpp:1043-1132) — is done here on the device:
 //   * bricks in lamda space (px x py x pz), ghost shell = cutneigh;
-//   * reneighbouring ("exchange + borders"): every rank all-gathers the 144-byte migration records of all atoms
-//     (x, v, q, s_hist, t_hist, tag, type), then selects its new local atoms and its ghost images from the gathered set
-//     with two count/scan/fill kernels.  One collective instead of 6-direction staged swaps: on NVSwitch every peer is one
-//     hop at full bandwidth, and the gathered set makes migration of s_hist/t_hist/v trivial;
-//   * forward (x,q), CG halo (d as double2), reverse (f): peer-to-peer boundary exchange.  At every exchange each rank
-//     lists, per peer, the local atoms that peer holds as ghosts (dist_build_plan); a step then packs those atoms,
-//     issues one grouped ncclSend/ncclRecv per peer pair and unpacks (+ image shift) — only the boundary layer moves
-//     (8-24 B per ghost).  rxb_dist_set_p2p(0) falls back to whole-slab all-gathers / reduce-scatter for comparison;
-//   * CG dots / sums / energies: ncclAllReduce on the device scalars, stream-ordered, no host sync.
-// Parity-tested against the single-GPU path (positions, forces, charges, energies, species; incl. migration).  What is
-// left on the table at N > 1 is NCCL launch latency per CG iteration (halo + all-reduce are serial with the SpMV).
+//   * reneighbouring ("exchange + borders"): atoms that left their brick travel as 144-byte records to their new owner
+//     only; every rank then works out which of its atoms (and periodic images) lie in the ghost shell of which rank and
+//     sends 48-byte records there (dist_exchange).  Received bytes per rank scale with the shell, not with the system;
+//   * forward (x,q) and reverse (f) every step: grouped ncclSend/ncclRecv of the boundary values between the ranks that
+//     share atoms, along the send lists the borders step produced;
+//   * every CG iteration: boundary values of the search direction and the four partial dot products are STORED straight
+//     into the consumers' memory over NVLink (CUDA IPC windows, flag-ordered, "peer exchange" below): no NCCL call and
+//     no host involvement inside the solve; falls back to grouped send/recv when peer mapping is unavailable;
+//   * energies / virial / status words: ncclAllReduce on device scalars, stream-ordered.
+// Parity-tested against the single-GPU path (positions, forces, charges, energies, species; incl. migration):
+// sw_reaxff_b200/dist.py parity_check, executed by bench.py before anything is timed at N > 1.
 #include <cub/cub.cuh>
 #include <nccl.h>
 
@@ -39,25 +39,20 @@ struct Dist {
   int grid[3] = {1, 1, 1}, coord[3] = {0, 0, 0};
   double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
   ncclComm_t comm = nullptr;
-  int chunk = 0;                 // slots per rank in the gathered arrays
-  std::vector<int> counts;       // local atoms per rank at the last exchange
-  DBuf<int> counts_d;
-  DBuf<double> rec_send, rec_all;        // [chunk][kRec], [world*chunk][kRec]
-  DBuf<double> rec2_send, rec2_all;      // compact post-migration records [..][5]
-  DBuf<double4> xq_all;                  // [world*chunk]
-  DBuf<double2> d_all;                   // [world*chunk]
-  DBuf<double> f_all, f_recv;            // [world*chunk][3], [chunk][3]
-  DBuf<int> gsrc;                        // per ghost: source slot in the gathered arrays
-  DBuf<long long> flag, off;             // selection scans
+  DBuf<double> rec_send;                 // [n][kRec] migration records of the local atoms
+  DBuf<long long> flag, off;             // stayer flags and their scan
   DBuf<char> temp;
-  // peer-to-peer boundary exchange plan (rebuilt at every exchange): ghosts are ordered by source slot, hence grouped by
-  // source rank; rank r sends me exactly the local atoms I listed, in my ghost order, so receives land in place
-  bool p2p = true;
+  // boundary exchange plan (rebuilt at every reneighbouring): my ghosts are grouped by source rank (goff), within a rank
+  // in the sender's (atom, image) order; sendlist[soff[r] ..) = my atoms rank r holds as ghosts, in that same order
   std::vector<int> need_from, send_to, goff, soff;   // per peer: ghosts I need / atoms I send, and their offsets
   int nsend = 0;
   DBuf<int> greq, sendlist, cnt_d, cnt_all_d;
   DBuf<double> sendbuf, recvbuf;
   DBuf<double> dots_all;                 // [world][4]: every rank's partial CG dot products (dist_forward2_dots)
+  DBuf<int> dest, cursor, emit_list;     // exchange/borders scratch: destination rank per atom, emission cursor and list
+  DBuf<unsigned long long> keys, keys2;  // sort keys of the leavers / of the emitted (rank, atom, image) triples
+  DBuf<double> mig_send, mig_recv, ghost_send, ghost_recv;
+  size_t recv_bytes_last = 0;            // payload this rank received at the last reneighbouring (migrants + ghosts)
   DBuf<int> send_s, self_s;              // sorted positions of the atoms I send / of the sources of my own periodic images
   DBuf<double> recv2;                    // staging of received double2 ghost values, ghost order
   // ---- peer-memory exchange (NVLink P2P stores, no NCCL in the CG iteration): see "peer exchange" below
@@ -92,141 +87,6 @@ __device__ __forceinline__ bool in_brick(const Brick& k, const double* l) {
   return l[0] >= k.lo[0] && l[0] < k.hi[0] && l[1] >= k.lo[1] && l[1] < k.hi[1] && l[2] >= k.lo[2] && l[2] < k.hi[2];
 }
 
-__global__ void k_wrap_pack(int n, BoxD b, double4* __restrict__ xq, const double* __restrict__ vel,
-                            const double* __restrict__ s_hist, const double* __restrict__ t_hist,
-                            const int* __restrict__ tag, const int* __restrict__ ltype, double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 p = xq[i];
-  double l[3];
-  x2lamda(b, p.x, p.y, p.z, l);
-  const int s0 = (int)floor(l[0]), s1 = (int)floor(l[1]), s2 = (int)floor(l[2]);
-  if (s0 | s1 | s2) {
-    double d[3];
-    shift_vec(b, s0, s1, s2, d);
-    p.x -= d[0]; p.y -= d[1]; p.z -= d[2];
-  }
-  double* r = rec + (size_t)kRec * i;
-  r[0] = p.x; r[1] = p.y; r[2] = p.z;
-  r[3] = vel[3 * i]; r[4] = vel[3 * i + 1]; r[5] = vel[3 * i + 2];
-  r[6] = p.w;
-  for (int k = 0; k < 5; k++) { r[7 + k] = s_hist[5 * (size_t)i + k]; r[12 + k] = t_hist[5 * (size_t)i + k]; }
-  r[17] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
-}
-
-__global__ void k_pack_compact(int n, const double4* __restrict__ xq, const int* __restrict__ tag, const int* __restrict__ ltype,
-                               double* __restrict__ rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double4 p = xq[i];
-  double* r = rec + (size_t)5 * i;
-  r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
-  r[4] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
-}
-
-__device__ __forceinline__ bool slot_valid(int s, int chunk, const int* counts) { return (s % chunk) < counts[s / chunk]; }
-
-__global__ void k_flag_locals(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
-                              Brick k, long long* __restrict__ flag) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s > nslots) return;
-  long long f = 0;
-  if (s < nslots && slot_valid(s, chunk, counts)) {
-    const double* r = rec + (size_t)kRec * s;
-    double l[3];
-    x2lamda(b, r[0], r[1], r[2], l);
-    f = in_brick(k, l) ? 1 : 0;
-  }
-  flag[s] = f;
-}
-
-__global__ void k_fill_locals(int nslots, const long long* __restrict__ flag, const long long* __restrict__ off,
-                              const double* __restrict__ rec, const int* __restrict__ map, int maplen, double4* __restrict__ xq,
-                              double* __restrict__ vel, double* __restrict__ s_hist, double* __restrict__ t_hist,
-                              int* __restrict__ tag, int* __restrict__ ltype, int* __restrict__ type) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nslots || !flag[s]) return;
-  const long long i = off[s];
-  const double* r = rec + (size_t)kRec * s;
-  xq[i] = make_double4(r[0], r[1], r[2], r[6]);
-  vel[3 * i] = r[3]; vel[3 * i + 1] = r[4]; vel[3 * i + 2] = r[5];
-  for (int k = 0; k < 5; k++) { s_hist[5 * i + k] = r[7 + k]; t_hist[5 * i + k] = r[12 + k]; }
-  const long long tt = __double_as_longlong(r[17]);
-  const int tg = (int)(tt >> 32), lt = (int)(tt & 0xffffffffLL);
-  tag[i] = tg; ltype[i] = lt;
-  type[i] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
-}
-
-// STRIDE doubles per record, charge at QOFF, packed (tag,type) at TOFF
-template <bool FILL, int STRIDE, int QOFF, int TOFF>
-__global__ void k_ghosts_dist(int nslots, int chunk, const int* __restrict__ counts, const double* __restrict__ rec, BoxD b,
-                              Brick k, int n, const int* __restrict__ map, int maplen, long long* __restrict__ count,
-                              const long long* __restrict__ off, double4* __restrict__ xq, int* __restrict__ tag,
-                              int* __restrict__ ltype, int* __restrict__ type, int* __restrict__ gsrc, int* __restrict__ shift) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s > nslots) return;
-  if (s == nslots || !slot_valid(s, chunk, counts)) { if (!FILL) count[s] = 0; return; }
-  const double* r = rec + (size_t)STRIDE * s;
-  double l[3];
-  x2lamda(b, r[0], r[1], r[2], l);
-  const bool mine = in_brick(k, l);
-  long long c = 0, w = FILL ? off[s] : 0;
-  for (int sz = -k.m[2]; sz <= k.m[2]; sz++) {
-    const double l2 = l[2] + sz;
-    if (!(l2 >= k.lo[2] - k.cg[2] && l2 < k.hi[2] + k.cg[2])) continue;
-    for (int sy = -k.m[1]; sy <= k.m[1]; sy++) {
-      const double l1 = l[1] + sy;
-      if (!(l1 >= k.lo[1] - k.cg[1] && l1 < k.hi[1] + k.cg[1])) continue;
-      for (int sx = -k.m[0]; sx <= k.m[0]; sx++) {
-        if (mine && !sx && !sy && !sz) continue;
-        const double l0 = l[0] + sx;
-        if (!(l0 >= k.lo[0] - k.cg[0] && l0 < k.hi[0] + k.cg[0])) continue;
-        if (FILL) {
-          double d[3];
-          shift_vec(b, sx, sy, sz, d);
-          const long long g = n + w;
-          xq[g] = make_double4(r[0] + d[0], r[1] + d[1], r[2] + d[2], r[QOFF]);
-          const long long tt = __double_as_longlong(r[TOFF]);
-          const int lt = (int)(tt & 0xffffffffLL);
-          tag[g] = (int)(tt >> 32); ltype[g] = lt;
-          type[g] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
-          gsrc[w] = s;
-          shift[3 * w] = sx; shift[3 * w + 1] = sy; shift[3 * w + 2] = sz;
-          w++;
-        } else {
-          c++;
-        }
-      }
-    }
-  }
-  if (!FILL) count[s] = c;
-}
-
-__global__ void k_ghost_x_from_all(int n, int nghost, BoxD b, const int* __restrict__ gsrc, const int* __restrict__ shift,
-                                   const double4* __restrict__ xq_all, double4* __restrict__ xq) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nghost) return;
-  double d[3];
-  shift_vec(b, shift[3 * g], shift[3 * g + 1], shift[3 * g + 2], d);
-  const double4 p = xq_all[gsrc[g]];
-  xq[n + g] = make_double4(p.x + d[0], p.y + d[1], p.z + d[2], p.w);
-}
-__global__ void k_ghost_d_from_all(int n, int nghost, const int* __restrict__ gsrc, const double2* __restrict__ d_all,
-                                   double2* __restrict__ vec) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < nghost) vec[n + g] = d_all[gsrc[g]];
-}
-__global__ void k_scatter_f(int n, int nghost, int my_off, const int* __restrict__ gsrc, const double* __restrict__ f,
-                            double* __restrict__ f_all) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n + nghost) return;
-  const long long dst = i < n ? (long long)my_off + i : gsrc[i - n];
-  const double fx = f[3 * i], fy = f[3 * i + 1], fz = f[3 * i + 2];
-  if (fx != 0.0) atomicAdd(&f_all[3 * dst], fx);
-  if (fy != 0.0) atomicAdd(&f_all[3 * dst + 1], fy);
-  if (fz != 0.0) atomicAdd(&f_all[3 * dst + 2], fz);
-}
-
 inline int nblk(long n, int t = 256) { return (int)((n + t - 1) / t); }
 
 }  // namespace
@@ -255,8 +115,6 @@ void System::dist_init(int rank, int world, const char* id128, int px, int py, i
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   RXB_NCCL(ncclCommInitRank(&D.comm, world, id, rank));
-  D.counts.assign(world, 0);
-  D.counts_d.resize(world);
   dist_peer_setup();
 }
 
@@ -280,7 +138,8 @@ void System::dist_destroy() {
 }
 
 int System::dist_world() const { return dist_ ? dist_->world : 1; }
-size_t System::slab() const { return dist_ ? (size_t)dist_->chunk : 0; }
+size_t System::slab() const { return 0; }
+size_t System::dist_last_recv_bytes() const { return dist_ ? dist_->recv_bytes_last : 0; }
 
 void System::dist_allreduce(double* dev_ptr, int count) {
   if (!dist_) return;
@@ -304,122 +163,338 @@ void System::dist_allgather_int(const int* send, int* recv, size_t count_per_ran
   RXB_NCCL(ncclAllGather(send, recv, count_per_rank, ncclInt, dist_->comm, st_));
 }
 
-// exchange + borders
+// ---- exchange + borders at reneighbouring: only migrants and boundary-shell atoms travel, and only between the ranks
+// concerned (LAMMPS Comm::exchange / Comm::borders semantics; the reference gets both from the LAMMPS core over MPI).
+//   exchange : every local atom is wrapped and assigned to the brick that contains it; the few that left travel as
+//              144-byte records (x, v, q, s_hist, t_hist, tag, type) straight to their new owner.  New local order =
+//              stayers in their old order, then arrivals by source rank: deterministic.
+//   borders  : every rank decides itself which of its atoms (and which periodic images of them) lie in the ghost shell
+//              of which rank - itself included - and sends 48-byte records (x, q, tag|type, image shift) there; the
+//              ghosts of a rank are ordered by (source rank, source atom index, image).  The sender therefore already
+//              holds the send lists of the per-step halos (forward x/q, CG direction, reverse f): no request round.
+// Two small all-gathers (W ints per rank each) carry the counts; the payload moves in grouped ncclSend/ncclRecv.
+namespace {
+constexpr int kGRec = 6;  // doubles per ghost record: x y z q (tag,type) shiftcode
+
+__device__ __forceinline__ int brick_of(double l, int g) {
+  int b = (int)floor(l * g);
+  return b < 0 ? 0 : (b >= g ? g - 1 : b);
+}
+
+// wrap into the box, pack the migration record, destination rank; leavers are counted per destination
+__global__ void k_mig_classify(int n, BoxD b, int gx, int gy, int gz, int me, double4* __restrict__ xq,
+                               const double* __restrict__ vel, const double* __restrict__ s_hist,
+                               const double* __restrict__ t_hist, const int* __restrict__ tag, const int* __restrict__ ltype,
+                               double* __restrict__ rec, int* __restrict__ dest, long long* __restrict__ stay_flag,
+                               int* __restrict__ cnt_to) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { stay_flag[n] = 0; return; }
+  double4 p = xq[i];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  const int s0 = (int)floor(l[0]), s1 = (int)floor(l[1]), s2 = (int)floor(l[2]);
+  if (s0 | s1 | s2) {
+    double d[3];
+    shift_vec(b, s0, s1, s2, d);
+    p.x -= d[0]; p.y -= d[1]; p.z -= d[2];
+    l[0] -= s0; l[1] -= s1; l[2] -= s2;
+  }
+  double* r = rec + (size_t)kRec * i;
+  r[0] = p.x; r[1] = p.y; r[2] = p.z;
+  r[3] = vel[3 * i]; r[4] = vel[3 * i + 1]; r[5] = vel[3 * i + 2];
+  r[6] = p.w;
+  for (int k = 0; k < 5; k++) { r[7 + k] = s_hist[5 * (size_t)i + k]; r[12 + k] = t_hist[5 * (size_t)i + k]; }
+  r[17] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
+  const int d = (brick_of(l[2], gz) * gy + brick_of(l[1], gy)) * gx + brick_of(l[0], gx);
+  dest[i] = d;
+  stay_flag[i] = d == me ? 1 : 0;
+  if (d != me) atomicAdd(&cnt_to[d], 1);
+}
+
+// leavers -> sort keys (destination, atom index): sorted, they are grouped by destination in atom order
+__global__ void k_mig_keys(int n, int me, const int* __restrict__ dest, const long long* __restrict__ stay_scan,
+                           unsigned long long* __restrict__ keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || dest[i] == me) return;
+  const long long slot = i - stay_scan[i];                 // leavers before i
+  keys[slot] = ((unsigned long long)dest[i] << 32) | (unsigned)i;
+}
+__global__ void k_mig_pack(int m, const unsigned long long* __restrict__ keys, const double* __restrict__ rec,
+                           double* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const int i = (int)(keys[e] & 0xffffffffu);
+  for (int k = 0; k < kRec; k++) out[(size_t)kRec * e + k] = rec[(size_t)kRec * i + k];
+}
+// new local atom a: a < nstay -> the a-th stayer (old index via the scan), else arrival a - nstay
+__global__ void k_mig_fill(int n_old, int nstay, int narr, const long long* __restrict__ stay_flag,
+                           const long long* __restrict__ stay_scan, const double* __restrict__ rec,
+                           const double* __restrict__ arr, const int* __restrict__ map, int maplen, double4* __restrict__ xq,
+                           double* __restrict__ vel, double* __restrict__ s_hist, double* __restrict__ t_hist,
+                           int* __restrict__ tag, int* __restrict__ ltype, int* __restrict__ type) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* r;
+  long long a;
+  if (t < n_old) {
+    if (!stay_flag[t]) return;
+    a = stay_scan[t];
+    r = rec + (size_t)kRec * t;
+  } else if (t < n_old + narr) {
+    a = nstay + (t - n_old);
+    r = arr + (size_t)kRec * (t - n_old);
+  } else {
+    return;
+  }
+  xq[a] = make_double4(r[0], r[1], r[2], r[6]);
+  vel[3 * a] = r[3]; vel[3 * a + 1] = r[4]; vel[3 * a + 2] = r[5];
+  for (int k = 0; k < 5; k++) { s_hist[5 * a + k] = r[7 + k]; t_hist[5 * a + k] = r[12 + k]; }
+  const long long tt = __double_as_longlong(r[17]);
+  const int lt = (int)(tt & 0xffffffffLL);
+  tag[a] = (int)(tt >> 32); ltype[a] = lt;
+  type[a] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
+}
+
+// borders: (atom i, image shift) pairs inside the ghost shell of each rank.  COUNT: per-rank totals; FILL: sort keys
+// (rank << 40 | atom << 5 | shift code) at an atomic cursor (sorted afterwards: deterministic order).
+struct Shell { double cg[3]; int grid[3]; int m[3]; };
+template <bool FILL>
+__global__ void k_border_emit(int n, BoxD b, Shell S, int me, const double4* __restrict__ xq, int* __restrict__ cnt_to,
+                              unsigned long long* __restrict__ keys, int* __restrict__ cursor) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  for (int sz = -S.m[2]; sz <= S.m[2]; sz++) {
+    const double l2 = l[2] + sz;
+    for (int bz = 0; bz < S.grid[2]; bz++) {
+      const double lo2 = (double)bz / S.grid[2], hi2 = bz == S.grid[2] - 1 ? 1.0 : (double)(bz + 1) / S.grid[2];
+      if (!(l2 >= lo2 - S.cg[2] && l2 < hi2 + S.cg[2])) continue;
+      for (int sy = -S.m[1]; sy <= S.m[1]; sy++) {
+        const double l1 = l[1] + sy;
+        for (int by = 0; by < S.grid[1]; by++) {
+          const double lo1 = (double)by / S.grid[1], hi1 = by == S.grid[1] - 1 ? 1.0 : (double)(by + 1) / S.grid[1];
+          if (!(l1 >= lo1 - S.cg[1] && l1 < hi1 + S.cg[1])) continue;
+          for (int sx = -S.m[0]; sx <= S.m[0]; sx++) {
+            const double l0 = l[0] + sx;
+            for (int bx = 0; bx < S.grid[0]; bx++) {
+              const double lo0 = (double)bx / S.grid[0], hi0 = bx == S.grid[0] - 1 ? 1.0 : (double)(bx + 1) / S.grid[0];
+              if (!(l0 >= lo0 - S.cg[0] && l0 < hi0 + S.cg[0])) continue;
+              const int r = (bz * S.grid[1] + by) * S.grid[0] + bx;
+              if (r == me && !sx && !sy && !sz) continue;          // the atom itself
+              if (FILL) {
+                const int code = ((sz + 2) * 5 + (sy + 2)) * 5 + (sx + 2);   // shifts in -2..2
+                keys[atomicAdd(cursor, 1)] = ((unsigned long long)r << 40) | ((unsigned long long)(unsigned)i << 7) | (unsigned)code;
+              } else {
+                atomicAdd(&cnt_to[r], 1);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+__global__ void k_border_pack(int m, const unsigned long long* __restrict__ keys, const double4* __restrict__ xq,
+                              const int* __restrict__ tag, const int* __restrict__ ltype, int* __restrict__ sendlist,
+                              double* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const unsigned long long k = keys[e];
+  const int i = (int)((k >> 7) & 0xffffffffULL), code = (int)(k & 127);
+  sendlist[e] = i;
+  const double4 p = xq[i];
+  double* r = out + (size_t)kGRec * e;
+  r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
+  r[4] = __longlong_as_double(((long long)tag[i] << 32) | (unsigned int)ltype[i]);
+  r[5] = (double)code;
+}
+__global__ void k_border_unpack(int nghost, int n, BoxD b, const double* __restrict__ rec, const int* __restrict__ map, int maplen,
+                                double4* __restrict__ xq, int* __restrict__ tag, int* __restrict__ ltype, int* __restrict__ type,
+                                int* __restrict__ shift) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const double* r = rec + (size_t)kGRec * g;
+  const int code = (int)r[5];
+  const int sx = code % 5 - 2, sy = (code / 5) % 5 - 2, sz = code / 25 - 2;
+  double d[3];
+  shift_vec(b, sx, sy, sz, d);
+  xq[n + g] = make_double4(r[0] + d[0], r[1] + d[1], r[2] + d[2], r[3]);
+  const long long tt = __double_as_longlong(r[4]);
+  const int lt = (int)(tt & 0xffffffffLL);
+  tag[n + g] = (int)(tt >> 32); ltype[n + g] = lt;
+  type[n + g] = (lt >= 1 && lt < maplen) ? map[lt] : -1;
+  shift[3 * g] = sx; shift[3 * g + 1] = sy; shift[3 * g + 2] = sz;
+}
+}  // namespace
+
+// all-gather one row of W ints per rank -> host table[a * W + b] (what rank a reports about rank b)
+static std::vector<int> gather_table(Dist& D, const int* row_dev, cudaStream_t st) {
+  const int W = D.world;
+  D.cnt_all_d.resize((size_t)W * W);
+  RXB_NCCL(ncclAllGather(row_dev, D.cnt_all_d.p, W, ncclInt, D.comm, st));
+  std::vector<int> all((size_t)W * W);
+  RXB_CUDA(cudaMemcpyAsync(all.data(), D.cnt_all_d.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  RXB_CUDA(cudaStreamSynchronize(st));
+  return all;
+}
+
 void System::dist_exchange() {
   Dist& D = *dist_;
+  const int W = D.world, me = D.rank;
   BoxD b;
   memcpy(b.h, box.h, sizeof(b.h));
   memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
-  // 1. counts
-  int my = n;
-  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
-  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  int mx = 0;
-  long long total = 0;
-  for (int c : D.counts) { mx = std::max(mx, c); total += c; }
-  // slots per rank: generous, so that the post-migration local counts fit as well (growth triggers a re-gather next time)
-  int want = std::max(mx, (int)((total / D.world) + (total / D.world) / 4 + 64));
-  if (want > D.chunk) D.chunk = want + want / 8;
-  int chunk = D.chunk;
-  int nslots = chunk * D.world;
-  // 2. migration records of the wrapped local atoms
-  D.rec_send.resize((size_t)chunk * kRec);
-  D.rec_all.resize((size_t)nslots * kRec);
-  k_wrap_pack<<<nblk(n), 256, 0, st_>>>(n, b, xq.p, v_d.p, q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, D.rec_send.p);
-  RXB_NCCL(ncclAllGather(D.rec_send.p, D.rec_all.p, (size_t)chunk * kRec, ncclDouble, D.comm, st_));
-  // 3. brick and shell in lamda space
-  Brick k;
-  const double cut = cutneigh();
-  k.cg[0] = cut * sqrt(b.h_inv[0] * b.h_inv[0] + b.h_inv[5] * b.h_inv[5] + b.h_inv[4] * b.h_inv[4]);
-  k.cg[1] = cut * sqrt(b.h_inv[1] * b.h_inv[1] + b.h_inv[3] * b.h_inv[3]);
-  k.cg[2] = cut * b.h_inv[2];
-  for (int t = 0; t < 3; t++) { k.lo[t] = D.lo[t]; k.hi[t] = D.hi[t]; k.m[t] = (int)ceil(k.cg[t]) + 1; }
-  // 4. new local atoms: flag, scan, fill (stable => deterministic order)
-  D.flag.resize(nslots + 1); D.off.resize(nslots + 1);
-  k_flag_locals<<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec_all.p, b, k, D.flag.p);
-  size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, nslots + 1, st_);
-  D.temp.resize(need + 16);
-  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
-  long long newn = 0;
-  RXB_CUDA(cudaMemcpyAsync(&newn, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  // (a brick may end up with more atoms than a slab slot holds: the slab is re-sized below, identically on every rank,
-  // from the all-gathered post-migration counts - no rank-local abort that would leave the others in a collective)
-  n = (int)newn;
-  N = n;
-  ensure_atom_capacity();
-  v_d.resize_keep((size_t)3 * std::max(n, chunk));
-  q_s_hist.resize((size_t)5 * std::max(n, chunk)); q_t_hist.resize((size_t)5 * std::max(n, chunk));
-  q_s_hist.n = (size_t)5 * n; q_t_hist.n = (size_t)5 * n;
   if (map_d.n != ff.map.size()) {
     map_d.resize(ff.map.size());
     RXB_CUDA(cudaMemcpyAsync(map_d.p, ff.map.data(), ff.map.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
   }
-  xq.resize_keep(std::max((size_t)n, (size_t)chunk)); xq.n = n;
-  tag.resize_keep(std::max((size_t)n, (size_t)chunk)); ltype_d.resize_keep(std::max((size_t)n, (size_t)chunk));
-  type.resize_keep(std::max((size_t)n, (size_t)chunk));
-  k_fill_locals<<<nblk(nslots), 256, 0, st_>>>(nslots, D.flag.p, D.off.p, D.rec_all.p, map_d.p, (int)ff.map.size(), xq.p, v_d.p,
-                                              q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, type.p);
-  // 5. post-migration layout: all-gather the new counts and a compact (x,y,z,q,tag|type) record of the NEW local atoms;
-  //    ghosts are selected from that, so their source slots refer to the layout every later halo exchange uses and come
-  //    out sorted by slot, i.e. grouped by source rank (what the peer-to-peer plan relies on)
-  my = n;
-  RXB_CUDA(cudaMemcpyAsync(D.counts_d.p + D.rank, &my, sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_NCCL(ncclAllGather(D.counts_d.p + D.rank, D.counts_d.p, 1, ncclInt, D.comm, st_));
-  RXB_CUDA(cudaMemcpyAsync(D.counts.data(), D.counts_d.p, D.world * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  {
-    int mx2 = 0;
-    for (int c : D.counts) mx2 = std::max(mx2, c);
-    if (mx2 > D.chunk) {           // same numbers on every rank, hence the same new slab size everywhere
-      D.chunk = mx2 + mx2 / 8 + 64;
-      chunk = D.chunk; nslots = chunk * D.world;
-      D.flag.resize(nslots + 1); D.off.resize(nslots + 1);
-      cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, nslots + 1, st_);
-      D.temp.resize(need + 16);
-      xq.resize_keep((size_t)chunk); tag.resize_keep((size_t)chunk); ltype_d.resize_keep((size_t)chunk); type.resize_keep((size_t)chunk);
-      xq.n = n;
-      v_d.resize_keep((size_t)3 * chunk);
-      { const size_t keep = q_s_hist.n; q_s_hist.resize_keep((size_t)5 * chunk); q_t_hist.resize_keep((size_t)5 * chunk); q_s_hist.n = keep; q_t_hist.n = keep; }
-    }
+  // ---------------- exchange: migrants to their new owners ----------------
+  const int n_old = n;
+  D.rec_send.resize((size_t)std::max(n_old, 1) * kRec);
+  D.dest.resize(std::max(n_old, 1)); D.flag.resize(n_old + 1); D.off.resize(n_old + 1);
+  D.cnt_d.resize(W);
+  RXB_CUDA(cudaMemsetAsync(D.cnt_d.p, 0, W * sizeof(int), st_));
+  k_mig_classify<<<nblk(n_old + 1), 256, 0, st_>>>(n_old, b, D.grid[0], D.grid[1], D.grid[2], me, xq.p, v_d.p, q_s_hist.p,
+                                                  q_t_hist.p, tag.p, ltype_d.p, D.rec_send.p, D.dest.p, D.flag.p, D.cnt_d.p);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, n_old + 1, st_);
+  D.temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, n_old + 1, st_);
+  const std::vector<int> mig = gather_table(D, D.cnt_d.p, st_);          // mig[a * W + b]: atoms leaving a for b
+  int nleave = 0, narr = 0;
+  std::vector<int> lv_off(W + 1, 0), ar_off(W + 1, 0);
+  for (int r = 0; r < W; r++) {
+    lv_off[r + 1] = lv_off[r] + mig[(size_t)me * W + r];
+    ar_off[r + 1] = ar_off[r] + mig[(size_t)r * W + me];
   }
-  D.rec2_send.resize((size_t)chunk * 5); D.rec2_all.resize((size_t)nslots * 5);
-  k_pack_compact<<<nblk(n), 256, 0, st_>>>(n, xq.p, tag.p, ltype_d.p, D.rec2_send.p);
-  RXB_NCCL(ncclAllGather(D.rec2_send.p, D.rec2_all.p, (size_t)chunk * 5, ncclDouble, D.comm, st_));
-  k_ghosts_dist<false, 5, 3, 4><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec2_all.p, b, k, n, map_d.p,
-                                                                  (int)ff.map.size(), D.flag.p, nullptr, nullptr, nullptr,
-                                                                  nullptr, nullptr, nullptr, nullptr);
-  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, nslots + 1, st_);
-  long long nghost = 0;
-  RXB_CUDA(cudaMemcpyAsync(&nghost, D.off.p + nslots, sizeof(long long), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  N = n + (int)nghost;
+  nleave = lv_off[W]; narr = ar_off[W];
+  const int nstay = n_old - nleave;
+  D.mig_send.resize((size_t)std::max(nleave, 1) * kRec); D.mig_recv.resize((size_t)std::max(narr, 1) * kRec);
+  if (nleave > 0) {
+    D.keys.resize(nleave); D.keys2.resize(nleave);
+    k_mig_keys<<<nblk(n_old), 256, 0, st_>>>(n_old, me, D.dest.p, D.off.p, D.keys.p);
+    size_t ns = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, ns, D.keys.p, D.keys2.p, nleave, 0, 40, st_);
+    D.temp.resize(ns + 16);
+    cub::DeviceRadixSort::SortKeys(D.temp.p, ns, D.keys.p, D.keys2.p, nleave, 0, 40, st_);
+    k_mig_pack<<<nblk(nleave), 256, 0, st_>>>(nleave, D.keys2.p, D.rec_send.p, D.mig_send.p);
+  }
+  if (nleave > 0 || narr > 0) {
+    RXB_NCCL(ncclGroupStart());
+    for (int r = 0; r < W; r++) {
+      if (r == me) continue;
+      const int ns_ = mig[(size_t)me * W + r], nr_ = mig[(size_t)r * W + me];
+      if (ns_ > 0) RXB_NCCL(ncclSend(D.mig_send.p + (size_t)kRec * lv_off[r], (size_t)kRec * ns_, ncclDouble, r, D.comm, st_));
+      if (nr_ > 0) RXB_NCCL(ncclRecv(D.mig_recv.p + (size_t)kRec * ar_off[r], (size_t)kRec * nr_, ncclDouble, r, D.comm, st_));
+    }
+    RXB_NCCL(ncclGroupEnd());
+  }
+  n = nstay + narr;
+  N = n;
   ensure_atom_capacity();
-  xq.resize_keep(std::max((size_t)N, (size_t)chunk)); xq.n = N;
-  D.gsrc.resize(std::max<size_t>(nghost, 1));
-  ghost_shift.resize(std::max<size_t>(3 * nghost, 3));
+  xq.resize_keep((size_t)std::max(n, 1)); xq.n = n;
+  tag.resize_keep((size_t)std::max(n, 1)); ltype_d.resize_keep((size_t)std::max(n, 1)); type.resize_keep((size_t)std::max(n, 1));
+  v_d.resize_keep((size_t)3 * std::max(n, 1));
+  q_s_hist.resize_keep((size_t)5 * std::max(n, 1)); q_t_hist.resize_keep((size_t)5 * std::max(n, 1));
+  // (stayers only move DOWN in the arrays and every source record was packed into rec_send first: in-place is safe)
+  k_mig_fill<<<nblk(n_old + narr), 256, 0, st_>>>(n_old, nstay, narr, D.flag.p, D.off.p, D.rec_send.p, D.mig_recv.p, map_d.p,
+                                                 (int)ff.map.size(), xq.p, v_d.p, q_s_hist.p, q_t_hist.p, tag.p, ltype_d.p, type.p);
+  q_s_hist.n = (size_t)5 * n; q_t_hist.n = (size_t)5 * n;
+
+  // ---------------- borders: ghost shells ----------------
+  Shell S;
+  const double cut = cutneigh();
+  S.cg[0] = cut * sqrt(b.h_inv[0] * b.h_inv[0] + b.h_inv[5] * b.h_inv[5] + b.h_inv[4] * b.h_inv[4]);
+  S.cg[1] = cut * sqrt(b.h_inv[1] * b.h_inv[1] + b.h_inv[3] * b.h_inv[3]);
+  S.cg[2] = cut * b.h_inv[2];
+  for (int t = 0; t < 3; t++) {
+    S.grid[t] = D.grid[t];
+    S.m[t] = (int)ceil(S.cg[t]);
+    if (S.m[t] > 2) throw std::runtime_error("rxb dist: the box is thinner than half the ghost cut-off in one direction");
+  }
+  RXB_CUDA(cudaMemsetAsync(D.cnt_d.p, 0, W * sizeof(int), st_));
+  k_border_emit<false><<<nblk(n), 256, 0, st_>>>(n, b, S, me, xq.p, D.cnt_d.p, nullptr, nullptr);
+  const std::vector<int> all = gather_table(D, D.cnt_d.p, st_);           // all[a * W + b]: ghosts a sends to b
+  D.need_from.assign(W, 0); D.send_to.assign(W, 0); D.goff.assign(W + 1, 0); D.soff.assign(W + 1, 0);
+  std::vector<int> emit_off(W + 1, 0);                                    // offsets in the sorted emission list (self included)
+  for (int r = 0; r < W; r++) {
+    D.need_from[r] = all[(size_t)r * W + me];
+    D.send_to[r] = (r == me) ? 0 : all[(size_t)me * W + r];
+    D.goff[r + 1] = D.goff[r] + D.need_from[r];
+    D.soff[r + 1] = D.soff[r] + D.send_to[r];
+    emit_off[r + 1] = emit_off[r] + all[(size_t)me * W + r];
+  }
+  const int nemit = emit_off[W], nself = all[(size_t)me * W + me], nghost = D.goff[W];
+  D.nsend = D.soff[W];
+  D.keys.resize(std::max(nemit, 1)); D.keys2.resize(std::max(nemit, 1));
+  D.cursor.resize(1);
+  RXB_CUDA(cudaMemsetAsync(D.cursor.p, 0, sizeof(int), st_));
+  k_border_emit<true><<<nblk(n), 256, 0, st_>>>(n, b, S, me, xq.p, nullptr, D.keys.p, D.cursor.p);
+  if (nemit > 0) {
+    size_t ns = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, ns, D.keys.p, D.keys2.p, nemit, 0, 48, st_);
+    D.temp.resize(ns + 16);
+    cub::DeviceRadixSort::SortKeys(D.temp.p, ns, D.keys.p, D.keys2.p, nemit, 0, 48, st_);
+  }
+  // pack every emitted pair (sorted: by rank, atom, image); emit_list[e] = source atom of emission e
+  D.emit_list.resize(std::max(nemit, 1));
+  D.ghost_send.resize((size_t)kGRec * std::max(nemit, 1)); D.ghost_recv.resize((size_t)kGRec * std::max(nghost, 1));
+  if (nemit > 0) k_border_pack<<<nblk(nemit), 256, 0, st_>>>(nemit, D.keys2.p, xq.p, tag.p, ltype_d.p, D.emit_list.p, D.ghost_send.p);
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == me) continue;
+    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.ghost_send.p + (size_t)kGRec * emit_off[r], (size_t)kGRec * D.send_to[r], ncclDouble, r, D.comm, st_));
+    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(D.ghost_recv.p + (size_t)kGRec * D.goff[r], (size_t)kGRec * D.need_from[r], ncclDouble, r, D.comm, st_));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  if (nself > 0)
+    RXB_CUDA(cudaMemcpyAsync(D.ghost_recv.p + (size_t)kGRec * D.goff[me], D.ghost_send.p + (size_t)kGRec * emit_off[me],
+                             (size_t)kGRec * nself * sizeof(double), cudaMemcpyDeviceToDevice, st_));
+  // send lists of the per-step halos: the emission list without the self segment; greq = sources of my own images
+  D.sendlist.resize(std::max(D.nsend, 1));
+  D.greq.resize(std::max(nghost, 1));
+  for (int r = 0; r < W; r++) {
+    const int cnt = all[(size_t)me * W + r];
+    if (cnt == 0) continue;
+    if (r == me) RXB_CUDA(cudaMemcpyAsync(D.greq.p + D.goff[me], D.emit_list.p + emit_off[r], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToDevice, st_));
+    else RXB_CUDA(cudaMemcpyAsync(D.sendlist.p + D.soff[r], D.emit_list.p + emit_off[r], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToDevice, st_));
+  }
+  N = n + nghost;
+  ensure_atom_capacity();
+  ghost_shift.resize(std::max<size_t>((size_t)3 * nghost, 3));
   ghost_owner.resize(std::max<size_t>(nghost, 1));
-  k_ghosts_dist<true, 5, 3, 4><<<nblk(nslots + 1), 256, 0, st_>>>(nslots, chunk, D.counts_d.p, D.rec2_all.p, b, k, n, map_d.p,
-                                                                 (int)ff.map.size(), nullptr, D.off.p, xq.p, tag.p, ltype_d.p,
-                                                                 type.p, D.gsrc.p, ghost_shift.p);
-  dist_build_plan();
-  D.xq_all.resize((size_t)nslots); D.d_all.resize((size_t)nslots);
-  D.f_all.resize((size_t)3 * nslots); D.f_recv.resize((size_t)3 * chunk);
-  kernel_launches += 6;
+  if (nghost > 0)
+    k_border_unpack<<<nblk(nghost), 256, 0, st_>>>(nghost, n, b, D.ghost_recv.p, map_d.p, (int)ff.map.size(), xq.p, tag.p, ltype_d.p,
+                                                  type.p, ghost_shift.p);
+  D.sendbuf.resize((size_t)4 * std::max(D.nsend, 1));
+  D.recvbuf.resize((size_t)3 * std::max(D.nsend, 1));
+  // peer exchange: where my values land in each consumer's halo (its ghost offset for source = me), and whether every
+  // rank's ghosts fit the halo windows (decided from the all-gathered table: the same answer on every rank)
+  {
+    std::vector<int> dst_off(W, 0);
+    long long max_ghosts = 0;
+    for (int p = 0; p < W; p++) {
+      long long tot = 0;
+      for (int r = 0; r < W; r++) {
+        if (r == me) dst_off[p] = (int)tot;
+        tot += all[(size_t)r * W + p];
+      }
+      max_ghosts = std::max(max_ghosts, tot);
+    }
+    D.peer_plan_ok = D.peer_ok && max_ghosts <= (long long)D.cap_g;
+    D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
+    RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
+    RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+    RXB_CUDA(cudaStreamSynchronize(st_));          // dst_off is a local that dies with this scope
+  }
+  D.recv_bytes_last = ((size_t)narr * kRec + (size_t)(nghost - nself) * kGRec) * sizeof(double);
+  kernel_launches += 10;
   RXB_CUDA(cudaGetLastError());
 }
 
 namespace {
-__global__ void k_plan_count(int nghost, int chunk, const int* __restrict__ gsrc, int* __restrict__ greq, int* __restrict__ cnt) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nghost) return;
-  const int s = gsrc[g];
-  greq[g] = s % chunk;
-  atomicAdd(&cnt[s / chunk], 1);
-}
 template <int W>
 __global__ void k_pack(int m, const int* __restrict__ list, const double* __restrict__ src, double* __restrict__ dst) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,59 +539,6 @@ __global__ void k_self_reverse_f(int n, int g0, int g1, const int* __restrict__ 
 }
 }  // namespace
 
-// Build the peer-to-peer plan: who needs which of my atoms (one small all-gather of counts + one grouped send/recv of
-// index lists per reneighbouring).
-void System::dist_build_plan() {
-  Dist& D = *dist_;
-  const int W = D.world, nghost = N - n;
-  D.cnt_d.resize(W); D.cnt_all_d.resize((size_t)W * W);
-  D.greq.resize(std::max(nghost, 1));
-  RXB_CUDA(cudaMemsetAsync(D.cnt_d.p, 0, W * sizeof(int), st_));
-  if (nghost > 0) k_plan_count<<<nblk(nghost), 256, 0, st_>>>(nghost, D.chunk, D.gsrc.p, D.greq.p, D.cnt_d.p);
-  RXB_NCCL(ncclAllGather(D.cnt_d.p, D.cnt_all_d.p, W, ncclInt, D.comm, st_));
-  std::vector<int> all((size_t)W * W);
-  RXB_CUDA(cudaMemcpyAsync(all.data(), D.cnt_all_d.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
-  D.need_from.assign(W, 0); D.send_to.assign(W, 0); D.goff.assign(W + 1, 0); D.soff.assign(W + 1, 0);
-  for (int r = 0; r < W; r++) {
-    D.need_from[r] = all[(size_t)D.rank * W + r];      // row a = what rank a needs from each rank
-    D.send_to[r] = (r == D.rank) ? 0 : all[(size_t)r * W + D.rank];
-    D.goff[r + 1] = D.goff[r] + D.need_from[r];
-    D.soff[r + 1] = D.soff[r] + D.send_to[r];
-  }
-  D.nsend = D.soff[W];
-  // peer exchange: where my values land in each consumer's halo (its ghost offset for source = me), and whether every
-  // rank's ghosts fit the halo windows (decided from the all-gathered table: the same answer on every rank)
-  {
-    std::vector<int> dst_off(W, 0);
-    long long max_ghosts = 0;
-    for (int p = 0; p < W; p++) {
-      long long tot = 0;
-      for (int r = 0; r < W; r++) {
-        if (r == D.rank) dst_off[p] = (int)tot;
-        tot += all[(size_t)p * W + r];
-      }
-      max_ghosts = std::max(max_ghosts, tot);
-    }
-    D.peer_plan_ok = D.peer_ok && max_ghosts <= (long long)D.cap_g;
-    D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
-    RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
-    RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
-    RXB_CUDA(cudaStreamSynchronize(st_));          // dst_off is a local that dies with this scope
-  }
-  D.sendlist.resize(std::max(D.nsend, 1));
-  D.sendbuf.resize((size_t)4 * std::max(D.nsend, 1));
-  D.recvbuf.resize((size_t)3 * std::max(D.nsend, 1));
-  RXB_NCCL(ncclGroupStart());
-  for (int r = 0; r < W; r++) {
-    if (r == D.rank) continue;
-    if (D.need_from[r] > 0) RXB_NCCL(ncclSend(D.greq.p + D.goff[r], D.need_from[r], ncclInt, r, D.comm, st_));
-    if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.sendlist.p + D.soff[r], D.send_to[r], ncclInt, r, D.comm, st_));
-  }
-  RXB_NCCL(ncclGroupEnd());
-  kernel_launches++;
-}
-
 // forward: my atoms -> peers' ghost slots (width doubles per atom), then my own periodic images
 template <int WD>
 static void p2p_forward(System& s, Dist& D, double* vec, int n, cudaStream_t st) {
@@ -540,14 +562,8 @@ void System::dist_forward_xq() {
   memcpy(b.h, box.h, sizeof(b.h));
   memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
   const int nghost = N - n;
-  if (D.p2p) {
-    p2p_forward<4>(*this, D, reinterpret_cast<double*>(xq.p), n, st_);
-    if (nghost > 0) k_shift_ghosts<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, ghost_shift.p, xq.p);
-    kernel_launches++;
-    return;
-  }
-  RXB_NCCL(ncclAllGather(xq.p, D.xq_all.p, (size_t)D.chunk * 4, ncclDouble, D.comm, st_));
-  if (nghost > 0) k_ghost_x_from_all<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, D.gsrc.p, ghost_shift.p, D.xq_all.p, xq.p);
+  p2p_forward<4>(*this, D, reinterpret_cast<double*>(xq.p), n, st_);
+  if (nghost > 0) k_shift_ghosts<<<nblk(nghost), 256, 0, st_>>>(n, nghost, b, ghost_shift.p, xq.p);
   kernel_launches++;
 }
 
@@ -834,29 +850,21 @@ void System::dist_peer_check() {
 
 void System::dist_reverse_f() {
   Dist& D = *dist_;
-  if (D.p2p) {
-    const int W = D.world;
-    RXB_NCCL(ncclGroupStart());
-    for (int r = 0; r < W; r++) {
-      if (r == D.rank) continue;
-      if (D.need_from[r] > 0) RXB_NCCL(ncclSend(f.p + (size_t)3 * (n + D.goff[r]), (size_t)3 * D.need_from[r], ncclDouble, r, D.comm, st_));
-      if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.recvbuf.p + (size_t)3 * D.soff[r], (size_t)3 * D.send_to[r], ncclDouble, r, D.comm, st_));
-    }
-    RXB_NCCL(ncclGroupEnd());
-    if (D.nsend > 0) k_unpack_add_f<<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, D.recvbuf.p, f.p);
-    const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
-    if (g1 > g0) k_self_reverse_f<<<nblk(g1 - g0), 256, 0, st_>>>(n, g0, g1, D.greq.p, f.p);
-    kernel_launches += 2;
-    return;
+  const int W = D.world;
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    if (D.need_from[r] > 0) RXB_NCCL(ncclSend(f.p + (size_t)3 * (n + D.goff[r]), (size_t)3 * D.need_from[r], ncclDouble, r, D.comm, st_));
+    if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.recvbuf.p + (size_t)3 * D.soff[r], (size_t)3 * D.send_to[r], ncclDouble, r, D.comm, st_));
   }
-  const size_t nslots = (size_t)D.chunk * D.world;
-  RXB_CUDA(cudaMemsetAsync(D.f_all.p, 0, 3 * nslots * sizeof(double), st_));
-  k_scatter_f<<<nblk(N), 256, 0, st_>>>(n, N - n, D.rank * D.chunk, D.gsrc.p, f.p, D.f_all.p);
-  RXB_NCCL(ncclReduceScatter(D.f_all.p, D.f_recv.p, (size_t)3 * D.chunk, ncclDouble, ncclSum, D.comm, st_));
-  RXB_CUDA(cudaMemcpyAsync(f.p, D.f_recv.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToDevice, st_));
-  kernel_launches++;
+  RXB_NCCL(ncclGroupEnd());
+  if (D.nsend > 0) k_unpack_add_f<<<nblk(D.nsend), 256, 0, st_>>>(D.nsend, D.sendlist.p, D.recvbuf.p, f.p);
+  const int g0 = D.goff[D.rank], g1 = D.goff[D.rank + 1];
+  if (g1 > g0) k_self_reverse_f<<<nblk(g1 - g0), 256, 0, st_>>>(n, g0, g1, D.greq.p, f.p);
+  kernel_launches += 2;
 }
 
-void System::dist_set_p2p(bool on) { if (dist_) dist_->p2p = on; }
+// (kept for ABI compatibility: the whole-slab all-gather transport of round 1 is gone, halos are always point to point)
+void System::dist_set_p2p(bool) {}
 
 }  // namespace rxb

@@ -207,13 +207,14 @@ class System {
   void dist_allreduce_max_int(int* dev_ptr, size_t count);
   void dist_allgather_int(const int* send, int* recv, size_t count_per_rank);
   void dist_exchange();          // exchange + borders at reneighbouring
-  void dist_build_plan();        // peer-to-peer send lists for the boundary exchange
+
   void dist_set_p2p(bool on);    // false: whole-slab all-gather halos (debug / comparison)
   void dist_forward_xq();        // ghosts <- owners (x + image shift, q)
   void dist_forward2(double2* vec);
   void dist_forward2_dots(double2* vec, double* dots);   // halo of vec + all-reduce of 4 dot products in one exchange
   void dist_reverse_f();
-  size_t slab() const;           // elements every all-gathered local array must be able to hold
+  size_t slab() const;           // (0: no all-gathered arrays any more)
+  size_t dist_last_recv_bytes() const;   // payload received at the last reneighbouring (migrants + ghost records)
 
   // ---- analysis outputs (rxb_analysis.cu): fix reax/c/bonds table, fix reax/c/species molecules ----
   struct BondTable { int n = 0, entries = 0, max_nb = 0; };
