@@ -162,10 +162,11 @@ int rxb_species_cluster(rxb_handle* h, int* cluster_of_local);
 int rxb_species_log_size(rxb_handle* h);
 int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* composition, long cap);
 
-/* CUDA-event timers on the launch stream (no sync inside a step).  out26 = 13 accumulated ms then 13 call counts for:
+/* CUDA-event timers on the launch stream (no sync inside a step).  out28 = 14 accumulated ms then 14 call counts for:
  * neigh, qeq far+H, qeq CG (whole solve), bond list, BO, bonded (all), nonbonded, dBond, SpMV (per launch), hbond items,
- * angle+torsion items, multi-body, enumeration.  enable: 1 reset+start, 0 stop, -1 read only. */
-int rxb_profile(rxb_handle* h, int enable, double* out26);
+ * angle+torsion items, multi-body, enumeration, SpMV boundary-row half (multi-GPU split).  enable: 1 reset+start, 0 stop,
+ * -1 read only. */
+int rxb_profile(rxb_handle* h, int enable, double* out28);
 /* Tests only: shrink the capacities of the growable lists (directed bonds, angle / torsion / hydrogen-bond work lists) and
  * of the per-atom shared-memory staging (bonds per atom, strong bonds per centre) so that every grow-and-replay branch
  * of the force phase can be driven on an ordinary cell (values <= 0 are left alone); read the current values back. */

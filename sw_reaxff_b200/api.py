@@ -319,13 +319,18 @@ class Rxb:
         self._chk(self.lib.rxb_profiler_range(int(start)))
 
     PHASES = ["neigh", "qeq_farH", "qeq_cg", "bond_list", "bond_orders", "bonded", "nonbonded", "dbond", "spmv",
-              "hbond_items", "angle_torsion_items", "multi_body", "enum"]
+              "hbond_items", "angle_torsion_items", "multi_body", "enum", "spmv_boundary"]
 
     def profile(self, enable=None):
-        """-> dict phase -> (total ms, calls) accumulated since the last profile(1)."""
-        out = np.zeros(26)
+        """-> dict phase -> (total ms, calls) accumulated since the last profile(1).  "spmv" = whole SpMVs: in multi-GPU
+        runs a SpMV is two launches (interior rows while the halo is in flight, then boundary rows); the time of the
+        second ("spmv_boundary") is added to "spmv" here, the call count is the number of SpMVs."""
+        nph = len(self.PHASES)
+        out = np.zeros(2 * nph)
         self._chk(self.lib.rxb_profile(self.h, -1 if enable is None else int(enable), _p(out)))
-        return {nm: (out[k], int(out[13 + k])) for k, nm in enumerate(self.PHASES)}
+        d = {nm: (out[k], int(out[nph + k])) for k, nm in enumerate(self.PHASES)}
+        d["spmv"] = (d["spmv"][0] + d["spmv_boundary"][0], d["spmv"][1])
+        return d
 
     def h_format(self):
         b = C.c_int(); nm = C.create_string_buffer(128)

@@ -676,8 +676,9 @@ PeerView peer_view(const Dist& D) {
   return P;
 }
 
-// vec: S-space double2 vector whose ghosts are refreshed (null: pure reduction); dots[ndots]: partial sums -> totals
-void peer_exchange(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
+// vec: S-space double2 vector whose ghosts are refreshed (null: pure reduction); dots[ndots]: partial sums -> totals.
+// push and pull are separate calls so that work which does not need the ghosts can be enqueued between them.
+void peer_push(System& s, Dist& D, double2* vec, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
   D.seq++;
   const int par = (int)(D.seq & 1);
   const PeerView P = peer_view(D);
@@ -687,12 +688,81 @@ void peer_exchange(System& s, Dist& D, double2* vec, int nghost, const int* gs_p
   k_peer_push<<<std::max(1, std::min(148, (work + 255) / 256)), 256, 0, st>>>(P, par, D.seq, nsend, D.send_s.p, D.soff_d.p,
                                                                            D.dst_off_d.p, vec, g0, g1, gs_pos, D.self_s.p,
                                                                            ndots, dots, D.done_d.p);
+  s.kernel_launches++;
+}
+void peer_pull(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
+  const int par = (int)(D.seq & 1);
+  const PeerView P = peer_view(D);
+  const int g0 = vec ? D.goff[D.rank] : 0, g1 = vec ? D.goff[D.rank + 1] : 0;
   const int ng = vec ? nghost : 0;
   k_peer_pull<<<std::max(1, std::min(296, (ng + 255) / 256)), 256, 0, st>>>(P, par, D.seq, ng, g0, g1, gs_pos, vec, ndots, dots,
                                                                          D.peer_err_d.p);
-  s.kernel_launches += 2;
+  s.kernel_launches++;
+}
+void peer_exchange(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
+  peer_push(s, D, vec, gs_pos, dots, ndots, st);
+  peer_pull(s, D, vec, nghost, gs_pos, dots, ndots, st);
+}
+
+// interior rows (every column local or an own periodic image for the whole reneighbouring interval) first, boundary rows
+// after: a row is interior when its atom sits at least the ghost cut-off inside every face the brick shares with ANOTHER rank
+__global__ void k_row_class(int n, BoxD b, double lo0, double lo1, double lo2, double hi0, double hi1, double hi2, double c0,
+                            double c1, double c2, int m0, int m1, int m2, const int* __restrict__ rowpos,
+                            const double4* __restrict__ xqs, long long* __restrict__ flag) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  if (r == n) { flag[n] = 0; return; }
+  const double4 p = xqs[rowpos[r]];
+  double l[3];
+  x2lamda(b, p.x, p.y, p.z, l);
+  const bool in0 = !m0 || (l[0] - lo0 >= c0 && hi0 - l[0] >= c0);
+  const bool in1 = !m1 || (l[1] - lo1 >= c1 && hi1 - l[1] >= c1);
+  const bool in2 = !m2 || (l[2] - lo2 >= c2 && hi2 - l[2] >= c2);
+  flag[r] = (in0 && in1 && in2) ? 1 : 0;
+}
+__global__ void k_row_order(int n, long long n_int, const long long* __restrict__ flag, const long long* __restrict__ scan,
+                            int* __restrict__ rowlist) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const long long before = scan[r];                       // interior rows before r
+  rowlist[flag[r] ? before : n_int + (r - before)] = r;
 }
 }  // namespace
+
+void System::dist_classify_rows() {
+  Dist& D = *dist_;
+  n_interior_ = 0;
+  if (!(D.peer_ok && D.peer_plan_ok) || n == 0) return;
+  BoxD b;
+  memcpy(b.h, box.h, sizeof(b.h));
+  memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
+  const double cut = cutneigh();
+  const double c0 = cut * sqrt(b.h_inv[0] * b.h_inv[0] + b.h_inv[5] * b.h_inv[5] + b.h_inv[4] * b.h_inv[4]);
+  const double c1 = cut * sqrt(b.h_inv[1] * b.h_inv[1] + b.h_inv[3] * b.h_inv[3]);
+  const double c2 = cut * b.h_inv[2];
+  D.flag.resize(n + 1); D.off.resize(n + 1);
+  q_rowlist.resize(n);
+  // a dimension with one brick has only this rank's own periodic images beyond its faces: no constraint there
+  k_row_class<<<nblk(n + 1), 256, 0, st_>>>(n, b, D.lo[0], D.lo[1], D.lo[2], D.hi[0], D.hi[1], D.hi[2], c0, c1, c2, D.grid[0] > 1,
+                                           D.grid[1] > 1, D.grid[2] > 1, rowpos.p, xqs.p, D.flag.p);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, D.flag.p, D.off.p, n + 1, st_);
+  D.temp.resize(need + 16);
+  cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, n + 1, st_);
+  long long n_int = 0;
+  RXB_CUDA(cudaMemcpyAsync(&n_int, D.off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  k_row_order<<<nblk(n), 256, 0, st_>>>(n, n_int, D.flag.p, D.off.p, q_rowlist.p);
+  // every rank takes the split path or none does not matter for correctness (push/pull are the same calls either way);
+  // a split with a tiny interior is not worth its extra launch
+  n_interior_ = n_int * 20 >= n ? (int)n_int : 0;
+  kernel_launches += 3;
+}
+
+void System::dist_push2(double2* vecS, double* dots, int ndots) { peer_push(*this, *dist_, vecS, gs_pos.p, dots, ndots, st_); }
+void System::dist_pull2(double2* vecS, double* dots, int ndots) {
+  peer_pull(*this, *dist_, vecS, N - n, gs_pos.p, dots, ndots, st_);
+}
 
 // Map every rank's window (CUDA IPC; all ranks are processes on one node).  Any failure on any rank (no peer access,
 // IPC disabled in the container, more than 16 ranks) leaves the NCCL send/recv path in place on ALL ranks.

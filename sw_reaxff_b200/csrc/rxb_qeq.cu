@@ -64,16 +64,19 @@ __global__ void k_forward2S(int nghost, const int* __restrict__ gs_pos, const in
   }
 }
 
-// y[row] = eta x[rowpos[row]] + sum_k H_k x[col_k] for the local rows; gate != null: skip when neither system is active
+// y[row] = eta x[rowpos[row]] + sum_k H_k x[col_k] for the rows rowlist[r0 .. r1) (rowlist == null: rows r0 .. r1);
+// gate != null: skip when neither system is active
 template <bool PACKED>
 __global__ void __launch_bounds__(kWarps * 32)
-k_spmv2(int n, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk, const int* __restrict__ col,
-        const double* __restrict__ val, double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row,
-        const double2* __restrict__ x, double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
+k_spmv2(int r0, int r1, const int* __restrict__ rowlist, int stride, const int* __restrict__ num,
+        const unsigned long long* __restrict__ hpk, const int* __restrict__ col, const double* __restrict__ val, double inv_quant,
+        const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
+        double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
   if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-  for (int i = wg; i < n; i += nwg) {
+  for (int t = r0 + wg; t < r1; t += nwg) {
+    const int i = rowlist ? rowlist[t] : t;
     const long long beg = (long long)i * stride;
     const int m = num[i];
     double ax = 0, ay = 0;
@@ -311,7 +314,20 @@ void System::qeq_iteration(int it) {
                                                  q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
   kernel_launches++;
   const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
-  // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange
+  // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange.  Multi-GPU with
+  // peer windows: the values are pushed, the INTERIOR rows (no column owned by another rank) are multiplied while they
+  // fly, then the ghosts are pulled and the boundary rows follow - the overlap the reference gets from
+  // sparse_matvec_C_spawn ... sparse_matvec_C_join around its MPI calls (fix_qeq_reax_sunway.cpp:1130-1143).
+  // Measured at N = 2 (A/B on one box, profiles/r02_split_ab.txt): the split costs more than the wait it hides - two launches
+  // per SpMV add two ramp-up/drain phases (+10 % SpMV time), the row list another 2 % - so it is OFF unless RXB_SPLIT=1.
+  if (qeq_split_rows() && dist_ && dist_peer_active() && n_interior_ > 0) {
+    double* dots = Q->dots[(it + 1) % 3];
+    dist_push2(q_d.p, dots, 4);
+    qeq_spmv(q_d.p, q_q.p, true, par_next, 0, n_interior_);
+    dist_pull2(q_d.p, dots, 4);
+    qeq_spmv(q_d.p, q_q.p, true, par_next, n_interior_, n);
+    return;
+  }
   if (dist_) dist_forward2_dots(q_d.p, Q->dots[(it + 1) % 3]);
   else qeq_forward_S(q_d.p);
   qeq_spmv(q_d.p, q_q.p, true, par_next);
@@ -326,11 +342,14 @@ void System::qeq_forward_S(double2* vecS) {
   }
 }
 
-void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity) {
+void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity, int r0, int r1) {
   const QeqDev* Q = reinterpret_cast<const QeqDev*>(q_scal.p);
-  const int ts = tick(StepTimers::SPMV);
+  if (r1 < 0) r1 = n;
+  if (r1 <= r0) return;
+  const int* rowlist = (qeq_split_rows() && dist_ && n_interior_ > 0) ? q_rowlist.p : nullptr;   // interior rows first, then boundary rows
+  const int ts = tick(r0 > 0 ? StepTimers::SPMV_B : StepTimers::SPMV);
   // one row per warp, blocks retire continuously: lets the high-priority bond-chain stream interleave on every SM
-  const int grid = std::max(1, (n + kWarps - 1) / kWarps);
+  const int grid = std::max(1, (r1 - r0 + kWarps - 1) / kWarps);
   // RXB_SPMV_SMEM=<bytes> (development knob): an unused dynamic shared-memory request per CTA caps the CTAs resident per SM,
   // i.e. how many warp slots the SpMV leaves to the bonded chain running beside it on the second stream
   static const int smem = [] {
@@ -343,11 +362,11 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity)
     return b;
   }();
   if (h_packed_)
-    k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(n, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_, rowpos.p,
-                                                    q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+    k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_,
+                                                    rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
   else
-    k_spmv2<false><<<grid, kWarps * 32, smem, st_>>>(n, vl.stride, far_num.p, nullptr, far_idx.p, H_val.p, 1.0, rowpos.p,
-                                                     q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+    k_spmv2<false><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, nullptr, far_idx.p, H_val.p, 1.0,
+                                                     rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
   tock(ts);
   kernel_launches++;
 }

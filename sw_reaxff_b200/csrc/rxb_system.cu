@@ -628,7 +628,7 @@ void System::build_neighbors() {
     RXB_CUDA(cudaMemsetAsync(disp2_d.p, 0, sizeof(double), st_));
   }
   x_build.n = (size_t)N;
-  if (dist_) dist_sorted_maps();
+  if (dist_) { dist_sorted_maps(); dist_classify_rows(); }
   // bond candidates for all rows (ghosts too): (reach of the longest possible bond <= bond_cut) + skin
   const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -98,7 +99,9 @@ struct Box {  // LAMMPS triclinic box, lo = 0
 struct Dist;  // multi-GPU state, rxb_dist.cu
 
 struct StepTimers {
-  enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, SPMV, HBOND, VALTOR, MULTI, ENUM, NUM };
+  // SPMV_B: the boundary-row half of a split SpMV (multi-GPU: interior rows run while the halo is in flight); its time
+  // belongs to the SPMV launch of the same iteration, which alone counts the calls
+  enum { NEIGH, QEQ_H, QEQ_CG, BONDS, BO, BONDED, NONB, DBOND, SPMV, HBOND, VALTOR, MULTI, ENUM, SPMV_B, NUM };
   double ms[NUM] = {0};
   long calls[NUM] = {0};
 };
@@ -141,7 +144,15 @@ class System {
   void qeq_settle_now() { (void)qeq_settle(); }
   void qeq_iteration(int it);
   void qeq_forward_S(double2* vecS);    // ghosts of an S-space vector <- owners (periodic images / peer ranks)
-  void qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity);
+  void qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity, int r0 = 0, int r1 = -1);   // rows r0 .. r1 of the row list
+  // multi-GPU: rows whose columns are all local (or own periodic images) come first in q_rowlist: they are multiplied while
+  // the halo of the search direction is in flight (rxb_dist.cu dist_classify_rows)
+  DBuf<int> q_rowlist;
+  int n_interior_ = 0;
+  static bool qeq_split_rows() { static const bool on = getenv("RXB_SPLIT") && atoi(getenv("RXB_SPLIT")) != 0; return on; }
+  void dist_classify_rows();
+  void dist_push2(double2* vecS, double* dots, int ndots);
+  void dist_pull2(double2* vecS, double* dots, int ndots);
   void qeq_finish(bool shift_hist);
   bool qeq_poll();
   void plugin_qeq_pre_force(bool wait_for_convergence = true);   // C ABI entry: QEq with the bonded chain started on the second stream
