@@ -127,6 +127,10 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
 /* per atom 16 doubles: total_bo,Delta_boc,Deltap,Deltap_boc,Delta,Delta_e,Delta_val,vlpex,nlp,Delta_lp,Clp,dDelta_lp,
  * nlp_temp,Delta_lp_temp,dDelta_lp_temp,CdDelta */
 int rxb_get_workspace(rxb_handle* h, double* w16);
+/* hydrogen-bond candidates of the last far-list sweep (the hbond list of Init_Forces_noQEq_HB_Full_C, reaxc_forces_sw64.c:
+ * 787-863, which this path never stores as a list): pairs2[2k], pairs2[2k+1] = H atom, acceptor-type partner within
+ * hbond_cut; unordered.  n_out = their number. */
+int rxb_get_hbond_pairs(rxb_handle* h, int* n_out, int* pairs2, int cap);
 /* far list == H pattern: num[nlocal], and for row i the entries off_verlet[i] .. +num[i] of idx/val */
 int rxb_get_far(rxb_handle* h, int* num, int* idx, double* val);
 /* ---- optional: page-lock the caller's per-atom arrays (atom->x, the force buffer) so that rxb_set_positions /

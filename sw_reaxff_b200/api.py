@@ -17,7 +17,7 @@ SYMBOLS = [
     "rxb_dist_unique_id", "rxb_dist_init", "rxb_dist_set_p2p", "rxb_md_get_tags",
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
-    "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps",
+    "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -301,6 +301,13 @@ class Rxb:
         fld = np.zeros((max(nb, 1), 31))
         self._chk(self.lib.rxb_get_bonds(self.h, _p(bs), _p(bc), _p(nbr), _p(sym), _p(fld)))
         return bs, bc, nbr[:nb], sym[:nb], fld[:nb]
+
+    def hbond_pairs(self):
+        n = C.c_int()
+        self._chk(self.lib.rxb_get_hbond_pairs(self.h, C.byref(n), None, 0))
+        p = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+        self._chk(self.lib.rxb_get_hbond_pairs(self.h, C.byref(n), _p(p), n.value))
+        return p[:n.value]
 
     def workspace(self):
         N = int(self.counts()[1])

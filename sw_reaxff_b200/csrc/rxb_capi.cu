@@ -320,6 +320,21 @@ int rxb_get_bonds(rxb_handle* h, int* b_start, int* b_cnt, int* nbr, int* sym, d
   });
 }
 
+int rxb_get_hbond_pairs(rxb_handle* h, int* n_out, int* pairs2, int cap) {
+  return guard([&] {
+    System& s = *h->sys;
+    int cnt[4] = {0, 0, 0, 0};
+    d2h(cnt, s.it_count.p, (size_t)4, s.stream());
+    const int m = cnt[2] < s.cap_hb ? cnt[2] : s.cap_hb;
+    if (n_out) *n_out = m;
+    if (pairs2 && m > 0) {
+      std::vector<int4> items((size_t)m);
+      d2h(items.data(), s.it_hb.p, (size_t)m, s.stream());
+      for (int k = 0; k < m && k < cap; k++) { pairs2[2 * k] = items[k].x; pairs2[2 * k + 1] = items[k].y; }
+    }
+  });
+}
+
 int rxb_get_workspace(rxb_handle* h, double* w16) {
   return guard([&] {
     System& s = *h->sys;

@@ -456,7 +456,9 @@ void System::qeq_pre_force(bool wait_for_convergence) {
   //  * plugin call (the caller wants matvecs back) / first solve: the host polls after the predicted count, then every
   //    few iterations.
   const int cap = qeq_imax + 1;
-  const int target = std::min(cap, qeq_predict_ > 0 ? qeq_predict_ + 2 : 8);
+  // prediction = the largest count of the last reneighbouring cycle + a margin (counts wander by a few iterations from
+  // step to step; a gated iteration costs ~7 us, an under-prediction a replay of the whole force phase)
+  const int target = std::min(cap, qeq_predict_ > 0 ? qeq_predict_ + 3 + qeq_predict_ / 8 : 8);
   qeq_it_ = 0;
   for (int it = 1; it <= target; it++) { qeq_iteration(it); qeq_it_ = it; }
   qeq_unsettled_ = false;
@@ -465,14 +467,21 @@ void System::qeq_pre_force(bool wait_for_convergence) {
       const int more = std::min(cap - qeq_it_, qeq_check_every);
       for (int k = 0; k < more; k++) { qeq_iteration(qeq_it_ + 1); qeq_it_++; }
     }
-    qeq_predict_ = std::max(matvecs_s, matvecs_t);
-    qeq_iters_total += qeq_predict_;
+    qeq_record_iterations();
   } else {
     qeq_unsettled_ = true;          // settled by qeq_settle() at the end-of-step synchronisation
   }
   qeq_finish(true);
   qeq_ran_this_step_ = true;
   tock(t_QEQ_CG);
+}
+
+void System::qeq_record_iterations() {
+  const int it = std::max(matvecs_s, matvecs_t);
+  qeq_iters_total += it;
+  qeq_recent_[qeq_recent_at_++ % 5] = it;
+  qeq_predict_ = 0;
+  for (int k = 0; k < 5; k++) qeq_predict_ = std::max(qeq_predict_, qeq_recent_[k]);
 }
 
 // End-of-step: has the solve that was enqueued without polling converged?  (Called right after the end-of-step
@@ -488,9 +497,8 @@ bool System::qeq_settle() {
     for (int k = 0; k < more; k++) { qeq_iteration(qeq_it_ + 1); qeq_it_++; }
     continued = true;
   }
-  qeq_predict_ = std::max(matvecs_s, matvecs_t);
-  qeq_iters_total += qeq_predict_;
-  if (continued) qeq_finish(false);
+  qeq_record_iterations();
+  if (continued) { qeq_finish(false); qeq_replays++; }
   return continued;
 }
 

@@ -263,7 +263,12 @@ System::System(int device) : device_(device) {
   {
     int lo = 0, hi = 0;  // numerically lower = higher priority
     RXB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    RXB_CUDA(cudaStreamCreateWithPriority(&st2_, cudaStreamNonBlocking, hi));
+    // Where the bonded chain runs (RXB_CHAIN_MODE, A/B in profiles/r02_chain_mode_ab.txt): 2 (default) = from the start of
+    // the step on a LOW-priority stream, so it fills what the bandwidth-bound CG solve leaves idle instead of displacing
+    // SpMV CTAs; 0 = the same on a high-priority stream (round 1: 0.2 ms/step slower); 1 = after the CG solve, beside the
+    // nonbonded kernel (no gain).
+    chain_mode_ = getenv("RXB_CHAIN_MODE") ? atoi(getenv("RXB_CHAIN_MODE")) : 2;
+    RXB_CUDA(cudaStreamCreateWithPriority(&st2_, cudaStreamNonBlocking, chain_mode_ == 2 ? lo : hi));
   }
   RXB_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   RXB_CUDA(cudaEventCreateWithFlags(&ev_far_, cudaEventDisableTiming));
@@ -849,13 +854,15 @@ void System::overlapped_front(bool wait_for_convergence) {
   RXB_CUDA(cudaMemsetAsync(CdDelta.p, 0, (size_t)N * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(en_d.p, 0, E_NUM * sizeof(double), st_));
   RXB_CUDA(cudaMemsetAsync(virial_d.p, 0, 6 * sizeof(double), st_));
-  RXB_CUDA(cudaEventRecord(ev_fork_, st_));
-  RXB_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
-  launch_bond_list(*this, v, dp_, st2_);
-  launch_bond_orders(*this, v, dp_, st2_);
-  launch_bonded_part1(*this, v, dp_, st2_);
-  if (g_odbg.on) cudaEventRecord(g_odbg.e[1], st2_);   // end of bond list + BO + multi
-  hook_after_far_ = true;
+  if (chain_mode_ != 1) {
+    RXB_CUDA(cudaEventRecord(ev_fork_, st_));
+    RXB_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+    launch_bond_list(*this, v, dp_, st2_);
+    launch_bond_orders(*this, v, dp_, st2_);
+    launch_bonded_part1(*this, v, dp_, st2_);
+    if (g_odbg.on) cudaEventRecord(g_odbg.e[1], st2_);   // end of bond list + BO + multi
+    hook_after_far_ = true;
+  }
   chain_inflight_ = true;
   qeq_pre_force(wait_for_convergence);   // K-farH, then after_far_hook() enqueues the rest of the chain on st2_, then CG
   if (g_odbg.on) cudaEventRecord(g_odbg.e[3], st_);    // end of CG
@@ -872,6 +879,15 @@ void System::overlapped_back(bool eflag, bool vflag) {
   chain_inflight_ = false;
   qeq_ran_this_step_ = false;
   update_shadow(st_);                    // no-op unless rxb_set_charges replaced the charges after the QEq hook (xqs carries q)
+  if (chain_mode_ == 1) {                // the whole chain beside the nonbonded kernel instead of beside the CG solve
+    RXB_CUDA(cudaEventRecord(ev_fork_, st_));
+    RXB_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+    launch_bond_list(*this, v, dp_, st2_);
+    launch_bond_orders(*this, v, dp_, st2_);
+    launch_bonded_part1(*this, v, dp_, st2_);
+    launch_bonded_part2(*this, v, dp_, st2_);
+    RXB_CUDA(cudaEventRecord(ev_join_, st2_));
+  }
   launch_nonbonded(*this, v, dp_, ev, st_);
   if (g_odbg.on) cudaEventRecord(g_odbg.e[5], st_);    // end of nonbonded
   RXB_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
@@ -902,7 +918,7 @@ void System::overlapped_back(bool eflag, bool vflag) {
 }
 
 void System::md_force_overlapped(bool ev) {
-  overlapped_front(false);
+  overlapped_front(getenv("RXB_QEQ_WAIT") != nullptr);
   overlapped_back(ev, ev);
 }
 
@@ -921,7 +937,7 @@ void System::md_force() {
   if (overlap && qeq_on && !profile) {
     md_force_overlapped(ev);
   } else {
-    if (qeq_on) qeq_pre_force(false);
+    if (qeq_on) qeq_pre_force(getenv("RXB_QEQ_WAIT") != nullptr);
     compute(ev, ev);
   }
   const int nghost = N - n;

@@ -159,6 +159,7 @@ class System {
   void plugin_compute(bool eflag, bool vflag);
   int matvecs_s = 0, matvecs_t = 0;
   long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
+  long qeq_replays = 0;      // solves that had to be continued after the end-of-step check (force phase replayed)
 
   // storage format of the off-diagonal H entries (rxb_dev.cuh): packed 8-byte words unless exact is requested, the taper
   // does not start at 0 (values then leave [0, bound]) or the atom count exceeds the 22-bit column field
@@ -322,6 +323,7 @@ class System {
   cudaStream_t st_ = nullptr, st2_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_far_ = nullptr, ev_join_ = nullptr;
   bool hook_after_far_ = false;
+  int chain_mode_ = 0;
   void after_far_hook();
   void md_force_overlapped(bool ev);
   void overlapped_front(bool wait_for_convergence);
@@ -341,7 +343,10 @@ class System {
   bool shadow_valid_ = false;            // xf / xs / xqs hold the current positions
   bool h_packed_ = false;
   double h_quant_ = 1.0;
-  int qeq_predict_ = 0, qeq_it_ = 0;     // iterations of the previous solve; loop index of the last launched sweep
+  int qeq_predict_ = 0, qeq_it_ = 0;     // largest iteration count of the last 5 solves; loop index of the last launched sweep
+  int qeq_recent_[5] = {0, 0, 0, 0, 0};
+  unsigned qeq_recent_at_ = 0;
+  void qeq_record_iterations();
   bool qeq_unsettled_ = false;
   double last_tap_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_swb_ = 0.0;   // what K-farH was last launched with (replays)
   cudaEvent_t run_ev_[2] = {nullptr, nullptr};

@@ -527,3 +527,33 @@ def test_qeq_async_enqueue_settles_in_pair_compute():
     assert r.qeq_matvecs() == mv_ref
     assert np.abs(r.get_charges() - q_ref).max() < 1e-12
     assert np.abs(f - f_ref).max() < 1e-9 * np.abs(f_ref).max()
+
+
+def test_hbond_candidate_set_exact(case):
+    """a5: the hydrogen-bond list is never stored on the device; its (H atom, acceptor-type partner within hbond_cut)
+    pairs are emitted by the far-list sweep.  As a SET they must equal the oracle's hbond list
+    (Init_Forces_noQEq_HB_Full_C semantics, reaxc_forces_sw64.c:787-863)."""
+    o, r, n = case["o"], case["r"], case["cfg"]["n"]
+    Hindex, hs, he, nbr = o.hbonds()
+    want = set()
+    for i in range(n):
+        h = Hindex[i]
+        if h >= 0:
+            for p in range(hs[h], he[h]):
+                want.add((i, int(nbr[p])))
+    got = r.hbond_pairs()
+    got_set = set(map(tuple, got.tolist()))
+    assert len(got_set) == len(got)              # no duplicates
+    assert got_set == want and len(want) > 0
+
+
+def test_workspace_columns_not_materialised_are_covered_by_their_consumers(case):
+    """rxb_get_workspace leaves columns 5 (Delta_e), 10 (Clp), 12 (nlp_temp) and 14 (dDelta_lp_temp) at zero: the fused
+    multi-body kernel keeps them in registers (they are one-line functions of the stored columns, reaxc_multi_body_sw64.c:
+    60-120).  What consumes them - e_lp, e_ov, e_un and the CdDelta they feed - is compared with the oracle here at 1e-9."""
+    o, res = case["o"], case["res"]
+    eo, _ = o.energies()
+    assert abs(res["pvector"][1] - (eo[1] + eo[2])) <= 1e-9 * max(abs(eo[1] + eo[2]), 1.0)     # e_ov + e_un
+    assert abs(res["pvector"][2] - eo[3]) <= 1e-9 * max(abs(eo[3]), 1.0)                       # e_lp
+    wg = case["r"].workspace()
+    assert rel(wg[:, 15], o.cddelta()) < 1e-9
