@@ -41,6 +41,11 @@ int rxb_pair_extract(rxb_handle* h, const char* name, double* out, int ntypes);
 /* ---- fix qeq/reax <nevery> <swa> <swb> <tol> reax/c   (fix_qeq_reax_sunway.cpp:76-99); neighbor <skin> bin */
 int rxb_fix_qeq(rxb_handle* h, double swa, double swb, double tolerance, int max_iter);
 int rxb_neighbor_skin(rxb_handle* h, double skin);
+/* fix qeq/reax ... <param file> instead of `reax/c` (FixQEqReaxSunway::pertype_parameters, fix_qeq_reax_sunway.cpp:198-245):
+ * chi, eta, gamma per LAMMPS type, arrays of ntypes + 1 doubles (index 0 unused), used by the charge equilibration only
+ * (H shielding, diagonal, right-hand side); the pair style keeps its force-field values.  ntypes = 0 or NULL arrays
+ * return to the pair style's values. */
+int rxb_fix_qeq_params(rxb_handle* h, int ntypes, const double* chi, const double* eta, const double* gamma);
 
 /* canonical flat dump of every parsed parameter (parity tests); returns the count, writes min(count, cap) values */
 long rxb_params_dump(rxb_handle* h, double* out, long cap);
@@ -158,6 +163,10 @@ int rxb_bond_table_get(rxb_handle* h, int* tag, int* type, int* off, int* nbr_ta
  * a host-driven loop calls rxb_species_step(ntimestep) after initial_integrate instead.
  * Result: nmole molecules ordered by their smallest atom ID; composition[m*ntypes + t] = atoms of type t+1 in molecule m
  * (summed over ranks when decomposed); cluster_of_local = molecule number 1..nmole per local atom. */
+/* ---- compute SPEC/ATOM, abo columns (compute_spec_atom_sunway.cpp:35-170 reading PairReaxCSunway::tmpbo, filled by FindBond,
+ * pair_reaxc_sunway.cpp:1170-1198): one sample, abo12[i*12 + k] = bond order (>= 0.10) of the k-th bond of local atom i to
+ * a partner of higher index, in bond-row order, zero padded.  (The q/x/v columns of the compute are host data.) */
+int rxb_spec_atom_abo(rxb_handle* h, double* abo12);
 int rxb_species_config(rxb_handle* h, int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms,
                        long ntimestep_now /* <0: the resident run's own counter */, int* reneighbor_reset);
 int rxb_species_step(rxb_handle* h, long ntimestep, int* found);

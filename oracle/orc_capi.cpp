@@ -3,6 +3,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -329,6 +330,16 @@ int orc_omp_threads(int set) {
   (void)set;
   return 1;
 #endif
+}
+
+// fix qeq/reax <param file>: chi / eta / gamma per ELEMENT index (the tests map LAMMPS types 1:1 onto elements), as
+// FixQEqReaxSunway::pertype_parameters + init_shielding would hold them (fix_qeq_reax_sunway.cpp:198-245, 440-454)
+void orc_qeq_override(void* hh, const double* chi, const double* eta, const double* gamma) {
+  QEq& q = ((OrcHandle*)hh)->md.qeq;
+  const int nt = (int)q.chi.size();
+  for (int i = 0; i < nt; i++) { q.chi[i] = chi[i]; q.eta[i] = eta[i]; q.gamma[i] = gamma[i]; }
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j < nt; j++) q.shld[(size_t)i * nt + j] = pow(q.gamma[i] * q.gamma[j], -1.5);
 }
 
 int orc_md_matvecs(void* hh, int which) { QEq& q = ((OrcHandle*)hh)->md.qeq; return which ? q.matvecs_t : q.matvecs_s; }

@@ -18,6 +18,7 @@ SYMBOLS = [
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
     "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
+    "rxb_fix_qeq_params", "rxb_spec_atom_abo",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -102,6 +103,14 @@ class Rxb:
 
     def fix_qeq(self, swa=0.0, swb=10.0, tol=1e-6, max_iter=200):
         self._chk(self.lib.rxb_fix_qeq(self.h, C.c_double(swa), C.c_double(swb), C.c_double(tol), int(max_iter)))
+
+    def fix_qeq_params(self, chi=None, eta=None, gamma=None):
+        """fix qeq/reax <param file>: chi/eta/gamma per LAMMPS type (arrays of ntypes + 1, index 0 unused); None = reax/c."""
+        if chi is None:
+            self._chk(self.lib.rxb_fix_qeq_params(self.h, 0, None, None, None))
+            return
+        chi = _f(chi); eta = _f(eta); gamma = _f(gamma)
+        self._chk(self.lib.rxb_fix_qeq_params(self.h, len(chi) - 1, _p(chi), _p(eta), _p(gamma)))
 
     def neighbor_skin(self, skin):
         self._chk(self.lib.rxb_neighbor_skin(self.h, C.c_double(skin)))
@@ -220,6 +229,12 @@ class Rxb:
         self._chk(self.lib.rxb_bond_table_get(self.h, _p(t["tag"]), _p(t["type"]), _p(t["off"]), _p(t["nbr"]), _p(t["bo"]),
                                               _p(t["abo"]), _p(t["nlp"]), _p(t["q"])))
         return t
+
+    def spec_atom_abo(self):
+        """compute SPEC/ATOM abo01..abo12: one sample [nlocal][12] of the bond orders FindBond would store."""
+        a = np.zeros((int(self.counts()[0]), 12))
+        self._chk(self.lib.rxb_spec_atom_abo(self.h, _p(a)))
+        return a
 
     def species_config(self, nevery, nrepeat, nfreq, natoms, ntypes=4, bocut=None, ntimestep=-1):
         """fix reax/c/species nevery nrepeat nfreq; bocut = (ntypes+1)^2 BOCut matrix (default 0.30).  Returns True

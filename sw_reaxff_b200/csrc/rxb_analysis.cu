@@ -246,6 +246,27 @@ int System::species_config(int nevery, int nrepeat, int nfreq, int ntypes, const
   return reset;
 }
 
+// compute SPEC/ATOM, the abo01..abo12 columns on their own (compute_spec_atom_sunway.cpp:142-170 reading
+// PairReaxCSunway::tmpbo, pair_reaxc_sunway.cpp:1170-1198): ONE sample of the bond orders (>= 0.10) of each local atom's
+// bonds to partners of higher index, in bond-row order, zero padded.  abo[nlocal][12].
+void System::spec_atom_abo(double* abo_host) {
+  RXB_CUDA(cudaSetDevice(device_));
+  const size_t m = (size_t)std::max(n, 1) * kMaxSpecBond;
+  DBuf<int> ids;
+  DBuf<double> acc;
+  ids.resize(m); acc.resize(m);
+  RXB_CUDA(cudaMemsetAsync(acc.p, 0, m * sizeof(double), st_));
+  sp_misc.resize(4);
+  RXB_CUDA(cudaMemsetAsync(sp_misc.p, 0, 4 * sizeof(int), st_));
+  if (n > 0) k_spec_sample<<<nblk(n), 256, 0, st_>>>(n, b_start.p, b_cnt.p, b_nbr.p, b_bo.p, ids.p, acc.p, sp_misc.p);
+  int err = 0;
+  RXB_CUDA(cudaMemcpyAsync(&err, sp_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+  if (n > 0) RXB_CUDA(cudaMemcpyAsync(abo_host, acc.p, (size_t)n * kMaxSpecBond * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  kernel_launches += 1;
+  if (err > kMaxSpecBond) throw std::runtime_error("Increase MAXSPECBOND in reaxc_defs_sunway.h");   // pair_reaxc_sunway.cpp:1194
+}
+
 void System::species_sample() {
   Species& S = species;
   const size_t m = (size_t)std::max(n, 1) * kMaxSpecBond;

@@ -188,6 +188,10 @@ int rxb_debug_set_caps(rxb_handle* h, int row_cap, int strong_cap, int cap_bonds
 int rxb_debug_get_caps(rxb_handle* h, int* out6) {
   return guard([&] { h->sys->debug_get_caps(out6); });
 }
+int rxb_spec_atom_abo(rxb_handle* h, double* abo12) { return guard([&] { h->sys->spec_atom_abo(abo12); }); }
+int rxb_fix_qeq_params(rxb_handle* h, int ntypes, const double* chi, const double* eta, const double* gamma) {
+  return guard([&] { h->sys->qeq_set_type_params(ntypes, chi, eta, gamma); });
+}
 int rxb_set_h_exact(rxb_handle* h, int on) { return guard([&] { h->sys->h_exact_request = on != 0; }); }
 int rxb_qeq_set_history(rxb_handle* h, const double* s_hist, const double* t_hist) {
   return guard([&] { h->sys->qeq_set_history(s_hist, t_hist); });

@@ -67,6 +67,10 @@ struct DevView {
   const float4* xs;      // N: fp32 shadow in S order (origin-relative x,y,z; element type bits in .w), refreshed every step
   double4* xqs;          // N: exact (x,y,z,q) in S order, refreshed every step (q again after the QEq solve)
   const int* type_s;     // N: element index in S order
+  // fix qeq/reax <param file> (fix_qeq_reax_sunway.cpp:198-245): chi / eta / gamma per LAMMPS type instead of the pair
+  // style's per-element values.  null = the "reax/c" mode.  shld_lt[(lt_i) * nlt + lt_j] = (gamma_i gamma_j)^-1.5
+  const int* ltype_s;    // N: LAMMPS type in S order
+  const double* shld_lt; const double* chi_lt; const double* eta_lt; int nlt;
   // far list == H sparsity pattern: r <= nonb_cut / swb, row r in slots vl_off[r] .. +far_num[r].  Two storage formats:
   //  packed (default): one 64-bit word per entry = column (22 bits) << 42 | round(H * 2^h_shift) (42-bit fixed point);
   //  exact           : int32 column in far_idx + fp64 value in H_val (systems beyond 2^22 atoms per GPU, parity tests).

@@ -109,6 +109,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
     // 2k + 1 - stride <= k: columns of this or an earlier chunk, all of which are in registers by then (the __syncwarp
     // orders the chunk's loads before its stores).
     const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
+    const int lti = v.shld_lt ? v.ltype_s[kself] : 0;
     const int i_atom = is_H ? v.row_atom[r] : 0;
     constexpr int kV = 2;
     for (int k0 = 0; k0 < num; k0 += 32 * kV) {
@@ -145,7 +146,7 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
               double T = qc.Tap[7] * r + qc.Tap[6];
               T = T * r + qc.Tap[5]; T = T * r + qc.Tap[4]; T = T * r + qc.Tap[3];
               T = T * r + qc.Tap[2]; T = T * r + qc.Tap[1]; T = T * r + qc.Tap[0];
-              const double x3 = r2 * r + shld[ti * nt + tj];
+              const double x3 = r2 * r + (v.shld_lt ? v.shld_lt[lti * v.nlt + v.ltype_s[j]] : shld[ti * nt + tj]);
               // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); the cube root differs by < 3e-13 relative
               val = T * kEvToKcal * fm::rcbrt_b(x3);
             }

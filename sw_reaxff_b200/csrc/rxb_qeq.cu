@@ -34,12 +34,16 @@ __global__ void k_qeq_init(int n, const int* __restrict__ rowpos, const int* __r
                            const int* __restrict__ type_s, const AtomPar* __restrict__ atom,
                            const double* __restrict__ s_hist, const double* __restrict__ t_hist, double2* __restrict__ x_row,
                            double2* __restrict__ xS, double2* __restrict__ b, double* __restrict__ Hdia_inv,
-                           double* __restrict__ eta_row, QeqDev* __restrict__ Q) {
+                           double* __restrict__ eta_row, QeqDev* __restrict__ Q, const int* __restrict__ ltype_s,
+                           const double* __restrict__ chi_lt, const double* __restrict__ eta_lt) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const int k = rowpos[j], i = row_atom[j];
     const int ti = type_s[k];
     double eta = 1.0, chi = 0.0;
-    if (ti >= 0) { eta = atom[ti].eta; chi = atom[ti].chi; }
+    if (ti >= 0) {
+      if (chi_lt) { const int lt = ltype_s[k]; eta = eta_lt[lt]; chi = chi_lt[lt]; }   // fix qeq/reax <param file>
+      else { eta = atom[ti].eta; chi = atom[ti].chi; }
+    }
     Hdia_inv[j] = 1. / eta;
     eta_row[j] = ti >= 0 ? eta : 0.0;
     b[j] = make_double2(-chi, -1.0);
@@ -434,7 +438,7 @@ void System::qeq_pre_force(bool wait_for_convergence) {
   q_scal.resize(sizeof(QeqDev) / sizeof(double) + 8);
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
   k_qeq_init<<<kVecBlocks, kVecThreads, 0, st_>>>(n, rowpos.p, row_atom.p, type_s.p, dp_.atom, q_s_hist.p, q_t_hist.p, q_x.p,
-                                                 q_xS.p, q_b.p, q_Hdia_inv.p, q_eta.p, Q);
+                                                 q_xS.p, q_b.p, q_Hdia_inv.p, q_eta.p, Q, v.ltype_s, v.chi_lt, v.eta_lt);
   qeq_forward_S(q_xS.p);
   qeq_spmv(q_xS.p, q_q.p, false, 0);
   k_pro1<<<kVecBlocks, kVecThreads, 0, st_>>>(n, rowpos.p, q_b.p, q_q.p, q_Hdia_inv.p, q_r.p, q_u.p, q_d.p);

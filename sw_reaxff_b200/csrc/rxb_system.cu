@@ -10,6 +10,8 @@
 #include <cmath>
 #include <unordered_map>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "rxb_system.h"
 
 namespace rxb {
@@ -81,14 +83,16 @@ __global__ void k_shadow(int N, const int* __restrict__ s2a, const double4* __re
 }
 
 // S-space maps of a fresh cell sort: inverse permutation, element per sorted position, "is a local atom" flags
-__global__ void k_sorted_maps(int N, int n, const int* __restrict__ s2a, const int* __restrict__ type, int* __restrict__ a2s,
-                              int* __restrict__ type_s, long long* __restrict__ row_flag) {
+__global__ void k_sorted_maps(int N, int n, const int* __restrict__ s2a, const int* __restrict__ type,
+                              const int* __restrict__ ltype, int* __restrict__ a2s, int* __restrict__ type_s,
+                              int* __restrict__ ltype_s, long long* __restrict__ row_flag) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > N) return;
   if (k == N) { row_flag[N] = 0; return; }
   const int i = s2a[k];
   a2s[i] = k;
   type_s[k] = type[i];
+  ltype_s[k] = ltype[i];
   row_flag[k] = i < n ? 1 : 0;
 }
 __global__ void k_sorted_rows(int N, const int* __restrict__ s2a, const long long* __restrict__ row_flag,
@@ -297,8 +301,18 @@ double* System::pin(size_t doubles) {
   return h_pin_;
 }
 
+// NVTX ranges (RXB_NVTX=1) named after the reference's GPTL regions, so that an nsys / ncu timeline of this path reads like
+// the reference's own profile (gptl.h regions in pair_reaxc_sunway.cpp, reaxc_forces_sunway.cpp, fix_qeq_reax_sunway.cpp)
+static const char* const kNvtxNames[StepTimers::NUM] = {
+    "full_build_sunway", "compute H Full c", "CG (sparse matvec in for)", "reaxc init forces noqeq", "reaxc bond orders c",
+    "reaxc bonded forces", "reaxc vdw coul full c", "reaxc total force", "slave sparse matvec c", "reaxc hydrogen bonds c",
+    "reaxc valence angles c + torsion angles c", "reaxc atom energy and bonds c", "enumerate bonded work lists",
+    "slave sparse matvec c (boundary rows)"};
+static const bool g_nvtx = getenv("RXB_NVTX") && atoi(getenv("RXB_NVTX")) != 0;
+
 int System::tick(int which, cudaStream_t st) {
-  if (!profile) return -1;
+  if (g_nvtx) nvtxRangePushA(kNvtxNames[which]);
+  if (!profile) return g_nvtx ? -2 : -1;
   if (!st) st = st_;
   if (ev_used_ + 2 > ev_pool_.size()) {
     for (int k = 0; k < 64; k++) { cudaEvent_t e; RXB_CUDA(cudaEventCreate(&e)); ev_pool_.push_back(e); }
@@ -309,6 +323,7 @@ int System::tick(int which, cudaStream_t st) {
   return (int)ev_pending_.size() - 1;
 }
 void System::tock(int id, cudaStream_t st) {
+  if (g_nvtx) nvtxRangePop();
   if (id < 0) return;
   RXB_CUDA(cudaEventRecord(ev_pool_[ev_pending_[id].b], st ? st : st_));
 }
@@ -548,7 +563,8 @@ void System::build_sorted_space() {
   s2a.n = (size_t)N;
   if (N == 0) return;
   RXB_CUDA(cudaMemcpyAsync(s2a.p, cells_a_.sorted_idx.p, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, st_));
-  k_sorted_maps<<<nblk(N + 1), 256, 0, st_>>>(N, n, s2a.p, type.p, a2s.p, type_s.p, row_flag.p);
+  ltype_s.resize(NN);
+  k_sorted_maps<<<nblk(N + 1), 256, 0, st_>>>(N, n, s2a.p, type.p, ltype_d.p, a2s.p, type_s.p, ltype_s.p, row_flag.p);
   size_t need = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, row_flag.p, row_scan.p, N + 1, st_);
   scan_temp.resize(need + 16);
@@ -561,11 +577,28 @@ void System::build_sorted_space() {
   kernel_launches += 4;
 }
 
+// fix qeq/reax <param file>: chi, eta, gamma per LAMMPS type (index 1..ntypes; ntypes = 0 returns to the pair style's values)
+void System::qeq_set_type_params(int ntypes, const double* chi, const double* eta, const double* gamma) {
+  RXB_CUDA(cudaSetDevice(device_));
+  qeq_chi_lt.clear(); qeq_eta_lt.clear(); qeq_gamma_lt.clear();
+  if (ntypes <= 0 || !chi || !eta || !gamma) return;
+  const int nlt = ntypes + 1;
+  qeq_chi_lt.assign(chi, chi + nlt); qeq_eta_lt.assign(eta, eta + nlt); qeq_gamma_lt.assign(gamma, gamma + nlt);
+  std::vector<double> blob((size_t)2 * nlt + (size_t)nlt * nlt, 0.0);
+  for (int t = 1; t < nlt; t++) { blob[t] = chi[t]; blob[nlt + t] = eta[t]; }
+  for (int i = 1; i < nlt; i++)
+    for (int j = 1; j < nlt; j++) blob[2 * nlt + (size_t)i * nlt + j] = pow(gamma[i] * gamma[j], -1.5);   // init_shielding :440-454
+  qeq_lt_d.resize(blob.size());
+  RXB_CUDA(cudaMemcpy(qeq_lt_d.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+
 // H entry format for the current settings (see rxb_dev.cuh); (re)allocates the far-list storage of the chosen format
 void System::choose_h_format() {
   double shld_min = 1e300;
   for (int i = 0; i < ff.nt; i++)
     for (int j = 0; j < ff.nt; j++) shld_min = std::min(shld_min, pow(ff.atom[i].gamma * ff.atom[j].gamma, -1.5));
+  for (size_t i = 1; i < qeq_gamma_lt.size(); i++)           // fix qeq/reax <param file>: its gammas define the bound
+    for (size_t j = 1; j < qeq_gamma_lt.size(); j++) shld_min = std::min(shld_min, pow(qeq_gamma_lt[i] * qeq_gamma_lt[j], -1.5));
   const double bound = 14.4 / cbrt(shld_min > 0 ? shld_min : 1e-300);          // Tap in [0,1] when the taper starts at 0
   const bool packed = !h_exact_request && qeq_swa == 0.0 && N < (1 << 22) && bound > 0 && bound < 1e6 && std::isfinite(bound);
   h_packed_ = packed;
@@ -594,6 +627,12 @@ DevView System::view() {
   v.xq = xq.p; v.type = type.p; v.tag = tag.p; v.f = f.p; v.CdDelta = CdDelta.p;
   v.vl_off = vl.off.p; v.vl_idx = vl.idx.p; v.vl_cnt = vl.cnt.p; v.vl_stride = vl.stride;
   v.s2a = s2a.p; v.rowpos = rowpos.p; v.row_atom = row_atom.p; v.xs = xs.p; v.xqs = xqs.p; v.type_s = type_s.p;
+  v.ltype_s = ltype_s.p;
+  const bool par_file = !qeq_gamma_lt.empty();
+  v.nlt = par_file ? (int)qeq_gamma_lt.size() : 0;
+  v.shld_lt = par_file ? qeq_lt_d.p + 2 * v.nlt : nullptr;
+  v.chi_lt = par_file ? qeq_lt_d.p : nullptr;
+  v.eta_lt = par_file ? qeq_lt_d.p + v.nlt : nullptr;
   disp2_d.resize(1);
   v.vl_cnt_in = vl.cnt_in.p; v.disp2 = disp2_d.p; v.vl_cut_in = vl.cut_in;
   v.bc_off = bc.off.p; v.bc_idx = bc.idx.p; v.bc_cnt = bc.cnt.p;

@@ -164,6 +164,11 @@ class System {
   // storage format of the off-diagonal H entries (rxb_dev.cuh): packed 8-byte words unless exact is requested, the taper
   // does not start at 0 (values then leave [0, bound]) or the atom count exceeds the 22-bit column field
   bool h_exact_request = false;
+  // fix qeq/reax <param file>: per-LAMMPS-type chi / eta / gamma used by the QEq instead of the pair style's (empty = reax/c)
+  std::vector<double> qeq_chi_lt, qeq_eta_lt, qeq_gamma_lt;
+  DBuf<double> qeq_lt_d;     // [chi | eta | shld matrix]
+  DBuf<int> ltype_s;
+  void qeq_set_type_params(int ntypes, const double* chi, const double* eta, const double* gamma);
   int h_bytes_per_entry() const { return h_packed_ ? 8 : 12; }
   const char* h_format_name() const {
     return h_packed_ ? "22-bit column + 42-bit fixed-point value in one 64-bit word (8 B)" : "fp64 value + int32 column (12 B)";
@@ -248,6 +253,7 @@ class System {
   int species_config(int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms_total, long now = -1);
   bool species_step(long step);                // the post_integrate hook of timestep `step`; true when molecules were found
   void species_sample();
+  void spec_atom_abo(double* abo_host);    // compute SPEC/ATOM abo columns, one sample: [nlocal][12]
   void species_find();
   void species_get_cluster(int* cluster_of_local);   // 1..nmole per local atom (vector_atom of the reference fix)
   DBuf<int> bt_cnt, bt_off, bt_tag, sp_id, sp_edges, sp_edges_all, sp_parent, sp_flag, sp_molidx, sp_comp, sp_misc;

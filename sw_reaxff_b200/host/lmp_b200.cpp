@@ -30,6 +30,30 @@ extern "C" long rxh_run_script(const char* script, int nvars, const char* const*
   }
 }
 
+// runs a script and returns the per-atom array of compute `cid` as evaluated at the last thermo output step:
+// out[nlocal][ncols], returns nlocal * ncols (tests of the compute SPEC/ATOM style)
+extern "C" long rxh_run_script_compute(const char* script, int nvars, const char* const* names, const char* const* values,
+                                       int device, const char* cid, double* out, long cap, int* ncols, char* err, int errlen) {
+  try {
+    LAMMPS lmp;
+    lmp.cuda_device = device;
+    lmp.echo_thermo = false;
+    for (int i = 0; i < nvars; i++) lmp.vars[names[i]] = values[i];
+    lmp.file(script);
+    for (auto& c : lmp.computes) {
+      if (c->id != cid) continue;
+      const long m = (long)c->array.size();
+      if (ncols) *ncols = c->size_peratom_cols ? c->size_peratom_cols : 1;
+      for (long k = 0; k < m && k < cap; k++) out[k] = c->array[k];
+      return m;
+    }
+    throw std::runtime_error(std::string("no compute with ID ") + cid);
+  } catch (const std::exception& e) {
+    if (err && errlen > 0) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return -1;
+  }
+}
+
 // velocities that `velocity all create T seed` gives the atoms of a data file (tests feed them to the CPU oracle)
 extern "C" long rxh_velocities(const char* datafile, double T, long seed, double* v, long cap_atoms) {
   try {

@@ -255,7 +255,13 @@ void LAMMPS::one(const std::string& raw) {
     } else error->all(FLERR, "Illegal variable command");
   } else if (c == "units") { need(2); if (w[1] != "real") error->all(FLERR, "only units real are supported by this driver"); }
   else if (c == "atom_style") { need(2); if (w[1] != "charge") error->all(FLERR, "Pair style reax/c requires atom attribute q"); }
-  else if (c == "boundary" || c == "thermo_style" || c == "dump" || c == "dump_modify" || c == "compute" || c == "echo" || c == "log") {}
+  else if (c == "compute") {
+    need(4);
+    if (w[3] == "SPEC/ATOM" || w[3] == "SPEC/ATOM/b200" || w[3] == "reax/c/atom")
+      computes.emplace_back(new ComputeSpecAtomB200(this, (int)argv.size(), argv.data()));
+    // (any other compute style of the reference's script - its thermo-only `compute reax all pair reax/c` - is a no-op here)
+  }
+  else if (c == "boundary" || c == "thermo_style" || c == "dump" || c == "dump_modify" || c == "echo" || c == "log") {}
   else if (c == "lattice") {
     need(3);
     if (w[1] != "custom") error->all(FLERR, "only 'lattice custom' is supported by this driver");
@@ -439,6 +445,7 @@ void LAMMPS::setup() {
   pair->compute(ev, ev);
   comm->reverse_comm(*atom);
   for (auto& f : fixes) f->setup(ev);
+  for (auto& c : computes) { c->init(); c->compute_peratom(); }
   if (echo_thermo) printf("    Step           Temp             PotEng             TotEng\n");
   thermo_line(ev);
   setup_done_ = true;
@@ -484,7 +491,7 @@ void LAMMPS::iterate(long nsteps) {
     lap(6, t0);
     for (auto& f : fixes) f->final_integrate();
     for (auto& f : fixes) if (f->nevery > 0 && update->ntimestep % f->nevery == 0) f->end_of_step();
-    if (ev) thermo_line(ev);
+    if (ev) { for (auto& c : computes) c->compute_peratom(); thermo_line(ev); }
     lap(7, t0);
   }
 }

@@ -24,6 +24,7 @@ struct Error {
   [[noreturn]] void all(const char* file, int line, const std::string& msg) const {
     throw std::runtime_error("ERROR: " + msg + " (" + file + ":" + std::to_string(line) + ")");
   }
+  [[noreturn]] void one(const char* file, int line, const std::string& msg) const { all(file, line, msg); }   // single rank: same thing
   void warning(const char*, int, const std::string& msg) const { fprintf(stderr, "WARNING: %s\n", msg.c_str()); }
 };
 #define FLERR __FILE__, __LINE__
@@ -85,6 +86,18 @@ struct Fix {
   virtual void final_integrate() {}
 };
 
+struct Compute {                                  // per-atom computes only (what compute SPEC/ATOM is)
+  LAMMPS* lmp;
+  std::string id, style;
+  int size_peratom_cols = 0;                      // 0: vector_atom, else array_atom with this many columns
+  std::vector<double> array;                      // [nlocal][max(size_peratom_cols, 1)]
+  long invoked_peratom = -1;
+  explicit Compute(LAMMPS* l) : lmp(l) {}
+  virtual ~Compute() {}
+  virtual void init() {}
+  virtual void compute_peratom() = 0;
+};
+
 struct Pair {
   LAMMPS* lmp;
   double eng_vdwl = 0, eng_coul = 0, virial[6] = {0, 0, 0, 0, 0, 0};
@@ -112,6 +125,7 @@ struct LAMMPS {
   Error error_, *error = &error_;
   std::unique_ptr<Pair> pair;
   std::vector<std::unique_ptr<Fix>> fixes;
+  std::vector<std::unique_ptr<Compute>> computes;  // evaluated on thermo output steps (stand-in for dump / fix ave/atom consumers)
   int thermo_every = 0;
   int cuda_device = 0;
   bool echo_thermo = true;

@@ -153,6 +153,60 @@ void* PairReaxCB200::extract(const char* str, int& dim) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+ComputeSpecAtomB200::ComputeSpecAtomB200(LAMMPS* l, int narg, char** arg) : Compute(l) {
+  Error* error = lmp->error;
+  if (narg < 4) error->all(FLERR, "Illegal compute reax/c/atom command");
+  id = arg[0]; style = arg[2];
+  const int nvalues = narg - 3;
+  size_peratom_cols = nvalues == 1 ? 0 : nvalues;
+  static const char* plain[7] = {"q", "x", "y", "z", "vx", "vy", "vz"};
+  for (int iarg = 3; iarg < narg; iarg++) {
+    int code = -1;
+    for (int k = 0; k < 7; k++) if (!strcmp(arg[iarg], plain[k])) code = k;
+    if (code < 0 && !strncmp(arg[iarg], "abo", 3) && strlen(arg[iarg]) == 5) {
+      const int k = atoi(arg[iarg] + 3);
+      if (k >= 1 && k <= 24 && arg[iarg][3] >= '0' && arg[iarg][3] <= '2') code = 10 + (k - 1);
+    }
+    if (code < 0) error->all(FLERR, "Invalid keyword in compute reax/c/atom command");
+    codes.push_back(code);
+  }
+}
+
+void ComputeSpecAtomB200::init() {
+  reaxc = dynamic_cast<PairReaxCB200*>(lmp->pair.get());
+  if (!reaxc) lmp->error->all(FLERR, "Cannot use compute SPEC/ATOM without pair_style reax/c");
+}
+
+void ComputeSpecAtomB200::compute_peratom() {
+  Atom* atom = lmp->atom;
+  invoked_peratom = lmp->update->ntimestep;
+  const int n = atom->nlocal, nv = (int)codes.size();
+  array.assign((size_t)n * nv, 0.0);
+  bool want_abo = false, want_q = false;
+  for (int c : codes) { want_abo = want_abo || c >= 10; want_q = want_q || c == 0; }
+  std::vector<double> abo, q;
+  if (want_abo) {          // tmpbo of the pair style's last force evaluation (FindBond), MAXSPECBOND = 12 columns
+    abo.assign((size_t)n * 12, 0.0);
+    if (rxb_spec_atom_abo(reaxc->rxb, abo.data())) lmp->error->all(FLERR, rxb_last_error());
+  }
+  if (want_q) {            // the device holds the current charges
+    q.assign((size_t)atom->nall(), 0.0);
+    if (rxb_get_charges(reaxc->rxb, q.data())) lmp->error->all(FLERR, rxb_last_error());
+  }
+  for (int i = 0; i < n; i++)
+    for (int v = 0; v < nv; v++) {
+      const int c = codes[v];
+      double val = 0.0;
+      if (c == 0) val = q[i];
+      else if (c <= 3) val = atom->x[3 * i + (c - 1)];
+      else if (c <= 6) val = atom->v[3 * i + (c - 4)];
+      else if (c - 10 < 12) val = abo[(size_t)i * 12 + (c - 10)];
+      // (abo13..abo24 index past the reference's own tmpbo rows - MAXSPECBOND is 12 - and are reported as 0 here)
+      array[(size_t)i * nv + v] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 FixQEqReaxB200::FixQEqReaxB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
   Error* error = lmp->error;
   if (narg < 8 || narg > 9) error->all(FLERR, "Illegal fix qeq/reax command");
@@ -160,7 +214,7 @@ FixQEqReaxB200::FixQEqReaxB200(LAMMPS* l, int narg, char** arg) : Fix(l) {
   nevery = atoi(arg[3]);
   if (nevery <= 0) error->all(FLERR, "Illegal fix qeq/reax command");
   swa = atof(arg[4]); swb = atof(arg[5]); tolerance = atof(arg[6]);
-  if (strcmp(arg[7], "reax/c") != 0) error->all(FLERR, "fix qeq/reax: only the reax/c parameter source is supported by this build");
+  pertype_option = arg[7];          // "reax/c" or a parameter file (pertype_parameters, fix_qeq_reax_sunway.cpp:198-245)
   if (narg == 9 && strcmp(arg[8], "dual") != 0) error->all(FLERR, "Illegal fix qeq/reax command");
   // ("dual" is accepted: both solves always run fused here)
 }
@@ -174,6 +228,27 @@ void FixQEqReaxB200::init() {
   if (fabs(swa) > 0.01) error->warning(FLERR, "Fix qeq/reax has non-zero lower Taper radius cutoff");
   else if (swb < 5) error->warning(FLERR, "Fix qeq/reax has very low Taper radius cutoff");
   if (rxb_fix_qeq(reaxc->rxb, swa, swb, tolerance, 200)) error->all(FLERR, rxb_last_error());
+  // pertype_parameters(): "reax/c" takes chi/eta/gamma from the pair style, anything else names a file with one
+  // `itype chi eta gamma` line per atom type
+  if (pertype_option == "reax/c") {
+    if (rxb_fix_qeq_params(reaxc->rxb, 0, nullptr, nullptr, nullptr)) error->all(FLERR, rxb_last_error());
+  } else {
+    const int ntypes = lmp->atom->ntypes;
+    std::vector<double> chi(ntypes + 1, 0.0), eta(ntypes + 1, 0.0), gamma(ntypes + 1, 0.0);
+    FILE* pf = fopen(pertype_option.c_str(), "r");
+    if (!pf) error->one(FLERR, "Fix qeq/reax parameter file could not be found");
+    int i;
+    for (i = 1; i <= ntypes && !feof(pf); i++) {
+      int itype = 0;
+      double v1 = 0, v2 = 0, v3 = 0;
+      if (fscanf(pf, "%d %lg %lg %lg", &itype, &v1, &v2, &v3) != 4) break;
+      if (itype < 1 || itype > ntypes) { fclose(pf); error->one(FLERR, "Fix qeq/reax invalid atom type in param file"); }
+      chi[itype] = v1; eta[itype] = v2; gamma[itype] = v3;
+    }
+    fclose(pf);
+    if (i <= ntypes) error->one(FLERR, "Invalid param file for fix qeq/reax");
+    if (rxb_fix_qeq_params(reaxc->rxb, ntypes, chi.data(), eta.data(), gamma.data())) error->all(FLERR, rxb_last_error());
+  }
 }
 
 void FixQEqReaxB200::setup_pre_force(int vflag) { pre_force(vflag); }

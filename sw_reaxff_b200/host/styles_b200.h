@@ -61,6 +61,7 @@ class FixQEqReaxB200 : public Fix {
   void pre_force(int vflag) override;                // :539-600
   int nevery = 1, matvecs = 0, matvecs_s = 0, matvecs_t = 0;
   double swa = 0.0, swb = 10.0, tolerance = 1e-6;
+  std::string pertype_option = "reax/c";
   PairReaxCB200* reaxc = nullptr;
 };
 
@@ -85,6 +86,15 @@ class FixReaxCBondsB200 : public Fix {               // fix ID all reax/c/bonds 
  private:
   std::vector<int> tag_, type_, off_, nbr_;
   std::vector<double> bo_, abo_, nlp_, q_;
+};
+
+class ComputeSpecAtomB200 : public Compute {         // compute ID all SPEC/ATOM q x y z vx vy vz abo01 ... abo24
+ public:
+  ComputeSpecAtomB200(LAMMPS* lmp, int narg, char** arg);   // compute_spec_atom_sunway.cpp:35-128
+  void init() override;
+  void compute_peratom() override;                   // :142-170 (+ the pack_* members :178-500)
+  std::vector<int> codes;                            // 0 q, 1-3 x y z, 4-6 vx vy vz, 10 + k: abo(k+1)
+  PairReaxCB200* reaxc = nullptr;
 };
 
 class FixReaxCSpeciesB200 : public Fix {             // fix ID all reax/c/species Nevery Nrepeat Nfreq file [cutoff i j v] [element ...]

@@ -557,3 +557,37 @@ def test_workspace_columns_not_materialised_are_covered_by_their_consumers(case)
     assert abs(res["pvector"][2] - eo[3]) <= 1e-9 * max(abs(eo[3]), 1.0)                       # e_lp
     wg = case["r"].workspace()
     assert rel(wg[:, 15], o.cddelta()) < 1e-9
+
+
+def test_fix_qeq_param_file_mode(tmp_path):
+    """fix qeq/reax ... <param file> (FixQEqReaxSunway::pertype_parameters, fix_qeq_reax_sunway.cpp:198-245): chi, eta and
+    gamma per atom type come from a file instead of the pair style; the QEq (H shielding, diagonal, right-hand side) must
+    use them while the pair style keeps its own.  Charges vs the oracle with the same overrides; also through the C++
+    host style reading the file, and its error texts."""
+    cfg = H.static_config(1, 1, 1, perturb=0.1, seed=13, qeq=False)
+    o = cfg["oracle"]
+    n, x, ty, tg, owner = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"]
+    r = make_rxb(1e-10)
+    chi0, eta0, gam0 = r.pair_extract("chi"), r.pair_extract("eta"), r.pair_extract("gamma")
+    chi = chi0 * np.array([0, 1.1, 0.9, 1.05, 0.95]); eta = eta0 * np.array([0, 0.97, 1.04, 1.0, 1.02])
+    gam = gam0 * np.array([0, 1.03, 0.98, 0.99, 1.01])
+    o.set_atoms(n, x, ty, tg, np.zeros(len(x)))
+    o.build_neighbors(12.5)
+    o.qeq_init(0.0, 10.0, 1e-10)
+    o.L.orc_qeq_override(o.h, H._c(chi[1:]), H._c(eta[1:]), H._c(gam[1:]))      # LAMMPS types 1..4 = elements 0..3
+    o.qeq_set_hist(np.zeros((n, 5)), np.zeros((n, 5)))
+    o.qeq_pre_force(owner)
+    r.set_atoms(n, x, ty, tg, None, owner)
+    r.neigh_build()
+    q_plain = None
+    r.qeq_pre_force(); q_plain = r.get_charges()
+    r.fix_qeq_params(chi, eta, gam)
+    r.qeq_set_history(np.zeros((n, 5)), np.zeros((n, 5)))
+    r.qeq_pre_force()
+    q = r.get_charges()
+    assert np.abs(q - o.q()).max() < 1e-8
+    assert np.abs(q - q_plain).max() > 1e-3          # the override really changes the answer
+    r.fix_qeq_params(None)                           # back to reax/c
+    r.qeq_set_history(np.zeros((n, 5)), np.zeros((n, 5)))
+    r.qeq_pre_force()
+    assert np.abs(r.get_charges() - q_plain).max() < 1e-9

@@ -179,3 +179,58 @@ def test_two_runs_in_one_script_reupload_after_setup(tmp_path):
             # the second run's setup() re-solves QEq from the extrapolated history to the same 1e-6 tolerance: charges, hence
             # e_ele / e_pol, agree to the solver tolerance, not to round-off
             np.testing.assert_allclose(sa[step][5:], sb[step][5:], rtol=5e-5, atol=1e-5)
+
+
+def run_script_compute(script, cid, **variables):
+    build_host()
+    L = C.CDLL(HOSTLIB)
+    L.rxh_run_script_compute.restype = C.c_long
+    names = (C.c_char_p * len(variables))(*[k.encode() for k in variables])
+    vals = (C.c_char_p * len(variables))(*[str(v).encode() for v in variables.values()])
+    out = np.zeros(400000)
+    ncols = C.c_int()
+    err = C.create_string_buffer(1024)
+    n = L.rxh_run_script_compute(script.encode(), len(variables), names, vals, 0, cid.encode(), out.ctypes.data_as(C.c_void_p),
+                                 C.c_long(out.size), C.byref(ncols), err, 1024)
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    return out[:n].reshape(-1, ncols.value)
+
+
+def test_compute_spec_atom_argument_errors(tmp_path):
+    """compute SPEC/ATOM argument validation (compute_spec_atom_sunway.cpp:38, 121) happens before any GPU work."""
+    head = "units real\natom_style charge\nread_data %s\n" % H.DATAFILE
+    p = tmp_path / "in.bad"
+    for line, msg in [("compute 1 all SPEC/ATOM", "Illegal compute reax/c/atom command"),
+                      ("compute 1 all SPEC/ATOM q abo25", "Invalid keyword in compute reax/c/atom command"),
+                      ("compute 1 all SPEC/ATOM q fx", "Invalid keyword in compute reax/c/atom command")]:
+        p.write_text(head + line + "\n")
+        with pytest.raises(RuntimeError, match=msg):
+            run_script(str(p))
+
+
+@pytest.mark.gpu
+def test_compute_spec_atom_standalone(tmp_path):
+    """compute ID all SPEC/ATOM q x y z vx abo01 ... as a style of its own (compute_spec_atom_sunway.cpp:35-170): the abo
+    columns are FindBond's tmpbo (pair_reaxc_sunway.cpp:1170-1198: bonds to partners of higher index with BO >= 0.10, in
+    bond-row order), q/x/v are the atom arrays."""
+    base = open(SCRIPT).read()
+    names = ["q", "x", "y", "z", "vx"] + ["abo%02d" % k for k in range(1, 13)]
+    s = tmp_path / "in.compute"
+    s.write_text(base.replace("thermo          5", "compute         sa all SPEC/ATOM %s\nthermo          5" % " ".join(names)))
+    a = run_script_compute(str(s), "sa", S=1, t=0, T=0, D=H.DATA)
+    assert a.shape == (384, len(names))
+    from sw_reaxff_b200 import Rxb
+    box, x, t, tag = H.tatb_cell(1, 1, 1)
+    r = Rxb(0)
+    r.pair_settings(H.CONTROL); r.pair_coeff(H.FFIELD, H.ELEMENTS); r.fix_qeq(0.0, 10.0, 1e-6)
+    r.md_setup(box, x, np.zeros_like(x), t, tag, H.MASS, dt=0.0625, every=5, thermo=5)
+    g = r.md_get()
+    assert np.abs(a[:, 0] - g["q"]).max() < 1e-9 and np.abs(a[:, 1:4] - g["x"]).max() < 1e-12 and np.abs(a[:, 4]).max() == 0.0
+    abo = r.spec_atom_abo()
+    assert np.abs(a[:, 5:] - abo).max() < 1e-12
+    bs, bc, nbr, _, fld = r.bonds()
+    for i in range(384):                                   # FindBond restated
+        want = [fld[p, 4] for p in range(bs[i], bs[i] + bc[i]) if nbr[p] >= i and fld[p, 4] >= 0.10]
+        assert np.allclose(abo[i, :len(want)], want, rtol=0, atol=1e-15) and np.all(abo[i, len(want):] == 0.0)
+    assert (abo > 0).sum() > 300
