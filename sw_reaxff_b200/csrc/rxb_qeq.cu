@@ -114,6 +114,43 @@ k_spmv2(int r0, int r1, const int* __restrict__ rowlist, int stride, const int* 
   }
 }
 
+// Deep-pipeline form of the packed SpMV (experiment, RXB_SPMV_DEEP=U): every lane issues U word loads, then U gathers, then
+// the FMAs, so a warp keeps 32 U entries in flight and the kernel can saturate HBM from fewer resident warps - which would
+// leave registers and warp slots to the bonded chain running beside it.
+template <int U>
+__global__ void __launch_bounds__(kWarps * 32)
+k_spmv2_deep(int r0, int r1, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk,
+             double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
+             double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
+  if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  for (int i = r0 + wg; i < r1; i += nwg) {
+    const unsigned long long* __restrict__ hp = hpk + (long long)i * stride;
+    const int m = num[i];
+    double ax = 0, ay = 0;
+    for (int k0 = 0; k0 < m; k0 += 32 * U) {
+      unsigned long long w[U];
+      double2 xj[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { const int k = k0 + 32 * u + lane; w[u] = k < m ? __ldcs(hp + k) : 0ULL; }
+#pragma unroll
+      for (int u = 0; u < U; u++) xj[u] = __ldg(x + (int)(w[u] >> kHColShift));     // padding words gather x[0] times 0
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const double h = __longlong_as_double((long long)((w[u] & kHValMask) | 0x4330000000000000ULL)) - 4503599627370496.0;
+        ax += h * xj[u].x; ay += h * xj[u].y;
+      }
+    }
+    ax = warp_sum(ax * inv_quant); ay = warp_sum(ay * inv_quant);
+    if (lane == 0) {
+      const double eta = eta_row[i];
+      const double2 xi = x[rowpos[i]];
+      y[i] = make_double2(eta * xi.x + ax, eta * xi.y + ay);
+    }
+  }
+}
+
 // prologue steps (fix_qeq_reax_sunway.cpp:1024-1105)
 __global__ void k_pro1(int n, const int* __restrict__ rowpos, const double2* __restrict__ b, const double2* __restrict__ q,
                        const double* __restrict__ Hd, double2* __restrict__ r, double2* __restrict__ u, double2* __restrict__ dS) {
@@ -365,7 +402,25 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
     }
     return b;
   }();
-  if (h_packed_)
+  // default: the deep-pipeline form with 8 words + 8 gathers in flight per lane (A/B on one box, profiles/r02_spmv_ab.txt:
+  // SpMV 5.72 -> 5.31 ms/step, step 11.64 -> 11.22; 16 per lane is no better; any occupancy cap is far worse)
+  static const int deep = getenv("RXB_SPMV_DEEP") ? atoi(getenv("RXB_SPMV_DEEP")) : 8;
+  static const int deep_grid = getenv("RXB_SPMV_GRID") ? atoi(getenv("RXB_SPMV_GRID")) : 0;   // persistent grid (CTAs), 0 = one row per warp
+  if (h_packed_ && deep && !rowlist) {
+    const int g = deep_grid > 0 ? deep_grid : grid;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      cudaFuncSetAttribute(k_spmv2_deep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(k_spmv2_deep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    if (deep >= 16)
+      k_spmv2_deep<16><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
+                                                      gated ? Q : nullptr, parity);
+    else
+      k_spmv2_deep<8><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
+                                                     gated ? Q : nullptr, parity);
+  } else if (h_packed_)
     k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_,
                                                     rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
   else
