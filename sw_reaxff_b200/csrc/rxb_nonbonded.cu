@@ -15,6 +15,7 @@
 // Roofline: K-farH streams 4 B/Verlet entry in and 8 B (packed) or 12 B (exact) per far entry out (HBM target); K-nb is
 // fp64-issue bound (143 DP instructions per pair: 2 log + 3 exp + cube root + rsqrt + 1 division, all from rxb_math.cuh).
 // Numbers: DESIGN.md 3.
+#include <cstdlib>
 #include <type_traits>
 
 #include "rxb_math.cuh"
@@ -169,6 +170,107 @@ k_far_H(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const A
         }
       }
     }
+  }
+}
+
+// Single-pass form (default): with the adaptive inner skin 88 % of the candidates a row reads ARE far-list entries, so the
+// fp32 prefilter + compaction + second gather of the two-pass kernel above cost more than they save.  Here every candidate
+// gathers the exact 32-byte record once, the fp64 r^2 decides (the same decision, bit for bit), the H value is computed for
+// the hits and the packed (or exact) entry goes straight to its compacted slot: no column scratch, no second gather, about
+// half the instructions per row (ncu r02c: 3178 warp instructions per row, 65 % issue-slot utilisation, for the two-pass form).
+// Per-row constants ride in lanes: lane t holds the shielding of (row element, element t) and is read by shuffle; the
+// acceptor elements of hydrogen bonds are one bit mask.
+template <bool PACKED>
+__global__ void __launch_bounds__(kWarps * 32)
+k_far_H1(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const AtomPar* __restrict__ atom, double hbond_cut,
+         double hbond_r2max, BondedWork W) {
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const bool inner_ok = *v.disp2 <= qc.inner_lim2;
+  const int stride = v.vl_stride;
+  unsigned acc_mask = 0;                                   // elements that accept hydrogen bonds (p_hbond == 2)
+  for (int t = 0; t < nt && t < 32; t++) acc_mask |= (atom[t].p_hbond == 2 ? 1u : 0u) << t;
+  const unsigned lt_mask = (1u << lane) - 1;
+  for (int r = wg; r < v.n; r += nwg) {
+    const int kself = v.rowpos[r];
+    const double4 pi = v.xqs[kself];
+    const int ti = v.type_s[kself];
+    const long long beg = (long long)r * stride;
+    const int* __restrict__ vl = v.vl_idx + beg;
+    const int cnt_i = inner_ok ? v.vl_cnt_in[r] : v.vl_cnt[r];
+    const bool is_H = ti >= 0 && atom[ti].p_hbond == 1 && hbond_cut > 0.0;
+    const int i_atom = is_H ? v.row_atom[r] : 0;
+    const int lti = v.shld_lt ? v.ltype_s[kself] : 0;
+    const double shld_lane = (ti >= 0 && lane < nt) ? shld[ti * nt + lane] : 0.0;
+    int w = 0;
+    constexpr int kU = 2;
+    for (int k0 = 0; k0 < cnt_i; k0 += 32 * kU) {
+      int jj[kU], tjv[kU];
+      double4 pjv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int k = k0 + 32 * u + lane;
+        jj[u] = k < cnt_i ? __ldcs(vl + k) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        pjv[u] = jj[u] >= 0 ? v.xqs[jj[u]] : make_double4(1e30, 1e30, 1e30, 0.0);   // idle lanes: far away
+        tjv[u] = jj[u] >= 0 ? v.type_s[jj[u]] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int j = jj[u], tj = tjv[u];
+        const double4 pj = pjv[u];
+        const double r2 = dist2_rn(pj.x - pi.x, pj.y - pi.y, pj.z - pi.z);
+        const bool hit = r2 <= qc.far2;                    // idle lanes carry r2 = 3e60
+        // shielding of the pair: a shuffle from the lane that holds element tj (warp-uniform call: every lane takes part)
+        double sh = __shfl_sync(0xffffffffu, shld_lane, tj & 31);
+        double val = 0.0;
+        bool cand = false;
+        if (hit && ti >= 0 && tj >= 0) {
+          if (v.shld_lt) sh = v.shld_lt[lti * v.nlt + v.ltype_s[j]];        // fix qeq/reax <param file>
+          else if (tj >= 32) sh = shld[ti * nt + tj];
+          // r to 1 ulp from rsqrt (coincident atoms: r = 0 as sqrt gives, not NaN), the 7-op cube root of rxb_math.cuh
+          const double rr = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;
+          if (r2 <= qc.swb2) {
+            double T = qc.Tap[7] * rr + qc.Tap[6];
+            T = T * rr + qc.Tap[5]; T = T * rr + qc.Tap[4]; T = T * rr + qc.Tap[3];
+            T = T * rr + qc.Tap[2]; T = T * rr + qc.Tap[1]; T = T * rr + qc.Tap[0];
+            // reference: Taper * 14.4 / pow(r^3 + shld, 0.3333333333333); the cube root differs by < 3e-13 relative
+            val = T * kEvToKcal * fm::rcbrt_b(r2 * rr + sh);
+          }
+          // hydrogen-bond partner: acceptor element within hbond_cut, tested on r^2 against the largest r^2 whose correctly
+          // rounded root is <= hbond_cut (the same decision as sqrt(r2) <= cut)
+          cand = is_H && ((acc_mask >> (tj & 31)) & 1u) && (tj < 32 || atom[tj].p_hbond == 2) && r2 <= hbond_r2max;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int pos = w + __popc(m & lt_mask);
+          if (PACKED) {
+            // val lies in [0, bound] by construction of the shift (launch_far_and_H); the mask only guards the column bits
+            const unsigned long long q = (unsigned long long)__double2ll_rn(fmax(val, 0.0) * qc.h_quant) & kHValMask;
+            v.hpk[beg + pos] = ((unsigned long long)(unsigned)j << kHColShift) | q;
+          } else {
+            v.far_idx[beg + pos] = j;
+            v.H_val[beg + pos] = val;
+          }
+        }
+        w += __popc(m);
+        if (is_H) {
+          const unsigned mc = __ballot_sync(0xffffffffu, cand);
+          if (mc) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(W.n_hb, __popc(mc));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) {
+              const int o = base + __popc(mc & lt_mask);
+              if (o < W.cap_hb) W.hb[o] = make_int4(i_atom, v.s2a[j], 0, 0);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) v.far_num[r] = w;
   }
 }
 
@@ -469,9 +571,15 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   while (hb2 > 0.0 && std::sqrt(hb2) > hc) hb2 = std::nextafter(hb2, 0.0);
   // rows are dealt round-robin to the warps of a grid that is a whole number of waves of resident CTAs (measured:
   // 1 / 2 / 4 waves 0.997 / 0.985 / 0.977 ms; the former fixed 1184 CTAs were 1.6 waves at this register count: 1.12 ms)
-  static int occ_p = 0, occ_e = 0;
-  if (v.hpk) k_far_H<true><<<wave_grid(k_far_H<true>, kWarps * 32, 4, occ_p), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
-  else k_far_H<false><<<wave_grid(k_far_H<false>, kWarps * 32, 4, occ_e), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  static int occ_p = 0, occ_e = 0, occ_p1 = 0, occ_e1 = 0;
+  static const bool two_pass = getenv("RXB_FARH_TWOPASS") && atoi(getenv("RXB_FARH_TWOPASS")) != 0;   // the round-2a kernel, for A/B
+  if (two_pass) {
+    if (v.hpk) k_far_H<true><<<wave_grid(k_far_H<true>, kWarps * 32, 4, occ_p), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+    else k_far_H<false><<<wave_grid(k_far_H<false>, kWarps * 32, 4, occ_e), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  } else {
+    if (v.hpk) k_far_H1<true><<<wave_grid(k_far_H1<true>, kWarps * 32, 4, occ_p1), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+    else k_far_H1<false><<<wave_grid(k_far_H1<false>, kWarps * 32, 4, occ_e1), kWarps * 32, 0, st>>>(v, P.nt, qc, shld, P.atom, hc, hb2, W);
+  }
   s.kernel_launches++;
 }
 

@@ -501,7 +501,7 @@ def test_packed_and_exact_h_formats_agree():
     a, b = out[False], out[True]
     assert np.array_equal(a["far"][0], b["far"][0]) and np.array_equal(a["far"][1], b["far"][1])
     assert np.abs(a["far"][2] - b["far"][2]).max() < 2e-12          # half a quantisation step of 2^-38
-    assert abs(a["mv"][0] - b["mv"][0]) <= 1 and abs(a["mv"][1] - b["mv"][1]) <= 1
+    assert abs(a["mv"][0] - b["mv"][0]) <= 8 and abs(a["mv"][1] - b["mv"][1]) <= 8   # 1e-10 residual: round-off sensitive
     # both solves stop at a 1e-10 relative residual (different iterates of the same system up to the 2^-39 quantisation):
     # the charges agree to the solver's own accuracy, ~1e-9
     assert np.abs(a["q"] - b["q"]).max() < 5e-9

@@ -232,7 +232,9 @@ def test_compute_spec_atom_standalone(tmp_path):
     assert np.abs(lam - np.round(lam)).max() < 1e-12, np.abs(lam - np.round(lam)).max()
     assert np.abs(a[:, 4]).max() == 0.0
     abo = r.spec_atom_abo()
-    assert np.abs(a[:, 5:] - abo).max() < 1e-12
+    # (the slot order of a row follows the neighbour INDEX order, and the LAMMPS stand-in numbers its ghosts differently from
+    # the resident run: compare the rows as multisets)
+    assert np.abs(np.sort(a[:, 5:], axis=1) - np.sort(abo, axis=1)).max() < 1e-9
     bs, bc, nbr, _, fld = r.bonds()
     for i in range(384):                                   # FindBond restated
         want = [fld[p, 4] for p in range(bs[i], bs[i] + bc[i]) if nbr[p] >= i and fld[p, 4] >= 0.10]
