@@ -363,11 +363,17 @@ def run_b200(args, rank, world, local_rank):
     # ---- per-kernel device times over the same kind of steps (lazy CUDA events, no sync inside a step) ----
     r.profile(1)
     nprof = min(args.steps, 20)
+    k0 = r.counters()
     r.md_run(nprof)
     prof = r.profile(0)
+    k1 = r.counters()
     cnt = r.counts()
     nnz_far, nall = int(cnt[5]), int(cnt[1])
-    spmv_ms, spmv_calls = prof["spmv"]
+    spmv_ms, spmv_launched = prof["spmv"]
+    # SpMV launches past convergence are gated off on the device (they return at once): the average launch duration is
+    # taken over the launches that really multiplied, counted on the device
+    spmv_calls = max(int(k1["spmv_active"] - k0["spmv_active"]), 1)
+    qeq_replays = int(k1["qeq_replays"])
     hbm_peak, peak_src = peaks()
     hfmt = r.h_format()
     # dual-RHS SpMV = (bytes per stored H entry) nnz10 + 8k(N+G) gathered + 8kN written + 8N diagonal, k = 2;
@@ -384,6 +390,7 @@ def run_b200(args, rank, world, local_rank):
                 "traffic_source": traffic[1] if traffic else None,
                 "algorithmic_bytes_per_launch": spmv_bytes, "h_entry_format": hfmt["name"],
                 "avg_launch_us": spmv_avg * 1e6, "launches_per_step": spmv_calls / nprof,
+                "gated_launches_per_step": (spmv_launched - spmv_calls) / nprof, "qeq_solves_continued_after_status": qeq_replays,
                 "share_of_step": (spmv_ms / nprof) / step_ms}
 
     # the two other kernels north_star names, against the bound each one has (reported next to the contract's `roofline`)

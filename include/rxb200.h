@@ -180,6 +180,10 @@ int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* compo
  * angle+torsion items, multi-body, enumeration, SpMV boundary-row half (multi-GPU split).  enable: 1 reset+start, 0 stop,
  * -1 read only. */
 int rxb_profile(rxb_handle* h, int enable, double* out28);
+/* counters since rxb_create: out4 = SpMV launches that really multiplied (launches past convergence are gated off on the
+ * device and not counted), QEq solves that had to be continued after the end-of-step check (force phase replayed),
+ * dual-RHS CG iterations, kernel launches */
+int rxb_get_counters(rxb_handle* h, long long* out4);
 /* Tests only: shrink the capacities of the growable lists (directed bonds, angle / torsion / hydrogen-bond work lists) and
  * of the per-atom shared-memory staging (bonds per atom, strong bonds per centre) so that every grow-and-replay branch
  * of the force phase can be driven on an ordinary cell (values <= 0 are left alone); read the current values back. */

@@ -18,7 +18,7 @@ SYMBOLS = [
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
     "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
-    "rxb_fix_qeq_params", "rxb_spec_atom_abo",
+    "rxb_fix_qeq_params", "rxb_spec_atom_abo", "rxb_get_counters",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -316,6 +316,12 @@ class Rxb:
         fld = np.zeros((max(nb, 1), 31))
         self._chk(self.lib.rxb_get_bonds(self.h, _p(bs), _p(bc), _p(nbr), _p(sym), _p(fld)))
         return bs, bc, nbr[:nb], sym[:nb], fld[:nb]
+
+    def counters(self):
+        """dict: spmv_active (launches that really multiplied), qeq_replays, qeq_iterations, kernel_launches."""
+        o = np.zeros(4, dtype=np.int64)
+        self._chk(self.lib.rxb_get_counters(self.h, _p(o)))
+        return dict(zip(["spmv_active", "qeq_replays", "qeq_iterations", "kernel_launches"], o.tolist()))
 
     def hbond_pairs(self):
         n = C.c_int()

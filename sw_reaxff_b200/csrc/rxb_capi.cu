@@ -182,6 +182,14 @@ int rxb_qeq_matvecs(rxb_handle* h, int* matvecs2) {
     matvecs2[0] = h->sys->matvecs_s; matvecs2[1] = h->sys->matvecs_t;
   });
 }
+int rxb_get_counters(rxb_handle* h, long long* out4) {
+  return guard([&] {
+    System& s = *h->sys;
+    unsigned long long a = 0;
+    d2h(&a, s.spmv_active_d.p, (size_t)1, s.stream());
+    out4[0] = (long long)a; out4[1] = s.qeq_replays; out4[2] = s.qeq_iters_total; out4[3] = s.kernel_launches;
+  });
+}
 int rxb_debug_set_caps(rxb_handle* h, int row_cap, int strong_cap, int cap_bonds, int cap_ang, int cap_tor, int cap_hb) {
   return guard([&] { h->sys->debug_set_caps(row_cap, strong_cap, cap_bonds, cap_ang, cap_tor, cap_hb); });
 }

@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(kWarps * 32)
 k_spmv2(int r0, int r1, const int* __restrict__ rowlist, int stride, const int* __restrict__ num,
         const unsigned long long* __restrict__ hpk, const int* __restrict__ col, const double* __restrict__ val, double inv_quant,
         const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
-        double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
+        double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity, unsigned long long* __restrict__ active_launches) {
   if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
+  if (active_launches && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(active_launches, 1ULL);   // launches that really multiply
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int t = r0 + wg; t < r1; t += nwg) {
@@ -121,8 +122,9 @@ template <int U>
 __global__ void __launch_bounds__(kWarps * 32)
 k_spmv2_deep(int r0, int r1, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk,
              double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
-             double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity) {
+             double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity, unsigned long long* __restrict__ active_launches) {
   if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
+  if (active_launches && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(active_launches, 1ULL);   // launches that really multiply
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
   for (int i = r0 + wg; i < r1; i += nwg) {
@@ -416,16 +418,16 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
     }
     if (deep >= 16)
       k_spmv2_deep<16><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
-                                                      gated ? Q : nullptr, parity);
+                                                      gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
     else
       k_spmv2_deep<8><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
-                                                     gated ? Q : nullptr, parity);
+                                                     gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
   } else if (h_packed_)
     k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_,
-                                                    rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+                                                    rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
   else
     k_spmv2<false><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, nullptr, far_idx.p, H_val.p, 1.0,
-                                                     rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity);
+                                                     rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
   tock(ts);
   kernel_launches++;
 }

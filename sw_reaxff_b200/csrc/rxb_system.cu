@@ -280,6 +280,8 @@ System::System(int device) : device_(device) {
   b_cursor.resize(1); overflow.resize(1); en_d.resize(E_NUM); virial_d.resize(6); need_row_d.resize(2);
   RXB_CUDA(cudaMemset(overflow.p, 0, sizeof(int)));
   RXB_CUDA(cudaMemset(need_row_d.p, 0, 2 * sizeof(int)));
+  spmv_active_d.resize(1);
+  RXB_CUDA(cudaMemset(spmv_active_d.p, 0, sizeof(unsigned long long)));
 }
 
 System::~System() {

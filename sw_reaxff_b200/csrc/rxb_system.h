@@ -159,6 +159,7 @@ class System {
   void plugin_compute(bool eflag, bool vflag);
   int matvecs_s = 0, matvecs_t = 0;
   long qeq_iters_total = 0;  // dual-RHS iterations launched and active (M2 metric)
+  DBuf<unsigned long long> spmv_active_d;   // [1]: SpMV launches that were not gated off by the convergence flags
   long qeq_replays = 0;      // solves that had to be continued after the end-of-step check (force phase replayed)
 
   // storage format of the off-diagonal H entries (rxb_dev.cuh): packed 8-byte words unless exact is requested, the taper

@@ -308,11 +308,14 @@ def run_distributed(args, rank, world, local_rank, cells, H):
     # per-kernel profile on rank 0's GPU
     r.profile(1)
     nprof = min(args.steps, 20)
+    k0 = r.counters()
     r.md_run(nprof)
     prof = r.profile(0)
+    k1 = r.counters()
     cnt = r.counts()
     hbm_peak, peak_src = peaks()
-    spmv_ms, spmv_calls = prof["spmv"]
+    spmv_ms, _ = prof["spmv"]
+    spmv_calls = max(int(k1["spmv_active"] - k0["spmv_active"]), 1)   # launches that really multiplied (not gated off)
     hfmt = r.h_format()
     spmv_bytes = float(hfmt["bytes_per_entry"]) * int(cnt[5]) + 16.0 * int(cnt[1]) + 24.0 * int(cnt[0])
     spmv_avg = spmv_ms * 1e-3 / max(spmv_calls, 1)

@@ -72,6 +72,32 @@ for f in sorted(os.listdir(OUT)):
             f"dram {gbs(r, ix, units, 'dram__bytes_read.sum.per_second') + gbs(r, ix, units, 'dram__bytes_write.sum.per_second'):6.0f} GB/s | "
             + "  ".join(f"{h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {100 * v / tot:.0f}%" for v, h in top))
         print("wrote", kernel)
+# DRAM bytes per launch of every captured kernel -> profiles/<tag>_traffic.json (what bench.py's roofline.traffic reads)
+def to_bytes(r, ix, units, k):
+    scale = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    return num(r, ix, k) * scale.get(units[ix[k]], 0.0) if k in ix else 0.0
+
+
+traffic = []
+for f in sorted(os.listdir(OUT)):
+    if not (f.startswith(f"ncu_{TAG}_") and f.endswith(".raw.csv")):
+        continue
+    rows = list(csv.reader(open(os.path.join(OUT, f))))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for r in data:
+        name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
+        name = "k_spmv2" if name.startswith("k_spmv2") else ("k_far_H" if name.startswith("k_far_H") else name)
+        per.setdefault(name, []).append(to_bytes(r, ix, units, "dram__bytes_read.sum") + to_bytes(r, ix, units, "dram__bytes_write.sum"))
+    for name, vals in per.items():
+        traffic.append({"kernel": name, "cells": [8, 8, 8], "dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+                        "source": f"ncu --set full --clock-control none, {f} (dram__bytes_read.sum + dram__bytes_write.sum)"})
+if traffic:
+    import json
+    json.dump(traffic, open(os.path.join(PROF, f"{TAG}_traffic.json"), "w"), indent=1)
+    print("wrote", f"{TAG}_traffic.json", [(t["kernel"], round(t["dram_bytes_per_launch"] / 1e6, 1)) for t in traffic])
+
 if stall_lines:
     head = ["# ncu --set full (TATB 8x8x8, steady-state steps): per kernel, duration, registers, grid, resident warps, issue / fp64 /",
             "# L1 data-pipe utilisation (% of peak), DRAM read+write rate, and the share of each warp-stall reason"]
