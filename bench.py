@@ -52,7 +52,8 @@ def committed_traffic(kernel, cells):
         try:
             for e in json.load(open(p)):
                 if e.get("kernel") == kernel and tuple(e.get("cells", ())) == tuple(cells):
-                    best = (float(e["dram_bytes_per_launch"]), os.path.relpath(p, ROOT) + " <- " + e.get("source", "?"))
+                    best = (float(e["dram_bytes_per_launch"]), os.path.relpath(p, ROOT) + " <- " + e.get("source", "?"),
+                            e.get("l1_data_pipe_pct"))
         except Exception:  # noqa: BLE001
             pass
     return best
@@ -387,6 +388,10 @@ def run_b200(args, rank, world, local_rank):
     roofline = {"kernel": "k_spmv2 (dual-RHS QEq SpMV, the largest single-kernel share of the step)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": traffic[0] if traffic else None,
+                "second_roof": ({"bound": "l1 data pipe (LSU wavefronts)", "busy_pct_under_ncu": traffic[2],
+                                 "note": "the 16-byte CG-vector gathers cost >= 4 wavefronts per 32 entries even when coherent: with "
+                                         "8-byte H entries the kernel sits on this roof as much as on HBM (DESIGN.md section 3)"}
+                                if traffic and traffic[2] is not None else None),
                 "traffic_source": traffic[1] if traffic else None,
                 "algorithmic_bytes_per_launch": spmv_bytes, "h_entry_format": hfmt["name"],
                 "avg_launch_us": spmv_avg * 1e6, "launches_per_step": spmv_calls / nprof,

@@ -624,11 +624,13 @@ k_peer_push(PeerView P, int par, unsigned long long seq, int nsend, const int* _
       d[k] = dots[k];
     }
   }
-  __threadfence_system();                               // every thread: its remote stores are visible system-wide ...
+  // the CTA barrier orders every thread's remote stores before thread 0's system-scope fence (fences are cumulative: the
+  // pattern of a grid barrier), so ONE fence per CTA makes the whole CTA's stores visible before its "done" ticket ...
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int t = atomicAdd(done, 1u);
-    if (t == gridDim.x - 1) {                           // ... before the last CTA publishes the sequence number
+    if (t == gridDim.x - 1) {                           // ... and the last CTA publishes the sequence number
       *done = 0;
       __threadfence_system();
       for (int p = 0; p < P.W; p++)
@@ -641,16 +643,15 @@ __global__ void __launch_bounds__(256)
 k_peer_pull(PeerView P, int par, unsigned long long seq, int nghost, int g0, int g1, const int* __restrict__ gs_pos,
             double2* __restrict__ vec, int ndots, double* __restrict__ dots, int* __restrict__ err) {
   __shared__ int ok;
-  if (threadIdx.x == 0) {
-    ok = 1;
-    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(P.base[P.me]);
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < P.W && threadIdx.x != P.me) {       // lane r polls the flag of rank r: the waits overlap
+    const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(P.base[P.me]) + threadIdx.x;
     const unsigned long long t0 = globaltimer_ns();
-    for (int r = 0; r < P.W && ok; r++) {
-      if (r == P.me) continue;
-      while (ld_acquire_sys(flags + r) < seq) {
-        if (globaltimer_ns() - t0 > 10000000000ULL) { ok = 0; atomicExch(err, 1); break; }   // 10 s: a peer is gone
-      }
+    while (*flag < seq) {
+      if (globaltimer_ns() - t0 > 10000000000ULL) { ok = 0; atomicExch(err, 1); break; }   // 10 s: a peer is gone
     }
+    __threadfence_system();                             // acquire: the peer's stores that preceded its flag are visible now
   }
   __syncthreads();
   if (!ok) return;

@@ -284,7 +284,8 @@ k_far_H1(DevView v, int nt, QeqConst qc, const double* __restrict__ shld, const 
 //   * the column index of chunk t+2 and the (position, type) gather of chunk t+1 are in flight while chunk t computes.
 // 1.97 -> 1.44 ms at 89.5 M pairs.  (Carrying two pairs per lane for more ILP was measured slower: 168 registers, 12 warps/SM.)
 constexpr int kNbPar = 12;  // D, alpha, inv_r_vdW, powgi | alpha_over_r_vdW, gamma, r_vdW, rcore | ecore, acore, lgcij, lgre
-constexpr int kNbThreads = 256, kNbCtas = 2, kNbWarps = kNbThreads / 32;
+// launch shape: 256 threads x 2 CTAs per SM (128 registers, 16 warps per SM) by default; RXB_NB_CFG=1 / 2 select 128 threads x
+// 5 / 6 CTAs (102 / 85 registers, 20 / 24 warps per SM) for A/B
 
 // column of far-list entry k of a row (packed: the top 22 bits of the 64-bit word)
 template <bool PACKED>
@@ -306,9 +307,10 @@ __device__ __forceinline__ int raw_col(FarRaw<PACKED> r) {
   else return r;
 }
 
-template <bool EV, bool PACKED>
+template <bool EV, bool PACKED, int kNbThreads = 256, int kNbCtas = 2>
 __global__ void __launch_bounds__(kNbThreads, kNbCtas)
 k_nonbonded(DevView v, DevParams P) {
+  constexpr int kNbWarps = kNbThreads / 32;
   extern __shared__ __align__(128) double nb_smem[];
   double* tab = nb_smem;                                   // fm::kTabDoubles
   double* red = nb_smem + fm::kTabDoubles;                 // 9 * kNbWarps
@@ -592,11 +594,21 @@ void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cu
     kt<<<wave_grid(kt, kWarps * 32, 2, occ[(v.hpk ? 2 : 0) + (evflag ? 1 : 0)]), kWarps * 32, 0, st>>>(v, P);
   } else {
     // math tables + block reduction scratch + 12 constants per type pair (96 B x nt^2: 4 types 1.5 KB, 40 types 154 KB)
-    const size_t smem = sizeof(double) * (fm::kTabDoubles + 9 * kNbWarps + (size_t)P.nt * P.nt * kNbPar);
-    auto kern = v.hpk ? (evflag ? k_nonbonded<true, true> : k_nonbonded<false, true>)
-                      : (evflag ? k_nonbonded<true, false> : k_nonbonded<false, false>);
+    // A/B on one box (TATB 8x8x8): 256 x 2 (128 registers) 1.425 ms, 128 x 5 (96 registers, 8 B of spills) 1.396 ms,
+    // 128 x 6 (80 registers, 56 B of spills) 1.500 ms
+    static const int cfg_env = getenv("RXB_NB_CFG") ? atoi(getenv("RXB_NB_CFG")) : 1;
+    const int cfg = v.hpk ? cfg_env : 0;                 // the A/B shapes exist for the packed list only
+    const int threads = cfg == 0 ? 256 : 128, ctas = cfg == 0 ? 2 : (cfg == 1 ? 5 : 6);
+    const size_t smem = sizeof(double) * (fm::kTabDoubles + 9 * (threads / 32) + (size_t)P.nt * P.nt * kNbPar);
+    using Kern = void (*)(DevView, DevParams);
+    Kern kern;
+    if (cfg == 0 || !v.hpk)
+      kern = v.hpk ? (evflag ? (Kern)k_nonbonded<true, true> : (Kern)k_nonbonded<false, true>)
+                   : (evflag ? (Kern)k_nonbonded<true, false> : (Kern)k_nonbonded<false, false>);
+    else if (cfg == 1) kern = evflag ? (Kern)k_nonbonded<true, true, 128, 5> : (Kern)k_nonbonded<false, true, 128, 5>;
+    else kern = evflag ? (Kern)k_nonbonded<true, true, 128, 6> : (Kern)k_nonbonded<false, true, 128, 6>;
     if (smem > 48 * 1024) RXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<148 * kNbCtas * 4, kNbThreads, smem, st>>>(v, P);
+    kern<<<148 * ((cfg == 0 || !v.hpk) ? 2 : ctas) * 4, (cfg == 0 || !v.hpk) ? 256 : threads, smem, st>>>(v, P);
   }
   s.kernel_launches++;
 }

@@ -85,13 +85,15 @@ for f in sorted(os.listdir(OUT)):
     rows = list(csv.reader(open(os.path.join(OUT, f))))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
-    per = collections.OrderedDict()
+    per, l1 = collections.OrderedDict(), {}
     for r in data:
         name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
         name = "k_spmv2" if name.startswith("k_spmv2") else ("k_far_H" if name.startswith("k_far_H") else name)
         per.setdefault(name, []).append(to_bytes(r, ix, units, "dram__bytes_read.sum") + to_bytes(r, ix, units, "dram__bytes_write.sum"))
+        l1.setdefault(name, []).append(num(r, ix, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"))
     for name, vals in per.items():
         traffic.append({"kernel": name, "cells": [8, 8, 8], "dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+                        "l1_data_pipe_pct": sum(l1[name]) / len(l1[name]),
                         "source": f"ncu --set full --clock-control none, {f} (dram__bytes_read.sum + dram__bytes_write.sum)"})
 if traffic:
     import json
