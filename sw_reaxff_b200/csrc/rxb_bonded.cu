@@ -144,11 +144,11 @@ k_multi(DevView v, DevParams P) {
       const double4 bo = v.b_bo[p];
       double cdbo = 0, cdbopi = 0, cdbopi2 = 0;
       if (c2corr && aj.is_carbon) {
-        const double vov3 = bo.x - Delta_i - 0.040 * pow(Delta_i, 4.);
+        const double vov3 = bo.x - Delta_i - 0.040 * sqr(sqr(Delta_i));
         if (vov3 > 3.) {
           e_lp += p_lp3 * sqr(vov3 - 3.0);
           cdbo += 2. * p_lp3 * (vov3 - 3.);
-          cdd_i += 2. * p_lp3 * (vov3 - 3.) * (-1. - 0.16 * pow(Delta_i, 3.));
+          cdd_i += 2. * p_lp3 * (vov3 - 3.) * (-1. - 0.16 * (Delta_i * Delta_i * Delta_i));
         }
       }
       const double Delta_j = v.Delta[j], Dlt_j = v.Delta_lp_temp[j];
@@ -218,21 +218,26 @@ __device__ __forceinline__ void calc_dcos(const double4& a, const double4& b, do
 }
 
 // ------------------------------------------------------------------------------------------------------------
-struct Omega { double omega; double di[3], dj[3], dk[3], dl[3]; };
+// Scalars of the dihedral i-j-k-l (reaxc_torsion_angles_sunway.cpp:95-170 Calculate_Omega).  The reference takes the two
+// valence angles, calls sin/cos on them, forms omega with atan2 and then only ever uses cos(omega), cos(2 omega),
+// cos(3 omega) (:1106-1130).  The angles themselves are acos() of a clamped cosine, so sin = sqrt((1-c)(1+c)) >= 0 and
+// cos = c reproduce them to an ulp, and cos(atan2(s, c)) = c / hypot(s, c): no fp64 trigonometric call (and none of their
+// 512-byte slow-path stack) is left.  The derivative vectors of the reference (dcos_omega_di .. dl) are linear
+// combinations of the three bond vectors, r_li and the valence-angle derivatives; only the five coefficients a1..a5 and
+// the scale 2/poem are returned, the torsion kernel folds them into one coefficient per (atom, base vector).
+struct Omega { double cos_omega, a1, a2, a3, a4, a5, sc; };
 
-__device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, const double4& gkl, const double* dvec_li,
-                                        double r_li, double theta_ijk, const double* ijk_di, const double* ijk_dj,
-                                        const double* ijk_dk, double theta_jkl, const double* jkl_di, const double* jkl_dj,
-                                        const double* jkl_dk, Omega& o) {
+__device__ __forceinline__ Omega calc_omega(const double4& gij, const double4& gjk, const double4& gkl, double r_li,
+                                            double sin_ijk, double cos_ijk, double sin_jkl, double cos_jkl) {
+  Omega o;
   const double r_ij = gij.x, r_jk = gjk.x, r_kl = gkl.x;
   const double vij[3] = {gij.y, gij.z, gij.w}, vjk[3] = {gjk.y, gjk.z, gjk.w}, vkl[3] = {gkl.y, gkl.z, gkl.w};
-  double sin_ijk = sin(theta_ijk), cos_ijk = cos(theta_ijk);
-  double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
   auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
   const double unnorm_cos_omega = -dot(vij, vjk) * dot(vjk, vkl) + sqr(r_jk) * dot(vij, vkl);
   const double cr[3] = {vjk[1] * vkl[2] - vjk[2] * vkl[1], vjk[2] * vkl[0] - vjk[0] * vkl[2], vjk[0] * vkl[1] - vjk[1] * vkl[0]};
   const double unnorm_sin_omega = -r_jk * dot(vij, cr);
-  o.omega = atan2(unnorm_sin_omega, unnorm_cos_omega);
+  const double hyp = sqrt(unnorm_sin_omega * unnorm_sin_omega + unnorm_cos_omega * unnorm_cos_omega);
+  o.cos_omega = hyp > 0 ? unnorm_cos_omega / hyp : (signbit(unnorm_cos_omega) ? -1.0 : 1.0);   // atan2(0, +-0) = 0, pi
   const double htra = r_ij + cos_ijk * (r_kl * cos_jkl - r_jk);
   const double htrb = r_jk - r_ij * cos_ijk - r_kl * cos_jkl;
   const double htrc = r_kl + cos_jkl * (r_ij * cos_ijk - r_jk);
@@ -253,15 +258,28 @@ __device__ __noinline__ void calc_omega(const double4& gij, const double4& gjk, 
   else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) sin_ijk = -kMinSine;
   if (sin_jkl >= 0 && sin_jkl <= kMinSine) sin_jkl = kMinSine;
   else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) sin_jkl = -kMinSine;
-  const double a1 = (htra - arg * hnra) / r_ij, a2 = (hthd - arg * hnhd) / sin_ijk, a3 = (hthe - arg * hnhe) / sin_jkl;
-  const double a4 = (htrc - arg * hnrc) / r_kl, a5 = htrb / r_jk, sc = 2.0 / poem;
-#pragma unroll
-  for (int t = 0; t < 3; t++) {
-    o.di[t] = sc * ((a1 * vij[t] + -1. * dvec_li[t]) + -a2 * ijk_dk[t]);
-    o.dj[t] = sc * (((-a1 * vij[t] + -a5 * vjk[t]) + -a2 * ijk_dj[t]) + -a3 * jkl_di[t]);
-    o.dk[t] = sc * (((-a4 * vkl[t] + a5 * vjk[t]) + -a2 * ijk_di[t]) + -a3 * jkl_dj[t]);
-    o.dl[t] = sc * ((a4 * vkl[t] + 1. * dvec_li[t]) + -a3 * jkl_dk[t]);
-  }
+  o.a1 = (htra - arg * hnra) / r_ij;
+  o.a2 = (hthd - arg * hnhd) / sin_ijk;
+  o.a3 = (hthe - arg * hnhe) / sin_jkl;
+  o.a4 = (htrc - arg * hnrc) / r_kl;
+  o.a5 = htrb / r_jk;
+  o.sc = 2.0 / poem;
+  return o;
+}
+
+// cos(theta) of the angle between two bond vectors of one centre, clamped like calc_theta, plus the three coefficients
+// that express the derivative vectors of calc_dcos in the bond vectors themselves:
+//   d/d(end of a) = P b - Q a,   d/d(end of b) = P a - R b,   d/d(centre) = -(both)
+struct DCos { double c, P, Q, R; };
+__device__ __forceinline__ DCos calc_dcos_coef(const double4& a, const double4& b) {
+  DCos o;
+  const double dot = a.y * b.y + a.z * b.z + a.w * b.w;
+  o.P = 1.0 / (a.x * b.x);
+  o.c = fmin(1.0, fmax(-1.0, dot / (a.x * b.x)));
+  const double Cdot_inv3 = dot * (o.P * o.P * o.P);
+  o.Q = Cdot_inv3 * (b.x * b.x);
+  o.R = Cdot_inv3 * (a.x * a.x);
+  return o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -326,8 +344,11 @@ k_enum(DevView v, DevParams P, BondedWork W) {
       const double dSBO1 = -8 * prod_SBO * (Delta_boc_j + p_val8 * vlpadj);
       double SBO2, CSBO2;
       if (SBO <= 0) { SBO2 = 0; CSBO2 = 0; }
-      else if (SBO > 0 && SBO <= 1) { SBO2 = pow(SBO, p_val9); CSBO2 = p_val9 * pow(SBO, p_val9 - 1); }
-      else if (SBO > 1 && SBO < 2) { SBO2 = 2 - pow(2 - SBO, p_val9); CSBO2 = p_val9 * pow(2 - SBO, p_val9 - 1); }
+      else if (SBO < 2) {   // s^(p-1) = s^p / s, s in (0, 1]: one pow() for both
+        const double sb = SBO <= 1 ? SBO : 2 - SBO, pw = pow(sb, p_val9);
+        SBO2 = SBO <= 1 ? pw : 2 - pw;
+        CSBO2 = p_val9 * (pw / sb);
+      }
       else { SBO2 = 2; CSBO2 = 0; }
       W.sbo[j] = make_double4(SBO2, CSBO2, dSBO1, dSBO2);
     }
@@ -453,10 +474,8 @@ k_hbond_items(DevView v, DevParams P, BondedWork W) {
       double theta, cos_theta, di[3], dj[3], dk[3];
       calc_theta(gij, gjk, theta, cos_theta);
       calc_dcos(gij, gjk, di, dj, dk);
-      const double sin_theta2 = sin(theta / 2.0);
-      double sin_xhz4 = sqr(sin_theta2);
-      sin_xhz4 *= sin_xhz4;
       const double cos_xhz1 = (1.0 - cos_theta);
+      const double sin_xhz4 = sqr(0.5 * cos_xhz1);   // sin^4(theta/2) = ((1 - cos theta)/2)^2: no sin(), no acos()
       const double exp_hb2 = exp(-hp.p_hb2 * BOij);
       const double exp_hb3 = exp(-hp.p_hb3 * (hp.r0_hb / r_jk + r_jk / hp.r0_hb - 2.0));
       const double ehb = hp.p_hb1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
@@ -483,7 +502,8 @@ k_hbond_items(DevView v, DevParams P, BondedWork W) {
 
 // ------------------------------------------------------------------------------------------------------------
 // K-angle: one thread per valence angle k-j-h   reaxc_torsion_angles_sunway.cpp:803-979
-__global__ void __launch_bounds__(kItemThreads, 3)
+template <int MINB>
+__global__ void __launch_bounds__(kItemThreads, MINB)
 k_angle_items(DevView v, DevParams P, BondedWork W) {
   const int nitems = min(*W.n_ang, W.cap_ang);
   const double p_val6 = P.gp[14], p_val10 = P.gp[17];
@@ -507,7 +527,7 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
     double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
     calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
     calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> h
-    double sin_theta_hjk = sin(theta_hjk);
+    double sin_theta_hjk = sqrt((1.0 - cos_theta_hjk) * (1.0 + cos_theta_hjk));   // theta = acos(c) in [0, pi]
     if (sin_theta_hjk < 1.0e-5) sin_theta_hjk = 1.0e-5;
     const AngleSet& as = P.angle[(type_k * nt + type_j) * nt + type_h];
     const double tbo_k = v.total_bo[k], tbo_h = v.total_bo[h];
@@ -516,12 +536,14 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
       const AnglePar tp = as.prm[c];
       if (!(fabs(tp.p_val1) > 0.001)) continue;
       const double p_val1 = tp.p_val1, p_val2 = tp.p_val2, p_val4 = tp.p_val4, p_val7 = tp.p_val7, theta_00 = tp.theta_00;
-      const double exp3jk = exp(-p_val3 * pow(BOA_jk, p_val4));
+      // BOA > 0 (both bonds are "strong"), so BOA^(p-1) = BOA^p / BOA: two pow() calls instead of four
+      const double pow_jk = pow(BOA_jk, p_val4), pow_hj = pow(BOA_hj, p_val4);
+      const double exp3jk = exp(-p_val3 * pow_jk);
       const double f7_jk = 1.0 - exp3jk;
-      const double Cf7jk = p_val3 * p_val4 * pow(BOA_jk, p_val4 - 1.0) * exp3jk;
-      const double exp3hj = exp(-p_val3 * pow(BOA_hj, p_val4));
+      const double Cf7jk = p_val3 * p_val4 * (pow_jk / BOA_jk) * exp3jk;
+      const double exp3hj = exp(-p_val3 * pow_hj);
       const double f7_hj = 1.0 - exp3hj;
-      const double Cf7hj = p_val3 * p_val4 * pow(BOA_hj, p_val4 - 1.0) * exp3hj;
+      const double Cf7hj = p_val3 * p_val4 * (pow_hj / BOA_hj) * exp3hj;
       const double expval7 = exp(-p_val7 * Delta_boc_j);
       const double trm8 = 1.0 + expval6 + expval7;
       const double f8_Dj = p_val5 - ((p_val5 - 1.0) * (2.0 + expval6) / trm8);
@@ -596,7 +618,8 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
 
 // ------------------------------------------------------------------------------------------------------------
 // K-tors: one thread per torsion h-j-k-l (= i-j-k-l)   reaxc_torsion_angles_sunway.cpp:994-1290
-__global__ void __launch_bounds__(kItemThreads, 4)
+template <int MINB>
+__global__ void __launch_bounds__(kItemThreads, MINB)
 k_torsion_items(DevView v, DevParams P, BondedWork W) {
   const int nitems = min(*W.n_tor, W.cap_tor);
   const double p_tor2 = P.gp[23], p_tor3 = P.gp[24], p_tor4 = P.gp[25], p_cot2 = P.gp[27];
@@ -613,20 +636,15 @@ k_torsion_items(DevView v, DevParams P, BondedWork W) {
     const double bo_hj = v.b_bo[ph].x, bo_kl = v.b_bo[pw].x;
     const double BOA_jk = bo_jk.x - thb_cut, BOA_ij = bo_hj - thb_cut, BOA_kl = bo_kl - thb_cut;
     const TorsPar fp = P.tors[((v.type[i] * nt + v.type[j]) * nt + v.type[k]) * nt + v.type[l]];
-    double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
-    calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
-    calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> i
-    double theta_jkl, cos_theta_jkl, jkl_di[3], jkl_dj[3], jkl_dk[3];
-    calc_theta(gkj, gkl, theta_jkl, cos_theta_jkl);
-    calc_dcos(gkj, gkl, jkl_di, jkl_dj, jkl_dk);  // di <-> j, dj <-> k, dk <-> l
-    const double r_ij = ghj.x, r_kl = gkl.x;
-    (void)r_ij; (void)r_kl;
-    const double sin_ijk = sin(theta_hjk), cos_ijk = cos(theta_hjk);
+    const DCos hjk = calc_dcos_coef(gjk, ghj);   // a = j->k, b = j->i
+    const DCos jkl = calc_dcos_coef(gkj, gkl);   // a = k->j, b = k->l
+    const double cos_theta_hjk = hjk.c, cos_theta_jkl = jkl.c;
+    const double cos_ijk = cos_theta_hjk, sin_ijk = sqrt((1.0 - cos_ijk) * (1.0 + cos_ijk));
     double tan_ijk_i;
     if (sin_ijk >= 0 && sin_ijk <= kMinSine) tan_ijk_i = cos_ijk / kMinSine;
     else if (sin_ijk <= 0 && sin_ijk >= -kMinSine) tan_ijk_i = cos_ijk / -kMinSine;
     else tan_ijk_i = cos_ijk / sin_ijk;
-    const double sin_jkl = sin(theta_jkl), cos_jkl = cos(theta_jkl);
+    const double cos_jkl = cos_theta_jkl, sin_jkl = sqrt((1.0 - cos_jkl) * (1.0 + cos_jkl));
     double tan_jkl_i;
     if (sin_jkl >= 0 && sin_jkl <= kMinSine) tan_jkl_i = cos_jkl / kMinSine;
     else if (sin_jkl <= 0 && sin_jkl >= -kMinSine) tan_jkl_i = cos_jkl / -kMinSine;
@@ -645,9 +663,9 @@ k_torsion_items(DevView v, DevParams P, BondedWork W) {
     const double4 xi = v.xq[i], xl = v.xq[l];
     const double dvec_li[3] = {xi.x - xl.x, xi.y - xl.y, xi.z - xl.z};
     const double r_li = sqrt(dvec_li[0] * dvec_li[0] + dvec_li[1] * dvec_li[1] + dvec_li[2] * dvec_li[2]);
-    Omega om;
-    calc_omega(ghj, gjk, gkl, dvec_li, r_li, theta_hjk, hjk_di, hjk_dj, hjk_dk, theta_jkl, jkl_di, jkl_dj, jkl_dk, om);
-    const double cos_omega = cos(om.omega), cos2omega = cos(2. * om.omega), cos3omega = cos(3. * om.omega);
+    const Omega om = calc_omega(ghj, gjk, gkl, r_li, sin_ijk, cos_ijk, sin_jkl, cos_jkl);
+    const double cos_omega = om.cos_omega, cos2omega = 2.0 * sqr(cos_omega) - 1.0;
+    const double cos3omega = cos_omega * (4.0 * sqr(cos_omega) - 3.0);
     const double exp_tor1 = exp(fp.p_tor1 * sqr(2.0 - bo_jk.z - f11_DjDk));
     const double fn10 = (1.0 - exp_tor2_ij) * (1.0 - exp_tor2_jk) * (1.0 - exp_tor2_kl);
     const double CV = 0.5 * (fp.V1 * (1.0 + cos_omega) + fp.V2 * exp_tor1 * (1.0 - cos2omega) + fp.V3 * (1.0 + cos3omega));
@@ -681,12 +699,20 @@ k_torsion_items(DevView v, DevParams P, BondedWork W) {
     atomicAdd(&v.b_Cdbo[pk], (CEtors5 + CEconj2));
     atomicAdd(&v.b_Cdbo[pw], (CEtors6 + CEconj3));
     const double c74 = CEtors7 + CEconj4, c85 = CEtors8 + CEconj5, c96 = CEtors9 + CEconj6;
+    // -force on i, j, k, l = c74 dcos(hjk) + c85 dcos(jkl) + c96 dcos(omega) (:1190-1290), every vector of which is a
+    // combination of A = j->k, B = j->i, C = k->j, D = k->l and r_li: one coefficient per (atom, base vector)
+    const double s96 = c96 * om.sc, uc = c74 - s96 * om.a2, wc = c85 - s96 * om.a3;
+    const double iA = uc * hjk.P, iB = s96 * om.a1 - uc * hjk.R;
+    const double lC = wc * jkl.P, lD = s96 * om.a4 - wc * jkl.R;
+    const double jA = uc * (hjk.Q - hjk.P) - s96 * om.a5, jB = uc * (hjk.R - hjk.P) - s96 * om.a1, jC = -wc * jkl.Q, jD = wc * jkl.P;
+    const double kA = s96 * om.a5 - uc * hjk.Q, kB = uc * hjk.P, kC = wc * (jkl.Q - jkl.P), kD = wc * (jkl.R - jkl.P) - s96 * om.a4;
+    const double A[3] = {gjk.y, gjk.z, gjk.w}, B[3] = {ghj.y, ghj.z, ghj.w}, C[3] = {gkj.y, gkj.z, gkj.w}, D[3] = {gkl.y, gkl.z, gkl.w};
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-      atomicAdd(&v.f[3 * i + t], -(c74 * hjk_dk[t] + c96 * om.di[t]));
-      atomicAdd(&v.f[3 * j + t], -(c74 * hjk_dj[t] + c85 * jkl_di[t] + c96 * om.dj[t]));
-      atomicAdd(&v.f[3 * k + t], -(c74 * hjk_di[t] + c85 * jkl_dj[t] + c96 * om.dk[t]));
-      atomicAdd(&v.f[3 * l + t], -(c85 * jkl_dk[t] + c96 * om.dl[t]));
+      atomicAdd(&v.f[3 * i + t], -(iA * A[t] + iB * B[t] - s96 * dvec_li[t]));
+      atomicAdd(&v.f[3 * j + t], -(jA * A[t] + jB * B[t] + jC * C[t] + jD * D[t]));
+      atomicAdd(&v.f[3 * k + t], -(kA * A[t] + kB * B[t] + kC * C[t] + kD * D[t]));
+      atomicAdd(&v.f[3 * l + t], -(lC * C[t] + lD * D[t] + s96 * dvec_li[t]));
     }
   }
   const int slots[2] = {E_TOR, E_CON};
@@ -798,8 +824,23 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
   k_hbond_items<<<wave_grid(k_hbond_items, kItemThreads, kItemWaves, occ_hb), kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::VALTOR, st);
-  k_angle_items<<<wave_grid(k_angle_items, kItemThreads, kItemWaves, occ_ang), kItemThreads, 0, st>>>(v, P, W);
-  k_torsion_items<<<wave_grid(k_torsion_items, kItemThreads, kItemWaves, occ_tor), kItemThreads, 0, st>>>(v, P, W);
+  // resident CTAs per SM the register allocation is bounded for (dev knobs RXB_ANG_OCC / RXB_TOR_OCC, A/B in
+  // profiles/r02_item_occ_ab.txt)
+  static const int ang_minb = getenv("RXB_ANG_OCC") ? atoi(getenv("RXB_ANG_OCC")) : 3;
+  static const int tor_minb = getenv("RXB_TOR_OCC") ? atoi(getenv("RXB_TOR_OCC")) : 3;
+#define RXB_ITEM_LAUNCH(K, MINB, OCC) \
+  K<MINB><<<wave_grid(K<MINB>, kItemThreads, kItemWaves, OCC), kItemThreads, 0, st>>>(v, P, W)
+  switch (ang_minb) {
+    case 4: RXB_ITEM_LAUNCH(k_angle_items, 4, occ_ang); break;
+    case 5: RXB_ITEM_LAUNCH(k_angle_items, 5, occ_ang); break;
+    default: RXB_ITEM_LAUNCH(k_angle_items, 3, occ_ang); break;
+  }
+  switch (tor_minb) {
+    case 4: RXB_ITEM_LAUNCH(k_torsion_items, 4, occ_tor); break;
+    case 5: RXB_ITEM_LAUNCH(k_torsion_items, 5, occ_tor); break;
+    default: RXB_ITEM_LAUNCH(k_torsion_items, 3, occ_tor); break;
+  }
+#undef RXB_ITEM_LAUNCH
   s.tock(t, st);
   s.kernel_launches += 4;
 }
