@@ -119,6 +119,19 @@ int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px,
 /* halo transport: 1 (default) peer-to-peer boundary exchange with ncclSend/ncclRecv, 0 whole-slab all-gather */
 int rxb_dist_set_p2p(rxb_handle* h, int on);
 
+/* ---- multi-rank LAMMPS: the host keeps ITS decomposition and ghost order and drives one handle per MPI rank / GPU through
+ *      the plugin calls above; the library runs what the reference does with comm->forward_comm_fix(this) and MPI_Allreduce
+ *      inside the CG loop (fix_qeq_reax_sunway.cpp:1043-1140, pack/unpack_forward_comm :1300-1370) on the device, over
+ *      NVLink peer windows or NCCL.  rxb_comm_init: once, instead of rxb_dist_init (id from rxb_dist_unique_id on rank 0,
+ *      broadcast by the host, e.g. MPI_Bcast).  rxb_comm_set_ghosts: COLLECTIVE, after every rxb_set_atoms and before
+ *      rxb_neigh_build; for ghost g (0 .. nghost-1, the host's order) owner_rank[g] is the rank that owns the real atom and
+ *      owner_index[g] its local index THERE (periodic images of own atoms: owner_rank = this rank).  LAMMPS obtains both
+ *      with one forward communication of (me, i) after borders(), see INTEGRATION.md.  In this mode rxb_pair_compute
+ *      returns this rank's partial energies/virial and the forces on its local AND ghost atoms (the host reverse-
+ *      communicates and reduces, as it does for the reference); rxb_get_charges returns q of local and ghost atoms. */
+int rxb_comm_init(rxb_handle* h, int rank, int world, const char* id128);
+int rxb_comm_set_ghosts(rxb_handle* h, int nghost, const int* owner_rank, const int* owner_index);
+
 /* ---- introspection (tests, fix reax/c/bonds, fix reax/c/species) ---- */
 /* counts[0..7] = nlocal, nall, verlet nnz, bond-candidate nnz, directed bonds, far nnz(sum), kernel launches, qeq iterations */
 int rxb_get_counts(rxb_handle* h, long long* counts8);

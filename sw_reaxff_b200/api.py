@@ -18,7 +18,7 @@ SYMBOLS = [
     "rxb_bond_table", "rxb_bond_table_get", "rxb_species_config", "rxb_species_step", "rxb_species_result",
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
     "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
-    "rxb_fix_qeq_params", "rxb_spec_atom_abo", "rxb_get_counters",
+    "rxb_fix_qeq_params", "rxb_spec_atom_abo", "rxb_get_counters", "rxb_comm_init", "rxb_comm_set_ghosts",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -288,6 +288,17 @@ class Rxb:
 
     def dist_set_p2p(self, on):
         self._chk(self.lib.rxb_dist_set_p2p(self.h, int(on)))
+
+    def comm_init(self, rank, world, uid):
+        """Host-planned halo (a multi-rank LAMMPS drives one handle per rank through the plugin calls)."""
+        assert len(uid) == 128
+        self._chk(self.lib.rxb_comm_init(self.h, int(rank), int(world), C.c_char_p(uid)))
+
+    def comm_set_ghosts(self, owner_rank, owner_index):
+        """Collective, after every set_atoms and before neigh_build: per ghost, the owning rank and the local index there."""
+        r = _i(owner_rank); k = _i(owner_index)
+        assert len(r) == len(k)
+        self._chk(self.lib.rxb_comm_set_ghosts(self.h, len(r), _p(r), _p(k)))
 
     # ---- introspection ----
     def cutoffs(self):

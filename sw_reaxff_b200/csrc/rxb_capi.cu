@@ -424,6 +424,13 @@ int rxb_dist_init(rxb_handle* h, int rank, int world, const char* id128, int px,
 
 int rxb_dist_set_p2p(rxb_handle* h, int on) { return guard([&] { h->sys->dist_set_p2p(on != 0); }); }
 
+int rxb_comm_init(rxb_handle* h, int rank, int world, const char* id128) {
+  return guard([&] { h->sys->comm_init(rank, world, id128); });
+}
+int rxb_comm_set_ghosts(rxb_handle* h, int nghost, const int* owner_rank, const int* owner_index) {
+  return guard([&] { h->sys->comm_set_ghosts(nghost, owner_rank, owner_index); });
+}
+
 int rxb_bond_table(rxb_handle* h, double bo_cut, int* nlocal, int* nentries, int* max_per_atom) {
   return guard([&] {
     auto t = h->sys->bond_table_build(bo_cut);

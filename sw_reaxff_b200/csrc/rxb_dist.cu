@@ -66,6 +66,11 @@ struct Dist {
   DBuf<int> dst_off_d, soff_d;           // per peer: where my values land in its halo; my send offsets (W + 1)
   DBuf<unsigned int> done_d;             // CTA completion counter of the push kernel
   DBuf<int> peer_err_d;                  // set when a wait timed out (a peer died): checked with the end-of-step status
+  // ---- host-planned halo (comm_init / comm_set_ghosts): the host owns the decomposition and the ghost ORDER, the plan
+  // above (ghosts grouped by source rank) addresses them through a permutation
+  bool external = false;
+  int plan_nghost = -1;                  // ghost count the current plan was made for
+  DBuf<int> gidx, gs_plan;               // plan slot -> ghost index (host order) / -> the ghost's sorted position
 };
 
 namespace {
@@ -556,8 +561,133 @@ static void p2p_forward(System& s, Dist& D, double* vec, int n, cudaStream_t st)
   s.kernel_launches += 2;
 }
 
+// ---- host-planned halo --------------------------------------------------------------------------------------------
+// The reference runs one MPI rank per core group and lets LAMMPS' Comm move ghosts (forward_comm_fix inside the CG loop,
+// fix_qeq_reax_sunway.cpp:1108-1140).  Here a multi-rank host keeps that decomposition and its own ghost order; what the
+// library needs to run the CG halo on the device is, per ghost, the owning rank and the atom's local index there - one
+// forward communication of (me, i) after borders() on the LAMMPS side.  From that every rank derives the
+// same direct plan the brick decomposition uses (ghosts grouped by source rank, senders' lists from a request exchange),
+// so the NVLink peer exchange and the NCCL fallback are shared; only the ghost order goes through a permutation.
+void System::comm_init(int rank, int world, const char* id128) {
+  RXB_CUDA(cudaSetDevice(device_));
+  if (dist_) throw std::runtime_error("rxb_comm_init: this handle already belongs to a communicator");
+  if (rank < 0 || rank >= world) throw std::runtime_error("rxb_comm_init: rank outside [0, world)");
+  dist_ = new Dist();
+  Dist& D = *dist_;
+  D.rank = rank; D.world = world; D.external = true;
+  D.grid[0] = D.grid[1] = D.grid[2] = 0;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  RXB_NCCL(ncclCommInitRank(&D.comm, world, id, rank));
+  dist_peer_setup();
+}
+
+void System::comm_set_ghosts(int nghost, const int* owner_rank, const int* owner_index) {
+  RXB_CUDA(cudaSetDevice(device_));
+  if (!dist_ || !dist_->external) throw std::runtime_error("rxb_comm_set_ghosts: call rxb_comm_init first");
+  if (nghost != N - n)
+    throw std::runtime_error("rxb_comm_set_ghosts: nghost = " + std::to_string(nghost) + " but rxb_set_atoms was given " +
+                             std::to_string(N - n) + " ghosts");
+  if (nghost > 0 && (!owner_rank || !owner_index)) throw std::runtime_error("rxb_comm_set_ghosts: null owner arrays");
+  Dist& D = *dist_;
+  const int W = D.world, me = D.rank;
+  // ghosts grouped by owning rank, host order kept inside a group
+  D.need_from.assign(W, 0); D.send_to.assign(W, 0); D.goff.assign(W + 1, 0); D.soff.assign(W + 1, 0);
+  for (int g = 0; g < nghost; g++) {
+    const int r = owner_rank[g];
+    if (r < 0 || r >= W) throw std::runtime_error("rxb_comm_set_ghosts: owner rank " + std::to_string(r) + " of ghost " + std::to_string(g) + " outside [0, world)");
+    if (r == me && (owner_index[g] < 0 || owner_index[g] >= n))
+      throw std::runtime_error("rxb_comm_set_ghosts: owner index of ghost " + std::to_string(g) + " is not a local atom");
+    D.need_from[r]++;
+  }
+  for (int r = 0; r < W; r++) D.goff[r + 1] = D.goff[r] + D.need_from[r];
+  std::vector<int> gidx(std::max(nghost, 1), 0), req(std::max(nghost, 1), 0), cur(D.goff.begin(), D.goff.end() - 1);
+  for (int g = 0; g < nghost; g++) {
+    const int p = cur[owner_rank[g]]++;
+    gidx[p] = g; req[p] = owner_index[g];
+  }
+  // who needs how many from whom (the same table on every rank)
+  D.cnt_d.resize(W);
+  RXB_CUDA(cudaMemcpyAsync(D.cnt_d.p, D.need_from.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
+  const std::vector<int> need = gather_table(D, D.cnt_d.p, st_);            // need[a * W + b]: ghosts of a owned by b
+  for (int r = 0; r < W; r++) {
+    D.send_to[r] = (r == me) ? 0 : need[(size_t)r * W + me];
+    D.soff[r + 1] = D.soff[r] + D.send_to[r];
+  }
+  D.nsend = D.soff[W];
+  // request exchange: the owner indices of my ghosts go to their owners and come back as my send lists
+  D.greq.resize(std::max(nghost, 1)); D.gidx.resize(std::max(nghost, 1)); D.sendlist.resize(std::max(D.nsend, 1));
+  RXB_CUDA(cudaMemcpyAsync(D.greq.p, req.data(), (size_t)std::max(nghost, 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(D.gidx.p, gidx.data(), (size_t)std::max(nghost, 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == me) continue;
+    if (D.need_from[r] > 0) RXB_NCCL(ncclSend(D.greq.p + D.goff[r], (size_t)D.need_from[r], ncclInt, r, D.comm, st_));
+    if (D.send_to[r] > 0) RXB_NCCL(ncclRecv(D.sendlist.p + D.soff[r], (size_t)D.send_to[r], ncclInt, r, D.comm, st_));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  std::vector<int> sl(std::max(D.nsend, 1), 0);
+  RXB_CUDA(cudaMemcpyAsync(sl.data(), D.sendlist.p, (size_t)D.nsend * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  D.sendbuf.resize((size_t)4 * std::max(D.nsend, 1));
+  D.recvbuf.resize((size_t)3 * std::max(D.nsend, 1));
+  // peer exchange: where my values land in each consumer's halo, and whether every rank's ghosts fit the windows
+  std::vector<int> dst_off(W, 0);
+  long long max_ghosts = 0;
+  for (int p = 0; p < W; p++) {
+    long long tot = 0;
+    for (int r = 0; r < W; r++) {
+      if (r == me) dst_off[p] = (int)tot;
+      tot += need[(size_t)p * W + r];
+    }
+    max_ghosts = std::max(max_ghosts, tot);
+  }
+  D.peer_plan_ok = D.peer_ok && max_ghosts <= (long long)D.cap_g;
+  D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
+  RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  for (int e = 0; e < D.nsend; e++)
+    if (sl[e] < 0 || sl[e] >= n)
+      throw std::runtime_error("rxb_comm_set_ghosts: a peer asked for local index " + std::to_string(sl[e]) + " but this rank has " +
+                               std::to_string(n) + " local atoms (owner_index must be the index on the OWNING rank)");
+  D.plan_nghost = nghost;
+  D.recv_bytes_last = (size_t)D.nsend * sizeof(int);
+  s2a.n = 0;                             // the sorted maps of the plan are made by the next rxb_neigh_build
+}
+
+namespace {
+__global__ void k_pack_q(int m, const int* __restrict__ list, const double4* __restrict__ xq, double* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m) out[e] = xq[list[e]].w;
+}
+__global__ void k_unpack_q(int nghost, int n, int g0, int g1, const int* __restrict__ gidx, const int* __restrict__ greq,
+                           const double* __restrict__ recv, double4* __restrict__ xq) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nghost) return;
+  xq[n + gidx[p]].w = (p >= g0 && p < g1) ? xq[greq[p]].w : recv[p];
+}
+}  // namespace
+
+// host-planned halo: the new charges of the real atoms -> their ghosts on every rank (the reference ends pre_force with
+// comm->forward_comm_fix(this) of q, fix_qeq_reax_sunway.cpp:1290-1298); positions are the host's business in this mode
+static void ext_forward_q(System& s, Dist& D, cudaStream_t st) {
+  const int W = D.world, nghost = s.N - s.n;
+  if (D.nsend > 0) k_pack_q<<<nblk(D.nsend), 256, 0, st>>>(D.nsend, D.sendlist.p, s.xq.p, D.sendbuf.p);
+  RXB_NCCL(ncclGroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == D.rank) continue;
+    if (D.send_to[r] > 0) RXB_NCCL(ncclSend(D.sendbuf.p + D.soff[r], (size_t)D.send_to[r], ncclDouble, r, D.comm, st));
+    if (D.need_from[r] > 0) RXB_NCCL(ncclRecv(D.recv2.p + D.goff[r], (size_t)D.need_from[r], ncclDouble, r, D.comm, st));
+  }
+  RXB_NCCL(ncclGroupEnd());
+  if (nghost > 0)
+    k_unpack_q<<<nblk(nghost), 256, 0, st>>>(nghost, s.n, D.goff[D.rank], D.goff[D.rank + 1], D.gidx.p, D.greq.p, D.recv2.p, s.xq.p);
+  s.kernel_launches += 2;
+}
+
 void System::dist_forward_xq() {
   Dist& D = *dist_;
+  if (D.external) { ext_forward_q(*this, D, st_); return; }
   BoxD b;
   memcpy(b.h, box.h, sizeof(b.h));
   memcpy(b.h_inv, box.h_inv, sizeof(b.h_inv));
@@ -760,9 +890,9 @@ void System::dist_classify_rows() {
   kernel_launches += 3;
 }
 
-void System::dist_push2(double2* vecS, double* dots, int ndots) { peer_push(*this, *dist_, vecS, gs_pos.p, dots, ndots, st_); }
+void System::dist_push2(double2* vecS, double* dots, int ndots) { peer_push(*this, *dist_, vecS, dist_gs(), dots, ndots, st_); }
 void System::dist_pull2(double2* vecS, double* dots, int ndots) {
-  peer_pull(*this, *dist_, vecS, N - n, gs_pos.p, dots, ndots, st_);
+  peer_pull(*this, *dist_, vecS, N - n, dist_gs(), dots, ndots, st_);
 }
 
 // Map every rank's window (CUDA IPC; all ranks are processes on one node).  Any failure on any rank (no peer access,
@@ -851,7 +981,16 @@ void System::dist_sorted_maps() {
   if (g1 > g0) k_map_idx<<<nblk(g1 - g0), 256, 0, st_>>>(g1 - g0, D.greq.p + g0, a2s.p, D.self_s.p);
   D.recv2.resize((size_t)2 * std::max(nghost, 1));
   kernel_launches += 2;
+  if (D.external) {
+    if (D.plan_nghost != nghost)
+      throw std::runtime_error("rxb_comm_set_ghosts must follow every rxb_set_atoms (the ghost plan is for " +
+                               std::to_string(D.plan_nghost) + " ghosts, the atom set has " + std::to_string(nghost) + ")");
+    D.gs_plan.resize(std::max(nghost, 1));
+    if (nghost > 0) { k_map_idx<<<nblk(nghost), 256, 0, st_>>>(nghost, D.gidx.p, gs_pos.p, D.gs_plan.p); kernel_launches++; }
+  }
 }
+const int* System::dist_gs() const { return dist_ && dist_->external ? dist_->gs_plan.p : gs_pos.p; }
+bool System::dist_external() const { return dist_ && dist_->external; }
 
 static void s_forward2(System& s, Dist& D, double2* vec, int n, int nghost, const int* gs_pos, double* dots, cudaStream_t st) {
   const int W = D.world;
@@ -877,7 +1016,7 @@ static void s_forward2(System& s, Dist& D, double2* vec, int n, int nghost, cons
 }
 
 void System::dist_forward2(double2* vec) {
-  s_forward2(*this, *dist_, vec, n, N - n, gs_pos.p, nullptr, st_);
+  s_forward2(*this, *dist_, vec, n, N - n, dist_gs(), nullptr, st_);
 }
 
 // sum of the per-rank partials in rank order: every rank adds the same numbers in the same order, so all ranks hold the
@@ -896,7 +1035,7 @@ __global__ void k_sum_dots(int world, int rank, const double* __restrict__ all, 
 // (the reference: MPI_Allreduce + comm->forward_comm_fix per iteration, fix_qeq_reax_sunway.cpp:1108-1140).
 void System::dist_forward2_dots(double2* vec, double* dots) {
   Dist& D = *dist_;
-  s_forward2(*this, D, vec, n, N - n, gs_pos.p, dots, st_);
+  s_forward2(*this, D, vec, n, N - n, dist_gs(), dots, st_);
   if (D.peer_ok && D.peer_plan_ok) return;         // the pull kernel has already formed the totals
   k_sum_dots<<<1, 32, 0, st_>>>(D.world, D.rank, D.dots_all.p, dots);
   kernel_launches++;

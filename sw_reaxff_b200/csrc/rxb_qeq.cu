@@ -462,7 +462,7 @@ bool System::qeq_poll() {
 
 void System::qeq_pre_force(bool wait_for_convergence) {
   if (n == 0) return;
-  if (q_s_hist.n != (size_t)5 * n && !dist_) qeq_reset_history();
+  if (q_s_hist.n != (size_t)5 * n && (!dist_ || dist_external())) qeq_reset_history();
   last_swb_ = qeq_swb;
   choose_h_format();                    // (taper start / exact request may have changed since the build)
   DevView v = view();

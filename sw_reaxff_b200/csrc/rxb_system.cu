@@ -674,7 +674,7 @@ void System::build_neighbors() {
     RXB_CUDA(cudaMemsetAsync(disp2_d.p, 0, sizeof(double), st_));
   }
   x_build.n = (size_t)N;
-  if (dist_) { dist_sorted_maps(); dist_classify_rows(); }
+  if (dist_) { dist_sorted_maps(); if (!dist_external()) dist_classify_rows(); }
   // bond candidates for all rows (ghosts too): (reach of the longest possible bond <= bond_cut) + skin
   const double cb = bond_reach() + skin;
   cells_b_.bin(xq.p, N, cb / 2.0, 2, st_);
@@ -734,7 +734,8 @@ void System::read_step_status(bool ev, int* h, int* wk) {
   if (dist_) dist_allreduce_max_int(status_d_.p + 16, 11);
   int host[32];
   RXB_CUDA(cudaMemcpyAsync(host, status_d_.p, 32 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  if (ev && dist_) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
+  // (host-planned halo: every rank reports its own partial sums, the host reduces them like the reference's MPI ranks)
+  if (ev && dist_ && !dist_external()) { dist_allreduce(en_d.p, E_NUM); dist_allreduce(virial_d.p, 6); }
   if (ev) {
     RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
     RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
@@ -812,6 +813,7 @@ void System::grow_staging() {
 void System::md_setup(const double* box6, int nlocal, const double* x, const double* v, const int* ltype, const int* tg,
                       const double* mass_by_type, int ntypes, double dt, int every) {
   RXB_CUDA(cudaSetDevice(device_));
+  if (dist_external()) throw std::runtime_error("rxb_md_setup: a handle in host-planned halo mode (rxb_comm_init) is driven through the plugin calls");
   box.set(box6[0], box6[1], box6[2], box6[3], box6[4], box6[5]);
   md_dt = dt; md_every = every; md_ago = 0; ntimestep = 0;
   std::vector<double> q0(nlocal, 0.0);

@@ -232,6 +232,12 @@ class System {
   void dist_forward2_dots(double2* vec, double* dots);   // halo of vec + all-reduce of 4 dot products in one exchange
   void dist_reverse_f();
   size_t slab() const;           // (0: no all-gathered arrays any more)
+  // host-planned halo: a multi-rank LAMMPS keeps its own decomposition and drives one handle per rank through the plugin
+  // calls; the ranks share an NCCL communicator and each tells the library, per ghost, who owns the real atom
+  void comm_init(int rank, int world, const char* id128);
+  void comm_set_ghosts(int nghost, const int* owner_rank, const int* owner_index);   // collective, after set_atoms
+  bool dist_external() const;
+  const int* dist_gs() const;    // sorted position of the ghost behind each slot of the exchange plan
   size_t dist_last_recv_bytes() const;   // payload received at the last reneighbouring (migrants + ghost records)
 
   // ---- analysis outputs (rxb_analysis.cu): fix reax/c/bonds table, fix reax/c/species molecules ----
