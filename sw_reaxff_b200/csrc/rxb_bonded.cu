@@ -524,9 +524,8 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
     const double Delta_boc_j = v.Delta_boc[j], Delta_j = v.Delta[j], Delta_val_j = v.Delta_val[j];
     const double p_val3 = P.atom[type_j].p_val3, p_val5 = P.atom[type_j].p_val5;
     const double expval6 = exp(p_val6 * Delta_boc_j);
-    double theta_hjk, cos_theta_hjk, hjk_di[3], hjk_dj[3], hjk_dk[3];
+    double theta_hjk, cos_theta_hjk;
     calc_theta(gjk, ghj, theta_hjk, cos_theta_hjk);
-    calc_dcos(gjk, ghj, hjk_di, hjk_dj, hjk_dk);  // di <-> k, dj <-> j, dk <-> h
     double sin_theta_hjk = sqrt((1.0 - cos_theta_hjk) * (1.0 + cos_theta_hjk));   // theta = acos(c) in [0, pi]
     if (sin_theta_hjk < 1.0e-5) sin_theta_hjk = 1.0e-5;
     const AngleSet& as = P.angle[(type_k * nt + type_j) * nt + type_h];
@@ -606,9 +605,16 @@ k_angle_items(DevView v, DevParams P, BondedWork W) {
     if (s5 != 0.0) atomicAdd(&W.sum56[j].x, s5);
     if (s6 != 0.0) atomicAdd(&W.sum56[j].y, s6);
     if (c8 != 0.0) {
-      fadd3(v.f, k, -c8, hjk_di[0], hjk_di[1], hjk_di[2]);
-      fadd3(v.f, j, -c8, hjk_dj[0], hjk_dj[1], hjk_dj[2]);
-      fadd3(v.f, h, -c8, hjk_dk[0], hjk_dk[1], hjk_dk[2]);
+      // d cos(theta) / d(k, j, h) as coefficients on the two bond vectors (see calc_dcos_coef), formed only now from the
+      // re-read geometry (an L1 hit) so that nine doubles do not stay live across the parameter-set loop above
+      const double4 a = v.b_geo[pk], b = v.b_geo[ph];
+      const DCos dc = calc_dcos_coef(a, b);
+      const double kA = -c8 * -dc.Q, kB = -c8 * dc.P, hA = -c8 * dc.P, hB = -c8 * -dc.R;
+      const double fk[3] = {kA * a.y + kB * b.y, kA * a.z + kB * b.z, kA * a.w + kB * b.w};
+      const double fh[3] = {hA * a.y + hB * b.y, hA * a.z + hB * b.z, hA * a.w + hB * b.w};
+      fadd3(v.f, k, 1.0, fk[0], fk[1], fk[2]);
+      fadd3(v.f, h, 1.0, fh[0], fh[1], fh[2]);
+      fadd3(v.f, j, -1.0, fk[0] + fh[0], fk[1] + fh[1], fk[2] + fh[2]);
     }
   }
   const int slots[3] = {E_ANG, E_PEN, E_COA};

@@ -589,6 +589,7 @@ void System::comm_set_ghosts(int nghost, const int* owner_rank, const int* owner
     throw std::runtime_error("rxb_comm_set_ghosts: nghost = " + std::to_string(nghost) + " but rxb_set_atoms was given " +
                              std::to_string(N - n) + " ghosts");
   if (nghost > 0 && (!owner_rank || !owner_index)) throw std::runtime_error("rxb_comm_set_ghosts: null owner arrays");
+  if (n == 0) throw std::runtime_error("rxb_comm_set_ghosts: a rank without local atoms cannot take part in the solve (rebalance the decomposition)");
   Dist& D = *dist_;
   const int W = D.world, me = D.rank;
   // ghosts grouped by owning rank, host order kept inside a group

@@ -967,7 +967,7 @@ void System::md_force_overlapped(bool ev) {
 
 // plugin path (C ABI): fix qeq/reax pre_force, then pair compute
 void System::plugin_qeq_pre_force(bool wait_for_convergence) {
-  if (overlap && !profile && !dist_ && n > 0) overlapped_front(wait_for_convergence);
+  if (overlap && !profile && (!dist_ || dist_external()) && n > 0) overlapped_front(wait_for_convergence);
   else { if (chain_inflight_) cancel_inflight(); qeq_pre_force(wait_for_convergence); }
 }
 void System::plugin_compute(bool eflag, bool vflag) {
