@@ -43,10 +43,11 @@ def main():
     serial = LC.HostComm(box, (1, 1, 1), 12.5)
     out = {"world": world, "cells": cells, "atoms": int(len(x)), "steps": steps}
     ok = True
-    for label, kw in (("peer", {}), ("nccl", {"RXB_PEER": "0"})):
+    for label, kw in (("peer", {}), ("peer_async_qeq", {}), ("nccl", {"RXB_PEER": "0"})):
         for k, val in kw.items():
             os.environ[k] = val
-        a = LC.host_md(Rxb, H, comm, rank, dev, box, x, v, t, tag, steps, uid=uid[0], use_comm=True, allgather=ag, tol=1e-10)
+        a = LC.host_md(Rxb, H, comm, rank, dev, box, x, v, t, tag, steps, uid=uid[0], use_comm=True, allgather=ag, tol=1e-10,
+                       async_qeq=label.endswith("async_qeq"))
         if label == "peer":
             b = LC.host_md(Rxb, H, serial, 0, dev, box, x, v, t, tag, steps, use_comm=False, tol=1e-10)
         c = LC.compare(a, b)

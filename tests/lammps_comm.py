@@ -85,7 +85,7 @@ class HostComm:
 
 
 def host_md(Rxb, H, comm, rank, device, box6, x, v, types, tags, steps, every=4, dt=0.25, tol=1e-8, uid=None, use_comm=True,
-            allgather=lambda o: [o], shuffle=True, exact_h=False):
+            allgather=lambda o: [o], shuffle=True, exact_h=False, async_qeq=False):
     """Velocity-Verlet NVE of the replicated global system, forces from one handle per rank through the plugin calls.
     Returns dict(pe[steps+1], ke[...], x, v, q (global, by atom), f (global), matvecs[...], nghost, peer)."""
     r = Rxb(device)
@@ -133,8 +133,13 @@ def host_md(Rxb, H, comm, rank, device, box6, x, v, types, tags, steps, every=4,
         local, src, shift, idx = state["local"], state["src"], state["shift"], state["idx"]
         if not first:
             r.set_positions(np.concatenate([x[local], x[src] + shift]))
-        mv = r.qeq_pre_force()
-        out = r.pair_compute(True, True)
+        if async_qeq:                  # enqueue only; the solve is settled inside pair_compute (non-thermo steps of the host styles)
+            r.qeq_pre_force_async()
+            out = r.pair_compute(True, True)
+            mv = r.qeq_matvecs()
+        else:
+            mv = r.qeq_pre_force()
+            out = r.pair_compute(True, True)
         q = r.get_charges()
         f = np.zeros((natoms, 3)); qg = np.zeros(natoms); pe = 0.0
         # reverse communication of the forces (local + ghost contributions summed onto the real atom) and thermo sums

@@ -31,14 +31,14 @@ def test_host_comm_ghost_shell_is_complete():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("peer", ["1", "0"])
-def test_comm_mode_one_rank_matches_plain_plugin_run(peer, monkeypatch):
+@pytest.mark.parametrize("peer,async_qeq", [("1", False), ("0", False), ("1", True)])
+def test_comm_mode_one_rank_matches_plain_plugin_run(peer, async_qeq, monkeypatch):
     from sw_reaxff_b200 import Rxb
     monkeypatch.setenv("RXB_PEER", peer)
     box, x, t, tag = H.tatb_cell(2, 2, 2)
     v = H.maxwell_velocities(t, 1500.0, 4242)
     comm = LC.HostComm(box, (1, 1, 1), 12.5)
-    a = LC.host_md(Rxb, H, comm, 0, 0, box, x, v, t, tag, 9, uid=Rxb.dist_unique_id(), use_comm=True, tol=1e-10)
+    a = LC.host_md(Rxb, H, comm, 0, 0, box, x, v, t, tag, 9, uid=Rxb.dist_unique_id(), use_comm=True, tol=1e-10, async_qeq=async_qeq)
     b = LC.host_md(Rxb, H, comm, 0, 0, box, x, v, t, tag, 9, use_comm=False, shuffle=False, tol=1e-10)
     c = LC.compare(a, b)
     assert c["ghost_q_err"] == 0.0
