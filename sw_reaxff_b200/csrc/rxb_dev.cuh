@@ -127,6 +127,14 @@ struct QeqDev {
   double sums[2];       // sum s, sum t
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialisation attribute may be scheduled
+// while its predecessor in the stream drains; pdl_wait() returns once the predecessor grid has completed and its writes
+// are visible (a no-op without the attribute), pdl_release() lets the NEXT kernel's CTAs be scheduled as soon as every CTA
+// of this grid has started.  Both are the first statements of the CG-loop kernels: the launch latency and the tail of
+// one kernel overlap the ramp-up of the next (3 dependent launches per CG iteration, ~35 iterations per step).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -737,6 +737,7 @@ __global__ void __launch_bounds__(256)
 k_peer_push(PeerView P, int par, unsigned long long seq, int nsend, const int* __restrict__ send_s, const int* __restrict__ soff,
             const int* __restrict__ dst_off, double2* vec, int g0, int g1, const int* __restrict__ gs_pos,
             const int* __restrict__ self_s, int ndots, const double* __restrict__ dots, unsigned int* __restrict__ done) {
+  pdl_wait(); pdl_release();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   // boundary values -> the consumers' halo (their ghost order)
   for (int e = tid; e < nsend; e += nth) {
@@ -773,6 +774,7 @@ k_peer_push(PeerView P, int par, unsigned long long seq, int nsend, const int* _
 __global__ void __launch_bounds__(256)
 k_peer_pull(PeerView P, int par, unsigned long long seq, int nghost, int g0, int g1, const int* __restrict__ gs_pos,
             double2* __restrict__ vec, int ndots, double* __restrict__ dots, int* __restrict__ err) {
+  pdl_wait(); pdl_release();
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -817,9 +819,8 @@ void peer_push(System& s, Dist& D, double2* vec, const int* gs_pos, double* dots
   const int g0 = vec ? D.goff[D.rank] : 0, g1 = vec ? D.goff[D.rank + 1] : 0;
   const int nsend = vec ? D.nsend : 0;
   const int work = std::max(nsend, g1 - g0);
-  k_peer_push<<<std::max(1, std::min(148, (work + 255) / 256)), 256, 0, st>>>(P, par, D.seq, nsend, D.send_s.p, D.soff_d.p,
-                                                                           D.dst_off_d.p, vec, g0, g1, gs_pos, D.self_s.p,
-                                                                           ndots, dots, D.done_d.p);
+  launch_pdl(k_peer_push, std::max(1, std::min(148, (work + 255) / 256)), 256, 0, st, P, par, D.seq, nsend, D.send_s.p, D.soff_d.p,
+             D.dst_off_d.p, vec, g0, g1, gs_pos, D.self_s.p, ndots, dots, D.done_d.p);
   s.kernel_launches++;
 }
 void peer_pull(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {
@@ -827,8 +828,8 @@ void peer_pull(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, 
   const PeerView P = peer_view(D);
   const int g0 = vec ? D.goff[D.rank] : 0, g1 = vec ? D.goff[D.rank + 1] : 0;
   const int ng = vec ? nghost : 0;
-  k_peer_pull<<<std::max(1, std::min(296, (ng + 255) / 256)), 256, 0, st>>>(P, par, D.seq, ng, g0, g1, gs_pos, vec, ndots, dots,
-                                                                         D.peer_err_d.p);
+  launch_pdl(k_peer_pull, std::max(1, std::min(296, (ng + 255) / 256)), 256, 0, st, P, par, D.seq, ng, g0, g1, gs_pos, vec, ndots, dots,
+             D.peer_err_d.p);
   s.kernel_launches++;
 }
 void peer_exchange(System& s, Dist& D, double2* vec, int nghost, const int* gs_pos, double* dots, int ndots, cudaStream_t st) {

@@ -62,6 +62,7 @@ __global__ void k_qeq_init(int n, const int* __restrict__ rowpos, const int* __r
 
 // periodic-image ghosts of an S-space vector <- their owners (single-rank forward_comm_fix)
 __global__ void k_forward2S(int nghost, const int* __restrict__ gs_pos, const int* __restrict__ gs_own, double2* __restrict__ vec) {
+  pdl_wait(); pdl_release();
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nghost; g += gridDim.x * blockDim.x) {
     const int o = gs_own[g];
     if (o >= 0) vec[gs_pos[g]] = vec[o];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 k_spmv2_deep(int r0, int r1, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk,
              double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
              double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity, unsigned long long* __restrict__ active_launches) {
+  pdl_wait(); pdl_release();
   if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
   if (active_launches && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(active_launches, 1ULL);   // launches that really multiply
   const int lane = threadIdx.x & 31;
@@ -226,6 +228,7 @@ k_cg_sweep(int n, int it, int first, double tol, int imax, const int* __restrict
            const double2* __restrict__ q, double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ u,
            double2* __restrict__ w, double2* __restrict__ p, double2* __restrict__ ss, double2* __restrict__ v,
            double2* __restrict__ z, double2* __restrict__ dS, QeqDev* __restrict__ Q) {
+  pdl_wait(); pdl_release();
   const int par = it & 1;
   const QeqState S = Q->st[par];
   QeqState T = S;  // state after the B part; identical in every thread
@@ -353,8 +356,8 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
 // one CG iteration of loop index `it`: fused sweep, halo of d (+ the dot products in multi-GPU runs), gated SpMV
 void System::qeq_iteration(int it) {
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
-  k_cg_sweep<<<kVecBlocks, kVecThreads, 0, st_>>>(n, it, it == 1, qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p, q_x.p, q_r.p,
-                                                 q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
+  launch_pdl(k_cg_sweep, kVecBlocks, kVecThreads, 0, st_, n, it, (int)(it == 1), qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p,
+             q_x.p, q_r.p, q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
   kernel_launches++;
   const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
   // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange.  Multi-GPU with
@@ -380,7 +383,7 @@ void System::qeq_forward_S(double2* vecS) {
   if (dist_) { dist_forward2(vecS); return; }
   const int nghost = N - n;
   if (nghost > 0) {
-    k_forward2S<<<std::min(148 * 8, (nghost + 255) / 256), 256, 0, st_>>>(nghost, gs_pos.p, gs_own.p, vecS);
+    launch_pdl(k_forward2S, std::min(148 * 8, (nghost + 255) / 256), 256, 0, st_, nghost, gs_pos.p, gs_own.p, vecS);
     kernel_launches++;
   }
 }
@@ -420,8 +423,8 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
       k_spmv2_deep<16><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
                                                       gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
     else
-      k_spmv2_deep<8><<<g, kWarps * 32, smem, st_>>>(r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p, xS, y_row,
-                                                     gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
+      launch_pdl(k_spmv2_deep<8>, g, kWarps * 32, smem, st_, r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_, rowpos.p, q_eta.p,
+                 xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
   } else if (h_packed_)
     k_spmv2<true><<<grid, kWarps * 32, smem, st_>>>(r0, r1, rowlist, vl.stride, far_num.p, hpk.p, nullptr, nullptr, 1.0 / h_quant_,
                                                     rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);

@@ -391,6 +391,20 @@ void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st);
 // Grid of a grid-stride kernel: a whole number of waves of the CTAs that fit on the 148 SMs at this kernel's register and
 // shared-memory footprint (a fixed 148 x k grid is a fractional number of waves whenever the footprint changes: measured
 // 13 % on the far-list kernel).  The occupancy is queried once per call site.
+// launch with the programmatic-dependent-launch attribute (see pdl_wait in rxb_dev.cuh); RXB_PDL=0 launches plainly
+inline bool pdl_enabled() { static const bool on = !(getenv("RXB_PDL") && atoi(getenv("RXB_PDL")) == 0); return on; }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch failed: ") + cudaGetErrorString(e));
+}
+
 template <class Kernel>
 inline int wave_grid(Kernel kernel, int threads, int waves, int& cache) {
   if (!cache) RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cache, kernel, threads, 0));
