@@ -585,9 +585,96 @@ void launch_far_and_H(System& s, DevView& v, const DevParams& P, const double* q
   s.kernel_launches++;
 }
 
+// Throughput form of the table mode for force-only steps (4 of 5 at thermo 5): when the CEvd / CEclmb coefficient sets of the
+// nt (nt + 1) / 2 unordered type pairs fit in shared memory (64 B per interval: N <= 318 knots for the 4 elements of TATB)
+// every CTA stages them once and a pair costs one square root, one index computation and two cubic Horner evaluations -
+// ~40 DP instructions against the 143 of the analytic kernel - with the coefficients coming from shared memory instead of
+// L2.  Same records, same operations and the same summation order as k_nonbonded_tab<false>, so the forces are
+// bit-identical to that kernel; what a coarse table costs in accuracy against the analytic form is measured by
+// tests/test_gpu_parity.py::test_tabulated_shared_memory_mode.  (reference: the table mode of reaxc_nonbonded_sunway.cpp:
+// 430-560 with LR_lookup_table from reaxc_lookup_sunway.cpp, whose builder is commented out there.)
+constexpr int kTabSmemThreads = 1024;
+__host__ __device__ inline int tab_pair_index(int a, int b, int nt) {   // unordered pair -> 0 .. nt (nt + 1) / 2 - 1
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  return lo * nt - lo * (lo - 1) / 2 + (hi - lo);
+}
+template <bool PACKED>
+__global__ void __launch_bounds__(kTabSmemThreads, 1)
+k_nonbonded_tab_smem(DevView v, DevParams P) {
+  extern __shared__ double4 s_lut[];   // [pair][interval][CEvd, CEclmb]
+  const int nt = P.nt, ln = P.lut_n;
+  const int npair = nt * (nt + 1) / 2;
+  for (int e = threadIdx.x; e < npair * ln * 2; e += blockDim.x) {
+    const int c = e & 1, r = (e >> 1) % ln, u = (e >> 1) / ln;
+    int ti = 0, rem = u;
+    while (rem >= nt - ti) { rem -= nt - ti; ti++; }
+    s_lut[e] = P.lut[((size_t)(ti * nt + ti + rem) * ln + r) * 4 + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const double nonb_cut2 = P.ctl.nonb_cut * P.ctl.nonb_cut;
+  const double dx = P.lut_dx, inv_dx = P.lut_inv_dx;
+  const int stride = v.vl_stride;
+  for (int i = wg; i < v.n; i += nwg) {
+    const int kself = v.rowpos[i];
+    const int ti = v.type_s[kself];
+    if (ti < 0) continue;
+    const double4 pi = v.xqs[kself];
+    const long long beg = (long long)i * stride;
+    const int num = v.far_num[i];
+    double fx = 0, fy = 0, fz = 0;
+    // same software pipeline as k_nonbonded: list word of chunk t+2 and the gather of chunk t+1 in flight
+    double4 p_cur = make_double4(0, 0, 0, 0);
+    int t_cur = -1;
+    if (lane < num) { const int j0 = far_col<PACKED>(v, beg, lane); p_cur = v.xqs[j0]; t_cur = v.type_s[j0]; }
+    FarRaw<PACKED> r_nxt = 32 + lane < num ? far_raw<PACKED>(v, beg, 32 + lane) : FarRaw<PACKED>(0);
+    for (int k0 = 0; k0 < num; k0 += 32) {
+      const FarRaw<PACKED> r_nn = k0 + 64 + lane < num ? far_raw<PACKED>(v, beg, k0 + 64 + lane) : FarRaw<PACKED>(0);
+      double4 p_nxt = make_double4(0, 0, 0, 0);
+      int t_nxt = -1;
+      if (k0 + 32 + lane < num) { const int jn = raw_col<PACKED>(r_nxt); p_nxt = v.xqs[jn]; t_nxt = v.type_s[jn]; }
+      const int tj = t_cur;
+      const double4 pj = p_cur;
+      p_cur = p_nxt; t_cur = t_nxt; r_nxt = r_nn;
+      if (tj < 0) continue;
+      const double dx_ = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      const double r2 = dist2_rn(dx_, dy, dz);
+      if (!(r2 <= nonb_cut2)) continue;
+      const double r_ij = sqrt(r2);
+      int r = (int)(r_ij * inv_dx);
+      if (r == 0) ++r;
+      const double dif = r_ij - (double)(r + 1) * dx;
+      const double4* rec = s_lut + ((size_t)tab_pair_index(ti, tj, nt) * ln + r) * 2;
+      const double4 cv = rec[0], cc = rec[1];
+      const double qq = pi.w * pj.w;
+      const double CEvd = ((cv.w * dif + cv.z) * dif + cv.y) * dif + cv.x;
+      const double CEclmb = (((cc.w * dif + cc.z) * dif + cc.y) * dif + cc.x) * qq;
+      const double ftot = CEvd + CEclmb;
+      fx += ftot * dx_; fy += ftot * dy; fz += ftot * dz;
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+      const int ia = v.row_atom[i];
+      atomicAdd(&v.f[3 * ia], fx); atomicAdd(&v.f[3 * ia + 1], fy); atomicAdd(&v.f[3 * ia + 2], fz);
+    }
+  }
+}
+
 void launch_nonbonded(System& s, DevView& v, const DevParams& P, bool evflag, cudaStream_t st) {
   if (v.n == 0) return;
   if (P.lut) {   // Compute_NonBonded_Forces: tabulate == 0 ? analytic : tables (reaxc_forces_sunway.cpp:148-160)
+    // force-only step and the force coefficient sets fit in shared memory: the throughput form (RXB_TAB_SMEM=0 keeps the
+    // L2 form; read at every launch so that a test can compare the two in one process)
+    const size_t tab_bytes = (size_t)(P.nt * (P.nt + 1) / 2) * P.lut_n * 2 * sizeof(double4);
+    const char* ts = getenv("RXB_TAB_SMEM");
+    if (!evflag && tab_bytes <= 200 * 1024 && !(ts && atoi(ts) == 0)) {
+      auto ks = v.hpk ? k_nonbonded_tab_smem<true> : k_nonbonded_tab_smem<false>;
+      RXB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      ks<<<148, kTabSmemThreads, tab_bytes, st>>>(v, P);
+      s.kernel_launches++;
+      return;
+    }
     static int occ[4] = {0, 0, 0, 0};
     auto kt = v.hpk ? (evflag ? k_nonbonded_tab<true, true> : k_nonbonded_tab<false, true>)
                     : (evflag ? k_nonbonded_tab<true, false> : k_nonbonded_tab<false, false>);

@@ -15,7 +15,8 @@ prof = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 box, x, t, tag = tatb_cell(nx, nx, nx)
 v = maxwell_velocities(t, 300.0, 12345)
 r = Rxb(0)
-r.pair_settings(CONTROL)
+tabn = int(os.environ.get("RXB_PROBE_TAB", "0"))      # > 0: table mode with that many knots (control file variant)
+r.pair_settings(control_variant("/tmp/control.probe_tab", tabn) if tabn > 0 else CONTROL)
 r.pair_coeff(FFIELD, ELEMENTS)
 r.fix_qeq(0.0, 10.0, 1e-6)
 r.md_setup(box, x, v, t, tag, MASS, dt=dt, every=5, thermo=5)

@@ -397,6 +397,39 @@ def test_tabulated_long_range_mode(tmp_path):
         assert rel(res["virial"], vo) < 10 * tol, name
 
 
+def test_tabulated_shared_memory_mode(tmp_path, monkeypatch):
+    """Coarse tables (tabulate_long_range 300: the CEvd / CEclmb coefficient sets of the 10 TATB type pairs fit in shared
+    memory) switch force-only steps to k_nonbonded_tab_smem.  It must give the forces of the L2-resident table kernel
+    (same records, same operations) and the oracle's table-mode forces; the price of the coarse table against the analytic
+    form is measured and bounded here."""
+    from sw_reaxff_b200 import Rxb
+    ctl = H.control_variant(tmp_path / "control.tab300", 300)
+    out = {}
+    for name, control in (("table", ctl), ("analytic", H.CONTROL)):
+        cfg = H.static_config(2, 1, 1, perturb=0.1, seed=22, qeq=True, oracle=H.Oracle(control=control))
+        o = cfg["oracle"]
+        n, x, ty, tg, owner, q = cfg["n"], cfg["x"], cfg["type"], cfg["tag"], cfg["owner"], cfg["q"]
+        o.set_atoms(n, x, ty, tg, q)
+        o.build_neighbors(12.5)
+        o.compute()
+        out[name] = o.forces()
+    r = Rxb(0)
+    r.pair_settings(ctl)
+    r.pair_coeff(H.FFIELD, H.ELEMENTS)
+    r.set_atoms(n, x, ty, tg, q, owner)
+    r.neigh_build()
+    f_ev = r.pair_compute(True, True)["f"].copy()          # energy step: L2-resident table kernel
+    monkeypatch.setenv("RXB_TAB_SMEM", "1")
+    f_smem = r.pair_compute(False, False)["f"].copy()      # force-only step: shared-memory tables
+    monkeypatch.setenv("RXB_TAB_SMEM", "0")
+    f_l2 = r.pair_compute(False, False)["f"].copy()        # force-only step, L2 tables
+    assert rel(f_smem, f_l2) < 1e-12 and rel(f_smem, f_ev) < 1e-12
+    assert rel(f_smem, out["table"]) < 1e-7
+    dev = rel(f_smem, out["analytic"])
+    print(f"coarse-table deviation from the analytic forces (N = 300): {dev:.3e}")
+    assert dev < 2e-3
+
+
 def test_neighbor_rows_outgrowing_the_stride_are_rebuilt():
     """Neighbour rows live at a fixed stride sized by the previous build.  Re-using one handle for a configuration whose
     rows are ~60 % longer (1.05 -> 0.90 linear scale) must trigger the re-run with a larger stride and still give the
