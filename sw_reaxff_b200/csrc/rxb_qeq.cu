@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(kVecThreads)
 k_cg_sweep(int n, int it, int first, double tol, int imax, const int* __restrict__ rowpos, const double* __restrict__ Hd,
            const double2* __restrict__ q, double2* __restrict__ x, double2* __restrict__ r, double2* __restrict__ u,
            double2* __restrict__ w, double2* __restrict__ p, double2* __restrict__ ss, double2* __restrict__ v,
-           double2* __restrict__ z, double2* __restrict__ dS, QeqDev* __restrict__ Q) {
+           double2* __restrict__ z, double2* __restrict__ dS, QeqDev* __restrict__ Q, const int* __restrict__ img_off,
+           const int* __restrict__ img_pos) {
   pdl_wait(); pdl_release();
   const int par = it & 1;
   const QeqState S = Q->st[par];
@@ -283,6 +284,8 @@ k_cg_sweep(int n, int it, int first, double tol, int imax, const int* __restrict
           dj.y = wj.y * hd;
         }
         r[j] = rj; u[j] = uj; w[j] = wj; dS[kj] = dj;
+        if (img_off)   // this row's periodic images (single-rank forward_comm_fix, fused)
+          for (int k = img_off[j], k1 = img_off[j + 1]; k < k1; k++) dS[img_pos[k]] = dj;
       }
     }
   if (actA0 | actA1) block_reduce_add<4>(acc, Q->dots[(it + 1) % 3]);
@@ -356,8 +359,10 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
 // one CG iteration of loop index `it`: fused sweep, halo of d (+ the dot products in multi-GPU runs), gated SpMV
 void System::qeq_iteration(int it) {
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
+  const bool fused = !dist_ && img_valid_;   // the sweep stores each row's value into its periodic images itself
   launch_pdl(k_cg_sweep, kVecBlocks, kVecThreads, 0, st_, n, it, (int)(it == 1), qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p,
-             q_x.p, q_r.p, q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q);
+             q_x.p, q_r.p, q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q, fused ? img_off.p : nullptr,
+             fused ? img_pos.p : nullptr);
   kernel_launches++;
   const int par_next = (it & 1) ^ 1;  // state written by this sweep (from the dot products of the sweep before it)
   // MPI_Allreduce(dot_local, 2) of each solve (:1132) and the boundary values of d travel in one exchange.  Multi-GPU with
@@ -375,7 +380,7 @@ void System::qeq_iteration(int it) {
     return;
   }
   if (dist_) dist_forward2_dots(q_d.p, Q->dots[(it + 1) % 3]);
-  else qeq_forward_S(q_d.p);
+  else if (!fused) qeq_forward_S(q_d.p);
   qeq_spmv(q_d.p, q_q.p, true, par_next);
 }
 

@@ -112,6 +112,28 @@ __global__ void k_sorted_ghosts(int n, int nghost, const int* __restrict__ a2s, 
   gs_own[g] = o >= 0 ? a2s[o] : -1;
 }
 
+// Periodic images of each local row, as a CSR list of sorted positions: lets the CG sweep store a row's new search-direction
+// value into its images itself (single-rank forward_comm_fix fused into the producer; no separate ghost-copy launch)
+__global__ void k_row_of_atom(int n, const int* __restrict__ row_atom, int* __restrict__ row_of_atom) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) row_of_atom[row_atom[r]] = r;
+}
+__global__ void k_img_count(int nghost, int n, const int* __restrict__ owner, const int* __restrict__ row_of_atom, int* __restrict__ cnt) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int o = owner[g];
+  if (o >= 0 && o < n) atomicAdd(&cnt[row_of_atom[o]], 1);
+}
+__global__ void k_img_fill(int nghost, int n, const int* __restrict__ owner, const int* __restrict__ row_of_atom,
+                           const int* __restrict__ off, int* __restrict__ cursor, const int* __restrict__ gs_pos, int* __restrict__ img_pos) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int o = owner[g];
+  if (o < 0 || o >= n) return;
+  const int r = row_of_atom[o];
+  img_pos[off[r] + atomicAdd(&cursor[r], 1)] = gs_pos[g];
+}
+
 // virial_fdotr over all atoms, pair_reaxc_sunway.cpp:674-702
 __global__ void k_fdotr(int N, const double4* __restrict__ xq, const double* __restrict__ f, double* __restrict__ virial) {
   double v[6] = {0, 0, 0, 0, 0, 0};
@@ -577,6 +599,23 @@ void System::build_sorted_space() {
   if (nghost > 0)
     k_sorted_ghosts<<<nblk(nghost), 256, 0, st_>>>(n, nghost, a2s.p, dist_ ? nullptr : ghost_owner.p, gs_pos.p, gs_own.p);
   kernel_launches += 4;
+  // image lists per row (single-rank runs; RXB_FUSE_FWD=0 keeps the separate ghost-copy kernel in the CG loop)
+  static const bool fuse_fwd = !(getenv("RXB_FUSE_FWD") && atoi(getenv("RXB_FUSE_FWD")) == 0);
+  img_valid_ = false;
+  if (!dist_ && fuse_fwd && nghost > 0 && n > 0) {
+    row_of_atom.resize(n); img_off.resize(n + 1); img_cur.resize(n + 1); img_pos.resize(nghost);
+    RXB_CUDA(cudaMemsetAsync(img_cur.p, 0, (size_t)(n + 1) * sizeof(int), st_));
+    k_row_of_atom<<<nblk(n), 256, 0, st_>>>(n, row_atom.p, row_of_atom.p);
+    k_img_count<<<nblk(nghost), 256, 0, st_>>>(nghost, n, ghost_owner.p, row_of_atom.p, img_cur.p);
+    size_t need2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need2, img_cur.p, img_off.p, n + 1, st_);
+    scan_temp.resize(need2 + 16);
+    cub::DeviceScan::ExclusiveSum(scan_temp.p, need2, img_cur.p, img_off.p, n + 1, st_);
+    RXB_CUDA(cudaMemsetAsync(img_cur.p, 0, (size_t)(n + 1) * sizeof(int), st_));
+    k_img_fill<<<nblk(nghost), 256, 0, st_>>>(nghost, n, ghost_owner.p, row_of_atom.p, img_off.p, img_cur.p, gs_pos.p, img_pos.p);
+    kernel_launches += 4;
+    img_valid_ = true;
+  }
 }
 
 // fix qeq/reax <param file>: chi, eta, gamma per LAMMPS type (index 1..ntypes; ntypes = 0 returns to the pair style's values)

@@ -285,6 +285,8 @@ class System {
   DBuf<float4> xf;           // fp32 shadow in atom order (bond-candidate prefilter)
   // S space (rxb_dev.cuh): cell-sorted order of the last neighbour build
   DBuf<int> s2a, a2s, rowpos, row_atom, type_s, gs_pos, gs_own;
+  DBuf<int> row_of_atom, img_off, img_cur, img_pos;   // periodic images of each row (CSR of sorted positions), single-rank runs
+  bool img_valid_ = false;
   DBuf<long long> row_flag, row_scan;
   DBuf<float4> xs;
   DBuf<double4> xqs;
