@@ -697,7 +697,10 @@ void System::build_neighbors() {
   const int t_NEIGH = tick(StepTimers::NEIGH);
   const double cn = cutneigh();
   // Verlet list for local rows: bins of cn/2, +-2 cells
-  cells_a_.bin(xq.p, N, cn / 2.0, 2, st_);
+  // bins of cn / reach, +-reach cells (RXB_VL_REACH, default 2): finer y/z bins make the sorted order - and with it every
+  // gather of the long-range kernels - more local and trim the candidate volume, at the price of more, shorter runs
+  static const int vl_reach = getenv("RXB_VL_REACH") ? std::max(1, atoi(getenv("RXB_VL_REACH"))) : 2;
+  cells_a_.bin(xq.p, N, cn / vl_reach, vl_reach, st_);
   build_sorted_space();
   // rows partitioned at far cut-off + kInnerSkin: between rebuilds the per-step far-list sweep reads only that block while
   // no atom has moved more than kInnerSkin / 2 (checked on the device every step)
