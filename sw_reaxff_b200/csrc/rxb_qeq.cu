@@ -155,6 +155,94 @@ k_spmv2_deep(int r0, int r1, int stride, const int* __restrict__ num, const unsi
   }
 }
 
+// Bulk-async form of the packed SpMV (experiment, RXB_SPMV_BULK=1): the H words of a row are contiguous, so one elected lane
+// per warp fetches them with cp.async.bulk (the TMA engine, SASS UBLKCP) into a warp-private double buffer in shared memory
+// and completion is signalled on an mbarrier; the copy of stage s+1 - the next 256 entries of the row, or the head of the
+// warp's NEXT row - is in flight while stage s is multiplied.  The word stream then costs no registers, no global LSU
+// wavefronts and no scoreboard slots; the 16-byte gathers of the CG vector stay as they are.  Persistent grid, one warp
+// walks rows wg, wg + nwarps, ...  Measured against k_spmv2_deep<8>: profiles/r02_spmv_ab.txt.
+constexpr int kBulkChunk = 256;   // entries per stage (2 KB): 8 per lane, the depth of the deep kernel
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_issue(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  if (bytes == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); return; }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' earlier generic reads of this buffer are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  for (int spin = 0; !ok; spin++) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (spin > (1 << 24)) __trap();    // a copy that never completes must not hang the GPU
+  }
+}
+__global__ void __launch_bounds__(kWarps * 32)
+k_spmv2_bulk(int r0, int r1, int stride, const int* __restrict__ num, const unsigned long long* __restrict__ hpk,
+             double inv_quant, const int* __restrict__ rowpos, const double* __restrict__ eta_row, const double2* __restrict__ x,
+             double2* __restrict__ y, const QeqDev* __restrict__ Q, int parity, unsigned long long* __restrict__ active_launches) {
+  pdl_wait(); pdl_release();
+  if (Q != nullptr && !(Q->st[parity].active[0] | Q->st[parity].active[1])) return;
+  if (active_launches && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(active_launches, 1ULL);
+  __shared__ __align__(16) unsigned long long s_buf[kWarps][2][kBulkChunk];
+  __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+  const unsigned bar[2] = {smem_u32(&s_bar[wib][0]), smem_u32(&s_bar[wib][1])};
+  const unsigned dst[2] = {smem_u32(&s_buf[wib][0][0]), smem_u32(&s_buf[wib][1][0])};
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[0]) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[1]) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  int i = r0 + wg;
+  if (i >= r1) return;
+  int m = num[i], c = 0;
+  auto stage_bytes = [](int mm, int cc) { return (unsigned)(((min(kBulkChunk, mm - cc * kBulkChunk) * 8) + 15) & ~15); };
+  if (lane == 0) bulk_issue(dst[0], hpk + (long long)i * stride, m > 0 ? stage_bytes(m, 0) : 0u, bar[0]);
+  double ax = 0, ay = 0;
+  for (unsigned s = 0;; s++) {
+    // the stage after this one: the next chunk of the row, or the head of the warp's next row
+    int ni = i, nc = c + 1, nm = m;
+    if (nc * kBulkChunk >= m) { ni = i + nwg; nc = 0; nm = ni < r1 ? num[ni] : 0; }
+    const bool has_next = ni < r1;
+    if (has_next && lane == 0)
+      bulk_issue(dst[(s + 1) & 1], hpk + (long long)ni * stride + (long long)nc * kBulkChunk, nm > 0 ? stage_bytes(nm, nc) : 0u,
+                 bar[(s + 1) & 1]);
+    bulk_wait(bar[s & 1], (s >> 1) & 1);
+    const unsigned long long* wbuf = &s_buf[wib][s & 1][0];
+    const int cnt = min(kBulkChunk, m - c * kBulkChunk);
+    unsigned long long w[8];
+    double2 xj[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int k = 32 * u + lane; w[u] = k < cnt ? wbuf[k] : 0ULL; }
+#pragma unroll
+    for (int u = 0; u < 8; u++) xj[u] = __ldg(x + (int)(w[u] >> kHColShift));
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const double h = __longlong_as_double((long long)((w[u] & kHValMask) | 0x4330000000000000ULL)) - 4503599627370496.0;
+      ax += h * xj[u].x; ay += h * xj[u].y;
+    }
+    if ((c + 1) * kBulkChunk >= m) {   // last stage of the row
+      ax = warp_sum(ax * inv_quant); ay = warp_sum(ay * inv_quant);
+      if (lane == 0) {
+        const double eta = eta_row[i];
+        const double2 xi = x[rowpos[i]];
+        y[i] = make_double2(eta * xi.x + ax, eta * xi.y + ay);
+      }
+      ax = 0; ay = 0;
+    }
+    __syncwarp();                      // every lane has read this buffer before stage s + 2 refills it
+    if (!has_next) break;
+    i = ni; c = nc; m = nm;
+  }
+}
+
 // prologue steps (fix_qeq_reax_sunway.cpp:1024-1105)
 __global__ void k_pro1(int n, const int* __restrict__ rowpos, const double2* __restrict__ b, const double2* __restrict__ q,
                        const double* __restrict__ Hd, double2* __restrict__ r, double2* __restrict__ u, double2* __restrict__ dS) {
@@ -416,7 +504,11 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
   // SpMV 5.72 -> 5.31 ms/step, step 11.64 -> 11.22; 16 per lane is no better; any occupancy cap is far worse)
   static const int deep = getenv("RXB_SPMV_DEEP") ? atoi(getenv("RXB_SPMV_DEEP")) : 8;
   static const int deep_grid = getenv("RXB_SPMV_GRID") ? atoi(getenv("RXB_SPMV_GRID")) : 0;   // persistent grid (CTAs), 0 = one row per warp
-  if (h_packed_ && deep && !rowlist) {
+  static const int bulk = getenv("RXB_SPMV_BULK") ? atoi(getenv("RXB_SPMV_BULK")) : 0;     // CTAs per SM of the bulk-async form, 0 = off
+  if (h_packed_ && bulk > 0 && !rowlist) {
+    launch_pdl(k_spmv2_bulk, std::min(148 * bulk, grid), kWarps * 32, 0, st_, r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_,
+               rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
+  } else if (h_packed_ && deep && !rowlist) {
     const int g = deep_grid > 0 ? deep_grid : grid;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
