@@ -7,7 +7,4 @@ import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1]); k = d['kernel_ms_per_step']
 print('$*', round(d['ms_per_step'], 3), 'cg', k['qeq_cg'], 'spmv', k['spmv'], 'non-spmv', round(k['qeq_cg'] - k['spmv'], 3))"
 }
-run RXB_PDL=1
-run RXB_PDL=0
-run RXB_PDL=1
-run RXB_PDL=0
+for v in ${AB_VALUES:-1 0 1 0}; do run ${AB_VAR:-RXB_PDL}=$v; done
