@@ -824,10 +824,10 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
     RXB_CUDA(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_enum));
     smem_enum_set = smem_enum;
   }
-  k_enum<<<wave_grid(k_enum, kWarps * 32, 1, occ_enum), kWarps * 32, smem_enum, st>>>(v, P, W);
+  k_enum<<<wave_grid(k_enum, kWarps * 32, chain_waves(), occ_enum), kWarps * 32, smem_enum, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::HBOND, st);
-  k_hbond_items<<<wave_grid(k_hbond_items, kItemThreads, kItemWaves, occ_hb), kItemThreads, 0, st>>>(v, P, W);
+  k_hbond_items<<<wave_grid(k_hbond_items, kItemThreads, kItemWaves * chain_waves(), occ_hb), kItemThreads, 0, st>>>(v, P, W);
   s.tock(t, st);
   t = s.tick(StepTimers::VALTOR, st);
   // resident CTAs per SM the register allocation is bounded for (dev knobs RXB_ANG_OCC / RXB_TOR_OCC, A/B in
@@ -835,7 +835,7 @@ void launch_bonded_part2(System& s, DevView& v, const DevParams& P, cudaStream_t
   static const int ang_minb = getenv("RXB_ANG_OCC") ? atoi(getenv("RXB_ANG_OCC")) : 3;
   static const int tor_minb = getenv("RXB_TOR_OCC") ? atoi(getenv("RXB_TOR_OCC")) : 3;
 #define RXB_ITEM_LAUNCH(K, MINB, OCC) \
-  K<MINB><<<wave_grid(K<MINB>, kItemThreads, kItemWaves, OCC), kItemThreads, 0, st>>>(v, P, W)
+  K<MINB><<<wave_grid(K<MINB>, kItemThreads, kItemWaves * chain_waves(), OCC), kItemThreads, 0, st>>>(v, P, W)
   switch (ang_minb) {
     case 4: RXB_ITEM_LAUNCH(k_angle_items, 4, occ_ang); break;
     case 5: RXB_ITEM_LAUNCH(k_angle_items, 5, occ_ang); break;
@@ -859,7 +859,7 @@ void launch_dbond(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   (void)P;
   if (v.N == 0) return;
   static int occ_dbond = 0;
-  k_dbond<<<wave_grid(k_dbond, kWarps * 32, 1, occ_dbond), kWarps * 32, 0, st>>>(v, s.bonded_work());
+  k_dbond<<<wave_grid(k_dbond, kWarps * 32, chain_waves(), occ_dbond), kWarps * 32, 0, st>>>(v, s.bonded_work());
   s.kernel_launches++;
 }
 

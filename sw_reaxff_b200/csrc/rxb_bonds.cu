@@ -333,7 +333,7 @@ void launch_bond_list(System& s, DevView& v, const DevParams& P, cudaStream_t st
 void launch_bond_orders(System& s, DevView& v, const DevParams& P, cudaStream_t st) {
   if (v.N == 0) return;
   static int occ = 0;
-  k_bond_orders<<<wave_grid(k_bond_orders, 256, 2, occ), 256, 0, st>>>(v, P);
+  k_bond_orders<<<wave_grid(k_bond_orders, 256, 2 * chain_waves(), occ), 256, 0, st>>>(v, P);
   k_bond_order_atoms<<<(v.N + 255) / 256, 256, 0, st>>>(v, P);
   s.kernel_launches += 2;
 }

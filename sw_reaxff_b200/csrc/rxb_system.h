@@ -407,6 +407,9 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch failed: ") + cudaGetErrorString(e));
 }
 
+// RXB_CHAIN_WAVES (development knob, default 1): multiplies the wave count of the bonded-chain kernels - more, shorter CTAs,
+// so that work queued on the low-priority stream hands the SMs back quickly when a solve kernel arrives
+inline int chain_waves() { static const int w = getenv("RXB_CHAIN_WAVES") ? std::max(1, atoi(getenv("RXB_CHAIN_WAVES"))) : 1; return w; }
 template <class Kernel>
 inline int wave_grid(Kernel kernel, int threads, int waves, int& cache) {
   if (!cache) RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cache, kernel, threads, 0));
