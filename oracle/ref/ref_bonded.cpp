@@ -131,7 +131,14 @@ void ref_bop_pairs(void* hp, int npairs, const int* ti, const int* tj, const dou
   }
 }
 
-// which: bit 0 = Torsion_Angles (valence + torsion), bit 1 = Hydrogen_Bonds, bit 2 = Add_dBond_to_Forces over i < j.
+// data->my_ext_press after the last ref_bonded call: what the control->virial = 1 (NPT) branches accumulate.  The LAMMPS
+// interface writes rel_box = 0 for every neighbour (pair_reaxc_sunway.cpp:927), and so does this harness (memset), so
+// every rvec_iMultiply(ext_press, rel_box, force) contribution is zero.
+static double g_ext_press[3] = {0, 0, 0};
+void ref_last_ext_press(double* out3) { for (int t = 0; t < 3; t++) out3[t] = g_ext_press[t]; }
+
+// which: bit 0 = Torsion_Angles (valence + torsion), bit 1 = Hydrogen_Bonds, bit 2 = Add_dBond_to_Forces over i < j,
+// bit 3 = Add_dBond_to_Forces_NPT over i < j (reaxc_bond_orders_sunway.cpp:41-180, the control->virial = 1 form).
 // fields31 / w16 are the oracle's dumps (orc_get_bonds / orc_get_workspace); Cd_in[3][nb], CdDelta_in[N] seed the
 // accumulators (zeros for an isolated term).  Outputs: en6 = e_ang,e_pen,e_coa,e_tor,e_con,e_hb; fCd[N][4] (-force,
 // CdDelta); Cd_out[3][nb].
@@ -226,6 +233,11 @@ int ref_bonded(void* hp, int which, int n, int N, const double* x, const int* ty
     for (int i = 0; i < N; i++)   // the stock driver loop: every bond once, from its lower-index end
       for (int pj = bidx[i]; pj < bend[i]; ++pj)
         if (i < bd[pj].nbr) Add_dBond_to_Forces(sys, i, pj, &ws, &lp);
+  if (which & 8)
+    for (int i = 0; i < N; i++)
+      for (int pj = bidx[i]; pj < bend[i]; ++pj)
+        if (i < bd[pj].nbr) Add_dBond_to_Forces_NPT(i, pj, &data, &ws, &lp);
+  for (int t = 0; t < 3; t++) g_ext_press[t] = data.my_ext_press[t];
 
   en6[0] = data.my_en.e_ang; en6[1] = data.my_en.e_pen; en6[2] = data.my_en.e_coa;
   en6[3] = data.my_en.e_tor; en6[4] = data.my_en.e_con; en6[5] = data.my_en.e_hb;

@@ -206,6 +206,33 @@ def test_valence_torsion_hbond_dbond_equal_reference_serial_routines(perturb, se
     assert relerr(-fcd3[:, :3], df) < 1e-10
 
 
+def test_npt_branches_same_forces_and_zero_ext_press():
+    """control->virial = 1 (PuReMD's NPT switch): Torsion_Angles and Hydrogen_Bonds take their serial branches and
+    Add_dBond_to_Forces_NPT replaces Add_dBond_to_Forces; each adds rvec_iMultiply(ext_press, rel_box, force) to
+    data->my_ext_press.  Behind the LAMMPS interface rel_box is zero for every neighbour (pair_reaxc_sunway.cpp:927), so the
+    branches must give the virial = 0 forces and a zero my_ext_press - which is why the product path has no NPT variant
+    (DESIGN.md section 8)."""
+    L, P = _ref_lib()
+    cfg, o = _state(0.08, 11, 0.95)
+    press = np.zeros(3)
+    get = lambda: (L.ref_last_ext_press(press.ctypes.data_as(C.c_void_p)), press.copy())[1]
+    en, fcd, cd = _call_ref(L, P, 1, cfg, o)                   # valence + torsion, virial = 1 branch
+    assert np.abs(fcd[:, :3]).max() > 1.0 and np.all(get() == 0.0)
+    o.phase(0); o.phase(7)
+    bs, be, nbr, sym, fld = o.bonds()
+    Cd_vt, CdD_vt = fld[:, 28:31].T.copy(), o.cddelta().copy()
+    en2, fcd2, cd2 = _call_ref(L, P, 2, cfg, o, Cd_in=Cd_vt, CdDelta_in=CdD_vt)     # hydrogen bonds, virial = 1 branch
+    assert abs(en2[5]) > 1.0 and np.all(get() == 0.0)
+    o.phase(6)
+    bs, be, nbr, sym, fld = o.bonds()
+    Cd_all, CdD_all = fld[:, 28:31].T.copy(), o.cddelta().copy()
+    _, f_plain, _ = _call_ref(L, P, 4, cfg, o, Cd_in=Cd_all, CdDelta_in=CdD_all)    # Add_dBond_to_Forces
+    _, f_npt, _ = _call_ref(L, P, 8, cfg, o, Cd_in=Cd_all, CdDelta_in=CdD_all)      # Add_dBond_to_Forces_NPT
+    assert np.all(get() == 0.0)
+    assert np.abs(f_plain[:, :3]).max() > 10.0
+    assert relerr(f_npt[:, :3], f_plain[:, :3]) < 1e-13
+
+
 def test_taper_equals_reference_Init_Taper():
     L, P = _ref_lib()
     tap = np.zeros(8)
