@@ -1,5 +1,7 @@
-// Bonded energy terms and the dE/dBO chain rule: all enumerated from the device bond CSR, one warp per centre atom,
-// grid-stride persistent blocks, fp64 atomics for the scatters.
+// Bonded energy terms and the dE/dBO chain rule, all from the device bond CSR.  A light integer kernel (K-enum, eight
+// lanes per centre atom) emits dense work lists of angles / torsions / hydrogen-bond candidates; the heavy fp64 kernels run
+// one thread per list item with every lane busy; K-multi runs one thread per atom (a 13-exp scalar chain), K-dbond 8 lanes
+// per atom.  One wave of resident CTAs per item kernel, fp64 atomics for the scatters.
 //
 //   K-multi : lone pair / over- / under-coordination + bond energy + e_pol
 //             /root/reference/reaxc_multi_body_sw64.c:21-333 (runs SERIALLY on the MPE in the reference)
@@ -9,9 +11,10 @@
 //             Calculate_Theta / dCos_Theta  reaxc_valence_angles_sunway.cpp:50-84, Calculate_Omega reaxc_torsion_angles_sunway.cpp:44-125
 //   K-dbond : Add_All_dBond_to_Forces_C, no-branch directed form /root/reference/reaxc_forces_sw64.c:500-587
 // The reference serialises scatter conflicts with locked software write caches (SWCACHE_UPDATE); here the per-bond
-// coefficient sums that every angle of a centre adds to ALL of its bonds are reduced in the warp first, and only
-// what genuinely leaves the warp's rows goes through atomicAdd(double).
-// Roofline: fp64-compute bound (acos/atan2/exp/pow per angle and per torsion), SURVEY.md §8d.
+// coefficient sums that every angle of a centre adds to ALL of its bonds (CEval5 / CEval6) are accumulated per centre and
+// applied inside K-dbond, everything else goes through atomicAdd(double).
+// Roofline: fp64 / latency bound (exp and pow per angle and torsion; no trigonometric call is left: the angles are acos()
+// of clamped cosines, so their sines, cos(n omega) and sin^4(theta/2) are algebra), SURVEY.md §8d, DESIGN.md §3.
 #include "rxb_system.h"
 
 namespace rxb {

@@ -3,9 +3,11 @@
 //   K-farH : write_reax_lists_c (r <= nonb_cut filter)   /root/reference/pair_reaxc_sw64.c:49-95,193-341
 //            + compute_H_Full_C / calculate_H            /root/reference/fix_qeq_reax_sw64.c:147-189, fix_qeq_reax_sunway.cpp:965-981
 //            The reference materialises 64-byte far_neighbor_data_full records (29 KB/atom/step) AND a separate
-//            600-wide H row; here both are ONE compacted int32 column list (+ one fp64 value) in the slots of the
-//            Verlet row, because "r <= nonb_cut" and "r <= swb" select the same pairs (both 10 A in every shipped
-//            input; if they differ the list takes the larger cut-off and each consumer re-tests its own).
+//            600-wide H row; here both are ONE compacted list in the slots of the Verlet row - a 64-bit word per entry
+//            (22-bit column + 42-bit fixed-point H value; or int32 column + fp64 value in the exact format) - because
+//            "r <= nonb_cut" and "r <= swb" select the same pairs (both 10 A in every shipped input; if they differ the
+//            list takes the larger cut-off and each consumer re-tests its own).  One pass (k_far_H1): exact gather, fp64
+//            decision, H value, warp compaction; the hydrogen-bond candidates ride on the same sweep.
 //   K-nb   : vdW_Coulomb_Energy_Full_C                   /root/reference/reaxc_nonbonded_sw64.c:40-258 (serial twin)
 //            full list, local i only, force on i only (no scatter), 1/2 energy per directed pair,
 //            pair virial + (-x_i (x) f_i) correction as reaxc_nonbonded_cpe.h:531-536 / reaxc_nonbonded_sw64.c:247-252.
