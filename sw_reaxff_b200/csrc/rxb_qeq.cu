@@ -487,7 +487,7 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
   if (r1 <= r0) return;
   const int* rowlist = (qeq_split_rows() && dist_ && n_interior_ > 0) ? q_rowlist.p : nullptr;   // interior rows first, then boundary rows
   const int ts = tick(r0 > 0 ? StepTimers::SPMV_B : StepTimers::SPMV);
-  // one row per warp, blocks retire continuously: lets the high-priority bond-chain stream interleave on every SM
+  // one row per warp, blocks retire continuously: the bond-chain stream (low priority) picks up the slots they free
   const int grid = std::max(1, (r1 - r0 + kWarps - 1) / kWarps);
   // RXB_SPMV_SMEM=<bytes> (development knob): an unused dynamic shared-memory request per CTA caps the CTAs resident per SM,
   // i.e. how many warp slots the SpMV leaves to the bonded chain running beside it on the second stream
