@@ -185,6 +185,10 @@ int rxb_species_config(rxb_handle* h, int nevery, int nrepeat, int nfreq, int nt
 int rxb_species_step(rxb_handle* h, long ntimestep, int* found);
 int rxb_species_result(rxb_handle* h, int* nmole, int* composition, long cap);
 int rxb_species_cluster(rxb_handle* h, int* cluster_of_local);
+/* `position` keyword (WritePos, fix_reaxc_species_sunway.cpp:814-925): the hidden fix ave/atom's result for the q, x, y, z
+ * columns of compute SPEC/ATOM over the window that just ended, [nlocal][4]; valid right after rxb_species_step found an
+ * output step */
+int rxb_species_avg_qxyz(rxb_handle* h, double* qxyz4);
 int rxb_species_log_size(rxb_handle* h);
 int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* composition, long cap);
 

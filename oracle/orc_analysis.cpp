@@ -111,14 +111,19 @@ bool SpeciesFix::post_integrate(const MD& md, long step) {
   if (step == ave_nvalid) {            // FixAveAtom::end_of_step
     pair_find_bond(md);                // the pair style refreshed tmpid/tmpbo in its last compute()
     const size_t m = (size_t)md.nlocal * MAXSPECBOND;
-    if (irepeat == 0) array.assign(m, 0.0);
+    if (irepeat == 0) { array.assign(m, 0.0); qxyz.assign((size_t)4 * md.nlocal, 0.0); }
     for (size_t k = 0; k < m; k++) array[k] += tmpbo[k];
+    for (int i = 0; i < md.nlocal; i++) {            // columns 0..3 of compute SPEC/ATOM: q, x, y, z (:142-170)
+      qxyz[4 * (size_t)i] += md.sys.q[i];
+      for (int t = 0; t < 3; t++) qxyz[4 * (size_t)i + 1 + t] += md.sys.x[3 * (size_t)i + t];
+    }
     irepeat++;
     if (irepeat < nrepeat) ave_nvalid += nevery;
     else {
       irepeat = 0;
       ave_nvalid = step + nfreq - (long)(nrepeat - 1) * nevery;
       for (size_t k = 0; k < m; k++) array[k] /= nrepeat;
+      for (double& a : qxyz) a /= nrepeat;
     }
   }
   if (step != nvalid) return false;
@@ -219,6 +224,74 @@ std::string SpeciesFix::formulas_text(long ntimestep) const {  // WriteFormulas 
   appendf(out, "%11d%11d\t", Nmole, Nspec);
   for (int i = 0; i < Nspec; i++) appendf(out, " %d\t", NMol[i]);
   out += "\n";
+  return out;
+}
+
+// WritePos :814-925.  x0 of a molecule is the fixed point of FindMolecule's anchor propagation (:530-532, :559-569 with
+// chAnchor :497-510): every atom starts from its own averaged position, bonded atoms take the lexicographically smaller
+// (x, then y, then z) of their two anchors until nothing changes, ghosts carry their owner's anchor unshifted
+// (pack/unpack_forward_comm :955-982) - i.e. the lexicographic minimum over the molecule.
+std::string SpeciesFix::pos_text(const MD& md, long ntimestep, const double* box6) {
+  static const char ele[4] = {'C', 'H', 'O', 'N'};
+  const int nlocal = md.nlocal;
+  const double* lo = box6;
+  const double* hi = box6 + 3;
+  const double box[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+  const double halfbox[3] = {box[0] / 2, box[1] / 2, box[2] / 2};
+  // (the reference shifts the averaged columns in place; they are re-zeroed by the next averaging cycle before anything
+  // reads them again, so a working copy is equivalent and keeps this routine repeatable)
+  std::vector<double> col = qxyz;
+  std::vector<double> anchor((size_t)3 * Nmole, 0.0);
+  std::vector<char> have(Nmole, 0);
+  for (int i = 0; i < nlocal; i++) {
+    const int m = nint(clusterID[i]) - 1;
+    const double* xi = &col[4 * (size_t)i + 1];
+    double* a = &anchor[3 * (size_t)m];
+    const bool less = !have[m] || xi[0] < a[0] || (xi[0] == a[0] && (xi[1] < a[1] || (xi[1] == a[1] && xi[2] < a[2])));
+    if (less) { a[0] = xi[0]; a[1] = xi[1]; a[2] = xi[2]; have[m] = 1; }
+  }
+  std::string out;
+  appendf(out, "Timestep %ld NMole %d  NSpec %d  xlo %f  xhi %f  ylo %f  yhi %f  zlo %f  zhi %f\n", ntimestep, Nmole, Nspec, lo[0],
+          hi[0], lo[1], hi[1], lo[2], hi[2]);
+  out += "ID\tAtom_Count\tType\tAve_q\t\tCoM_x\t\tCoM_y\t\tCoM_z\n";
+  std::vector<int> Name(ntypes);
+  for (int m = 1; m <= Nmole; m++) {
+    int count = 0;
+    double avq = 0.0, avx[3] = {0, 0, 0};
+    std::fill(Name.begin(), Name.end(), 0);
+    const double* x0 = &anchor[3 * (size_t)(m - 1)];
+    for (int i = 0; i < nlocal; i++) {
+      if (nint(clusterID[i]) != m) continue;
+      Name[md.ltype[i] - 1]++;
+      count++;
+      double* sa = &col[4 * (size_t)i];
+      avq += sa[0];
+      for (int t = 0; t < 3; t++) {
+        if ((x0[t] - sa[1 + t]) > halfbox[t]) sa[1 + t] += box[t];
+        if ((sa[1 + t] - x0[t]) > halfbox[t]) sa[1 + t] -= box[t];
+      }
+      for (int t = 0; t < 3; t++) avx[t] += sa[1 + t];
+    }
+    appendf(out, "%d\t%d\t", m, count);
+    for (int n = 0; n < ntypes; n++)
+      if (Name[n] != 0) {
+        appendf(out, "%c", ele[n]);
+        if (Name[n] != 1) appendf(out, "%d", Name[n]);
+      }
+    if (count > 0) {
+      avq /= count;
+      for (int k = 0; k < 3; k++) {
+        avx[k] /= count;
+        if (avx[k] >= hi[k]) avx[k] -= box[k];
+        if (avx[k] < lo[k]) avx[k] += box[k];
+        avx[k] -= lo[k];
+        avx[k] /= box[k];
+      }
+      appendf(out, "\t%.8f \t%.8f \t%.8f \t%.8f", avq, avx[0], avx[1], avx[2]);
+    }
+    out += "\n";
+  }
+  out += "#\n";
   return out;
 }
 

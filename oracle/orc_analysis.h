@@ -19,6 +19,7 @@ struct SpeciesFix {
   std::vector<double> BOCut;          // (ntypes+1)^2
   std::vector<int> tmpid;             // [N][MAXSPECBOND] local index of the bonded partner, 0 = unused
   std::vector<double> tmpbo, array;   // current and averaged bond orders
+  std::vector<double> qxyz;           // [nlocal][4]: the fix ave/atom result for compute SPEC/ATOM's q, x, y, z columns
   std::vector<double> clusterID;
   int Nmole = 0, Nspec = 0;
   std::vector<int> MolName, NMol, composition;
@@ -31,6 +32,8 @@ struct SpeciesFix {
   void sort_molecule(const MD& md);
   void find_species(const MD& md);
   std::string formulas_text(long ntimestep) const;
+  // WritePos (fix_reaxc_species_sunway.cpp:814-925) for the single-file form of `position`; box6 = boxlo[3], boxhi[3]
+  std::string pos_text(const MD& md, long ntimestep, const double* box6);
 };
 
 }  // namespace orc

@@ -314,6 +314,15 @@ long orc_md_species_text(void* hh, long ntimestep, char* out, long cap) {
   return copy_text(h->text, out, cap);
 }
 
+// `position` output of fix reax/c/species at the last output step; box6 = boxlo[3], boxhi[3]; avg_qxyz (optional) receives
+// the averaged q, x, y, z columns [nlocal][4] as they were BEFORE WritePos shifted them
+long orc_md_species_pos_text(void* hh, long ntimestep, const double* box6, double* avg_qxyz, char* out, long cap) {
+  OrcHandle* h = (OrcHandle*)hh;
+  if (avg_qxyz) memcpy(avg_qxyz, h->species.qxyz.data(), h->species.qxyz.size() * sizeof(double));
+  h->text = h->species.pos_text(h->md, ntimestep, box6);
+  return copy_text(h->text, out, cap);
+}
+
 // OpenMP threads of this library: set > 0 sets the count (independent of OMP_NUM_THREADS, which launchers such as torchrun
 // force to 1); returns the number of threads a parallel region actually gets (1 for the serial build).
 int orc_omp_threads(int set) {

@@ -101,10 +101,14 @@ int ref_bonds_write(const char* path, long ntimestep, double bg_cut, int nlocal,
 
 // fix reax/c/species nevery nrepeat nfreq: the output step `nfreq` with tmpid (current bond partners, [nlocal][12] local
 // indices, 0 = none) and avg_bo (the fix ave/atom result for the abo columns, [nlocal][12]).  cutoffs = ncut x (i, j, value).
-int ref_species_write(const char* path, int nevery, int nrepeat, int nfreq, int nlocal, int nghost, int ntypes, const int* type,
-                      const int* tag, const int* ghost_owner, const int* tmpid, const double* avg_bo, int ncut,
-                      const double* cutoffs, int* nmole_out, int* cluster_out, int* neighbor_every_out) {
+// ... plus, when pos_path is given, the `position posfreq pos_path` keyword: avg_qxyz = the fix ave/atom result for the
+// q, x, y, z columns ([nlocal][4]) and box6 = boxlo[3], boxhi[3] (WritePos, fix_reaxc_species_sunway.cpp:814-925).
+int ref_species_write_pos(const char* path, int nevery, int nrepeat, int nfreq, int nlocal, int nghost, int ntypes, const int* type,
+                          const int* tag, const int* ghost_owner, const int* tmpid, const double* avg_bo, int ncut,
+                          const double* cutoffs, int* nmole_out, int* cluster_out, int* neighbor_every_out,
+                          const char* pos_path, int posfreq, const double* avg_qxyz, const double* box6) {
   World W(nlocal, nghost, ntypes, type, tag, nullptr, ghost_owner, nlocal);
+  if (box6) for (int t = 0; t < 3; t++) { W.domain.boxlo[t] = box6[t]; W.domain.boxhi[t] = box6[3 + t]; }
   const int nall = nlocal + nghost;
   // pair style arrays the fix reads: tmpid[i][jj]
   std::vector<int*> idrow(nall + 16);
@@ -120,6 +124,7 @@ int ref_species_write(const char* path, int nevery, int nrepeat, int nfreq, int 
   std::vector<double> aflat((size_t)(nall + 16) * 31, 0.0);
   for (int i = 0; i < nall + 16; i++) arow[i] = &aflat[(size_t)i * 31];
   for (int i = 0; i < nlocal; i++) for (int k = 0; k < MAXSPECBOND; k++) arow[i][7 + k] = avg_bo[i * MAXSPECBOND + k];
+  if (avg_qxyz) for (int i = 0; i < nlocal; i++) for (int k = 0; k < 4; k++) arow[i][k] = avg_qxyz[4 * i + k];
   ave.array_atom = arow.data();
   Fix* fixes[1] = {&ave};
   W.modify.nfix = 1; W.modify.fix = fixes;
@@ -134,6 +139,7 @@ int ref_species_write(const char* path, int nevery, int nrepeat, int nfreq, int 
     snprintf(buf, sizeof buf, "%.17g", cutoffs[3 * c + 2]);
     sargs.push_back(buf);
   }
+  if (pos_path) { sargs.push_back("position"); sargs.push_back(std::to_string(posfreq)); sargs.push_back(pos_path); }
   std::vector<std::vector<char>> store;
   std::vector<char*> args;
   for (auto& a : sargs) { store.emplace_back(a.begin(), a.end()); store.back().push_back(0); }
@@ -153,6 +159,13 @@ int ref_species_write(const char* path, int nevery, int nrepeat, int nfreq, int 
     return -2;
   }
   return 0;
+}
+
+int ref_species_write(const char* path, int nevery, int nrepeat, int nfreq, int nlocal, int nghost, int ntypes, const int* type,
+                      const int* tag, const int* ghost_owner, const int* tmpid, const double* avg_bo, int ncut,
+                      const double* cutoffs, int* nmole_out, int* cluster_out, int* neighbor_every_out) {
+  return ref_species_write_pos(path, nevery, nrepeat, nfreq, nlocal, nghost, ntypes, type, tag, ghost_owner, tmpid, avg_bo, ncut,
+                               cutoffs, nmole_out, cluster_out, neighbor_every_out, nullptr, 0, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ SYMBOLS = [
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
     "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
     "rxb_fix_qeq_params", "rxb_spec_atom_abo", "rxb_get_counters", "rxb_comm_init", "rxb_comm_set_ghosts",
+    "rxb_species_avg_qxyz",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -262,6 +263,12 @@ class Rxb:
         c = np.zeros(int(self.counts()[0]), dtype=np.int32)
         self._chk(self.lib.rxb_species_cluster(self.h, _p(c)))
         return c
+
+    def species_avg_qxyz(self):
+        """Averaged q, x, y, z columns of the window that just ended ([nlocal][4]); input of the `position` output."""
+        a = np.zeros((int(self.counts()[0]), 4))
+        self._chk(self.lib.rxb_species_avg_qxyz(self.h, _p(a)))
+        return a
 
     def species_log(self):
         out = []

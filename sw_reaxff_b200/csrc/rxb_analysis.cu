@@ -84,6 +84,14 @@ __global__ void k_spec_sample(int n, const int* __restrict__ b_start, const int*
   for (; k < kMaxSpecBond; k++) ids[i * kMaxSpecBond + k] = 0;   // tmpid is zeroed before every FindBond (:783-790)
 }
 
+// one sample of compute SPEC/ATOM's q, x, y, z columns (compute_spec_atom_sunway.cpp:142-170), summed over the window
+__global__ void k_spec_qxyz(int n, const double4* __restrict__ xq, double* __restrict__ acc4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  acc4[4 * i] += p.w; acc4[4 * i + 1] += p.x; acc4[4 * i + 2] += p.y; acc4[4 * i + 3] += p.z;
+}
+
 // edges of the molecule graph in atom-ID space; COUNT pass sizes the list, FILL pass writes it
 template <bool FILL>
 __global__ void k_spec_edges(int n, int ntypes, double nrepeat, const int* __restrict__ ids,
@@ -273,6 +281,8 @@ void System::species_sample() {
   if (S.irepeat == 0) {
     sp_id.resize(m); sp_acc.resize(m);
     RXB_CUDA(cudaMemsetAsync(sp_acc.p, 0, m * sizeof(double), st_));
+    sp_qxyz.resize((size_t)4 * std::max(n, 1));
+    RXB_CUDA(cudaMemsetAsync(sp_qxyz.p, 0, (size_t)4 * std::max(n, 1) * sizeof(double), st_));
     sp_n_ = n;
   }
   if (n != sp_n_) throw std::runtime_error("fix reax/c/species: atoms migrated inside an averaging window");
@@ -280,11 +290,23 @@ void System::species_sample() {
   RXB_CUDA(cudaMemsetAsync(sp_misc.p, 0, 4 * sizeof(int), st_));
   if (n > 0)
     k_spec_sample<<<nblk(n), 256, 0, st_>>>(n, b_start.p, b_cnt.p, b_nbr.p, b_bo.p, sp_id.p, sp_acc.p, sp_misc.p);
+  if (n > 0) k_spec_qxyz<<<nblk(n), 256, 0, st_>>>(n, xq.p, sp_qxyz.p);
   int err = 0;
   RXB_CUDA(cudaMemcpyAsync(&err, sp_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaStreamSynchronize(st_));
-  kernel_launches += 1;
+  kernel_launches += 2;
   if (err > kMaxSpecBond) throw std::runtime_error("Increase MAXSPECBOND in reaxc_defs_sunway.h");   // pair_reaxc_sunway.cpp:1194
+}
+
+// the fix ave/atom result for the q, x, y, z columns: sums of the last complete window / nrepeat (`position` keyword)
+void System::species_avg_qxyz(double* out4) {
+  RXB_CUDA(cudaSetDevice(device_));
+  if (!species.on || sp_qxyz.n < (size_t)4 * sp_n_ || sp_n_ != n)
+    throw std::runtime_error("rxb_species_avg_qxyz: no complete averaging window for the current atoms");
+  if (species.irepeat != 0) throw std::runtime_error("rxb_species_avg_qxyz: called inside an averaging window");
+  RXB_CUDA(cudaMemcpyAsync(out4, sp_qxyz.p, (size_t)4 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  RXB_CUDA(cudaStreamSynchronize(st_));
+  for (size_t k = 0; k < (size_t)4 * n; k++) out4[k] /= species.nrepeat;
 }
 
 bool System::species_step(long step) {

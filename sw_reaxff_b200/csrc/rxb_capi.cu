@@ -464,6 +464,9 @@ int rxb_species_result(rxb_handle* h, int* nmole, int* composition, long cap) {
 int rxb_species_cluster(rxb_handle* h, int* cluster_of_local) {
   return guard([&] { h->sys->species_get_cluster(cluster_of_local); });
 }
+int rxb_species_avg_qxyz(rxb_handle* h, double* qxyz4) {
+  return guard([&] { h->sys->species_avg_qxyz(qxyz4); });
+}
 int rxb_species_log_size(rxb_handle* h) { return (int)h->sys->species_log.size(); }
 int rxb_species_log_get(rxb_handle* h, int k, long* step, int* nmole, int* composition, long cap) {
   return guard([&] {

@@ -260,11 +260,12 @@ class System {
   int species_config(int nevery, int nrepeat, int nfreq, int ntypes, const double* bocut, long natoms_total, long now = -1);
   bool species_step(long step);                // the post_integrate hook of timestep `step`; true when molecules were found
   void species_sample();
+  void species_avg_qxyz(double* out4);     // the averaged q, x, y, z columns of the last complete window: [nlocal][4]
   void spec_atom_abo(double* abo_host);    // compute SPEC/ATOM abo columns, one sample: [nlocal][12]
   void species_find();
   void species_get_cluster(int* cluster_of_local);   // 1..nmole per local atom (vector_atom of the reference fix)
   DBuf<int> bt_cnt, bt_off, bt_tag, sp_id, sp_edges, sp_edges_all, sp_parent, sp_flag, sp_molidx, sp_comp, sp_misc;
-  DBuf<double> bt_bo, sp_acc, sp_bocut;
+  DBuf<double> bt_bo, sp_acc, sp_bocut, sp_qxyz;   // sp_qxyz: [n][4] sums of q, x, y, z over the samples of the window
   BondTable bt_last_;
   int sp_n_ = -1;
 

@@ -379,14 +379,27 @@ FixReaxCSpeciesB200::FixReaxCSpeciesB200(LAMMPS* l, int narg, char** arg) : Fix(
       for (int i = 0; i < ntypes; i++) eletype.push_back(arg[iarg + 1 + i]);
       iarg += ntypes + 1;
     } else if (strcmp(arg[iarg], "position") == 0) {
-      error->all(FLERR, "fix reax/c/species: the position keyword is not supported by this build");
+      if (iarg + 3 > narg) error->all(FLERR, "Illegal fix reax/c/species command");
+      posflag_ = 1;
+      posfreq_ = atoi(arg[iarg + 1]);
+      if (posfreq_ < nfreq || (posfreq_ % nfreq != 0)) error->all(FLERR, "Illegal fix reax/c/species command");
+      filepos_ = arg[iarg + 2];
+      if (filepos_.find('*') != std::string::npos) multipos_ = 1;
+      else {
+        pos_ = fopen(filepos_.c_str(), "w");
+        if (!pos_) error->one(FLERR, "Cannot open fix reax/c/species position file");
+      }
+      iarg += 3;
     } else error->all(FLERR, "Illegal fix reax/c/species command");
   }
   if (eletype.empty()) { const char* d[4] = {"C", "H", "O", "N"}; for (int i = 0; i < ntypes && i < 4; i++) eletype.push_back(d[i]); }
   nev_ = nev;
 }
 
-FixReaxCSpeciesB200::~FixReaxCSpeciesB200() { if (fp) fclose(fp); }
+FixReaxCSpeciesB200::~FixReaxCSpeciesB200() {
+  if (fp) fclose(fp);
+  if (pos_) fclose(pos_);
+}
 
 void FixReaxCSpeciesB200::init() {
   Error* error = lmp->error;
@@ -419,6 +432,82 @@ void FixReaxCSpeciesB200::post_integrate() {
   if (rxb_species_cluster(reaxc->rxb, clusterID.data())) error->all(FLERR, rxb_last_error());
   write_formulas(comp);
   fflush(fp);
+  if (posflag_ && lmp->update->ntimestep % posfreq_ == 0) write_pos(comp);
+}
+
+// WritePos, fix_reaxc_species_sunway.cpp:814-925 (one rank).  The anchor x0 of a molecule - the fixed point of FindMolecule's
+// chAnchor propagation (:497-510, :530-532, :559-569) - is the lexicographically smallest averaged position of its atoms.
+void FixReaxCSpeciesB200::write_pos(const std::vector<int>& comp) {
+  Error* error = lmp->error;
+  const int nlocal = lmp->atom->nlocal;
+  std::vector<double> col((size_t)4 * std::max(nlocal, 1));
+  if (rxb_species_avg_qxyz(reaxc->rxb, col.data())) error->all(FLERR, rxb_last_error());
+  const long ntimestep = lmp->update->ntimestep;
+  if (multipos_) {                        // OpenPos: '*' -> timestep
+    if (pos_) fclose(pos_);
+    const size_t star = filepos_.find('*');
+    const std::string name = filepos_.substr(0, star) + std::to_string(ntimestep) + filepos_.substr(star + 1);
+    pos_ = fopen(name.c_str(), "w");
+    if (!pos_) error->one(FLERR, "Cannot open fix reax/c/species position file");
+  }
+  const Domain* d = lmp->domain;
+  const double lo[3] = {d->boxlo[0], d->boxlo[1], d->boxlo[2]};
+  const double hi[3] = {lo[0] + d->h[0], lo[1] + d->h[1], lo[2] + d->h[2]};
+  const double box[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+  const double halfbox[3] = {box[0] / 2, box[1] / 2, box[2] / 2};
+  std::vector<double> anchor((size_t)3 * std::max(Nmole, 1), 0.0);
+  std::vector<char> have(std::max(Nmole, 1), 0);
+  for (int i = 0; i < nlocal; i++) {
+    const int m = clusterID[i] - 1;
+    const double* xi = &col[4 * (size_t)i + 1];
+    double* a = &anchor[3 * (size_t)m];
+    const bool less = !have[m] || xi[0] < a[0] || (xi[0] == a[0] && (xi[1] < a[1] || (xi[1] == a[1] && xi[2] < a[2])));
+    if (less) { a[0] = xi[0]; a[1] = xi[1]; a[2] = xi[2]; have[m] = 1; }
+  }
+  fprintf(pos_, "Timestep %ld NMole %d  NSpec %d  xlo %f  xhi %f  ylo %f  yhi %f  zlo %f  zhi %f\n", ntimestep, Nmole, Nspec, lo[0],
+          hi[0], lo[1], hi[1], lo[2], hi[2]);
+  fprintf(pos_, "ID\tAtom_Count\tType\tAve_q\t\tCoM_x\t\tCoM_y\t\tCoM_z\n");
+  // members of every molecule in ascending local index (the reference scans all local atoms once per molecule)
+  std::vector<int> mstart(Nmole + 1, 0), member(nlocal);
+  for (int i = 0; i < nlocal; i++) mstart[clusterID[i]]++;
+  for (int m = 0; m < Nmole; m++) mstart[m + 1] += mstart[m];
+  { std::vector<int> cur(mstart.begin(), mstart.end() - 1); for (int i = 0; i < nlocal; i++) member[cur[clusterID[i] - 1]++] = i; }
+  for (int m = 1; m <= Nmole; m++) {
+    const int* Name = &comp[(size_t)(m - 1) * ntypes];
+    int count = 0;
+    double avq = 0.0, avx[3] = {0, 0, 0};
+    const double* x0 = &anchor[3 * (size_t)(m - 1)];
+    for (int k = mstart[m - 1]; k < mstart[m]; k++) {
+      double* sa = &col[4 * (size_t)member[k]];
+      count++;
+      avq += sa[0];
+      for (int t = 0; t < 3; t++) {
+        if ((x0[t] - sa[1 + t]) > halfbox[t]) sa[1 + t] += box[t];
+        if ((sa[1 + t] - x0[t]) > halfbox[t]) sa[1 + t] -= box[t];
+      }
+      for (int t = 0; t < 3; t++) avx[t] += sa[1 + t];
+    }
+    fprintf(pos_, "%d\t%d\t", m, count);
+    for (int n = 0; n < ntypes; n++)
+      if (Name[n] != 0) {
+        fprintf(pos_, "%s", eletype[n].c_str());
+        if (Name[n] != 1) fprintf(pos_, "%d", Name[n]);
+      }
+    if (count > 0) {
+      avq /= count;
+      for (int k = 0; k < 3; k++) {
+        avx[k] /= count;
+        if (avx[k] >= hi[k]) avx[k] -= box[k];
+        if (avx[k] < lo[k]) avx[k] += box[k];
+        avx[k] -= lo[k];
+        avx[k] /= box[k];
+      }
+      fprintf(pos_, "\t%.8f \t%.8f \t%.8f \t%.8f", avq, avx[0], avx[1], avx[2]);
+    }
+    fprintf(pos_, "\n");
+  }
+  if (!multipos_) fprintf(pos_, "#\n");
+  fflush(pos_);
 }
 
 // FindSpecies + WriteFormulas, fix_reaxc_species_sunway.cpp:652-717, 745-780

@@ -97,7 +97,7 @@ class ComputeSpecAtomB200 : public Compute {         // compute ID all SPEC/ATOM
   PairReaxCB200* reaxc = nullptr;
 };
 
-class FixReaxCSpeciesB200 : public Fix {             // fix ID all reax/c/species Nevery Nrepeat Nfreq file [cutoff i j v] [element ...]
+class FixReaxCSpeciesB200 : public Fix {             // fix ID all reax/c/species Nevery Nrepeat Nfreq file [cutoff i j v] [element ...] [position f file]
  public:
   FixReaxCSpeciesB200(LAMMPS* lmp, int narg, char** arg);  // fix_reaxc_species_sunway.cpp:50-252
   ~FixReaxCSpeciesB200() override;
@@ -115,6 +115,11 @@ class FixReaxCSpeciesB200 : public Fix {             // fix ID all reax/c/specie
   bool configured_ = false;
   int nev_ = 1;
   void write_formulas(const std::vector<int>& comp);
+  // `position posfreq filepos` (fix_reaxc_species_sunway.cpp:210-231, OpenPos :784-810, WritePos :814-925)
+  int posflag_ = 0, posfreq_ = 0, multipos_ = 0;
+  std::string filepos_;
+  FILE* pos_ = nullptr;
+  void write_pos(const std::vector<int>& comp);
 };
 
 }  // namespace LAMMPS_MINI

@@ -299,6 +299,17 @@ class Oracle:
     def md_species_text(self, step):
         return self._text("orc_md_species_text", step)
 
+    def md_species_pos(self, step, box6):
+        """-> (text of the `position` file block, averaged q/x/y/z columns [nlocal][4]); box6 = boxlo[3] + boxhi[3]."""
+        fn = self.L.orc_md_species_pos_text
+        fn.restype = C.c_long
+        b = np.ascontiguousarray(box6, dtype=np.float64)
+        avg = np.zeros((self.nlocal, 4))
+        need = fn(self.h, C.c_long(step), _p(b), _p(avg), None, C.c_long(0))
+        buf = C.create_string_buffer(need + 1)
+        fn(self.h, C.c_long(step), _p(b), None, buf, C.c_long(need + 1))
+        return buf.value.decode(), avg
+
 
 def _c(a):
     a = np.ascontiguousarray(a, dtype=np.float64)

@@ -84,7 +84,12 @@ def test_analysis_fix_argument_errors(tmp_path):
                       ("fix 4 all reax/c/species 2 5 25 %s" % out, "Illegal fix reax/c/species command"),
                       ("fix 4 all reax/c/species 1 5 5 %s cutoff 1 9 0.5" % out, "Illegal fix reax/c/species command"),
                       ("fix 4 all reax/c/species 1 5 5 %s cutoff 1 2 1.5" % out, "Illegal fix reax/c/species command"),
-                      ("fix 4 all reax/c/species 1 5 5 %s bogus" % out, "Illegal fix reax/c/species command")]:
+                      ("fix 4 all reax/c/species 1 5 5 %s bogus" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s position 5" % out, "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 10 %s position 5 %s.pos" % (out, out), "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s position 7 %s.pos" % (out, out), "Illegal fix reax/c/species command"),
+                      ("fix 4 all reax/c/species 1 5 5 %s position 5 /nonexistent_dir/p" % out,
+                       "Cannot open fix reax/c/species position file")]:
         p.write_text(head + line + "\n")
         with pytest.raises(RuntimeError, match=msg):
             run_script(str(p))
@@ -97,12 +102,13 @@ def test_analysis_fix_argument_errors(tmp_path):
 def test_script_with_bonds_and_species_fixes_matches_oracle(tmp_path):
     """The reference's C5-style input (fix reax/c/bonds N file + fix reax/c/species nevery nrepeat nfreq file) through the
     plugin path: both output files are byte-identical to the oracle's restatement of the reference writers."""
-    fb, fs = tmp_path / "bonds.out", tmp_path / "species.out"
+    fb, fs, fpos = tmp_path / "bonds.out", tmp_path / "species.out", tmp_path / "species.pos"
     lines = ["units real", "atom_style charge", "read_data %s" % H.DATAFILE,
              "pair_style reax/c %s" % H.CONTROL, "pair_coeff * * %s C H O N" % H.FFIELD,
              "neighbor 2.5 bin", "neigh_modify delay 0 every 5 check no", "fix 1 all nve",
              "fix 2 all qeq/reax 1 0.0 10.0 1.0e-10 reax/c", "fix 3 all reax/c/bonds 4 %s" % fb,
-             "fix 4 all reax/c/species 1 4 4 %s" % fs, "velocity all create 1500.0 4928459", "thermo 4", "timestep 0.0625", "run 8"]
+             "fix 4 all reax/c/species 1 4 4 %s position 4 %s" % (fs, fpos), "velocity all create 1500.0 4928459", "thermo 4",
+             "timestep 0.0625", "run 8"]
     p = tmp_path / "in.c5"
     p.write_text("\n".join(lines) + "\n")
     run_script(str(p))
@@ -112,16 +118,29 @@ def test_script_with_bonds_and_species_fixes_matches_oracle(tmp_path):
     o = H.Oracle()
     o.md_init(box, x, v, t, tag, dt=0.0625, qeq_tol=1e-10, every=4)    # the species fix resets reneighbouring to every 4
     o.md_species_init(1, 4, 4)
-    bonds, species = o.md_bonds_text(0), ""                            # setup(): end_of_step() / post_integrate()
+    bonds, species, pos = o.md_bonds_text(0), "", ""                   # setup(): end_of_step() / post_integrate()
+    box6 = np.array([0.0, 0.0, 0.0, box[0], box[1], box[2]])
     o.md_species_step(0)
     for step in range(1, 9):
         if o.md_species_step(step):          # post_integrate of this step: reads the previous step's bond list
             species += o.md_species_text(step)
+            pos += o.md_species_pos(step, box6)[0]
         o.md_run(1)
         if step % 4 == 0:
             bonds += o.md_bonds_text(step)   # end_of_step
     assert fb.read_text() == bonds
     assert fs.read_text() == species and species.count("# Timestep") == 2
+    # `position 4 file` (WritePos): molecule ids, atom counts and formulas exactly, the printed averages to the last digit
+    # or one unit of it (%.8f of quantities the two trajectories agree on to ~1e-10)
+    got, want = fpos.read_text().splitlines(), pos.splitlines()
+    assert len(got) == len(want) and sum(l.startswith("Timestep") for l in got) == 2
+    for a, b in zip(got, want):
+        fa, fb_ = a.split("\t"), b.split("\t")
+        if a.startswith(("Timestep", "ID", "#")):
+            assert a == b
+            continue
+        assert fa[:3] == fb_[:3] and len(fa) == len(fb_) == 7
+        assert np.allclose([float(v) for v in fa[3:]], [float(v) for v in fb_[3:]], rtol=0, atol=2.1e-8), (a, b)
 
 
 def host_velocities(T, seed):

@@ -463,3 +463,14 @@ def test_species_file_equals_reference_fix_reaxc_species(scale, T, cut, tmp_path
     assert open(path).read() == o.md_species_text(5)
     if cut:
         assert sp["nmole"] > 16
+    # `position 5 <file>`: the reference's WritePos on the averaged q, x, y, z columns against the oracle's restatement
+    box6 = np.array([0.0, 0.0, 0.0, box[0], box[1], box[2]])
+    pos_orc, qxyz = o.md_species_pos(5, box6)
+    assert np.abs(qxyz[:, 1:]).max() > 1.0 and np.abs(qxyz[:, 0]).max() > 1e-3
+    pos_path = str(tmp_path / "species.pos")
+    assert L.ref_species_write_pos(str(tmp_path / "species2.ref").encode(), 1, 5, 5, n, N - n, 4, p(ints[0]), p(ints[1]), p(ints[2]),
+                                   p(ids), p(avg), len(cuts), p(cuts) if len(cuts) else None, C.byref(nmole), p(cl),
+                                   C.byref(every), pos_path.encode(), 5, p(np.ascontiguousarray(qxyz)), p(box6)) == 0
+    ref_pos = open(pos_path).read()
+    assert ref_pos == pos_orc
+    assert ref_pos.count("\n") == sp["nmole"] + 3
