@@ -351,7 +351,9 @@ def run_b200(args, rank, world, local_rank):
     if ncu_range:
         r.profiler_range(1)
     with ClockSampler(local_rank) as cs:
+        hs0 = r.host_syncs()
         r.md_run(args.steps)                      # timed region: CUDA events on the launch stream inside
+        host_syncs = r.host_syncs() - hs0         # every stream / event wait of the library inside the timed region
         ms = r.md_last_run_ms()
     torch.cuda.synchronize()
     if ncu_range:
@@ -463,7 +465,8 @@ def run_b200(args, rank, world, local_rank):
         "config": {**config_for(cells, dt, TOL), "ghost_atoms": nall - natoms,
                    "l2": "inputs larger than L2 (H matrix + Verlet list > 1 GB per step vs 126 MB L2)",
                    "timing": "CUDA events on the launch stream around the K steps"},
-        "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "qeq_cg_iterations_per_s": qeq_iters / (ms * 1e-3),
+        "clocks": cs.summary(), "e2e": e2e, "gpu_launches": launches, "host_syncs_per_step": host_syncs / args.steps,
+        "qeq_cg_iterations_per_s": qeq_iters / (ms * 1e-3),
         "qeq_iterations_per_step": qeq_iters / args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "kernel_ms_per_step": breakdown, "other_kernels": other, "secondary": secondary, "configs": configs, "parity": parity,
     }

@@ -201,6 +201,9 @@ int rxb_profile(rxb_handle* h, int enable, double* out28);
  * device and not counted), QEq solves that had to be continued after the end-of-step check (force phase replayed),
  * dual-RHS CG iterations, kernel launches */
 int rxb_get_counters(rxb_handle* h, long long* out4);
+/* host-side waits on a CUDA stream or event issued by the library in this process so far (every one of them goes through
+ * one counting macro): the difference around a run / the number of steps is what "no host in the loop" means in numbers */
+long long rxb_host_sync_count(void);
 /* Tests only: shrink the capacities of the growable lists (directed bonds, angle / torsion / hydrogen-bond work lists) and
  * of the per-atom shared-memory staging (bonds per atom, strong bonds per centre) so that every grow-and-replay branch
  * of the force phase can be driven on an ordinary cell (values <= 0 are left alone); read the current values back. */

@@ -19,7 +19,7 @@ SYMBOLS = [
     "rxb_species_cluster", "rxb_species_log_size", "rxb_species_log_get", "rxb_host_register", "rxb_host_unregister", "rxb_lookup_dump", "rxb_get_cutoffs", "rxb_measure_fp64_tflops", "rxb_get_h_format",
     "rxb_qeq_matvecs", "rxb_set_h_exact", "rxb_debug_set_caps", "rxb_debug_get_caps", "rxb_get_hbond_pairs",
     "rxb_fix_qeq_params", "rxb_spec_atom_abo", "rxb_get_counters", "rxb_comm_init", "rxb_comm_set_ghosts",
-    "rxb_species_avg_qxyz",
+    "rxb_species_avg_qxyz", "rxb_host_sync_count",
 ]
 
 E_NAMES = ["e_bond", "e_ov", "e_un", "e_lp", "e_ang", "e_pen", "e_coa", "e_hb", "e_tor", "e_con", "e_vdW", "e_ele", "e_pol"]
@@ -340,6 +340,11 @@ class Rxb:
         o = np.zeros(4, dtype=np.int64)
         self._chk(self.lib.rxb_get_counters(self.h, _p(o)))
         return dict(zip(["spmv_active", "qeq_replays", "qeq_iterations", "kernel_launches"], o.tolist()))
+
+    def host_syncs(self):
+        """Host-side waits on a CUDA stream / event issued by the library in this process so far."""
+        self.lib.rxb_host_sync_count.restype = C.c_longlong
+        return int(self.lib.rxb_host_sync_count())
 
     def hbond_pairs(self):
         n = C.c_int()

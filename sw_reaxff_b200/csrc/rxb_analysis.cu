@@ -187,7 +187,7 @@ System::BondTable System::bond_table_build(double bo_cut) {
   int got[2] = {0, 0};
   RXB_CUDA(cudaMemcpyAsync(&got[0], bt_off.p + n, sizeof(int), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaMemcpyAsync(&got[1], sp_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   t.entries = got[0];
   t.max_nb = got[1];
   bt_tag.resize((size_t)std::max(t.entries, 1));
@@ -220,7 +220,7 @@ void System::bond_table_get(int* tag_out, int* type_out, int* off_out, int* nbr_
     k_gather_q<<<nblk(n), 256, 0, st_>>>(n, xq.p, x_stage.p);
     d2h(q_out, x_stage.p, (size_t)n * sizeof(double));
   }
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -249,7 +249,7 @@ int System::species_config(int nevery, int nrepeat, int nfreq, int ntypes, const
   S.nvalid_ave = nv;
   sp_bocut.resize((size_t)(ntypes + 1) * (ntypes + 1));
   RXB_CUDA(cudaMemcpyAsync(sp_bocut.p, bocut, sp_bocut.n * sizeof(double), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   species_log.clear();
   return reset;
 }
@@ -270,7 +270,7 @@ void System::spec_atom_abo(double* abo_host) {
   int err = 0;
   RXB_CUDA(cudaMemcpyAsync(&err, sp_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
   if (n > 0) RXB_CUDA(cudaMemcpyAsync(abo_host, acc.p, (size_t)n * kMaxSpecBond * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   kernel_launches += 1;
   if (err > kMaxSpecBond) throw std::runtime_error("Increase MAXSPECBOND in reaxc_defs_sunway.h");   // pair_reaxc_sunway.cpp:1194
 }
@@ -293,7 +293,7 @@ void System::species_sample() {
   if (n > 0) k_spec_qxyz<<<nblk(n), 256, 0, st_>>>(n, xq.p, sp_qxyz.p);
   int err = 0;
   RXB_CUDA(cudaMemcpyAsync(&err, sp_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   kernel_launches += 2;
   if (err > kMaxSpecBond) throw std::runtime_error("Increase MAXSPECBOND in reaxc_defs_sunway.h");   // pair_reaxc_sunway.cpp:1194
 }
@@ -305,7 +305,7 @@ void System::species_avg_qxyz(double* out4) {
     throw std::runtime_error("rxb_species_avg_qxyz: no complete averaging window for the current atoms");
   if (species.irepeat != 0) throw std::runtime_error("rxb_species_avg_qxyz: called inside an averaging window");
   RXB_CUDA(cudaMemcpyAsync(out4, sp_qxyz.p, (size_t)4 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   for (size_t k = 0; k < (size_t)4 * n; k++) out4[k] /= species.nrepeat;
 }
 
@@ -341,7 +341,7 @@ void System::species_find() {
   dist_allgather_int(sp_misc.p, cnts.p, 1);
   std::vector<int> hc(W);
   RXB_CUDA(cudaMemcpyAsync(hc.data(), cnts.p, W * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   const int mine = hc[dist_rank()];
   const int chunk = std::max(1, *std::max_element(hc.begin(), hc.end()));
   sp_edges.resize((size_t)2 * chunk);
@@ -366,7 +366,7 @@ void System::species_find() {
   cub::DeviceScan::ExclusiveSum(scan_temp.p, need, sp_flag.p, sp_molidx.p, M + 1, st_);
   int nmole = 0;
   RXB_CUDA(cudaMemcpyAsync(&nmole, sp_molidx.p + M, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   S.nmole = nmole;
   sp_comp.resize((size_t)std::max(1, nmole) * T + (size_t)std::max(n, 1));
   int* cluster = sp_comp.p + (size_t)std::max(1, nmole) * T;
@@ -376,7 +376,7 @@ void System::species_find() {
   S.composition.assign((size_t)nmole * T, 0);
   if (nmole > 0)
     RXB_CUDA(cudaMemcpyAsync(S.composition.data(), sp_comp.p, (size_t)nmole * T * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   RXB_CUDA(cudaGetLastError());
   kernel_launches += 6;
 }
@@ -385,7 +385,7 @@ void System::species_get_cluster(int* cluster_of_local) {
   if (species.nmole == 0 || n == 0) return;
   const int* cluster = sp_comp.p + (size_t)std::max(1, species.nmole) * species.ntypes;
   RXB_CUDA(cudaMemcpyAsync(cluster_of_local, cluster, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
 }
 
 }  // namespace rxb

@@ -36,7 +36,7 @@ template <class T>
 void d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
   if (n == 0) return;
   RXB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
-  RXB_CUDA(cudaStreamSynchronize(st));
+  RXB_SYNC(st);
 }
 
 // fp64 FMA throughput of this GPU, measured: 8 independent dependent-FMA chains per thread (enough ILP to cover the DFMA
@@ -190,6 +190,7 @@ int rxb_get_counters(rxb_handle* h, long long* out4) {
     out4[0] = (long long)a; out4[1] = s.qeq_replays; out4[2] = s.qeq_iters_total; out4[3] = s.kernel_launches;
   });
 }
+long long rxb_host_sync_count(void) { return host_sync_counter(); }
 int rxb_debug_set_caps(rxb_handle* h, int row_cap, int strong_cap, int cap_bonds, int cap_ang, int cap_tor, int cap_hb) {
   return guard([&] { h->sys->debug_set_caps(row_cap, strong_cap, cap_bonds, cap_ang, cap_tor, cap_hb); });
 }

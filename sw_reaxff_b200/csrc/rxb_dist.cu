@@ -341,7 +341,7 @@ static std::vector<int> gather_table(Dist& D, const int* row_dev, cudaStream_t s
   RXB_NCCL(ncclAllGather(row_dev, D.cnt_all_d.p, W, ncclInt, D.comm, st));
   std::vector<int> all((size_t)W * W);
   RXB_CUDA(cudaMemcpyAsync(all.data(), D.cnt_all_d.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-  RXB_CUDA(cudaStreamSynchronize(st));
+  RXB_SYNC(st);
   return all;
 }
 
@@ -492,7 +492,7 @@ void System::dist_exchange() {
     D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
     RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
     RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
-    RXB_CUDA(cudaStreamSynchronize(st_));          // dst_off is a local that dies with this scope
+    RXB_SYNC(st_);          // dst_off is a local that dies with this scope
   }
   D.recv_bytes_last = ((size_t)narr * kRec + (size_t)(nghost - nself) * kGRec) * sizeof(double);
   kernel_launches += 10;
@@ -646,7 +646,7 @@ void System::comm_set_ghosts(int nghost, const int* owner_rank, const int* owner
   D.dst_off_d.resize(W); D.soff_d.resize(W + 1);
   RXB_CUDA(cudaMemcpyAsync(D.dst_off_d.p, dst_off.data(), W * sizeof(int), cudaMemcpyHostToDevice, st_));
   RXB_CUDA(cudaMemcpyAsync(D.soff_d.p, D.soff.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   for (int e = 0; e < D.nsend; e++)
     if (sl[e] < 0 || sl[e] >= n)
       throw std::runtime_error("rxb_comm_set_ghosts: a peer asked for local index " + std::to_string(sl[e]) + " but this rank has " +
@@ -888,7 +888,7 @@ void System::dist_classify_rows() {
   cub::DeviceScan::ExclusiveSum(D.temp.p, need, D.flag.p, D.off.p, n + 1, st_);
   long long n_int = 0;
   RXB_CUDA(cudaMemcpyAsync(&n_int, D.off.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   k_row_order<<<nblk(n), 256, 0, st_>>>(n, n_int, D.flag.p, D.off.p, q_rowlist.p);
   // every rank takes the split path or none does not matter for correctness (push/pull are the same calls either way);
   // a split with a tiny interior is not worth its extra launch
@@ -940,7 +940,7 @@ void System::dist_peer_setup() {
   RXB_CUDA(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st_));
   RXB_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, D.comm, st_));
   RXB_CUDA(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   if (ok) {
     for (int r = 0; r < W; r++) {
       if (r == D.rank) { D.win_of[r] = D.win; continue; }
@@ -952,7 +952,7 @@ void System::dist_peer_setup() {
   RXB_CUDA(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st_));
   RXB_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclInt, ncclMin, D.comm, st_));
   RXB_CUDA(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   D.peer_ok = ok != 0;
   if (getenv("RXB_PEER_VERBOSE") && D.rank == 0)
     fprintf(stderr, "rxb dist: peer-memory exchange %s (%d ranks, halo capacity %zu ghosts)\n", D.peer_ok ? "ON" : "off (NCCL send/recv)",
@@ -1060,7 +1060,7 @@ void System::dist_peer_check() {
   if (!dist_ || !dist_->peer_ok) return;
   int err = 0;
   RXB_CUDA(cudaMemcpyAsync(&err, dist_->peer_err_d.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   if (err) throw std::runtime_error("rxb dist: peer-memory exchange timed out (a peer rank stopped responding)");
 }
 

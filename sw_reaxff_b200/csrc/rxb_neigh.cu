@@ -249,7 +249,7 @@ void CellList::bin(const double4* xq, int N, double bin_size, int reach_, cudaSt
   k_bounds<<<296, 256, 0, st>>>(xq, N, bounds.p);
   double got[6];
   RXB_CUDA(cudaMemcpyAsync(got, bounds.p, sizeof(got), cudaMemcpyDeviceToHost, st));
-  RXB_CUDA(cudaStreamSynchronize(st));
+  RXB_SYNC(st);
   for (int t = 0; t < 6; t++) { long long b; memcpy(&b, &got[t], 8); b = b >= 0 ? b : b ^ 0x7fffffffffffffffLL; memcpy(&got[t], &b, 8); }
   Grid g;
   long long nbins = 1;
@@ -302,7 +302,7 @@ void CellList::build(const double4* xq, int nrows, double cut, double cut_in, Cs
     RXB_CUDA(cudaMemsetAsync(out.stats.p, 0, 2 * sizeof(long long), st));
     if (nrows > 0) k_cnt_stats<<<std::min(1024, (nrows + 255) / 256), 256, 0, st>>>(out.cnt.p, nrows, out.stats.p);
     RXB_CUDA(cudaMemcpyAsync(host2, out.stats.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    RXB_CUDA(cudaStreamSynchronize(st));
+    RXB_SYNC(st);
   };
   auto stride_for = [](long long longest) { return (int)(((longest + longest / 16 + 32) + 31) / 32 * 32); };
   long long got[2] = {0, 0};

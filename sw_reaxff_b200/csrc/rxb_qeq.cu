@@ -436,12 +436,12 @@ void System::qeq_set_history(const double* s_hist, const double* t_hist) {
   q_s_hist.resize((size_t)5 * n); q_t_hist.resize((size_t)5 * n);
   RXB_CUDA(cudaMemcpyAsync(q_s_hist.p, s_hist, (size_t)5 * n * sizeof(double), cudaMemcpyHostToDevice, st_));
   RXB_CUDA(cudaMemcpyAsync(q_t_hist.p, t_hist, (size_t)5 * n * sizeof(double), cudaMemcpyHostToDevice, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
 }
 void System::qeq_get_history(double* s_hist, double* t_hist) {
   RXB_CUDA(cudaMemcpyAsync(s_hist, q_s_hist.p, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
   RXB_CUDA(cudaMemcpyAsync(t_hist, q_t_hist.p, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
 }
 
 // one CG iteration of loop index `it`: fused sweep, halo of d (+ the dot products in multi-GPU runs), gated SpMV
@@ -555,7 +555,7 @@ bool System::qeq_poll() {
   const int par_next = (qeq_it_ & 1) ^ 1;
   int host[4];
   RXB_CUDA(cudaMemcpyAsync(host, Q->st[par_next].active, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));   // active[2], iters[2]
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   matvecs_s = host[2]; matvecs_t = host[3];
   return !(host[0] | host[1]);
 }

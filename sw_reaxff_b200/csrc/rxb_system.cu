@@ -353,7 +353,7 @@ void System::tock(int id, cudaStream_t st) {
 }
 void System::resolve_timers() {
   if (ev_pending_.empty()) return;
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   for (const Pending& p : ev_pending_) {
     float ms = 0;
     RXB_CUDA(cudaEventElapsedTime(&ms, ev_pool_[p.a], ev_pool_[p.b]));
@@ -501,7 +501,7 @@ void System::set_atoms(int nlocal, int nghost, const double* x, const int* ltype
     k_pack_atoms<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, q ? x_stage.p + 3 * NN : nullptr, ltype_d.p, map_d.p, (int)ff.map.size(),
                                            xq.p, type.p);
   kernel_launches++;
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
 }
 
 // x_host must stay unchanged until the next synchronising call on this handle (rxb_qeq_pre_force / rxb_pair_compute)
@@ -525,7 +525,7 @@ void System::set_charges(const double* q_host) {
   x_stage.resize((size_t)3 * N);
   RXB_CUDA(cudaMemcpyAsync(x_stage.p, pp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st_));
   k_set_q<<<nblk(N), 256, 0, st_>>>(N, x_stage.p, xq.p);
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   kernel_launches++;
 }
 
@@ -534,12 +534,12 @@ void System::get_forces(double* f_host) {
   const size_t bytes = (size_t)3 * N * sizeof(double);
   if (is_pinned(f_host)) {
     RXB_CUDA(cudaMemcpyAsync(f_host, f.p, bytes, cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaStreamSynchronize(st_));
+    RXB_SYNC(st_);
     return;
   }
   double* pp = pin((size_t)3 * N);
   RXB_CUDA(cudaMemcpyAsync(pp, f.p, bytes, cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   memcpy(f_host, pp, bytes);
 }
 
@@ -549,7 +549,7 @@ void System::get_charges(double* q_host) {
   k_get_q<<<nblk(N), 256, 0, st_>>>(N, xq.p, x_stage.p);
   double* pp = pin((size_t)N);
   RXB_CUDA(cudaMemcpyAsync(pp, x_stage.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   memcpy(q_host, pp, (size_t)N * sizeof(double));
   kernel_launches++;
 }
@@ -782,7 +782,7 @@ void System::read_step_status(bool ev, int* h, int* wk) {
     RXB_CUDA(cudaMemcpyAsync(energies, en_d.p, E_NUM * sizeof(double), cudaMemcpyDeviceToHost, st_));
     RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
   }
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   if (dist_) dist_peer_check();
   h[0] = host[0]; h[1] = host[5] | (host[4] ? 2 : 0);
   wk[0] = host[1]; wk[1] = host[2]; wk[2] = host[3]; wk[3] = 0;
@@ -890,7 +890,7 @@ void System::md_make_ghosts() {
   cub::DeviceScan::ExclusiveSum(scan_temp.p, need, gcount.p, goff.p, n + 1, st_);
   long long nghost = 0;
   RXB_CUDA(cudaMemcpyAsync(&nghost, goff.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   N = n + (int)nghost;
   ensure_atom_capacity();
   ghost_owner.resize(std::max<size_t>(nghost, 1));
@@ -1059,6 +1059,7 @@ void System::md_run(int nsteps) {
     kernel_launches += 3;
   }
   RXB_CUDA(cudaEventRecord(run_ev_[1], st_));
+  ++::host_sync_counter();               // the wait at the end of the run
   RXB_CUDA(cudaEventSynchronize(run_ev_[1]));
   float ms = 0;
   RXB_CUDA(cudaEventElapsedTime(&ms, run_ev_[0], run_ev_[1]));
@@ -1071,14 +1072,14 @@ void System::md_get(double* x, double* v, double* fo, double* q) {
   if (x) {
     k_get_xyz<<<nblk(n), 256, 0, st_>>>(n, xq.p, x_stage.p);
     RXB_CUDA(cudaMemcpyAsync(x, x_stage.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaStreamSynchronize(st_));
+    RXB_SYNC(st_);
   }
   if (v) RXB_CUDA(cudaMemcpy(v, v_d.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
   if (fo) RXB_CUDA(cudaMemcpy(fo, f.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
   if (q) {
     k_get_q<<<nblk(n), 256, 0, st_>>>(n, xq.p, x_stage.p);
     RXB_CUDA(cudaMemcpyAsync(q, x_stage.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st_));
-    RXB_CUDA(cudaStreamSynchronize(st_));
+    RXB_SYNC(st_);
   }
 }
 
@@ -1089,7 +1090,7 @@ double System::md_kinetic() {
   if (dist_) dist_allreduce(virial_d.p, 1);
   double ke = 0;
   RXB_CUDA(cudaMemcpyAsync(&ke, virial_d.p, sizeof(double), cudaMemcpyDeviceToHost, st_));
-  RXB_CUDA(cudaStreamSynchronize(st_));
+  RXB_SYNC(st_);
   return 0.5 * kMvv2e * ke;
 }
 
@@ -1100,7 +1101,7 @@ std::vector<T> fetch(const T* dev, size_t count, cudaStream_t st) {
   std::vector<T> h(std::max<size_t>(count, 1));
   if (count) {
     RXB_CUDA(cudaMemcpyAsync(h.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
-    RXB_CUDA(cudaStreamSynchronize(st));
+    RXB_SYNC(st);
   }
   return h;
 }

@@ -23,6 +23,15 @@
                                std::to_string(__LINE__));                                                \
   } while (0)
 
+// every host-side wait on a stream goes through this: the count is what "no host in the loop" claims are checked against
+// (rxb_host_sync_count, reported per step by bench.py)
+inline long long& host_sync_counter() { static long long n = 0; return n; }
+#define RXB_SYNC(stream)                       \
+  do {                                         \
+    ++::host_sync_counter();                   \
+    RXB_CUDA(cudaStreamSynchronize(stream));   \
+  } while (0)
+
 namespace rxb {
 
 template <class T>
