@@ -1055,14 +1055,8 @@ void System::dist_sum_small(double* dev_ptr, int count) {
   dist_allreduce(dev_ptr, count);
 }
 
-// a wait of the peer exchange timed out (a peer process died): reported with the end-of-step status
-void System::dist_peer_check() {
-  if (!dist_ || !dist_->peer_ok) return;
-  int err = 0;
-  RXB_CUDA(cudaMemcpyAsync(&err, dist_->peer_err_d.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
-  RXB_SYNC(st_);
-  if (err) throw std::runtime_error("rxb dist: peer-memory exchange timed out (a peer rank stopped responding)");
-}
+// a wait of the peer exchange timed out (a peer process died): the flag travels with the end-of-step status (read_step_status)
+const int* System::dist_peer_err_ptr() const { return dist_ && dist_->peer_ok ? dist_->peer_err_d.p : nullptr; }
 
 void System::dist_reverse_f() {
   Dist& D = *dist_;

@@ -757,13 +757,15 @@ namespace {
 // slots: 0 bond cursor, 1..3 n_ang n_tor n_hb, 4 bond arrays too small, 5 fatal per-atom bits, 6..8 work list too small.
 // Slots 4..8 are 0/1 (or a bit mask whose any-non-zero matters), so the maximum over ranks is the OR over ranks.
 __global__ void k_gather_status(const int* __restrict__ cursor, const int* __restrict__ overflow, const int* __restrict__ counts,
-                                const int* __restrict__ need_row, int cap_ang, int cap_tor, int cap_hb, int* __restrict__ out) {
+                                const int* __restrict__ need_row, int cap_ang, int cap_tor, int cap_hb,
+                                const int* __restrict__ peer_err, int* __restrict__ out) {
   if (threadIdx.x == 0) {
     const int ov = overflow[0];
     out[0] = cursor[0]; out[1] = counts[0]; out[2] = counts[1]; out[3] = counts[2];
     out[4] = (ov & 2) ? 1 : 0; out[5] = ov & ~2;
     out[6] = counts[0] > cap_ang; out[7] = counts[1] > cap_tor; out[8] = counts[2] > cap_hb;
     out[9] = need_row[0]; out[10] = need_row[1];       // longest bond row / strong list that did not fit its staging
+    out[11] = peer_err ? peer_err[0] : 0;              // a wait of the peer exchange timed out (a peer rank is gone)
     for (int k = 0; k < 11; k++) out[16 + k] = out[k];
   }
 }
@@ -771,7 +773,8 @@ __global__ void k_gather_status(const int* __restrict__ cursor, const int* __res
 
 void System::read_step_status(bool ev, int* h, int* wk) {
   status_d_.resize(32);
-  k_gather_status<<<1, 32, 0, st_>>>(b_cursor.p, overflow.p, it_count.p, need_row_d.p, cap_ang, cap_tor, cap_hb, status_d_.p);
+  k_gather_status<<<1, 32, 0, st_>>>(b_cursor.p, overflow.p, it_count.p, need_row_d.p, cap_ang, cap_tor, cap_hb,
+                                     dist_ ? dist_peer_err_ptr() : nullptr, status_d_.p);
   kernel_launches++;
   if (dist_) dist_allreduce_max_int(status_d_.p + 16, 11);
   int host[32];
@@ -783,7 +786,7 @@ void System::read_step_status(bool ev, int* h, int* wk) {
     RXB_CUDA(cudaMemcpyAsync(virial, virial_d.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st_));
   }
   RXB_SYNC(st_);
-  if (dist_) dist_peer_check();
+  if (host[11]) throw std::runtime_error("rxb dist: peer-memory exchange timed out (a peer rank stopped responding)");
   h[0] = host[0]; h[1] = host[5] | (host[4] ? 2 : 0);
   wk[0] = host[1]; wk[1] = host[2]; wk[2] = host[3]; wk[3] = 0;
   for (int k = 0; k < 11; k++) need_[k] = host[16 + k];

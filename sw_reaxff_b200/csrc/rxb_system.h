@@ -230,7 +230,7 @@ class System {
   void dist_sum_small(double* dev_ptr, int count);   // <= 8 scalars; through the peer windows when they are active
   void dist_peer_setup();
   bool dist_peer_active() const;
-  void dist_peer_check();
+  const int* dist_peer_err_ptr() const;   // device flag set when a wait of the peer exchange timed out
   void dist_allreduce_max_int(int* dev_ptr, size_t count);
   void dist_allgather_int(const int* send, int* recv, size_t count_per_rank);
   void dist_exchange();          // exchange + borders at reneighbouring
