@@ -448,7 +448,9 @@ void System::qeq_get_history(double* s_hist, double* t_hist) {
 void System::qeq_iteration(int it) {
   QeqDev* Q = reinterpret_cast<QeqDev*>(q_scal.p);
   const bool fused = !dist_ && img_valid_;   // the sweep stores each row's value into its periodic images itself
-  launch_pdl(k_cg_sweep, kVecBlocks, kVecThreads, 0, st_, n, it, (int)(it == 1), qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p,
+  // two CTAs per SM (A/B on one box, RXB_SWEEP_BLOCKS: 148 -> 10.67, 296 -> 10.53, 444 -> 10.63, 592 -> 10.60, 1184 -> 10.72 ms/step)
+  static const int sweep_blocks = getenv("RXB_SWEEP_BLOCKS") ? atoi(getenv("RXB_SWEEP_BLOCKS")) : 148 * 2;
+  launch_pdl(k_cg_sweep, sweep_blocks, kVecThreads, 0, st_, n, it, (int)(it == 1), qeq_tol, qeq_imax, rowpos.p, q_Hdia_inv.p, q_q.p,
              q_x.p, q_r.p, q_u.p, q_w.p, q_p.p, q_ss.p, q_v.p, q_z.p, q_d.p, Q, fused ? img_off.p : nullptr,
              fused ? img_pos.p : nullptr);
   kernel_launches++;
