@@ -511,7 +511,11 @@ void System::qeq_spmv(const double2* xS, double2* y_row, bool gated, int parity,
     launch_pdl(k_spmv2_bulk, std::min(148 * bulk, grid), kWarps * 32, 0, st_, r0, r1, vl.stride, far_num.p, hpk.p, 1.0 / h_quant_,
                rowpos.p, q_eta.p, xS, y_row, gated ? Q : nullptr, parity, r0 == 0 ? spmv_active_d.p : nullptr);
   } else if (h_packed_ && deep && !rowlist) {
-    const int g = deep_grid > 0 ? deep_grid : grid;
+    // four waves of resident CTAs, each warp walking rows wg, wg + nwarps, ... (A/B on one box, TATB 8x8x8, step time: one row
+    // per warp = 24576 CTAs 10.53 ms; 1 wave 10.87; 2 waves 10.53; 4 waves 10.13; 6 waves 10.22; 8 waves 10.22; grids that are
+    // not a whole number of waves are worse: 4.67 waves 10.20, 5.33 waves 10.35) - SpMV 149 -> 136 us per launch
+    static int occ_deep = 0;
+    const int g = deep_grid > 0 ? deep_grid : (deep_grid < 0 ? grid : std::min(grid, wave_grid(k_spmv2_deep<8>, kWarps * 32, 4, occ_deep)));
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
       cudaFuncSetAttribute(k_spmv2_deep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
